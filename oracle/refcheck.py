@@ -1,0 +1,257 @@
+"""Pins the oracle against the reference's OWN model code (TEST INFRASTRUCTURE; runs only where /root/reference
+exists, i.e. in the build container - never on the GPU box).
+
+`import yomitoku` is impossible offline (timm, omegaconf, pyclipper, shapely, onnx*, pypdfium2 are not installed), so
+the reference's model files are loaded *by path*, unmodified, with stand-ins for the missing third-party imports:
+  * timm.models.vision_transformer.{VisionTransformer, PatchEmbed}, timm.models.helpers.named_apply - a minimal
+    restatement of timm 1.0.27's ViT (same parameter names) so that `Encoder(VisionTransformer)` and its
+    `forward_features_dynamic` (reference code) run;
+  * the `cfg` objects (OmegaConf in the reference) are attribute-dicts built from the reference's own config
+    dataclasses' values.
+Nothing is copied into the repo: modules are executed from /root/reference in-process.
+
+Usage:  python -m oracle.refcheck            (prints PASS/FAIL lines; exit code 0 iff all pass)
+"""
+import importlib.util
+import os
+import sys
+import types
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+REF = os.environ.get("YTK_REFERENCE", "/root/reference")
+SRC = os.path.join(REF, "src", "yomitoku")
+
+
+def available():
+    return os.path.isdir(SRC)
+
+
+class AttrDict(dict):
+    def __getattr__(self, k):
+        try:
+            return self[k]
+        except KeyError:
+            raise AttributeError(k)
+
+    def __setattr__(self, k, v):
+        self[k] = v
+
+
+# ---------------------------------------------------------------------------------- timm stand-in
+def _install_timm_standin():
+    if "timm" in sys.modules:
+        return
+
+    class PatchEmbed(nn.Module):
+        def __init__(self, img_size=224, patch_size=16, in_chans=3, embed_dim=768, **kw):
+            super().__init__()
+            img_size = tuple(img_size) if isinstance(img_size, (list, tuple)) else (img_size, img_size)
+            patch_size = tuple(patch_size) if isinstance(patch_size, (list, tuple)) else (patch_size, patch_size)
+            self.img_size, self.patch_size = img_size, patch_size
+            self.grid_size = (img_size[0] // patch_size[0], img_size[1] // patch_size[1])
+            self.num_patches = self.grid_size[0] * self.grid_size[1]
+            self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=patch_size)
+            self.norm = nn.Identity()
+
+        def forward(self, x):
+            return self.norm(self.proj(x).flatten(2).transpose(1, 2))
+
+    class Attention(nn.Module):
+        def __init__(self, dim, num_heads, qkv_bias):
+            super().__init__()
+            self.num_heads, self.head_dim = num_heads, dim // num_heads
+            self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+            self.proj = nn.Linear(dim, dim)
+
+        def forward(self, x):
+            B, N, C = x.shape
+            qkv = self.qkv(x).reshape(B, N, 3, self.num_heads, self.head_dim).permute(2, 0, 3, 1, 4)
+            x = F.scaled_dot_product_attention(qkv[0], qkv[1], qkv[2])
+            return self.proj(x.transpose(1, 2).reshape(B, N, C))
+
+    class Mlp(nn.Module):
+        def __init__(self, dim, hidden):
+            super().__init__()
+            self.fc1, self.act, self.fc2 = nn.Linear(dim, hidden), nn.GELU(), nn.Linear(hidden, dim)
+
+        def forward(self, x):
+            return self.fc2(self.act(self.fc1(x)))
+
+    class Block(nn.Module):
+        def __init__(self, dim, num_heads, mlp_ratio, qkv_bias):
+            super().__init__()
+            self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+            self.attn = Attention(dim, num_heads, qkv_bias)
+            self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+            self.mlp = Mlp(dim, int(dim * mlp_ratio))
+
+        def forward(self, x):
+            x = x + self.attn(self.norm1(x))
+            return x + self.mlp(self.norm2(x))
+
+    class VisionTransformer(nn.Module):
+        def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, global_pool="token",
+                     embed_dim=768, depth=12, num_heads=12, mlp_ratio=4.0, qkv_bias=True, class_token=True,
+                     drop_rate=0.0, attn_drop_rate=0.0, drop_path_rate=0.0, embed_layer=PatchEmbed, **kw):
+            super().__init__()
+            assert not class_token and num_classes == 0 and global_pool == ""
+            self.patch_embed = embed_layer(img_size=img_size, patch_size=patch_size, in_chans=in_chans,
+                                           embed_dim=embed_dim)
+            self.pos_embed = nn.Parameter(torch.randn(1, self.patch_embed.num_patches, embed_dim) * 0.02)
+            self.pos_drop = nn.Identity()
+            self.patch_drop = nn.Identity()
+            self.norm_pre = nn.Identity()
+            self.blocks = nn.Sequential(*[Block(embed_dim, num_heads, mlp_ratio, qkv_bias) for _ in range(depth)])
+            self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+
+        def no_weight_decay(self):
+            return {"pos_embed"}
+
+        def forward_features(self, x):
+            x = self.patch_embed(x) + self.pos_embed
+            return self.norm(self.blocks(self.norm_pre(x)))
+
+    def named_apply(fn, module, name="", depth_first=True, include_root=False):
+        if not depth_first and include_root:
+            fn(module=module, name=name)
+        for child_name, child in module.named_children():
+            child_name = ".".join((name, child_name)) if name else child_name
+            named_apply(fn=fn, module=child, name=child_name, depth_first=depth_first, include_root=True)
+        if depth_first and include_root:
+            fn(module=module, name=name)
+        return module
+
+    timm = types.ModuleType("timm")
+    models = types.ModuleType("timm.models")
+    vit = types.ModuleType("timm.models.vision_transformer")
+    helpers = types.ModuleType("timm.models.helpers")
+    vit.VisionTransformer, vit.PatchEmbed = VisionTransformer, PatchEmbed
+    helpers.named_apply = named_apply
+    timm.models, models.vision_transformer, models.helpers = models, vit, helpers
+    sys.modules.update({"timm": timm, "timm.models": models, "timm.models.vision_transformer": vit,
+                        "timm.models.helpers": helpers})
+
+
+def _load(modname, relpath, package=None):
+    path = os.path.join(SRC, relpath)
+    spec = importlib.util.spec_from_file_location(modname, path, submodule_search_locations=None)
+    mod = importlib.util.module_from_spec(spec)
+    if package:
+        mod.__package__ = package
+    sys.modules[modname] = mod
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _pkg(name):
+    if name not in sys.modules:
+        m = types.ModuleType(name)
+        m.__path__ = []
+        sys.modules[name] = m
+    return sys.modules[name]
+
+
+def load_reference_models():
+    """Returns (DBNet class, PARSeq class, ParseqTokenizer class) executed from /root/reference."""
+    _install_timm_standin()
+    _pkg("ytk_ref")
+    _pkg("ytk_ref.models")
+    _pkg("ytk_ref.models.layers")
+    _pkg("ytk_ref.postprocessor")
+    _load("ytk_ref.models.layers.dbnet_feature_attention", "models/layers/dbnet_feature_attention.py",
+          "ytk_ref.models.layers")
+    _load("ytk_ref.models.layers.parseq_transformer", "models/layers/parseq_transformer.py", "ytk_ref.models.layers")
+    db = _load("ytk_ref.models.dbnet_plus", "models/dbnet_plus.py", "ytk_ref.models")
+    ps = _load("ytk_ref.models.parseq", "models/parseq.py", "ytk_ref.models")
+    tk = _load("ytk_ref.postprocessor.parseq_tokenizer", "postprocessor/parseq_tokenizer.py", "ytk_ref.postprocessor")
+    return db.DBNet, ps.PARSeq, tk.ParseqTokenizer
+
+
+def reference_dbnet_cfg():
+    # values of reference configs/cfg_text_detector_dbnet_v2_1.py:5-21
+    return AttrDict(backbone=AttrDict(name="resnet50", dilation=True),
+                    decoder=AttrDict(in_channels=[256, 512, 1024, 2048], hidden_dim=256, adaptive=True, serial=True,
+                                     smooth=False, k=50))
+
+
+def reference_parseq_cfg(spec):
+    return AttrDict(
+        max_label_length=spec.max_label_length, decode_ar=spec.decode_ar, refine_iters=spec.refine_iters,
+        num_tokens=spec.num_tokens,
+        data=AttrDict(img_size=list(spec.img_size)),
+        encoder=AttrDict(patch_size=list(spec.patch), num_heads=spec.enc_heads, embed_dim=spec.embed_dim,
+                         mlp_ratio=spec.mlp_ratio, depth=spec.enc_depth),
+        decoder=AttrDict(embed_dim=spec.embed_dim, num_heads=spec.dec_heads, mlp_ratio=spec.dec_mlp_ratio, depth=1))
+
+
+def build_reference_dbnet(sd):
+    DBNet, _, _ = load_reference_models()
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = DBNet(reference_dbnet_cfg())
+    m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
+def build_reference_parseq(spec, sd, charset):
+    _, PARSeq, Tok = load_reference_models()
+    m = PARSeq(reference_parseq_cfg(spec))
+    m.load_state_dict(sd, strict=True)
+    m.tokenizer = Tok(charset)
+    return m.eval()
+
+
+def main():
+    from oracle import dbnet as odb
+    from oracle import parseq as ops
+    from oracle import weights
+    ok = True
+
+    def report(name, cond, detail=""):
+        nonlocal ok
+        ok = ok and bool(cond)
+        print("%s  %s  %s" % ("PASS" if cond else "FAIL", name, detail), flush=True)
+
+    torch.manual_seed(0)
+    # ---- DBNet
+    sd = weights.make_dbnet_state_dict(seed=1)
+    ref = build_reference_dbnet(sd)
+    x = torch.randn(1, 3, 96, 160)
+    with torch.inference_mode():
+        r = ref(x)["binary"]
+    o = odb.dbnet_forward(sd, x)
+    report("dbnet prob map vs reference DBNet.forward", torch.equal(r, o) or (r - o).abs().max() < 1e-6,
+           "max|d|=%.3g" % (r - o).abs().max().item())
+    # ---- PARSeq
+    charset = open(os.path.join(SRC, "resource", "charsetv2.txt"), encoding="utf-8").read()
+    for name, W, peaked in (("parseq-tiny-dynw-v4", 320, False), ("parseq-tiny-dynw-v4", 200, True),
+                            ("parseq-large-v4_1", 160, True)):
+        spec = ops.SPECS[name]
+        sd = weights.make_parseq_state_dict(spec, seed=3, peaked=peaked)
+        ref = build_reference_parseq(spec, sd, charset)
+        img = torch.rand(4, 3, 32, W, generator=torch.Generator().manual_seed(5)) * 2 - 1
+        with torch.inference_mode():
+            r = ref(img)
+        o, aux = ops.parseq_forward(sd, spec, img, return_aux=True)
+        same_shape = r.shape == o.shape
+        d = (r - o).abs().max().item() if same_shape else float("nan")
+        ids_same = same_shape and torch.equal(r.argmax(-1), o.argmax(-1))
+        report("parseq %s W=%d peaked=%d logits vs reference PARSeq.forward" % (name, W, peaked),
+               same_shape and d < 2e-4 and ids_same, "shape=%s max|d|=%.3g ar_steps=%d" % (tuple(o.shape), d,
+                                                                                           aux["ar_steps"]))
+        tok_r = ref.tokenizer.decode(r.softmax(-1))
+        tok_o = ops.Tokenizer(charset).decode(o.softmax(-1))
+        report("tokenizer decode strings+scores", tok_r[0] == tok_o[0] and
+               all(abs(a - b) <= 2e-3 * max(abs(a), 1e-30) for a, b in zip(tok_r[1], tok_o[1])))
+    return 0 if ok else 1
+
+
+if __name__ == "__main__":
+    if not available():
+        print("reference not present at %s; nothing to check" % REF)
+        sys.exit(0)
+    sys.exit(main())

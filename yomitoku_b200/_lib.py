@@ -1,0 +1,58 @@
+"""ctypes loader for libytk_b200.so (the C-ABI drop-in boundary, include/yomitoku_b200.h).
+
+There is no CPU fallback: if the CUDA library is missing the import of any device path raises loudly.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libytk_b200.so")
+_lib = None
+
+c_void_p = ctypes.c_void_p
+c_int = ctypes.c_int
+c_ll = ctypes.c_longlong
+c_float_p = ctypes.c_void_p
+
+
+class YtkError(RuntimeError):
+    pass
+
+
+def _declare(lib):
+    lib.ytk_last_error.restype = ctypes.c_char_p
+    lib.ytk_last_error.argtypes = []
+    lib.ytk_version.restype = c_int
+    lib.ytk_launch_count.restype = c_ll
+    lib.ytk_op_conv2d_bf16.restype = c_int
+    lib.ytk_op_conv2d_bf16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p,
+                                       c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_ll,
+                                       c_void_p, c_int, c_ll, c_int, c_int, c_void_p]
+    lib.ytk_op_linear_bf16.restype = c_int
+    lib.ytk_op_linear_bf16.argtypes = [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+                                       c_ll, c_void_p, c_int, c_ll, c_int, c_void_p]
+
+
+def lib():
+    """Return the loaded library; build it first if the sources are present and it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise YtkError(
+            "libytk_b200.so is not built (%s). Run `python -m yomitoku_b200.build` (needs nvcc). "
+            "There is no CPU fallback for the device path." % LIB_PATH)
+    l = ctypes.CDLL(LIB_PATH)
+    _declare(l)
+    _lib = l
+    return l
+
+
+def check(status):
+    if status != 0:
+        raise YtkError(lib().ytk_last_error().decode("utf-8", "replace"))
+
+
+def ptr(t):
+    """Device (or host) pointer of a torch tensor / None."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())

@@ -1,0 +1,600 @@
+// tcgen05 implicit-GEMM convolution / linear kernel for sm_100a.  See gemm_tc.h for the contract.
+//
+// Warp roles (192 threads, 1 CTA per SM, persistent over output tiles):
+//   warp 0      : TMA producer  (one elected lane) - A patch box + W box per 64-wide K block, STAGES-deep ring
+//   warp 1      : MMA issuer    (one lane)         - 4 x tcgen05.mma (K=16) per K block into a TMEM accumulator
+//   warps 2..5  : epilogue      (128 threads)      - tcgen05.ld -> bias/residual/activation -> global stores
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers (MMA <-> epilogue, 2 buffers).
+#include "gemm_tc.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <atomic>
+#include <mutex>
+
+#include "ptx.cuh"
+
+namespace ytk {
+
+// ------------------------------------------------------------------------------------------------ errors
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+const char* last_error() { return g_err; }
+
+static std::atomic<long long> g_launches{0};
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+int num_sms() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------ kernel
+constexpr int kBlockM = 128;
+constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
+constexpr int kABytes = kBlockM * kBlockK * 2;
+constexpr int kThreads = 192;
+
+template <int BLOCK_N>
+struct TileCfg {
+    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; 128/256/512 are powers of two
+    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+    if (act == ACT_RELU) return fmaxf(x, 0.f);
+    if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
+    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
+    return x;
+}
+
+struct TileCoord {
+    int img, h0, w0, n0;
+};
+__device__ __forceinline__ TileCoord decode_tile(const GemmArgs& a, int tile, int block_n) {
+    TileCoord t;
+    int m_tile = tile / a.tiles_n;
+    int n_tile = tile - m_tile * a.tiles_n;
+    int tw = m_tile % a.tiles_w;
+    int t2 = m_tile / a.tiles_w;
+    int th = t2 % a.tiles_h;
+    t.img = t2 / a.tiles_h;
+    t.h0 = th * (kBlockM >> a.bw_log2);
+    t.w0 = tw << a.bw_log2;
+    t.n0 = n_tile * block_n;
+    return t;
+}
+
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmMaps maps,
+                                                              const __grid_constant__ GemmArgs args) {
+    using Cfg = TileCfg<BLOCK_N>;
+    constexpr int STAGES = Cfg::kStages;
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw_addr = smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // 1024 B alignment for SWIZZLE_128B
+
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < STAGES; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tfull_bar[i], 1);
+            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+        }
+        fence_mbar_init();
+        tma_prefetch_desc(&maps.a[0]);
+        tma_prefetch_desc(&maps.b);
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int tiles_m = args.n_img * args.tiles_h * args.tiles_w;
+    const int total_tiles = tiles_m * args.tiles_n;
+    const int num_kb = args.ntaps * args.kpt;
+
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                const TileCoord tc = decode_tile(args, tile, BLOCK_N);
+                int tap = 0, cb = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1u);
+                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    uint8_t* sb = sa + kABytes;
+                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    const ConvTap tp = args.taps[tap];
+                    tma_load_4d(sa, &maps.a[tp.map], &full_bar[stage], cb * kBlockK, tc.w0 + tp.dw, tc.h0 + tp.dh,
+                                tc.img);
+                    tma_load_4d(sb, &maps.b, &full_bar[stage], kb * kBlockK, tc.n0, 0, 0);
+                    if (++cb == args.kpt) {
+                        cb = 0;
+                        ++tap;
+                    }
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ------------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint64_t da = umma_desc_sw128(a_addr);
+                    const uint64_t db = umma_desc_sw128(a_addr + kABytes);
+#pragma unroll
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
+                                  (kb | k) != 0 ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    if (++stage == STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(&tfull_bar[acc]);  // accumulator complete
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+        }
+    } else {
+        // ------------------------------------------------------------------ epilogue (warps 2..5)
+        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        const int row = q * 32 + lane;
+        const int bw_mask = (1 << args.bw_log2) - 1;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            const TileCoord tc = decode_tile(args, tile, BLOCK_N);
+            const int hh = tc.h0 + (row >> args.bw_log2);
+            const int ww = tc.w0 + (row & bw_mask);
+            const bool row_ok = (hh < args.Ho) && (ww < args.Wo);
+            const long long pix = (static_cast<long long>(tc.img) * args.Ho + hh) * args.Wo + ww;
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_addr =
+                tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+            for (int c = 0; c < BLOCK_N / 32; ++c) {
+                const int col0 = tc.n0 + c * 32;
+                if (col0 >= args.Cout) break;  // warp-uniform
+                uint32_t v[32];
+                tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), v);
+                tmem_ld_wait();
+                float f[32];
+#pragma unroll
+                for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                const bool full_chunk = (col0 + 32 <= args.Cout);
+
+                // output location
+                long long opix = pix;
+                int ocol = col0;
+                if (args.mode == EPI_SHUFFLE2X) {
+                    const int cq = args.Cout >> 2;
+                    const int sub = col0 / cq;
+                    ocol = col0 - sub * cq;
+                    opix = (static_cast<long long>(tc.img) * (2 * args.Ho) + (2 * hh + (sub >> 1))) * (2 * args.Wo) +
+                           (2 * ww + (sub & 1));
+                }
+                if (args.bias != nullptr) {
+                    if (full_chunk) {
+                        const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 b = __ldg(b4 + j);
+                            f[4 * j + 0] += b.x;
+                            f[4 * j + 1] += b.y;
+                            f[4 * j + 2] += b.z;
+                            f[4 * j + 3] += b.w;
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j)
+                            if (col0 + j < args.Cout) f[j] += __ldg(args.bias + col0 + j);
+                    }
+                }
+                if (row_ok) {
+                    if (args.resid != nullptr) {
+                        if (args.resid_f32) {
+                            const float* rp = reinterpret_cast<const float*>(args.resid) + opix * args.ldr + ocol;
+                            if (full_chunk) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    const float4 r = *reinterpret_cast<const float4*>(rp + 4 * j);
+                                    f[4 * j + 0] += r.x;
+                                    f[4 * j + 1] += r.y;
+                                    f[4 * j + 2] += r.z;
+                                    f[4 * j + 3] += r.w;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < args.Cout) f[j] += rp[j];
+                            }
+                        } else {
+                            const __nv_bfloat16* rp =
+                                reinterpret_cast<const __nv_bfloat16*>(args.resid) + opix * args.ldr + ocol;
+                            if (full_chunk) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 r = *reinterpret_cast<const uint4*>(rp + 8 * j);
+                                    f[8 * j + 0] += bf16_lo(r.x);
+                                    f[8 * j + 1] += bf16_hi(r.x);
+                                    f[8 * j + 2] += bf16_lo(r.y);
+                                    f[8 * j + 3] += bf16_hi(r.y);
+                                    f[8 * j + 4] += bf16_lo(r.z);
+                                    f[8 * j + 5] += bf16_hi(r.z);
+                                    f[8 * j + 6] += bf16_lo(r.w);
+                                    f[8 * j + 7] += bf16_hi(r.w);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < args.Cout) f[j] += __bfloat162float(rp[j]);
+                            }
+                        }
+                    }
+                    if (args.act != ACT_NONE) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], args.act);
+                    }
+                    if (args.out_f32) {
+                        float* op = reinterpret_cast<float*>(args.out) + opix * args.ldc + ocol;
+                        if (full_chunk) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                *reinterpret_cast<float4*>(op + 4 * j) =
+                                    make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < args.Cout) op[j] = f[j];
+                        }
+                    } else {
+                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + opix * args.ldc + ocol;
+                        if (full_chunk) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 o;
+                                o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+                                o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+                                o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+                                o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+                                *reinterpret_cast<uint4*>(op + 8 * j) = o;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < args.Cout) op[j] = __float2bfloat16(f[j]);
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            acc ^= 1;
+            if (acc == 0) acc_phase ^= 1u;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, []() {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+        if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = reinterpret_cast<EncodeTiledFn>(p);
+    });
+    return fn;
+}
+
+int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
+                      const uint32_t box[4]) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return 1;
+    }
+    cuuint64_t gd[4] = {dims[0], dims[1], dims[2], dims[3]};
+    cuuint64_t gs[3] = {strides_b[0], strides_b[1], strides_b[2]};
+    cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
+    cuuint32_t es[4] = {1, 1, 1, 1};
+    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed (%d): dims=%llu,%llu,%llu,%llu strides=%llu,%llu,%llu box=%u,%u,%u,%u "
+                  "base=%p",
+                  (int)r, (unsigned long long)dims[0], (unsigned long long)dims[1], (unsigned long long)dims[2],
+                  (unsigned long long)dims[3], (unsigned long long)strides_b[0], (unsigned long long)strides_b[1],
+                  (unsigned long long)strides_b[2], box[0], box[1], box[2], box[3], base);
+        return 1;
+    }
+    return 0;
+}
+
+static int pick_block_n(int Cout) {
+    if (Cout <= 64) return 64;
+    if (Cout <= 128) return 128;
+    if (Cout % 256 == 0 || Cout > 512) return 256;
+    if (Cout % 128 == 0) return 128;
+    return 256;
+}
+
+// Choose the BH x BW patch (BH*BW = 128) that wastes the fewest pixels.
+static int pick_bw_log2(int Ho, int Wo) {
+    int best = 7;
+    long long best_cost = -1;
+    for (int l = 3; l <= 7; ++l) {
+        int bw = 1 << l, bh = 128 >> l;
+        long long cost = (long long)((Wo + bw - 1) / bw) * ((Ho + bh - 1) / bh);
+        if (best_cost < 0 || cost < best_cost || (cost == best_cost && l > best)) {
+            best_cost = cost;
+            best = l;
+        }
+    }
+    return best;
+}
+
+static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout, const Epilogue& e) {
+    GemmArgs& a = plan->args;
+    plan->block_n = pick_block_n(Cout);
+    a.tiles_n = (Cout + plan->block_n - 1) / plan->block_n;
+    a.Cout = Cout;
+    a.bias = e.bias;
+    a.resid = e.resid;
+    a.resid_f32 = e.resid_f32;
+    a.ldr = e.ldr;
+    a.out = e.out;
+    a.out_f32 = e.out_f32;
+    a.ldc = e.ldc;
+    a.act = e.act;
+    a.mode = e.mode;
+    if (e.out == nullptr) {
+        set_error("gemm plan: null output");
+        return 1;
+    }
+    if ((e.out_f32 ? (e.ldc % 4) : (e.ldc % 8)) != 0) {
+        set_error("gemm plan: ldc=%lld must keep rows 16-byte aligned", e.ldc);
+        return 1;
+    }
+    if (e.resid && ((e.resid_f32 ? (e.ldr % 4) : (e.ldr % 8)) != 0)) {
+        set_error("gemm plan: ldr=%lld must keep rows 16-byte aligned", e.ldr);
+        return 1;
+    }
+    if (e.mode == EPI_SHUFFLE2X && ((Cout % 4) != 0 || ((Cout / 4) % 32) != 0)) {
+        set_error("gemm plan: SHUFFLE2X needs Cout/4 to be a multiple of 32 (Cout=%d)", Cout);
+        return 1;
+    }
+    // weights: [Cout][Ktot] bf16, K-major
+    uint64_t dims[4] = {(uint64_t)Ktot, (uint64_t)Cout, 1, 1};
+    uint64_t strides[3] = {(uint64_t)Ktot * 2, (uint64_t)Ktot * 2 * Cout, (uint64_t)Ktot * 2 * Cout};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)plan->block_n, 1, 1};
+    if (make_tmap_bf16_4d(&plan->maps.b, w_packed, dims, strides, box)) return 1;
+    const int tiles = a.n_img * a.tiles_h * a.tiles_w * a.tiles_n;
+    plan->grid = tiles < num_sms() ? tiles : num_sms();
+    if (plan->grid < 1) plan->grid = 1;
+    return 0;
+}
+
+int conv_plan_create(GemmPlan* plan, const void* in, const ConvGeom& g, const void* w_packed, const Epilogue& e) {
+    memset(plan, 0, sizeof(*plan));
+    GemmArgs& a = plan->args;
+    if (g.Cin % kBlockK != 0) {
+        set_error("conv plan: Cin=%d must be a multiple of %d", g.Cin, kBlockK);
+        return 1;
+    }
+    if (g.stride != 1 && g.stride != 2) {
+        set_error("conv plan: stride %d unsupported", g.stride);
+        return 1;
+    }
+    if (g.kh * g.kw > kMaxTaps) {
+        set_error("conv plan: %dx%d filter exceeds %d taps", g.kh, g.kw, kMaxTaps);
+        return 1;
+    }
+    const int Ho = (g.H + 2 * g.pad - g.dil * (g.kh - 1) - 1) / g.stride + 1;
+    const int Wo = (g.W + 2 * g.pad - g.dil * (g.kw - 1) - 1) / g.stride + 1;
+    a.Ho = Ho;
+    a.Wo = Wo;
+    a.n_img = g.N;
+    a.bw_log2 = pick_bw_log2(Ho, Wo);
+    const int bw = 1 << a.bw_log2, bh = 128 >> a.bw_log2;
+    a.tiles_w = (Wo + bw - 1) / bw;
+    a.tiles_h = (Ho + bh - 1) / bh;
+    a.kpt = g.Cin / kBlockK;
+    a.ntaps = g.kh * g.kw;
+    const uint64_t es = 2;
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)bw, (uint32_t)bh, 1};
+    const char* base = reinterpret_cast<const char*>(in);
+    if (g.stride == 1) {
+        uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
+        uint64_t strides[3] = {(uint64_t)g.in_ld * es, (uint64_t)g.in_ld * es * g.W, (uint64_t)g.in_ld * es * g.W * g.H};
+        if (make_tmap_bf16_4d(&plan->maps.a[0], base, dims, strides, box)) return 1;
+        for (int i = 1; i < 4; ++i) plan->maps.a[i] = plan->maps.a[0];
+        int t = 0;
+        for (int r = 0; r < g.kh; ++r)
+            for (int s = 0; s < g.kw; ++s, ++t) {
+                a.taps[t].map = 0;
+                a.taps[t].dh = r * g.dil - g.pad;
+                a.taps[t].dw = s * g.dil - g.pad;
+            }
+    } else {
+        // stride 2: input row 2*ho + (r*dil - pad) = 2*(ho + floor(o/2)) + (o mod 2): phase map (o mod 2), shift floor(o/2)
+        bool used[4] = {false, false, false, false};
+        int t = 0;
+        for (int r = 0; r < g.kh; ++r)
+            for (int s = 0; s < g.kw; ++s, ++t) {
+                const int oh = r * g.dil - g.pad, ow = s * g.dil - g.pad;
+                const int ph = ((oh % 2) + 2) % 2, pw = ((ow % 2) + 2) % 2;
+                a.taps[t].map = ph * 2 + pw;
+                a.taps[t].dh = (oh - ph) / 2;
+                a.taps[t].dw = (ow - pw) / 2;
+                used[ph * 2 + pw] = true;
+            }
+        int first = -1;
+        for (int p = 0; p < 4; ++p) {
+            if (!used[p]) continue;
+            const int ph = p >> 1, pw = p & 1;
+            const int hp = (g.H - ph + 1) / 2, wp = (g.W - pw + 1) / 2;
+            if (hp <= 0 || wp <= 0) {
+                set_error("conv plan: degenerate stride-2 phase");
+                return 1;
+            }
+            uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)wp, (uint64_t)hp, (uint64_t)g.N};
+            uint64_t strides[3] = {(uint64_t)g.in_ld * es * 2, (uint64_t)g.in_ld * es * g.W * 2,
+                                   (uint64_t)g.in_ld * es * g.W * g.H};
+            const char* pbase = base + ((size_t)ph * g.W + pw) * g.in_ld * es;
+            if (make_tmap_bf16_4d(&plan->maps.a[p], pbase, dims, strides, box)) return 1;
+            if (first < 0) first = p;
+        }
+        for (int p = 0; p < 4; ++p)
+            if (!used[p]) plan->maps.a[p] = plan->maps.a[first];
+    }
+    plan->flops = 2.0 * g.N * Ho * Wo * (double)g.Cout * g.Cin * g.kh * g.kw;
+    return finish_plan(plan, w_packed, g.kh * g.kw * g.Cin, g.Cout, e);
+}
+
+int gemm_plan_create(GemmPlan* plan, const void* A, long long lda, int M, int K, const void* Wt, int N,
+                     const Epilogue& e) {
+    memset(plan, 0, sizeof(*plan));
+    GemmArgs& a = plan->args;
+    if (K % kBlockK != 0) {
+        set_error("gemm plan: K=%d must be a multiple of %d", K, kBlockK);
+        return 1;
+    }
+    if (M < 1) {
+        set_error("gemm plan: M=%d", M);
+        return 1;
+    }
+    a.Ho = 1;
+    a.Wo = M;
+    a.n_img = 1;
+    a.bw_log2 = 7;
+    a.tiles_w = (M + 127) / 128;
+    a.tiles_h = 1;
+    a.kpt = K / kBlockK;
+    a.ntaps = 1;
+    a.taps[0].map = 0;
+    a.taps[0].dh = 0;
+    a.taps[0].dw = 0;
+    uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
+    uint64_t strides[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * M, (uint64_t)lda * 2 * M};
+    uint32_t box[4] = {(uint32_t)kBlockK, 128, 1, 1};
+    if (make_tmap_bf16_4d(&plan->maps.a[0], A, dims, strides, box)) return 1;
+    for (int i = 1; i < 4; ++i) plan->maps.a[i] = plan->maps.a[0];
+    plan->flops = 2.0 * M * (double)N * K;
+    return finish_plan(plan, Wt, K, N, e);
+}
+
+void gemm_plan_set_m(GemmPlan* plan, int M) {
+    GemmArgs& a = plan->args;
+    const double per_row = a.Wo > 0 ? plan->flops / a.Wo : 0.0;
+    a.Wo = M;
+    a.tiles_w = (M + 127) / 128;
+    plan->flops = per_row * M;
+    const int tiles = a.tiles_w * a.tiles_n;
+    plan->grid = tiles < num_sms() ? tiles : num_sms();
+    if (plan->grid < 1) plan->grid = 1;
+}
+
+template <int BLOCK_N>
+static int launch_bn(const GemmPlan* plan, cudaStream_t stream) {
+    using Cfg = TileCfg<BLOCK_N>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytes);
+        if (e != cudaSuccess) {
+            set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
+            return 1;
+        }
+        attr_set = true;
+    }
+    gemm_tc_kernel<BLOCK_N><<<plan->grid, kThreads, Cfg::kSmemBytes, stream>>>(plan->maps, plan->args);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("gemm_tc_kernel<%d> launch: %s", BLOCK_N, cudaGetErrorString(e));
+        return 1;
+    }
+    return 0;
+}
+
+int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream) {
+    switch (plan->block_n) {
+        case 64: return launch_bn<64>(plan, stream);
+        case 128: return launch_bn<128>(plan, stream);
+        case 256: return launch_bn<256>(plan, stream);
+        default: set_error("bad block_n %d", plan->block_n); return 1;
+    }
+}
+
+}  // namespace ytk

@@ -1,0 +1,103 @@
+// Implicit-GEMM convolution / linear layer on tcgen05 tensor cores (sm_100a).
+//
+//   D[pixel, co] = act( sum_{tap, ci} A[pixel + tap, ci] * W[co, tap, ci] + bias[co] (+ resid[pixel, co]) )
+//
+// A is an NHWC bf16 activation tensor read through 4-D TMA tensor maps: one 128-pixel M tile is a BH x BW spatial
+// patch (BH*BW = 128), and a filter tap is just a shifted TMA box whose out-of-bounds part is zero-filled by the
+// hardware (= convolution padding).  Stride-2 convolutions read through up to four "phase" tensor maps (even/odd
+// rows x even/odd columns).  A plain linear layer is the degenerate case H = 1, W = M, one tap.
+// W is a K-major bf16 matrix [Cout][taps*Cin] read through a 2-D TMA map.  Accumulators live in TMEM (fp32),
+// double-buffered so the epilogue of tile i overlaps the MMAs of tile i+1 (persistent CTAs, one per SM).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ytk {
+
+constexpr int kMaxTaps = 9;
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
+enum EpiMode : int {
+    EPI_NORMAL = 0,
+    EPI_SHUFFLE2X = 1,  // ConvTranspose2d(k=2,s=2): column block (i,j) of width Cout/4 goes to pixel (2h+i, 2w+j)
+};
+
+struct ConvTap {
+    int32_t map;  // which A tensor map (stride-2 phase)
+    int32_t dh;   // row offset added to the tile origin (in the phase map's coordinates)
+    int32_t dw;   // column offset
+};
+
+struct alignas(64) GemmMaps {
+    CUtensorMap a[4];
+    CUtensorMap b;
+};
+
+struct GemmArgs {
+    int Ho, Wo, n_img;             // output spatial extent (per image) and image count
+    int bw_log2;                   // tile patch: BW = 1 << bw_log2 columns, BH = 128 >> bw_log2 rows
+    int tiles_w, tiles_h, tiles_n; // tile grid
+    int Cout;                      // true number of output columns (<= tiles_n * BLOCK_N)
+    int kpt;                       // 64-channel K blocks per tap
+    int ntaps;
+    ConvTap taps[kMaxTaps];
+    const float* bias;             // [Cout] fp32 or null
+    const void* resid;             // [pixels, ldr] bf16 or fp32, or null; same pixel indexing as out
+    int resid_f32;
+    long long ldr;
+    void* out;                     // [pixels, ldc] bf16 or fp32
+    int out_f32;
+    long long ldc;
+    int act;
+    int mode;
+};
+
+struct Epilogue {
+    const float* bias = nullptr;
+    const void* resid = nullptr;
+    int resid_f32 = 0;
+    long long ldr = 0;
+    void* out = nullptr;
+    int out_f32 = 0;
+    long long ldc = 0;
+    int act = ACT_NONE;
+    int mode = EPI_NORMAL;
+};
+
+struct ConvGeom {
+    int N, H, W, Cin;      // input NHWC (Cin multiple of 64)
+    long long in_ld;       // channel stride of the input buffer in elements (>= Cin)
+    int kh, kw, stride, pad, dil;
+    int Cout;
+};
+
+// A prepared launch: tensor maps + arguments.  Built once per (layer, buffer set), launched many times.
+struct GemmPlan {
+    GemmMaps maps;
+    GemmArgs args;
+    int block_n;
+    int grid;
+    double flops;  // 2*M*N*K of the true problem (for roofline accounting)
+};
+
+// All return 0 on success, nonzero on failure (message via ytk::last_error()).
+int conv_plan_create(GemmPlan* plan, const void* in, const ConvGeom& g, const void* w_packed, const Epilogue& e);
+// A: [M, lda] bf16 row-major (K multiple of 64, first K columns used); Wt: [N, K] bf16 row-major.
+int gemm_plan_create(GemmPlan* plan, const void* A, long long lda, int M, int K, const void* Wt, int N,
+                     const Epilogue& e);
+// Same but the M extent can be changed per launch (rows beyond M are never stored).
+void gemm_plan_set_m(GemmPlan* plan, int M);
+int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream);
+
+// Generic 4-D tiled bf16 tensor map with 128B swizzle (dims/strides innermost first; strides in bytes for dims 1..3).
+int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
+                      const uint32_t box[4]);
+
+void set_error(const char* fmt, ...);
+const char* last_error();
+int num_sms();
+void count_launch(int n = 1);
+long long launch_count();
+
+}  // namespace ytk
