@@ -48,6 +48,40 @@ int ytk_op_linear_bf16(const void* A, long long lda, int M, int K, const void* W
                        const void* resid, int resid_f32, long long ldr, void* out, int out_f32, long long ldc, int act,
                        void* cuda_stream);
 
+/* ---- DBNet text detector: replaces `self.model(tensor)` in reference TextDetector.__call__
+ * (src/yomitoku/text_detector.py:127-129 -> models/dbnet_plus.py:243-246) and, in the fused u8 entry, also
+ * TextDetector.preprocess (text_detector.py:99-107, data/functions.py:196-264). ---- */
+typedef struct ytk_dbnet ytk_dbnet;
+
+/* One entry of the reference-keyed state_dict (host fp32; the strict key set of
+ * DBNet.state_dict() / PARSeq.state_dict() as stored in the HF model.safetensors). */
+typedef struct {
+    const char* name;
+    const float* data;
+    int ndim;
+    long long shape[4];
+} ytk_tensor;
+
+/* Folds BatchNorm, repacks weights to NHWC bf16 and uploads them.  shortest_size / limit_size are cfg.data.* of the
+ * detector config (reference configs/cfg_text_detector_dbnet_v2_1.py:23-26). */
+int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size, int limit_size, ytk_dbnet** out);
+void ytk_dbnet_destroy(ytk_dbnet* h);
+/* network input size for an H0 x W0 page = reference resize_shortest_edge (data/functions.py:212-224) */
+int ytk_dbnet_input_size(const ytk_dbnet* h, int H0, int W0, int* Hn, int* Wn);
+/* pages: [n_pages, H0, W0, 3] uint8 BGR (caller-owned; device pointer iff pages_on_device, else host - pinned for
+ * async copies).  prob_out: [n_pages, Hn, Wn] fp32 sigmoid map = preds["binary"][:, 0] of the reference. */
+int ytk_dbnet_forward_u8(ytk_dbnet* h, const uint8_t* pages, int pages_on_device, int n_pages, int H0, int W0,
+                         float* prob_out, int out_on_device, void* cuda_stream);
+/* model-level seam: x = normalised (n,3,H,W) fp32 exactly as the reference feeds DBNet.forward; H, W % 32 == 0 */
+int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x_nchw, int x_on_device, int n, int H, int W, float* prob_out,
+                          int out_on_device, void* cuda_stream);
+/* algorithmic conv FLOPs (2*MAC) of one forward at this shape (roofline accounting) */
+double ytk_dbnet_flops(ytk_dbnet* h, int n_pages, int Hn, int Wn);
+/* test hook: copy a named intermediate activation (NHWC) of the last run at this shape to host fp32.
+ * shape4 receives n,h,w,c.  Names: stem, pool, layer1..layer4, layerL.B, f1..f4, fuse, asf_a, bin1, bin2, prob. */
+int ytk_dbnet_debug_tensor(ytk_dbnet* h, int n_pages, int Hn, int Wn, const char* name, float* host_out,
+                           long long capacity, int* shape4);
+
 #ifdef __cplusplus
 }
 #endif

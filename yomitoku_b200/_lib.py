@@ -33,6 +33,47 @@ def _declare(lib):
                                        c_ll, c_void_p, c_int, c_ll, c_int, c_void_p]
 
 
+class YtkTensor(ctypes.Structure):
+    _fields_ = [("name", ctypes.c_char_p), ("data", ctypes.c_void_p), ("ndim", c_int), ("shape", c_ll * 4)]
+
+
+def _declare_dbnet(lib):
+    P = ctypes.POINTER
+    lib.ytk_dbnet_create.restype = c_int
+    lib.ytk_dbnet_create.argtypes = [P(YtkTensor), c_int, c_int, c_int, P(c_void_p)]
+    lib.ytk_dbnet_destroy.restype = None
+    lib.ytk_dbnet_destroy.argtypes = [c_void_p]
+    lib.ytk_dbnet_input_size.restype = c_int
+    lib.ytk_dbnet_input_size.argtypes = [c_void_p, c_int, c_int, P(c_int), P(c_int)]
+    lib.ytk_dbnet_forward_u8.restype = c_int
+    lib.ytk_dbnet_forward_u8.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.ytk_dbnet_forward_f32.restype = c_int
+    lib.ytk_dbnet_forward_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p]
+    lib.ytk_dbnet_flops.restype = ctypes.c_double
+    lib.ytk_dbnet_flops.argtypes = [c_void_p, c_int, c_int, c_int]
+    lib.ytk_dbnet_debug_tensor.restype = c_int
+    lib.ytk_dbnet_debug_tensor.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.c_char_p, c_void_p, c_ll, P(c_int)]
+
+
+def tensor_table(state_dict):
+    """state_dict (name -> torch tensor) -> (ctypes array of YtkTensor, keep-alive list). Tensors are converted to
+    contiguous host fp32; integer buffers (num_batches_tracked) are skipped."""
+    import torch
+    keep, rows = [], []
+    for name, t in state_dict.items():
+        if not torch.is_floating_point(t):
+            continue
+        t = t.detach().to("cpu", torch.float32).contiguous()
+        if t.dim() > 4:
+            raise YtkError("tensor %s has rank %d > 4" % (name, t.dim()))
+        nb = name.encode()
+        keep.append((t, nb))
+        shape = (c_ll * 4)(*(list(t.shape) + [1] * (4 - t.dim())))
+        rows.append(YtkTensor(nb, t.data_ptr(), t.dim(), shape))
+    arr = (YtkTensor * len(rows))(*rows)
+    return arr, keep
+
+
 def lib():
     """Return the loaded library; build it first if the sources are present and it is missing."""
     global _lib
@@ -44,6 +85,7 @@ def lib():
             "There is no CPU fallback for the device path." % LIB_PATH)
     l = ctypes.CDLL(LIB_PATH)
     _declare(l)
+    _declare_dbnet(l)
     _lib = l
     return l
 

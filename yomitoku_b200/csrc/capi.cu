@@ -1,7 +1,60 @@
 // extern "C" surface of libytk_b200.so (declared in include/yomitoku_b200.h).
 #include "../../include/yomitoku_b200.h"
 
+#include <map>
+#include <memory>
+#include <mutex>
+#include <tuple>
+
+#include "dbnet_engine.h"
+#include "dbnet_ops.h"
 #include "gemm_tc.h"
+
+struct ytk_dbnet {
+    ytk::DbnetModel model;
+    std::map<std::tuple<int, int, int>, std::unique_ptr<ytk::DbnetEngine>> engines;
+    std::mutex mu;
+    int shortest = 1280, limit = 1600;
+    void* stage = nullptr;  // device staging for host inputs
+    size_t stage_bytes = 0;
+};
+
+static ytk::DbnetEngine* get_engine(ytk_dbnet* h, int n, int Hn, int Wn) {
+    auto key = std::make_tuple(n, Hn, Wn);
+    auto it = h->engines.find(key);
+    if (it != h->engines.end()) return it->second.get();
+    auto e = std::make_unique<ytk::DbnetEngine>();
+    if (e->build(h->model, n, Hn, Wn)) return nullptr;
+    ytk::DbnetEngine* p = e.get();
+    h->engines[key] = std::move(e);
+    return p;
+}
+
+static int ensure_stage(ytk_dbnet* h, size_t bytes) {
+    if (h->stage_bytes >= bytes) return 0;
+    if (h->stage) cudaFree(h->stage);
+    h->stage = nullptr;
+    h->stage_bytes = 0;
+    if (cudaMalloc(&h->stage, bytes) != cudaSuccess) {
+        ytk::set_error("cudaMalloc(%zu) for input staging failed", bytes);
+        return 1;
+    }
+    h->stage_bytes = bytes;
+    return 0;
+}
+
+static int finish_forward(ytk::DbnetEngine* e, float* prob_out, int out_on_device, cudaStream_t st) {
+    if (e->run(st)) return YTK_ERR;
+    const size_t bytes = (size_t)e->N * e->Hn * e->Wn * sizeof(float);
+    cudaError_t err = cudaMemcpyAsync(prob_out, e->prob, bytes,
+                                      out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess && !out_on_device) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) {
+        ytk::set_error("DBNet output copy failed: %s", cudaGetErrorString(err));
+        return YTK_ERR;
+    }
+    return YTK_OK;
+}
 
 extern "C" {
 
@@ -43,6 +96,129 @@ int ytk_op_linear_bf16(const void* A, long long lda, int M, int K, const void* W
     ytk::GemmPlan plan;
     if (ytk::gemm_plan_create(&plan, A, lda, M, K, W, N, e)) return YTK_ERR;
     return ytk::gemm_plan_launch(&plan, static_cast<cudaStream_t>(cuda_stream)) ? YTK_ERR : YTK_OK;
+}
+
+int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size, int limit_size, ytk_dbnet** out) {
+    if (!tensors || !out) {
+        ytk::set_error("ytk_dbnet_create: null argument");
+        return YTK_ERR;
+    }
+    ytk::WeightSet ws;
+    for (int i = 0; i < n_tensors; ++i) {
+        ytk::TensorView v;
+        v.data = tensors[i].data;
+        v.ndim = tensors[i].ndim;
+        for (int d = 0; d < 4; ++d) v.shape[d] = d < v.ndim ? tensors[i].shape[d] : 1;
+        ws.map[tensors[i].name] = v;
+    }
+    auto h = std::make_unique<ytk_dbnet>();
+    h->shortest = shortest_size;
+    h->limit = limit_size;
+    if (h->model.load(ws)) return YTK_ERR;
+    *out = h.release();
+    return YTK_OK;
+}
+
+void ytk_dbnet_destroy(ytk_dbnet* h) {
+    if (!h) return;
+    if (h->stage) cudaFree(h->stage);
+    delete h;
+}
+
+int ytk_dbnet_input_size(const ytk_dbnet* h, int H0, int W0, int* Hn, int* Wn) {
+    ytk::dbnet_input_size(H0, W0, h->shortest, h->limit, Hn, Wn);
+    return YTK_OK;
+}
+
+int ytk_dbnet_forward_u8(ytk_dbnet* h, const uint8_t* pages, int pages_on_device, int n_pages, int H0, int W0,
+                         float* prob_out, int out_on_device, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    int Hn, Wn;
+    ytk::dbnet_input_size(H0, W0, h->shortest, h->limit, &Hn, &Wn);
+    if (Hn > H0 || Wn > W0) {
+        ytk::set_error("ytk_dbnet_forward_u8: page %dx%d would be upscaled to %dx%d; the fused u8 path implements "
+                       "OpenCV's INTER_AREA decimation only - resize on the host and call ytk_dbnet_forward_f32",
+                       H0, W0, Hn, Wn);
+        return YTK_ERR;
+    }
+    ytk::DbnetEngine* e = get_engine(h, n_pages, Hn, Wn);
+    if (!e) return YTK_ERR;
+    const uint8_t* src = pages;
+    if (!pages_on_device) {
+        const size_t bytes = (size_t)n_pages * H0 * W0 * 3;
+        if (ensure_stage(h, bytes)) return YTK_ERR;
+        if (cudaMemcpyAsync(h->stage, pages, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            ytk::set_error("H2D copy of pages failed");
+            return YTK_ERR;
+        }
+        src = reinterpret_cast<const uint8_t*>(h->stage);
+    }
+    if (ytk::launch_preprocess(src, n_pages, H0, W0, Hn, Wn, e->input, st)) {
+        ytk::set_error("preprocess launch failed");
+        return YTK_ERR;
+    }
+    return finish_forward(e, prob_out, out_on_device, st);
+}
+
+int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x, int x_on_device, int n, int H, int W, float* prob_out,
+                          int out_on_device, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ytk::DbnetEngine* e = get_engine(h, n, H, W);
+    if (!e) return YTK_ERR;
+    const float* src = x;
+    if (!x_on_device) {
+        const size_t bytes = (size_t)n * 3 * H * W * 4;
+        if (ensure_stage(h, bytes)) return YTK_ERR;
+        if (cudaMemcpyAsync(h->stage, x, bytes, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            ytk::set_error("H2D copy of input tensor failed");
+            return YTK_ERR;
+        }
+        src = reinterpret_cast<const float*>(h->stage);
+    }
+    if (ytk::launch_pack_nchw_f32(src, n, H, W, e->input, st)) {
+        ytk::set_error("input pack launch failed");
+        return YTK_ERR;
+    }
+    return finish_forward(e, prob_out, out_on_device, st);
+}
+
+double ytk_dbnet_flops(ytk_dbnet* h, int n_pages, int Hn, int Wn) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    ytk::DbnetEngine* e = get_engine(h, n_pages, Hn, Wn);
+    return e ? e->flops : -1.0;
+}
+
+int ytk_dbnet_debug_tensor(ytk_dbnet* h, int n_pages, int Hn, int Wn, const char* name, float* host_out,
+                           long long capacity, int* shape4) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    ytk::DbnetEngine* e = get_engine(h, n_pages, Hn, Wn);
+    if (!e) return YTK_ERR;
+    auto it = e->dbg.find(name);
+    if (it == e->dbg.end() || !it->second.p) {
+        ytk::set_error("no debug tensor named '%s'", name);
+        return YTK_ERR;
+    }
+    const ytk::DebugTensor& t = it->second;
+    const long long n = (long long)t.n * t.h * t.w * t.c;
+    shape4[0] = t.n; shape4[1] = t.h; shape4[2] = t.w; shape4[3] = t.c;
+    if (n > capacity) {
+        ytk::set_error("debug tensor '%s' needs %lld floats, capacity %lld", name, n, capacity);
+        return YTK_ERR;
+    }
+    cudaDeviceSynchronize();
+    if (t.f32) {
+        if (cudaMemcpy(host_out, t.p, n * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return YTK_ERR;
+    } else {
+        float* tmp = nullptr;
+        if (cudaMalloc(&tmp, n * 4) != cudaSuccess) return YTK_ERR;
+        ytk::launch_bf16_to_f32(t.p, tmp, n, 0);
+        cudaError_t err = cudaMemcpy(host_out, tmp, n * 4, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        if (err != cudaSuccess) return YTK_ERR;
+    }
+    return YTK_OK;
 }
 
 }  // extern "C"

@@ -554,6 +554,40 @@ int gemm_plan_create(GemmPlan* plan, const void* A, long long lda, int M, int K,
     return finish_plan(plan, Wt, K, N, e);
 }
 
+int stem_plan_create(GemmPlan* plan, const void* in_padded, int N, int Hn, int Wn, const void* w_packed,
+                     const Epilogue& e) {
+    memset(plan, 0, sizeof(*plan));
+    GemmArgs& a = plan->args;
+    const int Ho = Hn / 2, Wo = Wn / 2, Hp = Hn + 6, Wp = Wn + 8;
+    a.Ho = Ho;
+    a.Wo = Wo;
+    a.n_img = N;
+    a.bw_log2 = pick_bw_log2(Ho, Wo);
+    const int bw = 1 << a.bw_log2, bh = 128 >> a.bw_log2;
+    a.tiles_w = (Wo + bw - 1) / bw;
+    a.tiles_h = (Ho + bh - 1) / bh;
+    a.kpt = 1;
+    a.ntaps = 7;
+    const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)bw, (uint32_t)bh, 1};
+    const char* base = reinterpret_cast<const char*>(in_padded);
+    const uint64_t row_b = (uint64_t)Wp * 8 * 2;
+    for (int p = 0; p < 2; ++p) {
+        // input row 2*ho + r = 2*(ho + r/2) + (r & 1): phase p = r & 1 starts at padded row p, steps 2 rows
+        uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)((Hp - p + 1) / 2), (uint64_t)N};
+        uint64_t strides[3] = {32, 2 * row_b, (uint64_t)Hp * row_b};
+        if (make_tmap_bf16_4d(&plan->maps.a[p], base + p * row_b, dims, strides, box)) return 1;
+    }
+    plan->maps.a[2] = plan->maps.a[0];
+    plan->maps.a[3] = plan->maps.a[1];
+    for (int r = 0; r < 7; ++r) {
+        a.taps[r].map = r & 1;
+        a.taps[r].dh = r >> 1;
+        a.taps[r].dw = 0;
+    }
+    plan->flops = 2.0 * N * Ho * Wo * 64.0 * 448.0;
+    return finish_plan(plan, w_packed, 7 * 64, 64, e);
+}
+
 void gemm_plan_set_m(GemmPlan* plan, int M) {
     GemmArgs& a = plan->args;
     const double per_row = a.Wo > 0 ? plan->flops / a.Wo : 0.0;

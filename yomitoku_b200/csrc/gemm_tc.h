@@ -86,6 +86,11 @@ int conv_plan_create(GemmPlan* plan, const void* in, const ConvGeom& g, const vo
 // A: [M, lda] bf16 row-major (K multiple of 64, first K columns used); Wt: [N, K] bf16 row-major.
 int gemm_plan_create(GemmPlan* plan, const void* A, long long lda, int M, int K, const void* Wt, int N,
                      const Epilogue& e);
+// ResNet stem: 7x7 stride-2 pad-3 conv over a zero-padded 8-channel NHWC canvas [N, Hn+6, Wn+8, 8] (pixel (h,w) at
+// (h+3, w+3)).  One K block = one filter row = 8 pixels x 8 channels = 64 contiguous bf16, fetched with TMA boxes whose
+// rows overlap in memory (W stride = 2 pixels).  w_packed: [Cout][7][64] bf16.
+int stem_plan_create(GemmPlan* plan, const void* in_padded, int N, int Hn, int Wn, const void* w_packed,
+                     const Epilogue& e);
 // Same but the M extent can be changed per launch (rows beyond M are never stored).
 void gemm_plan_set_m(GemmPlan* plan, int M);
 int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream);
