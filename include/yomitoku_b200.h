@@ -82,6 +82,52 @@ double ytk_dbnet_flops(ytk_dbnet* h, int n_pages, int Hn, int Wn);
 int ytk_dbnet_debug_tensor(ytk_dbnet* h, int n_pages, int Hn, int Wn, const char* name, float* host_out,
                            long long capacity, int* shape4);
 
+/* ---- PARSeq text recognizer: replaces `self.model(data).softmax(-1)` + tokenizer arg-max in reference
+ * TextRecognizer._run_inference / postprocess (src/yomitoku/text_recognizer.py:247-256, 232-245 ->
+ * models/parseq.py:159-311, postprocessor/parseq_tokenizer.py:64-88). ---- */
+typedef struct ytk_parseq ytk_parseq;
+
+/* values of the recognizer config (reference configs/cfg_text_recognizer_parseq*.py) + repetition-stop knobs
+ * (models/parseq.py:93-96) */
+typedef struct {
+    int embed_dim, enc_heads, enc_depth, patch_h, patch_w, img_h, img_w, num_tokens, max_label_length, dec_heads,
+        mlp_ratio, dec_mlp_ratio, refine_iters, repetition_stop, rep_period_max, rep_min_run_p1, rep_min_repeats;
+} ytk_parseq_cfg;
+
+/* One crop of a packed recognizer call.  The canvas is the reference's `dataset.data[i]` (RGB uint8, 32 rows,
+ * w columns, black padded, data/functions.py:379-439); wp is the width the reference's _collate would pad it to
+ * (max width of its mini-batch, text_recognizer.py:146-156); group = index of that mini-batch (the AR loop stops
+ * per mini-batch, models/parseq.py:245-250). */
+typedef struct {
+    long long pix_off; /* byte offset of the canvas in the packed buffer */
+    int w;             /* stored canvas width */
+    int wp;            /* padded width (multiple of patch_w, >= w) */
+    int tok_off;       /* first encoder token row of this crop (crops are packed back to back) */
+    int ntok;          /* (32 / patch_h) * (wp / patch_w) */
+    int group;
+} ytk_crop;
+
+int ytk_parseq_create(const ytk_tensor* tensors, int n_tensors, const ytk_parseq_cfg* cfg, ytk_parseq** out);
+void ytk_parseq_destroy(ytk_parseq* h);
+void ytk_parseq_set_refine_iters(ytk_parseq* h, int refine_iters);
+/* crops_host: packed canvases (pinned host memory for async copies).  Outputs (host): ids / probs
+ * [n_crops, max_label_length + 1] = per-position arg-max token and its softmax probability (what
+ * BaseTokenizer.decode computes from the full distribution), group_len [n_groups] = AR steps each mini-batch ran
+ * (= number of valid positions when refine_iters == 0). */
+int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops_host, long long crops_bytes, const ytk_crop* crops,
+                             int n_crops, int n_groups, int32_t* ids_out, float* probs_out, int32_t* group_len_out,
+                             void* cuda_stream);
+/* model-level seam: images (B,3,32,W) fp32 as fed to PARSeq.forward (one mini-batch).  logits_out (optional)
+ * receives (B, S, C) fp32, S = max_label_length + 1 (only the first group_len positions are written when
+ * refine_iters == 0), WITHOUT the repetition patch; rep_cut_out [B] (-1 = none) lets the caller apply
+ * models/parseq.py:301-309.  memory_out (optional, host) receives the encoder output (B*N, D) fp32. */
+int ytk_parseq_forward_f32(ytk_parseq* h, const float* images, int images_on_device, int B, int W, float* logits_out,
+                           int logits_on_device, int32_t* ids_out, float* probs_out, int32_t* steps_out,
+                           int32_t* rep_cut_out, float* memory_out, void* cuda_stream);
+/* algorithmic FLOPs (2*MAC; GEMMs + attention) and AR steps of the last forward call */
+double ytk_parseq_last_flops(ytk_parseq* h);
+int ytk_parseq_last_steps(ytk_parseq* h);
+
 #ifdef __cplusplus
 }
 #endif

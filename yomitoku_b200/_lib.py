@@ -55,6 +55,38 @@ def _declare_dbnet(lib):
     lib.ytk_dbnet_debug_tensor.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.c_char_p, c_void_p, c_ll, P(c_int)]
 
 
+class YtkParseqCfg(ctypes.Structure):
+    _fields_ = [(n, c_int) for n in (
+        "embed_dim", "enc_heads", "enc_depth", "patch_h", "patch_w", "img_h", "img_w", "num_tokens",
+        "max_label_length", "dec_heads", "mlp_ratio", "dec_mlp_ratio", "refine_iters", "repetition_stop",
+        "rep_period_max", "rep_min_run_p1", "rep_min_repeats")]
+
+
+class YtkCrop(ctypes.Structure):
+    _fields_ = [("pix_off", c_ll), ("w", c_int), ("wp", c_int), ("tok_off", c_int), ("ntok", c_int),
+                ("group", c_int)]
+
+
+def _declare_parseq(lib):
+    P = ctypes.POINTER
+    lib.ytk_parseq_create.restype = c_int
+    lib.ytk_parseq_create.argtypes = [P(YtkTensor), c_int, P(YtkParseqCfg), P(c_void_p)]
+    lib.ytk_parseq_destroy.restype = None
+    lib.ytk_parseq_destroy.argtypes = [c_void_p]
+    lib.ytk_parseq_set_refine_iters.restype = None
+    lib.ytk_parseq_set_refine_iters.argtypes = [c_void_p, c_int]
+    lib.ytk_parseq_forward_crops.restype = c_int
+    lib.ytk_parseq_forward_crops.argtypes = [c_void_p, c_void_p, c_ll, P(YtkCrop), c_int, c_int, c_void_p, c_void_p,
+                                             c_void_p, c_void_p]
+    lib.ytk_parseq_forward_f32.restype = c_int
+    lib.ytk_parseq_forward_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                           c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.ytk_parseq_last_flops.restype = ctypes.c_double
+    lib.ytk_parseq_last_flops.argtypes = [c_void_p]
+    lib.ytk_parseq_last_steps.restype = c_int
+    lib.ytk_parseq_last_steps.argtypes = [c_void_p]
+
+
 def tensor_table(state_dict):
     """state_dict (name -> torch tensor) -> (ctypes array of YtkTensor, keep-alive list). Tensors are converted to
     contiguous host fp32; integer buffers (num_batches_tracked) are skipped."""
@@ -86,6 +118,7 @@ def lib():
     l = ctypes.CDLL(LIB_PATH)
     _declare(l)
     _declare_dbnet(l)
+    _declare_parseq(l)
     _lib = l
     return l
 

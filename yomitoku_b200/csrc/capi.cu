@@ -9,6 +9,13 @@
 #include "dbnet_engine.h"
 #include "dbnet_ops.h"
 #include "gemm_tc.h"
+#include "parseq_engine.h"
+
+struct ytk_parseq {
+    ytk::ParseqModel model;
+    ytk::ParseqEngine engine;
+    std::mutex mu;
+};
 
 struct ytk_dbnet {
     ytk::DbnetModel model;
@@ -220,5 +227,105 @@ int ytk_dbnet_debug_tensor(ytk_dbnet* h, int n_pages, int Hn, int Wn, const char
     }
     return YTK_OK;
 }
+
+int ytk_parseq_create(const ytk_tensor* tensors, int n_tensors, const ytk_parseq_cfg* cfg, ytk_parseq** out) {
+    if (!tensors || !cfg || !out) {
+        ytk::set_error("ytk_parseq_create: null argument");
+        return YTK_ERR;
+    }
+    ytk::WeightSet ws;
+    for (int i = 0; i < n_tensors; ++i) {
+        ytk::TensorView v;
+        v.data = tensors[i].data;
+        v.ndim = tensors[i].ndim;
+        for (int d = 0; d < 4; ++d) v.shape[d] = d < v.ndim ? tensors[i].shape[d] : 1;
+        ws.map[tensors[i].name] = v;
+    }
+    ytk::ParseqCfg c{cfg->embed_dim, cfg->enc_heads, cfg->enc_depth, cfg->patch_h, cfg->patch_w, cfg->img_h,
+                     cfg->img_w, cfg->num_tokens, cfg->max_label_length, cfg->dec_heads, cfg->mlp_ratio,
+                     cfg->dec_mlp_ratio, cfg->refine_iters, cfg->repetition_stop, cfg->rep_period_max,
+                     cfg->rep_min_run_p1, cfg->rep_min_repeats};
+    auto h = std::make_unique<ytk_parseq>();
+    if (h->model.load(ws, c)) return YTK_ERR;
+    h->engine.m = &h->model;
+    *out = h.release();
+    return YTK_OK;
+}
+
+void ytk_parseq_destroy(ytk_parseq* h) { delete h; }
+
+void ytk_parseq_set_refine_iters(ytk_parseq* h, int refine_iters) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    h->model.cfg.refine_iters = refine_iters;
+}
+
+int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops_host, long long crops_bytes, const ytk_crop* crops,
+                             int n_crops, int n_groups, int32_t* ids_out, float* probs_out, int32_t* group_len_out,
+                             void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->model.cfg.refine_iters > 1) {
+        ytk::set_error("refine_iters > 1 is not implemented on the device path");
+        return YTK_ERR;
+    }
+    ytk::ParseqBatch b;
+    b.crops = crops_host;
+    b.crops_bytes = crops_bytes;
+    b.ngroups = n_groups;
+    b.descs.resize(n_crops);
+    const int gh = h->model.gh, pw = h->model.cfg.pw;
+    for (int i = 0; i < n_crops; ++i) {
+        const ytk_crop& c = crops[i];
+        if (c.wp % pw != 0 || c.wp < c.w || c.ntok != gh * (c.wp / pw) || c.group < 0 || c.group >= n_groups ||
+            c.wp > h->model.cfg.img_w) {
+            ytk::set_error("ytk_parseq_forward_crops: inconsistent crop descriptor %d (w=%d wp=%d ntok=%d group=%d)", i,
+                           c.w, c.wp, c.ntok, c.group);
+            return YTK_ERR;
+        }
+        b.descs[i] = ytk::CropDesc{c.pix_off, c.w, c.wp, c.tok_off, c.ntok, c.group};
+    }
+    return h->engine.forward(b, ids_out, probs_out, group_len_out, nullptr, 0, nullptr,
+                             static_cast<cudaStream_t>(cuda_stream))
+               ? YTK_ERR
+               : YTK_OK;
+}
+
+int ytk_parseq_forward_f32(ytk_parseq* h, const float* images, int images_on_device, int B, int W, float* logits_out,
+                           int logits_on_device, int32_t* ids_out, float* probs_out, int32_t* steps_out,
+                           int32_t* rep_cut_out, float* memory_out, void* cuda_stream) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->model.cfg.refine_iters > 1) {
+        ytk::set_error("refine_iters > 1 is not implemented on the device path");
+        return YTK_ERR;
+    }
+    const int pw = h->model.cfg.pw, gh = h->model.gh;
+    if (W % pw != 0 || W > h->model.cfg.img_w || W <= 0) {
+        ytk::set_error("ytk_parseq_forward_f32: width %d must be a positive multiple of %d and <= %d", W, pw,
+                       h->model.cfg.img_w);
+        return YTK_ERR;
+    }
+    ytk::ParseqBatch b;
+    b.images_f32 = images;
+    b.images_on_device = images_on_device;
+    b.image_w = W;
+    b.crops_bytes = images_on_device ? 0 : (long long)B * 3 * 32 * W * 4;
+    b.ngroups = 1;
+    b.descs.resize(B);
+    const int ntok = gh * (W / pw);
+    for (int i = 0; i < B; ++i) b.descs[i] = ytk::CropDesc{0, W, W, i * ntok, ntok, 0};
+    int glen = 0;
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    if (h->engine.forward(b, ids_out, probs_out, &glen, logits_out, logits_on_device, memory_out, st)) return YTK_ERR;
+    if (steps_out) *steps_out = glen;
+    if (rep_cut_out) {
+        if (cudaMemcpy(rep_cut_out, h->engine.ar.rep_cut, sizeof(int) * B, cudaMemcpyDeviceToHost) != cudaSuccess) {
+            ytk::set_error("rep_cut copy failed");
+            return YTK_ERR;
+        }
+    }
+    return YTK_OK;
+}
+
+double ytk_parseq_last_flops(ytk_parseq* h) { return h->engine.flops; }
+int ytk_parseq_last_steps(ytk_parseq* h) { return h->engine.last_steps; }
 
 }  // extern "C"

@@ -223,7 +223,14 @@ int DbnetModel::load(const WeightSet& ws) {
         owned.push_back(convt1.bias);
         const TensorView *w2 = ws.need(bz + "6.weight", 64 * 4), *b2 = ws.need(bz + "6.bias", 1);
         if (!w2 || !b2) return 1;
-        memcpy(convt2_w, w2->data, 64 * 4 * 4);
+        // [ci][1][i'][j'] -> [k = i'*2+j'][ci] for the fused epilogue
+        std::vector<float> fw(4 * 64);
+        for (int ci = 0; ci < 64; ++ci)
+            for (int k = 0; k < 4; ++k) fw[k * 64 + ci] = w2->data[ci * 4 + k];
+        void* fd = nullptr;
+        if (upload(fw.data(), fw.size() * 4, &fd)) return 1;
+        convt2_w_dev = reinterpret_cast<float*>(fd);
+        owned.push_back(fd);
         convt2_b = b2->data[0];
     }
     return 0;
@@ -394,32 +401,27 @@ int DbnetEngine::build(const DbnetModel& m, int n, int Hn_, int Wn_) {
         });
     }
     // ---- binarize head
-    void *b1, *b2, *prob_;
+    void *b1, *prob_;
     if (alloc("bin1", N, H4, W4, 64, false, &b1)) return 1;
     if (add_conv(m.bin_conv, fuse, N, H4, W4, 256, b1, 64, ACT_RELU)) return 1;
-    if (alloc("bin2", N, H2, W2, 64, false, &b2)) return 1;
-    {
-        ConvGeom g{N, H4, W4, 64, 64, 1, 1, 1, 0, 1, 256};
-        Epilogue e;
-        e.bias = m.convt1.bias;
-        e.out = b2;
-        e.ldc = 64;
-        e.act = ACT_RELU;
-        e.mode = EPI_SHUFFLE2X;
-        auto plan = std::make_shared<GemmPlan>();
-        if (conv_plan_create(plan.get(), b1, g, m.convt1.w, e)) return 1;
-        flops += plan->flops;
-        steps.push_back([plan](cudaStream_t st) { return gemm_plan_launch(plan.get(), st); });
-    }
     if (alloc("prob", N, Hn, Wn, 1, true, &prob_)) return 1;
     prob = reinterpret_cast<float*>(prob_);
     {
-        const DbnetModel* mp = &m;
-        float* pp = prob;
-        steps.push_back([=](cudaStream_t st) {
-            return launch_convt2_sigmoid(b2, N, H2, W2, mp->convt2_w, mp->convt2_b, pp, st);
-        });
-        flops += 2.0 * N * H2 * W2 * 64.0 * 4.0;
+        // ConvT(64->64,2,2)+BN+ReLU and ConvT(64->1,2,2)+sigmoid fused into one GEMM epilogue: the 64x(H/2)x(W/2)
+        // intermediate never touches HBM.
+        ConvGeom g{N, H4, W4, 64, 64, 1, 1, 1, 0, 1, 256};
+        Epilogue e;
+        e.bias = m.convt1.bias;
+        e.out = prob_;
+        e.out_f32 = 1;
+        e.ldc = 4;
+        e.mode = EPI_CONVT_FINAL;
+        e.fin_w = m.convt2_w_dev;
+        e.fin_b = m.convt2_b;
+        auto plan = std::make_shared<GemmPlan>();
+        if (conv_plan_create(plan.get(), b1, g, m.convt1.w, e)) return 1;
+        flops += plan->flops + 2.0 * N * H2 * W2 * 64.0 * 4.0;
+        steps.push_back([plan](cudaStream_t st) { return gemm_plan_launch(plan.get(), st); });
     }
     return 0;
 }

@@ -47,7 +47,8 @@ struct DbnetModel {
     ConvW lateral[4], outproj[4], asf_conv, bin_conv, convt1;
     float *asf_w1 = nullptr, *asf_w2 = nullptr;  // device: channel_wise 1x1 convs (16x64, 64x16)
     float asf_sp3[9], asf_sp1, asf_att[4 * 64];  // host copies of the tiny attention weights
-    float convt2_w[64 * 4], convt2_b;
+    float* convt2_w_dev = nullptr;  // device [4][64]: last transposed conv, k = i'*2+j'
+    float convt2_b = 0.f;
     std::vector<void*> owned;
     int load(const WeightSet& ws);
     int load_conv(const WeightSet& ws, const std::string& wname, const std::string& bnname, int Cout, int Cin, int k,

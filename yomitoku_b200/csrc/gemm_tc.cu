@@ -46,7 +46,9 @@ int num_sms() {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // 64 bf16 = 128 B = one swizzle row
 constexpr int kABytes = kBlockM * kBlockK * 2;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kStagePitch = 80;     // bytes per staged row: 64 B payload + 16 B pad (conflict-free 16 B accesses)
+constexpr int kEpiStageBytes = 8 * 32 * kStagePitch;
 
 template <int BLOCK_N>
 struct TileCfg {
@@ -54,14 +56,21 @@ struct TileCfg {
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
     static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; 128/256/512 are powers of two
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes =
+        kStages * kStageBytes + kEpiStageBytes + 1024 /*final-conv weights*/ + 1024 /*align slack*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-    if (act == ACT_RELU) return fmaxf(x, 0.f);
+// ragged last columns of a row segment: element-wise copy (rare; kept out of line)
+__device__ __noinline__ void copy_elems(void* dst, const void* src, int n, int esz) {
+    if (esz == 4)
+        for (int e = 0; e < n; ++e) reinterpret_cast<uint32_t*>(dst)[e] = reinterpret_cast<const uint32_t*>(src)[e];
+    else
+        for (int e = 0; e < n; ++e) reinterpret_cast<uint16_t*>(dst)[e] = reinterpret_cast<const uint16_t*>(src)[e];
+}
+// exact-erf GELU / sigmoid: kept out of line so the fully unrolled epilogue stays small (instruction cache)
+__device__ __noinline__ float act_slow(float x, int act) {
     if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-x));
-    return x;
+    return 1.f / (1.f + __expf(-x));
 }
 
 struct TileCoord {
@@ -81,7 +90,10 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& a, int tile, in
     return t;
 }
 
-template <int BLOCK_N>
+// Epilogue variants are compile-time (OUT_F32: fp32 vs bf16 output; RESID: 0 none, 1 bf16, 2 fp32; MODE: EpiMode) so
+// that each instantiation carries only its own store path - one kernel with every path inlined is ~190 KB of SASS and
+// thrashes the instruction cache.
+template <int BLOCK_N, int OUT_F32, int RESID, int MODE>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmMaps maps,
                                                               const __grid_constant__ GemmArgs args) {
     using Cfg = TileCfg<BLOCK_N>;
@@ -90,7 +102,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // 1024 B alignment for SWIZZLE_128B
 
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::kStageBytes);
+    uint8_t* epi_stage = smem + STAGES * Cfg::kStageBytes;
+    float* fin_w = reinterpret_cast<float*>(epi_stage + kEpiStageBytes);  // [4][64] weights of the fused final conv
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageBytes + 1024);
     uint64_t* empty_bar = full_bar + STAGES;
     uint64_t* tfull_bar = empty_bar + STAGES;
     uint64_t* tempty_bar = tfull_bar + 2;
@@ -106,7 +120,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 4);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
         }
         fence_mbar_init();
         tma_prefetch_desc(&maps.a[0]);
@@ -115,6 +129,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if (warp == 1) {
         tmem_alloc(tmem_slot, Cfg::kTmemCols);
         tmem_relinquish();
+    }
+    if constexpr (MODE == EPI_CONVT_FINAL) {
+        if (threadIdx.x >= 64) fin_w[threadIdx.x - 64] = args.fin_w[threadIdx.x - 64];
     }
     tc_fence_before();
     __syncthreads();
@@ -189,10 +206,23 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
         }
     } else {
-        // ------------------------------------------------------------------ epilogue (warps 2..5)
-        const int q = warp & 3;  // TMEM lane quadrant this warp may access
+        // ------------------------------------------------------------------ epilogue (warps 2..9)
+        // Two warps per TMEM lane quadrant; each owns every other 32-column chunk.  Values go
+        // TMEM -> registers (row per thread) -> bias/residual/activation -> per-warp shared staging -> coalesced
+        // 16-byte global stores (4 lanes per 64-byte row segment), so DRAM sees whole sectors.
+        constexpr bool kFin = (MODE == EPI_CONVT_FINAL);
+        constexpr bool kWide = (OUT_F32 != 0) || (RESID == 2);  // 16 columns (64 B of fp32) per staging pass
+        constexpr int CPP = kWide ? 16 : 32;
+        constexpr int NPASS = 32 / CPP;
+        constexpr int OESZ = OUT_F32 ? 4 : 2;
+        constexpr int RESZ = (RESID == 2) ? 4 : 2;
+        const int q = warp & 3;            // TMEM lane quadrant this warp may access
+        const int wset = (warp - 2) >> 2;  // 0 or 1
         const int row = q * 32 + lane;
         const int bw_mask = (1 << args.bw_log2) - 1;
+        uint8_t* stage = epi_stage + (warp - 2) * (32 * kStagePitch);
+        uint8_t* my_row = stage + lane * kStagePitch;
+        const int piece = lane & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
         for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
@@ -200,14 +230,24 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const int hh = tc.h0 + (row >> args.bw_log2);
             const int ww = tc.w0 + (row & bw_mask);
             const bool row_ok = (hh < args.Ho) && (ww < args.Wo);
-            const long long pix = (static_cast<long long>(tc.img) * args.Ho + hh) * args.Wo + ww;
-
+            // rows this lane moves in the coalesced phase: rr = it * 8 + lane / 4
+            int c_h[4], c_w[4];
+            bool c_ok[4];
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = q * 32 + it * 8 + (lane >> 2);
+                c_h[it] = tc.h0 + (rr >> args.bw_log2);
+                c_w[it] = tc.w0 + (rr & bw_mask);
+                c_ok[it] = (c_h[it] < args.Ho) && (c_w[it] < args.Wo);
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_addr =
                 tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+            [[maybe_unused]] float dots[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
+                if (((kFin ? (c >> 1) : c) & 1) != wset) continue;  // chunk belongs to the other warp set
                 const int col0 = tc.n0 + c * 32;
                 if (col0 >= args.Cout) break;  // warp-uniform
                 uint32_t v[32];
@@ -216,20 +256,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 float f[32];
 #pragma unroll
                 for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-                const bool full_chunk = (col0 + 32 <= args.Cout);
-
-                // output location
-                long long opix = pix;
-                int ocol = col0;
-                if (args.mode == EPI_SHUFFLE2X) {
-                    const int cq = args.Cout >> 2;
-                    const int sub = col0 / cq;
-                    ocol = col0 - sub * cq;
-                    opix = (static_cast<long long>(tc.img) * (2 * args.Ho) + (2 * hh + (sub >> 1))) * (2 * args.Wo) +
-                           (2 * ww + (sub & 1));
-                }
                 if (args.bias != nullptr) {
-                    if (full_chunk) {
+                    if (col0 + 32 <= args.Cout) {
                         const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
@@ -241,83 +269,161 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         }
                     } else {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j)
-                            if (col0 + j < args.Cout) f[j] += __ldg(args.bias + col0 + j);
+                        for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + min(col0 + j, args.Cout - 1));
                     }
                 }
-                if (row_ok) {
-                    if (args.resid != nullptr) {
-                        if (args.resid_f32) {
-                            const float* rp = reinterpret_cast<const float*>(args.resid) + opix * args.ldr + ocol;
-                            if (full_chunk) {
+                if constexpr (kFin) {
+                    // fused ConvTranspose2d(64->1, 2, 2) + sigmoid: this chunk holds 32 of the 64 channels of output
+                    // pixel (2h+i, 2w+j) of the first transposed conv (after BN+ReLU)
+                    const int chan0 = (c & 1) * 32;
 #pragma unroll
-                                for (int j = 0; j < 8; ++j) {
-                                    const float4 r = *reinterpret_cast<const float4*>(rp + 4 * j);
-                                    f[4 * j + 0] += r.x;
-                                    f[4 * j + 1] += r.y;
-                                    f[4 * j + 2] += r.z;
-                                    f[4 * j + 3] += r.w;
+                    for (int j = 0; j < 32; ++j) {
+                        const float x = fmaxf(f[j], 0.f);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) dots[k] += x * fin_w[k * 64 + chan0 + j];
+                    }
+                    if (c & 1) {
+                        if (row_ok) {
+                            const int sub = c >> 1;  // (i, j) of the first transposed conv
+                            const long long oy = 2LL * (2 * hh + (sub >> 1)), ox = 2LL * (2 * ww + (sub & 1));
+                            float* op = reinterpret_cast<float*>(args.out) +
+                                        (static_cast<long long>(tc.img) * (4 * args.Ho) + oy) * (4LL * args.Wo) + ox;
+                            float2 r0, r1;
+                            r0.x = 1.f / (1.f + __expf(-(dots[0] + args.fin_b)));
+                            r0.y = 1.f / (1.f + __expf(-(dots[1] + args.fin_b)));
+                            r1.x = 1.f / (1.f + __expf(-(dots[2] + args.fin_b)));
+                            r1.y = 1.f / (1.f + __expf(-(dots[3] + args.fin_b)));
+                            *reinterpret_cast<float2*>(op) = r0;
+                            *reinterpret_cast<float2*>(op + 4LL * args.Wo) = r1;
+                        }
+                        dots[0] = dots[1] = dots[2] = dots[3] = 0.f;
+                    }
+                } else {
+                    // output location of this chunk (the pixel index is remapped by the pixel-shuffle mode)
+                    int ocol = col0, sub = 0;
+                    if constexpr (MODE == EPI_SHUFFLE2X) {
+                        const int cq = args.Cout >> 2;
+                        sub = col0 / cq;
+                        ocol = col0 - sub * cq;
+                    }
+                    long long c_pix[4];
+#pragma unroll
+                    for (int it = 0; it < 4; ++it) {
+                        if constexpr (MODE == EPI_SHUFFLE2X)
+                            c_pix[it] = (static_cast<long long>(tc.img) * (2 * args.Ho) + (2 * c_h[it] + (sub >> 1))) *
+                                            (2LL * args.Wo) +
+                                        (2 * c_w[it] + (sub & 1));
+                        else
+                            c_pix[it] = (static_cast<long long>(tc.img) * args.Ho + c_h[it]) * args.Wo + c_w[it];
+                    }
+#pragma unroll
+                    for (int p = 0; p < NPASS; ++p) {
+                        const int pc0 = ocol + p * CPP;                             // first output column of the pass
+                        const int valid = min(CPP, args.Cout - (col0 + p * CPP));   // valid columns (may be <= 0)
+                        if (valid > 0) {
+                            // ---- residual: coalesced global -> staging -> own row
+                            if constexpr (RESID != 0) {
+                                constexpr int per16 = 16 / RESZ;
+                                const int e0 = piece * per16;
+#pragma unroll
+                                for (int it = 0; it < 4; ++it) {
+                                    const int rr = it * 8 + (lane >> 2);
+                                    uint8_t* sp = stage + rr * kStagePitch + piece * 16;
+                                    uint4 val = make_uint4(0, 0, 0, 0);
+                                    if (c_ok[it] && e0 < valid) {
+                                        const char* gp = reinterpret_cast<const char*>(args.resid) +
+                                                         (c_pix[it] * args.ldr + pc0 + e0) * RESZ;
+                                        if (e0 + per16 <= valid) {
+                                            val = *reinterpret_cast<const uint4*>(gp);
+                                            *reinterpret_cast<uint4*>(sp) = val;
+                                        } else {  // ragged last columns: element-wise into the staging row
+                                            *reinterpret_cast<uint4*>(sp) = val;
+                                            copy_elems(sp, gp, valid - e0, RESZ);
+                                        }
+                                    } else {
+                                        *reinterpret_cast<uint4*>(sp) = val;
+                                    }
                                 }
-                            } else {
+                                __syncwarp();
+                                if constexpr (RESID == 2) {
+                                    const float4* rp = reinterpret_cast<const float4*>(my_row);
 #pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < args.Cout) f[j] += rp[j];
+                                    for (int j = 0; j < 4; ++j) {
+                                        const float4 r = rp[j];
+                                        f[p * 16 + 4 * j + 0] += r.x;
+                                        f[p * 16 + 4 * j + 1] += r.y;
+                                        f[p * 16 + 4 * j + 2] += r.z;
+                                        f[p * 16 + 4 * j + 3] += r.w;
+                                    }
+                                } else {
+                                    const uint4* rp = reinterpret_cast<const uint4*>(my_row);
+#pragma unroll
+                                    for (int j = 0; j < CPP / 8; ++j) {
+                                        const uint4 r = rp[j];
+                                        const int b = p * CPP + 8 * j;
+                                        f[b + 0] += bf16_lo(r.x); f[b + 1] += bf16_hi(r.x);
+                                        f[b + 2] += bf16_lo(r.y); f[b + 3] += bf16_hi(r.y);
+                                        f[b + 4] += bf16_lo(r.z); f[b + 5] += bf16_hi(r.z);
+                                        f[b + 6] += bf16_lo(r.w); f[b + 7] += bf16_hi(r.w);
+                                    }
+                                }
+                                __syncwarp();
                             }
-                        } else {
-                            const __nv_bfloat16* rp =
-                                reinterpret_cast<const __nv_bfloat16*>(args.resid) + opix * args.ldr + ocol;
-                            if (full_chunk) {
+                            // ---- activation + pack into the staging row (own row only)
+                            if (args.act == ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < CPP; ++j) f[p * CPP + j] = fmaxf(f[p * CPP + j], 0.f);
+                            } else if (args.act != ACT_NONE) {
+#pragma unroll
+                                for (int j = 0; j < CPP; ++j) f[p * CPP + j] = act_slow(f[p * CPP + j], args.act);
+                            }
+                            if constexpr (OUT_F32) {
+                                float4* wp = reinterpret_cast<float4*>(my_row);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    const uint4 r = *reinterpret_cast<const uint4*>(rp + 8 * j);
-                                    f[8 * j + 0] += bf16_lo(r.x);
-                                    f[8 * j + 1] += bf16_hi(r.x);
-                                    f[8 * j + 2] += bf16_lo(r.y);
-                                    f[8 * j + 3] += bf16_hi(r.y);
-                                    f[8 * j + 4] += bf16_lo(r.z);
-                                    f[8 * j + 5] += bf16_hi(r.z);
-                                    f[8 * j + 6] += bf16_lo(r.w);
-                                    f[8 * j + 7] += bf16_hi(r.w);
+                                    float4 o;
+                                    o.x = f[p * 16 + 4 * j + 0];
+                                    o.y = f[p * 16 + 4 * j + 1];
+                                    o.z = f[p * 16 + 4 * j + 2];
+                                    o.w = f[p * 16 + 4 * j + 3];
+                                    wp[j] = o;
                                 }
                             } else {
+                                uint4* wp = reinterpret_cast<uint4*>(my_row);
 #pragma unroll
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < args.Cout) f[j] += __bfloat162float(rp[j]);
+                                for (int j = 0; j < CPP / 8; ++j) {
+                                    const int b = p * CPP + 8 * j;
+                                    uint4 o;
+                                    o.x = pack_bf16(f[b + 0], f[b + 1]);
+                                    o.y = pack_bf16(f[b + 2], f[b + 3]);
+                                    o.z = pack_bf16(f[b + 4], f[b + 5]);
+                                    o.w = pack_bf16(f[b + 6], f[b + 7]);
+                                    wp[j] = o;
+                                }
                             }
-                        }
-                    }
-                    if (args.act != ACT_NONE) {
+                            __syncwarp();
+                            // ---- coalesced staging -> global
+                            {
+                                constexpr int per16 = 16 / OESZ;
+                                constexpr int row_bytes = CPP * OESZ;
+                                const int e0 = piece * per16;
+                                if (piece * 16 < row_bytes && e0 < valid) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) f[j] = apply_act(f[j], args.act);
-                    }
-                    if (args.out_f32) {
-                        float* op = reinterpret_cast<float*>(args.out) + opix * args.ldc + ocol;
-                        if (full_chunk) {
-#pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                *reinterpret_cast<float4*>(op + 4 * j) =
-                                    make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < args.Cout) op[j] = f[j];
-                        }
-                    } else {
-                        __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + opix * args.ldc + ocol;
-                        if (full_chunk) {
-#pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                uint4 o;
-                                o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-                                o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-                                o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-                                o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
-                                *reinterpret_cast<uint4*>(op + 8 * j) = o;
+                                    for (int it = 0; it < 4; ++it) {
+                                        if (!c_ok[it]) continue;
+                                        const int rr = it * 8 + (lane >> 2);
+                                        const uint8_t* sp = stage + rr * kStagePitch + piece * 16;
+                                        char* gp = reinterpret_cast<char*>(args.out) +
+                                                   (c_pix[it] * args.ldc + pc0 + e0) * OESZ;
+                                        if (e0 + per16 <= valid) {
+                                            *reinterpret_cast<uint4*>(gp) = *reinterpret_cast<const uint4*>(sp);
+                                        } else {
+                                            copy_elems(gp, sp, valid - e0, OESZ);
+                                        }
+                                    }
+                                }
                             }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < args.Cout) op[j] = __float2bfloat16(f[j]);
+                            __syncwarp();
                         }
                     }
                 }
@@ -418,11 +524,18 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
     a.ldc = e.ldc;
     a.act = e.act;
     a.mode = e.mode;
+    a.fin_w = e.fin_w;
+    a.fin_b = e.fin_b;
     if (e.out == nullptr) {
         set_error("gemm plan: null output");
         return 1;
     }
-    if ((e.out_f32 ? (e.ldc % 4) : (e.ldc % 8)) != 0) {
+    if (e.mode == EPI_CONVT_FINAL) {
+        if (Cout != 256 || e.fin_w == nullptr || !e.out_f32) {
+            set_error("gemm plan: CONVT_FINAL needs Cout=256, fp32 output and the final conv weights");
+            return 1;
+        }
+    } else if ((e.out_f32 ? (e.ldc % 4) : (e.ldc % 8)) != 0) {
         set_error("gemm plan: ldc=%lld must keep rows 16-byte aligned", e.ldc);
         return 1;
     }
@@ -599,27 +712,52 @@ void gemm_plan_set_m(GemmPlan* plan, int M) {
     if (plan->grid < 1) plan->grid = 1;
 }
 
-template <int BLOCK_N>
-static int launch_bn(const GemmPlan* plan, cudaStream_t stream) {
+template <int BLOCK_N, int OUT_F32, int RESID, int MODE>
+static int launch_variant(const GemmPlan* plan, cudaStream_t stream) {
     using Cfg = TileCfg<BLOCK_N>;
     static bool attr_set = false;
+    auto kern = gemm_tc_kernel<BLOCK_N, OUT_F32, RESID, MODE>;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             Cfg::kSmemBytes);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
             return 1;
         }
         attr_set = true;
     }
-    gemm_tc_kernel<BLOCK_N><<<plan->grid, kThreads, Cfg::kSmemBytes, stream>>>(plan->maps, plan->args);
+    kern<<<plan->grid, kThreads, Cfg::kSmemBytes, stream>>>(plan->maps, plan->args);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        set_error("gemm_tc_kernel<%d> launch: %s", BLOCK_N, cudaGetErrorString(e));
+        set_error("gemm_tc_kernel<%d,%d,%d,%d> launch: %s", BLOCK_N, OUT_F32, RESID, MODE, cudaGetErrorString(e));
         return 1;
     }
     return 0;
+}
+
+template <int BLOCK_N>
+static int launch_bn(const GemmPlan* plan, cudaStream_t stream) {
+    const GemmArgs& a = plan->args;
+    const int resid = a.resid == nullptr ? 0 : (a.resid_f32 ? 2 : 1);
+    if (a.mode == EPI_CONVT_FINAL) {
+        if constexpr (BLOCK_N == 256) return launch_variant<256, 1, 0, EPI_CONVT_FINAL>(plan, stream);
+        set_error("CONVT_FINAL needs BLOCK_N = 256");
+        return 1;
+    }
+    if (a.mode == EPI_SHUFFLE2X) {
+        if (resid == 0 && !a.out_f32) return launch_variant<BLOCK_N, 0, 0, EPI_SHUFFLE2X>(plan, stream);
+        if (resid == 0 && a.out_f32) return launch_variant<BLOCK_N, 1, 0, EPI_SHUFFLE2X>(plan, stream);
+        set_error("SHUFFLE2X epilogue does not take a residual");
+        return 1;
+    }
+    if (!a.out_f32) {
+        if (resid == 0) return launch_variant<BLOCK_N, 0, 0, EPI_NORMAL>(plan, stream);
+        if (resid == 1) return launch_variant<BLOCK_N, 0, 1, EPI_NORMAL>(plan, stream);
+        return launch_variant<BLOCK_N, 0, 2, EPI_NORMAL>(plan, stream);
+    }
+    if (resid == 0) return launch_variant<BLOCK_N, 1, 0, EPI_NORMAL>(plan, stream);
+    if (resid == 1) return launch_variant<BLOCK_N, 1, 1, EPI_NORMAL>(plan, stream);
+    return launch_variant<BLOCK_N, 1, 2, EPI_NORMAL>(plan, stream);
 }
 
 int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream) {

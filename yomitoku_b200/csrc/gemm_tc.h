@@ -21,6 +21,9 @@ enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
 enum EpiMode : int {
     EPI_NORMAL = 0,
     EPI_SHUFFLE2X = 1,  // ConvTranspose2d(k=2,s=2): column block (i,j) of width Cout/4 goes to pixel (2h+i, 2w+j)
+    // DBNet binarize tail: ConvT(64->64,2,2)+BN+ReLU as above (Cout = 256) immediately followed by
+    // ConvT(64->1,2,2)+sigmoid evaluated in registers; out = fp32 probability map [N, 4*Ho, 4*Wo]
+    EPI_CONVT_FINAL = 2,
 };
 
 struct ConvTap {
@@ -51,6 +54,8 @@ struct GemmArgs {
     long long ldc;
     int act;
     int mode;
+    const float* fin_w;            // EPI_CONVT_FINAL: device [4][64] fp32, k = i'*2+j' of the last transposed conv
+    float fin_b;
 };
 
 struct Epilogue {
@@ -63,6 +68,8 @@ struct Epilogue {
     long long ldc = 0;
     int act = ACT_NONE;
     int mode = EPI_NORMAL;
+    const float* fin_w = nullptr;
+    float fin_b = 0.f;
 };
 
 struct ConvGeom {

@@ -1,0 +1,500 @@
+// PARSeq recognizer (ViT encoder + 1-layer two-stream decoder, greedy AR decode + one refinement pass) as a launch
+// plan of tcgen05 GEMMs, tensor-core flash attention and small fused kernels.  Replaces reference
+// models/parseq.py:159-311 and models/layers/parseq_transformer.py:69-244 for inference.
+//
+// What differs from the reference *implementation* while keeping its *results* (SURVEY.md Appendix A):
+//  * ragged batches: all crops of a call are packed token-major ([T, D] matrices); each crop keeps the padded width
+//    its reference mini-batch would have given it, so pad columns stay real tokens (A9) without dense padding;
+//  * K/V caches: encoder memory K/V projected once, content K/V appended per step (exactly output preserving because
+//    the decoder has depth 1 and never updates the content stream, A15);
+//  * the query-side self-attention projection of LN_q(pos_queries) is row independent and precomputed at load time;
+//  * greedy arg-max, EOS bookkeeping, the repetition detector and the per-group early stop run on the device
+//    (zero host syncs per step; the host peeks at a pinned counter every few steps);
+//  * softmax + per-position max are fused after the head GEMM: only (id, prob) per position leave the device.
+// Data layout in HBM: residual stream fp32 [T, D]; GEMM operands bf16; content K/V cache [position][row][2D] bf16.
+#include "parseq_engine.h"
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "ptx.cuh"
+
+namespace ytk {
+
+#define CK(x)                                                                   \
+    do {                                                                        \
+        cudaError_t e_ = (x);                                                   \
+        if (e_ != cudaSuccess) {                                                \
+            set_error("%s failed: %s (%s:%d)", #x, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            return 1;                                                           \
+        }                                                                       \
+    } while (0)
+
+static inline uint16_t f2bf(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
+    u += 0x7fffu + ((u >> 16) & 1u);
+    return (uint16_t)(u >> 16);
+}
+
+// ---------------------------------------------------------------------------------------------- model
+static int up(std::vector<void*>& owned, const void* host, size_t bytes, void** dev) {
+    CK(cudaMalloc(dev, bytes));
+    CK(cudaMemcpy(*dev, host, bytes, cudaMemcpyHostToDevice));
+    owned.push_back(*dev);
+    return 0;
+}
+
+static int load_linear(std::vector<void*>& owned, const float* w, const float* b, int N, int K, LinearW* out) {
+    const int Kp = (K + 63) / 64 * 64;
+    std::vector<uint16_t> p((size_t)N * Kp, 0);
+    for (int n = 0; n < N; ++n)
+        for (int k = 0; k < K; ++k) p[(size_t)n * Kp + k] = f2bf(w[(size_t)n * K + k]);
+    if (up(owned, p.data(), p.size() * 2, &out->w)) return 1;
+    void* d = nullptr;
+    if (up(owned, b, (size_t)N * 4, &d)) return 1;
+    out->b = reinterpret_cast<float*>(d);
+    out->N = N;
+    out->K = Kp;
+    return 0;
+}
+
+static int load_linear_named(std::vector<void*>& owned, const WeightSet& ws, const std::string& wn,
+                             const std::string& bn, int N, int K, LinearW* out) {
+    const TensorView *w = ws.need(wn, (long long)N * K), *b = ws.need(bn, N);
+    if (!w || !b) return 1;
+    return load_linear(owned, w->data, b->data, N, K, out);
+}
+
+static int load_ln(std::vector<void*>& owned, const WeightSet& ws, const std::string& p, int D, LnW* out) {
+    const TensorView *g = ws.need(p + ".weight", D), *b = ws.need(p + ".bias", D);
+    if (!g || !b) return 1;
+    void* d = nullptr;
+    if (up(owned, g->data, (size_t)D * 4, &d)) return 1;
+    out->g = reinterpret_cast<float*>(d);
+    if (up(owned, b->data, (size_t)D * 4, &d)) return 1;
+    out->b = reinterpret_cast<float*>(d);
+    return 0;
+}
+
+static void host_ln(const float* x, const float* g, const float* b, int D, float eps, float* y) {
+    double s = 0;
+    for (int i = 0; i < D; ++i) s += x[i];
+    const double mean = s / D;
+    double q = 0;
+    for (int i = 0; i < D; ++i) q += (x[i] - mean) * (x[i] - mean);
+    const double rstd = 1.0 / std::sqrt(q / D + eps);
+    for (int i = 0; i < D; ++i) y[i] = (float)((x[i] - mean) * rstd) * g[i] + b[i];
+}
+
+int ParseqModel::load(const WeightSet& ws, const ParseqCfg& c) {
+    cfg = c;
+    const int D = c.D;
+    S = c.max_label_length + 1;
+    C = c.num_tokens - 2;
+    gh = c.img_h / c.ph;
+    full_gw = c.img_w / c.pw;
+    if (D % 64 != 0 || (D / c.enc_heads) % 16 != 0 || (D / c.dec_heads) % 8 != 0 || D / c.enc_heads > 96 ||
+        D / c.dec_heads > 96 || D > 1024) {
+        set_error("PARSeq device engine supports embed_dim %% 64 == 0 and head dims 32/48/64/96 (got D=%d, heads %d/%d)",
+                  D, c.enc_heads, c.dec_heads);
+        return 1;
+    }
+    if (S != 101) {
+        // kMaxS in parseq_ops.cu; shorter label lengths fit, longer do not
+        if (S > 101) {
+            set_error("max_label_length %d > 100 unsupported", c.max_label_length);
+            return 1;
+        }
+    }
+    const std::string e = "encoder.";
+    // patch embedding conv as a GEMM: weight [D,3,ph,pw] flattened to K = 3*ph*pw (order c,py,px)
+    {
+        const int K = 3 * c.ph * c.pw;
+        const TensorView *w = ws.need(e + "patch_embed.proj.weight", (long long)D * K),
+                         *b = ws.need(e + "patch_embed.proj.bias", D);
+        if (!w || !b) return 1;
+        if (load_linear(owned, w->data, b->data, D, K, &patch)) return 1;
+        Kpatch = patch.K;
+        const TensorView* pe = ws.need(e + "pos_embed", (long long)gh * full_gw * D);
+        if (!pe) return 1;
+        void* d = nullptr;
+        if (up(owned, pe->data, (size_t)gh * full_gw * D * 4, &d)) return 1;
+        pos_embed = reinterpret_cast<float*>(d);
+    }
+    blocks.resize(c.enc_depth);
+    for (int i = 0; i < c.enc_depth; ++i) {
+        const std::string p = e + "blocks." + std::to_string(i) + ".";
+        EncBlock& bk = blocks[i];
+        if (load_ln(owned, ws, p + "norm1", D, &bk.ln1) || load_ln(owned, ws, p + "norm2", D, &bk.ln2)) return 1;
+        if (load_linear_named(owned, ws, p + "attn.qkv.weight", p + "attn.qkv.bias", 3 * D, D, &bk.qkv)) return 1;
+        if (load_linear_named(owned, ws, p + "attn.proj.weight", p + "attn.proj.bias", D, D, &bk.proj)) return 1;
+        if (load_linear_named(owned, ws, p + "mlp.fc1.weight", p + "mlp.fc1.bias", c.mlp_ratio * D, D, &bk.fc1)) return 1;
+        if (load_linear_named(owned, ws, p + "mlp.fc2.weight", p + "mlp.fc2.bias", D, c.mlp_ratio * D, &bk.fc2)) return 1;
+    }
+    if (load_ln(owned, ws, e + "norm", D, &enc_norm)) return 1;
+    const std::string d = "decoder.layers.0.";
+    if (load_ln(owned, ws, d + "norm1", D, &norm1) || load_ln(owned, ws, d + "norm2", D, &norm2) ||
+        load_ln(owned, ws, d + "norm_c", D, &norm_c) || load_ln(owned, ws, "decoder.norm", D, &dec_norm))
+        return 1;
+    const TensorView *sw = ws.need(d + "self_attn.in_proj_weight", 3LL * D * D),
+                     *sb = ws.need(d + "self_attn.in_proj_bias", 3 * D),
+                     *cw = ws.need(d + "cross_attn.in_proj_weight", 3LL * D * D),
+                     *cb = ws.need(d + "cross_attn.in_proj_bias", 3 * D);
+    if (!sw || !sb || !cw || !cb) return 1;
+    if (load_linear(owned, sw->data + (size_t)D * D, sb->data + D, 2 * D, D, &self_kv)) return 1;
+    if (load_linear(owned, cw->data, cb->data, D, D, &cross_q)) return 1;
+    if (load_linear(owned, cw->data + (size_t)D * D, cb->data + D, 2 * D, D, &cross_kv)) return 1;
+    if (load_linear_named(owned, ws, d + "self_attn.out_proj.weight", d + "self_attn.out_proj.bias", D, D, &self_out))
+        return 1;
+    if (load_linear_named(owned, ws, d + "cross_attn.out_proj.weight", d + "cross_attn.out_proj.bias", D, D, &cross_out))
+        return 1;
+    if (load_linear_named(owned, ws, d + "linear1.weight", d + "linear1.bias", c.dec_mlp_ratio * D, D, &lin1)) return 1;
+    if (load_linear_named(owned, ws, d + "linear2.weight", d + "linear2.bias", D, c.dec_mlp_ratio * D, &lin2)) return 1;
+    if (load_linear_named(owned, ws, "head.weight", "head.bias", C, D, &head)) return 1;
+    const TensorView *em = ws.need("text_embed.embedding.weight", (long long)c.num_tokens * D),
+                     *pq = ws.need("pos_queries", (long long)S * D);
+    if (!em || !pq) return 1;
+    void* dv = nullptr;
+    if (up(owned, em->data, (size_t)c.num_tokens * D * 4, &dv)) return 1;
+    embed = reinterpret_cast<float*>(dv);
+    if (up(owned, pq->data, (size_t)S * D * 4, &dv)) return 1;
+    pos_q = reinterpret_cast<float*>(dv);
+    // ---- row-independent precomputation (fp32 on the host)
+    const TensorView *gq = ws.need(d + "norm_q.weight", D), *bq = ws.need(d + "norm_q.bias", D),
+                     *gc = ws.need(d + "norm_c.weight", D), *bc = ws.need(d + "norm_c.bias", D);
+    if (!gq || !bq || !gc || !bc) return 1;
+    {
+        std::vector<float> ln(D);
+        std::vector<uint16_t> q((size_t)S * D);
+        for (int i = 0; i < S; ++i) {
+            host_ln(pq->data + (size_t)i * D, gq->data, bq->data, D, 1e-5f, ln.data());
+            for (int n = 0; n < D; ++n) {
+                const float* wr = sw->data + (size_t)n * D;
+                double acc = sb->data[n];
+                for (int k = 0; k < D; ++k) acc += (double)wr[k] * ln[k];
+                q[(size_t)i * D + n] = f2bf((float)acc);
+            }
+        }
+        if (up(owned, q.data(), q.size() * 2, &q_self)) return 1;
+        // content position 0 = sqrt(D) * E[BOS] (no positional term), LN_c, K/V projection
+        std::vector<float> c0(D), l0(D);
+        const float sq = std::sqrt((float)D);
+        const int bos = c.num_tokens - 2;
+        for (int k = 0; k < D; ++k) c0[k] = sq * em->data[(size_t)bos * D + k];
+        host_ln(c0.data(), gc->data, bc->data, D, 1e-5f, l0.data());
+        std::vector<uint16_t> kv(2 * D);
+        for (int n = 0; n < 2 * D; ++n) {
+            const float* wr = sw->data + (size_t)(D + n) * D;
+            double acc = sb->data[D + n];
+            for (int k = 0; k < D; ++k) acc += (double)wr[k] * l0[k];
+            kv[n] = f2bf((float)acc);
+        }
+        if (up(owned, kv.data(), kv.size() * 2, &ckv0)) return 1;
+    }
+    return 0;
+}
+
+ParseqModel::~ParseqModel() {
+    for (void* p : owned) cudaFree(p);
+}
+
+// ---------------------------------------------------------------------------------------------- engine
+static int dmalloc(std::vector<void*>& bufs, void** p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    CK(cudaMalloc(p, bytes));
+    bufs.push_back(*p);
+    return 0;
+}
+
+int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int groups) {
+    if (tok <= cap_tok && rows <= cap_rows && crop_bytes <= cap_crop_bytes && groups <= cap_groups) return 0;
+    for (void* p : bufs) cudaFree(p);
+    bufs.clear();
+    cap_tok = std::max(cap_tok, tok);
+    cap_rows = std::max(cap_rows, rows);
+    cap_crop_bytes = std::max(cap_crop_bytes, crop_bytes);
+    cap_groups = std::max(cap_groups, groups);
+    const int D = m->cfg.D, S = m->S;
+    const long long T = (cap_tok + 127) / 128 * 128;
+    const long long B = cap_rows;
+    const long long R = B * S;
+    const long long Rp = (R + 127) / 128 * 128;
+    const int Hm = std::max(m->cfg.mlp_ratio, m->cfg.dec_mlp_ratio) * D;
+#define DM(ptr, bytes)                                                             \
+    do {                                                                           \
+        void* t_ = nullptr;                                                        \
+        if (dmalloc(bufs, &t_, (size_t)(bytes))) return 1;                         \
+        ptr = reinterpret_cast<decltype(ptr)>(t_);                                 \
+    } while (0)
+    DM(crops_dev, cap_crop_bytes + 64);
+    DM(descs_dev, sizeof(CropDesc) * B);
+    DM(seqs_enc, sizeof(SeqDesc) * B);
+    DM(seqs_ref, sizeof(SeqDesc) * B);
+    DM(A_patch, T * m->Kpatch * 2);
+    DM(x, T * D * 4);
+    DM(h, T * D * 2);
+    DM(qkv, T * 3 * D * 2);
+    DM(att, T * D * 2);
+    DM(mlp, std::max(T, Rp) * Hm * 2);
+    DM(mem, T * D * 2);
+    DM(memkv, T * 2 * D * 2);
+    DM(x1, Rp * D * 4);
+    DM(hb, Rp * D * 2);
+    DM(qc, Rp * D * 2);
+    DM(sa, Rp * D * 2);
+    DM(oc, Rp * D * 2);
+    mlpb = mlp;
+    DM(cin, Rp * D * 2);
+    DM(ckv, Rp * 2 * D * 2);
+    ldl = (m->C + 255) / 256 * 256;
+    logits_rows = (int)std::min<long long>(Rp, 16384);
+    if (logits_rows < B) logits_rows = (int)((B + 127) / 128 * 128);
+    DM(logits, (long long)logits_rows * ldl * 4);
+    DM(row_group, 4 * B);
+    DM(klen, 4 * B);
+    DM(kpad, 4 * B);
+    DM(ids, 4 * R);
+    DM(probs, 4 * R);
+    DM(ar_block, 4 * (2 * R + 3 * B + cap_groups + 2));
+#undef DM
+    ar.tgt = ar_block;
+    ar.raw = ar.tgt + R;
+    ar.rep_cut = ar.raw + R;
+    ar.rep_done = ar.rep_cut + B;
+    ar.has_eos = ar.rep_done + B;
+    ar.group_len = ar.has_eos + B;
+    ar.n_active = ar.group_len + cap_groups;
+    ar.step = ar.n_active + 1;
+    if (!host_flag) CK(cudaMallocHost(reinterpret_cast<void**>(&host_flag), 2 * sizeof(int)));
+    return 0;
+}
+
+ParseqEngine::~ParseqEngine() {
+    for (void* p : bufs) cudaFree(p);
+    if (host_flag) cudaFreeHost(host_flag);
+}
+
+namespace {
+struct Lin {
+    // small helper: build + launch a linear layer plan
+    static int run(const void* A, long long lda, int M, const LinearW& w, void* out, long long ldc, int out_f32, int act,
+                   const void* resid, int resid_f32, long long ldr, cudaStream_t st, double* flops,
+                   GemmPlan* keep = nullptr) {
+        Epilogue e;
+        e.bias = w.b;
+        e.resid = resid;
+        e.resid_f32 = resid_f32;
+        e.ldr = ldr;
+        e.out = out;
+        e.out_f32 = out_f32;
+        e.ldc = ldc;
+        e.act = act;
+        GemmPlan local;
+        GemmPlan* p = keep ? keep : &local;
+        if (gemm_plan_create(p, A, lda, M, w.K, w.w, w.N, e)) return 1;
+        if (flops) *flops += p->flops;
+        return gemm_plan_launch(p, st);
+    }
+};
+}  // namespace
+
+int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, int* group_len_out, float* logits_out,
+                          int logits_on_device, float* memory_out, cudaStream_t st) {
+    const ParseqCfg& c = m->cfg;
+    const int D = c.D, S = m->S, C = m->C;
+    const int B = (int)b.descs.size();
+    if (B == 0) return 0;
+    long long T = 0;
+    int max_ntok = 0;
+    for (const CropDesc& d : b.descs) {
+        T = std::max<long long>(T, (long long)d.tok_off + d.ntok);
+        max_ntok = std::max(max_ntok, d.ntok);
+        if (d.ntok > 800) {
+            set_error("crop with %d encoder tokens exceeds the supported 800", d.ntok);
+            return 1;
+        }
+    }
+    if (ensure(T, B, b.crops_bytes, b.ngroups)) return 1;
+    flops = 0;
+    const int R = B * S;
+    const int eos = 0, bos = c.num_tokens - 2, pad_id = c.num_tokens - 1;
+    // ---------------- upload descriptors (+ crops)
+    std::vector<SeqDesc> se(B), sr(B);
+    std::vector<int> rg(B);
+    for (int i = 0; i < B; ++i) {
+        se[i] = SeqDesc{b.descs[i].tok_off, b.descs[i].ntok, b.descs[i].tok_off, b.descs[i].ntok};
+        sr[i] = SeqDesc{i * S, S, b.descs[i].tok_off, b.descs[i].ntok};
+        rg[i] = b.descs[i].group;
+    }
+    CK(cudaMemcpyAsync(descs_dev, b.descs.data(), sizeof(CropDesc) * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(seqs_enc, se.data(), sizeof(SeqDesc) * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(seqs_ref, sr.data(), sizeof(SeqDesc) * B, cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(row_group, rg.data(), 4 * B, cudaMemcpyHostToDevice, st));
+    if (b.images_f32) {
+        const float* img = b.images_f32;
+        if (!b.images_on_device) {
+            const size_t bytes = (size_t)B * 3 * 32 * b.image_w * 4;
+            CK(cudaMemcpyAsync(crops_dev, img, bytes, cudaMemcpyHostToDevice, st));
+            img = reinterpret_cast<const float*>(crops_dev);
+        }
+        if (launch_patchify_f32(img, B, b.image_w, c.ph, c.pw, m->Kpatch, m->pos_embed, m->full_gw, D, A_patch, x, st))
+            return 1;
+    } else {
+        CK(cudaMemcpyAsync(crops_dev, b.crops, b.crops_bytes, cudaMemcpyHostToDevice, st));
+        if (launch_patchify_u8(crops_dev, descs_dev, B, c.ph, c.pw, m->Kpatch, m->pos_embed, m->full_gw, D, A_patch, x,
+                               (int)T, st))
+            return 1;
+    }
+    // the host vectors above must outlive the async copies
+    CK(cudaStreamSynchronize(st));
+    // ---------------- encoder (reference Encoder.forward, parseq_transformer.py:206-234)
+    const int Ti = (int)T;
+    if (Lin::run(A_patch, m->Kpatch, Ti, m->patch, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
+    const int hd_e = D / c.enc_heads;
+    for (const EncBlock& bk : m->blocks) {
+        if (launch_layernorm(x, Ti, D, bk.ln1.g, bk.ln1.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
+        if (Lin::run(h, D, Ti, bk.qkv, qkv, 3 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
+        const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+        if (launch_flash_attention(q, 3 * D, q + D, q + 2 * D, 3 * D, att, D, seqs_enc, B, max_ntok, c.enc_heads, hd_e,
+                                   st))
+            return 1;
+        if (Lin::run(att, D, Ti, bk.proj, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
+        if (launch_layernorm(x, Ti, D, bk.ln2.g, bk.ln2.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
+        if (Lin::run(h, D, Ti, bk.fc1, mlp, bk.fc1.N, 0, ACT_GELU, nullptr, 0, 0, st, &flops)) return 1;
+        if (Lin::run(mlp, bk.fc1.N, Ti, bk.fc2, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
+    }
+    for (const CropDesc& d : b.descs) flops += 4.0 * d.ntok * (double)d.ntok * D * c.enc_depth;
+    // memory = final LayerNorm (fp32 copy into x1-sized scratch only when the caller wants it)
+    if (launch_layernorm(x, Ti, D, m->enc_norm.g, m->enc_norm.b, 1e-6f, mem, memory_out ? x : nullptr, nullptr, 1,
+                         nullptr, 0, 0, st))
+        return 1;
+    if (memory_out) CK(cudaMemcpyAsync(memory_out, x, (size_t)Ti * D * 4, cudaMemcpyDeviceToHost, st));
+    // memory K/V once (the reference re-projects it in every AR step)
+    if (Lin::run(mem, D, Ti, m->cross_kv, memkv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
+    // ---------------- AR decode (reference parseq.py:192-252)
+    CK(cudaMemsetAsync(ar_block, 0, 4 * (size_t)(2 * R + 3 * B + cap_groups + 2), st));
+    if (launch_fill_i32(ar.tgt, pad_id, R, st)) return 1;
+    if (launch_fill_i32(ar.rep_cut, -1, B, st)) return 1;
+    {
+        std::vector<int> first(B, bos);  // tgt[:, 0] = BOS
+        CK(cudaMemcpy2DAsync(ar.tgt, sizeof(int) * S, first.data(), sizeof(int), sizeof(int), B, cudaMemcpyHostToDevice,
+                             st));
+        CK(cudaStreamSynchronize(st));
+    }
+    if (launch_bcast_rows(m->ckv0, ckv, 2 * D * 2, B, st)) return 1;
+    const int hd_d = D / c.dec_heads;
+    // plans reused by every step
+    GemmPlan p_so, p_cq, p_co, p_l1, p_l2, p_hd, p_kv;
+    Epilogue e;
+    auto mk = [&](GemmPlan* p, const void* A, long long lda, int M, const LinearW& w, void* out, long long ldc,
+                  int out_f32, int act, const void* resid, int resid_f32, long long ldr) {
+        Epilogue ep;
+        ep.bias = w.b;
+        ep.resid = resid;
+        ep.resid_f32 = resid_f32;
+        ep.ldr = ldr;
+        ep.out = out;
+        ep.out_f32 = out_f32;
+        ep.ldc = ldc;
+        ep.act = act;
+        return gemm_plan_create(p, A, lda, M, w.K, w.w, w.N, ep);
+    };
+    (void)e;
+    if (mk(&p_so, sa, D, B, m->self_out, x1, D, 1, ACT_NONE, nullptr, 0, 0)) return 1;
+    if (mk(&p_cq, hb, D, B, m->cross_q, qc, D, 0, ACT_NONE, nullptr, 0, 0)) return 1;
+    if (mk(&p_co, oc, D, B, m->cross_out, x1, D, 1, ACT_NONE, x1, 1, D)) return 1;
+    if (mk(&p_l1, hb, D, B, m->lin1, mlpb, m->lin1.N, 0, ACT_GELU, nullptr, 0, 0)) return 1;
+    if (mk(&p_l2, mlpb, m->lin1.N, B, m->lin2, x1, D, 1, ACT_NONE, x1, 1, D)) return 1;
+    if (mk(&p_hd, hb, D, B, m->head, logits, ldl, 1, ACT_NONE, nullptr, 0, 0)) return 1;
+    if (mk(&p_kv, cin, D, B, m->self_kv, ckv, 2 * D, 0, ACT_NONE, nullptr, 0, 0)) return 1;
+    const double step_flops = p_so.flops + p_cq.flops + p_co.flops + p_l1.flops + p_l2.flops + p_hd.flops + p_kv.flops;
+    int steps_run = 0;
+    for (int i = 0; i < S; ++i) {
+        if (launch_dec_self_attn(m->q_self, ckv, B, D, c.dec_heads, 0, ar.step, nullptr, nullptr, sa, st)) return 1;
+        if (gemm_plan_launch(&p_so, st)) return 1;
+        // x1 += pos_queries[i] (the query stream's residual input), then norm1
+        if (launch_layernorm(x1, B, D, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, 1, ar.step, 0, 1, st))
+            return 1;
+        if (gemm_plan_launch(&p_cq, st)) return 1;
+        if (launch_dec_cross_attn(qc, memkv, descs_dev, B, D, c.dec_heads, oc, st)) return 1;
+        if (gemm_plan_launch(&p_co, st)) return 1;
+        if (launch_layernorm(x1, B, D, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
+            return 1;
+        if (gemm_plan_launch(&p_l1, st)) return 1;
+        if (gemm_plan_launch(&p_l2, st)) return 1;
+        if (launch_layernorm(x1, B, D, m->dec_norm.g, m->dec_norm.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
+            return 1;
+        if (gemm_plan_launch(&p_hd, st)) return 1;
+        if (c.refine_iters == 0 || logits_out) {
+            if (c.refine_iters == 0) {
+                if (launch_softmax_max(logits, ldl, C, B, S, S, i, nullptr, eos, ids, probs, st)) return 1;
+                if (logits_out)
+                    CK(cudaMemcpy2DAsync(logits_out + (size_t)i * C, (size_t)S * C * 4, logits, ldl * 4, (size_t)C * 4, B,
+                                         logits_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+            }
+        }
+        if (launch_ar_control(logits, ldl, C, B, S, row_group, b.ngroups, ar, eos, c.rep_on, c.rep_period_max,
+                              c.rep_min_run_p1, c.rep_min_repeats, m->embed, m->pos_q, D, m->norm_c.g, m->norm_c.b, cin,
+                              st))
+            return 1;
+        steps_run = i + 1;
+        flops += step_flops;
+        if (i + 1 < S) {
+            p_kv.args.out = reinterpret_cast<__nv_bfloat16*>(ckv) + (size_t)(i + 1) * B * 2 * D;
+            if (gemm_plan_launch(&p_kv, st)) return 1;
+        }
+        // early stop: peek at the device-side counter every 4 steps (no sync on the other steps)
+        if ((i & 3) == 3 || i + 1 == S) {
+            CK(cudaMemcpyAsync(host_flag, ar.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            if (host_flag[0] == 0) break;
+        }
+    }
+    last_steps = steps_run;
+    for (const CropDesc& d : b.descs) flops += 4.0 * d.ntok * (double)D * steps_run;  // cross attention
+    if (c.refine_iters == 0) {
+        if (launch_apply_rep_cut(ar.rep_cut, B, S, C, eos, ids, probs, st)) return 1;
+    } else {
+        // ---------------- refinement (reference parseq.py:264-299), all 101 queries of every row
+        if (launch_refine_embed(ar.raw, row_group, ar.group_len, B, S, bos, eos, m->embed, m->pos_q, D, m->norm_c.g,
+                                m->norm_c.b, cin, klen, kpad, st))
+            return 1;
+        if (Lin::run(cin, D, R, m->self_kv, ckv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
+        if (launch_dec_self_attn(m->q_self, ckv, B, D, c.dec_heads, 1, nullptr, klen, kpad, sa, st)) return 1;
+        if (Lin::run(sa, D, R, m->self_out, x1, D, 1, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
+        if (launch_layernorm(x1, R, D, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, S, nullptr, 0, 1, st))
+            return 1;
+        if (Lin::run(hb, D, R, m->cross_q, qc, D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
+        const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(memkv);
+        if (launch_flash_attention(qc, D, kv, kv + D, 2 * D, oc, D, seqs_ref, B, S, c.dec_heads, hd_d, st)) return 1;
+        for (const CropDesc& d : b.descs) flops += 4.0 * S * (double)d.ntok * D;
+        if (Lin::run(oc, D, R, m->cross_out, x1, D, 1, ACT_NONE, x1, 1, D, st, &flops)) return 1;
+        if (launch_layernorm(x1, R, D, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
+            return 1;
+        if (Lin::run(hb, D, R, m->lin1, mlpb, m->lin1.N, 0, ACT_GELU, nullptr, 0, 0, st, &flops)) return 1;
+        if (Lin::run(mlpb, m->lin1.N, R, m->lin2, x1, D, 1, ACT_NONE, x1, 1, D, st, &flops)) return 1;
+        if (launch_layernorm(x1, R, D, m->dec_norm.g, m->dec_norm.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
+            return 1;
+        for (int r0 = 0; r0 < R; r0 += logits_rows) {
+            const int rows = std::min(logits_rows, R - r0);
+            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(hb) + (size_t)r0 * D;
+            if (Lin::run(a, D, rows, m->head, logits, ldl, 1, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
+            if (launch_softmax_max(logits, ldl, C, rows, S, 1, r0, ar.rep_cut, eos, ids, probs, st)) return 1;
+            if (logits_out) {
+                // model-level seam: materialise the (B, 101, C) logits; the repetition patch is applied by the caller
+                CK(cudaMemcpy2DAsync(logits_out + (size_t)r0 * C, (size_t)C * 4, logits, ldl * 4, (size_t)C * 4, rows,
+                                     logits_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    CK(cudaMemcpyAsync(ids_out, ids, 4 * (size_t)R, cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(probs_out, probs, 4 * (size_t)R, cudaMemcpyDeviceToHost, st));
+    if (group_len_out) CK(cudaMemcpyAsync(group_len_out, ar.group_len, 4 * (size_t)b.ngroups, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    return 0;
+}
+
+}  // namespace ytk

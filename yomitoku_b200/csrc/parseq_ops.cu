@@ -1,0 +1,955 @@
+// Non-GEMM kernels of the PARSeq recognizer (sm_100a): patchify, LayerNorm, flash attention over packed ragged
+// sequences, the decoder's small attention kernels and the device-side greedy / EOS / repetition control logic that
+// removes every host sync from the AR loop.  Reference: models/parseq.py:133-311, models/layers/parseq_transformer.py.
+#include "parseq_ops.h"
+
+#include <cfloat>
+
+#include "gemm_tc.h"
+#include "ptx.cuh"
+
+namespace ytk {
+
+// =================================================================================================== patchify
+// Replaces timm PatchEmbed.proj's im2col (reference parseq_transformer.py:220-227): the conv itself is a tcgen05 GEMM;
+// this kernel writes its A operand and seeds the fp32 residual stream with the cropped positional embedding.
+// Normalisation = ToTensor + Normalize(0.5, 0.5) (data/dataset.py:57-62); pixels right of the stored canvas are the
+// collate padding value -1.0 (text_recognizer.py:146-156).
+__global__ void patchify_u8_kernel(const uint8_t* __restrict__ crops, const CropDesc* __restrict__ descs, int ph,
+                                   int pw, int Kpad, const float* __restrict__ pos_embed, int full_gw, int D,
+                                   __nv_bfloat16* __restrict__ A, float* __restrict__ x) {
+    const CropDesc d = descs[blockIdx.y];
+    const int gw = d.wp / pw;
+    const int K = 3 * ph * pw;
+    for (int t = blockIdx.x; t < d.ntok; t += gridDim.x) {
+        const int gy = t / gw, gx = t - gy * gw;
+        const long long row = (long long)d.tok_off + t;
+        for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+            float v = 0.f;
+            if (k < K) {
+                const int c = k / (ph * pw);
+                const int r = k - c * ph * pw;
+                const int py = r / pw, px = r - py * pw;
+                const int yy = gy * ph + py, xx = gx * pw + px;
+                v = -1.f;
+                if (xx < d.w) {
+                    const float u = (float)crops[d.pix_off + ((long long)yy * d.w + xx) * 3 + c];
+                    v = (u / 255.f - 0.5f) / 0.5f;
+                }
+            }
+            A[row * Kpad + k] = __float2bfloat16(v);
+        }
+        const float* pe = pos_embed + ((long long)gy * full_gw + gx) * D;
+        for (int j = threadIdx.x; j < D; j += blockDim.x) x[row * D + j] = pe[j];
+    }
+}
+
+int launch_patchify_u8(const uint8_t* crops, const CropDesc* descs, int ncrops, int ph, int pw, int Kpad,
+                       const float* pos_embed, int full_gw, int D, void* A, float* x, int T, cudaStream_t st) {
+    (void)T;
+    dim3 grid(64, ncrops);
+    patchify_u8_kernel<<<grid, 128, 0, st>>>(crops, descs, ph, pw, Kpad, pos_embed, full_gw, D,
+                                             reinterpret_cast<__nv_bfloat16*>(A), x);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+__global__ void patchify_f32_kernel(const float* __restrict__ img, int W, int ph, int pw, int Kpad,
+                                    const float* __restrict__ pos_embed, int full_gw, int D,
+                                    __nv_bfloat16* __restrict__ A, float* __restrict__ x) {
+    const int b = blockIdx.y;
+    const int gw = W / pw, gh = 32 / ph;
+    const int ntok = gh * gw;
+    const int K = 3 * ph * pw;
+    for (int t = blockIdx.x; t < ntok; t += gridDim.x) {
+        const int gy = t / gw, gx = t - gy * gw;
+        const long long row = (long long)b * ntok + t;
+        for (int k = threadIdx.x; k < Kpad; k += blockDim.x) {
+            float v = 0.f;
+            if (k < K) {
+                const int c = k / (ph * pw);
+                const int r = k - c * ph * pw;
+                const int py = r / pw, px = r - py * pw;
+                v = img[(((long long)b * 3 + c) * 32 + gy * ph + py) * W + gx * pw + px];
+            }
+            A[row * Kpad + k] = __float2bfloat16(v);
+        }
+        const float* pe = pos_embed + ((long long)gy * full_gw + gx) * D;
+        for (int j = threadIdx.x; j < D; j += blockDim.x) x[row * D + j] = pe[j];
+    }
+}
+
+int launch_patchify_f32(const float* images, int B, int W, int ph, int pw, int Kpad, const float* pos_embed,
+                        int full_gw, int D, void* A, float* x, cudaStream_t st) {
+    dim3 grid(64, B);
+    patchify_f32_kernel<<<grid, 128, 0, st>>>(images, W, ph, pw, Kpad, pos_embed, full_gw, D,
+                                              reinterpret_cast<__nv_bfloat16*>(A), x);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// =================================================================================================== LayerNorm
+// One warp per row, fp32 statistics (two-pass over registers), bf16 (and optional fp32) output.
+constexpr int kLnMaxPerLane = 32;  // D <= 1024
+
+__global__ void layernorm_kernel(float* __restrict__ x, int M, int D, const float* __restrict__ gamma,
+                                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16,
+                                 float* __restrict__ out_f32, const float* __restrict__ addvec, int period,
+                                 const int* __restrict__ add_row0_dev, int add_row0, int writeback) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= M) return;
+    float* xr = x + (long long)warp * D;
+    const int per = (D + 31) / 32;
+    float v[kLnMaxPerLane];
+    const float* av = nullptr;
+    if (addvec != nullptr) {
+        const int r0 = add_row0_dev ? *add_row0_dev : add_row0;
+        av = addvec + (long long)((warp % period) + r0) * D;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        if (i < per) {
+            const int j = lane + 32 * i;
+            float t = 0.f;
+            if (j < D) {
+                t = xr[j];
+                if (av) {
+                    t += av[j];
+                    if (writeback) xr[j] = t;
+                }
+            }
+            v[i] = t;
+            s += t;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        if (i < per) {
+            const int j = lane + 32 * i;
+            if (j < D) {
+                const float dlt = v[i] - mean;
+                q += dlt * dlt;
+            }
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)D + eps);
+#pragma unroll
+    for (int i = 0; i < kLnMaxPerLane; ++i) {
+        if (i < per) {
+            const int j = lane + 32 * i;
+            if (j < D) {
+                const float y = (v[i] - mean) * rstd * gamma[j] + beta[j];
+                if (out_bf16) out_bf16[(long long)warp * D + j] = __float2bfloat16(y);
+                if (out_f32) out_f32[(long long)warp * D + j] = y;
+            }
+        }
+    }
+}
+
+int launch_layernorm(float* x, int M, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
+                     float* out_f32, const float* addvec, int period, const int* add_row0_dev, int add_row0,
+                     int writeback, cudaStream_t st) {
+    if (D > 32 * kLnMaxPerLane) {
+        set_error("layernorm: D=%d too large", D);
+        return 1;
+    }
+    if (M <= 0) return 0;
+    const int warps_per_block = 8;
+    layernorm_kernel<<<(M + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
+        x, M, D, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, addvec,
+        period > 0 ? period : 1, add_row0_dev, add_row0, writeback);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// =================================================================================================== flash attention
+// softmax(Q K^T / sqrt(hd)) V over packed ragged sequences (encoder self-attention: timm Attention /
+// F.scaled_dot_product_attention without mask, and the refinement cross-attention).  Tensor-core path: mma.sync
+// m16n8k16 bf16 with fp32 accumulation; 64 queries per CTA (4 warps x 16), 64-key tiles staged with cp.async.
+// HD = head dim (multiple of 16, <= 96).
+__device__ __forceinline__ void ldmatrix_x4(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3, uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3,
+                                                  uint32_t addr) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                               uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+template <int HD>
+__global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq,
+                                                         const __nv_bfloat16* __restrict__ K,
+                                                         const __nv_bfloat16* __restrict__ V, long long ldkv,
+                                                         __nv_bfloat16* __restrict__ O, long long ldo,
+                                                         const SeqDesc* __restrict__ seqs, float scale_log2) {
+    constexpr int LDS = HD + 8;  // padded row (bf16 elements): 16 B aligned rows, conflict-free ldmatrix
+    __shared__ __align__(16) __nv_bfloat16 sQ[64 * LDS];
+    __shared__ __align__(16) __nv_bfloat16 sK[64 * LDS];
+    __shared__ __align__(16) __nv_bfloat16 sV[64 * LDS];
+    const SeqDesc sd = seqs[blockIdx.z];
+    const int q0 = blockIdx.x * 64;
+    if (q0 >= sd.q_len) return;
+    const int head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    constexpr int CH = HD / 8;  // 16-byte chunks per row
+    // ---- Q tile
+    for (int i = threadIdx.x; i < 64 * CH; i += 128) {
+        const int r = i / CH, c = i - r * CH;
+        const bool ok = (q0 + r) < sd.q_len;
+        const __nv_bfloat16* src = Q + (long long)(sd.q_off + (ok ? q0 + r : 0)) * ldq + head * HD + c * 8;
+        cp_async16(smem_u32(&sQ[r * LDS + c * 8]), src, ok);
+    }
+    cp_async_commit();
+    float o[HD / 8][4];
+#pragma unroll
+    for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    uint32_t qf[HD / 16][4];
+    bool q_loaded = false;
+    for (int k0 = 0; k0 < sd.k_len; k0 += 64) {
+        __syncthreads();  // previous tile fully consumed
+        for (int i = threadIdx.x; i < 64 * CH; i += 128) {
+            const int r = i / CH, c = i - r * CH;
+            const bool ok = (k0 + r) < sd.k_len;
+            const long long rowi = (long long)(sd.k_off + (ok ? k0 + r : 0)) * ldkv + head * HD + c * 8;
+            cp_async16(smem_u32(&sK[r * LDS + c * 8]), K + rowi, ok);
+            cp_async16(smem_u32(&sV[r * LDS + c * 8]), V + rowi, ok);
+        }
+        cp_async_commit();
+        cp_async_wait_all();
+        __syncthreads();
+        if (!q_loaded) {
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) {
+                const int r = warp * 16 + (lane & 15);
+                const int c = kk * 16 + (lane >> 4) * 8;
+                ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], smem_u32(&sQ[r * LDS + c]));
+            }
+            q_loaded = true;
+        }
+        // ---- S = Q K^T for 16 queries x 64 keys
+        float s[8][4];
+#pragma unroll
+        for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+            for (int np = 0; np < 4; ++np) {  // pairs of 8-key groups
+                uint32_t b0, b1, b2, b3;
+                const int r = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+                const int c = kk * 16 + ((lane >> 3) & 1) * 8;
+                ldmatrix_x4(b0, b1, b2, b3, smem_u32(&sK[r * LDS + c]));
+                mma_bf16_16816(s[2 * np], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b0, b1);
+                mma_bf16_16816(s[2 * np + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b2, b3);
+            }
+        }
+        // ---- online softmax (rows lane/4 and lane/4 + 8 of this warp's 16 queries)
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int key = k0 + n * 8 + (lane & 3) * 2 + (e & 1);
+                const float val = (key < sd.k_len) ? s[n][e] * scale_log2 : -INFINITY;
+                s[n][e] = val;
+                mx[e >> 1] = fmaxf(mx[e >> 1], val);
+            }
+        }
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+        }
+        float corr[2], m_new[2];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            m_new[h] = fmaxf(m_run[h], mx[h]);
+            corr[h] = exp2f(m_run[h] - m_new[h]);  // m_run = -inf on the first tile -> 0
+            m_run[h] = m_new[h];
+            l_run[h] *= corr[h];
+        }
+#pragma unroll
+        for (int i = 0; i < HD / 8; ++i) {
+            o[i][0] *= corr[0];
+            o[i][1] *= corr[0];
+            o[i][2] *= corr[1];
+            o[i][3] *= corr[1];
+        }
+        uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
+        float ls[2] = {0.f, 0.f};
+#pragma unroll
+        for (int n = 0; n < 8; ++n) {
+            const float p0 = exp2f(s[n][0] - m_new[0]), p1 = exp2f(s[n][1] - m_new[0]);
+            const float p2 = exp2f(s[n][2] - m_new[1]), p3 = exp2f(s[n][3] - m_new[1]);
+            ls[0] += p0 + p1;
+            ls[1] += p2 + p3;
+            const int ks = n >> 1;
+            if ((n & 1) == 0) {
+                pf[ks][0] = pack_bf16(p0, p1);
+                pf[ks][1] = pack_bf16(p2, p3);
+            } else {
+                pf[ks][2] = pack_bf16(p0, p1);
+                pf[ks][3] = pack_bf16(p2, p3);
+            }
+        }
+        l_run[0] += ls[0];
+        l_run[1] += ls[1];
+        // ---- O += P V
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+#pragma unroll
+            for (int dp = 0; dp < HD / 16; ++dp) {  // pairs of 8-wide output column groups
+                uint32_t b0, b1, b2, b3;
+                const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = dp * 16 + (lane >> 4) * 8;
+                ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(&sV[r * LDS + c]));
+                mma_bf16_16816(o[2 * dp], pf[ks][0], pf[ks][1], pf[ks][2], pf[ks][3], b0, b1);
+                mma_bf16_16816(o[2 * dp + 1], pf[ks][0], pf[ks][1], pf[ks][2], pf[ks][3], b2, b3);
+            }
+        }
+    }
+    // ---- finalize
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 1);
+        l_run[h] += __shfl_xor_sync(0xffffffffu, l_run[h], 2);
+    }
+    const int r0 = q0 + warp * 16 + (lane >> 2);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        const int r = r0 + h * 8;
+        if (r < sd.q_len) {
+            const float inv = 1.f / l_run[h];
+            __nv_bfloat16* op = O + (long long)(sd.q_off + r) * ldo + head * HD + (lane & 3) * 2;
+#pragma unroll
+            for (int i = 0; i < HD / 8; ++i) {
+                *reinterpret_cast<uint32_t*>(op + i * 8) = pack_bf16(o[i][2 * h] * inv, o[i][2 * h + 1] * inv);
+            }
+        }
+    }
+}
+
+int launch_flash_attention(const void* Q, long long ldq, const void* K, const void* V, long long ldkv, void* O,
+                           long long ldo, const SeqDesc* seqs, int nseq, int max_q_len, int heads, int head_dim,
+                           cudaStream_t st) {
+    if (nseq <= 0) return 0;
+    dim3 grid((max_q_len + 63) / 64, heads, nseq);
+    const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
+    const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(Q), *k = reinterpret_cast<const __nv_bfloat16*>(K),
+                        *v = reinterpret_cast<const __nv_bfloat16*>(V);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(O);
+    switch (head_dim) {
+        case 32: flash_attn_kernel<32><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); break;
+        case 48: flash_attn_kernel<48><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); break;
+        case 64: flash_attn_kernel<64><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); break;
+        case 96: flash_attn_kernel<96><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); break;
+        default: set_error("flash attention: head_dim %d unsupported (32/48/64/96)", head_dim); return 1;
+    }
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// =================================================================================================== decoder self-attn
+// Query stream vs. content K/V cache (reference DecoderLayer.forward_stream self_attn, parseq_transformer.py:83-90).
+// One CTA per (row, head); K/V of that row+head staged in shared memory as fp32.
+constexpr int kMaxS = 101;
+constexpr int kMaxHd = 96;
+
+__global__ void __launch_bounds__(128) dec_self_attn_kernel(const __nv_bfloat16* __restrict__ q_shared,
+                                                            const __nv_bfloat16* __restrict__ ckv, int B, int D,
+                                                            int hd, int mode, const int* __restrict__ step_dev,
+                                                            const int* __restrict__ klen,
+                                                            const int* __restrict__ kpad,
+                                                            __nv_bfloat16* __restrict__ out) {
+    extern __shared__ float dsm[];
+    const int ldk = hd + 1;
+    float* sK = dsm;                       // [kMaxS][hd+1]
+    float* sV = sK + kMaxS * ldk;          // [kMaxS][hd+1]
+    float* sP = sV + kMaxS * ldk;          // [4][kMaxS+3]
+    float* sQ = sP + 4 * (kMaxS + 3);      // [4][hd]
+    const int row = blockIdx.x, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int nk, q_begin, q_end, pad;
+    if (mode == 0) {
+        const int i = *step_dev;
+        nk = i + 1;
+        q_begin = i;
+        q_end = i + 1;
+        pad = nk;
+    } else {
+        nk = klen[row];
+        q_begin = 0;
+        q_end = kMaxS;
+        pad = kpad[row];
+    }
+    for (int idx = threadIdx.x; idx < nk * hd; idx += 128) {
+        const int j = idx / hd, d = idx - j * hd;
+        const __nv_bfloat16* p = ckv + ((long long)j * B + row) * (2 * D) + head * hd + d;
+        sK[j * ldk + d] = __bfloat162float(p[0]);
+        sV[j * ldk + d] = __bfloat162float(p[D]);
+    }
+    __syncthreads();
+    const float scale = rsqrtf((float)hd);
+    float* myP = sP + warp * (kMaxS + 3);
+    float* myQ = sQ + warp * hd;
+    for (int qi = q_begin + warp; qi < q_end; qi += 4) {
+        for (int d = lane; d < hd; d += 32) myQ[d] = __bfloat162float(q_shared[(long long)qi * D + head * hd + d]);
+        __syncwarp();
+        float mx = -INFINITY;
+        for (int j = lane; j < nk; j += 32) {
+            const bool vis = (mode == 0) ? true : (((qi < 2) || (j <= qi)) && (j < pad));
+            float s = -INFINITY;
+            if (vis) {
+                s = 0.f;
+                for (int d = 0; d < hd; ++d) s += myQ[d] * sK[j * ldk + d];
+                s *= scale;
+            }
+            myP[j] = s;
+            mx = fmaxf(mx, s);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int j = lane; j < nk; j += 32) {
+            const float p = (myP[j] == -INFINITY) ? 0.f : __expf(myP[j] - mx);
+            myP[j] = p;
+            sum += p;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        __syncwarp();
+        const float inv = 1.f / sum;
+        const long long orow = (mode == 0) ? row : ((long long)row * kMaxS + qi);
+        for (int d = lane; d < hd; d += 32) {
+            float acc = 0.f;
+            for (int j = 0; j < nk; ++j) acc += myP[j] * sV[j * ldk + d];
+            out[orow * D + head * hd + d] = __float2bfloat16(acc * inv);
+        }
+        __syncwarp();
+    }
+}
+
+int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, int heads, int mode, const int* step_dev,
+                         const int* klen, const int* kpad, void* out, cudaStream_t st) {
+    const int hd = D / heads;
+    if (hd > kMaxHd) {
+        set_error("decoder self-attention: head dim %d > %d", hd, kMaxHd);
+        return 1;
+    }
+    dim3 grid(B, heads);
+    const int smem = (2 * kMaxS * (hd + 1) + 4 * (kMaxS + 3) + 4 * hd) * (int)sizeof(float);
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(dec_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) !=
+            cudaSuccess) {
+            set_error("dec_self_attn: cannot raise dynamic shared memory");
+            return 1;
+        }
+        attr_set = true;
+    }
+    dec_self_attn_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(q_shared),
+                                               reinterpret_cast<const __nv_bfloat16*>(ckv), B, D, hd, mode, step_dev,
+                                               klen, kpad, reinterpret_cast<__nv_bfloat16*>(out));
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// =================================================================================================== AR cross-attn
+// One query per row against the row's encoder memory (reference cross_attn, parseq_transformer.py:92).  The memory
+// K/V were projected ONCE (the reference re-projects them every step).  CTA per (row, head).
+constexpr int kMaxMem = 800;
+
+__global__ void __launch_bounds__(128) dec_cross_attn_kernel(const __nv_bfloat16* __restrict__ qc,
+                                                             const __nv_bfloat16* __restrict__ memkv,
+                                                             const CropDesc* __restrict__ descs, int D, int hd,
+                                                             __nv_bfloat16* __restrict__ out) {
+    __shared__ float sQ[kMaxHd];
+    __shared__ float sP[kMaxMem];
+    __shared__ float sRed[4];
+    __shared__ float sAcc[4][kMaxHd];
+    const int row = blockIdx.x, head = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const CropDesc d = descs[row];
+    const int n = d.ntok;
+    for (int i = threadIdx.x; i < hd; i += 128) sQ[i] = __bfloat162float(qc[(long long)row * D + head * hd + i]);
+    __syncthreads();
+    const float scale = rsqrtf((float)hd);
+    const __nv_bfloat16* kbase = memkv + (long long)d.tok_off * (2 * D) + head * hd;
+    float mx = -INFINITY;
+    for (int j = threadIdx.x; j < n; j += 128) {
+        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)j * (2 * D));
+        float s = 0.f;
+        for (int c = 0; c < hd / 8; ++c) {
+            const uint4 u = __ldg(kp + c);
+            s += sQ[c * 8 + 0] * bf16_lo(u.x) + sQ[c * 8 + 1] * bf16_hi(u.x) + sQ[c * 8 + 2] * bf16_lo(u.y) +
+                 sQ[c * 8 + 3] * bf16_hi(u.y) + sQ[c * 8 + 4] * bf16_lo(u.z) + sQ[c * 8 + 5] * bf16_hi(u.z) +
+                 sQ[c * 8 + 6] * bf16_lo(u.w) + sQ[c * 8 + 7] * bf16_hi(u.w);
+        }
+        s *= scale;
+        sP[j] = s;
+        mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if (lane == 0) sRed[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
+    __syncthreads();
+    float sum = 0.f;
+    for (int j = threadIdx.x; j < n; j += 128) {
+        const float p = __expf(sP[j] - mx);
+        sP[j] = p;
+        sum += p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if (lane == 0) sRed[warp] = sum;
+    __syncthreads();
+    sum = sRed[0] + sRed[1] + sRed[2] + sRed[3];
+    // PV: each warp takes a quarter of the keys; lanes own output dims
+    float acc[3] = {0.f, 0.f, 0.f};  // hd <= 96 -> up to 3 dims per lane
+    for (int j = warp; j < n; j += 4) {
+        const float p = sP[j];
+        const __nv_bfloat16* vp = kbase + (long long)j * (2 * D) + D;
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int dd = lane + 32 * t;
+            if (dd < hd) acc[t] += p * __bfloat162float(vp[dd]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int dd = lane + 32 * t;
+        if (dd < hd) sAcc[warp][dd] = acc[t];
+    }
+    __syncthreads();
+    for (int dd = threadIdx.x; dd < hd; dd += 128) {
+        const float v = (sAcc[0][dd] + sAcc[1][dd] + sAcc[2][dd] + sAcc[3][dd]) / sum;
+        out[(long long)row * D + head * hd + dd] = __float2bfloat16(v);
+    }
+}
+
+int launch_dec_cross_attn(const void* qc, const void* memkv, const CropDesc* descs, int B, int D, int heads, void* out,
+                          cudaStream_t st) {
+    const int hd = D / heads;
+    if (hd > kMaxHd || (hd % 8) != 0) {
+        set_error("decoder cross-attention: head dim %d unsupported", hd);
+        return 1;
+    }
+    dim3 grid(B, heads);
+    dec_cross_attn_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(qc),
+                                                reinterpret_cast<const __nv_bfloat16*>(memkv), descs, D, hd,
+                                                reinterpret_cast<__nv_bfloat16*>(out));
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// =================================================================================================== AR control
+// Per row: arg-max of the step's logits, the reference's bookkeeping (parseq.py:220-250) and the embedding of the
+// token that enters the context at position j = i + 1.  A second tiny kernel closes groups whose rows all hold an EOS.
+__device__ __forceinline__ void warp_argmax(float& v, int& idx) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, v, o);
+        const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+        if (ov > v || (ov == v && oi < idx)) {
+            v = ov;
+            idx = oi;
+        }
+    }
+}
+
+__device__ int detect_repeat(const int* seq, int n, int period_max, int min_run_p1, int min_repeats, int* period) {
+    // seq[0..n): emitted tokens; returns onset index or -1 (reference _detect_repeat_onset, parseq.py:108-128)
+    for (int p = 1; p <= period_max; ++p) {
+        if (n < 2 * p) continue;
+        int reps = 1, start = n - p;
+        while (start - p >= 0) {
+            bool same = true;
+            for (int t = 0; t < p; ++t)
+                if (seq[start - p + t] != seq[n - p + t]) {
+                    same = false;
+                    break;
+                }
+            if (!same) break;
+            ++reps;
+            start -= p;
+        }
+        if (reps >= (p == 1 ? min_run_p1 : min_repeats)) {
+            *period = p;
+            return start;
+        }
+    }
+    return -1;
+}
+
+__global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict__ logits, long long ldl, int C, int S,
+                                                         const int* __restrict__ row_group, ArState a, int eos_id,
+                                                         int rep_on, int rep_period_max, int rep_min_run_p1,
+                                                         int rep_min_repeats, const float* __restrict__ embed,
+                                                         const float* __restrict__ pos_q, int D,
+                                                         const float* __restrict__ g_c, const float* __restrict__ b_c,
+                                                         __nv_bfloat16* __restrict__ cin) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    __shared__ int s_tok;
+    __shared__ float s_stat[2];
+    const int row = blockIdx.x;
+    const int i = *a.step;
+    const int j = i + 1;
+    const int grp = row_group[row];
+    if (a.group_len[grp] != 0) return;  // group already finished: nothing more happens to its rows
+    const float* lr = logits + (long long)row * ldl;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = lr[c];
+        if (v > best) {  // strict: keeps the smallest index within a thread (ascending scan)
+            best = v;
+            bi = c;
+        }
+    }
+    warp_argmax(best, bi);
+    if ((threadIdx.x & 31) == 0) {
+        sv[threadIdx.x >> 5] = best;
+        si[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = sv[0];
+        int id = si[0];
+        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+            if (sv[w] > v || (sv[w] == v && si[w] < id)) {
+                v = sv[w];
+                id = si[w];
+            }
+        a.raw[row * S + i] = id;
+        int tok = id;
+        if (j < S) {
+            a.tgt[row * S + j] = id;
+            if (rep_on && !a.rep_done[row] && id != eos_id) {
+                int period = 0;
+                const int onset = detect_repeat(a.tgt + row * S + 1, j, rep_period_max, rep_min_run_p1, rep_min_repeats,
+                                                &period);
+                if (onset >= 0) {
+                    a.rep_cut[row] = onset + period;
+                    a.rep_done[row] = 1;
+                    a.tgt[row * S + j] = eos_id;
+                    tok = eos_id;
+                }
+            }
+            if (tok == eos_id) a.has_eos[row] = 1;
+        }
+        s_tok = tok;
+    }
+    __syncthreads();
+    if (j >= S) return;
+    // content embedding of position j: pos_queries[j-1] + sqrt(D) * E[tok], then LN_c (eps 1e-5)
+    const int tok = s_tok;
+    const float sq = sqrtf((float)D);
+    float loc[4];  // D <= 1024 with 256 threads
+    float s = 0.f;
+    for (int t = 0; t < 4; ++t) {
+        const int d = threadIdx.x + t * 256;
+        float v = 0.f;
+        if (d < D) v = pos_q[(long long)(j - 1) * D + d] + sq * embed[(long long)tok * D + d];
+        loc[t] = v;
+        s += v;
+    }
+    // block reduce (sum)
+    __shared__ float red[8];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        s_stat[0] = t / (float)D;
+    }
+    __syncthreads();
+    const float mean = s_stat[0];
+    float q = 0.f;
+    for (int t = 0; t < 4; ++t) {
+        const int d = threadIdx.x + t * 256;
+        if (d < D) q += (loc[t] - mean) * (loc[t] - mean);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        s_stat[1] = rsqrtf(t / (float)D + 1e-5f);
+    }
+    __syncthreads();
+    const float rstd = s_stat[1];
+    for (int t = 0; t < 4; ++t) {
+        const int d = threadIdx.x + t * 256;
+        if (d < D) cin[(long long)row * D + d] = __float2bfloat16((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
+    }
+}
+
+__global__ void ar_groups_kernel(const int* __restrict__ row_group, int B, int ngroups, ArState a, int S) {
+    // single block: a group finishes after step i when every one of its rows holds an EOS (parseq.py:245-250)
+    extern __shared__ int open_rows[];  // per group: rows without EOS
+    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) open_rows[g] = 0;
+    __syncthreads();
+    for (int r = threadIdx.x; r < B; r += blockDim.x)
+        if (!a.has_eos[r]) atomicAdd(&open_rows[row_group[r]], 1);
+    __syncthreads();
+    const int i = *a.step;
+    const int j = i + 1;
+    __shared__ int active;
+    if (threadIdx.x == 0) active = 0;
+    __syncthreads();
+    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) {
+        if (a.group_len[g] == 0) {
+            if (j >= S) a.group_len[g] = S;             // ran all the steps
+            else if (open_rows[g] == 0) a.group_len[g] = j;  // logits has j entries, tgt_in for refinement length j
+            else atomicAdd(&active, 1);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        *a.n_active = active;
+        *a.step = i + 1;
+    }
+}
+
+int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int ngroups,
+                      ArState a, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
+                      const float* embed, const float* pos_q, int D, const float* g_c, const float* b_c, void* cin,
+                      cudaStream_t st) {
+    if (D > 1024) {
+        set_error("ar_control: D=%d too large", D);
+        return 1;
+    }
+    ar_control_kernel<<<B, 256, 0, st>>>(logits, ldl, C, S, row_group, a, eos_id, rep_on, rep_period_max,
+                                         rep_min_run_p1, rep_min_repeats, embed, pos_q, D, g_c, b_c,
+                                         reinterpret_cast<__nv_bfloat16*>(cin));
+    ar_groups_kernel<<<1, 256, sizeof(int) * ngroups, st>>>(row_group, B, ngroups, a, S);
+    count_launch(2);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// =================================================================================================== refinement embed
+__global__ void __launch_bounds__(256) refine_embed_kernel(const int* __restrict__ raw,
+                                                           const int* __restrict__ row_group,
+                                                           const int* __restrict__ group_len, int S, int bos_id,
+                                                           int eos_id, const float* __restrict__ embed,
+                                                           const float* __restrict__ pos_q, int D,
+                                                           const float* __restrict__ g_c, const float* __restrict__ b_c,
+                                                           __nv_bfloat16* __restrict__ cin, int* __restrict__ klen,
+                                                           int* __restrict__ kpad) {
+    // grid (S, B): content position `pos` of row `row`; tgt_in = [BOS, raw[0..L-2]] (parseq.py:286)
+    const int pos = blockIdx.x, row = blockIdx.y;
+    const int L = group_len[row_group[row]];
+    if (pos == 0 && threadIdx.x == 0) {
+        klen[row] = L;
+        int first = L;  // first EOS in tgt_in -> keys at/after it are padding (parseq.py:288-290)
+        for (int p = 1; p < L; ++p)
+            if (raw[row * S + p - 1] == eos_id) {
+                first = p;
+                break;
+            }
+        kpad[row] = first;
+    }
+    __shared__ float red[8];
+    __shared__ float s_stat[2];
+    const float sq = sqrtf((float)D);
+    const int tok = (pos == 0) ? bos_id : ((pos < L) ? raw[row * S + pos - 1] : eos_id);
+    float loc[4];
+    float s = 0.f;
+    for (int t = 0; t < 4; ++t) {
+        const int d = threadIdx.x + t * 256;
+        float v = 0.f;
+        if (d < D) v = sq * embed[(long long)tok * D + d] + (pos > 0 ? pos_q[(long long)(pos - 1) * D + d] : 0.f);
+        loc[t] = v;
+        s += v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        s_stat[0] = t / (float)D;
+    }
+    __syncthreads();
+    const float mean = s_stat[0];
+    float q = 0.f;
+    for (int t = 0; t < 4; ++t) {
+        const int d = threadIdx.x + t * 256;
+        if (d < D) q += (loc[t] - mean) * (loc[t] - mean);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += red[w];
+        s_stat[1] = rsqrtf(t / (float)D + 1e-5f);
+    }
+    __syncthreads();
+    const float rstd = s_stat[1];
+    // layout [pos][row][D] so the K/V GEMM output lands in the cache layout [pos][row][2D]
+    const long long orow = (long long)pos * gridDim.y + row;
+    for (int t = 0; t < 4; ++t) {
+        const int d = threadIdx.x + t * 256;
+        if (d < D) cin[orow * D + d] = __float2bfloat16((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
+    }
+}
+
+int launch_refine_embed(const int* raw, const int* row_group, const int* group_len, int B, int S, int bos_id, int eos_id,
+                        const float* embed, const float* pos_q, int D, const float* g_c, const float* b_c, void* cin,
+                        int* klen, int* kpad, cudaStream_t st) {
+    dim3 grid(S, B);
+    refine_embed_kernel<<<grid, 256, 0, st>>>(raw, row_group, group_len, S, bos_id, eos_id, embed, pos_q, D, g_c, b_c,
+                                              reinterpret_cast<__nv_bfloat16*>(cin), klen, kpad);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// =================================================================================================== softmax max
+// Replaces `.softmax(-1)` + per-position max of the reference (text_recognizer.py:255, parseq_tokenizer.py:79-87):
+// only (argmax id, max probability) leave the device.  One CTA per logits row.
+__global__ void __launch_bounds__(256) softmax_max_kernel(const float* __restrict__ logits, long long ldl, int C, int S,
+                                                          long long g_stride, long long g_off,
+                                                          const int* __restrict__ rep_cut, int eos_id,
+                                                          int* __restrict__ ids, float* __restrict__ probs) {
+    const int r = blockIdx.x;  // local row in this logits buffer
+    const long long g = (long long)r * g_stride + g_off;  // global (crop*S + position)
+    const int crop = (int)(g / S), pos = (int)(g % S);
+    if (rep_cut != nullptr && rep_cut[crop] == pos) {  // parseq.py:301-309: logits = -30 everywhere, +30 at EOS
+        if (threadIdx.x == 0) {
+            ids[g] = eos_id;
+            probs[g] = 1.f / (1.f + (float)(C - 1) * expf(-60.f));
+        }
+        return;
+    }
+    const float* lr = logits + (long long)r * ldl;
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        const float v = lr[c];
+        if (v > best) {
+            best = v;
+            bi = c;
+        }
+    }
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    __shared__ float s_max;
+    warp_argmax(best, bi);
+    if ((threadIdx.x & 31) == 0) {
+        sv[threadIdx.x >> 5] = best;
+        si[threadIdx.x >> 5] = bi;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float v = sv[0];
+        int id = si[0];
+        for (int w = 1; w < 8; ++w)
+            if (sv[w] > v || (sv[w] == v && si[w] < id)) {
+                v = sv[w];
+                id = si[w];
+            }
+        s_max = v;
+        ids[g] = id;
+    }
+    __syncthreads();
+    const float mx = s_max;
+    float sum = 0.f;
+    for (int c = threadIdx.x; c < C; c += blockDim.x) sum += expf(lr[c] - mx);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int w = 0; w < 8; ++w) t += sv[w];
+        probs[g] = 1.f / t;
+    }
+}
+
+int launch_softmax_max(const float* logits, long long ldl, int C, int rows, int S, long long g_stride, long long g_off,
+                       const int* rep_cut, int eos_id, int* ids, float* probs, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    softmax_max_kernel<<<rows, 256, 0, st>>>(logits, ldl, C, S, g_stride, g_off, rep_cut, eos_id, ids, probs);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// Broadcast one row to many (content K/V of the BOS position is identical for every crop).
+__global__ void bcast_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int vec_per_row,
+                                  long long total) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < total) dst[i] = src[i % vec_per_row];
+}
+int launch_bcast_rows(const void* src, void* dst, int row_bytes, int rows, cudaStream_t st) {
+    const int vpr = row_bytes / 16;
+    const long long total = (long long)vpr * rows;
+    if (total <= 0) return 0;
+    bcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
+                                                                       reinterpret_cast<uint4*>(dst), vpr, total);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// refine_iters == 0: the AR logits are the output; apply the repetition patch after the loop (parseq.py:301-309).
+__global__ void apply_rep_cut_kernel(const int* __restrict__ rep_cut, int B, int S, int C, int eos_id,
+                                     int* __restrict__ ids, float* __restrict__ probs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    const int cut = rep_cut[r];
+    if (cut >= 0 && cut < S) {
+        ids[r * S + cut] = eos_id;
+        probs[r * S + cut] = 1.f / (1.f + (float)(C - 1) * expf(-60.f));
+    }
+}
+int launch_apply_rep_cut(const int* rep_cut, int B, int S, int C, int eos_id, int* ids, float* probs,
+                         cudaStream_t st) {
+    apply_rep_cut_kernel<<<(B + 127) / 128, 128, 0, st>>>(rep_cut, B, S, C, eos_id, ids, probs);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+__global__ void fill_i32_kernel(int* p, int v, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+int launch_fill_i32(int* p, int v, long long n, cudaStream_t st) {
+    if (n <= 0) return 0;
+    fill_i32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, v, n);
+    return cudaGetLastError() != cudaSuccess;
+}
+
+}  // namespace ytk

@@ -1,0 +1,382 @@
+"""Device-backed DBNet and PARSeq model objects: the `self.model` of TextDetector / TextRecognizer.
+
+They keep the surface the reference's modules touch from outside (SURVEY.md section 8b "model-level seam"):
+`model(tensor)`, `.eval()`, `.to(device)`, `.state_dict()/.load_state_dict()` (reference key set, Appendix C),
+`.from_pretrained(repo, cfg=cfg)`, `PARSeq.tokenizer`, `PARSeq.refine_iters`, `PARSeq.export_onnx` - but the forward
+pass is the hand-written sm_100a engine behind the C ABI (include/yomitoku_b200.h).  There is no CPU fallback: a
+forward without the CUDA library and a GPU raises.
+
+Reference: src/yomitoku/models/dbnet_plus.py:233-246, src/yomitoku/models/parseq.py:49-311.
+"""
+import ctypes
+import math
+import os
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _he_conv(g, cout, cin, kh, kw, gain=1.0):
+    return torch.randn(cout, cin, kh, kw, generator=g) * (gain * math.sqrt(2.0 / (cin * kh * kw)))
+
+
+class _DeviceModel:
+    """Minimal nn.Module-like shell around a C handle."""
+
+    def __init__(self):
+        self._sd = None
+        self._handle = None
+        self._device = torch.device("cpu")
+        self.training = False
+
+    def eval(self):
+        self.training = False
+        return self
+
+    def to(self, device):
+        self._device = torch.device(device) if not isinstance(device, torch.device) else device
+        return self
+
+    def state_dict(self):
+        return OrderedDict(self._sd)
+
+    def load_state_dict(self, sd, strict=True):
+        missing = [k for k in self._sd if k not in sd]
+        unexpected = [k for k in sd if k not in self._sd]
+        if strict and (missing or unexpected):
+            raise RuntimeError("Error(s) in loading state_dict: missing %s unexpected %s" % (missing[:5], unexpected[:5]))
+        for k in self._sd:
+            if k in sd:
+                if tuple(sd[k].shape) != tuple(self._sd[k].shape):
+                    raise RuntimeError("size mismatch for %s" % k)
+                self._sd[k] = sd[k].detach().clone()
+        self._release()
+        return self
+
+    def parameters(self):
+        return (v for v in self._sd.values() if torch.is_floating_point(v))
+
+    def _release(self):
+        raise NotImplementedError
+
+    def _require_cuda(self):
+        if not torch.cuda.is_available():
+            raise _lib.YtkError(
+                "%s runs only on a CUDA device (sm_100a): no GPU is visible and there is no CPU fallback on the "
+                "hot path" % type(self).__name__)
+
+    @classmethod
+    def from_pretrained(cls, repo, cfg=None, **kw):
+        """Loads the reference's HF `model.safetensors` (strict state_dict keys).  Offline (no hub cache) this raises
+        like huggingface_hub does."""
+        from huggingface_hub import hf_hub_download
+        from safetensors.torch import load_file
+        path = hf_hub_download(repo, "model.safetensors")
+        m = cls(cfg=cfg)
+        m.load_state_dict(load_file(path), strict=True)
+        return m
+
+
+# ======================================================================================================== DBNet
+def _dbnet_random_state_dict(seed=0):
+    """Random init with the reference's key set (DBNet(cfg) with from_pretrained=False, base.py:84-86)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+
+    def bn(p, c):
+        sd[p + ".weight"] = torch.ones(c)
+        sd[p + ".bias"] = torch.full((c,), 1e-4)
+        sd[p + ".running_mean"] = torch.zeros(c)
+        sd[p + ".running_var"] = torch.ones(c)
+        sd[p + ".num_batches_tracked"] = torch.tensor(0, dtype=torch.long)
+
+    b = "backbone.body."
+    sd[b + "conv1.weight"] = _he_conv(g, 64, 3, 7, 7)
+    bn(b + "bn1", 64)
+    inpl = 64
+    for li, (pl, nb) in enumerate(((64, 3), (128, 4), (256, 6), (512, 3)), start=1):
+        for i in range(nb):
+            q = "%slayer%d.%d." % (b, li, i)
+            sd[q + "conv1.weight"] = _he_conv(g, pl, inpl, 1, 1)
+            bn(q + "bn1", pl)
+            sd[q + "conv2.weight"] = _he_conv(g, pl, pl, 3, 3)
+            bn(q + "bn2", pl)
+            sd[q + "conv3.weight"] = _he_conv(g, pl * 4, pl, 1, 1, 0.5)
+            bn(q + "bn3", pl * 4)
+            if i == 0:
+                sd[q + "downsample.0.weight"] = _he_conv(g, pl * 4, inpl, 1, 1, 0.7)
+                bn(q + "downsample.1", pl * 4)
+            inpl = pl * 4
+    d = "decoder."
+    for i, c in enumerate((256, 512, 1024, 2048), start=1):
+        sd["%sinput_proj.layer%d.weight" % (d, i)] = _he_conv(g, 256, c, 1, 1, 0.7)
+    sd[d + "out_proj.layer1.weight"] = _he_conv(g, 64, 256, 3, 3)
+    for i in (2, 3, 4):
+        sd["%sout_proj.layer%d.0.weight" % (d, i)] = _he_conv(g, 64, 256, 3, 3)
+    for name, cin in (("binarize", 256), ("thresh", 257)):
+        q = d + name + "."
+        sd[q + "0.weight"] = _he_conv(g, 64, cin, 3, 3)
+        bn(q + "1", 64)
+        sd[q + "3.weight"] = torch.randn(64, 64, 2, 2, generator=g) * math.sqrt(2.0 / 64)
+        sd[q + "3.bias"] = torch.zeros(64)
+        bn(q + "4", 64)
+        sd[q + "6.weight"] = torch.randn(64, 1, 2, 2, generator=g) * math.sqrt(2.0 / 64)
+        sd[q + "6.bias"] = torch.zeros(1)
+    a = d + "concat_attention."
+    sd[a + "conv.weight"] = _he_conv(g, 64, 256, 3, 3)
+    sd[a + "conv.bias"] = torch.zeros(64)
+    e = a + "enhanced_attention."
+    sd[e + "channel_wise.1.weight"] = _he_conv(g, 16, 64, 1, 1)
+    sd[e + "channel_wise.3.weight"] = _he_conv(g, 64, 16, 1, 1)
+    sd[e + "spatial_wise.0.weight"] = torch.randn(1, 1, 3, 3, generator=g) * 0.5
+    sd[e + "spatial_wise.2.weight"] = torch.randn(1, 1, 1, 1, generator=g)
+    sd[e + "attention_wise.0.weight"] = _he_conv(g, 4, 64, 1, 1)
+    return sd
+
+
+class DBNet(_DeviceModel):
+    """reference models/dbnet_plus.py:233-246.  `model(tensor)` takes the normalised (1,3,H,W) fp32 tensor of
+    TextDetector.preprocess and returns OrderedDict(binary=(1,1,H,W) fp32 probabilities)."""
+
+    def __init__(self, cfg=None, seed=0):
+        super().__init__()
+        self.cfg = cfg
+        self._sd = _dbnet_random_state_dict(seed)
+        self._shortest = int(cfg.data.shortest_size) if cfg is not None else 1280
+        self._limit = int(cfg.data.limit_size) if cfg is not None else 1600
+
+    # -- handle management
+    def _ensure(self):
+        self._require_cuda()
+        if self._handle is None:
+            L = _lib.lib()
+            tab, keep = _lib.tensor_table(self._sd)
+            h = ctypes.c_void_p()
+            _lib.check(L.ytk_dbnet_create(tab, len(tab), self._shortest, self._limit, ctypes.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.lib().ytk_dbnet_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def input_size(self, h, w):
+        """(Hn, Wn) the network sees for an h x w page = reference resize_shortest_edge (functions.py:212-224)."""
+        from .data import shortest_edge_size
+        return shortest_edge_size(h, w, self._shortest, self._limit)
+
+    def __call__(self, tensor):
+        return self.forward(tensor)
+
+    def forward(self, tensor):
+        """Model-level seam: (N,3,H,W) fp32 (host or cuda) -> {"binary": (N,1,H,W) fp32 on the same device}."""
+        h = self._ensure()
+        if tensor.dim() != 4 or tensor.shape[1] != 3:
+            raise ValueError("DBNet expects (N,3,H,W), got %s" % (tuple(tensor.shape),))
+        n, _, H, W = tensor.shape
+        x = tensor.detach().to(torch.float32).contiguous()
+        on_dev = x.is_cuda
+        out = torch.empty((n, 1, H, W), dtype=torch.float32, device=x.device)
+        _lib.check(_lib.lib().ytk_dbnet_forward_f32(h, x.data_ptr(), 1 if on_dev else 0, n, H, W, out.data_ptr(),
+                                                    1 if on_dev else 0, None))
+        return OrderedDict(binary=out)
+
+    def detect_pages_u8(self, pages, out=None):
+        """Fused fast path: pages (n,H0,W0,3) uint8 BGR (numpy / torch, host or cuda) -> (n,Hn,Wn) fp32 probability
+        maps (pre-processing runs on the GPU).  Pages that would be up-scaled need the model-level seam."""
+        h = self._ensure()
+        t = pages if isinstance(pages, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(pages))
+        if t.dim() == 3:
+            t = t[None]
+        t = t.contiguous()
+        n, H0, W0, _ = t.shape
+        Hn, Wn = self.input_size(H0, W0)
+        if out is None:
+            out = torch.empty((n, Hn, Wn), dtype=torch.float32, device=t.device,
+                              pin_memory=(not t.is_cuda) and torch.cuda.is_available())
+        _lib.check(_lib.lib().ytk_dbnet_forward_u8(h, t.data_ptr(), 1 if t.is_cuda else 0, n, H0, W0, out.data_ptr(),
+                                                   1 if out.is_cuda else 0, None))
+        return out
+
+    def flops(self, n, Hn, Wn):
+        return _lib.lib().ytk_dbnet_flops(self._ensure(), n, Hn, Wn)
+
+
+# ======================================================================================================== PARSeq
+def _parseq_random_state_dict(cfg, seed=0):
+    """Random init with the reference's key set and init scheme (parseq.py:28-46,81-82: trunc-normal(0.02) linears /
+    embeddings, ones/zeros norms; encoder = timm ViT defaults)."""
+    g = torch.Generator().manual_seed(seed)
+    D = cfg.encoder.embed_dim
+    ph, pw = cfg.encoder.patch_size
+    gh, gw = cfg.data.img_size[0] // ph, cfg.data.img_size[1] // pw
+    depth, r = cfg.encoder.depth, cfg.encoder.mlp_ratio
+    S = cfg.max_label_length + 1
+
+    def tn(*shape):
+        return torch.randn(*shape, generator=g).clamp_(-2, 2) * 0.02
+
+    sd = OrderedDict()
+    e = "encoder."
+    sd[e + "pos_embed"] = tn(1, gh * gw, D)
+    sd[e + "patch_embed.proj.weight"] = torch.randn(D, 3, ph, pw, generator=g) * math.sqrt(1.0 / (3 * ph * pw))
+    sd[e + "patch_embed.proj.bias"] = torch.zeros(D)
+    for i in range(depth):
+        p = "%sblocks.%d." % (e, i)
+        sd[p + "norm1.weight"], sd[p + "norm1.bias"] = torch.ones(D), torch.zeros(D)
+        sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"] = tn(3 * D, D), torch.zeros(3 * D)
+        sd[p + "attn.proj.weight"], sd[p + "attn.proj.bias"] = tn(D, D), torch.zeros(D)
+        sd[p + "norm2.weight"], sd[p + "norm2.bias"] = torch.ones(D), torch.zeros(D)
+        sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"] = tn(r * D, D), torch.zeros(r * D)
+        sd[p + "mlp.fc2.weight"], sd[p + "mlp.fc2.bias"] = tn(D, r * D), torch.zeros(D)
+    sd[e + "norm.weight"], sd[e + "norm.bias"] = torch.ones(D), torch.zeros(D)
+    p = "decoder.layers.0."
+    for att in ("self_attn", "cross_attn"):
+        sd[p + att + ".in_proj_weight"] = torch.randn(3 * D, D, generator=g) * math.sqrt(2.0 / (4 * D))
+        sd[p + att + ".in_proj_bias"] = torch.zeros(3 * D)
+        sd[p + att + ".out_proj.weight"], sd[p + att + ".out_proj.bias"] = tn(D, D), torch.zeros(D)
+    H = cfg.decoder.mlp_ratio * D
+    sd[p + "linear1.weight"], sd[p + "linear1.bias"] = tn(H, D), torch.zeros(H)
+    sd[p + "linear2.weight"], sd[p + "linear2.bias"] = tn(D, H), torch.zeros(D)
+    for n in ("norm1", "norm2", "norm_q", "norm_c"):
+        sd[p + n + ".weight"], sd[p + n + ".bias"] = torch.ones(D), torch.zeros(D)
+    sd["decoder.norm.weight"], sd["decoder.norm.bias"] = torch.ones(D), torch.zeros(D)
+    sd["head.weight"], sd["head.bias"] = tn(cfg.num_tokens - 2, D), torch.zeros(cfg.num_tokens - 2)
+    sd["text_embed.embedding.weight"] = tn(cfg.num_tokens, D)
+    sd["pos_queries"] = tn(1, S, D)
+    return sd
+
+
+class PARSeq(_DeviceModel):
+    """reference models/parseq.py:49-311.  `model(images)` takes (B,3,32,W) fp32 in [-1,1] and returns logits
+    (B, S, C); `recognize_crops` is the fused ragged path that returns only (ids, probs)."""
+
+    def __init__(self, cfg=None, seed=0):
+        super().__init__()
+        self.cfg = cfg
+        self.max_label_length = cfg.max_label_length
+        self.decode_ar = cfg.decode_ar
+        self._refine_iters = int(cfg.refine_iters)
+        self.export_onnx = False
+        self.tokenizer = None
+        self.repetition_stop = bool(getattr(cfg, "repetition_stop", True))
+        self.rep_period_max = int(getattr(cfg, "rep_period_max", 8))
+        self.rep_min_run_p1 = int(getattr(cfg, "rep_min_run_p1", 8))
+        self.rep_min_repeats = int(getattr(cfg, "rep_min_repeats", 3))
+        self._sd = _parseq_random_state_dict(cfg, seed)
+        if not self.decode_ar:
+            raise NotImplementedError("decode_ar=0 (non-autoregressive decoding) is not on the device path")
+
+    @property
+    def refine_iters(self):
+        return self._refine_iters
+
+    @refine_iters.setter
+    def refine_iters(self, v):
+        self._refine_iters = int(v)
+        if self._handle is not None:
+            _lib.lib().ytk_parseq_set_refine_iters(self._handle, self._refine_iters)
+
+    @property
+    def num_classes(self):
+        return self.cfg.num_tokens - 2
+
+    def _ensure(self):
+        self._require_cuda()
+        if self._handle is None:
+            c = self.cfg
+            L = _lib.lib()
+            tab, keep = _lib.tensor_table(self._sd)
+            cc = _lib.YtkParseqCfg(c.encoder.embed_dim, c.encoder.num_heads, c.encoder.depth, c.encoder.patch_size[0],
+                                   c.encoder.patch_size[1], c.data.img_size[0], c.data.img_size[1], c.num_tokens,
+                                   c.max_label_length, c.decoder.num_heads, c.encoder.mlp_ratio, c.decoder.mlp_ratio,
+                                   self._refine_iters, 1 if self.repetition_stop else 0, self.rep_period_max,
+                                   self.rep_min_run_p1, self.rep_min_repeats)
+            h = ctypes.c_void_p()
+            _lib.check(L.ytk_parseq_create(tab, len(tab), ctypes.byref(cc), ctypes.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.lib().ytk_parseq_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def __call__(self, images, max_length=None):
+        return self.forward(images, max_length)
+
+    def forward(self, images, max_length=None):
+        """Model-level seam (one reference mini-batch): logits (B, S, C) fp32, S = 101 with refinement, else the
+        number of AR steps run; the repetition patch of parseq.py:301-309 is applied."""
+        if max_length is not None:
+            raise NotImplementedError("max_length is a training-time argument; inference uses None")
+        h = self._ensure()
+        x = images.detach().to(torch.float32).contiguous()
+        B, _, Hh, W = x.shape
+        if Hh != self.cfg.data.img_size[0]:
+            raise ValueError("PARSeq expects height %d" % self.cfg.data.img_size[0])
+        S, C = self.max_label_length + 1, self.num_classes
+        logits = torch.zeros((B, S, C), dtype=torch.float32, device=x.device)
+        ids = torch.empty((B, S), dtype=torch.int32)
+        probs = torch.empty((B, S), dtype=torch.float32)
+        rep = torch.empty((B,), dtype=torch.int32)
+        steps = ctypes.c_int(0)
+        _lib.check(_lib.lib().ytk_parseq_forward_f32(h, x.data_ptr(), 1 if x.is_cuda else 0, B, W, logits.data_ptr(),
+                                                     1 if x.is_cuda else 0, ids.data_ptr(), probs.data_ptr(),
+                                                     ctypes.byref(steps), rep.data_ptr(), None, None))
+        if self._refine_iters == 0:
+            logits = logits[:, : steps.value]
+        if self.repetition_stop:
+            for b, cut in enumerate(rep.tolist()):
+                if cut >= 0 and cut < logits.shape[1]:
+                    logits[b, cut, :] = -30.0
+                    logits[b, cut, 0] = 30.0
+        return logits
+
+    def recognize_crops(self, canvases, padded_widths, groups, n_groups):
+        """Fused ragged path.  canvases: list of (32, w_i, 3) uint8 RGB arrays (the reference's dataset.data[i]);
+        padded_widths[i]: width the reference collate would pad crop i to; groups[i]: its mini-batch index.
+        Returns ids (n,S) int32, probs (n,S) float32, group_len (n_groups,) int32 (numpy)."""
+        h = self._ensure()
+        n = len(canvases)
+        S = self.max_label_length + 1
+        ph, pw = self.cfg.encoder.patch_size
+        gh = self.cfg.data.img_size[0] // ph
+        sizes = [int(c.shape[0] * c.shape[1] * 3) for c in canvases]
+        total = int(sum(sizes))
+        buf = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
+        nb = buf.numpy()
+        descs = (_lib.YtkCrop * n)()
+        off = tok = 0
+        for i, c in enumerate(canvases):
+            nb[off:off + sizes[i]] = np.ascontiguousarray(c).reshape(-1)
+            wp = int(padded_widths[i])
+            ntok = gh * (wp // pw)
+            descs[i] = _lib.YtkCrop(off, int(c.shape[1]), wp, tok, ntok, int(groups[i]))
+            off += sizes[i]
+            tok += ntok
+        ids = np.empty((n, S), dtype=np.int32)
+        probs = np.empty((n, S), dtype=np.float32)
+        glen = np.empty((max(n_groups, 1),), dtype=np.int32)
+        _lib.check(_lib.lib().ytk_parseq_forward_crops(h, buf.data_ptr(), total, descs, n, n_groups,
+                                                       ids.ctypes.data, probs.ctypes.data, glen.ctypes.data, None))
+        return ids, probs, glen[:n_groups]
+
+    def last_flops(self):
+        return _lib.lib().ytk_parseq_last_flops(self._ensure())

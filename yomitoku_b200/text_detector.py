@@ -1,0 +1,92 @@
+"""TextDetector: DBNet++ behind the reference's module API.
+
+Mirrors reference src/yomitoku/text_detector.py:26-146 - same catalog names (`dbnet`, `dbnetv2`, `dbnetv2_1`),
+constructor kwargs, `preprocess` / `postprocess` / `__call__` contract and result schema.  The model forward (and,
+for pages that only need decimation, the resize + normalisation in front of it) runs as sm_100a kernels; contour
+extraction / unclip stay on the host like the reference.  `infer_onnx` is accepted and ignored:
+ONNX / multi-backend dispatch is out of scope for this path.
+"""
+import numpy as np
+import torch
+
+from .base import BaseModelCatalog, BaseModule
+from .config import TextDetectorDBNetConfig, TextDetectorDBNetV2_1Config, TextDetectorDBNetV2Config
+from .data import array_to_tensor, resize_shortest_edge, shortest_edge_size, standardization_image
+from .models import DBNet
+from .postprocessor import DBnetPostProcessor
+from .schemas import TextDetectorSchema
+
+
+class TextDetectorModelCatalog(BaseModelCatalog):
+    def __init__(self):
+        super().__init__()
+        self.register("dbnet", TextDetectorDBNetConfig, DBNet)
+        self.register("dbnetv2", TextDetectorDBNetV2Config, DBNet)
+        self.register("dbnetv2_1", TextDetectorDBNetV2_1Config, DBNet)
+
+
+class TextDetector(BaseModule):
+    model_catalog = TextDetectorModelCatalog()
+
+    def __init__(self, model_name="dbnetv2_1", path_cfg=None, device="cuda", visualize=False, from_pretrained=True,
+                 infer_onnx=False):
+        super().__init__()
+        self.load_model(model_name, path_cfg, from_pretrained=from_pretrained)
+        self.device = device
+        self.visualize = visualize
+        self.model.eval()
+        self.post_processor = DBnetPostProcessor(**self._cfg.post_process)
+        self.infer_onnx = False   # accepted for API compatibility; there is no ONNX path here
+        self.model.to(self.device)
+
+    def preprocess(self, img):
+        """BGR u8 page -> normalised (1,3,H',W') fp32 tensor; reference text_detector.py:99-107 (host path)."""
+        img = img.copy()
+        img = img[:, :, ::-1].astype(np.float32)
+        resized = resize_shortest_edge(img, self._cfg.data.shortest_size, self._cfg.data.limit_size)
+        return array_to_tensor(standardization_image(resized))
+
+    def postprocess(self, preds, image_size):
+        return self.post_processor(preds, image_size)
+
+    def _probability_map(self, img):
+        ori_h, ori_w = img.shape[:2]
+        hn, wn = shortest_edge_size(ori_h, ori_w, self._cfg.data.shortest_size, self._cfg.data.limit_size)
+        if hn <= ori_h and wn <= ori_w:
+            # decimation only: fused GPU pre-processing straight from the u8 page
+            prob = self.model.detect_pages_u8(np.ascontiguousarray(img))
+            return prob.cpu().numpy()[:, None] if prob.is_cuda else prob.numpy()[:, None]
+        tensor = self.preprocess(img)
+        with torch.inference_mode():
+            return self.model(tensor)["binary"].cpu().numpy()
+
+    def __call__(self, img):
+        """Apply the detection model to a BGR page (np.ndarray HxWx3 u8); returns (TextDetectorSchema, vis)."""
+        ori_h, ori_w = img.shape[:2]
+        preds = {"binary": self._probability_map(img)}
+        quads, scores = self.postprocess(preds, (ori_h, ori_w))
+        results = TextDetectorSchema(points=quads, scores=scores)
+        vis = None
+        if self.visualize:
+            vis = det_visualizer(img, quads, line_color=tuple(self._cfg.visualize.color[::-1]))
+        return results, vis
+
+    def detect_pages(self, pages):
+        """Batched entry (new surface): list of same-size BGR pages -> list of
+        TextDetectorSchema.  One device launch sequence for the whole batch, host post-processing per page."""
+        arr = np.stack([np.ascontiguousarray(p) for p in pages])
+        prob = self.model.detect_pages_u8(arr)
+        prob = prob.cpu().numpy() if prob.is_cuda else prob.numpy()
+        out = []
+        for i, p in enumerate(pages):
+            quads, scores = self.postprocess({"binary": prob[i:i + 1, None]}, p.shape[:2])
+            out.append(TextDetectorSchema(points=quads, scores=scores))
+        return out
+
+
+def det_visualizer(img, quads, line_color=(0, 255, 0), **_):
+    import cv2
+    out = img.copy()
+    for q in quads:
+        cv2.polylines(out, [np.array(q, dtype=np.int32)], True, line_color, 2)
+    return out

@@ -1,0 +1,217 @@
+"""TextRecognizer: PARSeq behind the reference's module API.
+
+Mirrors reference src/yomitoku/text_recognizer.py:33-399 - same catalog names, constructor kwargs, width-bucketing
+order (`np.argsort(content_widths)`, :135-140), mini-batch formation (`_make_mini_batch`, :158-203: width-budget greedy
+fill for configs that have `data.width_budget`, fixed `data.batch_size` chunks otherwise), per-batch padded width
+(`_collate`, :146-156), decode + NFKC + direction (`postprocess`, :232-245), optional 180-degree orientation fallback
+(:319-350) and result order restoration (:364-373).
+
+What changes: the mini-batches are *descriptors* - every crop keeps the padded width and the group id its reference
+mini-batch would give it (outputs depend on both) - and all crops of the call go to the GPU
+as ONE packed ragged launch sequence (`PARSeq.recognize_crops`); only (token id, probability) per position come back.
+`infer_onnx` / `num_parallel_batches` are accepted and ignored (no ONNX path; the reference's parallel path is
+unreachable, Appendix A17).
+"""
+import unicodedata
+
+import cv2
+import numpy as np
+
+from .base import BaseModelCatalog, BaseModule
+from .config import (TextRecognizerPARSeqConfig, TextRecognizerPARSeqLargeV41Config, TextRecognizerPARSeqSmallConfig,
+                     TextRecognizerPARSeqTinyConfig, TextRecognizerPARSeqTinyDynwV4Config,
+                     TextRecognizerPARSeqV2Config)
+from .data import ParseqDataset, resize_with_padding
+from .models import PARSeq
+from .postprocessor import ParseqTokenizer as Tokenizer
+from .schemas import TextRecognizerSchema
+
+
+def load_charset(charset_path):
+    with open(charset_path, "r", encoding="utf-8") as f:
+        return f.read()
+
+
+class TextRecognizerModelCatalog(BaseModelCatalog):
+    def __init__(self):
+        super().__init__()
+        self.register("parseq", TextRecognizerPARSeqConfig, PARSeq)
+        self.register("parseqv2", TextRecognizerPARSeqV2Config, PARSeq)
+        self.register("parseq-small", TextRecognizerPARSeqSmallConfig, PARSeq)
+        self.register("parseq-tiny", TextRecognizerPARSeqTinyConfig, PARSeq)
+        self.register("parseq-large-v4_1", TextRecognizerPARSeqLargeV41Config, PARSeq)
+        self.register("parseq-tiny-dynw-v4", TextRecognizerPARSeqTinyDynwV4Config, PARSeq)
+
+
+def plan_mini_batches(widths, order, dynamic_width, batch_size, width_budget=None, max_batch_size=None):
+    """Reference TextRecognizer._make_mini_batch (text_recognizer.py:158-203) on widths only.
+
+    widths[i]: canvas width of crop i (dataset[i].shape[-1]); order: iteration order (bucketing) or None.
+    Returns a list of index lists (the reference's mini-batches, in order)."""
+    indices = list(order) if order is not None else list(range(len(widths)))
+    batches = []
+    if dynamic_width and width_budget:
+        cur, cur_max = [], 0
+        for idx in indices:
+            w = widths[idx]
+            new_max = w if w > cur_max else cur_max
+            over_budget = (len(cur) + 1) * new_max > width_budget
+            over_count = max_batch_size is not None and len(cur) >= max_batch_size
+            if cur and (over_budget or over_count):
+                batches.append(cur)
+                cur = []
+                new_max = w
+            cur.append(idx)
+            cur_max = new_max
+        if cur:
+            batches.append(cur)
+        return batches
+    cur = []
+    for idx in indices:
+        cur.append(idx)
+        if len(cur) == batch_size:
+            batches.append(cur)
+            cur = []
+    if cur:
+        batches.append(cur)
+    return batches
+
+
+class TextRecognizer(BaseModule):
+    model_catalog = TextRecognizerModelCatalog()
+
+    def __init__(self, model_name="parseq-large-v4_1", path_cfg=None, device="cuda", visualize=False,
+                 from_pretrained=True, infer_onnx=False, rec_orientation_fallback=False,
+                 rec_orientation_fallback_thresh=0.75, batch_bucketing=False, dynamic_width=False,
+                 num_parallel_batches=1, source_downscale=False):
+        super().__init__()
+        self.load_model(model_name, path_cfg, from_pretrained=from_pretrained)
+        self.charset = load_charset(self._cfg.charset)
+        self.tokenizer = Tokenizer(self.charset)
+        self.device = device
+        self.model.tokenizer = self.tokenizer
+        self.model.eval()
+        self.visualize = visualize
+        self.infer_onnx = False
+        self.rec_orientation_fallback = rec_orientation_fallback
+        self.rec_orientation_fallback_thresh = rec_orientation_fallback_thresh
+        self.batch_bucketing = batch_bucketing
+        self.dynamic_width = dynamic_width
+        self.num_parallel_batches = num_parallel_batches
+        self.source_downscale = source_downscale
+        self.model.to(self.device)
+
+    # ------------------------------------------------------------------------------------------ batching
+    def preprocess(self, img, polygons):
+        """Crops + bucketing order + mini-batch plan; reference text_recognizer.py:115-144."""
+        if polygons is None:
+            h, w = img.shape[:2]
+            polygons = [[[0, 0], [w, 0], [w, h], [0, h]]]
+        dataset = ParseqDataset(self._cfg, img, polygons, dynamic_width=self.dynamic_width,
+                                source_downscale=self.source_downscale)
+        order = None
+        if self.batch_bucketing and len(dataset) == len(polygons) and len(dataset) > 1:
+            order = np.argsort(dataset.content_widths).tolist()
+        plan = self._make_mini_batch(dataset, order)
+        return plan, polygons, dataset, order
+
+    def _make_mini_batch(self, dataset, order=None):
+        widths = [d.shape[1] for d in dataset.data]
+        return plan_mini_batches(widths, order, self.dynamic_width, self._cfg.data.batch_size,
+                                 getattr(self._cfg.data, "width_budget", None),
+                                 getattr(self._cfg.data, "max_batch_size", None))
+
+    def _collate_widths(self, canvases, plan):
+        """Per crop: (padded width, group id) = what reference _collate (:146-156) does to each mini-batch."""
+        padded = [0] * len(canvases)
+        group = [0] * len(canvases)
+        for g, batch in enumerate(plan):
+            if self.dynamic_width:
+                wmax = max(canvases[i].shape[1] for i in batch)
+            else:
+                wmax = None
+            for i in batch:
+                padded[i] = wmax if wmax is not None else canvases[i].shape[1]
+                group[i] = g
+        return padded, group
+
+    # ------------------------------------------------------------------------------------------ inference
+    def _run_plan(self, canvases, plan):
+        """All mini-batches of `plan` in one packed device call; returns (ids, probs) in `canvases` order."""
+        flat = [i for b in plan for i in b]
+        padded, group = self._collate_widths(canvases, plan)
+        ids, probs, glen = self.model.recognize_crops([canvases[i] for i in flat], [padded[i] for i in flat],
+                                                      [group[i] for i in flat], len(plan))
+        if self.model.refine_iters == 0:
+            # the reference's output then has only `steps run` positions per mini-batch: cut what follows
+            for k, i in enumerate(flat):
+                L = int(glen[group[i]])
+                ids[k, L:] = self.tokenizer.eos_id
+                probs[k, L:] = 1.0
+        return flat, ids, probs
+
+    def postprocess_ids(self, ids, probs, points):
+        pred, score = self.tokenizer.decode_ids(ids, probs)
+        pred = [unicodedata.normalize("NFKC", x) for x in pred]
+        directions = []
+        for point in points:
+            point = np.array(point)
+            w = np.linalg.norm(point[0] - point[1])
+            h = np.linalg.norm(point[1] - point[2])
+            directions.append("vertical" if h > w * 2 else "horizontal")
+        return pred, score, directions
+
+    def postprocess(self, p, points):
+        """Reference entry (:232-245) on a softmax tensor (B,S,C)."""
+        mx, ids = p.max(-1)
+        return self.postprocess_ids(ids.cpu().numpy(), mx.float().cpu().numpy(), points)
+
+    def _run_batch_inference(self, canvases, plan, points_in_plan_order):
+        flat, ids, probs = self._run_plan(canvases, plan)
+        return self.postprocess_ids(ids, probs, points_in_plan_order)
+
+    def _apply_orientation_fallback(self, dataset, points, preds, scores, directions):
+        """Re-run low-score crops rotated by 180 degrees; reference text_recognizer.py:319-350."""
+        retry = [i for i, s in enumerate(scores) if s < self.rec_orientation_fallback_thresh]
+        if not retry:
+            return
+        img_size = self._cfg.data.img_size
+        canv = [resize_with_padding(cv2.rotate(dataset.roi_images[i], cv2.ROTATE_180), img_size) for i in retry]
+        bs = self._cfg.data.batch_size
+        plan = [list(range(s, min(s + bs, len(canv)))) for s in range(0, len(canv), bs)]
+        keep_dw = self.dynamic_width
+        self.dynamic_width = False           # the fallback batch is a fixed-width tensor in the reference (:205-210)
+        try:
+            r_preds, r_scores, r_dirs = self._run_batch_inference(canv, plan, [points[i] for i in retry])
+        finally:
+            self.dynamic_width = keep_dw
+        for j, idx in enumerate(retry):
+            if r_scores[j] > scores[idx] and r_scores[j] >= self.rec_orientation_fallback_thresh:
+                preds[idx], scores[idx], directions[idx] = r_preds[j], r_scores[j], r_dirs[j]
+
+    def __call__(self, img, points=None, vis=None):
+        """img: BGR page; points: list of quads (4 clockwise points).  Returns (TextRecognizerSchema, vis)."""
+        plan, points, dataset, order = self.preprocess(img, points)
+        n = len(dataset)
+        if n == 0:
+            preds, scores, directions = [], [], []
+        else:
+            # the reference pairs batch k's results with points[offset:offset+len] of the (possibly sorted) point
+            # list (:271-283, 364-373); with dropped quads `points` is longer than the dataset, exactly as there
+            pts = [points[i] for i in order] if order is not None else points
+            flat, ids, probs = self._run_plan(dataset.data, plan)
+            p, s, d = self.postprocess_ids(ids, probs, pts[: len(flat)])
+            if order is not None:
+                inverse = np.argsort(order)
+                preds = [p[i] for i in inverse]
+                scores = [s[i] for i in inverse]
+                directions = [d[i] for i in inverse]
+            else:
+                preds, scores, directions = p, s, d
+        if self.rec_orientation_fallback and n:
+            self._apply_orientation_fallback(dataset, points, preds, scores, directions)
+        results = TextRecognizerSchema(contents=preds, scores=scores, points=points, directions=directions)
+        if self.visualize:
+            if vis is None:
+                vis = img.copy()
+        return results, vis
