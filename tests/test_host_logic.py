@@ -1,0 +1,177 @@
+"""CPU: host-side logic of the product package (config, catalog, batching, post-processing, tokenizer) against the
+oracle and against the expectations the reference's own tests pin (tests/test_ocr.py, test_data.py, test_base.py)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parseq as ops
+from oracle import pipeline as opipe
+from yomitoku_b200 import OCR, DocumentAnalyzer, TextDetector, TextRecognizer
+from yomitoku_b200 import data as D
+from yomitoku_b200.base import BaseModelCatalog, BaseModule
+from yomitoku_b200.postprocessor import DBnetPostProcessor, ParseqTokenizer, offset_convex_polygon_round
+from yomitoku_b200.synth import synthetic_page, synthetic_prob_map
+from yomitoku_b200.text_recognizer import plan_mini_batches
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_ocr_config_plumbing_like_reference_test_ocr():
+    # reference tests/test_ocr.py:8-32
+    configs = {
+        "text_detector": {"path_cfg": os.path.join(HERE, "yaml", "text_detector.yaml"), "from_pretrained": False},
+        "text_recognizer": {"path_cfg": os.path.join(HERE, "yaml", "text_recognizer.yaml"), "from_pretrained": False,
+                            "model_name": "parseq-tiny-dynw-v4"},
+    }
+    ocr = OCR(configs=configs, device="cpu", visualize=True)
+    assert ocr.detector.device == torch.device("cpu")
+    assert ocr.recognizer.device == torch.device("cpu")
+    assert ocr.detector.visualize and ocr.recognizer.visualize
+    assert ocr.detector.post_processor.thresh == 0.4
+    assert ocr.recognizer.model.refine_iters == 0
+
+
+def test_invalid_config_raises_like_reference():
+    with pytest.raises(FileNotFoundError):
+        OCR(configs={"text_detector": {"path_cfg": "nope.yaml", "from_pretrained": False}}, device="cpu")
+    with pytest.raises(ValueError):
+        OCR(configs="invalid", device="cpu")
+    with pytest.raises(ValueError):
+        DocumentAnalyzer(configs="invalid", device="cpu")
+    with pytest.raises(ValueError):
+        TextDetector(model_name="unknown-model", from_pretrained=False, device="cpu")
+
+
+def test_catalog_behaviour_like_reference_test_base():
+    cat = BaseModelCatalog()
+    cat.register("a", dict, object)
+    with pytest.raises(ValueError):
+        cat.register("a", dict, object)
+    assert cat.get("A") == (dict, object)
+    with pytest.raises(ValueError):
+        cat.get("b")
+
+    class Bad(BaseModule):
+        model_catalog = None
+
+    with pytest.raises(NotImplementedError):
+        Bad()
+    names = TextRecognizer.model_catalog.list_model()
+    assert names == ["parseq", "parseqv2", "parseq-small", "parseq-tiny", "parseq-large-v4_1", "parseq-tiny-dynw-v4"]
+    assert TextDetector.model_catalog.list_model() == ["dbnet", "dbnetv2", "dbnetv2_1"]
+
+
+def test_no_cpu_fallback_on_the_device_path():
+    det = TextDetector(from_pretrained=False, device="cpu")
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(Exception) as e:
+        det(np.zeros((64, 64, 3), np.uint8))
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_resize_shortest_edge_rules():
+    # reference tests/test_data.py:83-101
+    for h, w in ((1200, 1600), (1600, 1200), (842, 596), (500, 3000), (40, 50)):
+        out = D.resize_shortest_edge(np.zeros((h, w, 3), np.float32), 1280, 1600)
+        oh, ow = out.shape[:2]
+        assert oh % 32 == 0 and ow % 32 == 0 and max(oh, ow) <= 1600
+        assert (oh, ow) == opipe.detector_input_size(h, w)
+    assert D.shortest_edge_size(1200, 1600, 1280, 1600) == (1184, 1600)
+
+
+def test_validate_quads_truth_table():
+    img = np.zeros((100, 200, 3), np.uint8)
+    assert D.validate_quads(img, [[0, 0], [200, 0], [200, 100], [0, 100]]) is True      # x2 == w allowed
+    assert D.validate_quads(img, [[0, 0], [201, 0], [201, 100], [0, 100]]) is None
+    assert D.validate_quads(img, [[-1, 0], [10, 0], [10, 10], [0, 10]]) is None
+    assert D.validate_quads(img, [[0, 0], [10, 0], [10, 10]]) is None
+    assert D.validate_quads(img, [[0, 0, 1], [10, 0], [10, 10], [0, 10]]) is None
+
+
+def test_crops_match_oracle():
+    page, quads = synthetic_page(3)
+    rgb = page[:, :, ::-1]
+    for dyn in (False, True):
+        for q in quads[:25] + [[[100, 100], [124, 100], [124, 400], [100, 400]]]:   # last one is vertical text
+            roi = D.rotate_text_image(D.extract_roi_with_perspective(rgb, q))
+            mine = D.resize_with_dynamic_padding(roi, [32, 800]) if dyn else D.resize_with_padding(roi, [32, 800])
+            ref, cw = opipe.make_crop(rgb, q, (32, 800), dyn)
+            assert np.array_equal(mine, ref)
+            assert cw == D.calc_resize_without_padding(roi, [32, 800])[1]
+            assert torch.equal(D.crop_to_tensor(mine), opipe.to_tensor(ref))
+
+
+@pytest.mark.parametrize("dyn,budget,cap,bs", [(True, 8000, 64, 10), (True, None, None, 128), (False, None, None, 128),
+                                               (True, 800, 3, 10)])
+def test_mini_batch_plan_matches_oracle(dyn, budget, cap, bs):
+    rng = np.random.default_rng(0)
+    widths = (rng.integers(9, 100, size=300) * 8).tolist()
+    for order in (None, np.argsort(widths).tolist()):
+        assert plan_mini_batches(widths, order, dyn, bs, budget, cap) == opipe.mini_batches(widths, order, dyn, bs,
+                                                                                            budget, cap)
+    plan = plan_mini_batches([320] * 16, None, True, 10, 8000, 64)
+    assert plan == [list(range(16))]            # BASELINE config 1: one batch, 16 * 320 <= 8000
+
+
+def test_postprocessor_matches_oracle_and_recovers_boxes():
+    page, quads = synthetic_page(1)
+    prob = synthetic_prob_map(quads, (1184, 1600), (1200, 1600))
+    pp = DBnetPostProcessor(2, 0.3, 0.4, 1500, 3.5)
+    got_q, got_s = pp({"binary": prob[None, None]}, (1200, 1600))
+    ref_q, ref_s = opipe.dbnet_postprocess(prob, (1200, 1600))
+    assert got_q == ref_q and np.allclose(got_s, ref_s)
+    assert len(got_q) == len(quads)
+    # every ground-truth box is found again within a few pixels (unclip grows the shrunk mask back)
+    gt = np.array([[q[0][0], q[0][1], q[2][0], q[2][1]] for q in quads], dtype=np.float32)
+    found = np.array([[min(p[0] for p in q), min(p[1] for p in q), max(p[0] for p in q), max(p[1] for p in q)]
+                      for q in got_q], dtype=np.float32)
+    for g in gt:
+        assert np.abs(found - g).max(axis=1).min() <= 12
+
+
+def test_clipper_offset_properties():
+    box = np.array([[10.7, 20.2], [110.9, 20.2], [110.9, 44.6], [10.7, 44.6]], dtype=np.float32)
+    for delta in (3.0, 7.25, 15.5):
+        out = offset_convex_polygon_round(box, delta)
+        assert np.array_equal(out, opipe.clipper_offset_box(box, delta))
+        # extents = int-truncated box grown by delta (rounded), corners rounded (inside the bounding rectangle)
+        assert abs(out[:, 0].min() - (10 - delta)) <= 0.5 and abs(out[:, 0].max() - (110 + delta)) <= 0.5
+        assert abs(out[:, 1].min() - (20 - delta)) <= 0.5 and abs(out[:, 1].max() - (44 + delta)) <= 0.5
+        r = np.hypot(out[:, 0] - np.clip(out[:, 0], 10, 110), out[:, 1] - np.clip(out[:, 1], 20, 44))
+        assert r.max() <= delta + 0.75          # every vertex lies within delta of the box (round joins)
+    rot = np.array([[0, 0], [100, 20], [96, 40], [-4, 20]], dtype=np.float32)
+    assert np.array_equal(offset_convex_polygon_round(rot, 5.0), opipe.clipper_offset_box(rot, 5.0))
+    assert np.array_equal(offset_convex_polygon_round(rot[::-1], 5.0)[:, 0].min(),
+                          offset_convex_polygon_round(rot, 5.0)[:, 0].min())   # orientation is fixed internally
+
+
+def test_tokenizer_decode_ids_matches_oracle(charset_v2):
+    tok, otok = ParseqTokenizer(charset_v2), ops.Tokenizer(charset_v2)
+    assert (tok.eos_id, tok.bos_id, tok.pad_id) == (0, 7119, 7120) and len(tok) == 7121
+    g = torch.Generator().manual_seed(0)
+    logits = torch.randn(6, 101, 7119, generator=g) * 3
+    logits[0, 5, 0] = 50.0
+    logits[1, 0, 0] = 50.0
+    logits[2, 100, 0] = 50.0
+    p = logits.softmax(-1)
+    s1, p1 = tok.decode(p)
+    s2, p2 = otok.decode(p)
+    assert s1 == s2 and np.allclose(p1, p2, rtol=1e-6, atol=0)
+    assert len(s1[0]) == 5 and s1[1] == "" and len(s1[2]) == 100 and len(s1[3]) == 101
+
+
+def test_recognizer_cpu_plumbing_config1():
+    # BASELINE config 1 (plumbing, no GPU): tiny-dynw, 16 crops whose tensors are 3x32x320 -> one batch
+    rec = TextRecognizer(model_name="parseq-tiny-dynw-v4", device="cpu", from_pretrained=False, dynamic_width=True,
+                         batch_bucketing=True)
+    page = np.full((600, 1400, 3), 255, np.uint8)
+    quads = [[[10, 10 + 34 * i], [266, 10 + 34 * i], [266, 42 + 34 * i], [10, 42 + 34 * i]] for i in range(16)]
+    plan, points, dataset, order = rec.preprocess(page, quads)
+    assert len(dataset) == 16 and all(d.shape == (32, 320, 3) for d in dataset.data)
+    assert len(plan) == 1 and sorted(plan[0]) == list(range(16))
+    assert dataset[0].shape == (3, 32, 320) and float(dataset[0].max()) == 1.0
+    padded, group = rec._collate_widths(dataset.data, plan)
+    assert padded == [320] * 16 and group == [0] * 16
