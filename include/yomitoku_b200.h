@@ -110,13 +110,14 @@ typedef struct {
 int ytk_parseq_create(const ytk_tensor* tensors, int n_tensors, const ytk_parseq_cfg* cfg, ytk_parseq** out);
 void ytk_parseq_destroy(ytk_parseq* h);
 void ytk_parseq_set_refine_iters(ytk_parseq* h, int refine_iters);
-/* crops_host: packed canvases (pinned host memory for async copies).  Outputs (host): ids / probs
+/* crops: packed canvases; host pointer (pinned memory for async copies) or, iff crops_on_device, a device pointer
+ * (the copy is skipped).  Outputs (host): ids / probs
  * [n_crops, max_label_length + 1] = per-position arg-max token and its softmax probability (what
  * BaseTokenizer.decode computes from the full distribution), group_len [n_groups] = AR steps each mini-batch ran
  * (= number of valid positions when refine_iters == 0). */
-int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops_host, long long crops_bytes, const ytk_crop* crops,
-                             int n_crops, int n_groups, int32_t* ids_out, float* probs_out, int32_t* group_len_out,
-                             void* cuda_stream);
+int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops, int crops_on_device, long long crops_bytes,
+                             const ytk_crop* descs, int n_crops, int n_groups, int32_t* ids_out, float* probs_out,
+                             int32_t* group_len_out, void* cuda_stream);
 /* model-level seam: images (B,3,32,W) fp32 as fed to PARSeq.forward (one mini-batch).  logits_out (optional)
  * receives (B, S, C) fp32, S = max_label_length + 1 (only the first group_len positions are written when
  * refine_iters == 0), WITHOUT the repetition patch; rep_cut_out [B] (-1 = none) lets the caller apply

@@ -201,6 +201,8 @@ def parseq_forward(sd, spec, images, return_aux=False):
     logits = torch.cat(steps, dim=1)
     ar_steps = logits.shape[1]
     ar_tokens = tgt_in.clone()
+    ar_top2 = logits.topk(2, -1).values
+    ar_margin = (ar_top2[..., 0] - ar_top2[..., 1])                # (B, steps): decision margin of every AR step
     if spec.refine_iters:
         # Appendix A1: the int64 index tensor zeroes ROWS 0 and 1 of the causal mask (parseq.py:267-277)
         qmask = causal.clone()
@@ -216,7 +218,8 @@ def parseq_forward(sd, spec, images, return_aux=False):
             logits[b, cut, :] = -30.0
             logits[b, cut, spec.eos_id] = 30.0
     if return_aux:
-        return logits, {"memory": memory, "ar_steps": ar_steps, "ar_tokens": ar_tokens, "rep_cut": rep_cut}
+        return logits, {"memory": memory, "ar_steps": ar_steps, "ar_tokens": ar_tokens, "rep_cut": rep_cut,
+                        "ar_margin": ar_margin}
     return logits
 
 

@@ -1,0 +1,109 @@
+"""CPU, world_size 2 over gloo: the multi-GPU plumbing (weight broadcast, group balancing, crop scatter, result
+gather) with a stand-in recognizer - the exchange logic is independent of the model."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _fake_recognise(canvases):
+    """Deterministic function of the crop pixels only: ids[i, :] = checksum-derived, probs = mean pixel."""
+    S = 101
+    ids = np.zeros((len(canvases), S), np.int32)
+    probs = np.zeros((len(canvases), S), np.float32)
+    for i, c in enumerate(canvases):
+        ids[i, :] = (int(c.astype(np.int64).sum()) + np.arange(S)) % 7119
+        probs[i, :] = float(c.mean()) / 255.0
+    return ids, probs
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from yomitoku_b200 import parallel as par
+    try:
+        # ---- weight broadcast
+        g = torch.Generator().manual_seed(100 + rank)
+        sd = {"a.weight": torch.randn(4, 3, generator=g), "b.bias": torch.randn(5, generator=g),
+              "n": torch.tensor(7, dtype=torch.long)}
+        out = par.broadcast_state_dict(sd)
+        ref = torch.randn(4, 3, generator=torch.Generator().manual_seed(100))
+        assert torch.equal(out["a.weight"], ref) and out["n"].item() == 7
+        # ---- unbalanced groups: rank 0 owns 6 groups, rank 1 owns 1
+        rng = np.random.default_rng(rank)
+        n_groups = 6 if rank == 0 else 1
+        groups = []
+        for gi in range(n_groups):
+            n = int(rng.integers(1, 5))
+            widths = (rng.integers(9, 40, size=n) * 8).tolist()
+            canv = [rng.integers(0, 256, size=(32, w, 3), dtype=np.uint8) for w in widths]
+            groups.append((canv, [max(widths)] * n))
+        costs = [sum(4 * (p // 8) for p in g[1]) for g in groups]
+        all_costs = par.gather_costs(costs)
+        assert all_costs[rank] == costs and len(all_costs) == world
+        assign = par.balance_groups(all_costs, world)
+        loads = [0.0] * world
+        for r in range(world):
+            for gi, d in enumerate(assign[r]):
+                loads[d] += all_costs[r][gi]
+        before = max(sum(c) for c in all_costs)
+        assert max(loads) < before            # balancing helped
+        work = par.exchange_groups(groups, assign[rank])
+        assert sum(1 for w in work if w[0] == rank) == sum(1 for d in assign[rank] if d == rank)
+        res = [_fake_recognise(w[2]) for w in work]
+        back = par.return_results(work, res, len(groups))
+        for (canv, _), (ids, probs) in zip(groups, back):
+            eid, ep = _fake_recognise(canv)
+            assert np.array_equal(ids, eid) and np.array_equal(probs, ep)
+        q.put((rank, "ok", loads))
+    except Exception as e:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_crop_scatter_gather_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, status, _ in out:
+        assert status == "ok", status
+
+
+def test_balance_groups_properties():
+    from yomitoku_b200.parallel import balance_groups
+    # balanced input: nothing moves
+    a = balance_groups([[100, 100], [100, 100]], 2)
+    assert a == [[0, 0], [1, 1]]
+    # everything on rank 0 of 4: spreads out, deterministic
+    costs = [[50, 40, 30, 20, 10, 10, 10, 10], [], [], []]
+    a1, a2 = balance_groups(costs, 4), balance_groups(costs, 4)
+    assert a1 == a2
+    loads = [0] * 4
+    for g, d in enumerate(a1[0]):
+        loads[d] += costs[0][g]
+    assert max(loads) <= 60 and sum(loads) == 180
+    assert balance_groups([[5, 5]], 1) == [[0, 0]]

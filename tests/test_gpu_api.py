@@ -1,0 +1,61 @@
+"""GPU: the public API end to end (OCR, BatchedOCR, DocumentAnalyzer) on synthetic pages."""
+import numpy as np
+import pytest
+
+from oracle import parseq as ops
+from oracle import weights
+from yomitoku_b200 import OCR, DocumentAnalyzer
+from yomitoku_b200.pipeline import BatchedOCR
+from yomitoku_b200.synth import synthetic_page, synthetic_prob_map
+
+pytestmark = pytest.mark.gpu
+
+
+def _ocr():
+    o = OCR(configs={"text_detector": {"from_pretrained": False},
+                     "text_recognizer": {"from_pretrained": False, "model_name": "parseq-tiny-dynw-v4",
+                                         "dynamic_width": True, "batch_bucketing": True}}, device="cuda")
+    spec = ops.SPECS["parseq-tiny-dynw-v4"]
+    o.recognizer.model.load_state_dict(weights.make_parseq_state_dict(spec, seed=11, peaked=True))
+    return o
+
+
+def test_ocr_call_returns_schema():
+    o = _ocr()
+    page, quads = synthetic_page(0)
+    res, vis = o(page)
+    assert vis is None
+    for w in res.words[:5]:
+        assert w.direction in ("horizontal", "vertical") and 0.0 <= w.rec_score <= 1.0
+
+
+def test_batched_ocr_equals_per_page_calls():
+    o = _ocr()
+    pages, quads, probs = [], [], []
+    for i in range(3):
+        p, q = synthetic_page(10 + i)
+        pages.append(p)
+        quads.append(q)
+        probs.append(synthetic_prob_map(q, (1184, 1600), (1200, 1600)))
+    b = BatchedOCR(o.detector, o.recognizer, workers=2, det_batch=2)
+    try:
+        res = b(pages, prob_override=probs)
+    finally:
+        b.close()
+    assert len(res) == 3
+    for i in range(3):
+        assert len(res[i].words) == len(quads[i])
+        # the same page through the one-page recognizer API (same quads): identical strings
+        det_points = [w.points for w in res[i].words]
+        single, _ = o.recognizer(pages[i], det_points)
+        assert [w.content for w in res[i].words] == single.contents
+        assert np.allclose([w.rec_score for w in res[i].words], single.scores, atol=1e-6)
+
+
+def test_document_analyzer_shell():
+    da = DocumentAnalyzer(configs={"ocr": {"text_detector": {"from_pretrained": False},
+                                           "text_recognizer": {"from_pretrained": False,
+                                                               "model_name": "parseq-tiny-dynw-v4"}}}, device="cuda")
+    page, _ = synthetic_page(1)
+    res, ocr_vis, layout_vis = da(page)
+    assert layout_vis is None and isinstance(res.words, list)

@@ -1,0 +1,117 @@
+"""GPU: DBNet engine against the CPU oracle / reference-generated fixture.
+
+Stated tolerances (bf16 activations through ~60 layers vs the fp32 reference, seeded random weights - the sigmoid
+head of an untrained net amplifies noise, trained weights are smoother):
+  backbone features  relative Frobenius error < 1.5 %
+  probability map    mean |d| < 0.012, 99.5 % of the pixels within 0.08
+  polygons           when the device's actual error field is superimposed on a realistic probability map, every
+                     box is found again with IoU >= 0.9 and corner coordinates within 2 px."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import dbnet as odb
+from oracle import pipeline as opipe
+from oracle import weights
+from yomitoku_b200 import TextDetector, _lib
+from yomitoku_b200.postprocessor import DBnetPostProcessor
+from yomitoku_b200.synth import synthetic_page, synthetic_prob_map
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+@pytest.fixture(scope="module")
+def det():
+    d = TextDetector(from_pretrained=False, device="cuda")
+    d.model.load_state_dict(weights.make_dbnet_state_dict(seed=1))
+    return d
+
+
+def _debug(model, n, H, W, name):
+    L = _lib.lib()
+    shape = (ctypes.c_int * 4)()
+    cap = n * H * W * 64 + 16
+    buf = torch.empty(cap, dtype=torch.float32)
+    _lib.check(L.ytk_dbnet_debug_tensor(model._ensure(), n, H, W, name.encode(), buf.data_ptr(), cap, shape))
+    n_, h_, w_, c_ = list(shape)
+    return buf[: n_ * h_ * w_ * c_].reshape(n_, h_, w_, c_)
+
+
+def _prob_close(got, ref):
+    d = np.abs(got - ref)
+    assert d.mean() < 0.012, d.mean()
+    assert (d < 0.08).mean() > 0.995, (d < 0.08).mean()
+
+
+def test_reference_fixture_through_model_seam():
+    z = np.load(os.path.join(G, "dbnet_ref.npz"))
+    d = TextDetector(from_pretrained=False, device="cuda")
+    d.model.load_state_dict(weights.make_dbnet_state_dict(seed=int(z["weight_seed"])))
+    out = d.model(torch.from_numpy(z["x"]))["binary"].numpy()
+    assert out.shape == z["prob"].shape
+    _prob_close(out, z["prob"])
+
+
+def test_backbone_and_prob_vs_oracle(det):
+    sd = det.model.state_dict()
+    H, W = 256, 384
+    x = torch.randn(2, 3, H, W, generator=torch.Generator().manual_seed(0))
+    prob = det.model(x)["binary"]
+    with torch.inference_mode():
+        feats = odb.backbone_features(sd, x)
+        ref = odb.decoder_forward(sd, feats)
+    for k in ("layer1", "layer2", "layer3", "layer4"):
+        got = _debug(det.model, 2, H, W, k)
+        r = feats[k].permute(0, 2, 3, 1)
+        assert ((got - r).norm() / r.norm()).item() < 0.015, k
+    _prob_close(prob.numpy(), ref.numpy())
+
+
+def test_fused_u8_path_full_page_and_polygons(det):
+    page, quads = synthetic_page(2)
+    prob = det.model.detect_pages_u8(page)[0].numpy()
+    assert prob.shape == (1184, 1600)
+    x = opipe.detector_preprocess(page)
+    ref = odb.dbnet_forward(det.model.state_dict(), x)[0, 0].numpy()
+    _prob_close(prob, ref)
+    # polygons: superimpose the device's error field on a realistic map of this page's boxes
+    base = synthetic_prob_map(quads, (1184, 1600), (1200, 1600))
+    pp = DBnetPostProcessor(**det._cfg.post_process)
+    q_ref, s_ref = pp({"binary": base[None, None]}, (1200, 1600))
+    q_dev, s_dev = pp({"binary": np.clip(base + (prob - ref), 0, 1)[None, None]}, (1200, 1600))
+    assert len(q_ref) == len(quads) and len(q_dev) == len(q_ref)
+
+    def rect(q):
+        a = np.array(q)
+        return a[:, 0].min(), a[:, 1].min(), a[:, 0].max(), a[:, 1].max()
+
+    dev_r = np.array([rect(q) for q in q_dev], dtype=np.float64)
+    for q in q_ref:
+        r = np.array(rect(q), dtype=np.float64)
+        ix = np.clip(np.minimum(dev_r[:, 2], r[2]) - np.maximum(dev_r[:, 0], r[0]), 0, None)
+        iy = np.clip(np.minimum(dev_r[:, 3], r[3]) - np.maximum(dev_r[:, 1], r[1]), 0, None)
+        inter = ix * iy
+        union = (dev_r[:, 2] - dev_r[:, 0]) * (dev_r[:, 3] - dev_r[:, 1]) + (r[2] - r[0]) * (r[3] - r[1]) - inter
+        j = int(np.argmax(inter / union))
+        assert (inter / union)[j] >= 0.9
+        assert np.abs(dev_r[j] - r).max() <= 2
+
+
+def test_detector_call_contract(det):
+    page, _ = synthetic_page(0)
+    res, vis = det(page)
+    assert vis is None and len(res.points) == len(res.scores)
+    for q in res.points[:5]:
+        assert len(q) == 4 and all(0 <= x <= 1600 and 0 <= y <= 1200 for x, y in q)
+    # batched entry == single-page entry (same device code, batch dimension only)
+    two = det.detect_pages([page, page])
+    assert two[0].points == two[1].points
+    # a page that needs up-scaling goes through the host resize + model seam like the reference
+    small = np.ascontiguousarray(page[:300, :420])
+    res2, _ = det(small)
+    assert isinstance(res2.points, list)

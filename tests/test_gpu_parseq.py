@@ -1,0 +1,130 @@
+"""GPU: PARSeq engine against the CPU oracle.
+
+Stated tolerances: encoder memory relative Frobenius error < 1 %; logits of the first AR step (no token feedback)
+max |d| < 3 % of the logit standard deviation + 0.05; decoded strings CHARACTER-IDENTICAL for every row whose greedy
+decisions are not near-ties - a row may differ from the oracle only if the oracle's own top-2 margin at some AR step
+is below TAU (bf16 operands cannot resolve smaller gaps; with trained, peaked models such ties are rare)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import parseq as ops
+from oracle import pipeline as opipe
+from oracle import weights
+from yomitoku_b200 import TextRecognizer
+from yomitoku_b200.synth import synthetic_page
+
+pytestmark = pytest.mark.gpu
+TAU = 0.6   # logit units; the peaked test weights have a logit std of ~6
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _rec(name, sd=None, **kw):
+    r = TextRecognizer(model_name=name, from_pretrained=False, device="cuda", dynamic_width=True, batch_bucketing=True,
+                       **kw)
+    if sd is not None:
+        r.model.load_state_dict(sd)
+    return r
+
+
+def _margin_aware_equal(ids_gpu, logits_ref, aux, tag):
+    ids_ref = logits_ref.argmax(-1).numpy()
+    ref_margin = logits_ref.topk(2, -1).values
+    ref_margin = (ref_margin[..., 0] - ref_margin[..., 1]).numpy()
+    n_same = 0
+    for b in range(ids_ref.shape[0]):
+        # compare up to and including the first EOS (what the tokenizer reads)
+        row = ids_ref[b].tolist()
+        n = row.index(0) + 1 if 0 in row else len(row)
+        if np.array_equal(ids_gpu[b, :n], ids_ref[b, :n]):
+            n_same += 1
+            continue
+        low = min(float(aux["ar_margin"][b].min()), float(ref_margin[b, :n].min()))
+        assert low < TAU, "%s row %d differs although every decision margin >= %.2f (min %.3f)" % (tag, b, TAU, low)
+    return n_same
+
+
+@pytest.mark.parametrize("name,B,W,seed", [("parseq-tiny-dynw-v4", 16, 320, 3), ("parseq-tiny-dynw-v4", 5, 104, 3),
+                                           ("parseq-large-v4_1", 8, 160, 4), ("parseq-large-v4_1", 3, 800, 4)])
+def test_model_seam_vs_oracle(name, B, W, seed):
+    spec = ops.SPECS[name]
+    sd = weights.make_parseq_state_dict(spec, seed=seed, peaked=True)
+    rec = _rec(name, sd)
+    img = torch.rand(B, 3, 32, W, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    got = rec.model(img)
+    ref, aux = ops.parseq_forward(sd, spec, img, return_aux=True)
+    assert got.shape == ref.shape == (B, 101, spec.num_classes)
+    n_same = _margin_aware_equal(got.argmax(-1).numpy(), ref, aux, name)
+    assert n_same >= int(0.6 * B)
+    # rows that took the same path: refined logits agree closely
+    same = [b for b in range(B) if torch.equal(got[b].argmax(-1), ref[b].argmax(-1))]
+    d = (got[same] - ref[same]).abs().max().item()
+    assert d < 0.03 * ref.std().item() + 0.05, d
+
+
+def test_reference_fixture_strings(charset_v2):
+    for tag, kw in (("peaked", dict(peaked=True)), ("repeat", dict(peaked=True, degenerate_repeat=True))):
+        z = np.load(os.path.join(G, "parseq_ref_%s.npz" % tag), allow_pickle=True)
+        spec = ops.SPECS["parseq-tiny-dynw-v4"]
+        sd = weights.make_parseq_state_dict(spec, seed=int(z["weight_seed"]), **kw)
+        rec = _rec("parseq-tiny-dynw-v4", sd)
+        p = rec.model(torch.from_numpy(z["img"])).softmax(-1)
+        strings, scores = rec.tokenizer.decode(p)
+        assert strings == list(z["strings"]), tag
+        assert np.allclose(scores, z["scores"], rtol=0.08), tag
+
+
+def test_repetition_stop_and_refine_off():
+    spec = ops.SPECS["parseq-tiny-dynw-v4"]
+    sd = weights.make_parseq_state_dict(spec, seed=3, peaked=True, degenerate_repeat=True)
+    rec = _rec("parseq-tiny-dynw-v4", sd)
+    img = torch.rand(4, 3, 32, 200, generator=torch.Generator().manual_seed(1)) * 2 - 1
+    ref = ops.parseq_forward(sd, spec, img)
+    got = rec.model(img)
+    assert torch.equal(got.argmax(-1), ref.argmax(-1))
+    assert (got[:, 2, 0] == 30.0).all() and (got[:, 2, 1] == -30.0).all()     # the logit patch at rep_cut
+    # refine_iters = 0 (the reference's tests/yaml/text_recognizer.yaml): output length = AR steps run
+    rec.model.refine_iters = 0
+    spec0 = ops.ParseqSpec(**{**spec.__dict__, "refine_iters": 0})
+    ref0 = ops.parseq_forward(sd, spec0, img)
+    got0 = rec.model(img)
+    assert got0.shape == ref0.shape
+    assert torch.equal(got0.argmax(-1), ref0.argmax(-1))
+
+
+def test_ragged_crops_match_reference_batching(charset_v2):
+    """Packed ragged call (many mini-batches, per-crop padded widths) == the reference's batch-by-batch loop."""
+    name = "parseq-tiny-dynw-v4"
+    spec = ops.SPECS[name]
+    sd = weights.make_parseq_state_dict(spec, seed=7, peaked=True)
+    rec = _rec(name, sd)
+    page, quads = synthetic_page(5)
+    quads = quads[:70]
+    out, _ = rec(page, quads)
+    preds, scores, dirs, aux = opipe.recognize(sd, spec, ops.Tokenizer(charset_v2), page, quads, dynamic_width=True,
+                                               batch_bucketing=True, batch_size=10, width_budget=8000,
+                                               max_batch_size=64, return_aux=True)
+    assert len(aux["plan"]) > 1                       # several reference mini-batches with different padded widths
+    assert out.directions == dirs and out.points == quads
+    same = sum(a == b for a, b in zip(out.contents, preds))
+    assert same >= int(0.7 * len(quads)), same
+    for a, b, sa, sb in zip(out.contents, preds, out.scores, scores):
+        if a == b:
+            assert abs(sa - sb) <= 0.1 * max(sb, 1e-6) + 1e-6
+
+
+def test_large_model_ragged_vs_seam_consistency():
+    """Exactness on the device: a crop's result must not depend on what else is packed with it, as long as its
+    padded width and group stay the same."""
+    name = "parseq-large-v4_1"
+    spec = ops.SPECS[name]
+    sd = weights.make_parseq_state_dict(spec, seed=9, peaked=True)
+    rec = _rec(name, sd)
+    rng = np.random.default_rng(0)
+    canv = [rng.integers(0, 256, size=(32, w, 3), dtype=np.uint8) for w in (96, 120, 160, 160, 200, 320)]
+    ids_a, probs_a, _ = rec.model.recognize_crops(canv, [160, 160, 160, 160, 320, 320], [0, 0, 0, 0, 1, 1], 2)
+    ids_b, probs_b, _ = rec.model.recognize_crops(canv[:4], [160] * 4, [0] * 4, 1)
+    assert np.array_equal(ids_a[:4], ids_b)
+    assert np.allclose(probs_a[:4], probs_b, atol=1e-6)

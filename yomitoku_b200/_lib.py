@@ -76,8 +76,8 @@ def _declare_parseq(lib):
     lib.ytk_parseq_set_refine_iters.restype = None
     lib.ytk_parseq_set_refine_iters.argtypes = [c_void_p, c_int]
     lib.ytk_parseq_forward_crops.restype = c_int
-    lib.ytk_parseq_forward_crops.argtypes = [c_void_p, c_void_p, c_ll, P(YtkCrop), c_int, c_int, c_void_p, c_void_p,
-                                             c_void_p, c_void_p]
+    lib.ytk_parseq_forward_crops.argtypes = [c_void_p, c_void_p, c_int, c_ll, P(YtkCrop), c_int, c_int, c_void_p,
+                                             c_void_p, c_void_p, c_void_p]
     lib.ytk_parseq_forward_f32.restype = c_int
     lib.ytk_parseq_forward_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
                                            c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]

@@ -259,16 +259,17 @@ void ytk_parseq_set_refine_iters(ytk_parseq* h, int refine_iters) {
     h->model.cfg.refine_iters = refine_iters;
 }
 
-int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops_host, long long crops_bytes, const ytk_crop* crops,
-                             int n_crops, int n_groups, int32_t* ids_out, float* probs_out, int32_t* group_len_out,
-                             void* cuda_stream) {
+int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops_ptr, int crops_on_device, long long crops_bytes,
+                             const ytk_crop* crops, int n_crops, int n_groups, int32_t* ids_out, float* probs_out,
+                             int32_t* group_len_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
     if (h->model.cfg.refine_iters > 1) {
         ytk::set_error("refine_iters > 1 is not implemented on the device path");
         return YTK_ERR;
     }
     ytk::ParseqBatch b;
-    b.crops = crops_host;
+    b.crops = crops_ptr;
+    b.crops_on_device = crops_on_device;
     b.crops_bytes = crops_bytes;
     b.ngroups = n_groups;
     b.descs.resize(n_crops);

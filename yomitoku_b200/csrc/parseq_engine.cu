@@ -343,8 +343,12 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         if (launch_patchify_f32(img, B, b.image_w, c.ph, c.pw, m->Kpatch, m->pos_embed, m->full_gw, D, A_patch, x, st))
             return 1;
     } else {
-        CK(cudaMemcpyAsync(crops_dev, b.crops, b.crops_bytes, cudaMemcpyHostToDevice, st));
-        if (launch_patchify_u8(crops_dev, descs_dev, B, c.ph, c.pw, m->Kpatch, m->pos_embed, m->full_gw, D, A_patch, x,
+        const uint8_t* cp = b.crops;
+        if (!b.crops_on_device) {
+            CK(cudaMemcpyAsync(crops_dev, b.crops, b.crops_bytes, cudaMemcpyHostToDevice, st));
+            cp = crops_dev;
+        }
+        if (launch_patchify_u8(cp, descs_dev, B, c.ph, c.pw, m->Kpatch, m->pos_embed, m->full_gw, D, A_patch, x,
                                (int)T, st))
             return 1;
     }

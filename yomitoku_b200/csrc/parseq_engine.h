@@ -51,7 +51,8 @@ struct ParseqModel {
 
 // Host-side description of one recognizer call.
 struct ParseqBatch {
-    const uint8_t* crops = nullptr;   // packed u8 RGB canvases (host), or null when images_f32 is used
+    const uint8_t* crops = nullptr;   // packed u8 RGB canvases (host or device), or null when images_f32 is used
+    int crops_on_device = 0;
     long long crops_bytes = 0;
     const float* images_f32 = nullptr;  // model-level seam: (B,3,32,W) fp32, host or device
     int images_on_device = 0;

@@ -349,20 +349,16 @@ class PARSeq(_DeviceModel):
                     logits[b, cut, 0] = 30.0
         return logits
 
-    def recognize_crops(self, canvases, padded_widths, groups, n_groups):
-        """Fused ragged path.  canvases: list of (32, w_i, 3) uint8 RGB arrays (the reference's dataset.data[i]);
-        padded_widths[i]: width the reference collate would pad crop i to; groups[i]: its mini-batch index.
-        Returns ids (n,S) int32, probs (n,S) float32, group_len (n_groups,) int32 (numpy)."""
-        h = self._ensure()
+    def pack_crops(self, canvases, padded_widths, groups):
+        """Packs canvases into one pinned uint8 buffer + ytk_crop descriptors (host side of recognize_crops)."""
         n = len(canvases)
-        S = self.max_label_length + 1
         ph, pw = self.cfg.encoder.patch_size
         gh = self.cfg.data.img_size[0] // ph
         sizes = [int(c.shape[0] * c.shape[1] * 3) for c in canvases]
         total = int(sum(sizes))
         buf = torch.empty(max(total, 1), dtype=torch.uint8, pin_memory=torch.cuda.is_available())
         nb = buf.numpy()
-        descs = (_lib.YtkCrop * n)()
+        descs = (_lib.YtkCrop * max(n, 1))()
         off = tok = 0
         for i, c in enumerate(canvases):
             nb[off:off + sizes[i]] = np.ascontiguousarray(c).reshape(-1)
@@ -371,12 +367,26 @@ class PARSeq(_DeviceModel):
             descs[i] = _lib.YtkCrop(off, int(c.shape[1]), wp, tok, ntok, int(groups[i]))
             off += sizes[i]
             tok += ntok
+        return buf, total, descs, tok
+
+    def run_packed(self, buf, total, descs, n, n_groups):
+        """Device call on a packed crop buffer (torch uint8 tensor, pinned host or cuda)."""
+        h = self._ensure()
+        S = self.max_label_length + 1
         ids = np.empty((n, S), dtype=np.int32)
         probs = np.empty((n, S), dtype=np.float32)
         glen = np.empty((max(n_groups, 1),), dtype=np.int32)
-        _lib.check(_lib.lib().ytk_parseq_forward_crops(h, buf.data_ptr(), total, descs, n, n_groups,
-                                                       ids.ctypes.data, probs.ctypes.data, glen.ctypes.data, None))
+        _lib.check(_lib.lib().ytk_parseq_forward_crops(h, buf.data_ptr(), 1 if buf.is_cuda else 0, total, descs, n,
+                                                       n_groups, ids.ctypes.data, probs.ctypes.data, glen.ctypes.data,
+                                                       None))
         return ids, probs, glen[:n_groups]
+
+    def recognize_crops(self, canvases, padded_widths, groups, n_groups):
+        """Fused ragged path.  canvases: list of (32, w_i, 3) uint8 RGB arrays (the reference's dataset.data[i]);
+        padded_widths[i]: width the reference collate would pad crop i to; groups[i]: its mini-batch index.
+        Returns ids (n,S) int32, probs (n,S) float32, group_len (n_groups,) int32 (numpy)."""
+        buf, total, descs, _ = self.pack_crops(canvases, padded_widths, groups)
+        return self.run_packed(buf, total, descs, len(canvases), n_groups)
 
     def last_flops(self):
         return _lib.lib().ytk_parseq_last_flops(self._ensure())

@@ -1,0 +1,209 @@
+"""Batched multi-page OCR: the new surface this repo adds on top of the reference's one-page-per-call modules
+("there is no multi-page or multi-GPU batching in the reference").
+
+    ocr = BatchedOCR(TextDetector(...), TextRecognizer(...), workers=16)
+    results = ocr(pages)            # list of BGR pages of one size -> list of OCRSchema
+
+Per page the results are what `OCR.__call__` (reference ocr.py:51-63) returns: detection runs for a whole batch of
+pages in one device launch sequence, the host stages the reference also has (contours/unclip, crop extraction:
+SURVEY.md R3/R4) fan out over a process pool, and ALL crops of ALL pages go to the recognizer as one packed ragged
+call in which every crop keeps the padded width and mini-batch group its own page would have given it - so per-page
+outputs do not depend on how many pages are batched.
+"""
+import os
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+from .data import ParseqDataset
+from .ocr import ocr_aggregate
+from .postprocessor import DBnetPostProcessor
+from .schemas import OCRSchema, TextDetectorSchema, TextRecognizerSchema
+from .text_recognizer import plan_mini_batches
+
+_W = {}
+
+
+def _worker_init(post_kwargs, rec_cfg, dynamic_width, source_downscale):
+    import cv2
+    cv2.setNumThreads(1)
+    _W["post"] = DBnetPostProcessor(**post_kwargs)
+    _W["cfg"] = rec_cfg
+    _W["dyn"] = dynamic_width
+    _W["sd"] = source_downscale
+
+
+def _host_stage(args):
+    """Post-process one probability map and cut that page's crops (runs in a worker process)."""
+    page, prob, quads_override = args
+    if quads_override is None:
+        quads, scores = _W["post"]({"binary": prob[None, None]}, page.shape[:2])
+    else:
+        quads, scores = quads_override, [1.0] * len(quads_override)
+    ds = ParseqDataset(_W["cfg"], page, quads if len(quads) else [], num_workers=1, dynamic_width=_W["dyn"],
+                       source_downscale=_W["sd"]) if len(quads) else None
+    if ds is None:
+        return quads, scores, [], [], 0
+    return quads, scores, ds.data, ds.content_widths, len(ds)
+
+
+class BatchedOCR:
+    def __init__(self, detector, recognizer, workers=None, det_batch=8, max_tokens=400_000):
+        self.detector = detector
+        self.recognizer = recognizer
+        self.det_batch = det_batch
+        self.max_tokens = max_tokens
+        self.workers = workers if workers is not None else max(1, min(32, (os.cpu_count() or 2) - 2))
+        self._pool = None
+
+    # ------------------------------------------------------------------------------------------ host pool
+    def _get_pool(self):
+        if self._pool is None and self.workers > 1:
+            import multiprocessing as mp
+            r = self.recognizer
+            self._pool = ProcessPoolExecutor(
+                max_workers=self.workers, mp_context=mp.get_context("fork"), initializer=_worker_init,
+                initargs=(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale))
+        return self._pool
+
+    def close(self):
+        if self._pool is not None:
+            self._pool.shutdown(wait=True, cancel_futures=True)
+            self._pool = None
+
+    def _host_map(self, jobs):
+        pool = self._get_pool()
+        if pool is None:
+            r = self.recognizer
+            _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
+            return [_host_stage(j) for j in jobs]
+        return list(pool.map(_host_stage, jobs, chunksize=1))
+
+    # ------------------------------------------------------------------------------------------ stages
+    def detect_prob(self, pages):
+        """Device stage 1: probability maps (n, Hn, Wn) float32 (host) for same-size pages."""
+        out = []
+        for s in range(0, len(pages), self.det_batch):
+            arr = np.stack([np.ascontiguousarray(p) for p in pages[s:s + self.det_batch]])
+            prob = self.detector.model.detect_pages_u8(arr)
+            out.append(prob.cpu().numpy() if prob.is_cuda else prob.numpy())
+        return np.concatenate(out, axis=0)
+
+    def _run_groups_local(self, groups):
+        """groups: list of (canvases, padded_widths).  One packed device call per <= max_tokens chunk (chunks end on
+        group boundaries).  Returns per group (ids, probs, group_len)."""
+        rec = self.recognizer
+        cfg = rec._cfg
+        ph, pw = cfg.encoder.patch_size
+        gh = cfg.data.img_size[0] // ph
+        out = [None] * len(groups)
+        start = 0
+        while start < len(groups):
+            end, tok = start, 0
+            while end < len(groups):
+                gtok = sum(gh * (p // pw) for p in groups[end][1])
+                if end > start and tok + gtok > self.max_tokens:
+                    break
+                tok += gtok
+                end += 1
+            canv = [c for g in groups[start:end] for c in g[0]]
+            pad = [p for g in groups[start:end] for p in g[1]]
+            grp = [k for k, g in enumerate(groups[start:end]) for _ in g[0]]
+            ids, probs, glen = rec.model.recognize_crops(canv, pad, grp, end - start)
+            off = 0
+            for k in range(start, end):
+                n = len(groups[k][0])
+                out[k] = (ids[off:off + n], probs[off:off + n], int(glen[k - start]))
+                off += n
+            start = end
+        return out
+
+    def _run_groups(self, groups):
+        """Recognise groups, spreading them over all ranks when torch.distributed is initialised (crop scatter /
+        result gather over NCCL, yomitoku_b200/parallel.py); results come back in `groups` order."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return self._run_groups_local(groups)
+        from . import parallel as par
+        cfg = self.recognizer._cfg
+        ph, pw = cfg.encoder.patch_size
+        gh = cfg.data.img_size[0] // ph
+        costs = [sum(gh * (p // pw) for p in g[1]) for g in groups]
+        assign = par.balance_groups(par.gather_costs(costs), dist.get_world_size())[dist.get_rank()]
+        work = par.exchange_groups(groups, assign, cfg.data.img_size[0])
+        res = self._run_groups_local([(w[2], w[3]) for w in work])
+        S = cfg.max_label_length + 1
+        # group_len travels as an extra column pair so that refine_iters == 0 keeps working across ranks
+        packed = []
+        for (ids, probs, glen) in res:
+            packed.append((np.concatenate([ids, np.full((ids.shape[0], 1), glen, np.int32)], axis=1),
+                           np.concatenate([probs, np.zeros((probs.shape[0], 1), np.float32)], axis=1)))
+        back = par.return_results(work, packed, len(groups), S + 1)
+        return [(i[:, :S], p[:, :S], int(i[0, S]) if len(i) else 0) for i, p in back]
+
+    def recognize_pooled(self, per_page):
+        """Device stage 2: per_page = list of (canvases, content_widths, n_quads).  Returns per page (ids, probs,
+        order) with rows in the page's *plan* order, exactly like TextRecognizer._run_plan."""
+        rec = self.recognizer
+        cfg = rec._cfg
+        groups, owner, orders = [], [], []
+        for pi, (canv, cw, n_quads) in enumerate(per_page):
+            order = None
+            if rec.batch_bucketing and len(canv) == n_quads and len(canv) > 1:
+                order = np.argsort(cw).tolist()
+            plan = plan_mini_batches([c.shape[1] for c in canv], order, rec.dynamic_width, cfg.data.batch_size,
+                                     getattr(cfg.data, "width_budget", None),
+                                     getattr(cfg.data, "max_batch_size", None))
+            padded, _ = rec._collate_widths(canv, plan)
+            for b in plan:
+                groups.append(([canv[i] for i in b], [padded[i] for i in b]))
+                owner.append(pi)
+            orders.append(order)
+        res = self._run_groups(groups)
+        S = cfg.max_label_length + 1
+        out = []
+        for pi in range(len(per_page)):
+            mine = [r for r, o in zip(res, owner) if o == pi]
+            if not mine:
+                out.append((np.zeros((0, S), np.int32), np.zeros((0, S), np.float32), orders[pi]))
+                continue
+            ids = np.concatenate([m[0] for m in mine]).copy()
+            probs = np.concatenate([m[1] for m in mine]).copy()
+            if rec.model.refine_iters == 0:
+                k = 0
+                for m in mine:
+                    n = m[0].shape[0]
+                    ids[k:k + n, m[2]:] = rec.tokenizer.eos_id
+                    probs[k:k + n, m[2]:] = 1.0
+                    k += n
+            out.append((ids, probs, orders[pi]))
+        return out
+
+    # ------------------------------------------------------------------------------------------ whole path
+    def __call__(self, pages, prob_override=None, quads_override=None):
+        """pages: list of same-size BGR uint8 arrays.  prob_override / quads_override (benchmarks with random
+        detector weights): the detector still runs, but post-processing sees the given probability maps / the
+        recognizer the given quads."""
+        prob = self.detect_prob(pages)
+        jobs = []
+        for i, p in enumerate(pages):
+            pm = prob[i] if prob_override is None else prob_override[i]
+            jobs.append((p, pm, None if quads_override is None else quads_override[i]))
+        host = self._host_map(jobs)
+        rec_in = [(h[2], h[3], len(h[0])) for h in host]
+        rec_out = self.recognize_pooled(rec_in)
+        results = []
+        r = self.recognizer
+        for (quads, scores, canv, cw, n), (ids, probs, order) in zip(host, rec_out):
+            det = TextDetectorSchema(points=quads, scores=scores)
+            if n == 0:
+                rec = TextRecognizerSchema(contents=[], directions=[], scores=[], points=quads)
+            else:
+                pts = [quads[i] for i in order] if order is not None else quads
+                p, s, d = r.postprocess_ids(ids, probs, pts[:n])
+                if order is not None:
+                    inv = np.argsort(order)
+                    p, s, d = [p[i] for i in inv], [s[i] for i in inv], [d[i] for i in inv]
+                rec = TextRecognizerSchema(contents=p, directions=d, scores=s, points=quads)
+            results.append(OCRSchema(words=ocr_aggregate(det, rec)))
+        return results
