@@ -132,18 +132,21 @@ def run_reference(args):
         return
     vals = []
     detail = None
-    for i in range(args.warmup + args.steps):
+    t_start = time.perf_counter()
+    warm, steps, i = args.warmup, args.steps, 0
+    while i < warm + steps:
         r = cpu_pipeline_rate(16, 30.0)
-        if i >= args.warmup:
+        if i >= warm:
             vals.append(r["pages_per_s"])
             detail = r
-        if i == 0 and args.warmup + args.steps > 1:
-            # keep the whole run within a few minutes: one sample costs (t_det + t_rec) seconds
-            per = 1.0 / r["pages_per_s"] * 16 / r["crops_per_page"] + r["t_det_s"]
-            budget = 240.0
-            max_iters = max(1, int(budget / max(per, 1e-3)))
-            if args.warmup + args.steps > max_iters:
-                args.steps = max(1, max_iters - args.warmup)
+        i += 1
+        per = (time.perf_counter() - t_start) / i
+        # keep the whole run within a few minutes (a step is a bounded sample, but K and W come from the driver)
+        if per * (warm + steps) > 240.0:
+            warm = min(warm, 1)
+            steps = max(1, int(240.0 / per) - warm)
+    if not vals:
+        vals, detail = [r["pages_per_s"]], r
     v = float(np.mean(vals))
     sample = ("1 page DBNet fp32 + post-processing, %d of %d crops through PARSeq %s (reference batching), "
               "recognizer time scaled to the page's crop count") % (detail["crops_sample"], detail["crops_per_page"],
@@ -326,7 +329,8 @@ def main():
                        "l2": "working set (%.1f GB activations per step) >> 126 MB L2; no explicit flush" %
                              (P * 1.2 + 4.0),
                        "ar_steps": int(L.ytk_parseq_last_steps(rec.model._ensure())),
-                       "weights": "seeded random init (from_pretrained=False)"},
+                       "weights": "seeded random init (from_pretrained=False)",
+                       "recognizer_phase_ms": rec.model.last_phase_ms()},
             "crops_per_s": world * n_crops * args.steps / (rec_ms / 1e3),
             "det_pages_per_s": world * P * args.steps / (det_ms / 1e3),
             "roofline": {"bound": "tensor", "achieved": det_tflops, "peak": pk["bf16_tflops_sustained"],

@@ -128,6 +128,8 @@ int ytk_parseq_forward_f32(ytk_parseq* h, const float* images, int images_on_dev
 /* algorithmic FLOPs (2*MAC; GEMMs + attention) and AR steps of the last forward call */
 double ytk_parseq_last_flops(ytk_parseq* h);
 int ytk_parseq_last_steps(ytk_parseq* h);
+/* CUDA-event times (ms) of the last forward: encoder, AR decode, refinement, output copies */
+void ytk_parseq_last_phase_ms(ytk_parseq* h, float* ms4);
 
 #ifdef __cplusplus
 }

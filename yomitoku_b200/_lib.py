@@ -85,6 +85,8 @@ def _declare_parseq(lib):
     lib.ytk_parseq_last_flops.argtypes = [c_void_p]
     lib.ytk_parseq_last_steps.restype = c_int
     lib.ytk_parseq_last_steps.argtypes = [c_void_p]
+    lib.ytk_parseq_last_phase_ms.restype = None
+    lib.ytk_parseq_last_phase_ms.argtypes = [c_void_p, c_void_p]
 
 
 def tensor_table(state_dict):

@@ -328,5 +328,8 @@ int ytk_parseq_forward_f32(ytk_parseq* h, const float* images, int images_on_dev
 
 double ytk_parseq_last_flops(ytk_parseq* h) { return h->engine.flops; }
 int ytk_parseq_last_steps(ytk_parseq* h) { return h->engine.last_steps; }
+void ytk_parseq_last_phase_ms(ytk_parseq* h, float* ms4) {
+    for (int i = 0; i < 4; ++i) ms4[i] = h->engine.phase_ms[i];
+}
 
 }  // extern "C"

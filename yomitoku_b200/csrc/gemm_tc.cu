@@ -250,6 +250,34 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 if (((kFin ? (c >> 1) : c) & 1) != wset) continue;  // chunk belongs to the other warp set
                 const int col0 = tc.n0 + c * 32;
                 if (col0 >= args.Cout) break;  // warp-uniform
+                // residual prefetch: issue the coalesced global loads of every pass of this chunk before touching TMEM so
+                // that their latency overlaps the accumulator load and the bias math
+                [[maybe_unused]] uint4 rres[NPASS][4];
+                if constexpr (RESID != 0 && !kFin) {
+                    constexpr int per16r = 16 / RESZ;
+                    int ocol_r = col0, sub_r = 0;
+                    if constexpr (MODE == EPI_SHUFFLE2X) {
+                        const int cq = args.Cout >> 2;
+                        sub_r = col0 / cq;
+                        ocol_r = col0 - sub_r * cq;
+                    }
+#pragma unroll
+                    for (int p = 0; p < NPASS; ++p) {
+                        const int validr = min(CPP, args.Cout - (col0 + p * CPP));
+                        const int e0 = piece * per16r;
+#pragma unroll
+                        for (int it = 0; it < 4; ++it) {
+                            rres[p][it] = make_uint4(0, 0, 0, 0);
+                            if (c_ok[it] && e0 + per16r <= validr) {
+                                const long long pixr =
+                                    (static_cast<long long>(tc.img) * args.Ho + c_h[it]) * args.Wo + c_w[it];
+                                const char* gp = reinterpret_cast<const char*>(args.resid) +
+                                                 (pixr * args.ldr + ocol_r + p * CPP + e0) * RESZ;
+                                rres[p][it] = *reinterpret_cast<const uint4*>(gp);
+                            }
+                        }
+                    }
+                }
                 uint32_t v[32];
                 tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), v);
                 tmem_ld_wait();
@@ -329,19 +357,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                 for (int it = 0; it < 4; ++it) {
                                     const int rr = it * 8 + (lane >> 2);
                                     uint8_t* sp = stage + rr * kStagePitch + piece * 16;
-                                    uint4 val = make_uint4(0, 0, 0, 0);
-                                    if (c_ok[it] && e0 < valid) {
+                                    *reinterpret_cast<uint4*>(sp) = rres[p][it];  // prefetched (zero when masked)
+                                    if (c_ok[it] && e0 < valid && e0 + per16 > valid) {
+                                        // ragged last columns: element-wise into the staging row
                                         const char* gp = reinterpret_cast<const char*>(args.resid) +
                                                          (c_pix[it] * args.ldr + pc0 + e0) * RESZ;
-                                        if (e0 + per16 <= valid) {
-                                            val = *reinterpret_cast<const uint4*>(gp);
-                                            *reinterpret_cast<uint4*>(sp) = val;
-                                        } else {  // ragged last columns: element-wise into the staging row
-                                            *reinterpret_cast<uint4*>(sp) = val;
-                                            copy_elems(sp, gp, valid - e0, RESZ);
-                                        }
-                                    } else {
-                                        *reinterpret_cast<uint4*>(sp) = val;
+                                        copy_elems(sp, gp, valid - e0, RESZ);
                                     }
                                 }
                                 __syncwarp();

@@ -269,12 +269,16 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
     ar.n_active = ar.group_len + cap_groups;
     ar.step = ar.n_active + 1;
     if (!host_flag) CK(cudaMallocHost(reinterpret_cast<void**>(&host_flag), 2 * sizeof(int)));
+    for (int i = 0; i < 5; ++i)
+        if (!ev[i]) CK(cudaEventCreate(&ev[i]));
     return 0;
 }
 
 ParseqEngine::~ParseqEngine() {
     for (void* p : bufs) cudaFree(p);
     if (host_flag) cudaFreeHost(host_flag);
+    for (int i = 0; i < 5; ++i)
+        if (ev[i]) cudaEventDestroy(ev[i]);
 }
 
 namespace {
@@ -355,6 +359,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     // the host vectors above must outlive the async copies
     CK(cudaStreamSynchronize(st));
     // ---------------- encoder (reference Encoder.forward, parseq_transformer.py:206-234)
+    CK(cudaEventRecord(ev[0], st));
     const int Ti = (int)T;
     if (Lin::run(A_patch, m->Kpatch, Ti, m->patch, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
     const int hd_e = D / c.enc_heads;
@@ -379,6 +384,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     // memory K/V once (the reference re-projects it in every AR step)
     if (Lin::run(mem, D, Ti, m->cross_kv, memkv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
     // ---------------- AR decode (reference parseq.py:192-252)
+    CK(cudaEventRecord(ev[1], st));
     CK(cudaMemsetAsync(ar_block, 0, 4 * (size_t)(2 * R + 3 * B + cap_groups + 2), st));
     if (launch_fill_i32(ar.tgt, pad_id, R, st)) return 1;
     if (launch_fill_i32(ar.rep_cut, -1, B, st)) return 1;
@@ -458,6 +464,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         }
     }
     last_steps = steps_run;
+    CK(cudaEventRecord(ev[2], st));
     for (const CropDesc& d : b.descs) flops += 4.0 * d.ntok * (double)D * steps_run;  // cross attention
     if (c.refine_iters == 0) {
         if (launch_apply_rep_cut(ar.rep_cut, B, S, C, eos, ids, probs, st)) return 1;
@@ -494,10 +501,13 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             }
         }
     }
+    CK(cudaEventRecord(ev[3], st));
     CK(cudaMemcpyAsync(ids_out, ids, 4 * (size_t)R, cudaMemcpyDeviceToHost, st));
     CK(cudaMemcpyAsync(probs_out, probs, 4 * (size_t)R, cudaMemcpyDeviceToHost, st));
     if (group_len_out) CK(cudaMemcpyAsync(group_len_out, ar.group_len, 4 * (size_t)b.ngroups, cudaMemcpyDeviceToHost, st));
+    CK(cudaEventRecord(ev[4], st));
     CK(cudaStreamSynchronize(st));
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&phase_ms[i], ev[i], ev[i + 1]);
     return 0;
 }
 

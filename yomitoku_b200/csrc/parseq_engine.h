@@ -89,6 +89,8 @@ struct ParseqEngine {
     int* host_flag = nullptr; // pinned: [n_active, step]
     double flops = 0;         // algorithmic FLOPs of the last forward (GEMMs + attention)
     int last_steps = 0;
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, encoder, AR, refine, end
+    float phase_ms[4] = {0, 0, 0, 0};  // encoder, AR decode, refinement, output copies of the last forward
 
     int ensure(long long tok, int rows, long long crop_bytes, int groups);
     // Runs encoder + AR decode + refinement.  Outputs (host): ids [rows*S], probs [rows*S], group_len [ngroups];

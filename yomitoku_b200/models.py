@@ -390,3 +390,9 @@ class PARSeq(_DeviceModel):
 
     def last_flops(self):
         return _lib.lib().ytk_parseq_last_flops(self._ensure())
+
+    def last_phase_ms(self):
+        """CUDA-event times of the last forward: dict(encoder, ar, refine, copy) in ms."""
+        a = (ctypes.c_float * 4)()
+        _lib.lib().ytk_parseq_last_phase_ms(self._ensure(), a)
+        return dict(zip(("encoder", "ar", "refine", "copy"), [float(v) for v in a]))

@@ -61,8 +61,20 @@ class BatchedOCR:
         if self._pool is None and self.workers > 1:
             import multiprocessing as mp
             r = self.recognizer
+            # forkserver: workers descend from a clean server process, never from this CUDA-initialised,
+            # multi-threaded one (forking that is undefined behaviour for the CUDA runtime and OpenCV's thread pool)
+            import sys
+            mf = getattr(sys.modules.get("__main__"), "__file__", None)
+            if mf is None or os.path.exists(mf):
+                ctx = mp.get_context("forkserver")
+                try:
+                    ctx.set_forkserver_preload(["yomitoku_b200.pipeline"])
+                except Exception:
+                    pass
+            else:  # `python -` / `python -c`: the spawn machinery cannot re-import __main__
+                ctx = mp.get_context("fork")
             self._pool = ProcessPoolExecutor(
-                max_workers=self.workers, mp_context=mp.get_context("fork"), initializer=_worker_init,
+                max_workers=self.workers, mp_context=ctx, initializer=_worker_init,
                 initargs=(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale))
         return self._pool
 
