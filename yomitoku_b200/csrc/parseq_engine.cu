@@ -258,7 +258,8 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
     DM(kpad, 4 * B);
     DM(ids, 4 * R);
     DM(probs, 4 * R);
-    DM(ar_block, 4 * (2 * R + 3 * B + cap_groups + 2));
+    ar_block_ints = (size_t)(2 * R + 3 * B + cap_groups + 2);
+    DM(ar_block, 4 * ar_block_ints);
 #undef DM
     ar.tgt = ar_block;
     ar.raw = ar.tgt + R;
@@ -385,7 +386,8 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     if (Lin::run(mem, D, Ti, m->cross_kv, memkv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
     // ---------------- AR decode (reference parseq.py:192-252)
     CK(cudaEventRecord(ev[1], st));
-    CK(cudaMemsetAsync(ar_block, 0, 4 * (size_t)(2 * R + 3 * B + cap_groups + 2), st));
+    // the ArState arrays live at capacity-based offsets: clear the whole block, not just the first rows
+    CK(cudaMemsetAsync(ar_block, 0, 4 * ar_block_ints, st));
     if (launch_fill_i32(ar.tgt, pad_id, R, st)) return 1;
     if (launch_fill_i32(ar.rep_cut, -1, B, st)) return 1;
     {

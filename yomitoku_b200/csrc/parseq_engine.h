@@ -86,6 +86,7 @@ struct ParseqEngine {
     float* probs = nullptr;
     ArState ar{};
     int* ar_block = nullptr;  // backing store of the ArState arrays
+    size_t ar_block_ints = 0;
     int* host_flag = nullptr; // pinned: [n_active, step]
     double flops = 0;         // algorithmic FLOPs of the last forward (GEMMs + attention)
     int last_steps = 0;
