@@ -67,12 +67,19 @@ __device__ __noinline__ void copy_elems(void* dst, const void* src, int n, int e
     else
         for (int e = 0; e < n; ++e) reinterpret_cast<uint16_t*>(dst)[e] = reinterpret_cast<const uint16_t*>(src)[e];
 }
-// exact-erf GELU / sigmoid: kept out of line so the fully unrolled epilogue stays small (instruction cache)
-__device__ __noinline__ float act_slow(float x, int act) {
-    if (act == ACT_GELU) return 0.5f * x * (1.f + erff(x * 0.70710678118654752440f));
-    return 1.f / (1.f + __expf(-x));
+// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) (torch.nn.GELU default, "exact") with erf from Abramowitz-Stegun 7.1.26
+// (|error| < 1.5e-7, i.e. below fp32 rounding of the surrounding arithmetic): one ex2 + one rcp + 7 FMAs, small
+// enough to inline 32x into the epilogue without blowing the instruction cache the way erff() does.
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float erf_abs = 1.f - poly * t * __expf(-z * z);
+    return 0.5f * x * (1.f + copysignf(erf_abs, x));
 }
-
 struct TileCoord {
     int img, h0, w0, n0;
 };
@@ -394,9 +401,13 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             if (args.act == ACT_RELU) {
 #pragma unroll
                                 for (int j = 0; j < CPP; ++j) f[p * CPP + j] = fmaxf(f[p * CPP + j], 0.f);
-                            } else if (args.act != ACT_NONE) {
+                            } else if (args.act == ACT_GELU) {
 #pragma unroll
-                                for (int j = 0; j < CPP; ++j) f[p * CPP + j] = act_slow(f[p * CPP + j], args.act);
+                                for (int j = 0; j < CPP; ++j) f[p * CPP + j] = gelu_fast(f[p * CPP + j]);
+                            } else if (args.act == ACT_SIGMOID) {
+#pragma unroll
+                                for (int j = 0; j < CPP; ++j)
+                                    f[p * CPP + j] = __fdividef(1.f, 1.f + __expf(-f[p * CPP + j]));
                             }
                             if constexpr (OUT_F32) {
                                 float4* wp = reinterpret_cast<float4*>(my_row);
@@ -534,6 +545,12 @@ static int pick_bw_log2(int Ho, int Wo) {
 static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout, const Epilogue& e) {
     GemmArgs& a = plan->args;
     plan->block_n = pick_block_n(Cout);
+    if (e.mode != EPI_CONVT_FINAL) {
+        // small problems (decode steps, coarse feature maps): shrink the N tile until the persistent grid fills the SMs
+        const int m_tiles = a.n_img * a.tiles_h * a.tiles_w;
+        while (plan->block_n > 64 && m_tiles * ((Cout + plan->block_n - 1) / plan->block_n) < num_sms())
+            plan->block_n >>= 1;
+    }
     a.tiles_n = (Cout + plan->block_n - 1) / plan->block_n;
     a.Cout = Cout;
     a.bias = e.bias;

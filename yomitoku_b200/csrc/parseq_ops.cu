@@ -90,66 +90,77 @@ int launch_patchify_f32(const float* images, int B, int W, int ph, int pw, int K
 
 // =================================================================================================== LayerNorm
 // One warp per row, fp32 statistics (two-pass over registers), bf16 (and optional fp32) output.
-constexpr int kLnMaxPerLane = 32;  // D <= 1024
+constexpr int kLnVec = 8;  // float4 per lane: D <= 1024, D % 4 == 0
 
-__global__ void layernorm_kernel(float* __restrict__ x, int M, int D, const float* __restrict__ gamma,
-                                 const float* __restrict__ beta, float eps, __nv_bfloat16* __restrict__ out_bf16,
-                                 float* __restrict__ out_f32, const float* __restrict__ addvec, int period,
-                                 const int* __restrict__ add_row0_dev, int add_row0, int writeback) {
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, int M, int D,
+                                                        const float* __restrict__ gamma,
+                                                        const float* __restrict__ beta, float eps,
+                                                        __nv_bfloat16* __restrict__ out_bf16,
+                                                        float* __restrict__ out_f32, const float* __restrict__ addvec,
+                                                        int period, const int* __restrict__ add_row0_dev,
+                                                        int add_row0, int writeback) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= M) return;
-    float* xr = x + (long long)warp * D;
-    const int per = (D + 31) / 32;
-    float v[kLnMaxPerLane];
-    const float* av = nullptr;
+    const int nvec = D >> 2;
+    float4* xr = reinterpret_cast<float4*>(x + (long long)warp * D);
+    float4 v[kLnVec];
+    // phase 1: all loads in flight at once (16 B per lane, 512 B contiguous per warp instruction)
+#pragma unroll
+    for (int i = 0; i < kLnVec; ++i) {
+        const int j = lane + 32 * i;
+        v[i] = (j < nvec) ? xr[j] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
     if (addvec != nullptr) {
         const int r0 = add_row0_dev ? *add_row0_dev : add_row0;
-        av = addvec + (long long)((warp % period) + r0) * D;
+        const float4* av = reinterpret_cast<const float4*>(addvec + (long long)((warp % period) + r0) * D);
+#pragma unroll
+        for (int i = 0; i < kLnVec; ++i) {
+            const int j = lane + 32 * i;
+            if (j < nvec) {
+                const float4 a = __ldg(av + j);
+                v[i].x += a.x; v[i].y += a.y; v[i].z += a.z; v[i].w += a.w;
+                if (writeback) xr[j] = v[i];
+            }
+        }
     }
     float s = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        if (i < per) {
-            const int j = lane + 32 * i;
-            float t = 0.f;
-            if (j < D) {
-                t = xr[j];
-                if (av) {
-                    t += av[j];
-                    if (writeback) xr[j] = t;
-                }
-            }
-            v[i] = t;
-            s += t;
-        }
-    }
+    for (int i = 0; i < kLnVec; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     const float mean = s / (float)D;
     float q = 0.f;
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        if (i < per) {
-            const int j = lane + 32 * i;
-            if (j < D) {
-                const float dlt = v[i] - mean;
-                q += dlt * dlt;
-            }
+    for (int i = 0; i < kLnVec; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+            q += (a * a + b * b) + (c * c + d * d);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
     const float rstd = rsqrtf(q / (float)D + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
-    for (int i = 0; i < kLnMaxPerLane; ++i) {
-        if (i < per) {
-            const int j = lane + 32 * i;
-            if (j < D) {
-                const float y = (v[i] - mean) * rstd * gamma[j] + beta[j];
-                if (out_bf16) out_bf16[(long long)warp * D + j] = __float2bfloat16(y);
-                if (out_f32) out_f32[(long long)warp * D + j] = y;
+    for (int i = 0; i < kLnVec; ++i) {
+        const int j = lane + 32 * i;
+        if (j < nvec) {
+            const float4 g = __ldg(g4 + j), b = __ldg(b4 + j);
+            float4 y;
+            y.x = (v[i].x - mean) * rstd * g.x + b.x;
+            y.y = (v[i].y - mean) * rstd * g.y + b.y;
+            y.z = (v[i].z - mean) * rstd * g.z + b.z;
+            y.w = (v[i].w - mean) * rstd * g.w + b.w;
+            if (out_bf16) {
+                uint2 o;
+                o.x = pack_bf16(y.x, y.y);
+                o.y = pack_bf16(y.z, y.w);
+                reinterpret_cast<uint2*>(out_bf16 + (long long)warp * D)[j] = o;
             }
+            if (out_f32) reinterpret_cast<float4*>(out_f32 + (long long)warp * D)[j] = y;
         }
     }
 }
@@ -157,8 +168,8 @@ __global__ void layernorm_kernel(float* __restrict__ x, int M, int D, const floa
 int launch_layernorm(float* x, int M, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
                      float* out_f32, const float* addvec, int period, const int* add_row0_dev, int add_row0,
                      int writeback, cudaStream_t st) {
-    if (D > 32 * kLnMaxPerLane) {
-        set_error("layernorm: D=%d too large", D);
+    if (D > 128 * kLnVec || (D & 3) != 0) {
+        set_error("layernorm: D=%d unsupported (multiple of 4, <= %d)", D, 128 * kLnVec);
         return 1;
     }
     if (M <= 0) return 0;
@@ -453,12 +464,91 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const __nv_bfloat16*
     }
 }
 
+// AR step: ONE query per row.  One warp per (row, head): lanes split the <= 101 cached keys for the scores, then split
+// the head dimension for the value sum.  Every access is a whole 32-byte sector of the K/V cache.
+__global__ void __launch_bounds__(128) dec_self_attn_ar_kernel(const __nv_bfloat16* __restrict__ q_shared,
+                                                               const __nv_bfloat16* __restrict__ ckv, int B, int D,
+                                                               int heads, int hd, const int* __restrict__ step_dev,
+                                                               __nv_bfloat16* __restrict__ out) {
+    __shared__ float sQ[4][kMaxHd];
+    __shared__ float sP[4][kMaxS + 3];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 4 + warp;
+    if (wid >= B * heads) return;
+    const int row = wid / heads, head = wid - row * heads;
+    const int i = *step_dev;
+    const int nk = i + 1;
+    for (int d = lane; d < hd; d += 32) sQ[warp][d] = __bfloat162float(q_shared[(long long)i * D + head * hd + d]);
+    __syncwarp();
+    const float scale = rsqrtf((float)hd);
+    float sc[4];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int j = lane + 32 * t;
+        float s = -INFINITY;
+        if (j < nk) {
+            const uint4* kp = reinterpret_cast<const uint4*>(ckv + ((long long)j * B + row) * (2 * D) + head * hd);
+            s = 0.f;
+            for (int c = 0; c < hd / 8; ++c) {
+                const uint4 u = __ldg(kp + c);
+                const float* qv = &sQ[warp][c * 8];
+                s += qv[0] * bf16_lo(u.x) + qv[1] * bf16_hi(u.x) + qv[2] * bf16_lo(u.y) + qv[3] * bf16_hi(u.y) +
+                     qv[4] * bf16_lo(u.z) + qv[5] * bf16_hi(u.z) + qv[6] * bf16_lo(u.w) + qv[7] * bf16_hi(u.w);
+            }
+            s *= scale;
+        }
+        sc[t] = s;
+        mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+        const int j = lane + 32 * t;
+        if (j < nk) {
+            const float p = __expf(sc[t] - mx);
+            sP[warp][j] = p;
+            sum += p;
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    const float inv = 1.f / sum;
+    float acc[3] = {0.f, 0.f, 0.f};  // hd <= 96
+    const __nv_bfloat16* vbase = ckv + (long long)row * (2 * D) + D + head * hd;
+    for (int j = 0; j < nk; ++j) {
+        const float p = sP[warp][j];
+        const __nv_bfloat16* vp = vbase + (long long)j * B * (2 * D);
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const int d = lane + 32 * t;
+            if (d < hd) acc[t] += p * __bfloat162float(vp[d]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 3; ++t) {
+        const int d = lane + 32 * t;
+        if (d < hd) out[(long long)row * D + head * hd + d] = __float2bfloat16(acc[t] * inv);
+    }
+}
+
 int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, int heads, int mode, const int* step_dev,
                          const int* klen, const int* kpad, void* out, cudaStream_t st) {
     const int hd = D / heads;
-    if (hd > kMaxHd) {
-        set_error("decoder self-attention: head dim %d > %d", hd, kMaxHd);
+    if (hd > kMaxHd || (hd % 8) != 0) {
+        set_error("decoder self-attention: head dim %d unsupported", hd);
         return 1;
+    }
+    if (mode == 0) {
+        const int warps = B * heads;
+        dec_self_attn_ar_kernel<<<(warps + 3) / 4, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(q_shared),
+                                                                 reinterpret_cast<const __nv_bfloat16*>(ckv), B, D, heads,
+                                                                 hd, step_dev, reinterpret_cast<__nv_bfloat16*>(out));
+        count_launch();
+        return cudaGetLastError() != cudaSuccess;
     }
     dim3 grid(B, heads);
     const int smem = (2 * kMaxS * (hd + 1) + 4 * (kMaxS + 3) + 4 * hd) * (int)sizeof(float);
@@ -472,8 +562,8 @@ int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, in
         attr_set = true;
     }
     dec_self_attn_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(q_shared),
-                                               reinterpret_cast<const __nv_bfloat16*>(ckv), B, D, hd, mode, step_dev,
-                                               klen, kpad, reinterpret_cast<__nv_bfloat16*>(out));
+                                                  reinterpret_cast<const __nv_bfloat16*>(ckv), B, D, hd, mode, step_dev,
+                                                  klen, kpad, reinterpret_cast<__nv_bfloat16*>(out));
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }

@@ -36,6 +36,8 @@ def _worker_init(post_kwargs, rec_cfg, dynamic_width, source_downscale):
 def _host_stage(args):
     """Post-process one probability map and cut that page's crops (runs in a worker process)."""
     page, prob, quads_override = args
+    if not isinstance(prob, np.ndarray):
+        prob = prob.numpy()          # shared-memory torch tensor (zero-copy view)
     if quads_override is None:
         quads, scores = _W["post"]({"binary": prob[None, None]}, page.shape[:2])
     else:
@@ -55,6 +57,8 @@ class BatchedOCR:
         self.max_tokens = max_tokens
         self.workers = workers if workers is not None else max(1, min(32, (os.cpu_count() or 2) - 2))
         self._pool = None
+        self._prob_ring = {}
+        self._prob_next = {}
 
     # ------------------------------------------------------------------------------------------ host pool
     def _get_pool(self):
@@ -92,14 +96,39 @@ class BatchedOCR:
         return list(pool.map(_host_stage, jobs, chunksize=1))
 
     # ------------------------------------------------------------------------------------------ stages
-    def detect_prob(self, pages):
-        """Device stage 1: probability maps (n, Hn, Wn) float32 (host) for same-size pages."""
-        out = []
+    def _shared_prob_buffer(self, n, hn, wn):
+        """Host buffer for n probability maps that (a) lives in shared memory, so worker processes receive a handle
+        instead of a 7.6 MB pickle per page, and (b) is page-locked, so the D2H copy is a plain async DMA.  A small ring
+        of buffers lets `submit` run ahead of `collect`."""
+        import torch
+        key = (n, hn, wn)
+        ring = self._prob_ring.setdefault(key, [])
+        if len(ring) < 3:
+            t = torch.empty((n, hn, wn), dtype=torch.float32).share_memory_()
+            if torch.cuda.is_available():
+                err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 4, 0)
+                if int(err) != 0:
+                    raise RuntimeError("cudaHostRegister failed: %s" % err)
+            ring.append(t)
+            return t
+        self._prob_next[key] = (self._prob_next.get(key, -1) + 1) % len(ring)
+        return ring[self._prob_next[key]]
+
+    def detect_prob(self, pages, shared=False):
+        """Device stage 1: probability maps (n, Hn, Wn) float32 (host) for same-size pages (numpy array, or a shared
+        pinned torch tensor when `shared`)."""
+        import torch
+        h0, w0 = pages[0].shape[:2]
+        hn, wn = self.detector.model.input_size(h0, w0)
+        if shared and hn <= h0 and wn <= w0:
+            out = self._shared_prob_buffer(len(pages), hn, wn)
+        else:
+            out = torch.empty((len(pages), hn, wn), dtype=torch.float32)
         for s in range(0, len(pages), self.det_batch):
-            arr = np.stack([np.ascontiguousarray(p) for p in pages[s:s + self.det_batch]])
-            prob = self.detector.model.detect_pages_u8(arr)
-            out.append(prob.cpu().numpy() if prob.is_cuda else prob.numpy())
-        return np.concatenate(out, axis=0)
+            e = min(len(pages), s + self.det_batch)
+            arr = np.stack([np.ascontiguousarray(p) for p in pages[s:e]])
+            self.detector.model.detect_pages_u8(arr, out=out[s:e])
+        return out if shared else out.numpy()
 
     def _run_groups_local(self, groups):
         """groups: list of (canvases, padded_widths).  One packed device call per <= max_tokens chunk (chunks end on
@@ -192,16 +221,26 @@ class BatchedOCR:
         return out
 
     # ------------------------------------------------------------------------------------------ whole path
-    def __call__(self, pages, prob_override=None, quads_override=None):
-        """pages: list of same-size BGR uint8 arrays.  prob_override / quads_override (benchmarks with random
-        detector weights): the detector still runs, but post-processing sees the given probability maps / the
-        recognizer the given quads."""
-        prob = self.detect_prob(pages)
+    def submit(self, pages, prob_override=None, quads_override=None):
+        """Stage 1 (device, synchronous: a few ms per page) + hand the host stage to the worker pool.  Returns a handle
+        for `collect`.  Submitting batch i+1 before collecting batch i overlaps its host stage (contours, unclip, crop
+        extraction) with the recognition of batch i on the GPU."""
+        pool = self._get_pool()
+        prob = self.detect_prob(pages, shared=pool is not None)
         jobs = []
         for i, p in enumerate(pages):
             pm = prob[i] if prob_override is None else prob_override[i]
             jobs.append((p, pm, None if quads_override is None else quads_override[i]))
-        host = self._host_map(jobs)
+        if pool is None:
+            r = self.recognizer
+            _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
+            return [_Done(_host_stage(j)) for j in jobs]
+        return [pool.submit(_host_stage, j) for j in jobs]
+
+    def collect(self, handle):
+        """Waits for the host stage of a submitted batch, recognises all its crops in one packed device call and
+        assembles per-page OCRSchema results."""
+        host = [f.result() for f in handle]
         rec_in = [(h[2], h[3], len(h[0])) for h in host]
         rec_out = self.recognize_pooled(rec_in)
         results = []
@@ -219,3 +258,17 @@ class BatchedOCR:
                 rec = TextRecognizerSchema(contents=p, directions=d, scores=s, points=quads)
             results.append(OCRSchema(words=ocr_aggregate(det, rec)))
         return results
+
+    def __call__(self, pages, prob_override=None, quads_override=None):
+        """pages: list of same-size BGR uint8 arrays.  prob_override / quads_override (benchmarks with random
+        detector weights): the detector still runs, but post-processing sees the given probability maps / the
+        recognizer the given quads."""
+        return self.collect(self.submit(pages, prob_override, quads_override))
+
+
+class _Done:
+    def __init__(self, value):
+        self._v = value
+
+    def result(self):
+        return self._v
