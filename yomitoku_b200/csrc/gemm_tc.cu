@@ -8,6 +8,7 @@
 #include "gemm_tc.h"
 
 #include <cstdarg>
+#include <cstdlib>
 #include <cstdio>
 #include <cstring>
 #include <atomic>
@@ -545,7 +546,8 @@ static int pick_bw_log2(int Ho, int Wo) {
 static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout, const Epilogue& e) {
     GemmArgs& a = plan->args;
     plan->block_n = pick_block_n(Cout);
-    if (e.mode != EPI_CONVT_FINAL) {
+    static const bool no_shrink = getenv("YTK_NO_SHRINK") != nullptr;  // debugging aid
+    if (e.mode != EPI_CONVT_FINAL && !no_shrink) {
         // small problems (decode steps, coarse feature maps): shrink the N tile until the persistent grid fills the SMs
         const int m_tiles = a.n_img * a.tiles_h * a.tiles_w;
         while (plan->block_n > 64 && m_tiles * ((Cout + plan->block_n - 1) / plan->block_n) < num_sms())

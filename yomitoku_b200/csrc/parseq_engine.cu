@@ -233,6 +233,7 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
     DM(descs_dev, sizeof(CropDesc) * B);
     DM(seqs_enc, sizeof(SeqDesc) * B);
     DM(seqs_ref, sizeof(SeqDesc) * B);
+    DM(seqs_self, sizeof(SeqDesc) * B);
     DM(A_patch, T * m->Kpatch * 2);
     DM(x, T * D * 4);
     DM(h, T * D * 2);
@@ -330,8 +331,11 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     std::vector<SeqDesc> se(B), sr(B);
     std::vector<int> rg(B);
     for (int i = 0; i < B; ++i) {
-        se[i] = SeqDesc{b.descs[i].tok_off, b.descs[i].ntok, b.descs[i].tok_off, b.descs[i].ntok};
-        sr[i] = SeqDesc{i * S, S, b.descs[i].tok_off, b.descs[i].ntok};
+        const CropDesc& cd = b.descs[i];
+        // encoder self-attention: q, k, v are column blocks of the packed qkv matrix (row stride 3D)
+        se[i] = SeqDesc{cd.tok_off, cd.ntok, cd.tok_off, cd.ntok, (long long)cd.tok_off * 3 * D, cd.ntok, 0};
+        // refinement cross-attention: queries = the row's 101 positions, keys = its encoder memory (row stride 2D)
+        sr[i] = SeqDesc{i * S, S, i * S, cd.ntok, (long long)cd.tok_off * 2 * D, cd.ntok, 0};
         rg[i] = b.descs[i].group;
     }
     CK(cudaMemcpyAsync(descs_dev, b.descs.data(), sizeof(CropDesc) * B, cudaMemcpyHostToDevice, st));
@@ -369,7 +373,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         if (Lin::run(h, D, Ti, bk.qkv, qkv, 3 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
         const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
         if (launch_flash_attention(q, 3 * D, q + D, q + 2 * D, 3 * D, att, D, seqs_enc, B, max_ntok, c.enc_heads, hd_e,
-                                   st))
+                                   0, st))
             return 1;
         if (Lin::run(att, D, Ti, bk.proj, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
         if (launch_layernorm(x, Ti, D, bk.ln2.g, bk.ln2.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
@@ -476,13 +480,20 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
                                 m->norm_c.b, cin, klen, kpad, st))
             return 1;
         if (Lin::run(cin, D, R, m->self_kv, ckv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
-        if (launch_dec_self_attn(m->q_self, ckv, B, D, c.dec_heads, 1, nullptr, klen, kpad, sa, st)) return 1;
+        // masked tensor-core attention: 101 shared queries x the row's content keys (cache layout [pos][row][2D])
+        if (launch_refine_seqs(klen, kpad, B, S, D, seqs_self, st)) return 1;
+        {
+            const __nv_bfloat16* ck = reinterpret_cast<const __nv_bfloat16*>(ckv);
+            if (launch_flash_attention(m->q_self, D, ck, ck + D, (long long)B * 2 * D, sa, D, seqs_self, B, S,
+                                       c.dec_heads, hd_d, 1, st))
+                return 1;
+        }
         if (Lin::run(sa, D, R, m->self_out, x1, D, 1, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
         if (launch_layernorm(x1, R, D, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, S, nullptr, 0, 1, st))
             return 1;
         if (Lin::run(hb, D, R, m->cross_q, qc, D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
         const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(memkv);
-        if (launch_flash_attention(qc, D, kv, kv + D, 2 * D, oc, D, seqs_ref, B, S, c.dec_heads, hd_d, st)) return 1;
+        if (launch_flash_attention(qc, D, kv, kv + D, 2 * D, oc, D, seqs_ref, B, S, c.dec_heads, hd_d, 0, st)) return 1;
         for (const CropDesc& d : b.descs) flops += 4.0 * S * (double)d.ntok * D;
         if (Lin::run(oc, D, R, m->cross_out, x1, D, 1, ACT_NONE, x1, 1, D, st, &flops)) return 1;
         if (launch_layernorm(x1, R, D, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))

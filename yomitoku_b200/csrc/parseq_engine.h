@@ -74,6 +74,7 @@ struct ParseqEngine {
     CropDesc* descs_dev = nullptr;
     SeqDesc* seqs_enc = nullptr;
     SeqDesc* seqs_ref = nullptr;
+    SeqDesc* seqs_self = nullptr;
     void *A_patch = nullptr, *h = nullptr, *qkv = nullptr, *att = nullptr, *mlp = nullptr, *mem = nullptr,
          *memkv = nullptr;
     float* x = nullptr;

@@ -4,6 +4,7 @@
 #include "parseq_ops.h"
 
 #include <cfloat>
+#include <cstdlib>
 
 #include "gemm_tc.h"
 #include "ptx.cuh"
@@ -211,7 +212,7 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
-template <int HD>
+template <int HD, int MASKED>
 __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq,
                                                          const __nv_bfloat16* __restrict__ K,
                                                          const __nv_bfloat16* __restrict__ V, long long ldkv,
@@ -246,7 +247,7 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
         for (int i = threadIdx.x; i < 64 * CH; i += 128) {
             const int r = i / CH, c = i - r * CH;
             const bool ok = (k0 + r) < sd.k_len;
-            const long long rowi = (long long)(sd.k_off + (ok ? k0 + r : 0)) * ldkv + head * HD + c * 8;
+            const long long rowi = sd.k_base + (long long)(ok ? k0 + r : 0) * ldkv + head * HD + c * 8;
             cp_async16(smem_u32(&sK[r * LDS + c * 8]), K + rowi, ok);
             cp_async16(smem_u32(&sV[r * LDS + c * 8]), V + rowi, ok);
         }
@@ -285,7 +286,12 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int key = k0 + n * 8 + (lane & 3) * 2 + (e & 1);
-                const float val = (key < sd.k_len) ? s[n][e] * scale_log2 : -INFINITY;
+                bool vis = key < sd.k_len;
+                if (MASKED) {
+                    const int qi = q0 + warp * 16 + (lane >> 2) + (e >> 1) * 8;
+                    vis = vis && ((qi < 2) || (key <= qi)) && (key < sd.kpad);
+                }
+                const float val = vis ? s[n][e] * scale_log2 : -INFINITY;
                 s[n][e] = val;
                 mx[e >> 1] = fmaxf(mx[e >> 1], val);
             }
@@ -355,7 +361,7 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
         const int r = r0 + h * 8;
         if (r < sd.q_len) {
             const float inv = 1.f / l_run[h];
-            __nv_bfloat16* op = O + (long long)(sd.q_off + r) * ldo + head * HD + (lane & 3) * 2;
+            __nv_bfloat16* op = O + (long long)(sd.o_off + r) * ldo + head * HD + (lane & 3) * 2;
 #pragma unroll
             for (int i = 0; i < HD / 8; ++i) {
                 *reinterpret_cast<uint32_t*>(op + i * 8) = pack_bf16(o[i][2 * h] * inv, o[i][2 * h + 1] * inv);
@@ -366,20 +372,26 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
 
 int launch_flash_attention(const void* Q, long long ldq, const void* K, const void* V, long long ldkv, void* O,
                            long long ldo, const SeqDesc* seqs, int nseq, int max_q_len, int heads, int head_dim,
-                           cudaStream_t st) {
+                           int masked, cudaStream_t st) {
     if (nseq <= 0) return 0;
     dim3 grid((max_q_len + 63) / 64, heads, nseq);
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
     const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(Q), *k = reinterpret_cast<const __nv_bfloat16*>(K),
                         *v = reinterpret_cast<const __nv_bfloat16*>(V);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(O);
+#define YTK_FA(HD_)                                                                                          \
+    do {                                                                                                     \
+        if (masked) flash_attn_kernel<HD_, 1><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); \
+        else flash_attn_kernel<HD_, 0><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2);   \
+    } while (0)
     switch (head_dim) {
-        case 32: flash_attn_kernel<32><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); break;
-        case 48: flash_attn_kernel<48><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); break;
-        case 64: flash_attn_kernel<64><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); break;
-        case 96: flash_attn_kernel<96><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); break;
+        case 32: YTK_FA(32); break;
+        case 48: YTK_FA(48); break;
+        case 64: YTK_FA(64); break;
+        case 96: YTK_FA(96); break;
         default: set_error("flash attention: head_dim %d unsupported (32/48/64/96)", head_dim); return 1;
     }
+#undef YTK_FA
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
@@ -542,7 +554,8 @@ int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, in
         set_error("decoder self-attention: head dim %d unsupported", hd);
         return 1;
     }
-    if (mode == 0) {
+    static const bool old_ar = getenv("YTK_OLD_SELF_ATTN") != nullptr;  // debugging aid
+    if (mode == 0 && !old_ar) {
         const int warps = B * heads;
         dec_self_attn_ar_kernel<<<(warps + 3) / 4, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(q_shared),
                                                                  reinterpret_cast<const __nv_bfloat16*>(ckv), B, D, heads,
@@ -1028,6 +1041,28 @@ __global__ void apply_rep_cut_kernel(const int* __restrict__ rep_cut, int B, int
 int launch_apply_rep_cut(const int* rep_cut, int B, int S, int C, int eos_id, int* ids, float* probs,
                          cudaStream_t st) {
     apply_rep_cut_kernel<<<(B + 127) / 128, 128, 0, st>>>(rep_cut, B, S, C, eos_id, ids, probs);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
+// Per-row descriptors of the refinement self-attention: queries = the shared projected pos_queries (rows 0..S-1 of
+// q_shared), keys = this row's content K/V cache (key j at ckv[(j*B + row) * 2D]), output rows row*S ...
+__global__ void refine_seqs_kernel(const int* __restrict__ klen, const int* __restrict__ kpad, int B, int S, int D,
+                                   SeqDesc* __restrict__ seqs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= B) return;
+    SeqDesc d;
+    d.q_off = 0;
+    d.q_len = S;
+    d.o_off = r * S;
+    d.k_len = klen[r];
+    d.k_base = (long long)r * (2 * D);
+    d.kpad = kpad[r];
+    d.pad_ = 0;
+    seqs[r] = d;
+}
+int launch_refine_seqs(const int* klen, const int* kpad, int B, int S, int D, SeqDesc* seqs, cudaStream_t st) {
+    refine_seqs_kernel<<<(B + 127) / 128, 128, 0, st>>>(klen, kpad, B, S, D, seqs);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }

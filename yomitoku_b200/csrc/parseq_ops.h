@@ -31,11 +31,19 @@ int launch_layernorm(float* x, int M, int D, const float* gamma, const float* be
 
 // Flash attention over packed sequences, bf16 in/out, fp32 softmax; no mask.
 struct SeqDesc {
-    int q_off, q_len, k_off, k_len;
+    int q_off;         // first query row (rows of Q, stride ldq)
+    int q_len;
+    int o_off;         // first output row (rows of O, stride ldo)
+    int k_len;         // number of keys
+    long long k_base;  // element offset of key 0 inside K / V (key j at k_base + j * ldkv)
+    int kpad;          // masked mode: keys >= kpad are padding
+    int pad_;
 };
+// masked = 0: plain softmax(QK^T)V.  masked = 1: PARSeq refinement self-attention - key j is visible to query i iff
+// (i < 2 || j <= i) && j < kpad (reference parseq.py:267-297; rows 0 and 1 of the causal mask are cleared).
 int launch_flash_attention(const void* Q, long long ldq, const void* K, const void* V, long long ldkv, void* O,
                            long long ldo, const SeqDesc* seqs, int nseq, int max_q_len, int heads, int head_dim,
-                           cudaStream_t st);
+                           int masked, cudaStream_t st);
 
 // Decoder self-attention of the query stream against the per-row content K/V cache.
 //  q_shared: [101, D] bf16 (projected LN_q(pos_queries), identical for every row)
@@ -79,6 +87,7 @@ int launch_softmax_max(const float* logits, long long ldl, int C, int rows, int 
 int launch_bcast_rows(const void* src, void* dst, int row_bytes, int rows, cudaStream_t st);
 int launch_apply_rep_cut(const int* rep_cut, int B, int S, int C, int eos_id, int* ids, float* probs, cudaStream_t st);
 
+int launch_refine_seqs(const int* klen, const int* kpad, int B, int S, int D, SeqDesc* seqs, cudaStream_t st);
 int launch_fill_i32(int* p, int v, long long n, cudaStream_t st);
 
 }  // namespace ytk
