@@ -304,6 +304,9 @@ __global__ void asf_apply_kernel(const uint4* __restrict__ a, const float* __res
                                  const float* __restrict__ gvec, int n_img, int H, int W, const AsfW wts,
                                  uint4* __restrict__ fuse /* [pix][256 ch] in place */) {
     // 8 threads per pixel: each owns 8 channels of `a` (attention logits) and then scales 32 channels of `fuse`
+    __shared__ float s_att[4][64];  // thread-dependent indexing: shared memory, not the (serialising) constant bank
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) s_att[i >> 6][i & 63] = wts.att[i >> 6][i & 63];
+    __syncthreads();
     const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const long long pix = t >> 3;
     const int cg = (int)(t & 7);
@@ -330,7 +333,7 @@ __global__ void asf_apply_kernel(const uint4* __restrict__ a, const float* __res
         for (int j = 0; j < 8; ++j) {
             const float z = s + f[j] + __ldg(gvec + img * 64 + cg * 8 + j);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) part[k] += wts.att[k][cg * 8 + j] * z;
+            for (int k = 0; k < 4; ++k) part[k] += s_att[k][cg * 8 + j] * z;
         }
     }
 #pragma unroll

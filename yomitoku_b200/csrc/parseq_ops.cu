@@ -593,7 +593,6 @@ __global__ void __launch_bounds__(128) dec_cross_attn_kernel(const __nv_bfloat16
     __shared__ float sQ[kMaxHd];
     __shared__ float sP[kMaxMem];
     __shared__ float sRed[4];
-    __shared__ float sAcc[4][kMaxHd];
     const int row = blockIdx.x, head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const CropDesc d = descs[row];
@@ -633,26 +632,29 @@ __global__ void __launch_bounds__(128) dec_cross_attn_kernel(const __nv_bfloat16
     if (lane == 0) sRed[warp] = sum;
     __syncthreads();
     sum = sRed[0] + sRed[1] + sRed[2] + sRed[3];
-    // PV: each warp takes a quarter of the keys; lanes own output dims
-    float acc[3] = {0.f, 0.f, 0.f};  // hd <= 96 -> up to 3 dims per lane
-    for (int j = warp; j < n; j += 4) {
-        const float p = sP[j];
-        const __nv_bfloat16* vp = kbase + (long long)j * (2 * D) + D;
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int dd = lane + 32 * t;
-            if (dd < hd) acc[t] += p * __bfloat162float(vp[dd]);
+    // PV with 16-byte loads: thread = (key subset, 8-wide chunk of the head dim); partial sums meet in shared memory
+    const int nch = hd >> 3;                 // chunks per row (<= 12)
+    const int nsub = 128 / nch;              // key subsets (>= 10)
+    const int ch = threadIdx.x % nch, sub = threadIdx.x / nch;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (sub < nsub) {
+        for (int j = sub; j < n; j += nsub) {
+            const float p = sP[j];
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(kbase + (long long)j * (2 * D) + D) + ch);
+            acc[0] += p * bf16_lo(u.x); acc[1] += p * bf16_hi(u.x); acc[2] += p * bf16_lo(u.y); acc[3] += p * bf16_hi(u.y);
+            acc[4] += p * bf16_lo(u.z); acc[5] += p * bf16_hi(u.z); acc[6] += p * bf16_lo(u.w); acc[7] += p * bf16_hi(u.w);
         }
     }
+    __shared__ float red[1024];              // [nsub][hd], nsub * hd <= 128 * 8
+    if (sub < nsub) {
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        const int dd = lane + 32 * t;
-        if (dd < hd) sAcc[warp][dd] = acc[t];
+        for (int e = 0; e < 8; ++e) red[sub * hd + ch * 8 + e] = acc[e];
     }
     __syncthreads();
     for (int dd = threadIdx.x; dd < hd; dd += 128) {
-        const float v = (sAcc[0][dd] + sAcc[1][dd] + sAcc[2][dd] + sAcc[3][dd]) / sum;
-        out[(long long)row * D + head * hd + dd] = __float2bfloat16(v);
+        float v = 0.f;
+        for (int k = 0; k < nsub; ++k) v += red[k * hd + dd];
+        out[(long long)row * D + head * hd + dd] = __float2bfloat16(v / sum);
     }
 }
 
