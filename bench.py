@@ -209,7 +209,8 @@ def main():
         quads.append(q)
     Hn, Wn = det.model.input_size(1200, 1600)
     probs_syn = [synthetic_prob_map(q, (Hn, Wn), (1200, 1600)) for q in quads]
-    ocr = BatchedOCR(det, rec, det_batch=8)
+    ncpu = os.cpu_count() or 2
+    ocr = BatchedOCR(det, rec, det_batch=8, workers=max(2, min(32, (ncpu - 2 * world) // world)))
     # ---------------- device-resident inputs for `value`
     pages_dev = torch.from_numpy(np.stack(pages)).cuda()
     prob_dev = torch.empty((P, Hn, Wn), dtype=torch.float32, device="cuda")

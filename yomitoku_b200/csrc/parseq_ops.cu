@@ -478,11 +478,14 @@ __global__ void __launch_bounds__(128) dec_self_attn_kernel(const __nv_bfloat16*
 
 // AR step: ONE query per row.  One warp per (row, head): lanes split the <= 101 cached keys for the scores, then split
 // the head dimension for the value sum.  Every access is a whole 32-byte sector of the K/V cache.
+template <int HD>
 __global__ void __launch_bounds__(128) dec_self_attn_ar_kernel(const __nv_bfloat16* __restrict__ q_shared,
                                                                const __nv_bfloat16* __restrict__ ckv, int B, int D,
-                                                               int heads, int hd, const int* __restrict__ step_dev,
+                                                               int heads, const int* __restrict__ step_dev,
                                                                __nv_bfloat16* __restrict__ out) {
-    __shared__ float sQ[4][kMaxHd];
+    constexpr int NCH = HD / 8;        // 16-byte chunks per K/V row
+    constexpr int NSUB = 32 / NCH;     // key subsets in the value phase (lanes >= NSUB*NCH idle)
+    __shared__ float sQ[4][HD];
     __shared__ float sP[4][kMaxS + 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wid = blockIdx.x * 4 + warp;
@@ -490,9 +493,9 @@ __global__ void __launch_bounds__(128) dec_self_attn_ar_kernel(const __nv_bfloat
     const int row = wid / heads, head = wid - row * heads;
     const int i = *step_dev;
     const int nk = i + 1;
-    for (int d = lane; d < hd; d += 32) sQ[warp][d] = __bfloat162float(q_shared[(long long)i * D + head * hd + d]);
+    for (int d = lane; d < HD; d += 32) sQ[warp][d] = __bfloat162float(q_shared[(long long)i * D + head * HD + d]);
     __syncwarp();
-    const float scale = rsqrtf((float)hd);
+    const float scale = rsqrtf((float)HD);
     float sc[4];
     float mx = -INFINITY;
 #pragma unroll
@@ -500,13 +503,17 @@ __global__ void __launch_bounds__(128) dec_self_attn_ar_kernel(const __nv_bfloat
         const int j = lane + 32 * t;
         float s = -INFINITY;
         if (j < nk) {
-            const uint4* kp = reinterpret_cast<const uint4*>(ckv + ((long long)j * B + row) * (2 * D) + head * hd);
+            const uint4* kp = reinterpret_cast<const uint4*>(ckv + ((long long)j * B + row) * (2 * D) + head * HD);
+            uint4 u[NCH];
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) u[c] = __ldg(kp + c);   // all loads of the row in flight together
             s = 0.f;
-            for (int c = 0; c < hd / 8; ++c) {
-                const uint4 u = __ldg(kp + c);
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
                 const float* qv = &sQ[warp][c * 8];
-                s += qv[0] * bf16_lo(u.x) + qv[1] * bf16_hi(u.x) + qv[2] * bf16_lo(u.y) + qv[3] * bf16_hi(u.y) +
-                     qv[4] * bf16_lo(u.z) + qv[5] * bf16_hi(u.z) + qv[6] * bf16_lo(u.w) + qv[7] * bf16_hi(u.w);
+                s += qv[0] * bf16_lo(u[c].x) + qv[1] * bf16_hi(u[c].x) + qv[2] * bf16_lo(u[c].y) +
+                     qv[3] * bf16_hi(u[c].y) + qv[4] * bf16_lo(u[c].z) + qv[5] * bf16_hi(u[c].z) +
+                     qv[6] * bf16_lo(u[c].w) + qv[7] * bf16_hi(u[c].w);
             }
             s *= scale;
         }
@@ -529,21 +536,35 @@ __global__ void __launch_bounds__(128) dec_self_attn_ar_kernel(const __nv_bfloat
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     __syncwarp();
     const float inv = 1.f / sum;
-    float acc[3] = {0.f, 0.f, 0.f};  // hd <= 96
-    const __nv_bfloat16* vbase = ckv + (long long)row * (2 * D) + D + head * hd;
-    for (int j = 0; j < nk; ++j) {
-        const float p = sP[warp][j];
-        const __nv_bfloat16* vp = vbase + (long long)j * B * (2 * D);
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const int d = lane + 32 * t;
-            if (d < hd) acc[t] += p * __bfloat162float(vp[d]);
+    // value phase: lane = (key subset, 16-byte chunk); partial sums of the subsets are folded with shuffles
+    const int ch = lane % NCH, sub = lane / NCH;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (sub < NSUB) {
+        const __nv_bfloat16* vbase = ckv + (long long)row * (2 * D) + D + head * HD;
+#pragma unroll 4
+        for (int j = sub; j < nk; j += NSUB) {
+            const float p = sP[warp][j];
+            const uint4 u = __ldg(reinterpret_cast<const uint4*>(vbase + (long long)j * B * (2 * D)) + ch);
+            acc[0] += p * bf16_lo(u.x); acc[1] += p * bf16_hi(u.x); acc[2] += p * bf16_lo(u.y); acc[3] += p * bf16_hi(u.y);
+            acc[4] += p * bf16_lo(u.z); acc[5] += p * bf16_hi(u.z); acc[6] += p * bf16_lo(u.w); acc[7] += p * bf16_hi(u.w);
         }
     }
 #pragma unroll
-    for (int t = 0; t < 3; ++t) {
-        const int d = lane + 32 * t;
-        if (d < hd) out[(long long)row * D + head * hd + d] = __float2bfloat16(acc[t] * inv);
+    for (int g = 1; g < NSUB; ++g) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const float o = __shfl_down_sync(0xffffffffu, acc[e], g * NCH);
+            if (sub == 0) acc[e] += (lane + g * NCH < 32) ? o : 0.f;
+        }
+    }
+    // note: the fold above adds subset g's ORIGINAL partials only into subset 0 (lanes < NCH)
+    if (lane < NCH) {
+        uint4 o;
+        o.x = pack_bf16(acc[0] * inv, acc[1] * inv);
+        o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+        o.z = pack_bf16(acc[4] * inv, acc[5] * inv);
+        o.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+        reinterpret_cast<uint4*>(out + (long long)row * D + head * HD)[lane] = o;
     }
 }
 
@@ -557,9 +578,17 @@ int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, in
     static const bool old_ar = getenv("YTK_OLD_SELF_ATTN") != nullptr;  // debugging aid
     if (mode == 0 && !old_ar) {
         const int warps = B * heads;
-        dec_self_attn_ar_kernel<<<(warps + 3) / 4, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(q_shared),
-                                                                 reinterpret_cast<const __nv_bfloat16*>(ckv), B, D, heads,
-                                                                 hd, step_dev, reinterpret_cast<__nv_bfloat16*>(out));
+        const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(q_shared),
+                            *kv = reinterpret_cast<const __nv_bfloat16*>(ckv);
+        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+        const unsigned grid = (warps + 3) / 4;
+        switch (hd) {
+            case 32: dec_self_attn_ar_kernel<32><<<grid, 128, 0, st>>>(q, kv, B, D, heads, step_dev, o); break;
+            case 48: dec_self_attn_ar_kernel<48><<<grid, 128, 0, st>>>(q, kv, B, D, heads, step_dev, o); break;
+            case 64: dec_self_attn_ar_kernel<64><<<grid, 128, 0, st>>>(q, kv, B, D, heads, step_dev, o); break;
+            case 96: dec_self_attn_ar_kernel<96><<<grid, 128, 0, st>>>(q, kv, B, D, heads, step_dev, o); break;
+            default: set_error("decoder self-attention: head dim %d unsupported (32/48/64/96)", hd); return 1;
+        }
         count_launch();
         return cudaGetLastError() != cudaSuccess;
     }
@@ -586,11 +615,13 @@ int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, in
 // K/V were projected ONCE (the reference re-projects them every step).  CTA per (row, head).
 constexpr int kMaxMem = 800;
 
+template <int HD>
 __global__ void __launch_bounds__(128) dec_cross_attn_kernel(const __nv_bfloat16* __restrict__ qc,
                                                              const __nv_bfloat16* __restrict__ memkv,
-                                                             const CropDesc* __restrict__ descs, int D, int hd,
+                                                             const CropDesc* __restrict__ descs, int D,
                                                              __nv_bfloat16* __restrict__ out) {
-    __shared__ float sQ[kMaxHd];
+    constexpr int hd = HD;
+    __shared__ float sQ[HD];
     __shared__ float sP[kMaxMem];
     __shared__ float sRed[4];
     const int row = blockIdx.x, head = blockIdx.y;
@@ -604,9 +635,13 @@ __global__ void __launch_bounds__(128) dec_cross_attn_kernel(const __nv_bfloat16
     float mx = -INFINITY;
     for (int j = threadIdx.x; j < n; j += 128) {
         const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)j * (2 * D));
+        uint4 uu[HD / 8];
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) uu[c] = __ldg(kp + c);   // the whole K row in flight at once
         float s = 0.f;
-        for (int c = 0; c < hd / 8; ++c) {
-            const uint4 u = __ldg(kp + c);
+#pragma unroll
+        for (int c = 0; c < HD / 8; ++c) {
+            const uint4 u = uu[c];
             s += sQ[c * 8 + 0] * bf16_lo(u.x) + sQ[c * 8 + 1] * bf16_hi(u.x) + sQ[c * 8 + 2] * bf16_lo(u.y) +
                  sQ[c * 8 + 3] * bf16_hi(u.y) + sQ[c * 8 + 4] * bf16_lo(u.z) + sQ[c * 8 + 5] * bf16_hi(u.z) +
                  sQ[c * 8 + 6] * bf16_lo(u.w) + sQ[c * 8 + 7] * bf16_hi(u.w);
@@ -638,6 +673,7 @@ __global__ void __launch_bounds__(128) dec_cross_attn_kernel(const __nv_bfloat16
     const int ch = threadIdx.x % nch, sub = threadIdx.x / nch;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (sub < nsub) {
+#pragma unroll 4
         for (int j = sub; j < n; j += nsub) {
             const float p = sP[j];
             const uint4 u = __ldg(reinterpret_cast<const uint4*>(kbase + (long long)j * (2 * D) + D) + ch);
@@ -666,9 +702,15 @@ int launch_dec_cross_attn(const void* qc, const void* memkv, const CropDesc* des
         return 1;
     }
     dim3 grid(B, heads);
-    dec_cross_attn_kernel<<<grid, 128, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(qc),
-                                                reinterpret_cast<const __nv_bfloat16*>(memkv), descs, D, hd,
-                                                reinterpret_cast<__nv_bfloat16*>(out));
+    const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(qc), *kv = reinterpret_cast<const __nv_bfloat16*>(memkv);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    switch (hd) {
+        case 32: dec_cross_attn_kernel<32><<<grid, 128, 0, st>>>(q, kv, descs, D, o); break;
+        case 48: dec_cross_attn_kernel<48><<<grid, 128, 0, st>>>(q, kv, descs, D, o); break;
+        case 64: dec_cross_attn_kernel<64><<<grid, 128, 0, st>>>(q, kv, descs, D, o); break;
+        case 96: dec_cross_attn_kernel<96><<<grid, 128, 0, st>>>(q, kv, descs, D, o); break;
+        default: set_error("decoder cross-attention: head dim %d unsupported (32/48/64/96)", hd); return 1;
+    }
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
