@@ -36,6 +36,8 @@ def _worker_init(post_kwargs, rec_cfg, dynamic_width, source_downscale):
 def _host_stage(args):
     """Post-process one probability map and cut that page's crops (runs in a worker process)."""
     page, prob, quads_override = args
+    if not isinstance(page, np.ndarray):
+        page = page.numpy()          # shared-memory torch tensor (zero-copy view)
     if not isinstance(prob, np.ndarray):
         prob = prob.numpy()          # shared-memory torch tensor (zero-copy view)
     if quads_override is None:
@@ -59,6 +61,7 @@ class BatchedOCR:
         self._pool = None
         self._prob_ring = {}
         self._prob_next = {}
+        self._last_pages = None
 
     # ------------------------------------------------------------------------------------------ host pool
     def _get_pool(self):
@@ -114,6 +117,23 @@ class BatchedOCR:
         self._prob_next[key] = (self._prob_next.get(key, -1) + 1) % len(ring)
         return ring[self._prob_next[key]]
 
+    def _shared_page_buffer(self, n, h, w):
+        """Shared + page-locked staging for the u8 pages of one batch: one memcpy per page replaces np.stack, the H2D
+        copy becomes an async DMA, and the workers get a handle instead of a 5.8 MB pickle per page."""
+        import torch
+        key = ("pages", n, h, w)
+        ring = self._prob_ring.setdefault(key, [])
+        if len(ring) < 3:
+            t = torch.empty((n, h, w, 3), dtype=torch.uint8).share_memory_()
+            if torch.cuda.is_available():
+                err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel(), 0)
+                if int(err) != 0:
+                    raise RuntimeError("cudaHostRegister failed: %s" % err)
+            ring.append(t)
+            return t
+        self._prob_next[key] = (self._prob_next.get(key, -1) + 1) % len(ring)
+        return ring[self._prob_next[key]]
+
     def detect_prob(self, pages, shared=False):
         """Device stage 1: probability maps (n, Hn, Wn) float32 (host) for same-size pages (numpy array, or a shared
         pinned torch tensor when `shared`)."""
@@ -124,10 +144,18 @@ class BatchedOCR:
             out = self._shared_prob_buffer(len(pages), hn, wn)
         else:
             out = torch.empty((len(pages), hn, wn), dtype=torch.float32)
+        if shared and hn <= h0 and wn <= w0:
+            stage = self._shared_page_buffer(len(pages), h0, w0)
+            sn = stage.numpy()
+            for i, p in enumerate(pages):
+                np.copyto(sn[i], p)
+            self._last_pages = stage
+        else:
+            stage = torch.from_numpy(np.stack([np.ascontiguousarray(p) for p in pages]))
+            self._last_pages = None
         for s in range(0, len(pages), self.det_batch):
             e = min(len(pages), s + self.det_batch)
-            arr = np.stack([np.ascontiguousarray(p) for p in pages[s:e]])
-            self.detector.model.detect_pages_u8(arr, out=out[s:e])
+            self.detector.model.detect_pages_u8(stage[s:e], out=out[s:e])
         return out if shared else out.numpy()
 
     def _run_groups_local(self, groups):
@@ -228,9 +256,11 @@ class BatchedOCR:
         pool = self._get_pool()
         prob = self.detect_prob(pages, shared=pool is not None)
         jobs = []
+        shared_pages = self._last_pages if pool is not None else None
         for i, p in enumerate(pages):
             pm = prob[i] if prob_override is None else prob_override[i]
-            jobs.append((p, pm, None if quads_override is None else quads_override[i]))
+            jobs.append((p if shared_pages is None else shared_pages[i], pm,
+                         None if quads_override is None else quads_override[i]))
         if pool is None:
             r = self.recognizer
             _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
@@ -245,18 +275,22 @@ class BatchedOCR:
         rec_out = self.recognize_pooled(rec_in)
         results = []
         r = self.recognizer
+        from .schemas import WordPrediction
         for (quads, scores, canv, cw, n), (ids, probs, order) in zip(host, rec_out):
-            det = TextDetectorSchema(points=quads, scores=scores)
             if n == 0:
-                rec = TextRecognizerSchema(contents=[], directions=[], scores=[], points=quads)
+                p, s, d = [], [], []
             else:
                 pts = [quads[i] for i in order] if order is not None else quads
                 p, s, d = r.postprocess_ids(ids, probs, pts[:n])
                 if order is not None:
                     inv = np.argsort(order)
                     p, s, d = [p[i] for i in inv], [s[i] for i in inv], [d[i] for i in inv]
-                rec = TextRecognizerSchema(contents=p, directions=d, scores=s, points=quads)
-            results.append(OCRSchema(words=ocr_aggregate(det, rec)))
+            # same pairing as ocr_aggregate (reference ocr.py:6-24); the values are produced by this module with
+            # the right types, so the pydantic models are built without re-validating every coordinate
+            words = [WordPrediction.model_construct(points=q, content=c, direction=dd, det_score=float(ds),
+                                                    rec_score=float(rs))
+                     for q, ds, c, rs, dd in zip(quads, scores, p, s, d)]
+            results.append(OCRSchema.model_construct(words=words))
         return results
 
     def __call__(self, pages, prob_override=None, quads_override=None):
