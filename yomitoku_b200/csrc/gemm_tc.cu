@@ -50,6 +50,7 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kStagePitch = 80;     // bytes per staged row: 64 B payload + 16 B pad (conflict-free 16 B accesses)
 constexpr int kEpiStageBytes = 8 * 32 * kStagePitch;
+constexpr bool kDirectDefault = false;  // default epilogue store path when YTK_EPI is unset
 
 template <int BLOCK_N>
 struct TileCfg {
@@ -72,15 +73,19 @@ __device__ __noinline__ void copy_elems(void* dst, const void* src, int n, int e
 // (|error| < 1.5e-7, i.e. below fp32 rounding of the surrounding arithmetic): one ex2 + one rcp + 7 FMAs, small
 // enough to inline 32x into the epilogue without blowing the instruction cache the way erff() does.
 __device__ __forceinline__ float gelu_fast(float x) {
+    // Phi(x) = x >= 0 ? 1 - h : h with h = 0.5 * poly(t) * t * exp(-z^2), z = |x| / sqrt 2, t = 1 / (1 + 0.3275911 z)
     const float z = fabsf(x) * 0.70710678118654752440f;
     const float t = __fdividef(1.f, fmaf(0.3275911f, z, 1.f));
-    float poly = fmaf(1.061405429f, t, -1.453152027f);
-    poly = fmaf(poly, t, 1.421413741f);
-    poly = fmaf(poly, t, -0.284496736f);
-    poly = fmaf(poly, t, 0.254829592f);
-    const float erf_abs = 1.f - poly * t * __expf(-z * z);
-    return 0.5f * x * (1.f + copysignf(erf_abs, x));
+    float p = fmaf(0.5307027145f, t, -0.7265760135f);
+    p = fmaf(p, t, 0.7107068705f);
+    p = fmaf(p, t, -0.142248368f);
+    p = fmaf(p, t, 0.127414796f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * (z * -1.4426950408889634f)));
+    const float h = p * t * e;
+    return x * ((x >= 0.f) ? 1.f - h : h);
 }
+
 struct TileCoord {
     int img, h0, w0, n0;
 };
@@ -101,7 +106,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& a, int tile, in
 // Epilogue variants are compile-time (OUT_F32: fp32 vs bf16 output; RESID: 0 none, 1 bf16, 2 fp32; MODE: EpiMode) so
 // that each instantiation carries only its own store path - one kernel with every path inlined is ~190 KB of SASS and
 // thrashes the instruction cache.
-template <int BLOCK_N, int OUT_F32, int RESID, int MODE>
+template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmMaps maps,
                                                               const __grid_constant__ GemmArgs args) {
     using Cfg = TileCfg<BLOCK_N>;
@@ -260,8 +265,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 if (col0 >= args.Cout) break;  // warp-uniform
                 // residual prefetch: issue the coalesced global loads of every pass of this chunk before touching TMEM so
                 // that their latency overlaps the accumulator load and the bias math
+                // DIRECT variant: the thread's own row segment (32 columns) straight from / to global memory
+                [[maybe_unused]] uint4 dres[RESID == 2 ? 8 : 4];
+                if constexpr (RESID != 0 && !kFin && DIRECT) {
+                    const long long pixo = (static_cast<long long>(tc.img) * args.Ho + hh) * args.Wo + ww;
+                    const bool fullc = row_ok && (col0 + 32 <= args.Cout);
+                    const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(args.resid) +
+                                                                     (pixo * args.ldr + col0) * RESZ);
+#pragma unroll
+                    for (int j = 0; j < (RESID == 2 ? 8 : 4); ++j) dres[j] = fullc ? gp[j] : make_uint4(0, 0, 0, 0);
+                }
                 [[maybe_unused]] uint4 rres[NPASS][4];
-                if constexpr (RESID != 0 && !kFin) {
+                if constexpr (RESID != 0 && !kFin && !DIRECT) {
                     constexpr int per16r = 16 / RESZ;
                     int ocol_r = col0, sub_r = 0;
                     if constexpr (MODE == EPI_SHUFFLE2X) {
@@ -333,6 +348,91 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                             *reinterpret_cast<float2*>(op + 4LL * args.Wo) = r1;
                         }
                         dots[0] = dots[1] = dots[2] = dots[3] = 0.f;
+                    }
+                } else if constexpr (DIRECT) {
+                    int ocol = col0, sub = 0;
+                    long long opix = (static_cast<long long>(tc.img) * args.Ho + hh) * args.Wo + ww;
+                    if constexpr (MODE == EPI_SHUFFLE2X) {
+                        const int cq = args.Cout >> 2;
+                        sub = col0 / cq;
+                        ocol = col0 - sub * cq;
+                        opix = (static_cast<long long>(tc.img) * (2 * args.Ho) + (2 * hh + (sub >> 1))) * (2LL * args.Wo) +
+                               (2 * ww + (sub & 1));
+                    }
+                    const bool fullc = (col0 + 32 <= args.Cout);
+                    if constexpr (RESID == 2) {
+                        if (fullc) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                f[4 * j + 0] += __uint_as_float(dres[j].x);
+                                f[4 * j + 1] += __uint_as_float(dres[j].y);
+                                f[4 * j + 2] += __uint_as_float(dres[j].z);
+                                f[4 * j + 3] += __uint_as_float(dres[j].w);
+                            }
+                        } else if (row_ok) {
+                            const float* rp = reinterpret_cast<const float*>(args.resid) + opix * args.ldr + ocol;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < args.Cout) f[j] += rp[j];
+                        }
+                    } else if constexpr (RESID == 1) {
+                        if (fullc) {
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                f[8 * j + 0] += bf16_lo(dres[j].x); f[8 * j + 1] += bf16_hi(dres[j].x);
+                                f[8 * j + 2] += bf16_lo(dres[j].y); f[8 * j + 3] += bf16_hi(dres[j].y);
+                                f[8 * j + 4] += bf16_lo(dres[j].z); f[8 * j + 5] += bf16_hi(dres[j].z);
+                                f[8 * j + 6] += bf16_lo(dres[j].w); f[8 * j + 7] += bf16_hi(dres[j].w);
+                            }
+                        } else if (row_ok) {
+                            const __nv_bfloat16* rp =
+                                reinterpret_cast<const __nv_bfloat16*>(args.resid) + opix * args.ldr + ocol;
+#pragma unroll
+                            for (int j = 0; j < 32; ++j)
+                                if (col0 + j < args.Cout) f[j] += __bfloat162float(rp[j]);
+                        }
+                    }
+                    if (args.act == ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = fmaxf(f[j], 0.f);
+                    } else if (args.act == ACT_GELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = gelu_fast(f[j]);
+                    } else if (args.act == ACT_SIGMOID) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __fdividef(1.f, 1.f + __expf(-f[j]));
+                    }
+                    if (row_ok) {
+                        if constexpr (OUT_F32) {
+                            float* op = reinterpret_cast<float*>(args.out) + opix * args.ldc + ocol;
+                            if (fullc) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    reinterpret_cast<float4*>(op)[j] =
+                                        make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < args.Cout) op[j] = f[j];
+                            }
+                        } else {
+                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + opix * args.ldc + ocol;
+                            if (fullc) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    uint4 o;
+                                    o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
+                                    o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
+                                    o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
+                                    o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+                                    reinterpret_cast<uint4*>(op)[j] = o;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 32; ++j)
+                                    if (col0 + j < args.Cout) op[j] = __float2bfloat16(f[j]);
+                            }
+                        }
                     }
                 } else {
                     // output location of this chunk (the pixel index is remapped by the pixel-shuffle mode)
@@ -752,11 +852,11 @@ void gemm_plan_set_m(GemmPlan* plan, int M) {
     if (plan->grid < 1) plan->grid = 1;
 }
 
-template <int BLOCK_N, int OUT_F32, int RESID, int MODE>
-static int launch_variant(const GemmPlan* plan, cudaStream_t stream) {
+template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT>
+static int launch_variant2(const GemmPlan* plan, cudaStream_t stream) {
     using Cfg = TileCfg<BLOCK_N>;
     static bool attr_set = false;
-    auto kern = gemm_tc_kernel<BLOCK_N, OUT_F32, RESID, MODE>;
+    auto kern = gemm_tc_kernel<BLOCK_N, OUT_F32, RESID, MODE, DIRECT>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) {
@@ -769,10 +869,34 @@ static int launch_variant(const GemmPlan* plan, cudaStream_t stream) {
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
-        set_error("gemm_tc_kernel<%d,%d,%d,%d> launch: %s", BLOCK_N, OUT_F32, RESID, MODE, cudaGetErrorString(e));
+        set_error("gemm_tc_kernel<%d,%d,%d,%d,%d> launch: %s", BLOCK_N, OUT_F32, RESID, MODE, DIRECT,
+                  cudaGetErrorString(e));
         return 1;
     }
     return 0;
+}
+
+// Epilogue store path: staged (coalesced through shared memory) or direct (row per thread).  YTK_EPI=direct|staged
+// overrides the default for A/B measurements.
+static int epi_direct_mode() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("YTK_EPI");
+        mode = (e && e[0] == 'd') ? 1 : ((e && e[0] == 's') ? 0 : 2);  // 2 = per-variant default
+    }
+    return mode;
+}
+
+template <int BLOCK_N, int OUT_F32, int RESID, int MODE>
+static int launch_variant(const GemmPlan* plan, cudaStream_t stream) {
+    if constexpr (MODE == EPI_CONVT_FINAL) {
+        return launch_variant2<BLOCK_N, OUT_F32, RESID, MODE, 0>(plan, stream);
+    } else {
+        const int m = epi_direct_mode();
+        const bool direct = (m == 1) || (m == 2 && kDirectDefault);
+        if (direct) return launch_variant2<BLOCK_N, OUT_F32, RESID, MODE, 1>(plan, stream);
+        return launch_variant2<BLOCK_N, OUT_F32, RESID, MODE, 0>(plan, stream);
+    }
 }
 
 template <int BLOCK_N>
