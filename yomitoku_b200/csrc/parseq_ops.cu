@@ -401,6 +401,9 @@ int launch_flash_attention(const void* Q, long long ldq, const void* K, const vo
 // One CTA per (row, head); K/V of that row+head staged in shared memory as fp32.
 constexpr int kMaxS = 101;
 constexpr int kMaxHd = 96;
+constexpr int kMaxMem = 800;
+static int launch_single_query_attn(int mode, const void* qsrc, const void* kv, int B, int D, int heads,
+                                    const int* step_dev, const CropDesc* descs, void* out, cudaStream_t st);
 
 __global__ void __launch_bounds__(128) dec_self_attn_kernel(const __nv_bfloat16* __restrict__ q_shared,
                                                             const __nv_bfloat16* __restrict__ ckv, int B, int D,
@@ -575,8 +578,10 @@ int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, in
         set_error("decoder self-attention: head dim %d unsupported", hd);
         return 1;
     }
-    static const bool old_ar = getenv("YTK_OLD_SELF_ATTN") != nullptr;  // debugging aid
-    if (mode == 0 && !old_ar) {
+    static const bool old_ar = getenv("YTK_OLD_ATTN") != nullptr;  // A/B aid: previous kernels
+    if (mode == 0 && !old_ar)
+        return launch_single_query_attn(0, q_shared, ckv, B, D, heads, step_dev, nullptr, out, st);
+    if (mode == 0) {
         const int warps = B * heads;
         const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(q_shared),
                             *kv = reinterpret_cast<const __nv_bfloat16*>(ckv);
@@ -610,10 +615,144 @@ int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, in
     return cudaGetLastError() != cudaSuccess;
 }
 
+// =================================================================================================== single-query attention
+// Both attentions of an AR step have ONE query per (row, head) against a strided list of cached K/V rows:
+//   mode 0  self : q = q_shared[step], keys = content cache rows (stride B*2D), nk = step + 1
+//   mode 1  cross: q = qc[row],        keys = the row's encoder memory K/V (stride 2D), nk = ntok
+// One warp per (row, head), no block-level synchronisation.  LPK lanes share a key (each owns CPL 16-byte chunks of the
+// head dim), 32/LPK key subsets run side by side, so every lane keeps several independent 16-byte loads in flight -
+// the step is HBM-bound on exactly these reads (profiles/README_r01.md).
+template <int HD>
+__global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const __nv_bfloat16* __restrict__ qsrc,
+                                                                const __nv_bfloat16* __restrict__ kv, int B, int D,
+                                                                int heads, const int* __restrict__ step_dev,
+                                                                const CropDesc* __restrict__ descs,
+                                                                __nv_bfloat16* __restrict__ out) {
+    constexpr int NCH = HD / 8;
+    constexpr int LPK = (NCH % 4 == 0) ? 4 : 2;   // lanes per key
+    constexpr int CPL = NCH / LPK;                // 16-byte chunks per lane
+    constexpr int NSUB = 32 / LPK;                // key subsets
+    __shared__ float sP[4][kMaxMem];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wid = blockIdx.x * 4 + warp;
+    if (wid >= B * heads) return;
+    const int row = wid / heads, head = wid - row * heads;
+    const int part = lane % LPK, sub = lane / LPK;
+    int nk;
+    long long kstride;
+    const __nv_bfloat16 *qp, *kbase;
+    if (mode == 0) {
+        const int i = *step_dev;
+        nk = i + 1;
+        kstride = (long long)B * 2 * D;
+        qp = qsrc + (long long)i * D + head * HD;
+        kbase = kv + (long long)row * (2 * D) + head * HD;
+    } else {
+        const CropDesc d = descs[row];
+        nk = d.ntok;
+        kstride = 2 * D;
+        qp = qsrc + (long long)row * D + head * HD;
+        kbase = kv + (long long)d.tok_off * (2 * D) + head * HD;
+    }
+    // this lane's slice of the query in registers
+    float q[8 * CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(qp) + part * CPL + c);
+        q[8 * c + 0] = bf16_lo(u.x); q[8 * c + 1] = bf16_hi(u.x); q[8 * c + 2] = bf16_lo(u.y); q[8 * c + 3] = bf16_hi(u.y);
+        q[8 * c + 4] = bf16_lo(u.z); q[8 * c + 5] = bf16_hi(u.z); q[8 * c + 6] = bf16_lo(u.w); q[8 * c + 7] = bf16_hi(u.w);
+    }
+    const float scale = rsqrtf((float)HD);
+    float* myP = sP[warp];
+    // ---- scores
+#pragma unroll 4
+    for (int j0 = 0; j0 < nk; j0 += NSUB) {   // warp-uniform trip count: the shuffles below need every lane
+        const int j = j0 + sub;
+        const bool valid = j < nk;
+        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)(valid ? j : 0) * kstride) + part * CPL;
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const uint4 u = valid ? __ldg(kp + c) : make_uint4(0, 0, 0, 0);
+            s += q[8 * c + 0] * bf16_lo(u.x) + q[8 * c + 1] * bf16_hi(u.x) + q[8 * c + 2] * bf16_lo(u.y) +
+                 q[8 * c + 3] * bf16_hi(u.y) + q[8 * c + 4] * bf16_lo(u.z) + q[8 * c + 5] * bf16_hi(u.z) +
+                 q[8 * c + 6] * bf16_lo(u.w) + q[8 * c + 7] * bf16_hi(u.w);
+        }
+#pragma unroll
+        for (int o = 1; o < LPK; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (valid && part == 0) myP[j] = s * scale;
+    }
+    __syncwarp();
+    float mx = -INFINITY;
+    for (int j = lane; j < nk; j += 32) mx = fmaxf(mx, myP[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    float sum = 0.f;
+    for (int j = lane; j < nk; j += 32) {
+        const float p = __expf(myP[j] - mx);
+        myP[j] = p;
+        sum += p;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    __syncwarp();
+    // ---- weighted value sum
+    float acc[8 * CPL];
+#pragma unroll
+    for (int e = 0; e < 8 * CPL; ++e) acc[e] = 0.f;
+#pragma unroll 4
+    for (int j = sub; j < nk; j += NSUB) {
+        const float p = myP[j];
+        const uint4* vp = reinterpret_cast<const uint4*>(kbase + (long long)j * kstride + D) + part * CPL;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            const uint4 u = __ldg(vp + c);
+            acc[8 * c + 0] += p * bf16_lo(u.x); acc[8 * c + 1] += p * bf16_hi(u.x);
+            acc[8 * c + 2] += p * bf16_lo(u.y); acc[8 * c + 3] += p * bf16_hi(u.y);
+            acc[8 * c + 4] += p * bf16_lo(u.z); acc[8 * c + 5] += p * bf16_hi(u.z);
+            acc[8 * c + 6] += p * bf16_lo(u.w); acc[8 * c + 7] += p * bf16_hi(u.w);
+        }
+    }
+#pragma unroll
+    for (int o = LPK; o < 32; o <<= 1) {
+#pragma unroll
+        for (int e = 0; e < 8 * CPL; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+    }
+    if (sub == 0) {
+        const float inv = 1.f / sum;
+        uint4* op = reinterpret_cast<uint4*>(out + (long long)row * D + head * HD) + part * CPL;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+            uint4 o;
+            o.x = pack_bf16(acc[8 * c + 0] * inv, acc[8 * c + 1] * inv);
+            o.y = pack_bf16(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv);
+            o.z = pack_bf16(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv);
+            o.w = pack_bf16(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv);
+            op[c] = o;
+        }
+    }
+}
+
+static int launch_single_query_attn(int mode, const void* qsrc, const void* kv, int B, int D, int heads,
+                                    const int* step_dev, const CropDesc* descs, void* out, cudaStream_t st) {
+    const int hd = D / heads;
+    const unsigned grid = (B * heads + 3) / 4;
+    const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(qsrc), *k = reinterpret_cast<const __nv_bfloat16*>(kv);
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    switch (hd) {
+        case 32: single_query_attn_kernel<32><<<grid, 128, 0, st>>>(mode, q, k, B, D, heads, step_dev, descs, o); break;
+        case 48: single_query_attn_kernel<48><<<grid, 128, 0, st>>>(mode, q, k, B, D, heads, step_dev, descs, o); break;
+        case 64: single_query_attn_kernel<64><<<grid, 128, 0, st>>>(mode, q, k, B, D, heads, step_dev, descs, o); break;
+        case 96: single_query_attn_kernel<96><<<grid, 128, 0, st>>>(mode, q, k, B, D, heads, step_dev, descs, o); break;
+        default: set_error("single-query attention: head dim %d unsupported (32/48/64/96)", hd); return 1;
+    }
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
+}
+
 // =================================================================================================== AR cross-attn
 // One query per row against the row's encoder memory (reference cross_attn, parseq_transformer.py:92).  The memory
 // K/V were projected ONCE (the reference re-projects them every step).  CTA per (row, head).
-constexpr int kMaxMem = 800;
 
 template <int HD>
 __global__ void __launch_bounds__(128) dec_cross_attn_kernel(const __nv_bfloat16* __restrict__ qc,
@@ -701,6 +840,8 @@ int launch_dec_cross_attn(const void* qc, const void* memkv, const CropDesc* des
         set_error("decoder cross-attention: head dim %d unsupported", hd);
         return 1;
     }
+    static const bool old_ar = getenv("YTK_OLD_ATTN") != nullptr;  // A/B aid: previous kernel
+    if (!old_ar) return launch_single_query_attn(1, qc, memkv, B, D, heads, nullptr, descs, out, st);
     dim3 grid(B, heads);
     const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(qc), *kv = reinterpret_cast<const __nv_bfloat16*>(memkv);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
