@@ -914,11 +914,19 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
     const float* lr = logits + (long long)row * ldl;
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float v = lr[c];
-        if (v > best) {  // strict: keeps the smallest index within a thread (ascending scan)
-            best = v;
-            bi = c;
+    {
+        const int nvec = C >> 2;
+        const float4* l4 = reinterpret_cast<const float4*>(lr);
+        for (int v = threadIdx.x; v < nvec; v += blockDim.x) {   // strict '>' keeps the smallest index (ascending)
+            const float4 x = __ldg(l4 + v);
+            if (x.x > best) { best = x.x; bi = 4 * v; }
+            if (x.y > best) { best = x.y; bi = 4 * v + 1; }
+            if (x.z > best) { best = x.z; bi = 4 * v + 2; }
+            if (x.w > best) { best = x.w; bi = 4 * v + 3; }
+        }
+        for (int c = 4 * nvec + threadIdx.x; c < C; c += blockDim.x) {
+            const float v = lr[c];
+            if (v > best) { best = v; bi = c; }
         }
     }
     warp_argmax(best, bi);
@@ -1129,6 +1137,31 @@ int launch_refine_embed(const int* raw, const int* row_group, const int* group_l
 // =================================================================================================== softmax max
 // Replaces `.softmax(-1)` + per-position max of the reference (text_recognizer.py:255, parseq_tokenizer.py:79-87):
 // only (argmax id, max probability) leave the device.  One CTA per logits row.
+// online (max, sum-exp, arg-max) triple: one pass over the row
+struct SmStat {
+    float m, s;
+    int i;
+};
+__device__ __forceinline__ void sm_push(SmStat& a, float v, int idx) {
+    if (v > a.m) {
+        a.s = a.s * __expf(a.m - v) + 1.f;
+        a.m = v;
+        a.i = idx;
+    } else {
+        a.s += __expf(v - a.m);
+    }
+}
+__device__ __forceinline__ void sm_merge(SmStat& a, const SmStat& b) {
+    if (b.s == 0.f) return;  // empty partial (no elements seen)
+    if (b.m > a.m || (b.m == a.m && b.i < a.i)) {
+        a.s = a.s * __expf(a.m - b.m) + b.s;
+        a.m = b.m;
+        a.i = b.i;
+    } else {
+        a.s += b.s * __expf(b.m - a.m);
+    }
+}
+
 __global__ void __launch_bounds__(256) softmax_max_kernel(const float* __restrict__ logits, long long ldl, int C, int S,
                                                           long long g_stride, long long g_off,
                                                           const int* __restrict__ rep_cut, int eos_id,
@@ -1143,48 +1176,34 @@ __global__ void __launch_bounds__(256) softmax_max_kernel(const float* __restric
         }
         return;
     }
-    const float* lr = logits + (long long)r * ldl;
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) {
-        const float v = lr[c];
-        if (v > best) {
-            best = v;
-            bi = c;
-        }
+    const float* lr = logits + (long long)r * ldl;   // rows are 16-byte aligned (ldl % 4 == 0)
+    SmStat st{-INFINITY, 0.f, 0x7fffffff};
+    const int nvec = C >> 2;
+    const float4* l4 = reinterpret_cast<const float4*>(lr);
+    for (int v = threadIdx.x; v < nvec; v += 256) {
+        const float4 x = __ldg(l4 + v);
+        sm_push(st, x.x, 4 * v);
+        sm_push(st, x.y, 4 * v + 1);
+        sm_push(st, x.z, 4 * v + 2);
+        sm_push(st, x.w, 4 * v + 3);
     }
-    __shared__ float sv[8];
-    __shared__ int si[8];
-    __shared__ float s_max;
-    warp_argmax(best, bi);
-    if ((threadIdx.x & 31) == 0) {
-        sv[threadIdx.x >> 5] = best;
-        si[threadIdx.x >> 5] = bi;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float v = sv[0];
-        int id = si[0];
-        for (int w = 1; w < 8; ++w)
-            if (sv[w] > v || (sv[w] == v && si[w] < id)) {
-                v = sv[w];
-                id = si[w];
-            }
-        s_max = v;
-        ids[g] = id;
-    }
-    __syncthreads();
-    const float mx = s_max;
-    float sum = 0.f;
-    for (int c = threadIdx.x; c < C; c += blockDim.x) sum += expf(lr[c] - mx);
+    for (int c = 4 * nvec + threadIdx.x; c < C; c += 256) sm_push(st, lr[c], c);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if ((threadIdx.x & 31) == 0) sv[threadIdx.x >> 5] = sum;
+    for (int o = 16; o > 0; o >>= 1) {
+        SmStat b;
+        b.m = __shfl_xor_sync(0xffffffffu, st.m, o);
+        b.s = __shfl_xor_sync(0xffffffffu, st.s, o);
+        b.i = __shfl_xor_sync(0xffffffffu, st.i, o);
+        sm_merge(st, b);
+    }
+    __shared__ SmStat sw[8];
+    if ((threadIdx.x & 31) == 0) sw[threadIdx.x >> 5] = st;
     __syncthreads();
     if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += sv[w];
-        probs[g] = 1.f / t;
+        SmStat a = sw[0];
+        for (int w = 1; w < 8; ++w) sm_merge(a, sw[w]);
+        ids[g] = a.i;
+        probs[g] = 1.f / a.s;
     }
 }
 
