@@ -293,14 +293,11 @@ def main():
         sync_all()
         t0 = time.perf_counter()
         n_words = 0
-        # documented pipelined use of the public API: submit step i+1 (detector + host stage in the pool) before
-        # collecting step i (recognizer), so host post-processing overlaps device work; exactly `steps` batches
-        pending = ocr.submit(pages, prob_override=probs_syn)
-        for i in range(args.steps):
-            nxt = ocr.submit(pages, prob_override=probs_syn) if i + 1 < args.steps else None
-            res = ocr.collect(pending)
+        # documented pipelined use of the public API: `BatchedOCR.stream` runs the detector + host stage of the next
+        # batches (own thread, own CUDA stream, process pool) while the recognizer works on the current one; exactly
+        # `steps` batches of P pages go through
+        for res in ocr.stream([pages] * args.steps, lookahead=2, prob_override=[probs_syn] * args.steps):
             n_words += sum(len(r.words) for r in res)
-            pending = nxt
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")

@@ -19,6 +19,11 @@ import torch
 from . import _lib
 
 
+def _stream_ptr(stream):
+    """torch.cuda.Stream (or None = default stream) -> cudaStream_t for the C ABI."""
+    return None if stream is None else ctypes.c_void_p(stream.cuda_stream)
+
+
 def _he_conv(g, cout, cin, kh, kw, gain=1.0):
     return torch.randn(cout, cin, kh, kw, generator=g) * (gain * math.sqrt(2.0 / (cin * kh * kw)))
 
@@ -191,7 +196,7 @@ class DBNet(_DeviceModel):
                                                     1 if on_dev else 0, None))
         return OrderedDict(binary=out)
 
-    def detect_pages_u8(self, pages, out=None):
+    def detect_pages_u8(self, pages, out=None, stream=None):
         """Fused fast path: pages (n,H0,W0,3) uint8 BGR (numpy / torch, host or cuda) -> (n,Hn,Wn) fp32 probability
         maps (pre-processing runs on the GPU).  Pages that would be up-scaled need the model-level seam."""
         h = self._ensure()
@@ -205,7 +210,7 @@ class DBNet(_DeviceModel):
             out = torch.empty((n, Hn, Wn), dtype=torch.float32, device=t.device,
                               pin_memory=(not t.is_cuda) and torch.cuda.is_available())
         _lib.check(_lib.lib().ytk_dbnet_forward_u8(h, t.data_ptr(), 1 if t.is_cuda else 0, n, H0, W0, out.data_ptr(),
-                                                   1 if out.is_cuda else 0, None))
+                                                   1 if out.is_cuda else 0, _stream_ptr(stream)))
         return out
 
     def flops(self, n, Hn, Wn):
@@ -369,7 +374,7 @@ class PARSeq(_DeviceModel):
             tok += ntok
         return buf, total, descs, tok
 
-    def run_packed(self, buf, total, descs, n, n_groups):
+    def run_packed(self, buf, total, descs, n, n_groups, stream=None):
         """Device call on a packed crop buffer (torch uint8 tensor, pinned host or cuda)."""
         h = self._ensure()
         S = self.max_label_length + 1
@@ -378,7 +383,7 @@ class PARSeq(_DeviceModel):
         glen = np.empty((max(n_groups, 1),), dtype=np.int32)
         _lib.check(_lib.lib().ytk_parseq_forward_crops(h, buf.data_ptr(), 1 if buf.is_cuda else 0, total, descs, n,
                                                        n_groups, ids.ctypes.data, probs.ctypes.data, glen.ctypes.data,
-                                                       None))
+                                                       _stream_ptr(stream)))
         return ids, probs, glen[:n_groups]
 
     def recognize_crops(self, canvases, padded_widths, groups, n_groups):

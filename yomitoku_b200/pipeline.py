@@ -60,7 +60,8 @@ class BatchedOCR:
         self.workers = workers if workers is not None else max(1, min(32, (os.cpu_count() or 2) - 2))
         self._pool = None
         self._prob_ring = {}
-        self._prob_next = {}
+        self._slot = 0              # ring slot (pages + probability maps) of the batch being submitted
+        self._slot_busy = {}        # slot -> futures of the batch that last used it
         self._last_pages = None
 
     # ------------------------------------------------------------------------------------------ host pool
@@ -105,36 +106,34 @@ class BatchedOCR:
         of buffers lets `submit` run ahead of `collect`."""
         import torch
         key = (n, hn, wn)
-        ring = self._prob_ring.setdefault(key, [])
-        if len(ring) < 3:
+        ring = self._prob_ring.setdefault(key, {})
+        slot = self._slot
+        if slot not in ring:
             t = torch.empty((n, hn, wn), dtype=torch.float32).share_memory_()
             if torch.cuda.is_available():
                 err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 4, 0)
                 if int(err) != 0:
                     raise RuntimeError("cudaHostRegister failed: %s" % err)
-            ring.append(t)
-            return t
-        self._prob_next[key] = (self._prob_next.get(key, -1) + 1) % len(ring)
-        return ring[self._prob_next[key]]
+            ring[slot] = t
+        return ring[slot]
 
     def _shared_page_buffer(self, n, h, w):
         """Shared + page-locked staging for the u8 pages of one batch: one memcpy per page replaces np.stack, the H2D
         copy becomes an async DMA, and the workers get a handle instead of a 5.8 MB pickle per page."""
         import torch
         key = ("pages", n, h, w)
-        ring = self._prob_ring.setdefault(key, [])
-        if len(ring) < 3:
+        ring = self._prob_ring.setdefault(key, {})
+        slot = self._slot
+        if slot not in ring:
             t = torch.empty((n, h, w, 3), dtype=torch.uint8).share_memory_()
             if torch.cuda.is_available():
                 err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel(), 0)
                 if int(err) != 0:
                     raise RuntimeError("cudaHostRegister failed: %s" % err)
-            ring.append(t)
-            return t
-        self._prob_next[key] = (self._prob_next.get(key, -1) + 1) % len(ring)
-        return ring[self._prob_next[key]]
+            ring[slot] = t
+        return ring[slot]
 
-    def detect_prob(self, pages, shared=False):
+    def detect_prob(self, pages, shared=False, stream=None):
         """Device stage 1: probability maps (n, Hn, Wn) float32 (host) for same-size pages (numpy array, or a shared
         pinned torch tensor when `shared`)."""
         import torch
@@ -155,10 +154,10 @@ class BatchedOCR:
             self._last_pages = None
         for s in range(0, len(pages), self.det_batch):
             e = min(len(pages), s + self.det_batch)
-            self.detector.model.detect_pages_u8(stage[s:e], out=out[s:e])
+            self.detector.model.detect_pages_u8(stage[s:e], out=out[s:e], stream=stream)
         return out if shared else out.numpy()
 
-    def _run_groups_local(self, groups):
+    def _run_groups_local(self, groups, stream=None):
         """groups: list of (canvases, padded_widths).  One packed device call per <= max_tokens chunk (chunks end on
         group boundaries).  Returns per group (ids, probs, group_len)."""
         rec = self.recognizer
@@ -178,7 +177,8 @@ class BatchedOCR:
             canv = [c for g in groups[start:end] for c in g[0]]
             pad = [p for g in groups[start:end] for p in g[1]]
             grp = [k for k, g in enumerate(groups[start:end]) for _ in g[0]]
-            ids, probs, glen = rec.model.recognize_crops(canv, pad, grp, end - start)
+            buf, total, descs, _ = rec.model.pack_crops(canv, pad, grp)
+            ids, probs, glen = rec.model.run_packed(buf, total, descs, len(canv), end - start, stream=stream)
             off = 0
             for k in range(start, end):
                 n = len(groups[k][0])
@@ -187,12 +187,12 @@ class BatchedOCR:
             start = end
         return out
 
-    def _run_groups(self, groups):
+    def _run_groups(self, groups, stream=None):
         """Recognise groups, spreading them over all ranks when torch.distributed is initialised (crop scatter /
         result gather over NCCL, yomitoku_b200/parallel.py); results come back in `groups` order."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return self._run_groups_local(groups)
+            return self._run_groups_local(groups, stream)
         from . import parallel as par
         cfg = self.recognizer._cfg
         ph, pw = cfg.encoder.patch_size
@@ -200,7 +200,7 @@ class BatchedOCR:
         costs = [sum(gh * (p // pw) for p in g[1]) for g in groups]
         assign = par.balance_groups(par.gather_costs(costs), dist.get_world_size())[dist.get_rank()]
         work = par.exchange_groups(groups, assign, cfg.data.img_size[0])
-        res = self._run_groups_local([(w[2], w[3]) for w in work])
+        res = self._run_groups_local([(w[2], w[3]) for w in work], stream)
         S = cfg.max_label_length + 1
         # group_len travels as an extra column pair so that refine_iters == 0 keeps working across ranks
         packed = []
@@ -210,7 +210,7 @@ class BatchedOCR:
         back = par.return_results(work, packed, len(groups), S + 1)
         return [(i[:, :S], p[:, :S], int(i[0, S]) if len(i) else 0) for i, p in back]
 
-    def recognize_pooled(self, per_page):
+    def recognize_pooled(self, per_page, stream=None):
         """Device stage 2: per_page = list of (canvases, content_widths, n_quads).  Returns per page (ids, probs,
         order) with rows in the page's *plan* order, exactly like TextRecognizer._run_plan."""
         rec = self.recognizer
@@ -228,7 +228,7 @@ class BatchedOCR:
                 groups.append(([canv[i] for i in b], [padded[i] for i in b]))
                 owner.append(pi)
             orders.append(order)
-        res = self._run_groups(groups)
+        res = self._run_groups(groups, stream)
         S = cfg.max_label_length + 1
         out = []
         for pi in range(len(per_page)):
@@ -249,12 +249,16 @@ class BatchedOCR:
         return out
 
     # ------------------------------------------------------------------------------------------ whole path
-    def submit(self, pages, prob_override=None, quads_override=None):
+    def submit(self, pages, prob_override=None, quads_override=None, stream=None):
         """Stage 1 (device, synchronous: a few ms per page) + hand the host stage to the worker pool.  Returns a handle
         for `collect`.  Submitting batch i+1 before collecting batch i overlaps its host stage (contours, unclip, crop
         extraction) with the recognition of batch i on the GPU."""
         pool = self._get_pool()
-        prob = self.detect_prob(pages, shared=pool is not None)
+        # staging ring: 3 slots; a slot is reused only after the host stage of its previous batch has finished
+        self._slot = (self._slot + 1) % 3
+        for f in self._slot_busy.pop(self._slot, []):
+            f.result()
+        prob = self.detect_prob(pages, shared=pool is not None, stream=stream)
         jobs = []
         shared_pages = self._last_pages if pool is not None else None
         for i, p in enumerate(pages):
@@ -265,14 +269,16 @@ class BatchedOCR:
             r = self.recognizer
             _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
             return [_Done(_host_stage(j)) for j in jobs]
-        return [pool.submit(_host_stage, j) for j in jobs]
+        futs = [pool.submit(_host_stage, j) for j in jobs]
+        self._slot_busy[self._slot] = futs
+        return futs
 
-    def collect(self, handle):
+    def collect(self, handle, stream=None):
         """Waits for the host stage of a submitted batch, recognises all its crops in one packed device call and
         assembles per-page OCRSchema results."""
         host = [f.result() for f in handle]
         rec_in = [(h[2], h[3], len(h[0])) for h in host]
-        rec_out = self.recognize_pooled(rec_in)
+        rec_out = self.recognize_pooled(rec_in, stream)
         results = []
         r = self.recognizer
         from .schemas import WordPrediction
@@ -293,11 +299,51 @@ class BatchedOCR:
             results.append(OCRSchema.model_construct(words=words))
         return results
 
+    def stream(self, batches, lookahead=2, prob_override=None, quads_override=None):
+        """Pipelined iteration over many batches: `for results in ocr.stream(list_of_page_lists): ...` yields the
+        per-batch result lists in order.  prob_override / quads_override, if given, are per-batch lists."""
+        return _stream_impl(self, batches, lookahead, prob_override, quads_override)
+
     def __call__(self, pages, prob_override=None, quads_override=None):
         """pages: list of same-size BGR uint8 arrays.  prob_override / quads_override (benchmarks with random
         detector weights): the detector still runs, but post-processing sees the given probability maps / the
         recognizer the given quads."""
         return self.collect(self.submit(pages, prob_override, quads_override))
+
+
+def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
+    """Generator behind BatchedOCR.stream: a detector thread (own CUDA stream) runs `lookahead` batches ahead and feeds
+    the host pool; the calling thread collects in order on the recognizer stream.  ctypes releases the GIL inside the
+    C calls, so DBNet(i+1..), the host stages and PARSeq(i) overlap."""
+    import queue
+    import threading
+    import torch
+    det_stream = torch.cuda.Stream(priority=-1) if torch.cuda.is_available() else None
+    rec_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
+    q = queue.Queue(maxsize=max(1, lookahead))
+    err = []
+
+    def producer():
+        try:
+            for k, pages in enumerate(batches):
+                po = None if prob_override is None else prob_override[k]
+                qo = None if quads_override is None else quads_override[k]
+                q.put(ocr.submit(pages, po, qo, stream=det_stream))
+        except BaseException as e:  # surfaced in the consumer
+            err.append(e)
+        finally:
+            q.put(None)
+
+    t = threading.Thread(target=producer, daemon=True)
+    t.start()
+    while True:
+        h = q.get()
+        if h is None:
+            break
+        yield ocr.collect(h, stream=rec_stream)
+    t.join()
+    if err:
+        raise err[0]
 
 
 class _Done:
