@@ -386,6 +386,19 @@ class PARSeq(_DeviceModel):
                                                        _stream_ptr(stream)))
         return ids, probs, glen[:n_groups]
 
+    def run_packed_ptr(self, ptr, on_device, total, descs, n, n_groups, stream=None):
+        """Device call on `total` bytes of crop canvases at address `ptr` (page-locked host or device memory); descs is
+        a numpy structured array with the layout of ytk_crop."""
+        h = self._ensure()
+        S = self.max_label_length + 1
+        ids = np.empty((n, S), dtype=np.int32)
+        probs = np.empty((n, S), dtype=np.float32)
+        glen = np.empty((max(n_groups, 1),), dtype=np.int32)
+        dp = ctypes.cast(descs.ctypes.data, ctypes.POINTER(_lib.YtkCrop))
+        _lib.check(_lib.lib().ytk_parseq_forward_crops(h, ptr, on_device, total, dp, n, n_groups, ids.ctypes.data,
+                                                       probs.ctypes.data, glen.ctypes.data, _stream_ptr(stream)))
+        return ids, probs, glen[:n_groups]
+
     def recognize_crops(self, canvases, padded_widths, groups, n_groups):
         """Fused ragged path.  canvases: list of (32, w_i, 3) uint8 RGB arrays (the reference's dataset.data[i]);
         padded_widths[i]: width the reference collate would pad crop i to; groups[i]: its mini-batch index.

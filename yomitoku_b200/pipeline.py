@@ -34,8 +34,11 @@ def _worker_init(post_kwargs, rec_cfg, dynamic_width, source_downscale):
 
 
 def _host_stage(args):
-    """Post-process one probability map and cut that page's crops (runs in a worker process)."""
-    page, prob, quads_override = args
+    """Post-process one probability map and cut that page's crops (runs in a worker process).  With an `arena`
+    (shared page-locked uint8 tensor slice owned by this page) the canvases are written back to back into it and only
+    their widths travel back; canvases that do not fit are returned as arrays (`spill`)."""
+    page, prob, quads_override = args[:3]
+    arena = args[3] if len(args) > 3 else None
     if not isinstance(page, np.ndarray):
         page = page.numpy()          # shared-memory torch tensor (zero-copy view)
     if not isinstance(prob, np.ndarray):
@@ -48,7 +51,46 @@ def _host_stage(args):
                        source_downscale=_W["sd"]) if len(quads) else None
     if ds is None:
         return quads, scores, [], [], 0
-    return quads, scores, ds.data, ds.content_widths, len(ds)
+    if arena is None:
+        return quads, scores, ds.data, ds.content_widths, len(ds)
+    an = arena.numpy()
+    cap, off, widths, spill = an.shape[0], 0, [], []
+    for c in ds.data:
+        nb = c.size
+        if not spill and off + nb <= cap:
+            an[off:off + nb] = c.reshape(-1)
+            off += nb
+            widths.append(c.shape[1])
+        else:
+            spill.append(c)
+    return quads, scores, _ArenaRef(widths, spill, ds.data[0].shape[0]), ds.content_widths, len(ds)
+
+
+class _ArenaRef:
+    """What a worker sends back instead of canvases: the widths of the crops it wrote into its arena slice."""
+
+    def __init__(self, widths, spill, height):
+        self.widths, self.spill, self.height = widths, spill, height
+
+
+class _PageCrops:
+    """Crops of one page living in the shared arena at absolute byte offsets `offs` (list-like over canvases)."""
+
+    def __init__(self, arena_np, base, ref):
+        self.arena_np = arena_np
+        self.height = ref.height
+        self.widths = list(ref.widths)
+        sizes = np.asarray(self.widths, dtype=np.int64) * (3 * self.height)
+        self.offs = (base + np.concatenate([[0], np.cumsum(sizes)[:-1]])).astype(np.int64) if len(sizes) else \
+            np.zeros((0,), np.int64)
+
+    def __len__(self):
+        return len(self.widths)
+
+    def __getitem__(self, i):
+        w = self.widths[i]
+        o = int(self.offs[i])
+        return self.arena_np[o:o + self.height * w * 3].reshape(self.height, w, 3)
 
 
 class BatchedOCR:
@@ -63,6 +105,7 @@ class BatchedOCR:
         self._slot = 0              # ring slot (pages + probability maps) of the batch being submitted
         self._slot_busy = {}        # slot -> futures of the batch that last used it
         self._last_pages = None
+        self.crop_cap = 8 << 20     # arena bytes per page; doubled when a page spills
 
     # ------------------------------------------------------------------------------------------ host pool
     def _get_pool(self):
@@ -133,6 +176,22 @@ class BatchedOCR:
             ring[slot] = t
         return ring[slot]
 
+    def _shared_crop_arena(self, n):
+        """Shared + page-locked arena the workers write a batch's crop canvases into (`crop_cap` bytes per page): no
+        pickling of ~4 MB of crops per page, no packing copy, and the H2D copy of the crops is one DMA from here."""
+        import torch
+        key = ("crops", n, self.crop_cap)
+        ring = self._prob_ring.setdefault(key, {})
+        slot = self._slot
+        if slot not in ring:
+            t = torch.empty((n * self.crop_cap,), dtype=torch.uint8).share_memory_()
+            if torch.cuda.is_available():
+                err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel(), 0)
+                if int(err) != 0:
+                    raise RuntimeError("cudaHostRegister failed: %s" % err)
+            ring[slot] = t
+        return ring[slot]
+
     def detect_prob(self, pages, shared=False, stream=None):
         """Device stage 1: probability maps (n, Hn, Wn) float32 (host) for same-size pages (numpy array, or a shared
         pinned torch tensor when `shared`)."""
@@ -187,6 +246,48 @@ class BatchedOCR:
             start = end
         return out
 
+    def _run_groups_arena(self, groups, arena, height, stream=None):
+        """Like _run_groups_local for crops that already sit in the page-locked arena: groups = (widths, padded widths,
+        absolute arena offsets).  Descriptors are built with numpy; the device call copies one span of the arena."""
+        from . import _lib
+        rec = self.recognizer
+        cfg = rec._cfg
+        ph, pw = cfg.encoder.patch_size
+        gh = cfg.data.img_size[0] // ph
+        out = [None] * len(groups)
+        gtok = [gh * (int(np.sum(g[1])) // pw) for g in groups]
+        dt = np.dtype(_lib.YtkCrop)
+        start = 0
+        while start < len(groups):
+            end, tok = start, 0
+            while end < len(groups) and not (end > start and tok + gtok[end] > self.max_tokens):
+                tok += gtok[end]
+                end += 1
+            sel = groups[start:end]
+            w = np.concatenate([np.asarray(g[0], np.int64) for g in sel])
+            wp = np.concatenate([np.asarray(g[1], np.int64) for g in sel])
+            offs = np.concatenate([g[2] for g in sel])
+            n = w.shape[0]
+            lo = int(offs.min())
+            hi = int((offs + w * (3 * height)).max())
+            ntok = gh * (wp // pw)
+            descs = np.zeros(n, dtype=dt)
+            descs["pix_off"] = offs - lo
+            descs["w"] = w
+            descs["wp"] = wp
+            descs["tok_off"] = np.cumsum(ntok) - ntok
+            descs["ntok"] = ntok
+            descs["group"] = np.repeat(np.arange(end - start), [len(g[0]) for g in sel])
+            ids, probs, glen = rec.model.run_packed_ptr(arena.data_ptr() + lo, 0, hi - lo, descs, n, end - start,
+                                                        stream=stream)
+            off = 0
+            for k in range(start, end):
+                m = len(groups[k][0])
+                out[k] = (ids[off:off + m], probs[off:off + m], int(glen[k - start]))
+                off += m
+            start = end
+        return out
+
     def _run_groups(self, groups, stream=None):
         """Recognise groups, spreading them over all ranks when torch.distributed is initialised (crop scatter /
         result gather over NCCL, yomitoku_b200/parallel.py); results come back in `groups` order."""
@@ -210,25 +311,34 @@ class BatchedOCR:
         back = par.return_results(work, packed, len(groups), S + 1)
         return [(i[:, :S], p[:, :S], int(i[0, S]) if len(i) else 0) for i, p in back]
 
-    def recognize_pooled(self, per_page, stream=None):
-        """Device stage 2: per_page = list of (canvases, content_widths, n_quads).  Returns per page (ids, probs,
-        order) with rows in the page's *plan* order, exactly like TextRecognizer._run_plan."""
+    def recognize_pooled(self, per_page, stream=None, arena=None):
+        """Device stage 2: per_page = list of (canvases, content_widths, n_quads); canvases is a list of arrays or a
+        `_PageCrops` view of `arena`.  Returns per page (ids, probs, order) with rows in the page's *plan* order,
+        exactly like TextRecognizer._run_plan."""
         rec = self.recognizer
         cfg = rec._cfg
+        import torch.distributed as dist
+        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+        in_arena = arena is not None and not distributed and all(isinstance(p[0], _PageCrops) for p in per_page)
         groups, owner, orders = [], [], []
         for pi, (canv, cw, n_quads) in enumerate(per_page):
             order = None
             if rec.batch_bucketing and len(canv) == n_quads and len(canv) > 1:
                 order = np.argsort(cw).tolist()
-            plan = plan_mini_batches([c.shape[1] for c in canv], order, rec.dynamic_width, cfg.data.batch_size,
+            widths = canv.widths if isinstance(canv, _PageCrops) else [c.shape[1] for c in canv]
+            plan = plan_mini_batches(widths, order, rec.dynamic_width, cfg.data.batch_size,
                                      getattr(cfg.data, "width_budget", None),
                                      getattr(cfg.data, "max_batch_size", None))
-            padded, _ = rec._collate_widths(canv, plan)
+            padded, _ = rec._collate_widths(widths, plan)
             for b in plan:
-                groups.append(([canv[i] for i in b], [padded[i] for i in b]))
+                if in_arena:   # (widths, padded widths, arena offsets): no pixel is touched on the host
+                    groups.append(([widths[i] for i in b], [padded[i] for i in b], canv.offs[b]))
+                else:
+                    groups.append(([canv[i] for i in b], [padded[i] for i in b]))
                 owner.append(pi)
             orders.append(order)
-        res = self._run_groups(groups, stream)
+        res = self._run_groups_arena(groups, arena, per_page[0][0].height if per_page else 32, stream) \
+            if in_arena else self._run_groups(groups, stream)
         S = cfg.max_label_length + 1
         out = []
         for pi in range(len(per_page)):
@@ -261,24 +371,42 @@ class BatchedOCR:
         prob = self.detect_prob(pages, shared=pool is not None, stream=stream)
         jobs = []
         shared_pages = self._last_pages if pool is not None else None
+        arena = self._shared_crop_arena(len(pages)) if pool is not None else None
+        cap = self.crop_cap
         for i, p in enumerate(pages):
             pm = prob[i] if prob_override is None else prob_override[i]
-            jobs.append((p if shared_pages is None else shared_pages[i], pm,
-                         None if quads_override is None else quads_override[i]))
+            job = (p if shared_pages is None else shared_pages[i], pm,
+                   None if quads_override is None else quads_override[i])
+            jobs.append(job if arena is None else job + (arena[i * cap:(i + 1) * cap],))
         if pool is None:
             r = self.recognizer
             _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
-            return [_Done(_host_stage(j)) for j in jobs]
+            return _Handle([_Done(_host_stage(j)) for j in jobs], None, 0)
         futs = [pool.submit(_host_stage, j) for j in jobs]
         self._slot_busy[self._slot] = futs
-        return futs
+        return _Handle(futs, arena, cap)
 
     def collect(self, handle, stream=None):
         """Waits for the host stage of a submitted batch, recognises all its crops in one packed device call and
         assembles per-page OCRSchema results."""
-        host = [f.result() for f in handle]
+        host = [f.result() for f in handle.futures]
+        arena = handle.arena
+        if arena is not None:
+            an = arena.numpy()
+            fixed = []
+            for i, h in enumerate(host):
+                ref = h[2]
+                if isinstance(ref, _ArenaRef):
+                    crops = _PageCrops(an, i * handle.cap, ref)
+                    if ref.spill:       # arena slice too small for this page: generic path now, larger slices next time
+                        crops = [crops[k] for k in range(len(crops))] + list(ref.spill)
+                        self.crop_cap = max(self.crop_cap, 2 * handle.cap)
+                        arena = None
+                    h = (h[0], h[1], crops, h[3], h[4])
+                fixed.append(h)
+            host = fixed
         rec_in = [(h[2], h[3], len(h[0])) for h in host]
-        rec_out = self.recognize_pooled(rec_in, stream)
+        rec_out = self.recognize_pooled(rec_in, stream, arena=arena)
         results = []
         r = self.recognizer
         from .schemas import WordPrediction
@@ -344,6 +472,13 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
     t.join()
     if err:
         raise err[0]
+
+
+class _Handle:
+    """What `submit` returns: the host-stage futures of a batch + the crop arena its workers write into."""
+
+    def __init__(self, futures, arena, cap):
+        self.futures, self.arena, self.cap = futures, arena, cap
 
 
 class _Done:

@@ -123,15 +123,13 @@ class TextRecognizer(BaseModule):
 
     def _collate_widths(self, canvases, plan):
         """Per crop: (padded width, group id) = what reference _collate (:146-156) does to each mini-batch."""
-        padded = [0] * len(canvases)
-        group = [0] * len(canvases)
+        widths = [c if isinstance(c, (int, np.integer)) else c.shape[1] for c in canvases]   # canvases or widths
+        padded = [0] * len(widths)
+        group = [0] * len(widths)
         for g, batch in enumerate(plan):
-            if self.dynamic_width:
-                wmax = max(canvases[i].shape[1] for i in batch)
-            else:
-                wmax = None
+            wmax = max(widths[i] for i in batch) if self.dynamic_width else None
             for i in batch:
-                padded[i] = wmax if wmax is not None else canvases[i].shape[1]
+                padded[i] = wmax if wmax is not None else widths[i]
                 group[i] = g
         return padded, group
 
@@ -153,12 +151,12 @@ class TextRecognizer(BaseModule):
     def postprocess_ids(self, ids, probs, points):
         pred, score = self.tokenizer.decode_ids(ids, probs)
         pred = [unicodedata.normalize("NFKC", x) for x in pred]
-        directions = []
-        for point in points:
-            point = np.array(point)
-            w = np.linalg.norm(point[0] - point[1])
-            h = np.linalg.norm(point[1] - point[2])
-            directions.append("vertical" if h > w * 2 else "horizontal")
+        if len(points) == 0:
+            return pred, score, []
+        pts = np.asarray(points, dtype=np.float64)          # (n, 4, 2); same float64 norms as np.linalg.norm per quad
+        w = np.sqrt(((pts[:, 0] - pts[:, 1]) ** 2).sum(axis=1))
+        h = np.sqrt(((pts[:, 1] - pts[:, 2]) ** 2).sum(axis=1))
+        directions = ["vertical" if v else "horizontal" for v in (h > w * 2).tolist()]
         return pred, score, directions
 
     def postprocess(self, p, points):
