@@ -22,6 +22,23 @@ from .schemas import OCRSchema, TextDetectorSchema, TextRecognizerSchema
 from .text_recognizer import plan_mini_batches
 
 _W = {}
+TRACE = None     # set to a list to collect (stage, thread name, t0, t1) tuples (scripts/gpu_trace_e2e.py)
+
+
+class _span:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        if TRACE is not None:
+            import time
+            self.t0 = time.perf_counter()
+
+    def __exit__(self, *a):
+        if TRACE is not None:
+            import threading
+            import time
+            TRACE.append((self.name, threading.current_thread().name, self.t0, time.perf_counter()))
 
 
 def _worker_init(post_kwargs, rec_cfg, dynamic_width, source_downscale):
@@ -37,6 +54,8 @@ def _host_stage(args):
     """Post-process one probability map and cut that page's crops (runs in a worker process).  With an `arena`
     (shared page-locked uint8 tensor slice owned by this page) the canvases are written back to back into it and only
     their widths travel back; canvases that do not fit are returned as arrays (`spill`)."""
+    import time
+    t0 = time.perf_counter()
     page, prob, quads_override = args[:3]
     arena = args[3] if len(args) > 3 else None
     if not isinstance(page, np.ndarray):
@@ -47,6 +66,7 @@ def _host_stage(args):
         quads, scores = _W["post"]({"binary": prob[None, None]}, page.shape[:2])
     else:
         quads, scores = quads_override, [1.0] * len(quads_override)
+    t1 = time.perf_counter()
     ds = ParseqDataset(_W["cfg"], page, quads if len(quads) else [], num_workers=1, dynamic_width=_W["dyn"],
                        source_downscale=_W["sd"]) if len(quads) else None
     if ds is None:
@@ -63,7 +83,8 @@ def _host_stage(args):
             widths.append(c.shape[1])
         else:
             spill.append(c)
-    return quads, scores, _ArenaRef(widths, spill, ds.data[0].shape[0]), ds.content_widths, len(ds)
+    return quads, scores, _ArenaRef(widths, spill, ds.data[0].shape[0]), ds.content_widths, len(ds), \
+        (t0, t1, time.perf_counter())
 
 
 class _ArenaRef:
@@ -94,7 +115,7 @@ class _PageCrops:
 
 
 class BatchedOCR:
-    def __init__(self, detector, recognizer, workers=None, det_batch=8, max_tokens=400_000):
+    def __init__(self, detector, recognizer, workers=None, det_batch=8, max_tokens=1_000_000):
         self.detector = detector
         self.recognizer = recognizer
         self.det_batch = det_batch
@@ -205,8 +226,9 @@ class BatchedOCR:
         if shared and hn <= h0 and wn <= w0:
             stage = self._shared_page_buffer(len(pages), h0, w0)
             sn = stage.numpy()
-            for i, p in enumerate(pages):
-                np.copyto(sn[i], p)
+            with _span("detect.stage_pages"):
+                for i, p in enumerate(pages):
+                    np.copyto(sn[i], p)
             self._last_pages = stage
         else:
             stage = torch.from_numpy(np.stack([np.ascontiguousarray(p) for p in pages]))
@@ -278,8 +300,9 @@ class BatchedOCR:
             descs["tok_off"] = np.cumsum(ntok) - ntok
             descs["ntok"] = ntok
             descs["group"] = np.repeat(np.arange(end - start), [len(g[0]) for g in sel])
-            ids, probs, glen = rec.model.run_packed_ptr(arena.data_ptr() + lo, 0, hi - lo, descs, n, end - start,
-                                                        stream=stream)
+            with _span("recognize.device"):
+                ids, probs, glen = rec.model.run_packed_ptr(arena.data_ptr() + lo, 0, hi - lo, descs, n, end - start,
+                                                            stream=stream)
             off = 0
             for k in range(start, end):
                 m = len(groups[k][0])
@@ -366,9 +389,11 @@ class BatchedOCR:
         pool = self._get_pool()
         # staging ring: 3 slots; a slot is reused only after the host stage of its previous batch has finished
         self._slot = (self._slot + 1) % 3
-        for f in self._slot_busy.pop(self._slot, []):
-            f.result()
-        prob = self.detect_prob(pages, shared=pool is not None, stream=stream)
+        with _span("submit.wait_slot"):
+            for f in self._slot_busy.pop(self._slot, []):
+                f.result()
+        with _span("submit.detect"):
+            prob = self.detect_prob(pages, shared=pool is not None, stream=stream)
         jobs = []
         shared_pages = self._last_pages if pool is not None else None
         arena = self._shared_crop_arena(len(pages)) if pool is not None else None
@@ -382,14 +407,19 @@ class BatchedOCR:
             r = self.recognizer
             _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
             return _Handle([_Done(_host_stage(j)) for j in jobs], None, 0)
-        futs = [pool.submit(_host_stage, j) for j in jobs]
+        with _span("submit.jobs"):
+            futs = [pool.submit(_host_stage, j) for j in jobs]
         self._slot_busy[self._slot] = futs
         return _Handle(futs, arena, cap)
 
     def collect(self, handle, stream=None):
         """Waits for the host stage of a submitted batch, recognises all its crops in one packed device call and
         assembles per-page OCRSchema results."""
-        host = [f.result() for f in handle.futures]
+        return self._assemble(*self._recognize_handle(handle, stream))
+
+    def _recognize_handle(self, handle, stream=None):
+        with _span("collect.wait_host"):
+            host = [f.result() for f in handle.futures]
         arena = handle.arena
         if arena is not None:
             an = arena.numpy()
@@ -402,15 +432,24 @@ class BatchedOCR:
                         crops = [crops[k] for k in range(len(crops))] + list(ref.spill)
                         self.crop_cap = max(self.crop_cap, 2 * handle.cap)
                         arena = None
+                    if TRACE is not None and len(h) > 5:
+                        TRACE.append(("worker.post", "worker", h[5][0], h[5][1]))
+                        TRACE.append(("worker.crops", "worker", h[5][1], h[5][2]))
                     h = (h[0], h[1], crops, h[3], h[4])
                 fixed.append(h)
             host = fixed
         rec_in = [(h[2], h[3], len(h[0])) for h in host]
-        rec_out = self.recognize_pooled(rec_in, stream, arena=arena)
+        with _span("collect.recognize"):
+            rec_out = self.recognize_pooled(rec_in, stream, arena=arena)
+        return host, rec_out
+
+    def _assemble(self, host, rec_out):
         results = []
+        _t = _span("collect.assemble")
+        _t.__enter__()
         r = self.recognizer
         from .schemas import WordPrediction
-        for (quads, scores, canv, cw, n), (ids, probs, order) in zip(host, rec_out):
+        for (quads, scores, canv, cw, n, *_), (ids, probs, order) in zip(host, rec_out):
             if n == 0:
                 p, s, d = [], [], []
             else:
@@ -425,6 +464,7 @@ class BatchedOCR:
                                                     rec_score=float(rs))
                      for q, ds, c, rs, dd in zip(quads, scores, p, s, d)]
             results.append(OCRSchema.model_construct(words=words))
+        _t.__exit__()
         return results
 
     def stream(self, batches, lookahead=2, prob_override=None, quads_override=None):
@@ -440,9 +480,10 @@ class BatchedOCR:
 
 
 def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
-    """Generator behind BatchedOCR.stream: a detector thread (own CUDA stream) runs `lookahead` batches ahead and feeds
-    the host pool; the calling thread collects in order on the recognizer stream.  ctypes releases the GIL inside the
-    C calls, so DBNet(i+1..), the host stages and PARSeq(i) overlap."""
+    """Generator behind BatchedOCR.stream, three stages in order: a detector thread (own CUDA stream) runs up to
+    `lookahead` batches ahead and feeds the host pool; a recognizer thread waits for each batch's host stage and runs
+    the packed PARSeq call on its own stream; the calling thread turns ids into strings / schemas and yields.  ctypes
+    releases the GIL inside the C calls, so DBNet(i+2), host stage(i+1), PARSeq(i) and assembly(i-1) overlap."""
     import queue
     import threading
     import torch
@@ -462,14 +503,32 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
         finally:
             q.put(None)
 
-    t = threading.Thread(target=producer, daemon=True)
-    t.start()
+    q2 = queue.Queue(maxsize=2)
+
+    def recognizer():
+        try:
+            while True:
+                h = q.get()
+                if h is None:
+                    break
+                q2.put(ocr._recognize_handle(h, stream=rec_stream))
+        except BaseException as e:
+            err.append(e)
+            while q.get() is not None:      # keep draining so that the producer can finish
+                pass
+        finally:
+            q2.put(None)
+
+    threads = [threading.Thread(target=producer, daemon=True), threading.Thread(target=recognizer, daemon=True)]
+    for t in threads:
+        t.start()
     while True:
-        h = q.get()
-        if h is None:
+        item = q2.get()
+        if item is None:
             break
-        yield ocr.collect(h, stream=rec_stream)
-    t.join()
+        yield ocr._assemble(*item)
+    for t in threads:
+        t.join()
     if err:
         raise err[0]
 
