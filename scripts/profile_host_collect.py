@@ -34,13 +34,13 @@ def main():
     rec.model.run_packed_ptr = lambda ptr, on_device, total, descs, n, n_groups, stream=None: \
         fake_run_packed(None, total, descs, n, n_groups)
     ocr = BatchedOCR(det, rec, det_batch=8, workers=W)
-    import torch
-    ocr.detect_prob = lambda pages, shared=False, stream=None: torch.from_numpy(np.stack(probs))
-    for _ in range(2):
-        h = ocr.submit(pages)
+    det.model.detect_pages_u8 = lambda *a, **k: None      # no GPU here: the maps come from prob_override
+    det.model.input_size = lambda h, w: (Hn, Wn)
+    for _ in range(4):
+        h = ocr.submit(pages, prob_override=probs)
         ocr.collect(h)
     t0 = time.perf_counter()
-    h = ocr.submit(pages)
+    h = ocr.submit(pages, prob_override=probs)
     t1 = time.perf_counter()
     host = [f.result() for f in h.futures]
     t2 = time.perf_counter()

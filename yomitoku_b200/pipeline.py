@@ -41,6 +41,71 @@ class _span:
             TRACE.append((self.name, threading.current_thread().name, self.t0, time.perf_counter()))
 
 
+class _SharedBuf:
+    """A file in /dev/shm mapped into this process and page-locked for DMA.  Worker processes map the same file once
+    (by path, `_attach`) and keep it mapped, so a job carries a tiny (path, offset, shape) descriptor instead of a
+    pickled array or a per-job file-descriptor hand-over."""
+
+    def __init__(self, nbytes):
+        import mmap
+        import tempfile
+        import torch
+        self.nbytes = int(nbytes)
+        fd, self.path = tempfile.mkstemp(prefix="ytk_b200_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        try:
+            os.ftruncate(fd, self.nbytes)
+            self.mm = mmap.mmap(fd, self.nbytes)
+        finally:
+            os.close(fd)
+        self.np = np.frombuffer(self.mm, dtype=np.uint8)
+        self.torch = torch.from_numpy(self.np)
+        self.registered = False
+        if torch.cuda.is_available():
+            err = torch.cuda.cudart().cudaHostRegister(self.np.ctypes.data, self.nbytes, 0)
+            if int(err) != 0:
+                self.close()
+                raise RuntimeError("cudaHostRegister failed: %s" % err)
+            self.registered = True
+
+    def view(self, offset, shape, dtype):
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        return self.np[offset:offset + n].view(dtype).reshape(shape)
+
+    def desc(self, offset, shape, dtype):
+        return ("shm", self.path, self.nbytes, int(offset), tuple(int(v) for v in shape), np.dtype(dtype).str)
+
+    def close(self):
+        if self.registered:
+            import torch
+            torch.cuda.cudart().cudaHostUnregister(self.np.ctypes.data)
+            self.registered = False
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
+_ATTACHED = {}
+
+
+def _attach(desc):
+    """Worker side of _SharedBuf.desc: numpy view into the (cached) mapping."""
+    import mmap
+    _, path, nbytes, offset, shape, dtype = desc
+    arr = _ATTACHED.get(path)
+    if arr is None:
+        if len(_ATTACHED) > 64:
+            _ATTACHED.clear()
+        fd = os.open(path, os.O_RDWR)
+        try:
+            arr = np.frombuffer(mmap.mmap(fd, nbytes), dtype=np.uint8)
+        finally:
+            os.close(fd)
+        _ATTACHED[path] = arr
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    return arr[offset:offset + n].view(dtype).reshape(shape)
+
+
 def _worker_init(post_kwargs, rec_cfg, dynamic_width, source_downscale):
     import cv2
     cv2.setNumThreads(1)
@@ -58,10 +123,12 @@ def _host_stage(args):
     t0 = time.perf_counter()
     page, prob, quads_override = args[:3]
     arena = args[3] if len(args) > 3 else None
-    if not isinstance(page, np.ndarray):
-        page = page.numpy()          # shared-memory torch tensor (zero-copy view)
-    if not isinstance(prob, np.ndarray):
-        prob = prob.numpy()          # shared-memory torch tensor (zero-copy view)
+    if isinstance(page, tuple):
+        page = _attach(page)         # zero-copy views of the parent's shared staging buffers
+    if isinstance(prob, tuple):
+        prob = _attach(prob)
+    if isinstance(arena, tuple):
+        arena = _attach(arena)
     if quads_override is None:
         quads, scores = _W["post"]({"binary": prob[None, None]}, page.shape[:2])
     else:
@@ -73,7 +140,7 @@ def _host_stage(args):
         return quads, scores, [], [], 0
     if arena is None:
         return quads, scores, ds.data, ds.content_widths, len(ds)
-    an = arena.numpy()
+    an = arena
     cap, off, widths, spill = an.shape[0], 0, [], []
     for c in ds.data:
         nb = c.size
@@ -125,7 +192,7 @@ class BatchedOCR:
         self._prob_ring = {}
         self._slot = 0              # ring slot (pages + probability maps) of the batch being submitted
         self._slot_busy = {}        # slot -> futures of the batch that last used it
-        self._last_pages = None
+        self._last_shared = None
         self.crop_cap = 8 << 20     # arena bytes per page; doubled when a page spills
 
     # ------------------------------------------------------------------------------------------ host pool
@@ -154,6 +221,17 @@ class BatchedOCR:
         if self._pool is not None:
             self._pool.shutdown(wait=True, cancel_futures=True)
             self._pool = None
+        for ring in self._prob_ring.values():
+            for buf in ring.values():
+                buf.close()
+        self._prob_ring = {}
+        self._slot_busy = {}
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def _host_map(self, jobs):
         pool = self._get_pool()
@@ -164,79 +242,40 @@ class BatchedOCR:
         return list(pool.map(_host_stage, jobs, chunksize=1))
 
     # ------------------------------------------------------------------------------------------ stages
-    def _shared_prob_buffer(self, n, hn, wn):
-        """Host buffer for n probability maps that (a) lives in shared memory, so worker processes receive a handle
-        instead of a 7.6 MB pickle per page, and (b) is page-locked, so the D2H copy is a plain async DMA.  A small ring
-        of buffers lets `submit` run ahead of `collect`."""
-        import torch
-        key = (n, hn, wn)
+    def _shared(self, kind, nbytes):
+        """Shared + page-locked staging buffer of the current ring slot (pages, probability maps or crop arena)."""
+        key = (kind, int(nbytes))
         ring = self._prob_ring.setdefault(key, {})
-        slot = self._slot
-        if slot not in ring:
-            t = torch.empty((n, hn, wn), dtype=torch.float32).share_memory_()
-            if torch.cuda.is_available():
-                err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel() * 4, 0)
-                if int(err) != 0:
-                    raise RuntimeError("cudaHostRegister failed: %s" % err)
-            ring[slot] = t
-        return ring[slot]
-
-    def _shared_page_buffer(self, n, h, w):
-        """Shared + page-locked staging for the u8 pages of one batch: one memcpy per page replaces np.stack, the H2D
-        copy becomes an async DMA, and the workers get a handle instead of a 5.8 MB pickle per page."""
-        import torch
-        key = ("pages", n, h, w)
-        ring = self._prob_ring.setdefault(key, {})
-        slot = self._slot
-        if slot not in ring:
-            t = torch.empty((n, h, w, 3), dtype=torch.uint8).share_memory_()
-            if torch.cuda.is_available():
-                err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel(), 0)
-                if int(err) != 0:
-                    raise RuntimeError("cudaHostRegister failed: %s" % err)
-            ring[slot] = t
-        return ring[slot]
-
-    def _shared_crop_arena(self, n):
-        """Shared + page-locked arena the workers write a batch's crop canvases into (`crop_cap` bytes per page): no
-        pickling of ~4 MB of crops per page, no packing copy, and the H2D copy of the crops is one DMA from here."""
-        import torch
-        key = ("crops", n, self.crop_cap)
-        ring = self._prob_ring.setdefault(key, {})
-        slot = self._slot
-        if slot not in ring:
-            t = torch.empty((n * self.crop_cap,), dtype=torch.uint8).share_memory_()
-            if torch.cuda.is_available():
-                err = torch.cuda.cudart().cudaHostRegister(t.data_ptr(), t.numel(), 0)
-                if int(err) != 0:
-                    raise RuntimeError("cudaHostRegister failed: %s" % err)
-            ring[slot] = t
-        return ring[slot]
+        if self._slot not in ring:
+            ring[self._slot] = _SharedBuf(nbytes)
+        return ring[self._slot]
 
     def detect_prob(self, pages, shared=False, stream=None):
-        """Device stage 1: probability maps (n, Hn, Wn) float32 (host) for same-size pages (numpy array, or a shared
-        pinned torch tensor when `shared`)."""
+        """Device stage 1: probability maps (n, Hn, Wn) float32 on the host for same-size pages.  With `shared` (pages
+        that are only decimated) pages and maps go through the shared page-locked ring - the H2D/D2H copies are plain
+        DMAs and the workers read both without a copy; `self._last_shared` then holds the two buffers."""
         import torch
+        n = len(pages)
         h0, w0 = pages[0].shape[:2]
         hn, wn = self.detector.model.input_size(h0, w0)
+        self._last_shared = None
         if shared and hn <= h0 and wn <= w0:
-            out = self._shared_prob_buffer(len(pages), hn, wn)
-        else:
-            out = torch.empty((len(pages), hn, wn), dtype=torch.float32)
-        if shared and hn <= h0 and wn <= w0:
-            stage = self._shared_page_buffer(len(pages), h0, w0)
-            sn = stage.numpy()
+            pb = self._shared("pages", n * h0 * w0 * 3)
+            ob = self._shared("prob", n * hn * wn * 4)
+            sn = pb.view(0, (n, h0, w0, 3), np.uint8)
             with _span("detect.stage_pages"):
                 for i, p in enumerate(pages):
                     np.copyto(sn[i], p)
-            self._last_pages = stage
+            stage = pb.torch.view(n, h0, w0, 3)
+            out = ob.torch.view(torch.float32).view(n, hn, wn)
+            self._last_shared = (pb, ob)
         else:
             stage = torch.from_numpy(np.stack([np.ascontiguousarray(p) for p in pages]))
-            self._last_pages = None
-        for s in range(0, len(pages), self.det_batch):
-            e = min(len(pages), s + self.det_batch)
+            out = torch.empty((n, hn, wn), dtype=torch.float32)
+        for s in range(0, n, self.det_batch):
+            e = min(n, s + self.det_batch)
             self.detector.model.detect_pages_u8(stage[s:e], out=out[s:e], stream=stream)
-        return out if shared else out.numpy()
+        return out.numpy()
 
     def _run_groups_local(self, groups, stream=None):
         """groups: list of (canvases, padded_widths).  One packed device call per <= max_tokens chunk (chunks end on
@@ -301,7 +340,7 @@ class BatchedOCR:
             descs["ntok"] = ntok
             descs["group"] = np.repeat(np.arange(end - start), [len(g[0]) for g in sel])
             with _span("recognize.device"):
-                ids, probs, glen = rec.model.run_packed_ptr(arena.data_ptr() + lo, 0, hi - lo, descs, n, end - start,
+                ids, probs, glen = rec.model.run_packed_ptr(arena.np.ctypes.data + lo, 0, hi - lo, descs, n, end - start,
                                                             stream=stream)
             off = 0
             for k in range(start, end):
@@ -395,14 +434,23 @@ class BatchedOCR:
         with _span("submit.detect"):
             prob = self.detect_prob(pages, shared=pool is not None, stream=stream)
         jobs = []
-        shared_pages = self._last_pages if pool is not None else None
-        arena = self._shared_crop_arena(len(pages)) if pool is not None else None
-        cap = self.crop_cap
+        sh = self._last_shared if pool is not None else None
+        arena, cap = None, self.crop_cap
+        if sh is not None:
+            pb, ob = sh
+            arena = self._shared("crops", len(pages) * cap)
+            h0, w0 = pages[0].shape[:2]
+            if prob_override is not None:      # benchmarks with random detector weights: overwrite the D2H result
+                for i in range(len(pages)):
+                    np.copyto(prob[i], prob_override[i])
         for i, p in enumerate(pages):
-            pm = prob[i] if prob_override is None else prob_override[i]
-            job = (p if shared_pages is None else shared_pages[i], pm,
-                   None if quads_override is None else quads_override[i])
-            jobs.append(job if arena is None else job + (arena[i * cap:(i + 1) * cap],))
+            qo = None if quads_override is None else quads_override[i]
+            if sh is None:
+                jobs.append((p, prob[i] if prob_override is None else prob_override[i], qo))
+            else:      # descriptors only: the workers map the three buffers themselves
+                jobs.append((pb.desc(i * h0 * w0 * 3, (h0, w0, 3), np.uint8),
+                             ob.desc(i * prob[i].nbytes, prob[i].shape, np.float32), qo,
+                             arena.desc(i * cap, (cap,), np.uint8)))
         if pool is None:
             r = self.recognizer
             _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
@@ -422,7 +470,7 @@ class BatchedOCR:
             host = [f.result() for f in handle.futures]
         arena = handle.arena
         if arena is not None:
-            an = arena.numpy()
+            an = arena.np
             fixed = []
             for i, h in enumerate(host):
                 ref = h[2]
