@@ -288,8 +288,9 @@ def main():
     # ---------------- e2e through the public batched API from host pages
     e2e = None
     if not args.no_e2e:
-        for _ in range(2):
-            ocr(pages, prob_override=probs_syn)
+        # warm-up through the same entry point: touches every slot of the staging ring, starts the worker pool
+        for _ in ocr.stream([pages] * max(3, args.warmup), lookahead=2, prob_override=[probs_syn] * max(3, args.warmup)):
+            pass
         sync_all()
         t0 = time.perf_counter()
         n_words = 0

@@ -26,8 +26,8 @@ def main():
     probs = [synthetic_prob_map(q, (Hn, Wn), (1200, 1600)) for q in quads]
     ncpu = os.cpu_count() or 2
     ocr = pl.BatchedOCR(det, rec, det_batch=8, workers=max(2, min(32, ncpu - 2)))
-    for _ in range(2):
-        ocr(pages, prob_override=probs)
+    for _ in ocr.stream([pages] * 3, lookahead=look, prob_override=[probs] * 3):
+        pass
     torch.cuda.synchronize()
     pl.TRACE = []
     t0 = time.perf_counter()

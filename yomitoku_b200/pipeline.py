@@ -543,6 +543,8 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
     def producer():
         try:
             for k, pages in enumerate(batches):
+                with _span("producer.next_batch"):
+                    pass
                 po = None if prob_override is None else prob_override[k]
                 qo = None if quads_override is None else quads_override[k]
                 q.put(ocr.submit(pages, po, qo, stream=det_stream))
