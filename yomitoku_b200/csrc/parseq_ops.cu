@@ -211,144 +211,186 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool v
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
-template <int HD, int MASKED>
-__global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq,
-                                                         const __nv_bfloat16* __restrict__ K,
-                                                         const __nv_bfloat16* __restrict__ V, long long ldkv,
-                                                         __nv_bfloat16* __restrict__ O, long long ldo,
-                                                         const SeqDesc* __restrict__ seqs, float scale_log2) {
+template <int HD, int MASKED, int QT>
+__global__ void __launch_bounds__(QT * 2, QT == 128 ? 2 : 3) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq,
+                                                            const __nv_bfloat16* __restrict__ K,
+                                                            const __nv_bfloat16* __restrict__ V, long long ldkv,
+                                                            __nv_bfloat16* __restrict__ O, long long ldo,
+                                                            const SeqDesc* __restrict__ seqs, float scale_log2) {
+    // QT queries per CTA (one warp per 16), 64-key tiles double-buffered with cp.async.  Warps whose 16 queries lie
+    // beyond q_len only help loading; the MMA loops stop at the last 16-key group that holds a valid key.
     constexpr int LDS = HD + 8;  // padded row (bf16 elements): 16 B aligned rows, conflict-free ldmatrix
-    __shared__ __align__(16) __nv_bfloat16 sQ[64 * LDS];
-    __shared__ __align__(16) __nv_bfloat16 sK[64 * LDS];
-    __shared__ __align__(16) __nv_bfloat16 sV[64 * LDS];
+    constexpr int NT = QT * 2;   // threads
+    extern __shared__ __align__(16) unsigned char fa_smem[];
+    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);  // [QT][LDS]
+    __nv_bfloat16* sK = sQ + QT * LDS;                               // [2][64][LDS]
+    __nv_bfloat16* sV = sK + 2 * 64 * LDS;                           // [2][64][LDS]
     const SeqDesc sd = seqs[blockIdx.z];
-    const int q0 = blockIdx.x * 64;
+    const int q0 = blockIdx.x * QT;
     if (q0 >= sd.q_len) return;
     const int head = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool active = q0 + warp * 16 < sd.q_len;
     constexpr int CH = HD / 8;  // 16-byte chunks per row
-    // ---- Q tile
-    for (int i = threadIdx.x; i < 64 * CH; i += 128) {
-        const int r = i / CH, c = i - r * CH;
-        const bool ok = (q0 + r) < sd.q_len;
-        const __nv_bfloat16* src = Q + (long long)(sd.q_off + (ok ? q0 + r : 0)) * ldq + head * HD + c * 8;
-        cp_async16(smem_u32(&sQ[r * LDS + c * 8]), src, ok);
+    // keys this CTA can ever see (causal rows stop at their own index, rows 0/1 and the unmasked kernel see them all)
+    int k_end = sd.k_len;
+    if (MASKED) k_end = min(k_end, sd.kpad);
+    if (MASKED && q0 >= 2) k_end = min(k_end, q0 + QT);
+    const int ntiles = (k_end + 63) / 64;
+    auto load_kv = [&](int t, int buf) {
+        const int k0 = t * 64;
+        __nv_bfloat16* dK = sK + buf * 64 * LDS;
+        __nv_bfloat16* dV = sV + buf * 64 * LDS;
+        const int rows = min(64, ((k_end - k0 + 15) >> 4) << 4);  // only 16-key groups that are used
+        for (int i = threadIdx.x; i < rows * CH; i += NT) {
+            const int r = i / CH, c = i - r * CH;
+            const bool ok = (k0 + r) < sd.k_len;
+            const long long rowi = sd.k_base + (long long)(ok ? k0 + r : 0) * ldkv + head * HD + c * 8;
+            cp_async16(smem_u32(&dK[r * LDS + c * 8]), K + rowi, ok);
+            cp_async16(smem_u32(&dV[r * LDS + c * 8]), V + rowi, ok);
+        }
+    };
+    // ---- Q tile + first K/V tile
+    {
+        const int qrows = min(QT, ((sd.q_len - q0 + 15) >> 4) << 4);
+        for (int i = threadIdx.x; i < qrows * CH; i += NT) {
+            const int r = i / CH, c = i - r * CH;
+            const bool ok = (q0 + r) < sd.q_len;
+            const __nv_bfloat16* src = Q + (long long)(sd.q_off + (ok ? q0 + r : 0)) * ldq + head * HD + c * 8;
+            cp_async16(smem_u32(&sQ[r * LDS + c * 8]), src, ok);
+        }
     }
+    if (ntiles > 0) load_kv(0, 0);
     cp_async_commit();
     float o[HD / 8][4];
 #pragma unroll
     for (int i = 0; i < HD / 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     uint32_t qf[HD / 16][4];
-    bool q_loaded = false;
-    for (int k0 = 0; k0 < sd.k_len; k0 += 64) {
-        __syncthreads();  // previous tile fully consumed
-        for (int i = threadIdx.x; i < 64 * CH; i += 128) {
-            const int r = i / CH, c = i - r * CH;
-            const bool ok = (k0 + r) < sd.k_len;
-            const long long rowi = sd.k_base + (long long)(ok ? k0 + r : 0) * ldkv + head * HD + c * 8;
-            cp_async16(smem_u32(&sK[r * LDS + c * 8]), K + rowi, ok);
-            cp_async16(smem_u32(&sV[r * LDS + c * 8]), V + rowi, ok);
-        }
+    for (int t = 0; t < ntiles; ++t) {
+        const int k0 = t * 64, buf = t & 1;
+        if (t + 1 < ntiles) load_kv(t + 1, buf ^ 1);  // buffer buf^1 was released by the barrier ending tile t-1
         cp_async_commit();
-        cp_async_wait_all();
+        cp_async_wait_group<1>();  // tile t (and Q) landed; tile t+1 may still be in flight
         __syncthreads();
-        if (!q_loaded) {
+        if (active) {
+            const __nv_bfloat16* tK = sK + buf * 64 * LDS;
+            const __nv_bfloat16* tV = sV + buf * 64 * LDS;
+            if (t == 0) {
 #pragma unroll
-            for (int kk = 0; kk < HD / 16; ++kk) {
-                const int r = warp * 16 + (lane & 15);
-                const int c = kk * 16 + (lane >> 4) * 8;
-                ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], smem_u32(&sQ[r * LDS + c]));
-            }
-            q_loaded = true;
-        }
-        // ---- S = Q K^T for 16 queries x 64 keys
-        float s[8][4];
-#pragma unroll
-        for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
-#pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-#pragma unroll
-            for (int np = 0; np < 4; ++np) {  // pairs of 8-key groups
-                uint32_t b0, b1, b2, b3;
-                const int r = np * 16 + (lane & 7) + ((lane >> 4) << 3);
-                const int c = kk * 16 + ((lane >> 3) & 1) * 8;
-                ldmatrix_x4(b0, b1, b2, b3, smem_u32(&sK[r * LDS + c]));
-                mma_bf16_16816(s[2 * np], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b0, b1);
-                mma_bf16_16816(s[2 * np + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b2, b3);
-            }
-        }
-        // ---- online softmax (rows lane/4 and lane/4 + 8 of this warp's 16 queries)
-        float mx[2] = {-INFINITY, -INFINITY};
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int key = k0 + n * 8 + (lane & 3) * 2 + (e & 1);
-                bool vis = key < sd.k_len;
-                if (MASKED) {
-                    const int qi = q0 + warp * 16 + (lane >> 2) + (e >> 1) * 8;
-                    vis = vis && ((qi < 2) || (key <= qi)) && (key < sd.kpad);
+                for (int kk = 0; kk < HD / 16; ++kk) {
+                    const int r = warp * 16 + (lane & 15);
+                    const int c = kk * 16 + (lane >> 4) * 8;
+                    ldmatrix_x4(qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], smem_u32(&sQ[r * LDS + c]));
                 }
-                const float val = vis ? s[n][e] * scale_log2 : -INFINITY;
-                s[n][e] = val;
-                mx[e >> 1] = fmaxf(mx[e >> 1], val);
+            }
+            // 16-key groups of this tile this warp needs
+            int kmax = k_end;
+            if (MASKED && q0 + warp * 16 >= 2) kmax = min(kmax, q0 + warp * 16 + 16);
+            const int ng = min(4, (kmax - k0 + 15) >> 4);
+            if (ng > 0) {
+                // ---- S = Q K^T for 16 queries x 64 keys
+                float s[8][4];
+#pragma unroll
+                for (int n = 0; n < 8; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+                for (int kk = 0; kk < HD / 16; ++kk) {
+#pragma unroll
+                    for (int np = 0; np < 4; ++np) {  // pairs of 8-key groups
+                        if (np < ng) {
+                            uint32_t b0, b1, b2, b3;
+                            const int r = np * 16 + (lane & 7) + ((lane >> 4) << 3);
+                            const int c = kk * 16 + ((lane >> 3) & 1) * 8;
+                            ldmatrix_x4(b0, b1, b2, b3, smem_u32(&tK[r * LDS + c]));
+                            mma_bf16_16816(s[2 * np], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b0, b1);
+                            mma_bf16_16816(s[2 * np + 1], qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3], b2, b3);
+                        }
+                    }
+                }
+                // ---- online softmax (rows lane/4 and lane/4 + 8 of this warp's 16 queries)
+                float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int key = k0 + n * 8 + (lane & 3) * 2 + (e & 1);
+                        bool vis = key < sd.k_len;
+                        if (MASKED) {
+                            const int qi = q0 + warp * 16 + (lane >> 2) + (e >> 1) * 8;
+                            vis = vis && ((qi < 2) || (key <= qi)) && (key < sd.kpad);
+                        }
+                        const float val = vis ? s[n][e] * scale_log2 : -INFINITY;
+                        s[n][e] = val;
+                        mx[e >> 1] = fmaxf(mx[e >> 1], val);
+                    }
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
+                    mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
+                }
+                float corr[2], m_new[2], m_use[2];
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    m_new[h] = fmaxf(m_run[h], mx[h]);
+                    // a row that has seen no visible key yet keeps m = -inf: use 0 as the exponent offset (p = 0)
+                    m_use[h] = m_new[h] == -INFINITY ? 0.f : m_new[h];
+                    corr[h] = exp2f(m_run[h] - m_use[h]);  // m_run = -inf before the first visible key -> 0
+                    m_run[h] = m_new[h];
+                    l_run[h] *= corr[h];
+                }
+#pragma unroll
+                for (int i = 0; i < HD / 8; ++i) {
+                    o[i][0] *= corr[0];
+                    o[i][1] *= corr[0];
+                    o[i][2] *= corr[1];
+                    o[i][3] *= corr[1];
+                }
+                uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
+                float ls[2] = {0.f, 0.f};
+#pragma unroll
+                for (int n = 0; n < 8; ++n) {
+                    const float p0 = exp2f(s[n][0] - m_use[0]), p1 = exp2f(s[n][1] - m_use[0]);
+                    const float p2 = exp2f(s[n][2] - m_use[1]), p3 = exp2f(s[n][3] - m_use[1]);
+                    ls[0] += p0 + p1;
+                    ls[1] += p2 + p3;
+                    const int ks = n >> 1;
+                    if ((n & 1) == 0) {
+                        pf[ks][0] = pack_bf16(p0, p1);
+                        pf[ks][1] = pack_bf16(p2, p3);
+                    } else {
+                        pf[ks][2] = pack_bf16(p0, p1);
+                        pf[ks][3] = pack_bf16(p2, p3);
+                    }
+                }
+                l_run[0] += ls[0];
+                l_run[1] += ls[1];
+                // ---- O += P V
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks) {
+                    if (ks < ng) {
+#pragma unroll
+                        for (int dp = 0; dp < HD / 16; ++dp) {  // pairs of 8-wide output column groups
+                            uint32_t b0, b1, b2, b3;
+                            const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                            const int c = dp * 16 + (lane >> 4) * 8;
+                            ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(&tV[r * LDS + c]));
+                            mma_bf16_16816(o[2 * dp], pf[ks][0], pf[ks][1], pf[ks][2], pf[ks][3], b0, b1);
+                            mma_bf16_16816(o[2 * dp + 1], pf[ks][0], pf[ks][1], pf[ks][2], pf[ks][3], b2, b3);
+                        }
+                    }
+                }
             }
         }
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 1));
-            mx[h] = fmaxf(mx[h], __shfl_xor_sync(0xffffffffu, mx[h], 2));
-        }
-        float corr[2], m_new[2];
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-            m_new[h] = fmaxf(m_run[h], mx[h]);
-            corr[h] = exp2f(m_run[h] - m_new[h]);  // m_run = -inf on the first tile -> 0
-            m_run[h] = m_new[h];
-            l_run[h] *= corr[h];
-        }
-#pragma unroll
-        for (int i = 0; i < HD / 8; ++i) {
-            o[i][0] *= corr[0];
-            o[i][1] *= corr[0];
-            o[i][2] *= corr[1];
-            o[i][3] *= corr[1];
-        }
-        uint32_t pf[4][4];  // P as A fragments: 4 k-steps of 16 keys
-        float ls[2] = {0.f, 0.f};
-#pragma unroll
-        for (int n = 0; n < 8; ++n) {
-            const float p0 = exp2f(s[n][0] - m_new[0]), p1 = exp2f(s[n][1] - m_new[0]);
-            const float p2 = exp2f(s[n][2] - m_new[1]), p3 = exp2f(s[n][3] - m_new[1]);
-            ls[0] += p0 + p1;
-            ls[1] += p2 + p3;
-            const int ks = n >> 1;
-            if ((n & 1) == 0) {
-                pf[ks][0] = pack_bf16(p0, p1);
-                pf[ks][1] = pack_bf16(p2, p3);
-            } else {
-                pf[ks][2] = pack_bf16(p0, p1);
-                pf[ks][3] = pack_bf16(p2, p3);
-            }
-        }
-        l_run[0] += ls[0];
-        l_run[1] += ls[1];
-        // ---- O += P V
-#pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-            for (int dp = 0; dp < HD / 16; ++dp) {  // pairs of 8-wide output column groups
-                uint32_t b0, b1, b2, b3;
-                const int r = ks * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int c = dp * 16 + (lane >> 4) * 8;
-                ldmatrix_x4_trans(b0, b1, b2, b3, smem_u32(&sV[r * LDS + c]));
-                mma_bf16_16816(o[2 * dp], pf[ks][0], pf[ks][1], pf[ks][2], pf[ks][3], b0, b1);
-                mma_bf16_16816(o[2 * dp + 1], pf[ks][0], pf[ks][1], pf[ks][2], pf[ks][3], b2, b3);
-            }
-        }
+        __syncthreads();  // tile t fully consumed: its buffer may be refilled
     }
+    cp_async_wait_all();
+    if (!active) return;
     // ---- finalize
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -370,19 +412,42 @@ __global__ void __launch_bounds__(128) flash_attn_kernel(const __nv_bfloat16* __
     }
 }
 
+template <int HD, int MASKED, int QT>
+static int launch_fa(dim3 grid, const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, const __nv_bfloat16* v,
+                     long long ldkv, __nv_bfloat16* o, long long ldo, const SeqDesc* seqs, float scale_log2,
+                     cudaStream_t st) {
+    constexpr int smem = (QT + 4 * 64) * (HD + 8) * 2;
+    static bool attr = false;
+    if (!attr) {
+        if (cudaFuncSetAttribute(flash_attn_kernel<HD, MASKED, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+            cudaSuccess) {
+            set_error("flash attention: cannot reserve %d bytes of shared memory", smem);
+            return 1;
+        }
+        attr = true;
+    }
+    flash_attn_kernel<HD, MASKED, QT><<<grid, QT * 2, smem, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2);
+    return 0;
+}
+
 int launch_flash_attention(const void* Q, long long ldq, const void* K, const void* V, long long ldkv, void* O,
                            long long ldo, const SeqDesc* seqs, int nseq, int max_q_len, int heads, int head_dim,
                            int masked, cudaStream_t st) {
     if (nseq <= 0) return 0;
-    dim3 grid((max_q_len + 63) / 64, heads, nseq);
+    // 128-query tiles (8 warps) halve the K/V re-reads of the typical 92..200-token crop; short sequences keep 64
+    const int qt = max_q_len > 64 ? 128 : 64;
+    dim3 grid((max_q_len + qt - 1) / qt, heads, nseq);
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
     const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(Q), *k = reinterpret_cast<const __nv_bfloat16*>(K),
                         *v = reinterpret_cast<const __nv_bfloat16*>(V);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(O);
-#define YTK_FA(HD_)                                                                                          \
-    do {                                                                                                     \
-        if (masked) flash_attn_kernel<HD_, 1><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2); \
-        else flash_attn_kernel<HD_, 0><<<grid, 128, 0, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2);   \
+    int rc = 0;
+#define YTK_FA(HD_)                                                                                      \
+    do {                                                                                                 \
+        if (masked && qt == 128) rc = launch_fa<HD_, 1, 128>(grid, q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2, st); \
+        else if (masked) rc = launch_fa<HD_, 1, 64>(grid, q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2, st);          \
+        else if (qt == 128) rc = launch_fa<HD_, 0, 128>(grid, q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2, st);      \
+        else rc = launch_fa<HD_, 0, 64>(grid, q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2, st);                      \
     } while (0)
     switch (head_dim) {
         case 32: YTK_FA(32); break;
@@ -392,6 +457,7 @@ int launch_flash_attention(const void* Q, long long ldq, const void* K, const vo
         default: set_error("flash attention: head_dim %d unsupported (32/48/64/96)", head_dim); return 1;
     }
 #undef YTK_FA
+    if (rc) return 1;
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
