@@ -259,7 +259,7 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
     DM(kpad, 4 * B);
     DM(ids, 4 * R);
     DM(probs, 4 * R);
-    ar_block_ints = (size_t)(2 * R + 3 * B + cap_groups + 2);
+    ar_block_ints = (size_t)(2 * R + 3 * B + 2 * cap_groups + 3);
     DM(ar_block, 4 * ar_block_ints);
 #undef DM
     ar.tgt = ar_block;
@@ -270,6 +270,8 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
     ar.group_len = ar.has_eos + B;
     ar.n_active = ar.group_len + cap_groups;
     ar.step = ar.n_active + 1;
+    ar.open_rows = ar.step + 1;
+    ar.ticket = ar.open_rows + cap_groups;
     if (!host_flag) CK(cudaMallocHost(reinterpret_cast<void**>(&host_flag), 2 * sizeof(int)));
     for (int i = 0; i < 5; ++i)
         if (!ev[i]) CK(cudaEventCreate(&ev[i]));

@@ -962,8 +962,8 @@ __device__ int detect_repeat(const int* seq, int n, int period_max, int min_run_
 }
 
 __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict__ logits, long long ldl, int C, int S,
-                                                         const int* __restrict__ row_group, ArState a, int eos_id,
-                                                         int rep_on, int rep_period_max, int rep_min_run_p1,
+                                                         const int* __restrict__ row_group, int ngroups, ArState a,
+                                                         int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1,
                                                          int rep_min_repeats, const float* __restrict__ embed,
                                                          const float* __restrict__ pos_q, int D,
                                                          const float* __restrict__ g_c, const float* __restrict__ b_c,
@@ -972,135 +972,145 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
     __shared__ int si[8];
     __shared__ int s_tok;
     __shared__ float s_stat[2];
+    __shared__ float red[8];
+    __shared__ int s_last;
     const int row = blockIdx.x;
     const int i = *a.step;
     const int j = i + 1;
     const int grp = row_group[row];
-    if (a.group_len[grp] != 0) return;  // group already finished: nothing more happens to its rows
-    const float* lr = logits + (long long)row * ldl;
-    float best = -INFINITY;
-    int bi = 0x7fffffff;
-    {
-        const int nvec = C >> 2;
-        const float4* l4 = reinterpret_cast<const float4*>(lr);
-        for (int v = threadIdx.x; v < nvec; v += blockDim.x) {   // strict '>' keeps the smallest index (ascending)
-            const float4 x = __ldg(l4 + v);
-            if (x.x > best) { best = x.x; bi = 4 * v; }
-            if (x.y > best) { best = x.y; bi = 4 * v + 1; }
-            if (x.z > best) { best = x.z; bi = 4 * v + 2; }
-            if (x.w > best) { best = x.w; bi = 4 * v + 3; }
-        }
-        for (int c = 4 * nvec + threadIdx.x; c < C; c += blockDim.x) {
-            const float v = lr[c];
-            if (v > best) { best = v; bi = c; }
-        }
-    }
-    warp_argmax(best, bi);
-    if ((threadIdx.x & 31) == 0) {
-        sv[threadIdx.x >> 5] = best;
-        si[threadIdx.x >> 5] = bi;
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float v = sv[0];
-        int id = si[0];
-        for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
-            if (sv[w] > v || (sv[w] == v && si[w] < id)) {
-                v = sv[w];
-                id = si[w];
+    const bool running = a.group_len[grp] == 0;  // finished group: nothing more happens to its rows
+    if (running) {
+        const float* lr = logits + (long long)row * ldl;
+        float best = -INFINITY;
+        int bi = 0x7fffffff;
+        {
+            const int nvec = C >> 2;
+            const float4* l4 = reinterpret_cast<const float4*>(lr);
+            for (int v = threadIdx.x; v < nvec; v += blockDim.x) {   // strict '>' keeps the smallest index (ascending)
+                const float4 x = __ldg(l4 + v);
+                if (x.x > best) { best = x.x; bi = 4 * v; }
+                if (x.y > best) { best = x.y; bi = 4 * v + 1; }
+                if (x.z > best) { best = x.z; bi = 4 * v + 2; }
+                if (x.w > best) { best = x.w; bi = 4 * v + 3; }
             }
-        a.raw[row * S + i] = id;
-        int tok = id;
-        if (j < S) {
-            a.tgt[row * S + j] = id;
-            if (rep_on && !a.rep_done[row] && id != eos_id) {
-                int period = 0;
-                const int onset = detect_repeat(a.tgt + row * S + 1, j, rep_period_max, rep_min_run_p1, rep_min_repeats,
-                                                &period);
-                if (onset >= 0) {
-                    a.rep_cut[row] = onset + period;
-                    a.rep_done[row] = 1;
-                    a.tgt[row * S + j] = eos_id;
-                    tok = eos_id;
+            for (int c = 4 * nvec + threadIdx.x; c < C; c += blockDim.x) {
+                const float v = lr[c];
+                if (v > best) { best = v; bi = c; }
+            }
+        }
+        warp_argmax(best, bi);
+        if ((threadIdx.x & 31) == 0) {
+            sv[threadIdx.x >> 5] = best;
+            si[threadIdx.x >> 5] = bi;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float v = sv[0];
+            int id = si[0];
+            for (int w = 1; w < (int)(blockDim.x >> 5); ++w)
+                if (sv[w] > v || (sv[w] == v && si[w] < id)) {
+                    v = sv[w];
+                    id = si[w];
+                }
+            a.raw[row * S + i] = id;
+            int tok = id;
+            int has = a.has_eos[row];
+            if (j < S) {
+                a.tgt[row * S + j] = id;
+                if (rep_on && !a.rep_done[row] && id != eos_id) {
+                    int period = 0;
+                    const int onset = detect_repeat(a.tgt + row * S + 1, j, rep_period_max, rep_min_run_p1,
+                                                    rep_min_repeats, &period);
+                    if (onset >= 0) {
+                        a.rep_cut[row] = onset + period;
+                        a.rep_done[row] = 1;
+                        a.tgt[row * S + j] = eos_id;
+                        tok = eos_id;
+                    }
+                }
+                if (tok == eos_id) {
+                    a.has_eos[row] = 1;
+                    has = 1;
                 }
             }
-            if (tok == eos_id) a.has_eos[row] = 1;
+            if (!has) atomicAdd(&a.open_rows[grp], 1);
+            s_tok = tok;
         }
-        s_tok = tok;
-    }
-    __syncthreads();
-    if (j >= S) return;
-    // content embedding of position j: pos_queries[j-1] + sqrt(D) * E[tok], then LN_c (eps 1e-5)
-    const int tok = s_tok;
-    const float sq = sqrtf((float)D);
-    float loc[4];  // D <= 1024 with 256 threads
-    float s = 0.f;
-    for (int t = 0; t < 4; ++t) {
-        const int d = threadIdx.x + t * 256;
-        float v = 0.f;
-        if (d < D) v = pos_q[(long long)(j - 1) * D + d] + sq * embed[(long long)tok * D + d];
-        loc[t] = v;
-        s += v;
-    }
-    // block reduce (sum)
-    __shared__ float red[8];
+        __syncthreads();
+        if (j < S) {
+            // content embedding of position j: pos_queries[j-1] + sqrt(D) * E[tok], then LN_c (eps 1e-5)
+            const int tok = s_tok;
+            const float sq = sqrtf((float)D);
+            float loc[4];  // D <= 1024 with 256 threads
+            float s = 0.f;
+            for (int t = 0; t < 4; ++t) {
+                const int d = threadIdx.x + t * 256;
+                float v = 0.f;
+                if (d < D) v = pos_q[(long long)(j - 1) * D + d] + sq * embed[(long long)tok * D + d];
+                loc[t] = v;
+                s += v;
+            }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += red[w];
-        s_stat[0] = t / (float)D;
-    }
-    __syncthreads();
-    const float mean = s_stat[0];
-    float q = 0.f;
-    for (int t = 0; t < 4; ++t) {
-        const int d = threadIdx.x + t * 256;
-        if (d < D) q += (loc[t] - mean) * (loc[t] - mean);
-    }
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float t = 0.f;
+                for (int w = 0; w < 8; ++w) t += red[w];
+                s_stat[0] = t / (float)D;
+            }
+            __syncthreads();
+            const float mean = s_stat[0];
+            float q = 0.f;
+            for (int t = 0; t < 4; ++t) {
+                const int d = threadIdx.x + t * 256;
+                if (d < D) q += (loc[t] - mean) * (loc[t] - mean);
+            }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
-    __syncthreads();
+            for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float t = 0.f;
+                for (int w = 0; w < 8; ++w) t += red[w];
+                s_stat[1] = rsqrtf(t / (float)D + 1e-5f);
+            }
+            __syncthreads();
+            const float rstd = s_stat[1];
+            for (int t = 0; t < 4; ++t) {
+                const int d = threadIdx.x + t * 256;
+                if (d < D) cin[(long long)row * D + d] = __float2bfloat16((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
+            }
+        }
+    }
+    // ---- the CTA that finishes last closes the step: a group ends after step i when every one of its rows holds an
+    // EOS (parseq.py:245-250).  Every CTA read *a.step / group_len before taking its ticket, so the updates below
+    // cannot be seen by this launch.
     if (threadIdx.x == 0) {
-        float t = 0.f;
-        for (int w = 0; w < 8; ++w) t += red[w];
-        s_stat[1] = rsqrtf(t / (float)D + 1e-5f);
+        __threadfence();
+        s_last = atomicAdd(a.ticket, 1) == (int)gridDim.x - 1;
     }
     __syncthreads();
-    const float rstd = s_stat[1];
-    for (int t = 0; t < 4; ++t) {
-        const int d = threadIdx.x + t * 256;
-        if (d < D) cin[(long long)row * D + d] = __float2bfloat16((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
-    }
-}
-
-__global__ void ar_groups_kernel(const int* __restrict__ row_group, int B, int ngroups, ArState a, int S) {
-    // single block: a group finishes after step i when every one of its rows holds an EOS (parseq.py:245-250)
-    extern __shared__ int open_rows[];  // per group: rows without EOS
-    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) open_rows[g] = 0;
-    __syncthreads();
-    for (int r = threadIdx.x; r < B; r += blockDim.x)
-        if (!a.has_eos[r]) atomicAdd(&open_rows[row_group[r]], 1);
-    __syncthreads();
-    const int i = *a.step;
-    const int j = i + 1;
+    if (!s_last) return;
+    __threadfence();
     __shared__ int active;
     if (threadIdx.x == 0) active = 0;
     __syncthreads();
     for (int g = threadIdx.x; g < ngroups; g += blockDim.x) {
         if (a.group_len[g] == 0) {
-            if (j >= S) a.group_len[g] = S;             // ran all the steps
-            else if (open_rows[g] == 0) a.group_len[g] = j;  // logits has j entries, tgt_in for refinement length j
+            const int open = atomicExch(&a.open_rows[g], 0);
+            if (j >= S) a.group_len[g] = S;          // ran all the steps
+            else if (open == 0) a.group_len[g] = j;  // logits has j entries, tgt_in for refinement length j
             else atomicAdd(&active, 1);
+        } else {
+            a.open_rows[g] = 0;
         }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
         *a.n_active = active;
         *a.step = i + 1;
+        *a.ticket = 0;
     }
 }
 
@@ -1112,11 +1122,10 @@ int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, c
         set_error("ar_control: D=%d too large", D);
         return 1;
     }
-    ar_control_kernel<<<B, 256, 0, st>>>(logits, ldl, C, S, row_group, a, eos_id, rep_on, rep_period_max,
+    ar_control_kernel<<<B, 256, 0, st>>>(logits, ldl, C, S, row_group, ngroups, a, eos_id, rep_on, rep_period_max,
                                          rep_min_run_p1, rep_min_repeats, embed, pos_q, D, g_c, b_c,
                                          reinterpret_cast<__nv_bfloat16*>(cin));
-    ar_groups_kernel<<<1, 256, sizeof(int) * ngroups, st>>>(row_group, B, ngroups, a, S);
-    count_launch(2);
+    count_launch(1);
     return cudaGetLastError() != cudaSuccess;
 }
 

@@ -66,6 +66,8 @@ struct ArState {
     int* group_len;  // [G] number of AR steps the group ran (0 = still running)
     int* n_active;   // [1] groups still running
     int* step;       // [1] current step i
+    int* open_rows;  // [G] scratch: rows of the group that hold no EOS yet (zero between steps)
+    int* ticket;     // [1] scratch: CTAs of ar_control that are done with the current step (zero between steps)
 };
 // Arg-max over the head logits + the reference's per-step control logic (parseq.py:220-250) + content embedding of
 // the emitted token (text_embed * sqrt(D) + pos_queries[j-1]) normalised by LN_c -> cin bf16 [B, D].
