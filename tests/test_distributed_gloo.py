@@ -79,6 +79,88 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+class _StubModel:
+    """Stands in for models.PARSeq: both device entry points, computed from the crop pixels on the host."""
+    refine_iters = 1
+    max_label_length = 100
+
+    def __init__(self, cfg):
+        self.cfg = cfg
+
+    def pack_crops(self, canvases, padded, groups):
+        return canvases, sum(c.size for c in canvases), None, 0
+
+    def run_packed(self, buf, total, descs, n, n_groups, stream=None):
+        ids, probs = _fake_recognise(buf)
+        return ids, probs, np.full((n_groups,), 101, np.int32)
+
+    def run_packed_ptr(self, ptr, on_device, total, descs, n, n_groups, stream=None):
+        import ctypes
+        raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
+        canv = [raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3].reshape(32, int(d["w"]), 3)
+                for d in descs]
+        ids, probs = _fake_recognise(canv)
+        return ids, probs, np.full((n_groups,), 101, np.int32)
+
+
+def _worker_pipeline(rank, world, port, q):
+    """BatchedOCR._run_groups across 2 ranks with crops that live in the shared arena (stub recognizer)."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from yomitoku_b200 import pipeline as pl
+        from yomitoku_b200.config import TextRecognizerPARSeqLargeV41Config, to_config
+        cfg = to_config(TextRecognizerPARSeqLargeV41Config())
+
+        class Rec:
+            _cfg = cfg
+            model = _StubModel(cfg)
+
+        ocr = pl.BatchedOCR(None, Rec(), workers=1)
+        rng = np.random.default_rng(10 + rank)
+        arena = pl._SharedBuf(1 << 20)
+        n_groups = 7 if rank == 0 else 1
+        groups, expect, off = [], [], 0
+        for gi in range(n_groups):
+            n = int(rng.integers(1, 5))
+            widths = (rng.integers(9, 30, size=n) * 8).tolist()
+            offs = []
+            canv = []
+            for w in widths:
+                c = rng.integers(0, 256, size=(32, w, 3), dtype=np.uint8)
+                arena.np[off:off + c.size] = c.reshape(-1)
+                offs.append(off)
+                off += c.size
+                canv.append(c)
+            groups.append((widths, [max(widths)] * n, np.asarray(offs, np.int64)))
+            expect.append(_fake_recognise(canv))
+        res = ocr._run_groups(groups, None, arena, 32)
+        for (ids, probs, glen), (eid, ep) in zip(res, expect):
+            assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101
+        arena.close()
+        q.put((rank, "ok", None))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipeline_groups_arena_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pipeline, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, status, _ in out:
+        assert status == "ok", status
+
+
 def test_crop_scatter_gather_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -350,20 +350,40 @@ class BatchedOCR:
             start = end
         return out
 
-    def _run_groups(self, groups, stream=None):
+    def _run_groups(self, groups, stream=None, arena=None, height=32):
         """Recognise groups, spreading them over all ranks when torch.distributed is initialised (crop scatter /
-        result gather over NCCL, yomitoku_b200/parallel.py); results come back in `groups` order."""
+        result gather over NCCL, yomitoku_b200/parallel.py); results come back in `groups` order.  Groups are
+        (canvases, padded widths) or, with `arena`, (widths, padded widths, arena offsets); only groups that leave this
+        rank are ever materialised as pixel arrays."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            if arena is not None:
+                return self._run_groups_arena(groups, arena, height, stream)
             return self._run_groups_local(groups, stream)
         from . import parallel as par
         cfg = self.recognizer._cfg
         ph, pw = cfg.encoder.patch_size
         gh = cfg.data.img_size[0] // ph
-        costs = [sum(gh * (p // pw) for p in g[1]) for g in groups]
-        assign = par.balance_groups(par.gather_costs(costs), dist.get_world_size())[dist.get_rank()]
-        work = par.exchange_groups(groups, assign, cfg.data.img_size[0])
-        res = self._run_groups_local([(w[2], w[3]) for w in work], stream)
+        rank = dist.get_rank()
+        costs = [gh * (int(np.sum(g[1])) // pw) for g in groups]
+        assign = par.balance_groups(par.gather_costs(costs), dist.get_world_size())[rank]
+
+        def pixels(g):
+            if arena is None:
+                return g[0]
+            an = arena.np
+            return [an[int(o):int(o) + height * int(w) * 3].reshape(height, int(w), 3) for w, o in zip(g[0], g[2])]
+
+        send = [(pixels(g) if assign[k] != rank else None, g[1]) for k, g in enumerate(groups)]
+        work = par.exchange_groups(send, assign, cfg.data.img_size[0])
+        mine = [k for k in range(len(groups)) if assign[k] == rank]        # exchange_groups lists own groups first
+        if arena is not None:
+            res = self._run_groups_arena([groups[k] for k in mine], arena, height, stream)
+        else:
+            res = self._run_groups_local([groups[k] for k in mine], stream)
+        foreign = work[len(mine):]
+        if foreign:
+            res = res + self._run_groups_local([(w[2], w[3]) for w in foreign], stream)
         S = cfg.max_label_length + 1
         # group_len travels as an extra column pair so that refine_iters == 0 keeps working across ranks
         packed = []
@@ -379,9 +399,7 @@ class BatchedOCR:
         exactly like TextRecognizer._run_plan."""
         rec = self.recognizer
         cfg = rec._cfg
-        import torch.distributed as dist
-        distributed = dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
-        in_arena = arena is not None and not distributed and all(isinstance(p[0], _PageCrops) for p in per_page)
+        in_arena = arena is not None and all(isinstance(p[0], _PageCrops) for p in per_page)
         groups, owner, orders = [], [], []
         for pi, (canv, cw, n_quads) in enumerate(per_page):
             order = None
@@ -399,8 +417,8 @@ class BatchedOCR:
                     groups.append(([canv[i] for i in b], [padded[i] for i in b]))
                 owner.append(pi)
             orders.append(order)
-        res = self._run_groups_arena(groups, arena, per_page[0][0].height if per_page else 32, stream) \
-            if in_arena else self._run_groups(groups, stream)
+        res = self._run_groups(groups, stream, arena if in_arena else None,
+                               per_page[0][0].height if in_arena and per_page else 32)
         S = cfg.max_label_length + 1
         out = []
         for pi in range(len(per_page)):
