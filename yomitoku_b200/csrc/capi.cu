@@ -15,12 +15,14 @@ struct ytk_parseq {
     ytk::ParseqModel model;
     ytk::ParseqEngine engine;
     std::mutex mu;
+    int device = 0;  // the device current at create(); every later call binds the calling thread to it
 };
 
 struct ytk_dbnet {
     ytk::DbnetModel model;
     std::map<std::tuple<int, int, int>, std::unique_ptr<ytk::DbnetEngine>> engines;
     std::mutex mu;
+    int device = 0;
     int shortest = 1280, limit = 1600;
     void* stage = nullptr;  // device staging for host inputs
     size_t stage_bytes = 0;
@@ -119,6 +121,7 @@ int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size
         ws.map[tensors[i].name] = v;
     }
     auto h = std::make_unique<ytk_dbnet>();
+    cudaGetDevice(&h->device);
     h->shortest = shortest_size;
     h->limit = limit_size;
     if (h->model.load(ws)) return YTK_ERR;
@@ -140,6 +143,7 @@ int ytk_dbnet_input_size(const ytk_dbnet* h, int H0, int W0, int* Hn, int* Wn) {
 int ytk_dbnet_forward_u8(ytk_dbnet* h, const uint8_t* pages, int pages_on_device, int n_pages, int H0, int W0,
                          float* prob_out, int out_on_device, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     int Hn, Wn;
     ytk::dbnet_input_size(H0, W0, h->shortest, h->limit, &Hn, &Wn);
@@ -171,6 +175,7 @@ int ytk_dbnet_forward_u8(ytk_dbnet* h, const uint8_t* pages, int pages_on_device
 int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x, int x_on_device, int n, int H, int W, float* prob_out,
                           int out_on_device, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     ytk::DbnetEngine* e = get_engine(h, n, H, W);
     if (!e) return YTK_ERR;
@@ -193,6 +198,7 @@ int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x, int x_on_device, int n, 
 
 double ytk_dbnet_flops(ytk_dbnet* h, int n_pages, int Hn, int Wn) {
     std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
     ytk::DbnetEngine* e = get_engine(h, n_pages, Hn, Wn);
     return e ? e->flops : -1.0;
 }
@@ -200,6 +206,7 @@ double ytk_dbnet_flops(ytk_dbnet* h, int n_pages, int Hn, int Wn) {
 int ytk_dbnet_debug_tensor(ytk_dbnet* h, int n_pages, int Hn, int Wn, const char* name, float* host_out,
                            long long capacity, int* shape4) {
     std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
     ytk::DbnetEngine* e = get_engine(h, n_pages, Hn, Wn);
     if (!e) return YTK_ERR;
     auto it = e->dbg.find(name);
@@ -246,6 +253,7 @@ int ytk_parseq_create(const ytk_tensor* tensors, int n_tensors, const ytk_parseq
                      cfg->dec_mlp_ratio, cfg->refine_iters, cfg->repetition_stop, cfg->rep_period_max,
                      cfg->rep_min_run_p1, cfg->rep_min_repeats};
     auto h = std::make_unique<ytk_parseq>();
+    cudaGetDevice(&h->device);
     if (h->model.load(ws, c)) return YTK_ERR;
     h->engine.m = &h->model;
     *out = h.release();
@@ -256,6 +264,7 @@ void ytk_parseq_destroy(ytk_parseq* h) { delete h; }
 
 void ytk_parseq_set_refine_iters(ytk_parseq* h, int refine_iters) {
     std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
     h->model.cfg.refine_iters = refine_iters;
 }
 
@@ -263,6 +272,7 @@ int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops_ptr, int crops_
                              const ytk_crop* crops, int n_crops, int n_groups, int32_t* ids_out, float* probs_out,
                              int32_t* group_len_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
     if (h->model.cfg.refine_iters > 1) {
         ytk::set_error("refine_iters > 1 is not implemented on the device path");
         return YTK_ERR;
@@ -294,6 +304,7 @@ int ytk_parseq_forward_f32(ytk_parseq* h, const float* images, int images_on_dev
                            int logits_on_device, int32_t* ids_out, float* probs_out, int32_t* steps_out,
                            int32_t* rep_cut_out, float* memory_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
     if (h->model.cfg.refine_iters > 1) {
         ytk::set_error("refine_iters > 1 is not implemented on the device path");
         return YTK_ERR;

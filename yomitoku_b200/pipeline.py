@@ -557,9 +557,13 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
     rec_stream = torch.cuda.Stream() if torch.cuda.is_available() else None
     q = queue.Queue(maxsize=max(1, lookahead))
     err = []
+    dev = torch.cuda.current_device() if torch.cuda.is_available() else None
 
     def producer():
         try:
+            if dev is not None:
+                torch.cuda.set_device(dev)      # the current device is per host thread
+
             for k, pages in enumerate(batches):
                 with _span("producer.next_batch"):
                     pass
@@ -575,6 +579,8 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
 
     def recognizer():
         try:
+            if dev is not None:
+                torch.cuda.set_device(dev)
             while True:
                 h = q.get()
                 if h is None:
