@@ -61,6 +61,43 @@ static int load_linear(std::vector<void*>& owned, const float* w, const float* b
     return 0;
 }
 
+// Generalised load: output row n goes to row rowmap[n] of an [Np][Kp] matrix (identity when null), input feature k to
+// column colmap[k]; rows may be scaled (softmax-scale folding).  Rows / columns that nothing maps to are zero, so
+// padded features stay exactly zero through the whole network.
+static int load_linear_ex(std::vector<void*>& owned, const float* w, const float* b, int N, int K,
+                          const std::vector<int>* rowmap, int Np, const std::vector<int>* colmap, int Kp,
+                          const std::vector<float>* rowscale, LinearW* out) {
+    if (!rowmap && !colmap && !rowscale && Np == N && Kp == K) return load_linear(owned, w, b, N, K, out);
+    std::vector<float> w2((size_t)Np * Kp, 0.f), b2(Np, 0.f);
+    for (int n = 0; n < N; ++n) {
+        const int r = rowmap ? (*rowmap)[n] : n;
+        const float sc = rowscale ? (*rowscale)[n] : 1.f;
+        float* dst = &w2[(size_t)r * Kp];
+        const float* src = w + (size_t)n * K;
+        if (colmap)
+            for (int k = 0; k < K; ++k) dst[(*colmap)[k]] = src[k] * sc;
+        else
+            for (int k = 0; k < K; ++k) dst[k] = src[k] * sc;
+        b2[r] = b[n] * sc;
+    }
+    return load_linear(owned, w2.data(), b2.data(), Np, Kp, out);
+}
+
+static int up_padded(std::vector<void*>& owned, const float* src, long long rows, int D, int Dp, float scale,
+                     float** dev) {
+    void* d = nullptr;
+    if (D == Dp && scale == 1.f) {
+        if (up(owned, src, (size_t)rows * D * 4, &d)) return 1;
+    } else {
+        std::vector<float> t((size_t)rows * Dp, 0.f);
+        for (long long r = 0; r < rows; ++r)
+            for (int k = 0; k < D; ++k) t[(size_t)r * Dp + k] = src[(size_t)r * D + k] * scale;
+        if (up(owned, t.data(), t.size() * 4, &d)) return 1;
+    }
+    *dev = reinterpret_cast<float*>(d);
+    return 0;
+}
+
 static int load_linear_named(std::vector<void*>& owned, const WeightSet& ws, const std::string& wn,
                              const std::string& bn, int N, int K, LinearW* out) {
     const TensorView *w = ws.need(wn, (long long)N * K), *b = ws.need(bn, N);
@@ -68,15 +105,11 @@ static int load_linear_named(std::vector<void*>& owned, const WeightSet& ws, con
     return load_linear(owned, w->data, b->data, N, K, out);
 }
 
-static int load_ln(std::vector<void*>& owned, const WeightSet& ws, const std::string& p, int D, LnW* out) {
+static int load_ln(std::vector<void*>& owned, const WeightSet& ws, const std::string& p, int D, int Dp, LnW* out) {
     const TensorView *g = ws.need(p + ".weight", D), *b = ws.need(p + ".bias", D);
     if (!g || !b) return 1;
-    void* d = nullptr;
-    if (up(owned, g->data, (size_t)D * 4, &d)) return 1;
-    out->g = reinterpret_cast<float*>(d);
-    if (up(owned, b->data, (size_t)D * 4, &d)) return 1;
-    out->b = reinterpret_cast<float*>(d);
-    return 0;
+    // zero gamma / beta on the padded features: LayerNorm then writes exact zeros there
+    return up_padded(owned, g->data, 1, D, Dp, 1.f, &out->g) || up_padded(owned, b->data, 1, D, Dp, 1.f, &out->b);
 }
 
 static void host_ln(const float* x, const float* g, const float* b, int D, float eps, float* y) {
@@ -91,24 +124,56 @@ static void host_ln(const float* x, const float* g, const float* b, int D, float
 
 int ParseqModel::load(const WeightSet& ws, const ParseqCfg& c) {
     cfg = c;
-    const int D = c.D;
+    const int D = c.D;  // real embed_dim
+    Dr = D;
     S = c.max_label_length + 1;
     C = c.num_tokens - 2;
     gh = c.img_h / c.ph;
     full_gw = c.img_w / c.pw;
-    if (D % 64 != 0 || (D / c.enc_heads) % 16 != 0 || (D / c.dec_heads) % 8 != 0 || D / c.enc_heads > 96 ||
-        D / c.dec_heads > 96 || D > 1024) {
-        set_error("PARSeq device engine supports embed_dim %% 64 == 0 and head dims 32/48/64/96 (got D=%d, heads %d/%d)",
-                  D, c.enc_heads, c.dec_heads);
+    if (D % c.enc_heads != 0 || D % c.dec_heads != 0 || (D & 3) != 0) {
+        set_error("PARSeq: embed_dim %d must be a multiple of 4 and of the head counts %d/%d", D, c.enc_heads,
+                  c.dec_heads);
         return 1;
     }
-    if (S != 101) {
-        // kMaxS in parseq_ops.cu; shorter label lengths fit, longer do not
-        if (S > 101) {
-            set_error("max_label_length %d > 100 unsupported", c.max_label_length);
-            return 1;
-        }
+    // The kernels want embed_dim % 64 == 0 and head dims that are multiples of 16 (tensor-core fragments).  Models
+    // that do not fit (parseq-tiny: D 368, 8 heads of 46) run as the mathematically identical zero-padded model:
+    // every head is padded to hdp features whose weights are zero, the residual stream to Dp = heads * hdp columns
+    // that stay exactly zero, LayerNorm statistics use the real D (launch_layernorm's d_real), and the 1/sqrt(hd)
+    // and sqrt(D) factors of the real model are folded into the q projections / the embedding table.
+    const int hd_e = D / c.enc_heads, hd_d = D / c.dec_heads;
+    int hdp_e = (hd_e + 15) / 16 * 16;
+    while ((c.enc_heads * hdp_e) % 64 != 0) hdp_e += 16;
+    const int Dp = c.enc_heads * hdp_e;
+    const int hdp_d = Dp / c.dec_heads;
+    if (Dp % c.dec_heads != 0 || hdp_d < hd_d || hdp_d % 16 != 0 || hdp_e > 96 || hdp_d > 96 || Dp > 1024) {
+        set_error("PARSeq device engine: cannot lay out embed_dim %d with %d/%d heads (padded width %d, head dims %d/%d; "
+                  "supported head dims 32/48/64/96, width <= 1024)",
+                  D, c.enc_heads, c.dec_heads, Dp, hdp_e, hdp_d);
+        return 1;
     }
+    if (hdp_e != 32 && hdp_e != 48 && hdp_e != 64 && hdp_e != 96) {
+        set_error("PARSeq device engine: encoder head dim %d (padded %d) unsupported (32/48/64/96)", hd_e, hdp_e);
+        return 1;
+    }
+    if (hdp_d != 32 && hdp_d != 48 && hdp_d != 64 && hdp_d != 96) {
+        set_error("PARSeq device engine: decoder head dim %d (padded %d) unsupported (32/48/64/96)", hd_d, hdp_d);
+        return 1;
+    }
+    if (S > 101) {  // kMaxS in parseq_ops.cu; shorter label lengths fit, longer do not
+        set_error("max_label_length %d > 100 unsupported", c.max_label_length);
+        return 1;
+    }
+    cfg.D = Dp;
+    const bool padded = Dp != D;
+    std::vector<int> he(D), hdm(D);  // real feature -> padded per-head position (encoder / decoder head layout)
+    for (int i = 0; i < D; ++i) {
+        he[i] = (i / hd_e) * hdp_e + i % hd_e;
+        hdm[i] = (i / hd_d) * hdp_d + i % hd_d;
+    }
+    const std::vector<int>* HE = padded ? &he : nullptr;
+    const std::vector<int>* HD = padded ? &hdm : nullptr;
+    const float qs_e = std::sqrt((float)hdp_e / (float)hd_e), qs_d = std::sqrt((float)hdp_d / (float)hd_d);
+    const float es = std::sqrt((float)D / (float)Dp);  // kernels multiply the embedding by sqrt(Dp)
     const std::string e = "encoder.";
     // patch embedding conv as a GEMM: weight [D,3,ph,pw] flattened to K = 3*ph*pw (order c,py,px)
     {
@@ -116,66 +181,115 @@ int ParseqModel::load(const WeightSet& ws, const ParseqCfg& c) {
         const TensorView *w = ws.need(e + "patch_embed.proj.weight", (long long)D * K),
                          *b = ws.need(e + "patch_embed.proj.bias", D);
         if (!w || !b) return 1;
-        if (load_linear(owned, w->data, b->data, D, K, &patch)) return 1;
+        if (load_linear_ex(owned, w->data, b->data, D, K, nullptr, Dp, nullptr, K, nullptr, &patch)) return 1;
         Kpatch = patch.K;
         const TensorView* pe = ws.need(e + "pos_embed", (long long)gh * full_gw * D);
         if (!pe) return 1;
-        void* d = nullptr;
-        if (up(owned, pe->data, (size_t)gh * full_gw * D * 4, &d)) return 1;
-        pos_embed = reinterpret_cast<float*>(d);
+        if (up_padded(owned, pe->data, (long long)gh * full_gw, D, Dp, 1.f, &pos_embed)) return 1;
     }
     blocks.resize(c.enc_depth);
+    std::vector<int> qkv_map;
+    std::vector<float> qkv_scale;
+    if (padded) {
+        qkv_map.resize(3 * D);
+        qkv_scale.assign(3 * D, 1.f);
+        for (int w3 = 0; w3 < 3; ++w3)
+            for (int i = 0; i < D; ++i) {
+                qkv_map[w3 * D + i] = w3 * Dp + he[i];
+                if (w3 == 0) qkv_scale[i] = qs_e;
+            }
+    }
     for (int i = 0; i < c.enc_depth; ++i) {
         const std::string p = e + "blocks." + std::to_string(i) + ".";
         EncBlock& bk = blocks[i];
-        if (load_ln(owned, ws, p + "norm1", D, &bk.ln1) || load_ln(owned, ws, p + "norm2", D, &bk.ln2)) return 1;
-        if (load_linear_named(owned, ws, p + "attn.qkv.weight", p + "attn.qkv.bias", 3 * D, D, &bk.qkv)) return 1;
-        if (load_linear_named(owned, ws, p + "attn.proj.weight", p + "attn.proj.bias", D, D, &bk.proj)) return 1;
-        if (load_linear_named(owned, ws, p + "mlp.fc1.weight", p + "mlp.fc1.bias", c.mlp_ratio * D, D, &bk.fc1)) return 1;
-        if (load_linear_named(owned, ws, p + "mlp.fc2.weight", p + "mlp.fc2.bias", D, c.mlp_ratio * D, &bk.fc2)) return 1;
+        if (load_ln(owned, ws, p + "norm1", D, Dp, &bk.ln1) || load_ln(owned, ws, p + "norm2", D, Dp, &bk.ln2))
+            return 1;
+        const TensorView *qw = ws.need(p + "attn.qkv.weight", 3LL * D * D), *qb = ws.need(p + "attn.qkv.bias", 3 * D),
+                         *pw_ = ws.need(p + "attn.proj.weight", (long long)D * D),
+                         *pb = ws.need(p + "attn.proj.bias", D),
+                         *w1 = ws.need(p + "mlp.fc1.weight", (long long)c.mlp_ratio * D * D),
+                         *b1 = ws.need(p + "mlp.fc1.bias", c.mlp_ratio * D),
+                         *w2 = ws.need(p + "mlp.fc2.weight", (long long)c.mlp_ratio * D * D),
+                         *b2 = ws.need(p + "mlp.fc2.bias", D);
+        if (!qw || !qb || !pw_ || !pb || !w1 || !b1 || !w2 || !b2) return 1;
+        if (load_linear_ex(owned, qw->data, qb->data, 3 * D, D, padded ? &qkv_map : nullptr, 3 * Dp, nullptr, Dp,
+                           padded ? &qkv_scale : nullptr, &bk.qkv))
+            return 1;
+        if (load_linear_ex(owned, pw_->data, pb->data, D, D, nullptr, Dp, HE, Dp, nullptr, &bk.proj)) return 1;
+        if (load_linear_ex(owned, w1->data, b1->data, c.mlp_ratio * D, D, nullptr, c.mlp_ratio * D, nullptr, Dp, nullptr,
+                           &bk.fc1))
+            return 1;
+        if (load_linear_ex(owned, w2->data, b2->data, D, c.mlp_ratio * D, nullptr, Dp, nullptr, c.mlp_ratio * D, nullptr,
+                           &bk.fc2))
+            return 1;
     }
-    if (load_ln(owned, ws, e + "norm", D, &enc_norm)) return 1;
+    if (load_ln(owned, ws, e + "norm", D, Dp, &enc_norm)) return 1;
     const std::string d = "decoder.layers.0.";
-    if (load_ln(owned, ws, d + "norm1", D, &norm1) || load_ln(owned, ws, d + "norm2", D, &norm2) ||
-        load_ln(owned, ws, d + "norm_c", D, &norm_c) || load_ln(owned, ws, "decoder.norm", D, &dec_norm))
+    if (load_ln(owned, ws, d + "norm1", D, Dp, &norm1) || load_ln(owned, ws, d + "norm2", D, Dp, &norm2) ||
+        load_ln(owned, ws, d + "norm_c", D, Dp, &norm_c) || load_ln(owned, ws, "decoder.norm", D, Dp, &dec_norm))
         return 1;
     const TensorView *sw = ws.need(d + "self_attn.in_proj_weight", 3LL * D * D),
                      *sb = ws.need(d + "self_attn.in_proj_bias", 3 * D),
                      *cw = ws.need(d + "cross_attn.in_proj_weight", 3LL * D * D),
                      *cb = ws.need(d + "cross_attn.in_proj_bias", 3 * D);
     if (!sw || !sb || !cw || !cb) return 1;
-    if (load_linear(owned, sw->data + (size_t)D * D, sb->data + D, 2 * D, D, &self_kv)) return 1;
-    if (load_linear(owned, cw->data, cb->data, D, D, &cross_q)) return 1;
-    if (load_linear(owned, cw->data + (size_t)D * D, cb->data + D, 2 * D, D, &cross_kv)) return 1;
-    if (load_linear_named(owned, ws, d + "self_attn.out_proj.weight", d + "self_attn.out_proj.bias", D, D, &self_out))
+    std::vector<int> kv_map;
+    std::vector<float> q_scale;
+    if (padded) {
+        kv_map.resize(2 * D);
+        for (int w2 = 0; w2 < 2; ++w2)
+            for (int i = 0; i < D; ++i) kv_map[w2 * D + i] = w2 * Dp + hdm[i];
+        q_scale.assign(D, qs_d);
+    }
+    const std::vector<int>* KV = padded ? &kv_map : nullptr;
+    if (load_linear_ex(owned, sw->data + (size_t)D * D, sb->data + D, 2 * D, D, KV, 2 * Dp, nullptr, Dp, nullptr,
+                       &self_kv))
         return 1;
-    if (load_linear_named(owned, ws, d + "cross_attn.out_proj.weight", d + "cross_attn.out_proj.bias", D, D, &cross_out))
+    if (load_linear_ex(owned, cw->data, cb->data, D, D, HD, Dp, nullptr, Dp, padded ? &q_scale : nullptr, &cross_q))
         return 1;
-    if (load_linear_named(owned, ws, d + "linear1.weight", d + "linear1.bias", c.dec_mlp_ratio * D, D, &lin1)) return 1;
-    if (load_linear_named(owned, ws, d + "linear2.weight", d + "linear2.bias", D, c.dec_mlp_ratio * D, &lin2)) return 1;
-    if (load_linear_named(owned, ws, "head.weight", "head.bias", C, D, &head)) return 1;
+    if (load_linear_ex(owned, cw->data + (size_t)D * D, cb->data + D, 2 * D, D, KV, 2 * Dp, nullptr, Dp, nullptr,
+                       &cross_kv))
+        return 1;
+    {
+        const TensorView *ow = ws.need(d + "self_attn.out_proj.weight", (long long)D * D),
+                         *ob = ws.need(d + "self_attn.out_proj.bias", D),
+                         *xw = ws.need(d + "cross_attn.out_proj.weight", (long long)D * D),
+                         *xb = ws.need(d + "cross_attn.out_proj.bias", D),
+                         *l1w = ws.need(d + "linear1.weight", (long long)c.dec_mlp_ratio * D * D),
+                         *l1b = ws.need(d + "linear1.bias", c.dec_mlp_ratio * D),
+                         *l2w = ws.need(d + "linear2.weight", (long long)c.dec_mlp_ratio * D * D),
+                         *l2b = ws.need(d + "linear2.bias", D), *hw = ws.need("head.weight", (long long)C * D),
+                         *hb_ = ws.need("head.bias", C);
+        if (!ow || !ob || !xw || !xb || !l1w || !l1b || !l2w || !l2b || !hw || !hb_) return 1;
+        if (load_linear_ex(owned, ow->data, ob->data, D, D, nullptr, Dp, HD, Dp, nullptr, &self_out)) return 1;
+        if (load_linear_ex(owned, xw->data, xb->data, D, D, nullptr, Dp, HD, Dp, nullptr, &cross_out)) return 1;
+        if (load_linear_ex(owned, l1w->data, l1b->data, c.dec_mlp_ratio * D, D, nullptr, c.dec_mlp_ratio * D, nullptr,
+                           Dp, nullptr, &lin1))
+            return 1;
+        if (load_linear_ex(owned, l2w->data, l2b->data, D, c.dec_mlp_ratio * D, nullptr, Dp, nullptr,
+                           c.dec_mlp_ratio * D, nullptr, &lin2))
+            return 1;
+        if (load_linear_ex(owned, hw->data, hb_->data, C, D, nullptr, C, nullptr, Dp, nullptr, &head)) return 1;
+    }
     const TensorView *em = ws.need("text_embed.embedding.weight", (long long)c.num_tokens * D),
                      *pq = ws.need("pos_queries", (long long)S * D);
     if (!em || !pq) return 1;
-    void* dv = nullptr;
-    if (up(owned, em->data, (size_t)c.num_tokens * D * 4, &dv)) return 1;
-    embed = reinterpret_cast<float*>(dv);
-    if (up(owned, pq->data, (size_t)S * D * 4, &dv)) return 1;
-    pos_q = reinterpret_cast<float*>(dv);
-    // ---- row-independent precomputation (fp32 on the host)
+    if (up_padded(owned, em->data, c.num_tokens, D, Dp, es, &embed)) return 1;
+    if (up_padded(owned, pq->data, S, D, Dp, 1.f, &pos_q)) return 1;
+    // ---- row-independent precomputation (fp32 on the host, in the real model's feature space)
     const TensorView *gq = ws.need(d + "norm_q.weight", D), *bq = ws.need(d + "norm_q.bias", D),
                      *gc = ws.need(d + "norm_c.weight", D), *bc = ws.need(d + "norm_c.bias", D);
     if (!gq || !bq || !gc || !bc) return 1;
     {
         std::vector<float> ln(D);
-        std::vector<uint16_t> q((size_t)S * D);
+        std::vector<uint16_t> q((size_t)S * Dp, 0);
         for (int i = 0; i < S; ++i) {
             host_ln(pq->data + (size_t)i * D, gq->data, bq->data, D, 1e-5f, ln.data());
             for (int n = 0; n < D; ++n) {
                 const float* wr = sw->data + (size_t)n * D;
                 double acc = sb->data[n];
                 for (int k = 0; k < D; ++k) acc += (double)wr[k] * ln[k];
-                q[(size_t)i * D + n] = f2bf((float)acc);
+                q[(size_t)i * Dp + hdm[n]] = f2bf((float)acc * (padded ? qs_d : 1.f));
             }
         }
         if (up(owned, q.data(), q.size() * 2, &q_self)) return 1;
@@ -185,12 +299,12 @@ int ParseqModel::load(const WeightSet& ws, const ParseqCfg& c) {
         const int bos = c.num_tokens - 2;
         for (int k = 0; k < D; ++k) c0[k] = sq * em->data[(size_t)bos * D + k];
         host_ln(c0.data(), gc->data, bc->data, D, 1e-5f, l0.data());
-        std::vector<uint16_t> kv(2 * D);
+        std::vector<uint16_t> kv(2 * Dp, 0);
         for (int n = 0; n < 2 * D; ++n) {
             const float* wr = sw->data + (size_t)(D + n) * D;
             double acc = sb->data[D + n];
             for (int k = 0; k < D; ++k) acc += (double)wr[k] * l0[k];
-            kv[n] = f2bf((float)acc);
+            kv[(n / D) * Dp + hdm[n % D]] = f2bf((float)acc);
         }
         if (up(owned, kv.data(), kv.size() * 2, &ckv0)) return 1;
     }
@@ -371,23 +485,25 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     if (Lin::run(A_patch, m->Kpatch, Ti, m->patch, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
     const int hd_e = D / c.enc_heads;
     for (const EncBlock& bk : m->blocks) {
-        if (launch_layernorm(x, Ti, D, bk.ln1.g, bk.ln1.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
+        if (launch_layernorm(x, Ti, D, m->Dr, bk.ln1.g, bk.ln1.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
         if (Lin::run(h, D, Ti, bk.qkv, qkv, 3 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
         const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
         if (launch_flash_attention(q, 3 * D, q + D, q + 2 * D, 3 * D, att, D, seqs_enc, B, max_ntok, c.enc_heads, hd_e,
                                    0, st))
             return 1;
         if (Lin::run(att, D, Ti, bk.proj, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
-        if (launch_layernorm(x, Ti, D, bk.ln2.g, bk.ln2.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
+        if (launch_layernorm(x, Ti, D, m->Dr, bk.ln2.g, bk.ln2.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
         if (Lin::run(h, D, Ti, bk.fc1, mlp, bk.fc1.N, 0, ACT_GELU, nullptr, 0, 0, st, &flops)) return 1;
         if (Lin::run(mlp, bk.fc1.N, Ti, bk.fc2, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
     }
     for (const CropDesc& d : b.descs) flops += 4.0 * d.ntok * (double)d.ntok * D * c.enc_depth;
     // memory = final LayerNorm (fp32 copy into x1-sized scratch only when the caller wants it)
-    if (launch_layernorm(x, Ti, D, m->enc_norm.g, m->enc_norm.b, 1e-6f, mem, memory_out ? x : nullptr, nullptr, 1,
+    if (launch_layernorm(x, Ti, D, m->Dr, m->enc_norm.g, m->enc_norm.b, 1e-6f, mem, memory_out ? x : nullptr, nullptr, 1,
                          nullptr, 0, 0, st))
         return 1;
-    if (memory_out) CK(cudaMemcpyAsync(memory_out, x, (size_t)Ti * D * 4, cudaMemcpyDeviceToHost, st));
+    if (memory_out)  // [T, real D] for the caller
+        CK(cudaMemcpy2DAsync(memory_out, (size_t)m->Dr * 4, x, (size_t)D * 4, (size_t)m->Dr * 4, Ti,
+                             cudaMemcpyDeviceToHost, st));
     // memory K/V once (the reference re-projects it in every AR step)
     if (Lin::run(mem, D, Ti, m->cross_kv, memkv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
     // ---------------- AR decode (reference parseq.py:192-252)
@@ -434,16 +550,16 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         if (launch_dec_self_attn(m->q_self, ckv, B, D, c.dec_heads, 0, ar.step, nullptr, nullptr, sa, st)) return 1;
         if (gemm_plan_launch(&p_so, st)) return 1;
         // x1 += pos_queries[i] (the query stream's residual input), then norm1
-        if (launch_layernorm(x1, B, D, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, 1, ar.step, 0, 1, st))
+        if (launch_layernorm(x1, B, D, m->Dr, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, 1, ar.step, 0, 1, st))
             return 1;
         if (gemm_plan_launch(&p_cq, st)) return 1;
         if (launch_dec_cross_attn(qc, memkv, descs_dev, B, D, c.dec_heads, oc, st)) return 1;
         if (gemm_plan_launch(&p_co, st)) return 1;
-        if (launch_layernorm(x1, B, D, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
+        if (launch_layernorm(x1, B, D, m->Dr, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
             return 1;
         if (gemm_plan_launch(&p_l1, st)) return 1;
         if (gemm_plan_launch(&p_l2, st)) return 1;
-        if (launch_layernorm(x1, B, D, m->dec_norm.g, m->dec_norm.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
+        if (launch_layernorm(x1, B, D, m->Dr, m->dec_norm.g, m->dec_norm.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
             return 1;
         if (gemm_plan_launch(&p_hd, st)) return 1;
         if (c.refine_iters == 0 || logits_out) {
@@ -455,7 +571,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             }
         }
         if (launch_ar_control(logits, ldl, C, B, S, row_group, b.ngroups, ar, eos, c.rep_on, c.rep_period_max,
-                              c.rep_min_run_p1, c.rep_min_repeats, m->embed, m->pos_q, D, m->norm_c.g, m->norm_c.b, cin,
+                              c.rep_min_run_p1, c.rep_min_repeats, m->embed, m->pos_q, D, m->Dr, m->norm_c.g, m->norm_c.b, cin,
                               st))
             return 1;
         steps_run = i + 1;
@@ -478,7 +594,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         if (launch_apply_rep_cut(ar.rep_cut, B, S, C, eos, ids, probs, st)) return 1;
     } else {
         // ---------------- refinement (reference parseq.py:264-299), all 101 queries of every row
-        if (launch_refine_embed(ar.raw, row_group, ar.group_len, B, S, bos, eos, m->embed, m->pos_q, D, m->norm_c.g,
+        if (launch_refine_embed(ar.raw, row_group, ar.group_len, B, S, bos, eos, m->embed, m->pos_q, D, m->Dr, m->norm_c.g,
                                 m->norm_c.b, cin, klen, kpad, st))
             return 1;
         if (Lin::run(cin, D, R, m->self_kv, ckv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
@@ -491,18 +607,18 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
                 return 1;
         }
         if (Lin::run(sa, D, R, m->self_out, x1, D, 1, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
-        if (launch_layernorm(x1, R, D, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, S, nullptr, 0, 1, st))
+        if (launch_layernorm(x1, R, D, m->Dr, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, S, nullptr, 0, 1, st))
             return 1;
         if (Lin::run(hb, D, R, m->cross_q, qc, D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
         const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(memkv);
         if (launch_flash_attention(qc, D, kv, kv + D, 2 * D, oc, D, seqs_ref, B, S, c.dec_heads, hd_d, 0, st)) return 1;
         for (const CropDesc& d : b.descs) flops += 4.0 * S * (double)d.ntok * D;
         if (Lin::run(oc, D, R, m->cross_out, x1, D, 1, ACT_NONE, x1, 1, D, st, &flops)) return 1;
-        if (launch_layernorm(x1, R, D, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
+        if (launch_layernorm(x1, R, D, m->Dr, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
             return 1;
         if (Lin::run(hb, D, R, m->lin1, mlpb, m->lin1.N, 0, ACT_GELU, nullptr, 0, 0, st, &flops)) return 1;
         if (Lin::run(mlpb, m->lin1.N, R, m->lin2, x1, D, 1, ACT_NONE, x1, 1, D, st, &flops)) return 1;
-        if (launch_layernorm(x1, R, D, m->dec_norm.g, m->dec_norm.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
+        if (launch_layernorm(x1, R, D, m->Dr, m->dec_norm.g, m->dec_norm.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
             return 1;
         for (int r0 = 0; r0 < R; r0 += logits_rows) {
             const int rows = std::min(logits_rows, R - r0);

@@ -33,7 +33,8 @@ struct EncBlock {
 };
 
 struct ParseqModel {
-    ParseqCfg cfg;
+    ParseqCfg cfg;  // cfg.D is the PADDED width every kernel works with; Dr the model's real embed_dim
+    int Dr = 0;
     int S, C, gh, full_gw, Kpatch;
     LinearW patch;
     float* pos_embed = nullptr;  // fp32 [gh*full_gw, D]

@@ -93,7 +93,7 @@ int launch_patchify_f32(const float* images, int B, int W, int ph, int pw, int K
 // One warp per row, fp32 statistics (two-pass over registers), bf16 (and optional fp32) output.
 constexpr int kLnVec = 8;  // float4 per lane: D <= 1024, D % 4 == 0
 
-__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, int M, int D,
+__global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, int M, int D, int d_real,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
                                                         __nv_bfloat16* __restrict__ out_bf16,
@@ -130,19 +130,21 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, i
     for (int i = 0; i < kLnVec; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    const float mean = s / (float)D;
+    // statistics over the d_real leading features; columns d_real..D are zero padding (zero in, zero gamma/beta)
+    const float mean = s / (float)d_real;
+    const int nvec_real = d_real >> 2;
     float q = 0.f;
 #pragma unroll
     for (int i = 0; i < kLnVec; ++i) {
         const int j = lane + 32 * i;
-        if (j < nvec) {
+        if (j < nvec_real) {
             const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
             q += (a * a + b * b) + (c * c + d * d);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-    const float rstd = rsqrtf(q / (float)D + eps);
+    const float rstd = rsqrtf(q / (float)d_real + eps);
     const float4* g4 = reinterpret_cast<const float4*>(gamma);
     const float4* b4 = reinterpret_cast<const float4*>(beta);
 #pragma unroll
@@ -166,17 +168,17 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, i
     }
 }
 
-int launch_layernorm(float* x, int M, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
-                     float* out_f32, const float* addvec, int period, const int* add_row0_dev, int add_row0,
-                     int writeback, cudaStream_t st) {
-    if (D > 128 * kLnVec || (D & 3) != 0) {
+int launch_layernorm(float* x, int M, int D, int d_real, const float* gamma, const float* beta, float eps,
+                     void* out_bf16, float* out_f32, const float* addvec, int period, const int* add_row0_dev,
+                     int add_row0, int writeback, cudaStream_t st) {
+    if (D > 128 * kLnVec || (D & 3) != 0 || (d_real & 3) != 0 || d_real > D || d_real <= 0) {
         set_error("layernorm: D=%d unsupported (multiple of 4, <= %d)", D, 128 * kLnVec);
         return 1;
     }
     if (M <= 0) return 0;
     const int warps_per_block = 8;
     layernorm_kernel<<<(M + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        x, M, D, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, addvec,
+        x, M, D, d_real, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, addvec,
         period > 0 ? period : 1, add_row0_dev, add_row0, writeback);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
@@ -965,7 +967,7 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
                                                          const int* __restrict__ row_group, int ngroups, ArState a,
                                                          int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1,
                                                          int rep_min_repeats, const float* __restrict__ embed,
-                                                         const float* __restrict__ pos_q, int D,
+                                                         const float* __restrict__ pos_q, int D, int d_real,
                                                          const float* __restrict__ g_c, const float* __restrict__ b_c,
                                                          __nv_bfloat16* __restrict__ cin) {
     __shared__ float sv[8];
@@ -1057,14 +1059,14 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
             if (threadIdx.x == 0) {
                 float t = 0.f;
                 for (int w = 0; w < 8; ++w) t += red[w];
-                s_stat[0] = t / (float)D;
+                s_stat[0] = t / (float)d_real;
             }
             __syncthreads();
             const float mean = s_stat[0];
             float q = 0.f;
             for (int t = 0; t < 4; ++t) {
                 const int d = threadIdx.x + t * 256;
-                if (d < D) q += (loc[t] - mean) * (loc[t] - mean);
+                if (d < d_real) q += (loc[t] - mean) * (loc[t] - mean);
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -1073,7 +1075,7 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
             if (threadIdx.x == 0) {
                 float t = 0.f;
                 for (int w = 0; w < 8; ++w) t += red[w];
-                s_stat[1] = rsqrtf(t / (float)D + 1e-5f);
+                s_stat[1] = rsqrtf(t / (float)d_real + 1e-5f);
             }
             __syncthreads();
             const float rstd = s_stat[1];
@@ -1116,14 +1118,14 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
 
 int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int ngroups,
                       ArState a, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
-                      const float* embed, const float* pos_q, int D, const float* g_c, const float* b_c, void* cin,
-                      cudaStream_t st) {
+                      const float* embed, const float* pos_q, int D, int d_real, const float* g_c, const float* b_c,
+                      void* cin, cudaStream_t st) {
     if (D > 1024) {
         set_error("ar_control: D=%d too large", D);
         return 1;
     }
     ar_control_kernel<<<B, 256, 0, st>>>(logits, ldl, C, S, row_group, ngroups, a, eos_id, rep_on, rep_period_max,
-                                         rep_min_run_p1, rep_min_repeats, embed, pos_q, D, g_c, b_c,
+                                         rep_min_run_p1, rep_min_repeats, embed, pos_q, D, d_real, g_c, b_c,
                                          reinterpret_cast<__nv_bfloat16*>(cin));
     count_launch(1);
     return cudaGetLastError() != cudaSuccess;
@@ -1134,7 +1136,7 @@ __global__ void __launch_bounds__(256) refine_embed_kernel(const int* __restrict
                                                            const int* __restrict__ row_group,
                                                            const int* __restrict__ group_len, int S, int bos_id,
                                                            int eos_id, const float* __restrict__ embed,
-                                                           const float* __restrict__ pos_q, int D,
+                                                           const float* __restrict__ pos_q, int D, int d_real,
                                                            const float* __restrict__ g_c, const float* __restrict__ b_c,
                                                            __nv_bfloat16* __restrict__ cin, int* __restrict__ klen,
                                                            int* __restrict__ kpad) {
@@ -1171,14 +1173,14 @@ __global__ void __launch_bounds__(256) refine_embed_kernel(const int* __restrict
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += red[w];
-        s_stat[0] = t / (float)D;
+        s_stat[0] = t / (float)d_real;   // padded features are zero: the sum is over the real ones
     }
     __syncthreads();
     const float mean = s_stat[0];
     float q = 0.f;
     for (int t = 0; t < 4; ++t) {
         const int d = threadIdx.x + t * 256;
-        if (d < D) q += (loc[t] - mean) * (loc[t] - mean);
+        if (d < d_real) q += (loc[t] - mean) * (loc[t] - mean);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
@@ -1187,7 +1189,7 @@ __global__ void __launch_bounds__(256) refine_embed_kernel(const int* __restrict
     if (threadIdx.x == 0) {
         float t = 0.f;
         for (int w = 0; w < 8; ++w) t += red[w];
-        s_stat[1] = rsqrtf(t / (float)D + 1e-5f);
+        s_stat[1] = rsqrtf(t / (float)d_real + 1e-5f);
     }
     __syncthreads();
     const float rstd = s_stat[1];
@@ -1200,10 +1202,10 @@ __global__ void __launch_bounds__(256) refine_embed_kernel(const int* __restrict
 }
 
 int launch_refine_embed(const int* raw, const int* row_group, const int* group_len, int B, int S, int bos_id, int eos_id,
-                        const float* embed, const float* pos_q, int D, const float* g_c, const float* b_c, void* cin,
-                        int* klen, int* kpad, cudaStream_t st) {
+                        const float* embed, const float* pos_q, int D, int d_real, const float* g_c, const float* b_c,
+                        void* cin, int* klen, int* kpad, cudaStream_t st) {
     dim3 grid(S, B);
-    refine_embed_kernel<<<grid, 256, 0, st>>>(raw, row_group, group_len, S, bos_id, eos_id, embed, pos_q, D, g_c, b_c,
+    refine_embed_kernel<<<grid, 256, 0, st>>>(raw, row_group, group_len, S, bos_id, eos_id, embed, pos_q, D, d_real, g_c, b_c,
                                               reinterpret_cast<__nv_bfloat16*>(cin), klen, kpad);
     count_launch();
     return cudaGetLastError() != cudaSuccess;

@@ -25,9 +25,10 @@ int launch_patchify_f32(const float* images, int B, int W, int ph, int pw, int K
 
 // LayerNorm over the last dim of fp32 rows -> bf16 (and optionally fp32) output.  If addvec != null the row first
 // gets addvec[(row % period) + add_row0, :] added (and is written back to x when writeback != 0).
-int launch_layernorm(float* x, int M, int D, const float* gamma, const float* beta, float eps, void* out_bf16,
-                     float* out_f32, const float* addvec, int period, const int* add_row0_dev, int add_row0,
-                     int writeback, cudaStream_t st);
+// d_real <= D: statistics run over the first d_real features, the rest is zero padding (ParseqModel::load).
+int launch_layernorm(float* x, int M, int D, int d_real, const float* gamma, const float* beta, float eps,
+                     void* out_bf16, float* out_f32, const float* addvec, int period, const int* add_row0_dev,
+                     int add_row0, int writeback, cudaStream_t st);
 
 // Flash attention over packed sequences, bf16 in/out, fp32 softmax; no mask.
 struct SeqDesc {
@@ -73,13 +74,13 @@ struct ArState {
 // the emitted token (text_embed * sqrt(D) + pos_queries[j-1]) normalised by LN_c -> cin bf16 [B, D].
 int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int ngroups,
                       ArState st_, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
-                      const float* embed, const float* pos_q, int D, const float* g_c, const float* b_c, void* cin,
-                      cudaStream_t st);
+                      const float* embed, const float* pos_q, int D, int d_real, const float* g_c, const float* b_c,
+                      void* cin, cudaStream_t st);
 // Content embeddings for the refinement pass: [B*S, D] bf16 = LN_c(content(row,pos)) from the raw tokens; also
 // emits klen (= group_len[group]) and kpad (first EOS position in [BOS, raw...]) per row.
 int launch_refine_embed(const int* raw, const int* row_group, const int* group_len, int B, int S, int bos_id, int eos_id,
-                        const float* embed, const float* pos_q, int D, const float* g_c, const float* b_c, void* cin,
-                        int* klen, int* kpad, cudaStream_t st);
+                        const float* embed, const float* pos_q, int D, int d_real, const float* g_c, const float* b_c,
+                        void* cin, int* klen, int* kpad, cudaStream_t st);
 
 // Row-wise softmax statistics of logits: ids = argmax, probs = softmax max; applies the repetition logit patch
 // (position == rep_cut[row] -> EOS with probability 1).
