@@ -166,8 +166,8 @@ def detect_repeat_onset(seq, period_max=8, min_run_p1=8, min_repeats=3):
 @torch.inference_mode()
 def parseq_forward(sd, spec, images, return_aux=False):
     """reference PARSeq.forward (parseq.py:159-311) for the inference configuration (max_length=None,
-    export_onnx=False, decode_ar=1).  Returns logits (B, S, C): S = 101 when refine_iters > 0, else the number of AR
-    steps run."""
+    export_onnx=False).  Returns logits (B, S, C): S = 101 when refine_iters > 0 or decode_ar == 0, else the number
+    of AR steps run."""
     bs = images.shape[0]
     S = spec.max_label_length + 1
     memory = encoder_forward(sd, spec, images)
@@ -178,7 +178,11 @@ def parseq_forward(sd, spec, images, return_aux=False):
     rep_cut = [None] * bs
     rep_done = [False] * bs
     steps = []
-    for i in range(S):
+    if not spec.decode_ar:
+        # parseq.py:252-262: no prior context, the input is just <bos>; all positions are queried at once, no masks
+        out = decode(sd, spec, tgt_in[:, :1], memory, pos_q, None)
+        steps.append(F.linear(out, sd["head.weight"], sd["head.bias"]))
+    for i in range(S if spec.decode_ar else 0):
         j = i + 1
         out = decode(sd, spec, tgt_in[:, :j], memory, pos_q[:, i:j], causal[i:j, :j])
         p_i = F.linear(out, sd["head.weight"], sd["head.bias"])

@@ -228,9 +228,16 @@ def main():
            "max|d|=%.3g" % (r - o).abs().max().item())
     # ---- PARSeq
     charset = open(os.path.join(SRC, "resource", "charsetv2.txt"), encoding="utf-8").read()
-    for name, W, peaked in (("parseq-tiny-dynw-v4", 320, False), ("parseq-tiny-dynw-v4", 200, True),
-                            ("parseq-large-v4_1", 160, True)):
-        spec = ops.SPECS[name]
+    import dataclasses
+    for name, W, peaked, over in (("parseq-tiny-dynw-v4", 320, False, {}), ("parseq-tiny-dynw-v4", 200, True, {}),
+                                  ("parseq-large-v4_1", 160, True, {}),
+                                  # the cfg switches of the decoder: non-AR decode, no / repeated refinement
+                                  ("parseq-tiny-dynw-v4", 200, True, {"decode_ar": 0}),
+                                  ("parseq-tiny-dynw-v4", 200, True, {"decode_ar": 0, "refine_iters": 0}),
+                                  ("parseq-tiny-dynw-v4", 200, True, {"refine_iters": 2}),
+                                  ("parseq-tiny-dynw-v4", 200, True, {"refine_iters": 0}),
+                                  ("parseq-tiny", 208, True, {})):
+        spec = dataclasses.replace(ops.SPECS[name], **over)
         sd = weights.make_parseq_state_dict(spec, seed=3, peaked=peaked)
         ref = build_reference_parseq(spec, sd, charset)
         img = torch.rand(4, 3, 32, W, generator=torch.Generator().manual_seed(5)) * 2 - 1
@@ -240,7 +247,7 @@ def main():
         same_shape = r.shape == o.shape
         d = (r - o).abs().max().item() if same_shape else float("nan")
         ids_same = same_shape and torch.equal(r.argmax(-1), o.argmax(-1))
-        report("parseq %s W=%d peaked=%d logits vs reference PARSeq.forward" % (name, W, peaked),
+        report("parseq %s W=%d peaked=%d %s logits vs reference PARSeq.forward" % (name, W, peaked, over or ""),
                same_shape and d < 2e-4 and ids_same, "shape=%s max|d|=%.3g ar_steps=%d" % (tuple(o.shape), d,
                                                                                            aux["ar_steps"]))
         tok_r = ref.tokenizer.decode(r.softmax(-1))

@@ -71,6 +71,31 @@ def test_model_seam_vs_oracle(name, B, W, seed):
         assert d < 0.03 * ref.std().item() + 0.05, d
 
 
+@pytest.mark.parametrize("over", [{"decode_ar": 0}, {"decode_ar": 0, "refine_iters": 0}, {"refine_iters": 2},
+                                  {"decode_ar": 0, "refine_iters": 2}])
+def test_decoder_switches_vs_oracle(over):
+    """cfg.decode_ar / cfg.refine_iters (reference parseq.py:192,252-299): non-autoregressive first pass, repeated
+    refinement.  The oracle is pinned against the reference for the same switches (oracle/refcheck.py)."""
+    import dataclasses
+    name = "parseq-tiny-dynw-v4"
+    spec = dataclasses.replace(ops.SPECS[name], **over)
+    sd = weights.make_parseq_state_dict(spec, seed=3, peaked=True)
+    rec = _rec(name)
+    rec.model.decode_ar = spec.decode_ar
+    rec.model.refine_iters = spec.refine_iters
+    rec.model.load_state_dict(sd)
+    img = torch.rand(6, 3, 32, 200, generator=torch.Generator().manual_seed(5)) * 2 - 1
+    got = rec.model(img)
+    ref, aux = ops.parseq_forward(sd, spec, img, return_aux=True)
+    assert got.shape == ref.shape
+    n_same = _margin_aware_equal(got.argmax(-1).numpy(), ref, aux, str(over))
+    assert n_same >= 3
+    same = [b for b in range(6) if torch.equal(got[b].argmax(-1), ref[b].argmax(-1)) and
+            float(aux["ar_margin"][b].min()) >= TAU]
+    if same:
+        assert (got[same] - ref[same]).abs().max().item() < 0.03 * ref.std().item() + 0.05
+
+
 def test_reference_fixture_strings(charset_v2):
     for tag, kw in (("peaked", dict(peaked=True)), ("repeat", dict(peaked=True, degenerate_repeat=True))):
         z = np.load(os.path.join(G, "parseq_ref_%s.npz" % tag), allow_pickle=True)

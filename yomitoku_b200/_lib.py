@@ -59,7 +59,7 @@ class YtkParseqCfg(ctypes.Structure):
     _fields_ = [(n, c_int) for n in (
         "embed_dim", "enc_heads", "enc_depth", "patch_h", "patch_w", "img_h", "img_w", "num_tokens",
         "max_label_length", "dec_heads", "mlp_ratio", "dec_mlp_ratio", "refine_iters", "repetition_stop",
-        "rep_period_max", "rep_min_run_p1", "rep_min_repeats")]
+        "rep_period_max", "rep_min_run_p1", "rep_min_repeats", "decode_ar")]
 
 
 class YtkCrop(ctypes.Structure):

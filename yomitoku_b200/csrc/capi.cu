@@ -251,7 +251,7 @@ int ytk_parseq_create(const ytk_tensor* tensors, int n_tensors, const ytk_parseq
     ytk::ParseqCfg c{cfg->embed_dim, cfg->enc_heads, cfg->enc_depth, cfg->patch_h, cfg->patch_w, cfg->img_h,
                      cfg->img_w, cfg->num_tokens, cfg->max_label_length, cfg->dec_heads, cfg->mlp_ratio,
                      cfg->dec_mlp_ratio, cfg->refine_iters, cfg->repetition_stop, cfg->rep_period_max,
-                     cfg->rep_min_run_p1, cfg->rep_min_repeats};
+                     cfg->rep_min_run_p1, cfg->rep_min_repeats, cfg->decode_ar};
     auto h = std::make_unique<ytk_parseq>();
     cudaGetDevice(&h->device);
     if (h->model.load(ws, c)) return YTK_ERR;
@@ -273,10 +273,6 @@ int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops_ptr, int crops_
                              int32_t* group_len_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
     cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
-    if (h->model.cfg.refine_iters > 1) {
-        ytk::set_error("refine_iters > 1 is not implemented on the device path");
-        return YTK_ERR;
-    }
     ytk::ParseqBatch b;
     b.crops = crops_ptr;
     b.crops_on_device = crops_on_device;
@@ -305,10 +301,6 @@ int ytk_parseq_forward_f32(ytk_parseq* h, const float* images, int images_on_dev
                            int32_t* rep_cut_out, float* memory_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
     cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
-    if (h->model.cfg.refine_iters > 1) {
-        ytk::set_error("refine_iters > 1 is not implemented on the device path");
-        return YTK_ERR;
-    }
     const int pw = h->model.cfg.pw, gh = h->model.gh;
     if (W % pw != 0 || W > h->model.cfg.img_w || W <= 0) {
         ytk::set_error("ytk_parseq_forward_f32: width %d must be a positive multiple of %d and <= %d", W, pw,

@@ -369,6 +369,7 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
     if (logits_rows < B) logits_rows = (int)((B + 127) / 128 * 128);
     DM(logits, (long long)logits_rows * ldl * 4);
     DM(row_group, 4 * B);
+    DM(glen_const, 4 * 2 * (size_t)std::max(cap_groups, 1));
     DM(klen, 4 * B);
     DM(kpad, 4 * B);
     DM(ids, 4 * R);
@@ -518,8 +519,10 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
                              st));
         CK(cudaStreamSynchronize(st));
     }
-    if (launch_bcast_rows(m->ckv0, ckv, 2 * D * 2, B, st)) return 1;
+    int steps_run = 0;
     const int hd_d = D / c.dec_heads;
+    if (c.decode_ar) {
+    if (launch_bcast_rows(m->ckv0, ckv, 2 * D * 2, B, st)) return 1;
     // plans reused by every step
     GemmPlan p_so, p_cq, p_co, p_l1, p_l2, p_hd, p_kv;
     Epilogue e;
@@ -545,7 +548,6 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     if (mk(&p_hd, hb, D, B, m->head, logits, ldl, 1, ACT_NONE, nullptr, 0, 0)) return 1;
     if (mk(&p_kv, cin, D, B, m->self_kv, ckv, 2 * D, 0, ACT_NONE, nullptr, 0, 0)) return 1;
     const double step_flops = p_so.flops + p_cq.flops + p_co.flops + p_l1.flops + p_l2.flops + p_hd.flops + p_kv.flops;
-    int steps_run = 0;
     for (int i = 0; i < S; ++i) {
         if (launch_dec_self_attn(m->q_self, ckv, B, D, c.dec_heads, 0, ar.step, nullptr, nullptr, sa, st)) return 1;
         if (gemm_plan_launch(&p_so, st)) return 1;
@@ -587,18 +589,35 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             if (host_flag[0] == 0) break;
         }
     }
+    } else {
+        // decode_ar == 0 (parseq.py:252-262): no AR loop; the first decoder pass below sees only <bos> as context
+        if (launch_fill_i32(ar.group_len, S, b.ngroups, st)) return 1;
+        steps_run = S;
+    }
     last_steps = steps_run;
     CK(cudaEventRecord(ev[2], st));
-    for (const CropDesc& d : b.descs) flops += 4.0 * d.ntok * (double)D * steps_run;  // cross attention
-    if (c.refine_iters == 0) {
+    if (c.decode_ar)
+        for (const CropDesc& d : b.descs) flops += 4.0 * d.ntok * (double)D * steps_run;  // cross attention
+    // Decoder passes over all S queries (reference parseq.py:252-299): with decode_ar == 0 a first pass whose context is
+    // <bos> alone, then `refine_iters` passes whose context is [<bos>, arg-max of the previous logits[:, :-1]].
+    const int n_pass = c.refine_iters + (c.decode_ar ? 0 : 1);
+    if (n_pass == 0) {
         if (launch_apply_rep_cut(ar.rep_cut, B, S, C, eos, ids, probs, st)) return 1;
     } else {
-        // ---------------- refinement (reference parseq.py:264-299), all 101 queries of every row
-        if (launch_refine_embed(ar.raw, row_group, ar.group_len, B, S, bos, eos, m->embed, m->pos_q, D, m->Dr, m->norm_c.g,
+        if (launch_fill_i32(glen_const, S, b.ngroups, st)) return 1;
+        if (launch_fill_i32(glen_const + cap_groups, 1, b.ngroups, st)) return 1;
+    }
+    for (int pass = 0; pass < n_pass; ++pass) {
+        const bool first = pass == 0, final = pass + 1 == n_pass;
+        // context tokens: raw[row][p-1] is the token at position p >= 1; L (per group) = context length
+        const int* raw = (first && c.decode_ar) ? ar.raw : ids;
+        const int* glen = first ? (c.decode_ar ? ar.group_len : glen_const + cap_groups) : glen_const;
+        if (launch_refine_embed(raw, row_group, glen, B, S, bos, eos, m->embed, m->pos_q, D, m->Dr, m->norm_c.g,
                                 m->norm_c.b, cin, klen, kpad, st))
             return 1;
         if (Lin::run(cin, D, R, m->self_kv, ckv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
-        // masked tensor-core attention: 101 shared queries x the row's content keys (cache layout [pos][row][2D])
+        // masked tensor-core attention: 101 shared queries x the row's content keys (cache layout [pos][row][2D]);
+        // rows 0/1 see every key, row q >= 2 the keys <= q, nobody sees keys at/after the first EOS (Appendix A1)
         if (launch_refine_seqs(klen, kpad, B, S, D, seqs_self, st)) return 1;
         {
             const __nv_bfloat16* ck = reinterpret_cast<const __nv_bfloat16*>(ckv);
@@ -624,8 +643,10 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             const int rows = std::min(logits_rows, R - r0);
             const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(hb) + (size_t)r0 * D;
             if (Lin::run(a, D, rows, m->head, logits, ldl, 1, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
-            if (launch_softmax_max(logits, ldl, C, rows, S, 1, r0, ar.rep_cut, eos, ids, probs, st)) return 1;
-            if (logits_out) {
+            // the repetition patch (parseq.py:301-309) applies to the final logits only
+            if (launch_softmax_max(logits, ldl, C, rows, S, 1, r0, final ? ar.rep_cut : nullptr, eos, ids, probs, st))
+                return 1;
+            if (logits_out && final) {
                 // model-level seam: materialise the (B, 101, C) logits; the repetition patch is applied by the caller
                 CK(cudaMemcpy2DAsync(logits_out + (size_t)r0 * C, (size_t)C * 4, logits, ldl * 4, (size_t)C * 4, rows,
                                      logits_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));

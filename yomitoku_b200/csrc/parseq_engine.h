@@ -13,7 +13,7 @@ namespace ytk {
 
 struct ParseqCfg {
     int D, enc_heads, enc_depth, ph, pw, img_h, img_w, num_tokens, max_label_length, dec_heads, mlp_ratio,
-        dec_mlp_ratio, refine_iters, rep_on, rep_period_max, rep_min_run_p1, rep_min_repeats;
+        dec_mlp_ratio, refine_iters, rep_on, rep_period_max, rep_min_run_p1, rep_min_repeats, decode_ar;
 };
 
 struct LinearW {
@@ -85,6 +85,7 @@ struct ParseqEngine {
     int logits_rows = 0;
     long long ldl = 0;
     int *row_group = nullptr, *klen = nullptr, *kpad = nullptr, *ids = nullptr;
+    int* glen_const = nullptr;  // [2][cap_groups]: context lengths S and 1 for the non-AR decoder passes
     float* probs = nullptr;
     ArState ar{};
     int* ar_block = nullptr;  // backing store of the ArState arrays

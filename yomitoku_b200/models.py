@@ -279,8 +279,6 @@ class PARSeq(_DeviceModel):
         self.rep_min_run_p1 = int(getattr(cfg, "rep_min_run_p1", 8))
         self.rep_min_repeats = int(getattr(cfg, "rep_min_repeats", 3))
         self._sd = _parseq_random_state_dict(cfg, seed)
-        if not self.decode_ar:
-            raise NotImplementedError("decode_ar=0 (non-autoregressive decoding) is not on the device path")
 
     @property
     def refine_iters(self):
@@ -306,7 +304,7 @@ class PARSeq(_DeviceModel):
                                    c.encoder.patch_size[1], c.data.img_size[0], c.data.img_size[1], c.num_tokens,
                                    c.max_label_length, c.decoder.num_heads, c.encoder.mlp_ratio, c.decoder.mlp_ratio,
                                    self._refine_iters, 1 if self.repetition_stop else 0, self.rep_period_max,
-                                   self.rep_min_run_p1, self.rep_min_repeats)
+                                   self.rep_min_run_p1, self.rep_min_repeats, 1 if self.decode_ar else 0)
             h = ctypes.c_void_p()
             _lib.check(L.ytk_parseq_create(tab, len(tab), ctypes.byref(cc), ctypes.byref(h)))
             self._handle = h
