@@ -24,5 +24,5 @@ def test_library_builds_loads_and_exports_header_symbols():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.YtkCrop) == 32            # long long + 5 ints (+ padding)
-    assert ctypes.sizeof(_lib.YtkParseqCfg) == 17 * 4
+    assert ctypes.sizeof(_lib.YtkParseqCfg) == 18 * 4    # 17 config ints + decode_ar
     assert ctypes.sizeof(_lib.YtkTensor) == 8 + 8 + 8 + 32
