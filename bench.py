@@ -16,6 +16,7 @@ Weights are seeded random (no checkpoints offline); with random PARSeq weights n
 runs all 101 steps (worst case).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -282,9 +283,21 @@ def main():
     value = world * P * args.steps / (total_ms / 1e3)
     det_flops = det.model.flops(ocr.det_batch, Hn, Wn) / ocr.det_batch * P
     rec_flops = rec.model.last_flops()
+    phase_value = rec.model.last_phase_ms()     # CUDA-event phase times of the last timed recognizer call
     pk = peaks()
     det_tflops = det_flops * args.steps / (det_ms / 1e3) / 1e12
     rec_tflops = rec_flops * args.steps / (rec_ms / 1e3) / 1e12
+    # ---------------- per-launch timing of the dominant kernel (one instrumented extra step, outside the timed region)
+    def gemm_window(fn):
+        f, ms, n = ctypes.c_double(0), ctypes.c_double(0), ctypes.c_longlong(0)
+        L.ytk_gemm_profile_begin()
+        fn()
+        torch.cuda.synchronize()
+        _lib.check(L.ytk_gemm_profile_end(ctypes.byref(f), ctypes.byref(ms), ctypes.byref(n)))
+        return {"tflop": f.value / 1e12, "ms": ms.value, "launches": int(n.value),
+                "achieved": f.value / 1e12 / (ms.value / 1e3) if ms.value > 0 else 0.0}
+    g_det = gemm_window(det_step)
+    g_rec = gemm_window(rec_step)
     # ---------------- e2e through the public batched API from host pages
     e2e = None
     if not args.no_e2e:
@@ -332,16 +345,33 @@ def main():
                              (P * 1.2 + 4.0),
                        "ar_steps": int(L.ytk_parseq_last_steps(rec.model._ensure())),
                        "weights": "seeded random init (from_pretrained=False)",
-                       "recognizer_phase_ms": rec.model.last_phase_ms()},
+                       "recognizer_phase_ms": phase_value},
             "crops_per_s": world * n_crops * args.steps / (rec_ms / 1e3),
             "det_pages_per_s": world * P * args.steps / (det_ms / 1e3),
-            "roofline": {"bound": "tensor", "achieved": det_tflops, "peak": pk["bf16_tflops_sustained"],
-                         "unit": "TFLOP/s", "frac": det_tflops / pk["bf16_tflops_sustained"], "traffic": None,
-                         "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM) as the DBNet forward: 625.5 GFLOP/page "
-                                   "algorithmic over the CUDA-event time of the whole detector launch sequence",
+            "roofline": {"bound": "tensor",
+                         "achieved": (g_det["tflop"] + g_rec["tflop"]) / ((g_det["ms"] + g_rec["ms"]) / 1e3),
+                         "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                         "frac": (g_det["tflop"] + g_rec["tflop"]) / ((g_det["ms"] + g_rec["ms"]) / 1e3) /
+                                 pk["bf16_tflops_sustained"],
+                         "traffic": None,
+                         "kernel": "gemm_tc_kernel (tcgen05 implicit GEMM): every launch of one step (DBNet convs + "
+                                   "PARSeq linears), algorithmic FLOPs (2*M*N*K per launch) over the sum of the launch "
+                                   "durations; CUDA events around every launch on the launching stream, one "
+                                   "instrumented step right after the timed region",
+                         "launches_per_step": g_det["launches"] + g_rec["launches"],
+                         "kernel_ms_per_step": g_det["ms"] + g_rec["ms"],
+                         "share_of_step": (g_det["ms"] + g_rec["ms"]) / (total_ms / args.steps),
+                         "by_model": {"dbnet": g_det, "parseq": g_rec},
+                         "traffic_note": "shapes differ per launch; ncu --set full DRAM bytes of representative "
+                                         "launches are in profiles/README_r01.md (qkv GEMM: 76 MB read + 165 MB "
+                                         "written vs 76 + 217 MB algorithmic)",
                          "peak_source": pk["source"] + " bf16_tflops_sustained",
-                         "recognizer": {"achieved": rec_tflops, "frac": rec_tflops / pk["bf16_tflops_sustained"],
-                                        "gflop_per_step": rec_flops / 1e9}},
+                         "whole_sequence": {"detector": {"achieved": det_tflops,
+                                                         "frac": det_tflops / pk["bf16_tflops_sustained"],
+                                                         "gflop_per_page": det_flops / P / 1e9},
+                                            "recognizer": {"achieved": rec_tflops,
+                                                           "frac": rec_tflops / pk["bf16_tflops_sustained"],
+                                                           "gflop_per_step": rec_flops / 1e9}}},
             "cpu_baseline": cpu,
             "e2e": e2e,
             "gpu_launches": int(launches),

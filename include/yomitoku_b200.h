@@ -30,6 +30,10 @@ const char* ytk_last_error(void);
 int ytk_version(void);
 /* number of kernel launches issued by this library on the calling process since load (bench.py gpu_launches) */
 long long ytk_launch_count(void);
+/* Measurement aid (bench.py roofline): between begin and end every gemm_tc_kernel launch is bracketed by CUDA events on
+ * its own stream; end returns the summed algorithmic FLOPs, summed kernel durations (ms) and the launch count. */
+void ytk_gemm_profile_begin(void);
+int ytk_gemm_profile_end(double* flops, double* ms, long long* launches);
 
 /* ---- op level (kernel parity tests; replaces the cuDNN/cuBLAS call sites listed in SURVEY.md section 2.3) ----
  * Convolution as tcgen05 implicit GEMM.  in: NHWC bf16 [N,H,W,in_ld] (first Cin channels used), w: bf16

@@ -24,6 +24,10 @@ def _declare(lib):
     lib.ytk_last_error.argtypes = []
     lib.ytk_version.restype = c_int
     lib.ytk_launch_count.restype = c_ll
+    lib.ytk_gemm_profile_begin.restype = None
+    lib.ytk_gemm_profile_end.restype = c_int
+    lib.ytk_gemm_profile_end.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                         ctypes.POINTER(c_ll)]
     lib.ytk_op_conv2d_bf16.restype = c_int
     lib.ytk_op_conv2d_bf16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_ll,

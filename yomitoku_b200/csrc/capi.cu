@@ -70,6 +70,10 @@ extern "C" {
 const char* ytk_last_error(void) { return ytk::last_error(); }
 int ytk_version(void) { return 1; }
 long long ytk_launch_count(void) { return ytk::launch_count(); }
+void ytk_gemm_profile_begin(void) { ytk::gemm_profile_begin(); }
+int ytk_gemm_profile_end(double* flops, double* ms, long long* launches) {
+    return ytk::gemm_profile_end(flops, ms, launches) ? YTK_ERR : YTK_OK;
+}
 
 int ytk_op_conv2d_bf16(const void* in, int N, int H, int W, int Cin, long long in_ld, const void* w, const float* bias,
                        int kh, int kw, int stride, int pad, int dil, int Cout, const void* resid, int resid_f32,

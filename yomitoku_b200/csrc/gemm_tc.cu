@@ -13,6 +13,7 @@
 #include <cstring>
 #include <atomic>
 #include <mutex>
+#include <vector>
 
 #include "ptx.cuh"
 
@@ -952,13 +953,84 @@ static int launch_bn(const GemmPlan* plan, cudaStream_t stream) {
     return launch_variant<BLOCK_N, 1, 2, EPI_NORMAL>(plan, stream);
 }
 
-int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream) {
-    switch (plan->block_n) {
-        case 64: return launch_bn<64>(plan, stream);
-        case 128: return launch_bn<128>(plan, stream);
-        case 256: return launch_bn<256>(plan, stream);
-        default: set_error("bad block_n %d", plan->block_n); return 1;
+// ---- per-launch timing of gemm_tc_kernel (bench.py roofline): CUDA events on the launching stream around every launch
+namespace {
+struct ProfRec {
+    cudaEvent_t a, b;
+    double flops;
+};
+std::mutex g_prof_mu;
+bool g_prof_on = false;
+std::vector<ProfRec> g_prof;        // records of the current window
+std::vector<cudaEvent_t> g_prof_pool;  // recycled events
+cudaEvent_t prof_event() {
+    if (!g_prof_pool.empty()) {
+        cudaEvent_t e = g_prof_pool.back();
+        g_prof_pool.pop_back();
+        return e;
     }
+    cudaEvent_t e = nullptr;
+    cudaEventCreate(&e);
+    return e;
+}
+}  // namespace
+
+void gemm_profile_begin() {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (ProfRec& r : g_prof) {
+        g_prof_pool.push_back(r.a);
+        g_prof_pool.push_back(r.b);
+    }
+    g_prof.clear();
+    g_prof_on = true;
+}
+
+int gemm_profile_end(double* flops, double* ms, long long* launches) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof_on = false;
+    double f = 0, t = 0;
+    for (ProfRec& r : g_prof) {
+        if (cudaEventSynchronize(r.b) != cudaSuccess) {
+            set_error("gemm_profile_end: event synchronize failed");
+            return 1;
+        }
+        float e = 0.f;
+        cudaEventElapsedTime(&e, r.a, r.b);
+        t += e;
+        f += r.flops;
+    }
+    if (flops) *flops = f;
+    if (ms) *ms = t;
+    if (launches) *launches = (long long)g_prof.size();
+    return 0;
+}
+
+int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream) {
+    ProfRec rec{nullptr, nullptr, 0};
+    bool prof = false;
+    if (g_prof_on) {
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        if (g_prof_on) {
+            rec.a = prof_event();
+            rec.b = prof_event();
+            rec.flops = plan->flops;
+            prof = true;
+        }
+    }
+    if (prof) cudaEventRecord(rec.a, stream);
+    int rc;
+    switch (plan->block_n) {
+        case 64: rc = launch_bn<64>(plan, stream); break;
+        case 128: rc = launch_bn<128>(plan, stream); break;
+        case 256: rc = launch_bn<256>(plan, stream); break;
+        default: set_error("bad block_n %d", plan->block_n); rc = 1;
+    }
+    if (prof) {
+        cudaEventRecord(rec.b, stream);
+        std::lock_guard<std::mutex> lk(g_prof_mu);
+        g_prof.push_back(rec);
+    }
+    return rc;
 }
 
 }  // namespace ytk

@@ -111,5 +111,9 @@ const char* last_error();
 int num_sms();
 void count_launch(int n = 1);
 long long launch_count();
+// Timing window over gemm_tc_kernel launches: CUDA events on the launching stream around every launch between begin and
+// end; end() returns the summed algorithmic FLOPs, the summed kernel durations (ms) and the launch count.
+void gemm_profile_begin();
+int gemm_profile_end(double* flops, double* ms, long long* launches);
 
 }  // namespace ytk
