@@ -522,7 +522,8 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     int steps_run = 0;
     const int hd_d = D / c.dec_heads;
     if (c.decode_ar) {
-    if (launch_bcast_rows(m->ckv0, ckv, 2 * D * 2, B, st)) return 1;
+    // content K/V cache [row][position 0..S-1][2D]; position 0 (<bos>) is the same for every row
+    if (launch_bcast_rows(m->ckv0, ckv, 2 * D * 2, (long long)S * 2 * D * 2, B, st)) return 1;
     // plans reused by every step
     GemmPlan p_so, p_cq, p_co, p_l1, p_l2, p_hd, p_kv;
     Epilogue e;
@@ -546,10 +547,10 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     if (mk(&p_l1, hb, D, B, m->lin1, mlpb, m->lin1.N, 0, ACT_GELU, nullptr, 0, 0)) return 1;
     if (mk(&p_l2, mlpb, m->lin1.N, B, m->lin2, x1, D, 1, ACT_NONE, x1, 1, D)) return 1;
     if (mk(&p_hd, hb, D, B, m->head, logits, ldl, 1, ACT_NONE, nullptr, 0, 0)) return 1;
-    if (mk(&p_kv, cin, D, B, m->self_kv, ckv, 2 * D, 0, ACT_NONE, nullptr, 0, 0)) return 1;
+    if (mk(&p_kv, cin, D, B, m->self_kv, ckv, (long long)S * 2 * D, 0, ACT_NONE, nullptr, 0, 0)) return 1;
     const double step_flops = p_so.flops + p_cq.flops + p_co.flops + p_l1.flops + p_l2.flops + p_hd.flops + p_kv.flops;
     for (int i = 0; i < S; ++i) {
-        if (launch_dec_self_attn(m->q_self, ckv, B, D, c.dec_heads, 0, ar.step, nullptr, nullptr, sa, st)) return 1;
+        if (launch_dec_self_attn(m->q_self, ckv, B, S, D, c.dec_heads, ar.step, sa, st)) return 1;
         if (gemm_plan_launch(&p_so, st)) return 1;
         // x1 += pos_queries[i] (the query stream's residual input), then norm1
         if (launch_layernorm(x1, B, D, m->Dr, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, 1, ar.step, 0, 1, st))
@@ -579,7 +580,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         steps_run = i + 1;
         flops += step_flops;
         if (i + 1 < S) {
-            p_kv.args.out = reinterpret_cast<__nv_bfloat16*>(ckv) + (size_t)(i + 1) * B * 2 * D;
+            p_kv.args.out = reinterpret_cast<__nv_bfloat16*>(ckv) + (size_t)(i + 1) * 2 * D;  // position i+1 of every row
             if (gemm_plan_launch(&p_kv, st)) return 1;
         }
         // early stop: peek at the device-side counter every 4 steps (no sync on the other steps)
@@ -616,12 +617,12 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
                                 m->norm_c.b, cin, klen, kpad, st))
             return 1;
         if (Lin::run(cin, D, R, m->self_kv, ckv, 2 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
-        // masked tensor-core attention: 101 shared queries x the row's content keys (cache layout [pos][row][2D]);
+        // masked tensor-core attention: 101 shared queries x the row's content keys (cache layout [row][pos][2D]);
         // rows 0/1 see every key, row q >= 2 the keys <= q, nobody sees keys at/after the first EOS (Appendix A1)
         if (launch_refine_seqs(klen, kpad, B, S, D, seqs_self, st)) return 1;
         {
             const __nv_bfloat16* ck = reinterpret_cast<const __nv_bfloat16*>(ckv);
-            if (launch_flash_attention(m->q_self, D, ck, ck + D, (long long)B * 2 * D, sa, D, seqs_self, B, S,
+            if (launch_flash_attention(m->q_self, D, ck, ck + D, 2 * D, sa, D, seqs_self, B, S,
                                        c.dec_heads, hd_d, 1, st))
                 return 1;
         }

@@ -464,236 +464,22 @@ int launch_flash_attention(const void* Q, long long ldq, const void* K, const vo
     return cudaGetLastError() != cudaSuccess;
 }
 
-// =================================================================================================== decoder self-attn
-// Query stream vs. content K/V cache (reference DecoderLayer.forward_stream self_attn, parseq_transformer.py:83-90).
-// One CTA per (row, head); K/V of that row+head staged in shared memory as fp32.
+// =================================================================================================== decoder attention
 constexpr int kMaxS = 101;
 constexpr int kMaxHd = 96;
 constexpr int kMaxMem = 800;
-static int launch_single_query_attn(int mode, const void* qsrc, const void* kv, int B, int D, int heads,
-                                    const int* step_dev, const CropDesc* descs, void* out, cudaStream_t st);
-
-__global__ void __launch_bounds__(128) dec_self_attn_kernel(const __nv_bfloat16* __restrict__ q_shared,
-                                                            const __nv_bfloat16* __restrict__ ckv, int B, int D,
-                                                            int hd, int mode, const int* __restrict__ step_dev,
-                                                            const int* __restrict__ klen,
-                                                            const int* __restrict__ kpad,
-                                                            __nv_bfloat16* __restrict__ out) {
-    extern __shared__ float dsm[];
-    const int ldk = hd + 1;
-    float* sK = dsm;                       // [kMaxS][hd+1]
-    float* sV = sK + kMaxS * ldk;          // [kMaxS][hd+1]
-    float* sP = sV + kMaxS * ldk;          // [4][kMaxS+3]
-    float* sQ = sP + 4 * (kMaxS + 3);      // [4][hd]
-    const int row = blockIdx.x, head = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    int nk, q_begin, q_end, pad;
-    if (mode == 0) {
-        const int i = *step_dev;
-        nk = i + 1;
-        q_begin = i;
-        q_end = i + 1;
-        pad = nk;
-    } else {
-        nk = klen[row];
-        q_begin = 0;
-        q_end = kMaxS;
-        pad = kpad[row];
-    }
-    for (int idx = threadIdx.x; idx < nk * hd; idx += 128) {
-        const int j = idx / hd, d = idx - j * hd;
-        const __nv_bfloat16* p = ckv + ((long long)j * B + row) * (2 * D) + head * hd + d;
-        sK[j * ldk + d] = __bfloat162float(p[0]);
-        sV[j * ldk + d] = __bfloat162float(p[D]);
-    }
-    __syncthreads();
-    const float scale = rsqrtf((float)hd);
-    float* myP = sP + warp * (kMaxS + 3);
-    float* myQ = sQ + warp * hd;
-    for (int qi = q_begin + warp; qi < q_end; qi += 4) {
-        for (int d = lane; d < hd; d += 32) myQ[d] = __bfloat162float(q_shared[(long long)qi * D + head * hd + d]);
-        __syncwarp();
-        float mx = -INFINITY;
-        for (int j = lane; j < nk; j += 32) {
-            const bool vis = (mode == 0) ? true : (((qi < 2) || (j <= qi)) && (j < pad));
-            float s = -INFINITY;
-            if (vis) {
-                s = 0.f;
-                for (int d = 0; d < hd; ++d) s += myQ[d] * sK[j * ldk + d];
-                s *= scale;
-            }
-            myP[j] = s;
-            mx = fmaxf(mx, s);
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-        float sum = 0.f;
-        for (int j = lane; j < nk; j += 32) {
-            const float p = (myP[j] == -INFINITY) ? 0.f : __expf(myP[j] - mx);
-            myP[j] = p;
-            sum += p;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-        __syncwarp();
-        const float inv = 1.f / sum;
-        const long long orow = (mode == 0) ? row : ((long long)row * kMaxS + qi);
-        for (int d = lane; d < hd; d += 32) {
-            float acc = 0.f;
-            for (int j = 0; j < nk; ++j) acc += myP[j] * sV[j * ldk + d];
-            out[orow * D + head * hd + d] = __float2bfloat16(acc * inv);
-        }
-        __syncwarp();
-    }
-}
-
-// AR step: ONE query per row.  One warp per (row, head): lanes split the <= 101 cached keys for the scores, then split
-// the head dimension for the value sum.  Every access is a whole 32-byte sector of the K/V cache.
-template <int HD>
-__global__ void __launch_bounds__(128) dec_self_attn_ar_kernel(const __nv_bfloat16* __restrict__ q_shared,
-                                                               const __nv_bfloat16* __restrict__ ckv, int B, int D,
-                                                               int heads, const int* __restrict__ step_dev,
-                                                               __nv_bfloat16* __restrict__ out) {
-    constexpr int NCH = HD / 8;        // 16-byte chunks per K/V row
-    constexpr int NSUB = 32 / NCH;     // key subsets in the value phase (lanes >= NSUB*NCH idle)
-    __shared__ float sQ[4][HD];
-    __shared__ float sP[4][kMaxS + 3];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int wid = blockIdx.x * 4 + warp;
-    if (wid >= B * heads) return;
-    const int row = wid / heads, head = wid - row * heads;
-    const int i = *step_dev;
-    const int nk = i + 1;
-    for (int d = lane; d < HD; d += 32) sQ[warp][d] = __bfloat162float(q_shared[(long long)i * D + head * HD + d]);
-    __syncwarp();
-    const float scale = rsqrtf((float)HD);
-    float sc[4];
-    float mx = -INFINITY;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int j = lane + 32 * t;
-        float s = -INFINITY;
-        if (j < nk) {
-            const uint4* kp = reinterpret_cast<const uint4*>(ckv + ((long long)j * B + row) * (2 * D) + head * HD);
-            uint4 u[NCH];
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) u[c] = __ldg(kp + c);   // all loads of the row in flight together
-            s = 0.f;
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                const float* qv = &sQ[warp][c * 8];
-                s += qv[0] * bf16_lo(u[c].x) + qv[1] * bf16_hi(u[c].x) + qv[2] * bf16_lo(u[c].y) +
-                     qv[3] * bf16_hi(u[c].y) + qv[4] * bf16_lo(u[c].z) + qv[5] * bf16_hi(u[c].z) +
-                     qv[6] * bf16_lo(u[c].w) + qv[7] * bf16_hi(u[c].w);
-            }
-            s *= scale;
-        }
-        sc[t] = s;
-        mx = fmaxf(mx, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    float sum = 0.f;
-#pragma unroll
-    for (int t = 0; t < 4; ++t) {
-        const int j = lane + 32 * t;
-        if (j < nk) {
-            const float p = __expf(sc[t] - mx);
-            sP[warp][j] = p;
-            sum += p;
-        }
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    __syncwarp();
-    const float inv = 1.f / sum;
-    // value phase: lane = (key subset, 16-byte chunk); partial sums of the subsets are folded with shuffles
-    const int ch = lane % NCH, sub = lane / NCH;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (sub < NSUB) {
-        const __nv_bfloat16* vbase = ckv + (long long)row * (2 * D) + D + head * HD;
-#pragma unroll 4
-        for (int j = sub; j < nk; j += NSUB) {
-            const float p = sP[warp][j];
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(vbase + (long long)j * B * (2 * D)) + ch);
-            acc[0] += p * bf16_lo(u.x); acc[1] += p * bf16_hi(u.x); acc[2] += p * bf16_lo(u.y); acc[3] += p * bf16_hi(u.y);
-            acc[4] += p * bf16_lo(u.z); acc[5] += p * bf16_hi(u.z); acc[6] += p * bf16_lo(u.w); acc[7] += p * bf16_hi(u.w);
-        }
-    }
-#pragma unroll
-    for (int g = 1; g < NSUB; ++g) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            const float o = __shfl_down_sync(0xffffffffu, acc[e], g * NCH);
-            if (sub == 0) acc[e] += (lane + g * NCH < 32) ? o : 0.f;
-        }
-    }
-    // note: the fold above adds subset g's ORIGINAL partials only into subset 0 (lanes < NCH)
-    if (lane < NCH) {
-        uint4 o;
-        o.x = pack_bf16(acc[0] * inv, acc[1] * inv);
-        o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
-        o.z = pack_bf16(acc[4] * inv, acc[5] * inv);
-        o.w = pack_bf16(acc[6] * inv, acc[7] * inv);
-        reinterpret_cast<uint4*>(out + (long long)row * D + head * HD)[lane] = o;
-    }
-}
-
-int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, int heads, int mode, const int* step_dev,
-                         const int* klen, const int* kpad, void* out, cudaStream_t st) {
-    const int hd = D / heads;
-    if (hd > kMaxHd || (hd % 8) != 0) {
-        set_error("decoder self-attention: head dim %d unsupported", hd);
-        return 1;
-    }
-    static const bool old_ar = getenv("YTK_OLD_ATTN") != nullptr;  // A/B aid: previous kernels
-    if (mode == 0 && !old_ar)
-        return launch_single_query_attn(0, q_shared, ckv, B, D, heads, step_dev, nullptr, out, st);
-    if (mode == 0) {
-        const int warps = B * heads;
-        const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(q_shared),
-                            *kv = reinterpret_cast<const __nv_bfloat16*>(ckv);
-        __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-        const unsigned grid = (warps + 3) / 4;
-        switch (hd) {
-            case 32: dec_self_attn_ar_kernel<32><<<grid, 128, 0, st>>>(q, kv, B, D, heads, step_dev, o); break;
-            case 48: dec_self_attn_ar_kernel<48><<<grid, 128, 0, st>>>(q, kv, B, D, heads, step_dev, o); break;
-            case 64: dec_self_attn_ar_kernel<64><<<grid, 128, 0, st>>>(q, kv, B, D, heads, step_dev, o); break;
-            case 96: dec_self_attn_ar_kernel<96><<<grid, 128, 0, st>>>(q, kv, B, D, heads, step_dev, o); break;
-            default: set_error("decoder self-attention: head dim %d unsupported (32/48/64/96)", hd); return 1;
-        }
-        count_launch();
-        return cudaGetLastError() != cudaSuccess;
-    }
-    dim3 grid(B, heads);
-    const int smem = (2 * kMaxS * (hd + 1) + 4 * (kMaxS + 3) + 4 * hd) * (int)sizeof(float);
-    static bool attr_set = false;
-    if (!attr_set) {
-        if (cudaFuncSetAttribute(dec_self_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) !=
-            cudaSuccess) {
-            set_error("dec_self_attn: cannot raise dynamic shared memory");
-            return 1;
-        }
-        attr_set = true;
-    }
-    dec_self_attn_kernel<<<grid, 128, smem, st>>>(reinterpret_cast<const __nv_bfloat16*>(q_shared),
-                                                  reinterpret_cast<const __nv_bfloat16*>(ckv), B, D, hd, mode, step_dev,
-                                                  klen, kpad, reinterpret_cast<__nv_bfloat16*>(out));
-    count_launch();
-    return cudaGetLastError() != cudaSuccess;
-}
 
 // =================================================================================================== single-query attention
 // Both attentions of an AR step have ONE query per (row, head) against a strided list of cached K/V rows:
-//   mode 0  self : q = q_shared[step], keys = content cache rows (stride B*2D), nk = step + 1
+//   mode 0  self : q = q_shared[step], keys = the row's content cache [row][pos][2D] (stride 2D), nk = step + 1
 //   mode 1  cross: q = qc[row],        keys = the row's encoder memory K/V (stride 2D), nk = ntok
 // One warp per (row, head), no block-level synchronisation.  LPK lanes share a key (each owns CPL 16-byte chunks of the
 // head dim), 32/LPK key subsets run side by side, so every lane keeps several independent 16-byte loads in flight -
 // the step is HBM-bound on exactly these reads (profiles/README_r01.md).
 template <int HD>
 __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const __nv_bfloat16* __restrict__ qsrc,
-                                                                const __nv_bfloat16* __restrict__ kv, int B, int D,
-                                                                int heads, const int* __restrict__ step_dev,
+                                                                const __nv_bfloat16* __restrict__ kv, int B, int S,
+                                                                int D, int heads, const int* __restrict__ step_dev,
                                                                 const CropDesc* __restrict__ descs,
                                                                 __nv_bfloat16* __restrict__ out) {
     constexpr int NCH = HD / 8;
@@ -712,9 +498,9 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
     if (mode == 0) {
         const int i = *step_dev;
         nk = i + 1;
-        kstride = (long long)B * 2 * D;
+        kstride = 2 * D;
         qp = qsrc + (long long)i * D + head * HD;
-        kbase = kv + (long long)row * (2 * D) + head * HD;
+        kbase = kv + (long long)row * S * (2 * D) + head * HD;
     } else {
         const CropDesc d = descs[row];
         nk = d.ntok;
@@ -801,127 +587,35 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
     }
 }
 
-static int launch_single_query_attn(int mode, const void* qsrc, const void* kv, int B, int D, int heads,
+static int launch_single_query_attn(int mode, const void* qsrc, const void* kv, int B, int S, int D, int heads,
                                     const int* step_dev, const CropDesc* descs, void* out, cudaStream_t st) {
     const int hd = D / heads;
     const unsigned grid = (B * heads + 3) / 4;
     const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(qsrc), *k = reinterpret_cast<const __nv_bfloat16*>(kv);
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     switch (hd) {
-        case 32: single_query_attn_kernel<32><<<grid, 128, 0, st>>>(mode, q, k, B, D, heads, step_dev, descs, o); break;
-        case 48: single_query_attn_kernel<48><<<grid, 128, 0, st>>>(mode, q, k, B, D, heads, step_dev, descs, o); break;
-        case 64: single_query_attn_kernel<64><<<grid, 128, 0, st>>>(mode, q, k, B, D, heads, step_dev, descs, o); break;
-        case 96: single_query_attn_kernel<96><<<grid, 128, 0, st>>>(mode, q, k, B, D, heads, step_dev, descs, o); break;
+        case 32: single_query_attn_kernel<32><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
+        case 48: single_query_attn_kernel<48><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
+        case 64: single_query_attn_kernel<64><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
+        case 96: single_query_attn_kernel<96><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
         default: set_error("single-query attention: head dim %d unsupported (32/48/64/96)", hd); return 1;
     }
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
 
-// =================================================================================================== AR cross-attn
-// One query per row against the row's encoder memory (reference cross_attn, parseq_transformer.py:92).  The memory
-// K/V were projected ONCE (the reference re-projects them every step).  CTA per (row, head).
-
-template <int HD>
-__global__ void __launch_bounds__(128) dec_cross_attn_kernel(const __nv_bfloat16* __restrict__ qc,
-                                                             const __nv_bfloat16* __restrict__ memkv,
-                                                             const CropDesc* __restrict__ descs, int D,
-                                                             __nv_bfloat16* __restrict__ out) {
-    constexpr int hd = HD;
-    __shared__ float sQ[HD];
-    __shared__ float sP[kMaxMem];
-    __shared__ float sRed[4];
-    const int row = blockIdx.x, head = blockIdx.y;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const CropDesc d = descs[row];
-    const int n = d.ntok;
-    for (int i = threadIdx.x; i < hd; i += 128) sQ[i] = __bfloat162float(qc[(long long)row * D + head * hd + i]);
-    __syncthreads();
-    const float scale = rsqrtf((float)hd);
-    const __nv_bfloat16* kbase = memkv + (long long)d.tok_off * (2 * D) + head * hd;
-    float mx = -INFINITY;
-    for (int j = threadIdx.x; j < n; j += 128) {
-        const uint4* kp = reinterpret_cast<const uint4*>(kbase + (long long)j * (2 * D));
-        uint4 uu[HD / 8];
-#pragma unroll
-        for (int c = 0; c < HD / 8; ++c) uu[c] = __ldg(kp + c);   // the whole K row in flight at once
-        float s = 0.f;
-#pragma unroll
-        for (int c = 0; c < HD / 8; ++c) {
-            const uint4 u = uu[c];
-            s += sQ[c * 8 + 0] * bf16_lo(u.x) + sQ[c * 8 + 1] * bf16_hi(u.x) + sQ[c * 8 + 2] * bf16_lo(u.y) +
-                 sQ[c * 8 + 3] * bf16_hi(u.y) + sQ[c * 8 + 4] * bf16_lo(u.z) + sQ[c * 8 + 5] * bf16_hi(u.z) +
-                 sQ[c * 8 + 6] * bf16_lo(u.w) + sQ[c * 8 + 7] * bf16_hi(u.w);
-        }
-        s *= scale;
-        sP[j] = s;
-        mx = fmaxf(mx, s);
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    if (lane == 0) sRed[warp] = mx;
-    __syncthreads();
-    mx = fmaxf(fmaxf(sRed[0], sRed[1]), fmaxf(sRed[2], sRed[3]));
-    __syncthreads();
-    float sum = 0.f;
-    for (int j = threadIdx.x; j < n; j += 128) {
-        const float p = __expf(sP[j] - mx);
-        sP[j] = p;
-        sum += p;
-    }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    if (lane == 0) sRed[warp] = sum;
-    __syncthreads();
-    sum = sRed[0] + sRed[1] + sRed[2] + sRed[3];
-    // PV with 16-byte loads: thread = (key subset, 8-wide chunk of the head dim); partial sums meet in shared memory
-    const int nch = hd >> 3;                 // chunks per row (<= 12)
-    const int nsub = 128 / nch;              // key subsets (>= 10)
-    const int ch = threadIdx.x % nch, sub = threadIdx.x / nch;
-    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    if (sub < nsub) {
-#pragma unroll 4
-        for (int j = sub; j < n; j += nsub) {
-            const float p = sP[j];
-            const uint4 u = __ldg(reinterpret_cast<const uint4*>(kbase + (long long)j * (2 * D) + D) + ch);
-            acc[0] += p * bf16_lo(u.x); acc[1] += p * bf16_hi(u.x); acc[2] += p * bf16_lo(u.y); acc[3] += p * bf16_hi(u.y);
-            acc[4] += p * bf16_lo(u.z); acc[5] += p * bf16_hi(u.z); acc[6] += p * bf16_lo(u.w); acc[7] += p * bf16_hi(u.w);
-        }
-    }
-    __shared__ float red[1024];              // [nsub][hd], nsub * hd <= 128 * 8
-    if (sub < nsub) {
-#pragma unroll
-        for (int e = 0; e < 8; ++e) red[sub * hd + ch * 8 + e] = acc[e];
-    }
-    __syncthreads();
-    for (int dd = threadIdx.x; dd < hd; dd += 128) {
-        float v = 0.f;
-        for (int k = 0; k < nsub; ++k) v += red[k * hd + dd];
-        out[(long long)row * D + head * hd + dd] = __float2bfloat16(v / sum);
-    }
+// Query stream vs. content K/V cache (reference DecoderLayer.forward_stream self_attn, parseq_transformer.py:83-90):
+// AR step i = *step_dev, one query (position i) per row, keys 0..i of the row's cache.
+int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int S, int D, int heads, const int* step_dev,
+                         void* out, cudaStream_t st) {
+    return launch_single_query_attn(0, q_shared, ckv, B, S, D, heads, step_dev, nullptr, out, st);
 }
 
+// One query per row against the row's encoder memory (reference cross_attn, parseq_transformer.py:92).  The memory
+// K/V were projected ONCE (the reference re-projects them every step).
 int launch_dec_cross_attn(const void* qc, const void* memkv, const CropDesc* descs, int B, int D, int heads, void* out,
                           cudaStream_t st) {
-    const int hd = D / heads;
-    if (hd > kMaxHd || (hd % 8) != 0) {
-        set_error("decoder cross-attention: head dim %d unsupported", hd);
-        return 1;
-    }
-    static const bool old_ar = getenv("YTK_OLD_ATTN") != nullptr;  // A/B aid: previous kernel
-    if (!old_ar) return launch_single_query_attn(1, qc, memkv, B, D, heads, nullptr, descs, out, st);
-    dim3 grid(B, heads);
-    const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(qc), *kv = reinterpret_cast<const __nv_bfloat16*>(memkv);
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
-    switch (hd) {
-        case 32: dec_cross_attn_kernel<32><<<grid, 128, 0, st>>>(q, kv, descs, D, o); break;
-        case 48: dec_cross_attn_kernel<48><<<grid, 128, 0, st>>>(q, kv, descs, D, o); break;
-        case 64: dec_cross_attn_kernel<64><<<grid, 128, 0, st>>>(q, kv, descs, D, o); break;
-        case 96: dec_cross_attn_kernel<96><<<grid, 128, 0, st>>>(q, kv, descs, D, o); break;
-        default: set_error("decoder cross-attention: head dim %d unsupported (32/48/64/96)", hd); return 1;
-    }
-    count_launch();
-    return cudaGetLastError() != cudaSuccess;
+    return launch_single_query_attn(1, qc, memkv, B, 0, D, heads, nullptr, descs, out, st);
 }
 
 // =================================================================================================== AR control
@@ -1193,8 +887,8 @@ __global__ void __launch_bounds__(256) refine_embed_kernel(const int* __restrict
     }
     __syncthreads();
     const float rstd = s_stat[1];
-    // layout [pos][row][D] so the K/V GEMM output lands in the cache layout [pos][row][2D]
-    const long long orow = (long long)pos * gridDim.y + row;
+    // layout [row][pos][D]: the K/V GEMM output is the cache layout [row][pos][2D]
+    const long long orow = (long long)row * S + pos;
     for (int t = 0; t < 4; ++t) {
         const int d = threadIdx.x + t * 256;
         if (d < D) cin[orow * D + d] = __float2bfloat16((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
@@ -1294,16 +988,17 @@ int launch_softmax_max(const float* logits, long long ldl, int C, int rows, int 
 
 // Broadcast one row to many (content K/V of the BOS position is identical for every crop).
 __global__ void bcast_rows_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, int vec_per_row,
-                                  long long total) {
+                                  long long dst_stride_vec, long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < total) dst[i] = src[i % vec_per_row];
+    if (i < total) dst[(i / vec_per_row) * dst_stride_vec + i % vec_per_row] = src[i % vec_per_row];
 }
-int launch_bcast_rows(const void* src, void* dst, int row_bytes, int rows, cudaStream_t st) {
+int launch_bcast_rows(const void* src, void* dst, int row_bytes, long long dst_stride_bytes, int rows,
+                      cudaStream_t st) {
     const int vpr = row_bytes / 16;
     const long long total = (long long)vpr * rows;
     if (total <= 0) return 0;
-    bcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(src),
-                                                                       reinterpret_cast<uint4*>(dst), vpr, total);
+    bcast_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        reinterpret_cast<const uint4*>(src), reinterpret_cast<uint4*>(dst), vpr, dst_stride_bytes / 16, total);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
@@ -1327,7 +1022,7 @@ int launch_apply_rep_cut(const int* rep_cut, int B, int S, int C, int eos_id, in
 }
 
 // Per-row descriptors of the refinement self-attention: queries = the shared projected pos_queries (rows 0..S-1 of
-// q_shared), keys = this row's content K/V cache (key j at ckv[(j*B + row) * 2D]), output rows row*S ...
+// q_shared), keys = this row's content K/V cache (key j at ckv[(row*S + j) * 2D]), output rows row*S ...
 __global__ void refine_seqs_kernel(const int* __restrict__ klen, const int* __restrict__ kpad, int B, int S, int D,
                                    SeqDesc* __restrict__ seqs) {
     const int r = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1337,7 +1032,7 @@ __global__ void refine_seqs_kernel(const int* __restrict__ klen, const int* __re
     d.q_len = S;
     d.o_off = r * S;
     d.k_len = klen[r];
-    d.k_base = (long long)r * (2 * D);
+    d.k_base = (long long)r * S * (2 * D);
     d.kpad = kpad[r];
     d.pad_ = 0;
     seqs[r] = d;

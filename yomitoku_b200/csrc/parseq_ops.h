@@ -46,15 +46,11 @@ int launch_flash_attention(const void* Q, long long ldq, const void* K, const vo
                            long long ldo, const SeqDesc* seqs, int nseq, int max_q_len, int heads, int head_dim,
                            int masked, cudaStream_t st);
 
-// Decoder self-attention of the query stream against the per-row content K/V cache.
-//  q_shared: [101, D] bf16 (projected LN_q(pos_queries), identical for every row)
-//  ckv: [101 positions][B rows][2D] bf16
-//  mode 0 (AR step i = *step_dev): one query (position i), keys 0..i            -> out[row, :]
-//  mode 1 (refinement): 101 queries, keys < klen[row]; key j visible to query i iff (i < 2 || j <= i) && j < kpad[row]
-int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int D, int heads, int mode, const int* step_dev,
-                         const int* klen, const int* kpad, void* out, cudaStream_t st);
-
-// AR cross attention: one query per row against that row's memory K/V.
+// AR attention, one query per (row, head) (single_query_attn_kernel):
+//  self : step i = *step_dev, q = q_shared[i], keys 0..i of the row's content K/V cache [row][S positions][2D] -> out[row]
+//  cross: q = qc[row], keys = the row's encoder memory K/V (projected once)                                  -> out[row]
+int launch_dec_self_attn(const void* q_shared, const void* ckv, int B, int S, int D, int heads, const int* step_dev,
+                         void* out, cudaStream_t st);
 int launch_dec_cross_attn(const void* qc, const void* memkv, const CropDesc* descs, int B, int D, int heads, void* out,
                           cudaStream_t st);
 
@@ -87,7 +83,8 @@ int launch_refine_embed(const int* raw, const int* row_group, const int* group_l
 // Output index of local row r is r * g_stride + g_off (= crop * S + position).
 int launch_softmax_max(const float* logits, long long ldl, int C, int rows, int S, long long g_stride, long long g_off,
                        const int* rep_cut, int eos_id, int* ids, float* probs, cudaStream_t st);
-int launch_bcast_rows(const void* src, void* dst, int row_bytes, int rows, cudaStream_t st);
+int launch_bcast_rows(const void* src, void* dst, int row_bytes, long long dst_stride_bytes, int rows,
+                      cudaStream_t st);
 int launch_apply_rep_cut(const int* rep_cut, int B, int S, int C, int eos_id, int* ids, float* probs, cudaStream_t st);
 
 int launch_refine_seqs(const int* klen, const int* kpad, int B, int S, int D, SeqDesc* seqs, cudaStream_t st);
