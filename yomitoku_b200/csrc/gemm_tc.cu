@@ -154,11 +154,20 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    // Cluster mode (args.cluster == 2): the two CTAs of a cluster take the M-adjacent tiles (2p, 2p+1) of the same N
+    // tile in lock step.  Each fetches HALF of the weight tile and multicasts it into both shared memories, so the
+    // L2 -> SM traffic per k block drops from A + B to A + B/2; a stage is refilled only when both CTAs' MMAs have
+    // released it (the commit arrives on both CTAs' empty barriers).
+    const int cl = args.cluster > 1 ? args.cluster : 1;
+    const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
+    const uint16_t cmask = static_cast<uint16_t>((1u << cl) - 1u);
+    const int worker = cl > 1 ? static_cast<int>(blockIdx.x) / cl : static_cast<int>(blockIdx.x);
+    const int n_workers = cl > 1 ? static_cast<int>(gridDim.x) / cl : static_cast<int>(gridDim.x);
 
     if (threadIdx.x == 0) {
         for (int i = 0; i < STAGES; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], 1);
+            mbar_init(&empty_bar[i], cl);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
@@ -177,30 +186,53 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
+    if (cl > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles_m = args.n_img * args.tiles_h * args.tiles_w;
-    const int total_tiles = tiles_m * args.tiles_n;
     const int num_kb = args.ntaps * args.kpt;
+    // work units: tiles, or (pair of M tiles) x (N tile) in cluster mode; a CTA whose M tile does not exist ("ghost")
+    // still takes part in the weight multicast and the barrier protocol, but loads no A, issues no MMA, stores nothing
+    const int total_units = cl > 1 ? ((tiles_m + cl - 1) / cl) * args.tiles_n : tiles_m * args.tiles_n;
+    auto unit_tile = [&](int u, bool& ghost) {
+        if (cl == 1) {
+            ghost = false;
+            return u;
+        }
+        const int mp = u / args.tiles_n, nt = u - mp * args.tiles_n;
+        const int mt = mp * cl + static_cast<int>(crank);
+        ghost = mt >= tiles_m;
+        return mt * args.tiles_n + nt;
+    };
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int u = worker; u < total_units; u += n_workers) {
+                bool ghost;
+                const int tile = unit_tile(u, ghost);
                 const TileCoord tc = decode_tile(args, tile, BLOCK_N);
                 int tap = 0, cb = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
                     uint8_t* sa = smem + stage * Cfg::kStageBytes;
                     uint8_t* sb = sa + kABytes;
-                    mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                    mbar_expect_tx(&full_bar[stage], ghost ? Cfg::kStageBytes - kABytes : Cfg::kStageBytes);
                     const ConvTap tp = args.taps[tap];
-                    tma_load_4d(sa, &maps.a[tp.map], &full_bar[stage], cb * kBlockK, tc.w0 + tp.dw, tc.h0 + tp.dh,
-                                tc.img);
-                    tma_load_4d(sb, &maps.b, &full_bar[stage], kb * kBlockK, tc.n0, 0, 0);
+                    if (!ghost)
+                        tma_load_4d(sa, &maps.a[tp.map], &full_bar[stage], cb * kBlockK, tc.w0 + tp.dw, tc.h0 + tp.dh,
+                                    tc.img);
+                    if (cl > 1) {
+                        // my slice of the weight tile (rows crank * BLOCK_N/cl ...), delivered to every CTA of the cluster
+                        const int rows = BLOCK_N / cl;
+                        tma_load_4d_mc(sb + crank * (rows * kBlockK * 2), &maps.b, &full_bar[stage], kb * kBlockK,
+                                       tc.n0 + static_cast<int>(crank) * rows, 0, 0, cmask);
+                    } else {
+                        tma_load_4d(sb, &maps.b, &full_bar[stage], kb * kBlockK, tc.n0, 0, 0);
+                    }
                     if (++cb == args.kpt) {
                         cb = 0;
                         ++tap;
@@ -220,7 +252,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            for (int u = worker; u < total_units; u += n_workers) {
+                bool ghost;
+                (void)unit_tile(u, ghost);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
@@ -230,13 +264,18 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
                     const uint64_t da = umma_desc_sw128(a_addr);
                     const uint64_t db = umma_desc_sw128(a_addr + kABytes);
+                    if (!ghost) {
 #pragma unroll
-                    for (int k = 0; k < kBlockK / 16; ++k) {
-                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-                        umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k), idesc,
-                                  (kb | k) != 0 ? 1u : 0u);
+                        for (int k = 0; k < kBlockK / 16; ++k) {
+                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                            umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                      idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
-                    umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+                    // frees the smem slot once these MMAs have read it - in cluster mode on every CTA of the cluster,
+                    // because the peers multicast into this CTA's slot as well
+                    if (cl > 1) umma_commit_mc(&empty_bar[stage], cmask);
+                    else umma_commit(&empty_bar[stage]);
                     if (++stage == STAGES) {
                         stage = 0;
                         phase ^= 1u;
@@ -267,7 +306,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         const int piece = lane & 3;
         int acc = 0;
         uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (int u = worker; u < total_units; u += n_workers) {
+            bool ghost;
+            const int tile = unit_tile(u, ghost);
+            if (ghost) {  // nothing to store: just hand the accumulator buffer back
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+                continue;
+            }
             const TileCoord tc = decode_tile(args, tile, BLOCK_N);
             const int hh = tc.h0 + (row >> args.bw_log2);
             const int ww = tc.w0 + (row & bw_mask);
@@ -600,6 +651,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
+    if (cl > 1) cluster_sync_all();  // no CTA leaves while a peer can still signal its barriers
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
@@ -716,12 +768,17 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
         set_error("gemm plan: SHUFFLE2X needs Cout/4 to be a multiple of 32 (Cout=%d)", Cout);
         return 1;
     }
-    // weights: [Cout][Ktot] bf16, K-major
+    // Large problems run as CTA pairs that multicast the weight tile (gemm_tc_kernel, "cluster mode"): worth it once
+    // every SM has several tiles to work through; YTK_NO_CLUSTER=1 switches it off (A/B aid).
+    const int tiles_m = a.n_img * a.tiles_h * a.tiles_w;
+    const int tiles = tiles_m * a.tiles_n;
+    static const bool no_cluster = getenv("YTK_NO_CLUSTER") != nullptr;
+    a.cluster = (!no_cluster && e.mode != EPI_CONVT_FINAL && tiles >= 4 * num_sms() && tiles_m >= 8) ? 2 : 1;
+    // weights: [Cout][Ktot] bf16, K-major; in cluster mode a CTA fetches block_n / cluster rows per k block
     uint64_t dims[4] = {(uint64_t)Ktot, (uint64_t)Cout, 1, 1};
     uint64_t strides[3] = {(uint64_t)Ktot * 2, (uint64_t)Ktot * 2 * Cout, (uint64_t)Ktot * 2 * Cout};
-    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)plan->block_n, 1, 1};
+    uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(plan->block_n / a.cluster), 1, 1};
     if (make_tmap_bf16_4d(&plan->maps.b, w_packed, dims, strides, box)) return 1;
-    const int tiles = a.n_img * a.tiles_h * a.tiles_w * a.tiles_n;
     plan->grid = tiles < num_sms() ? tiles : num_sms();
     if (plan->grid < 1) plan->grid = 1;
     return 0;
@@ -893,6 +950,46 @@ static int launch_variant2(const GemmPlan* plan, cudaStream_t stream) {
             return 1;
         }
         attr_set = true;
+    }
+    if (plan->args.cluster > 1) {
+        // persistent grid = every cluster the device can hold at once (clusters cannot straddle GPCs, so this can be
+        // fewer than num_sms / 2), capped by the number of work units
+        const int cl = plan->args.cluster;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        static int max_clusters = -1;
+        if (max_clusters < 0) {
+            cfg.gridDim = dim3((num_sms() / cl) * cl);
+            int n = 0;
+            cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+            if (e != cudaSuccess || n < 1) {
+                set_error("cudaOccupancyMaxActiveClusters: %s (n=%d)", cudaGetErrorString(e), n);
+                return 1;
+            }
+            max_clusters = n;
+        }
+        const GemmArgs& a = plan->args;
+        const int tiles_m = a.n_img * a.tiles_h * a.tiles_w;
+        const int units = ((tiles_m + cl - 1) / cl) * a.tiles_n;
+        const int clusters = units < max_clusters ? units : max_clusters;
+        cfg.gridDim = dim3(clusters * cl);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->maps, plan->args);
+        count_launch();
+        if (e != cudaSuccess) {
+            set_error("gemm_tc_kernel<%d,%d,%d,%d,%d> cluster launch: %s", BLOCK_N, OUT_F32, RESID, MODE, DIRECT,
+                      cudaGetErrorString(e));
+            return 1;
+        }
+        return 0;
     }
     kern<<<plan->grid, kThreads, Cfg::kSmemBytes, stream>>>(plan->maps, plan->args);
     count_launch();

@@ -56,6 +56,8 @@ struct GemmArgs {
     int mode;
     const float* fin_w;            // EPI_CONVT_FINAL: device [4][64] fp32, k = i'*2+j' of the last transposed conv
     float fin_b;
+    int cluster;                   // 1, or 2: CTA pairs (thread-block cluster) work on M-adjacent tiles of one N tile
+                                   // and multicast the weight tile - each CTA fetches half of it from L2
 };
 
 struct Epilogue {
@@ -84,7 +86,7 @@ struct GemmPlan {
     GemmMaps maps;
     GemmArgs args;
     int block_n;
-    int grid;
+    int grid;      // CTAs to launch (cluster mode: set at launch from the occupancy query)
     double flops;  // 2*M*N*K of the true problem (for roofline accounting)
 };
 
