@@ -58,6 +58,10 @@ struct TileCfg {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    // CTA-pair mode: a CTA stages only half of the weight tile; the ring lives in the same kStages * kStageBytes bytes
+    static constexpr int kStageBytes2 = kABytes + kBBytes / 2;
+    static constexpr int kStages2 =
+        (kStages * kStageBytes / kStageBytes2) > 8 ? 8 : (kStages * kStageBytes / kStageBytes2);
     static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; 128/256/512 are powers of two
     static constexpr int kSmemBytes =
         kStages * kStageBytes + kEpiStageBytes + 1024 /*final-conv weights*/ + 1024 /*align slack*/ + 256 /*barriers*/;
@@ -139,61 +143,75 @@ template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmMaps maps,
                                                               const __grid_constant__ GemmArgs args) {
     using Cfg = TileCfg<BLOCK_N>;
-    constexpr int STAGES = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // 1024 B alignment for SWIZZLE_128B
 
-    uint8_t* epi_stage = smem + STAGES * Cfg::kStageBytes;
+    // CTA-pair mode (args.cluster == 2, launched as clusters of 2 = the two SMs of a TPC): the pair computes the
+    // M-adjacent tiles (2p, 2p+1) of one N tile with ONE tcgen05.mma.cta_group::2 (256 x BLOCK_N x 16) per k step.
+    // Each CTA stages its own 128-row A tile and only HALF of the weight tile (the MMA reads the other half from the
+    // peer's shared memory), so an SM's shared-memory traffic per k block drops from (A + B) filled + (A + B) read to
+    // (A + B/2) + (A + B/2): with both operands in shared memory the single-CTA kernel is bound by exactly that
+    // bandwidth (tensor pipe 68 % active, profiles/README_r01.md).  Protocol: both producers' TMA bytes are counted on
+    // the LEADER's (rank 0) full barrier; the leader's MMA thread issues for the pair and its commits arrive on both
+    // CTAs' empty / accumulator-full barriers; both CTAs' epilogue warps release the accumulator on the leader's
+    // accumulator-empty barrier.
+    const int cl = args.cluster > 1 ? 2 : 1;
+    const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
+    const bool leader = crank == 0;
+    constexpr uint16_t kPairMask = 0x3;
+    const int worker = cl > 1 ? static_cast<int>(blockIdx.x) / cl : static_cast<int>(blockIdx.x);
+    const int n_workers = cl > 1 ? static_cast<int>(gridDim.x) / cl : static_cast<int>(gridDim.x);
+    const int stage_bytes = cl > 1 ? Cfg::kStageBytes2 : Cfg::kStageBytes;
+    const int nstages = cl > 1 ? Cfg::kStages2 : Cfg::kStages;
+
+    uint8_t* epi_stage = smem + Cfg::kStages * Cfg::kStageBytes;  // same carve-up in both modes (ring <= this size)
     float* fin_w = reinterpret_cast<float*>(epi_stage + kEpiStageBytes);  // [4][64] weights of the fused final conv
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageBytes + 1024);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;
+    uint64_t* empty_bar = full_bar + 8;
+    uint64_t* tfull_bar = empty_bar + 8;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    // Cluster mode (args.cluster == 2): the two CTAs of a cluster take the M-adjacent tiles (2p, 2p+1) of the same N
-    // tile in lock step.  Each fetches HALF of the weight tile and multicasts it into both shared memories, so the
-    // L2 -> SM traffic per k block drops from A + B to A + B/2; a stage is refilled only when both CTAs' MMAs have
-    // released it (the commit arrives on both CTAs' empty barriers).
-    const int cl = args.cluster > 1 ? args.cluster : 1;
-    const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
-    const uint16_t cmask = static_cast<uint16_t>((1u << cl) - 1u);
-    const int worker = cl > 1 ? static_cast<int>(blockIdx.x) / cl : static_cast<int>(blockIdx.x);
-    const int n_workers = cl > 1 ? static_cast<int>(gridDim.x) / cl : static_cast<int>(gridDim.x);
 
     if (threadIdx.x == 0) {
-        for (int i = 0; i < STAGES; ++i) {
+        for (int i = 0; i < nstages; ++i) {
             mbar_init(&full_bar[i], 1);
-            mbar_init(&empty_bar[i], cl);
+            mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tfull_bar[i], 1);
-            mbar_init(&tempty_bar[i], 8);  // one arrive per epilogue warp
+            mbar_init(&tempty_bar[i], 8 * cl);  // one arrive per epilogue warp (of both CTAs in pair mode)
         }
         fence_mbar_init();
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b);
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, Cfg::kTmemCols);
-        tmem_relinquish();
+        if (cl > 1) {
+            tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
+            tmem_relinquish_cg2();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::kTmemCols);
+            tmem_relinquish();
+        }
     }
     if constexpr (MODE == EPI_CONVT_FINAL) {
         if (threadIdx.x >= 64) fin_w[threadIdx.x - 64] = args.fin_w[threadIdx.x - 64];
     }
     tc_fence_before();
     __syncthreads();
-    if (cl > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is multicast to them
+    if (cl > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
     const int tiles_m = args.n_img * args.tiles_h * args.tiles_w;
     const int num_kb = args.ntaps * args.kpt;
-    // work units: tiles, or (pair of M tiles) x (N tile) in cluster mode; a CTA whose M tile does not exist ("ghost")
-    // still takes part in the weight multicast and the barrier protocol, but loads no A, issues no MMA, stores nothing
+    // work units: tiles, or (pair of M tiles) x (N tile) in pair mode; a rank-1 CTA whose M tile does not exist
+    // ("ghost", odd tile counts) still stages its half of the weights and follows the barrier protocol, but loads no A
+    // and stores nothing (its accumulator rows are garbage)
     const int total_units = cl > 1 ? ((tiles_m + cl - 1) / cl) * args.tiles_n : tiles_m * args.tiles_n;
     auto unit_tile = [&](int u, bool& ghost) {
         if (cl == 1) {
@@ -211,33 +229,41 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
+            // pair mode: every TMA of the pair signals the leader's full barrier
+            const uint32_t full0 = cl > 1 ? mapa_u32(&full_bar[0], 0) : 0u;
             for (int u = worker; u < total_units; u += n_workers) {
                 bool ghost;
                 const int tile = unit_tile(u, ghost);
                 const TileCoord tc = decode_tile(args, tile, BLOCK_N);
+                // does the pair's rank-1 tile exist?  (the leader must know how many bytes to expect)
+                const bool peer_ghost = cl > 1 && ((u / args.tiles_n) * 2 + 1 >= tiles_m);
                 int tap = 0, cb = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1u);
-                    uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                    uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + kABytes;
-                    mbar_expect_tx(&full_bar[stage], ghost ? Cfg::kStageBytes - kABytes : Cfg::kStageBytes);
                     const ConvTap tp = args.taps[tap];
-                    if (!ghost)
+                    if (cl > 1) {
+                        if (leader)
+                            mbar_expect_tx(&full_bar[stage],
+                                           2 * Cfg::kStageBytes2 - (peer_ghost ? kABytes : 0));
+                        const uint32_t fb = full0 + static_cast<uint32_t>(stage) * 8u;
+                        if (!ghost)
+                            tma_load_4d_cg2(sa, &maps.a[tp.map], fb, cb * kBlockK, tc.w0 + tp.dw, tc.h0 + tp.dh, tc.img);
+                        // my half of the weight tile: rows n0 + rank * BLOCK_N/2 ...
+                        tma_load_4d_cg2(sb, &maps.b, fb, kb * kBlockK, tc.n0 + static_cast<int>(crank) * (BLOCK_N / 2), 0,
+                                        0);
+                    } else {
+                        mbar_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                         tma_load_4d(sa, &maps.a[tp.map], &full_bar[stage], cb * kBlockK, tc.w0 + tp.dw, tc.h0 + tp.dh,
                                     tc.img);
-                    if (cl > 1) {
-                        // my slice of the weight tile (rows crank * BLOCK_N/cl ...), delivered to every CTA of the cluster
-                        const int rows = BLOCK_N / cl;
-                        tma_load_4d_mc(sb + crank * (rows * kBlockK * 2), &maps.b, &full_bar[stage], kb * kBlockK,
-                                       tc.n0 + static_cast<int>(crank) * rows, 0, 0, cmask);
-                    } else {
                         tma_load_4d(sb, &maps.b, &full_bar[stage], kb * kBlockK, tc.n0, 0, 0);
                     }
                     if (++cb == args.kpt) {
                         cb = 0;
                         ++tap;
                     }
-                    if (++stage == STAGES) {
+                    if (++stage == nstages) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -245,43 +271,45 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
         }
     } else if (warp == 1) {
-        // ------------------------------------------------------------------ MMA issuer
-        if (lane == 0) {
+        // ------------------------------------------------------------------ MMA issuer (pair mode: the leader only)
+        if (lane == 0 && (cl == 1 || leader)) {
             constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
+            constexpr uint32_t idesc2 = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
             for (int u = worker; u < total_units; u += n_workers) {
-                bool ghost;
-                (void)unit_tile(u, ghost);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1u);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + static_cast<uint32_t>(acc * BLOCK_N);
                 for (int kb = 0; kb < num_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t a_addr = smem_u32(smem + stage * Cfg::kStageBytes);
+                    const uint32_t a_addr = smem_u32(smem + stage * stage_bytes);
                     const uint64_t da = umma_desc_sw128(a_addr);
                     const uint64_t db = umma_desc_sw128(a_addr + kABytes);
-                    if (!ghost) {
 #pragma unroll
-                        for (int k = 0; k < kBlockK / 16; ++k) {
-                            // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                    for (int k = 0; k < kBlockK / 16; ++k) {
+                        // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
+                        if (cl > 1)
+                            umma_bf16_cg2(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                                          idesc2, (kb | k) != 0 ? 1u : 0u);
+                        else
                             umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                                       idesc, (kb | k) != 0 ? 1u : 0u);
-                        }
                     }
-                    // frees the smem slot once these MMAs have read it - in cluster mode on every CTA of the cluster,
-                    // because the peers multicast into this CTA's slot as well
-                    if (cl > 1) umma_commit_mc(&empty_bar[stage], cmask);
+                    // frees the smem slot once these MMAs have read it (on both CTAs of a pair)
+                    if (cl > 1) umma_commit_cg2(&empty_bar[stage], kPairMask);
                     else umma_commit(&empty_bar[stage]);
-                    if (++stage == STAGES) {
+                    if (++stage == nstages) {
                         stage = 0;
                         phase ^= 1u;
                     }
                 }
-                umma_commit(&tfull_bar[acc]);  // accumulator complete
+                // accumulator complete
+                if (cl > 1) umma_commit_cg2(&tfull_bar[acc], kPairMask);
+                else umma_commit(&tfull_bar[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
             }
@@ -309,12 +337,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         for (int u = worker; u < total_units; u += n_workers) {
             bool ghost;
             const int tile = unit_tile(u, ghost);
-            if (ghost) {  // nothing to store: just hand the accumulator buffer back
+            if (ghost) {  // nothing to store: just hand the accumulator buffer back to the leader
                 mbar_wait(&tfull_bar[acc], acc_phase);
                 tc_fence_after();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
                 continue;
@@ -643,7 +671,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (cl > 1) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));  // the leader's MMA thread waits on it
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
@@ -651,11 +682,12 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (cl > 1) cluster_sync_all();  // no CTA leaves while a peer can still signal its barriers
+    if (cl > 1) cluster_sync_all();  // no CTA leaves while its peer can still read its memories / signal its barriers
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if (cl > 1) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
