@@ -139,7 +139,7 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& a, int tile, in
 // Epilogue variants are compile-time (OUT_F32: fp32 vs bf16 output; RESID: 0 none, 1 bf16, 2 fp32; MODE: EpiMode) so
 // that each instantiation carries only its own store path - one kernel with every path inlined is ~190 KB of SASS and
 // thrashes the instruction cache.
-template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT>
+template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmMaps maps,
                                                               const __grid_constant__ GemmArgs args) {
     using Cfg = TileCfg<BLOCK_N>;
@@ -156,8 +156,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     // the LEADER's (rank 0) full barrier; the leader's MMA thread issues for the pair and its commits arrive on both
     // CTAs' empty / accumulator-full barriers; both CTAs' epilogue warps release the accumulator on the leader's
     // accumulator-empty barrier.
-    const int cl = args.cluster > 1 ? 2 : 1;
-    const uint32_t crank = cl > 1 ? cluster_ctarank() : 0u;
+    constexpr int cl = PAIR ? 2 : 1;  // pair kernels contain cta_group::2 instructions and must be launched as clusters
+    uint32_t crank = 0u;
+    if constexpr (PAIR) crank = cluster_ctarank();
     const bool leader = crank == 0;
     constexpr uint16_t kPairMask = 0x3;
     const int worker = cl > 1 ? static_cast<int>(blockIdx.x) / cl : static_cast<int>(blockIdx.x);
@@ -190,7 +191,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         tma_prefetch_desc(&maps.b);
     }
     if (warp == 1) {
-        if (cl > 1) {
+        if constexpr (PAIR) {
             tmem_alloc_cg2(tmem_slot, Cfg::kTmemCols);
             tmem_relinquish_cg2();
         } else {
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     }
     tc_fence_before();
     __syncthreads();
-    if (cl > 1) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled on them
+    if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -230,7 +231,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             int stage = 0;
             uint32_t phase = 0;
             // pair mode: every TMA of the pair signals the leader's full barrier
-            const uint32_t full0 = cl > 1 ? mapa_u32(&full_bar[0], 0) : 0u;
+            uint32_t full0 = 0u;
+            if constexpr (PAIR) full0 = mapa_u32(&full_bar[0], 0);
             for (int u = worker; u < total_units; u += n_workers) {
                 bool ghost;
                 const int tile = unit_tile(u, ghost);
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     uint8_t* sa = smem + stage * stage_bytes;
                     uint8_t* sb = sa + kABytes;
                     const ConvTap tp = args.taps[tap];
-                    if (cl > 1) {
+                    if constexpr (PAIR) {
                         if (leader)
                             mbar_expect_tx(&full_bar[stage],
                                            2 * Cfg::kStageBytes2 - (peer_ghost ? kABytes : 0));
@@ -292,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
-                        if (cl > 1)
+                        if constexpr (PAIR)
                             umma_bf16_cg2(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                                           idesc2, (kb | k) != 0 ? 1u : 0u);
                         else
@@ -300,7 +302,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                       idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     // frees the smem slot once these MMAs have read it (on both CTAs of a pair)
-                    if (cl > 1) umma_commit_cg2(&empty_bar[stage], kPairMask);
+                    if constexpr (PAIR) umma_commit_cg2(&empty_bar[stage], kPairMask);
                     else umma_commit(&empty_bar[stage]);
                     if (++stage == nstages) {
                         stage = 0;
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     }
                 }
                 // accumulator complete
-                if (cl > 1) umma_commit_cg2(&tfull_bar[acc], kPairMask);
+                if constexpr (PAIR) umma_commit_cg2(&tfull_bar[acc], kPairMask);
                 else umma_commit(&tfull_bar[acc]);
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
@@ -342,7 +344,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 tc_fence_after();
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+                if constexpr (PAIR) {
+                    if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+                }
                 acc ^= 1;
                 if (acc == 0) acc_phase ^= 1u;
                 continue;
@@ -672,7 +676,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
-                if (cl > 1) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));  // the leader's MMA thread waits on it
+                if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));  // the leader's MMA thread waits
                 else mbar_arrive(&tempty_bar[acc]);
             }
             acc ^= 1;
@@ -682,11 +686,11 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 
     tc_fence_before();
     __syncthreads();
-    if (cl > 1) cluster_sync_all();  // no CTA leaves while its peer can still read its memories / signal its barriers
+    if constexpr (PAIR) cluster_sync_all();  // no CTA leaves while its peer can still use its memories / barriers
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        if (cl > 1) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
+        if constexpr (PAIR) tmem_dealloc_cg2(tmem_base, Cfg::kTmemCols);
         else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
@@ -970,11 +974,11 @@ void gemm_plan_set_m(GemmPlan* plan, int M) {
     if (plan->grid < 1) plan->grid = 1;
 }
 
-template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT>
-static int launch_variant2(const GemmPlan* plan, cudaStream_t stream) {
+template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT, int PAIR>
+static int launch_variant3(const GemmPlan* plan, cudaStream_t stream) {
     using Cfg = TileCfg<BLOCK_N>;
     static bool attr_set = false;
-    auto kern = gemm_tc_kernel<BLOCK_N, OUT_F32, RESID, MODE, DIRECT>;
+    auto kern = gemm_tc_kernel<BLOCK_N, OUT_F32, RESID, MODE, DIRECT, PAIR>;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) {
@@ -983,7 +987,7 @@ static int launch_variant2(const GemmPlan* plan, cudaStream_t stream) {
         }
         attr_set = true;
     }
-    if (plan->args.cluster > 1) {
+    if constexpr (PAIR != 0) {
         // persistent grid = every cluster the device can hold at once (clusters cannot straddle GPCs, so this can be
         // fewer than num_sms / 2), capped by the number of work units
         const int cl = plan->args.cluster;
@@ -1022,16 +1026,25 @@ static int launch_variant2(const GemmPlan* plan, cudaStream_t stream) {
             return 1;
         }
         return 0;
+    } else {
+        kern<<<plan->grid, kThreads, Cfg::kSmemBytes, stream>>>(plan->maps, plan->args);
+        count_launch();
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("gemm_tc_kernel<%d,%d,%d,%d,%d> launch: %s", BLOCK_N, OUT_F32, RESID, MODE, DIRECT,
+                      cudaGetErrorString(e));
+            return 1;
+        }
+        return 0;
     }
-    kern<<<plan->grid, kThreads, Cfg::kSmemBytes, stream>>>(plan->maps, plan->args);
-    count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        set_error("gemm_tc_kernel<%d,%d,%d,%d,%d> launch: %s", BLOCK_N, OUT_F32, RESID, MODE, DIRECT,
-                  cudaGetErrorString(e));
-        return 1;
+}
+
+template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT>
+static int launch_variant2(const GemmPlan* plan, cudaStream_t stream) {
+    if constexpr (MODE != EPI_CONVT_FINAL && DIRECT == 0) {
+        if (plan->args.cluster > 1) return launch_variant3<BLOCK_N, OUT_F32, RESID, MODE, DIRECT, 1>(plan, stream);
     }
-    return 0;
+    return launch_variant3<BLOCK_N, OUT_F32, RESID, MODE, DIRECT, 0>(plan, stream);
 }
 
 // Epilogue store path: staged (coalesced through shared memory) or direct (row per thread).  YTK_EPI=direct|staged
