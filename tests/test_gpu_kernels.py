@@ -27,8 +27,8 @@ def _check(got, ref, tol=6e-3):
     (128, 64, 64, 0, None, True), (300, 128, 200, 0, None, False), (1000, 768, 2304, 2, None, False),
     (517, 768, 7119, 0, None, True), (640, 3072, 768, 0, "f32", True), (33, 192, 576, 1, "bf16", False),
     (257, 192, 200, 3, "f32", False), (129, 64, 100, 0, "bf16", True),
-    # >= 4 tiles per SM: CTA-pair cluster mode with the weight tile multicast; 75 / 149 M tiles are odd, so the last
-    # pair has a ghost CTA; N = 2304 has 9 full N tiles, N = 7119 a ragged last one, K = 3072 wraps the stage ring
+    # >= 4 tiles per SM: CTA-pair kernel (tcgen05.mma.cta_group::2, half weight tile per SM); 75 / 149 M tiles are odd,
+    # so the last pair has a ghost CTA; N = 2304 has 9 full N tiles, N = 7119 a ragged last one, K = 3072 wraps the stage ring
     (128 * 74 + 5, 768, 2304, 2, None, False), (128 * 148 + 77, 192, 768, 0, "f32", True),
     (128 * 21 + 1, 768, 7119, 0, None, True), (128 * 200, 3072, 768, 0, "f32", True)])
 def test_linear(M, K, N, act, resid, f32):
@@ -61,7 +61,8 @@ def test_linear(M, K, N, act, resid, f32):
     (1, 37, 50, 128, 128, 3, 1, 2, 2, 1, True), (1, 38, 52, 64, 128, 3, 2, 1, 1, 1, False),
     (1, 37, 51, 64, 128, 3, 2, 1, 1, 1, False), (2, 38, 52, 256, 512, 1, 2, 0, 1, 0, False),
     (1, 74, 100, 512, 512, 3, 1, 2, 2, 1, True),
-    # cluster mode (>= 4 tiles per SM): layer-1-like 3x3 and a residual 1x1 on a 296x400 map, odd tile counts
+    # big maps (>= 4 tiles per SM, odd tile counts): layer-1-like 3x3 and a residual 1x1 on a 296x400 map; these take
+    # the CTA-pair kernel as well when YTK_PAIR_CONV=1 is set (off by default: convs lose to the pair's lock step)
     (1, 296, 400, 64, 64, 3, 1, 1, 1, 1, False), (1, 296, 400, 64, 256, 1, 1, 0, 1, 1, True),
     (3, 148, 200, 128, 128, 3, 2, 1, 1, 1, False)])
 def test_conv(N, H, W, Cin, Cout, k, s, p, d, act, resid):

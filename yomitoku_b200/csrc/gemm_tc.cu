@@ -760,7 +760,8 @@ static int pick_bw_log2(int Ho, int Wo) {
     return best;
 }
 
-static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout, const Epilogue& e) {
+static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout, const Epilogue& e,
+                       bool allow_pair = false) {
     GemmArgs& a = plan->args;
     plan->block_n = pick_block_n(Cout);
     static const bool no_shrink = getenv("YTK_NO_SHRINK") != nullptr;  // debugging aid
@@ -804,12 +805,18 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
         set_error("gemm plan: SHUFFLE2X needs Cout/4 to be a multiple of 32 (Cout=%d)", Cout);
         return 1;
     }
-    // Large problems run as CTA pairs that multicast the weight tile (gemm_tc_kernel, "cluster mode"): worth it once
-    // every SM has several tiles to work through; YTK_NO_CLUSTER=1 switches it off (A/B aid).
+    // Large plain GEMMs (the PARSeq linears) run as CTA pairs (gemm_tc_kernel PAIR: tcgen05.mma.cta_group::2), worth it
+    // once every SM has several tiles to work through.  Measured on the bench shapes: PARSeq encoder 62.0 -> 60.9 ms;
+    // the DBNet convolutions that would qualify are epilogue / HBM bound and LOSE 5 % to the pair's lock step, so
+    // convolutions stay single-CTA.  YTK_NO_CLUSTER=1 switches pair mode off, YTK_PAIR_CONV=1 on for convs (A/B aids).
     const int tiles_m = a.n_img * a.tiles_h * a.tiles_w;
     const int tiles = tiles_m * a.tiles_n;
     static const bool no_cluster = getenv("YTK_NO_CLUSTER") != nullptr;
-    a.cluster = (!no_cluster && e.mode != EPI_CONVT_FINAL && tiles >= 4 * num_sms() && tiles_m >= 8) ? 2 : 1;
+    static const bool pair_conv = getenv("YTK_PAIR_CONV") != nullptr;
+    a.cluster = (!no_cluster && (allow_pair || pair_conv) && e.mode != EPI_CONVT_FINAL && tiles >= 4 * num_sms() &&
+                 tiles_m >= 8)
+                    ? 2
+                    : 1;
     // weights: [Cout][Ktot] bf16, K-major; in cluster mode a CTA fetches block_n / cluster rows per k block
     uint64_t dims[4] = {(uint64_t)Ktot, (uint64_t)Cout, 1, 1};
     uint64_t strides[3] = {(uint64_t)Ktot * 2, (uint64_t)Ktot * 2 * Cout, (uint64_t)Ktot * 2 * Cout};
@@ -926,7 +933,7 @@ int gemm_plan_create(GemmPlan* plan, const void* A, long long lda, int M, int K,
     if (make_tmap_bf16_4d(&plan->maps.a[0], A, dims, strides, box)) return 1;
     for (int i = 1; i < 4; ++i) plan->maps.a[i] = plan->maps.a[0];
     plan->flops = 2.0 * M * (double)N * K;
-    return finish_plan(plan, Wt, K, N, e);
+    return finish_plan(plan, Wt, K, N, e, /*allow_pair=*/true);
 }
 
 int stem_plan_create(GemmPlan* plan, const void* in_padded, int N, int Hn, int Wn, const void* w_packed,
