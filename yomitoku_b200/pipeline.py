@@ -250,9 +250,9 @@ class BatchedOCR:
             ring[self._slot] = _SharedBuf(nbytes)
         return ring[self._slot]
 
-    def detect_prob(self, pages, shared=False, stream=None):
-        """Device stage 1: probability maps (n, Hn, Wn) float32 on the host for same-size pages.  With `shared` (pages
-        that are only decimated) pages and maps go through the shared page-locked ring - the H2D/D2H copies are plain
+    def _stage(self, pages, shared):
+        """Host staging of a batch of same-size pages: (stage (n,H,W,3) u8 tensor, out (n,Hn,Wn) f32 tensor).  With
+        `shared` (pages that are only decimated) both live in the shared page-locked ring - the H2D/D2H copies are plain
         DMAs and the workers read both without a copy; `self._last_shared` then holds the two buffers."""
         import torch
         n = len(pages)
@@ -272,8 +272,13 @@ class BatchedOCR:
         else:
             stage = torch.from_numpy(np.stack([np.ascontiguousarray(p) for p in pages]))
             out = torch.empty((n, hn, wn), dtype=torch.float32)
-        for s in range(0, n, self.det_batch):
-            e = min(n, s + self.det_batch)
+        return stage, out
+
+    def detect_prob(self, pages, shared=False, stream=None):
+        """Device stage 1: probability maps (n, Hn, Wn) float32 on the host for same-size pages."""
+        stage, out = self._stage(pages, shared)
+        for s in range(0, len(pages), self.det_batch):
+            e = min(len(pages), s + self.det_batch)
             self.detector.model.detect_pages_u8(stage[s:e], out=out[s:e], stream=stream)
         return out.numpy()
 
@@ -449,32 +454,38 @@ class BatchedOCR:
         with _span("submit.wait_slot"):
             for f in self._slot_busy.pop(self._slot, []):
                 f.result()
-        with _span("submit.detect"):
-            prob = self.detect_prob(pages, shared=pool is not None, stream=stream)
-        jobs = []
+        n = len(pages)
+        stage, out = self._stage(pages, shared=pool is not None)
+        prob = out.numpy()
         sh = self._last_shared if pool is not None else None
         arena, cap = None, self.crop_cap
         if sh is not None:
             pb, ob = sh
-            arena = self._shared("crops", len(pages) * cap)
+            arena = self._shared("crops", n * cap)
             h0, w0 = pages[0].shape[:2]
-            if prob_override is not None:      # benchmarks with random detector weights: overwrite the D2H result
-                for i in range(len(pages)):
-                    np.copyto(prob[i], prob_override[i])
-        for i, p in enumerate(pages):
-            qo = None if quads_override is None else quads_override[i]
-            if sh is None:
-                jobs.append((p, prob[i] if prob_override is None else prob_override[i], qo))
-            else:      # descriptors only: the workers map the three buffers themselves
-                jobs.append((pb.desc(i * h0 * w0 * 3, (h0, w0, 3), np.uint8),
-                             ob.desc(i * prob[i].nbytes, prob[i].shape, np.float32), qo,
-                             arena.desc(i * cap, (cap,), np.uint8)))
         if pool is None:
             r = self.recognizer
             _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
-            return _Handle([_Done(_host_stage(j)) for j in jobs], None, 0)
-        with _span("submit.jobs"):
-            futs = [pool.submit(_host_stage, j) for j in jobs]
+        futs = []
+        # detection in chunks of det_batch pages; a chunk's host jobs start while the next chunk is on the device
+        for s in range(0, n, self.det_batch):
+            e = min(n, s + self.det_batch)
+            with _span("submit.detect"):
+                self.detector.model.detect_pages_u8(stage[s:e], out=out[s:e], stream=stream)
+            for i in range(s, e):
+                qo = None if quads_override is None else quads_override[i]
+                if sh is None:
+                    job = (pages[i], prob[i] if prob_override is None else prob_override[i], qo)
+                else:
+                    if prob_override is not None:   # benchmarks with random detector weights: overwrite the D2H result
+                        np.copyto(prob[i], prob_override[i])
+                    # descriptors only: the workers map the three buffers themselves
+                    job = (pb.desc(i * h0 * w0 * 3, (h0, w0, 3), np.uint8),
+                           ob.desc(i * prob[i].nbytes, prob[i].shape, np.float32), qo,
+                           arena.desc(i * cap, (cap,), np.uint8))
+                futs.append(_Done(_host_stage(job)) if pool is None else pool.submit(_host_stage, job))
+        if pool is None:
+            return _Handle(futs, None, 0)
         self._slot_busy[self._slot] = futs
         return _Handle(futs, arena, cap)
 
