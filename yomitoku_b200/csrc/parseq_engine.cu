@@ -374,7 +374,7 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
     DM(kpad, 4 * B);
     DM(ids, 4 * R);
     DM(probs, 4 * R);
-    ar_block_ints = (size_t)(2 * R + 3 * B + 2 * cap_groups + 3);
+    ar_block_ints = (size_t)(2 * R + 3 * B + 2 * cap_groups + 8);
     DM(ar_block, 4 * ar_block_ints);
 #undef DM
     ar.tgt = ar_block;
@@ -383,11 +383,15 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
     ar.rep_done = ar.rep_cut + B;
     ar.has_eos = ar.rep_done + B;
     ar.group_len = ar.has_eos + B;
-    ar.n_active = ar.group_len + cap_groups;
+    ar.open_rows = ar.group_len + cap_groups;
+    // per-part scalars (the AR loop may run as two row ranges on two streams): [n_active, step, ticket, pad] x 2
+    ar.n_active = ar.open_rows + cap_groups;
     ar.step = ar.n_active + 1;
-    ar.open_rows = ar.step + 1;
-    ar.ticket = ar.open_rows + cap_groups;
-    if (!host_flag) CK(cudaMallocHost(reinterpret_cast<void**>(&host_flag), 2 * sizeof(int)));
+    ar.ticket = ar.n_active + 2;
+    if (!host_flag) CK(cudaMallocHost(reinterpret_cast<void**>(&host_flag), 4 * sizeof(int)));
+    if (!st2) CK(cudaStreamCreateWithFlags(&st2, cudaStreamNonBlocking));
+    if (!ev_fork) CK(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    if (!ev_join) CK(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
     for (int i = 0; i < 5; ++i)
         if (!ev[i]) CK(cudaEventCreate(&ev[i]));
     return 0;
@@ -396,6 +400,9 @@ int ParseqEngine::ensure(long long tok, int rows, long long crop_bytes, int grou
 ParseqEngine::~ParseqEngine() {
     for (void* p : bufs) cudaFree(p);
     if (host_flag) cudaFreeHost(host_flag);
+    if (st2) cudaStreamDestroy(st2);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     for (int i = 0; i < 5; ++i)
         if (ev[i]) cudaEventDestroy(ev[i]);
 }
@@ -522,74 +529,164 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     int steps_run = 0;
     const int hd_d = D / c.dec_heads;
     if (c.decode_ar) {
-    // content K/V cache [row][position 0..S-1][2D]; position 0 (<bos>) is the same for every row
-    if (launch_bcast_rows(m->ckv0, ckv, 2 * D * 2, (long long)S * 2 * D * 2, B, st)) return 1;
-    // plans reused by every step
-    GemmPlan p_so, p_cq, p_co, p_l1, p_l2, p_hd, p_kv;
-    Epilogue e;
-    auto mk = [&](GemmPlan* p, const void* A, long long lda, int M, const LinearW& w, void* out, long long ldc,
-                  int out_f32, int act, const void* resid, int resid_f32, long long ldr) {
-        Epilogue ep;
-        ep.bias = w.b;
-        ep.resid = resid;
-        ep.resid_f32 = resid_f32;
-        ep.ldr = ldr;
-        ep.out = out;
-        ep.out_f32 = out_f32;
-        ep.ldc = ldc;
-        ep.act = act;
-        return gemm_plan_create(p, A, lda, M, w.K, w.w, w.N, ep);
-    };
-    (void)e;
-    if (mk(&p_so, sa, D, B, m->self_out, x1, D, 1, ACT_NONE, nullptr, 0, 0)) return 1;
-    if (mk(&p_cq, hb, D, B, m->cross_q, qc, D, 0, ACT_NONE, nullptr, 0, 0)) return 1;
-    if (mk(&p_co, oc, D, B, m->cross_out, x1, D, 1, ACT_NONE, x1, 1, D)) return 1;
-    if (mk(&p_l1, hb, D, B, m->lin1, mlpb, m->lin1.N, 0, ACT_GELU, nullptr, 0, 0)) return 1;
-    if (mk(&p_l2, mlpb, m->lin1.N, B, m->lin2, x1, D, 1, ACT_NONE, x1, 1, D)) return 1;
-    if (mk(&p_hd, hb, D, B, m->head, logits, ldl, 1, ACT_NONE, nullptr, 0, 0)) return 1;
-    if (mk(&p_kv, cin, D, B, m->self_kv, ckv, (long long)S * 2 * D, 0, ACT_NONE, nullptr, 0, 0)) return 1;
-    const double step_flops = p_so.flops + p_cq.flops + p_co.flops + p_l1.flops + p_l2.flops + p_hd.flops + p_kv.flops;
-    for (int i = 0; i < S; ++i) {
-        if (launch_dec_self_attn(m->q_self, ckv, B, S, D, c.dec_heads, ar.step, sa, st)) return 1;
-        if (gemm_plan_launch(&p_so, st)) return 1;
-        // x1 += pos_queries[i] (the query stream's residual input), then norm1
-        if (launch_layernorm(x1, B, D, m->Dr, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, 1, ar.step, 0, 1, st))
-            return 1;
-        if (gemm_plan_launch(&p_cq, st)) return 1;
-        if (launch_dec_cross_attn(qc, memkv, descs_dev, B, D, c.dec_heads, oc, st)) return 1;
-        if (gemm_plan_launch(&p_co, st)) return 1;
-        if (launch_layernorm(x1, B, D, m->Dr, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
-            return 1;
-        if (gemm_plan_launch(&p_l1, st)) return 1;
-        if (gemm_plan_launch(&p_l2, st)) return 1;
-        if (launch_layernorm(x1, B, D, m->Dr, m->dec_norm.g, m->dec_norm.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))
-            return 1;
-        if (gemm_plan_launch(&p_hd, st)) return 1;
-        if (c.refine_iters == 0 || logits_out) {
-            if (c.refine_iters == 0) {
-                if (launch_softmax_max(logits, ldl, C, B, S, S, i, nullptr, eos, ids, probs, st)) return 1;
-                if (logits_out)
-                    CK(cudaMemcpy2DAsync(logits_out + (size_t)i * C, (size_t)S * C * 4, logits, ldl * 4, (size_t)C * 4, B,
-                                         logits_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st));
+        // content K/V cache [row][position 0..S-1][2D]; position 0 (<bos>) is the same for every row
+        if (launch_bcast_rows(m->ckv0, ckv, 2 * D * 2, (long long)S * 2 * D * 2, B, st)) return 1;
+        // The decode loop runs as one or two PARTS (row ranges that end on a group boundary), each on its own stream:
+        // a step is a chain of small dependent kernels - HBM-bound attention over the K/V caches, seven GEMMs with
+        // M = rows, LayerNorms, arg-max - that leaves most of the machine idle; with two independent chains in flight
+        // one part's GEMMs overlap the other part's attention.  Parts share nothing but read-only weights / memory K/V.
+        struct Part {
+            int r0, rows, g0, ng;
+            ArState a;
+            cudaStream_t st;
+            GemmPlan p_so, p_cq, p_co, p_l1, p_l2, p_hd, p_kv;
+            double step_flops;
+            int* flag;
+            bool done;
+        };
+        int nparts = 1, split_row = B;
+        {
+            const char* ev_ = getenv("YTK_AR_SPLIT_MIN");
+            const int split_min = ev_ ? atoi(ev_) : 1024;
+            bool sorted = true;
+            int best = -1;
+            for (int r = 1; r < B; ++r) {
+                if (rg[r] < rg[r - 1]) sorted = false;
+                if (rg[r] != rg[r - 1] && (best < 0 || std::abs(r - B / 2) < std::abs(best - B / 2))) best = r;
+            }
+            if (sorted && best > 0 && B >= split_min && split_min > 0) {
+                nparts = 2;
+                split_row = best;
             }
         }
-        if (launch_ar_control(logits, ldl, C, B, S, row_group, b.ngroups, ar, eos, c.rep_on, c.rep_period_max,
-                              c.rep_min_run_p1, c.rep_min_repeats, m->embed, m->pos_q, D, m->Dr, m->norm_c.g, m->norm_c.b, cin,
-                              st))
-            return 1;
-        steps_run = i + 1;
-        flops += step_flops;
-        if (i + 1 < S) {
-            p_kv.args.out = reinterpret_cast<__nv_bfloat16*>(ckv) + (size_t)(i + 1) * 2 * D;  // position i+1 of every row
-            if (gemm_plan_launch(&p_kv, st)) return 1;
+        auto b16 = [](void* p, size_t elems) { return static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p) + elems); };
+        Part parts[2];
+        for (int k = 0; k < nparts; ++k) {
+            Part& p = parts[k];
+            p.r0 = k == 0 ? 0 : split_row;
+            p.rows = k == 0 ? split_row : B - split_row;
+            if (nparts == 1) p.rows = B;
+            p.g0 = nparts == 1 ? 0 : rg[p.r0];
+            p.ng = nparts == 1 ? b.ngroups : rg[p.r0 + p.rows - 1] - p.g0 + 1;
+            p.a = ar;
+            p.a.tgt = ar.tgt + (size_t)p.r0 * S;
+            p.a.raw = ar.raw + (size_t)p.r0 * S;
+            p.a.rep_cut = ar.rep_cut + p.r0;
+            p.a.rep_done = ar.rep_done + p.r0;
+            p.a.has_eos = ar.has_eos + p.r0;
+            p.a.n_active = ar.n_active + 4 * k;
+            p.a.step = ar.step + 4 * k;
+            p.a.ticket = ar.ticket + 4 * k;
+            p.st = k == 0 ? st : st2;
+            p.flag = host_flag + 2 * k;
+            p.done = false;
+            const size_t r0 = (size_t)p.r0;
+            auto mk = [&](GemmPlan* pl, const void* A, long long lda, const LinearW& w, void* out, long long ldc,
+                          int out_f32, int act, const void* resid, int resid_f32, long long ldr) {
+                Epilogue ep;
+                ep.bias = w.b;
+                ep.resid = resid;
+                ep.resid_f32 = resid_f32;
+                ep.ldr = ldr;
+                ep.out = out;
+                ep.out_f32 = out_f32;
+                ep.ldc = ldc;
+                ep.act = act;
+                return gemm_plan_create(pl, A, lda, p.rows, w.K, w.w, w.N, ep);
+            };
+            float* x1p = x1 + r0 * D;
+            if (mk(&p.p_so, b16(sa, r0 * D), D, m->self_out, x1p, D, 1, ACT_NONE, nullptr, 0, 0)) return 1;
+            if (mk(&p.p_cq, b16(hb, r0 * D), D, m->cross_q, b16(qc, r0 * D), D, 0, ACT_NONE, nullptr, 0, 0)) return 1;
+            if (mk(&p.p_co, b16(oc, r0 * D), D, m->cross_out, x1p, D, 1, ACT_NONE, x1p, 1, D)) return 1;
+            if (mk(&p.p_l1, b16(hb, r0 * D), D, m->lin1, b16(mlpb, r0 * m->lin1.N), m->lin1.N, 0, ACT_GELU, nullptr, 0, 0))
+                return 1;
+            if (mk(&p.p_l2, b16(mlpb, r0 * m->lin1.N), m->lin1.N, m->lin2, x1p, D, 1, ACT_NONE, x1p, 1, D)) return 1;
+            if (mk(&p.p_hd, b16(hb, r0 * D), D, m->head, logits + r0 * ldl, ldl, 1, ACT_NONE, nullptr, 0, 0)) return 1;
+            if (mk(&p.p_kv, b16(cin, r0 * D), D, m->self_kv, b16(ckv, r0 * S * 2 * D), (long long)S * 2 * D, 0, ACT_NONE,
+                   nullptr, 0, 0))
+                return 1;
+            p.step_flops = p.p_so.flops + p.p_cq.flops + p.p_co.flops + p.p_l1.flops + p.p_l2.flops + p.p_hd.flops +
+                           p.p_kv.flops;
         }
-        // early stop: peek at the device-side counter every 4 steps (no sync on the other steps)
-        if ((i & 3) == 3 || i + 1 == S) {
-            CK(cudaMemcpyAsync(host_flag, ar.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost, st));
-            CK(cudaStreamSynchronize(st));
-            if (host_flag[0] == 0) break;
+        if (nparts > 1) {  // fork: the second stream starts after everything issued so far
+            CK(cudaEventRecord(ev_fork, st));
+            CK(cudaStreamWaitEvent(st2, ev_fork, 0));
         }
-    }
+        auto launch_step = [&](Part& p, int i) -> int {
+            const size_t r0 = (size_t)p.r0;
+            cudaStream_t ps = p.st;
+            float* x1p = x1 + r0 * D;
+            void* hbp = b16(hb, r0 * D);
+            float* lg = logits + r0 * ldl;
+            if (launch_dec_self_attn(m->q_self, b16(ckv, r0 * S * 2 * D), p.rows, S, D, c.dec_heads, p.a.step,
+                                     b16(sa, r0 * D), ps))
+                return 1;
+            if (gemm_plan_launch(&p.p_so, ps)) return 1;
+            // x1 += pos_queries[i] (the query stream's residual input), then norm1
+            if (launch_layernorm(x1p, p.rows, D, m->Dr, m->norm1.g, m->norm1.b, 1e-5f, hbp, nullptr, m->pos_q, 1, p.a.step, 0,
+                                 1, ps))
+                return 1;
+            if (gemm_plan_launch(&p.p_cq, ps)) return 1;
+            if (launch_dec_cross_attn(b16(qc, r0 * D), memkv, descs_dev + p.r0, p.rows, D, c.dec_heads, b16(oc, r0 * D), ps))
+                return 1;
+            if (gemm_plan_launch(&p.p_co, ps)) return 1;
+            if (launch_layernorm(x1p, p.rows, D, m->Dr, m->norm2.g, m->norm2.b, 1e-5f, hbp, nullptr, nullptr, 1, nullptr, 0, 0,
+                                 ps))
+                return 1;
+            if (gemm_plan_launch(&p.p_l1, ps)) return 1;
+            if (gemm_plan_launch(&p.p_l2, ps)) return 1;
+            if (launch_layernorm(x1p, p.rows, D, m->Dr, m->dec_norm.g, m->dec_norm.b, 1e-5f, hbp, nullptr, nullptr, 1, nullptr,
+                                 0, 0, ps))
+                return 1;
+            if (gemm_plan_launch(&p.p_hd, ps)) return 1;
+            if (c.refine_iters == 0) {
+                if (launch_softmax_max(lg, ldl, C, p.rows, S, S, i, nullptr, eos, ids + r0 * S, probs + r0 * S, ps)) return 1;
+                if (logits_out)
+                    CK(cudaMemcpy2DAsync(logits_out + (r0 * S + (size_t)i) * C, (size_t)S * C * 4, lg, ldl * 4,
+                                         (size_t)C * 4, p.rows,
+                                         logits_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ps));
+            }
+            if (launch_ar_control(lg, ldl, C, p.rows, S, row_group + p.r0, p.g0, p.ng, p.a, eos, c.rep_on, c.rep_period_max,
+                                  c.rep_min_run_p1, c.rep_min_repeats, m->embed, m->pos_q, D, m->Dr, m->norm_c.g, m->norm_c.b,
+                                  b16(cin, r0 * D), ps))
+                return 1;
+            flops += p.step_flops;
+            if (i + 1 < S) {
+                // K/V of the token that just entered the context: position i+1 of every row of the part
+                p.p_kv.args.out = reinterpret_cast<__nv_bfloat16*>(ckv) + r0 * S * 2 * D + (size_t)(i + 1) * 2 * D;
+                if (gemm_plan_launch(&p.p_kv, ps)) return 1;
+            }
+            return 0;
+        };
+        for (int i = 0; i < S; ++i) {
+            bool any = false;
+            for (int k = 0; k < nparts; ++k)
+                if (!parts[k].done) {
+                    if (launch_step(parts[k], i)) return 1;
+                    any = true;
+                }
+            if (!any) break;
+            steps_run = i + 1;
+            // early stop: peek at the device-side counters every 4 steps (no sync on the other steps)
+            if ((i & 3) == 3 || i + 1 == S) {
+                for (int k = 0; k < nparts; ++k)
+                    if (!parts[k].done)
+                        CK(cudaMemcpyAsync(parts[k].flag, parts[k].a.n_active, 2 * sizeof(int), cudaMemcpyDeviceToHost,
+                                           parts[k].st));
+                bool all = true;
+                for (int k = 0; k < nparts; ++k)
+                    if (!parts[k].done) {
+                        CK(cudaStreamSynchronize(parts[k].st));
+                        if (parts[k].flag[0] == 0) parts[k].done = true;
+                        else all = false;
+                    }
+                if (all) break;
+            }
+        }
+        if (nparts > 1) {  // join
+            CK(cudaEventRecord(ev_join, st2));
+            CK(cudaStreamWaitEvent(st, ev_join, 0));
+        }
     } else {
         // decode_ar == 0 (parseq.py:252-262): no AR loop; the first decoder pass below sees only <bos> as context
         if (launch_fill_i32(ar.group_len, S, b.ngroups, st)) return 1;

@@ -90,7 +90,9 @@ struct ParseqEngine {
     ArState ar{};
     int* ar_block = nullptr;  // backing store of the ArState arrays
     size_t ar_block_ints = 0;
-    int* host_flag = nullptr; // pinned: [n_active, step]
+    int* host_flag = nullptr; // pinned: [n_active, step] per AR part
+    cudaStream_t st2 = nullptr;  // second stream of the two-part AR loop
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     double flops = 0;         // algorithmic FLOPs of the last forward (GEMMs + attention)
     int last_steps = 0;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};  // start, encoder, AR, refine, end

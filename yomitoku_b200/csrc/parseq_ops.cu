@@ -658,8 +658,8 @@ __device__ int detect_repeat(const int* seq, int n, int period_max, int min_run_
 }
 
 __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict__ logits, long long ldl, int C, int S,
-                                                         const int* __restrict__ row_group, int ngroups, ArState a,
-                                                         int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1,
+                                                         const int* __restrict__ row_group, int g0, int ngroups,
+                                                         ArState a, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1,
                                                          int rep_min_repeats, const float* __restrict__ embed,
                                                          const float* __restrict__ pos_q, int D, int d_real,
                                                          const float* __restrict__ g_c, const float* __restrict__ b_c,
@@ -792,7 +792,7 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
     __shared__ int active;
     if (threadIdx.x == 0) active = 0;
     __syncthreads();
-    for (int g = threadIdx.x; g < ngroups; g += blockDim.x) {
+    for (int g = g0 + threadIdx.x; g < g0 + ngroups; g += blockDim.x) {  // the groups of this launch's rows
         if (a.group_len[g] == 0) {
             const int open = atomicExch(&a.open_rows[g], 0);
             if (j >= S) a.group_len[g] = S;          // ran all the steps
@@ -810,15 +810,15 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
     }
 }
 
-int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int ngroups,
-                      ArState a, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
+int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int g0,
+                      int ngroups, ArState a, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
                       const float* embed, const float* pos_q, int D, int d_real, const float* g_c, const float* b_c,
                       void* cin, cudaStream_t st) {
     if (D > 1024) {
         set_error("ar_control: D=%d too large", D);
         return 1;
     }
-    ar_control_kernel<<<B, 256, 0, st>>>(logits, ldl, C, S, row_group, ngroups, a, eos_id, rep_on, rep_period_max,
+    ar_control_kernel<<<B, 256, 0, st>>>(logits, ldl, C, S, row_group, g0, ngroups, a, eos_id, rep_on, rep_period_max,
                                          rep_min_run_p1, rep_min_repeats, embed, pos_q, D, d_real, g_c, b_c,
                                          reinterpret_cast<__nv_bfloat16*>(cin));
     count_launch(1);

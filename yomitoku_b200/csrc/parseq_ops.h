@@ -68,8 +68,8 @@ struct ArState {
 };
 // Arg-max over the head logits + the reference's per-step control logic (parseq.py:220-250) + content embedding of
 // the emitted token (text_embed * sqrt(D) + pos_queries[j-1]) normalised by LN_c -> cin bf16 [B, D].
-int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int ngroups,
-                      ArState st_, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
+int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int g0,
+                      int ngroups, ArState st_, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
                       const float* embed, const float* pos_q, int D, int d_real, const float* g_c, const float* b_c,
                       void* cin, cudaStream_t st);
 // Content embeddings for the refinement pass: [B*S, D] bf16 = LN_c(content(row,pos)) from the raw tokens; also
