@@ -52,6 +52,31 @@ def test_batched_ocr_equals_per_page_calls():
         assert np.allclose([w.rec_score for w in res[i].words], single.scores, atol=1e-6)
 
 
+def test_stream_equals_batched_calls():
+    """BatchedOCR.stream (detector / recognizer / assembly threads, two CUDA streams, staging ring reuse over more
+    batches than ring slots) yields, in order, exactly what per-batch calls return."""
+    o = _ocr()
+    batches, overrides = [], []
+    for k in range(5):
+        pages, probs = [], []
+        for i in range(2):
+            p, q = synthetic_page(40 + 2 * k + i)
+            pages.append(p)
+            probs.append(synthetic_prob_map(q, (1184, 1600), (1200, 1600)))
+        batches.append(pages)
+        overrides.append(probs)
+    b = BatchedOCR(o.detector, o.recognizer, workers=3, det_batch=1)
+    try:
+        ref = [b(pg, prob_override=po) for pg, po in zip(batches, overrides)]
+        got = list(b.stream(batches, lookahead=2, prob_override=overrides))
+    finally:
+        b.close()
+    assert len(got) == len(ref) == 5
+    for g, r in zip(got, ref):
+        assert [[w.content for w in page.words] for page in g] == [[w.content for w in page.words] for page in r]
+        assert [[w.points for w in page.words] for page in g] == [[w.points for w in page.words] for page in r]
+
+
 def test_document_analyzer_shell():
     da = DocumentAnalyzer(configs={"ocr": {"text_detector": {"from_pretrained": False},
                                            "text_recognizer": {"from_pretrained": False,

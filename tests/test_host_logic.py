@@ -175,3 +175,69 @@ def test_recognizer_cpu_plumbing_config1():
     assert dataset[0].shape == (3, 32, 320) and float(dataset[0].max()) == 1.0
     padded, group = rec._collate_widths(dataset.data, plan)
     assert padded == [320] * 16 and group == [0] * 16
+
+
+def test_batched_pipeline_with_stub_models():
+    """CPU: the whole host side of BatchedOCR (shared staging ring, worker pool, crop arena, descriptor building,
+    three-stage stream, result assembly) with the two device calls replaced by stand-ins that compute from the bytes
+    they are handed.  Per page the recognizer stand-in must see exactly the crops the one-page ParseqDataset cuts."""
+    import ctypes
+
+    from yomitoku_b200 import TextDetector, TextRecognizer
+    from yomitoku_b200.data import ParseqDataset
+    from yomitoku_b200.pipeline import BatchedOCR
+    from yomitoku_b200.postprocessor import DBnetPostProcessor
+    from yomitoku_b200.synth import synthetic_page, synthetic_prob_map
+
+    det = TextDetector(from_pretrained=False, device="cpu")
+    rec = TextRecognizer(model_name="parseq-tiny-dynw-v4", from_pretrained=False, device="cpu", dynamic_width=True,
+                         batch_bucketing=True)
+    Hn, Wn = 1184, 1600
+    batches, maps = [], []
+    for k in range(4):        # more batches than ring slots
+        pages, pm = [], []
+        for i in range(2):
+            p, q = synthetic_page(70 + 2 * k + i)
+            pages.append(p)
+            pm.append(synthetic_prob_map(q, (Hn, Wn), (1200, 1600)))
+        batches.append(pages)
+        maps.append(pm)
+    det.model.input_size = lambda h, w: (Hn, Wn)
+    det.model.detect_pages_u8 = lambda pages, out=None, stream=None: out      # maps come from prob_override
+    S = rec.model.max_label_length + 1
+    seen = []
+
+    def fake_ptr(ptr, on_device, total, descs, n, n_groups, stream=None):
+        raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
+        ids = np.zeros((n, S), np.int32)
+        for r, d in enumerate(descs):
+            c = raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3]
+            ids[r, 0] = 1 + int(c.astype(np.int64).sum()) % 7000
+            ids[r, 1] = 1 + int(d["wp"]) % 7000
+            seen.append((int(d["w"]), int(d["wp"]), int(d["group"]), int(c.astype(np.int64).sum())))
+        return ids, np.full((n, S), 0.5, np.float32), np.full((n_groups,), S, np.int32)
+
+    rec.model.run_packed_ptr = fake_ptr
+    ocr = BatchedOCR(det, rec, workers=2, det_batch=1)
+    try:
+        got = list(ocr.stream(batches, lookahead=2, prob_override=maps))
+        again = [ocr(pg, prob_override=pm) for pg, pm in zip(batches, maps)]
+    finally:
+        ocr.close()
+    post = DBnetPostProcessor(**dict(det._cfg.post_process))
+    assert len(got) == 4
+    for k in range(4):
+        for i in range(2):
+            quads, scores = post({"binary": maps[k][i][None, None]}, (1200, 1600))
+            ds = ParseqDataset(rec._cfg, batches[k][i], quads, num_workers=1, dynamic_width=True)
+            words = got[k][i].words
+            assert [w.points for w in words] == quads and len(words) == len(ds)
+            # first decoded char encodes the crop's pixel checksum: every word got ITS crop, in detection order
+            expect = [rec.tokenizer._itos[1 + int(c.astype(np.int64).sum()) % 7000] for c in ds.data]
+            assert [w.content[0] for w in words] == [unicodedata_nfkc(e)[0] for e in expect]
+            assert [[w.content for w in pg.words] for pg in again[k]] == [[w.content for w in pg.words] for pg in got[k]]
+
+
+def unicodedata_nfkc(s):
+    import unicodedata
+    return unicodedata.normalize("NFKC", s)
