@@ -136,6 +136,32 @@ int ytk_parseq_last_steps(ytk_parseq* h);
 /* CUDA-event times (ms) of the last forward: encoder, AR decode, refinement, output copies */
 void ytk_parseq_last_phase_ms(ytk_parseq* h, float* ms4);
 
+/* ---- Device-side crop extraction: replaces the pixel work of ParseqDataset._preprocess_on (reference
+ * src/yomitoku/data/dataset.py:106-123): extract_roi_with_perspective (data/functions.py:301-333, cv2.warpPerspective),
+ * rotate_text_image (:336-350) and resize_with_padding / resize_with_dynamic_padding (:379-439, cv2.resize INTER_AREA +
+ * paste on a black canvas), bit-exact with OpenCV 4.13 for 8UC3.  The scalar decisions (bounding box, output size,
+ * rotation, content and canvas size, the inverse perspective matrix) stay on the host: one record per crop
+ * (yomitoku_b200/data.py: crop_geometry).  The canvases come out packed exactly as ytk_parseq_forward_crops takes them
+ * with crops_on_device = 1, so no crop pixel leaves the GPU. ---- */
+typedef struct {
+    double minv[9];    /* cv2.invert(cv2.getPerspectiveTransform(quad - (x0,y0), [[0,0],[w,0],[w,h],[0,h]])), row major */
+    long long roi_off; /* byte offset of this crop's rectified ROI in scratch_dev: w*h*3 bytes */
+    long long pix_off; /* byte offset of this crop's canvas in canvases_dev: canvas_h*canvas_w*3 bytes, RGB */
+    int page;          /* index into pages_dev */
+    int x0, y0, rw, rh; /* bounding-box slice of the (int64-truncated) quad inside the page */
+    int w, h;          /* rectified size: (int |p0p1|, int |p1p2|) */
+    int rot;           /* 1 = rotate 90 degrees counter-clockwise after the warp (h > 2w) */
+    int cw, ch;        /* content size after the down-scale-only fit (calc_resize_without_padding) */
+    int canvas_w, canvas_h;
+} ytk_crop_geom;
+
+/* pages_dev: [n_pages, H0, W0, 3] uint8 BGR in device memory (e.g. the buffer handed to ytk_dbnet_forward_u8 with
+ * pages_on_device = 1); geoms: host array; scratch_dev / canvases_dev: caller-owned device buffers.  Asynchronous on
+ * cuda_stream (the geoms array may be reused as soon as the call returns). */
+int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, const ytk_crop_geom* geoms, int n_crops,
+                         uint8_t* scratch_dev, long long scratch_bytes, uint8_t* canvases_dev, long long canvases_bytes,
+                         void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -17,6 +17,13 @@ from oracle import refcheck, weights  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+def crops_ref_page():
+    """Page of crops_ref.npz: 3x3-px blocks of seeded noise (pure numpy, so the test rebuilds it instead of storing
+    3.5 MB)."""
+    g = np.random.default_rng(1717)
+    return np.kron(g.integers(0, 256, size=(234, 567, 3), dtype=np.uint8), np.ones((3, 3, 1), np.uint8))[:700, :1700]
+
+
 def main():
     assert refcheck.available(), "needs /root/reference"
     torch.manual_seed(0)
@@ -70,6 +77,48 @@ def main():
         roi = fn.rotate_text_image(fn.extract_roi_with_perspective(page, q), thresh_aspect=2)
         crops["fixed%d" % i] = fn.resize_with_padding(roi, [32, 800])
         crops["dyn%d" % i] = fn.resize_with_dynamic_padding(roi, [32, 800])
+    # ---- more crops through the reference's own functions, for the device-side crop extraction (csrc/crop_math.h):
+    # rotated rectangles, general quadrilaterals, tall (rotated) and very wide lines, integer shrink ratios
+    rng2 = np.random.default_rng(17)
+    page2 = crops_ref_page()
+    quads2 = []
+    for k in range(48):
+        kind = k % 6
+        if kind == 0:
+            w, h = int(rng2.integers(4, 380)), int(rng2.integers(4, 120))
+            x, y = int(rng2.integers(0, 1700 - w)), int(rng2.integers(0, 700 - h))
+            q = [[x, y], [x + w, y], [x + w, y + h], [x, y + h]]
+        elif kind in (1, 2):
+            cx, cy = rng2.uniform(160, 1540), rng2.uniform(160, 540)
+            w, h = rng2.uniform(6, 280), rng2.uniform(6, 90)
+            a = rng2.uniform(-0.5, 0.5) if kind == 1 else rng2.uniform(-3.1, 3.1)
+            c, sn = np.cos(a), np.sin(a)
+            pts = np.array([[-w / 2, -h / 2], [w / 2, -h / 2], [w / 2, h / 2], [-w / 2, h / 2]])
+            q = (pts @ np.array([[c, sn], [-sn, c]]) + [cx, cy] + rng2.uniform(-3, 3, (4, 2)) * (kind == 2)).tolist()
+        elif kind == 3:
+            w = int(rng2.integers(3, 50))
+            h = int(rng2.integers(2 * w + 1, 690))
+            x, y = int(rng2.integers(0, 1700 - w)), int(rng2.integers(0, 700 - h))
+            q = [[x, y], [x + w, y], [x + w, y + h], [x, y + h]]
+        elif kind == 4:
+            w, h = int(rng2.integers(801, 1700)), int(rng2.integers(8, 80))
+            x, y = int(rng2.integers(0, 1700 - w + 1)), int(rng2.integers(0, 700 - h))
+            q = [[x, y], [x + w, y], [x + w, y + h], [x, y + h]]
+        else:
+            r = int(rng2.integers(2, 5))
+            h, w = 32 * r, r * int(rng2.integers(2, 150))
+            x, y = int(rng2.integers(0, 1700 - w)), int(rng2.integers(0, 700 - h))
+            q = [[x, y], [x + w, y], [x + w, y + h], [x, y + h]]
+        quads2.append(q)
+    crops2 = {}
+    for i, q in enumerate(quads2):
+        assert fn.validate_quads(page2, q) is not None
+        roi = fn.rotate_text_image(fn.extract_roi_with_perspective(page2, q), thresh_aspect=2)
+        dyn = fn.resize_with_dynamic_padding(roi, [32, 800])
+        crops2["dyn%d" % i] = dyn
+        if i % 8 == 0:
+            crops2["fixed%d" % i] = fn.resize_with_padding(roi, [32, 800])
+    np.savez_compressed(os.path.join(OUT, "crops_ref.npz"), quads=np.array(quads2, dtype=np.float64), **crops2)
     std = fn.standardization_image(page.astype(np.float32))
     np.savez_compressed(os.path.join(OUT, "host_ref.npz"), sizes=np.array(sizes), resized=np.array(res), page=page,
                         quads=np.array(quads), std=std, **crops)

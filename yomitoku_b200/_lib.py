@@ -93,6 +93,12 @@ def _declare_parseq(lib):
     lib.ytk_parseq_last_phase_ms.argtypes = [c_void_p, c_void_p]
 
 
+def _declare_crops(lib):
+    lib.ytk_extract_crops_u8.restype = c_int
+    lib.ytk_extract_crops_u8.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll,
+                                         c_void_p]
+
+
 def tensor_table(state_dict):
     """state_dict (name -> torch tensor) -> (ctypes array of YtkTensor, keep-alive list). Tensors are converted to
     contiguous host fp32; integer buffers (num_batches_tracked) are skipped."""
@@ -125,6 +131,7 @@ def lib():
     _declare(l)
     _declare_dbnet(l)
     _declare_parseq(l)
+    _declare_crops(l)
     _lib = l
     return l
 

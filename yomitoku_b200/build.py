@@ -22,6 +22,11 @@ NVCC_FLAGS = [
 ]
 
 
+# OpenCV's float / double expressions are not contracted into FMAs: the bit-exact restatement in crop_math.h needs the
+# same (csrc/crop_ops.cu header)
+EXTRA_FLAGS = {"crop_ops.cu": ["--fmad=false"]}
+
+
 def _sources():
     return sorted(f for f in os.listdir(CSRC) if f.endswith(".cu"))
 
@@ -35,12 +40,13 @@ def _stamp():
             h.update(open(p, "rb").read())
     h.update(open(os.path.join(HERE, "..", "include", "yomitoku_b200.h"), "rb").read())
     h.update(" ".join(NVCC_FLAGS).encode())
+    h.update(repr(sorted(EXTRA_FLAGS.items())).encode())
     return h.hexdigest()
 
 
 def _compile(src):
     obj = os.path.join(BUILD, src[:-3] + ".o")
-    cmd = ["nvcc"] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    cmd = ["nvcc"] + NVCC_FLAGS + EXTRA_FLAGS.get(src, []) + ["-c", os.path.join(CSRC, src), "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))

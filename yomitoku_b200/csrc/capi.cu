@@ -6,6 +6,7 @@
 #include <mutex>
 #include <tuple>
 
+#include "crop_ops.h"
 #include "dbnet_engine.h"
 #include "dbnet_ops.h"
 #include "gemm_tc.h"
@@ -235,6 +236,55 @@ int ytk_dbnet_debug_tensor(ytk_dbnet* h, int n_pages, int Hn, int Wn, const char
         cudaError_t err = cudaMemcpy(host_out, tmp, n * 4, cudaMemcpyDeviceToHost);
         cudaFree(tmp);
         if (err != cudaSuccess) return YTK_ERR;
+    }
+    return YTK_OK;
+}
+
+static_assert(sizeof(ytk_crop_geom) == sizeof(ytk::CropGeom), "ytk_crop_geom and ytk::CropGeom must have one layout");
+
+int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, const ytk_crop_geom* geoms, int n_crops,
+                         uint8_t* scratch_dev, long long scratch_bytes, uint8_t* canvases_dev, long long canvases_bytes,
+                         void* cuda_stream) {
+    if (n_crops == 0) return YTK_OK;
+    if (!pages_dev || !geoms || !scratch_dev || !canvases_dev || n_pages <= 0 || H0 <= 0 || W0 <= 0 || n_crops < 0) {
+        ytk::set_error("ytk_extract_crops_u8: null or empty argument");
+        return YTK_ERR;
+    }
+    for (int i = 0; i < n_crops; ++i) {
+        const ytk_crop_geom& g = geoms[i];
+        const long long sw = g.rot ? g.h : g.w, sh = g.rot ? g.w : g.h;
+        const bool ok = g.page >= 0 && g.page < n_pages && g.x0 >= 0 && g.y0 >= 0 && g.rw >= 1 && g.rh >= 1 &&
+                        (long long)g.x0 + g.rw <= W0 && (long long)g.y0 + g.rh <= H0 && g.w >= 1 && g.h >= 1 &&
+                        (g.rot == 0 || g.rot == 1) && g.cw >= 1 && g.ch >= 1 && g.cw <= sw && g.ch <= sh &&
+                        g.cw <= g.canvas_w && g.ch <= g.canvas_h && g.roi_off >= 0 &&
+                        g.roi_off + (long long)g.w * g.h * 3 <= scratch_bytes && g.pix_off >= 0 &&
+                        g.pix_off + (long long)g.canvas_w * g.canvas_h * 3 <= canvases_bytes;
+        if (!ok) {
+            ytk::set_error("ytk_extract_crops_u8: inconsistent crop record %d (page %d, roi %d,%d %dx%d, out %dx%d rot %d, "
+                           "content %dx%d, canvas %dx%d)", i, g.page, g.x0, g.y0, g.rw, g.rh, g.w, g.h, g.rot, g.cw,
+                           g.ch, g.canvas_w, g.canvas_h);
+            return YTK_ERR;
+        }
+    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, pages_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        ytk::set_error("ytk_extract_crops_u8: pages_dev is not a device pointer");
+        return YTK_ERR;
+    }
+    cudaSetDevice(attr.device);  // host threads start on device 0: the device that owns the pages is the one that counts
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ytk::CropGeom* dev = nullptr;
+    const size_t bytes = (size_t)n_crops * sizeof(ytk::CropGeom);
+    cudaError_t err = cudaMallocAsync(reinterpret_cast<void**>(&dev), bytes, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(dev, geoms, bytes, cudaMemcpyHostToDevice, st);
+    int rc = 0;
+    if (err == cudaSuccess)
+        rc = ytk::launch_extract_crops(pages_dev, H0, W0, dev, n_crops, scratch_dev, canvases_dev, st);
+    if (dev) cudaFreeAsync(dev, st);
+    if (err != cudaSuccess || rc) {
+        ytk::set_error("ytk_extract_crops_u8: %s", err != cudaSuccess ? cudaGetErrorString(err) : "kernel launch failed");
+        return YTK_ERR;
     }
     return YTK_OK;
 }

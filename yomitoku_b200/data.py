@@ -123,6 +123,68 @@ def crop_to_tensor(crop_u8):
     return t.sub_(0.5).div_(0.5)
 
 
+# ------------------------------------------------------------------------------------------ device-side crop extraction
+# Layout of ytk_crop_geom (include/yomitoku_b200.h) / ytk::CropGeom (csrc/crop_math.h).
+CROP_GEOM_DTYPE = np.dtype([
+    ("minv", "<f8", (9,)), ("roi_off", "<i8"), ("pix_off", "<i8"), ("page", "<i4"), ("x0", "<i4"), ("y0", "<i4"),
+    ("rw", "<i4"), ("rh", "<i4"), ("w", "<i4"), ("h", "<i4"), ("rot", "<i4"), ("cw", "<i4"), ("ch", "<i4"),
+    ("canvas_w", "<i4"), ("canvas_h", "<i4")], align=True)
+
+
+def crop_geometry(img_shape, quads, target_size, dynamic_width, page=0, align=8, margin=64):
+    """Everything about the crops of one page that follows from the quads alone - the host half of the device-side
+    crop extraction (csrc/crop_ops.cu does the pixel work).  Per valid quad, exactly the scalar decisions of
+    `ParseqDataset._preprocess_on` (reference data/dataset.py:106-123): bounding-box slice and output size of
+    extract_roi_with_perspective (functions.py:301-333; the 3x3 matrix comes from the same cv2.getPerspectiveTransform
+    call, inverted like cv2.warpPerspective does internally), the rotation test of rotate_text_image (:336-350), the
+    down-scale-only size of calc_resize_without_padding (:353-376) and the canvas width of resize_with_padding /
+    resize_with_dynamic_padding (:379-439).
+
+    Returns (geoms, keep): a CROP_GEOM_DTYPE array for the valid quads (roi_off / pix_off are filled by the caller) and
+    the indices of those quads; invalid quads are dropped like validate_quads does (functions.py:267-298)."""
+    H, W = int(img_shape[0]), int(img_shape[1])
+    th, tw = int(target_size[0]), int(target_size[1])
+    out = np.zeros(len(quads), dtype=CROP_GEOM_DTYPE)
+    keep = []
+    k = 0
+    for qi, quad in enumerate(quads):
+        if len(quad) != 4 or any(len(p) != 2 for p in quad):
+            continue
+        q = np.array(quad, dtype=np.int64)
+        x0, y0, x1, y1 = int(q[:, 0].min()), int(q[:, 1].min()), int(q[:, 0].max()), int(q[:, 1].max())
+        if x0 < 0 or x1 > W or y0 < 0 or y1 > H:
+            continue
+        ql = q - np.array([x0, y0], dtype=np.int64)
+        w = int(np.linalg.norm(ql[0] - ql[1]))
+        h = int(np.linalg.norm(ql[1] - ql[2]))
+        if w <= 0 or h <= 0 or x1 <= x0 or y1 <= y0:
+            # the reference fails inside cv2.warpPerspective here (empty source or destination)
+            raise cv2.error("crop_geometry: degenerate quad %s (roi %dx%d, output %dx%d)" % (quad, x1 - x0, y1 - y0, w, h))
+        m = cv2.getPerspectiveTransform(np.float32(ql), np.float32([[0, 0], [w, 0], [w, h], [0, h]]))
+        g = out[k]
+        g["minv"] = cv2.invert(m)[1].reshape(-1)
+        g["page"], g["x0"], g["y0"], g["rw"], g["rh"], g["w"], g["h"] = page, x0, y0, x1 - x0, y1 - y0, w, h
+        rot = h > 2 * w
+        sh, sw = (w, h) if rot else (h, w)
+        s = min(tw / sw if sw > tw else 1.0, th / sh if sh > th else 1.0)
+        ch, cw = max(1, int(sh * s)), max(1, int(sw * s))
+        g["rot"], g["cw"], g["ch"] = int(rot), cw, ch
+        g["canvas_w"] = min(tw, ((cw + margin + align - 1) // align) * align) if dynamic_width else tw
+        g["canvas_h"] = th
+        keep.append(qi)
+        k += 1
+    return out[:k], keep
+
+
+def layout_crop_buffers(geoms):
+    """Fills roi_off / pix_off (crops packed back to back) and returns (scratch_bytes, canvas_bytes)."""
+    roi = geoms["w"].astype(np.int64) * geoms["h"] * 3
+    pix = geoms["canvas_w"].astype(np.int64) * geoms["canvas_h"] * 3
+    geoms["roi_off"] = np.cumsum(roi) - roi
+    geoms["pix_off"] = np.cumsum(pix) - pix
+    return int(roi.sum()), int(pix.sum())
+
+
 class ParseqDataset:
     """Crops of one page for the recognizer; reference data/dataset.py:44-129.
 

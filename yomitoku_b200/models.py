@@ -85,6 +85,35 @@ class _DeviceModel:
         return m
 
 
+def extract_crops_device(pages_dev, geoms, stream=None):
+    """Device-side crop extraction (C ABI ytk_extract_crops_u8, csrc/crop_ops.cu).
+
+    pages_dev: (n, H0, W0, 3) uint8 BGR cuda tensor; geoms: CROP_GEOM_DTYPE records (data.crop_geometry) - their
+    roi_off / pix_off are (re)assigned here, crops packed back to back in record order.  Returns (canvases, total
+    bytes): a flat uint8 cuda tensor holding every crop's (canvas_h, canvas_w, 3) RGB canvas at geoms["pix_off"], ready
+    for PARSeq.run_packed_ptr(..., on_device=1).  Asynchronous on `stream` (default: the current stream)."""
+    from .data import CROP_GEOM_DTYPE, layout_crop_buffers
+    if not (isinstance(pages_dev, torch.Tensor) and pages_dev.is_cuda and pages_dev.dtype == torch.uint8
+            and pages_dev.dim() == 4 and pages_dev.shape[3] == 3 and pages_dev.is_contiguous()):
+        raise ValueError("extract_crops_device: pages_dev must be a contiguous (n, H, W, 3) uint8 cuda tensor")
+    if not (isinstance(geoms, np.ndarray) and geoms.dtype == CROP_GEOM_DTYPE and geoms.flags.c_contiguous):
+        raise ValueError("extract_crops_device: geoms must be a contiguous CROP_GEOM_DTYPE array")
+    scratch_bytes, total = layout_crop_buffers(geoms)      # writes roi_off / pix_off into the caller's records
+    ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(pages_dev.device)
+    with ctx:
+        scratch = torch.empty(max(scratch_bytes, 1), dtype=torch.uint8, device=pages_dev.device)
+        canv = torch.empty(max(total, 1), dtype=torch.uint8, device=pages_dev.device)
+    n, H0, W0, _ = pages_dev.shape
+    _lib.check(_lib.lib().ytk_extract_crops_u8(pages_dev.data_ptr(), n, H0, W0, geoms.ctypes.data, len(geoms),
+                                               scratch.data_ptr(), scratch_bytes, canv.data_ptr(), total,
+                                               _stream_ptr(stream)))
+    if stream is not None:
+        # the scratch buffer is only read by the canvas kernel queued on `stream`: hand it back to the allocator in
+        # stream order
+        scratch.record_stream(stream)
+    return canv, total
+
+
 # ======================================================================================================== DBNet
 def _dbnet_random_state_dict(seed=0):
     """Random init with the reference's key set (DBNet(cfg) with from_pretrained=False, base.py:84-86)."""

@@ -15,7 +15,7 @@ from concurrent.futures import ProcessPoolExecutor
 
 import numpy as np
 
-from .data import ParseqDataset
+from .data import CROP_GEOM_DTYPE, ParseqDataset, crop_geometry, layout_crop_buffers
 from .ocr import ocr_aggregate
 from .postprocessor import DBnetPostProcessor
 from .schemas import OCRSchema, TextDetectorSchema, TextRecognizerSchema
@@ -123,6 +123,10 @@ def _host_stage(args):
     t0 = time.perf_counter()
     page, prob, quads_override = args[:3]
     arena = args[3] if len(args) > 3 else None
+    geom_only = len(args) > 4 and args[4] == "geom"
+    if geom_only:
+        # device-side crop extraction: only the page SHAPE is needed here; the pixels never reach this process
+        page = np.empty((page[1], page[2], 0), np.uint8)
     if isinstance(page, tuple):
         page = _attach(page)         # zero-copy views of the parent's shared staging buffers
     if isinstance(prob, tuple):
@@ -134,6 +138,11 @@ def _host_stage(args):
     else:
         quads, scores = quads_override, [1.0] * len(quads_override)
     t1 = time.perf_counter()
+    if geom_only:
+        if not len(quads):
+            return quads, scores, np.zeros(0, CROP_GEOM_DTYPE), [], 0
+        geoms, _ = crop_geometry(page.shape, quads, _W["cfg"].data.img_size, _W["dyn"])
+        return quads, scores, geoms, geoms["cw"].tolist(), len(geoms), (t0, t1, time.perf_counter())
     ds = ParseqDataset(_W["cfg"], page, quads if len(quads) else [], num_workers=1, dynamic_width=_W["dyn"],
                        source_downscale=_W["sd"]) if len(quads) else None
     if ds is None:
@@ -181,10 +190,30 @@ class _PageCrops:
         return self.arena_np[o:o + self.height * w * 3].reshape(self.height, w, 3)
 
 
+class _PageGeoms:
+    """Crops of one page that exist only as ytk_crop_geom records (device-side extraction): `widths` are the canvas
+    widths the crops will have, `base` the index of the page's first record in the step's record array."""
+
+    def __init__(self, geoms, base):
+        self.geoms = geoms
+        self.base = base
+        self.widths = geoms["canvas_w"].tolist()
+        self.height = int(geoms["canvas_h"][0]) if len(geoms) else 32
+
+    def __len__(self):
+        return len(self.widths)
+
+
 class BatchedOCR:
-    def __init__(self, detector, recognizer, workers=None, det_batch=8, max_tokens=1_000_000):
+    def __init__(self, detector, recognizer, workers=None, det_batch=8, max_tokens=1_000_000, device_crops=None):
         self.detector = detector
         self.recognizer = recognizer
+        # device-side crop extraction (csrc/crop_ops.cu): pages stay in HBM after detection, the host stage only
+        # produces quads + per-crop records, the canvases are cut on the GPU (bit-exact with the OpenCV path).  Not
+        # available with source_downscale (the pyramid levels are host images).
+        if device_crops is None:
+            device_crops = os.environ.get("YTK_DEVICE_CROPS", "0") == "1"
+        self.device_crops = bool(device_crops) and not recognizer.source_downscale
         self.det_batch = det_batch
         self.max_tokens = max_tokens
         self.workers = workers if workers is not None else max(1, min(32, (os.cpu_count() or 2) - 2))
@@ -355,6 +384,65 @@ class BatchedOCR:
             start = end
         return out
 
+    def _run_groups_dev(self, groups, geoms, pages_dev, stream=None):
+        """Groups whose crops exist only as records: groups = (widths, padded widths, record indices into `geoms`).
+        The canvases of a <= max_tokens chunk are cut on the device (ytk_extract_crops_u8) in group order and go to
+        PARSeq without leaving HBM.  With torch.distributed the canvases are brought to the host once and take the
+        arena path, so that groups can still be balanced across ranks."""
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        from .models import extract_crops_device
+        rec = self.recognizer
+        cfg = rec._cfg
+        ph, pw = cfg.encoder.patch_size
+        gh = cfg.data.img_size[0] // ph
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            idx = np.concatenate([g[2] for g in groups]) if groups else np.zeros(0, np.int64)
+            sel = geoms[idx].copy()
+            canv, _ = extract_crops_device(pages_dev, sel, stream)
+            host = _HostCanvases(canv, stream)
+            offs, k = sel["pix_off"], 0
+            agroups = []
+            for g in groups:
+                agroups.append((g[0], g[1], offs[k:k + len(g[0])]))
+                k += len(g[0])
+            return self._run_groups(agroups, stream, host, int(sel["canvas_h"][0]) if len(sel) else 32)
+        out = [None] * len(groups)
+        gtok = [gh * (int(np.sum(g[1])) // pw) for g in groups]
+        dt = np.dtype(_lib.YtkCrop)
+        start = 0
+        while start < len(groups):
+            end, tok = start, 0
+            while end < len(groups) and not (end > start and tok + gtok[end] > self.max_tokens):
+                tok += gtok[end]
+                end += 1
+            chunk = groups[start:end]
+            sel = geoms[np.concatenate([g[2] for g in chunk])].copy()
+            with _span("recognize.crops_device"):
+                canv, total = extract_crops_device(pages_dev, sel, stream)
+            wp = np.concatenate([np.asarray(g[1], np.int64) for g in chunk])
+            n = sel.shape[0]
+            ntok = gh * (wp // pw)
+            descs = np.zeros(n, dtype=dt)
+            descs["pix_off"] = sel["pix_off"]
+            descs["w"] = sel["canvas_w"]
+            descs["wp"] = wp
+            descs["tok_off"] = np.cumsum(ntok) - ntok
+            descs["ntok"] = ntok
+            descs["group"] = np.repeat(np.arange(end - start), [len(g[0]) for g in chunk])
+            with _span("recognize.device"):
+                ids, probs, glen = rec.model.run_packed_ptr(canv.data_ptr(), 1, total, descs, n, end - start,
+                                                            stream=stream)
+            del canv
+            off = 0
+            for k in range(start, end):
+                m = len(groups[k][0])
+                out[k] = (ids[off:off + m], probs[off:off + m], int(glen[k - start]))
+                off += m
+            start = end
+        return out
+
     def _run_groups(self, groups, stream=None, arena=None, height=32):
         """Recognise groups, spreading them over all ranks when torch.distributed is initialised (crop scatter /
         result gather over NCCL, yomitoku_b200/parallel.py); results come back in `groups` order.  Groups are
@@ -398,32 +486,39 @@ class BatchedOCR:
         back = par.return_results(work, packed, len(groups), S + 1)
         return [(i[:, :S], p[:, :S], int(i[0, S]) if len(i) else 0) for i, p in back]
 
-    def recognize_pooled(self, per_page, stream=None, arena=None):
+    def recognize_pooled(self, per_page, stream=None, arena=None, pages_dev=None):
         """Device stage 2: per_page = list of (canvases, content_widths, n_quads); canvases is a list of arrays or a
         `_PageCrops` view of `arena`.  Returns per page (ids, probs, order) with rows in the page's *plan* order,
         exactly like TextRecognizer._run_plan."""
         rec = self.recognizer
         cfg = rec._cfg
         in_arena = arena is not None and all(isinstance(p[0], _PageCrops) for p in per_page)
+        in_dev = pages_dev is not None and all(isinstance(p[0], _PageGeoms) for p in per_page)
         groups, owner, orders = [], [], []
         for pi, (canv, cw, n_quads) in enumerate(per_page):
             order = None
             if rec.batch_bucketing and len(canv) == n_quads and len(canv) > 1:
                 order = np.argsort(cw).tolist()
-            widths = canv.widths if isinstance(canv, _PageCrops) else [c.shape[1] for c in canv]
+            widths = canv.widths if isinstance(canv, (_PageCrops, _PageGeoms)) else [c.shape[1] for c in canv]
             plan = plan_mini_batches(widths, order, rec.dynamic_width, cfg.data.batch_size,
                                      getattr(cfg.data, "width_budget", None),
                                      getattr(cfg.data, "max_batch_size", None))
             padded, _ = rec._collate_widths(widths, plan)
             for b in plan:
-                if in_arena:   # (widths, padded widths, arena offsets): no pixel is touched on the host
+                if in_dev:     # (widths, padded widths, record indices): the pixels are cut on the device
+                    groups.append(([widths[i] for i in b], [padded[i] for i in b], canv.base + np.asarray(b, np.int64)))
+                elif in_arena:   # (widths, padded widths, arena offsets): no pixel is touched on the host
                     groups.append(([widths[i] for i in b], [padded[i] for i in b], canv.offs[b]))
                 else:
                     groups.append(([canv[i] for i in b], [padded[i] for i in b]))
                 owner.append(pi)
             orders.append(order)
-        res = self._run_groups(groups, stream, arena if in_arena else None,
-                               per_page[0][0].height if in_arena and per_page else 32)
+        if in_dev:
+            geoms = np.concatenate([p[0].geoms for p in per_page]) if per_page else np.zeros(0, CROP_GEOM_DTYPE)
+            res = self._run_groups_dev(groups, geoms, pages_dev, stream)
+        else:
+            res = self._run_groups(groups, stream, arena if in_arena else None,
+                                   per_page[0][0].height if in_arena and per_page else 32)
         S = cfg.max_label_length + 1
         out = []
         for pi in range(len(per_page)):
@@ -459,10 +554,17 @@ class BatchedOCR:
         prob = out.numpy()
         sh = self._last_shared if pool is not None else None
         arena, cap = None, self.crop_cap
+        h0, w0 = pages[0].shape[:2]
+        pages_dev = None
+        if self.device_crops:
+            # the pages stay in HBM for the crop kernels of this batch; the tensor belongs to the handle (no ring slot
+            # to guard) and the detector reads the same copy
+            with _span("submit.pages_h2d"):
+                pages_dev = self._upload_pages(stage, stream)
         if sh is not None:
             pb, ob = sh
-            arena = self._shared("crops", n * cap)
-            h0, w0 = pages[0].shape[:2]
+            if pages_dev is None:
+                arena = self._shared("crops", n * cap)
         if pool is None:
             r = self.recognizer
             _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
@@ -471,11 +573,18 @@ class BatchedOCR:
         for s in range(0, n, self.det_batch):
             e = min(n, s + self.det_batch)
             with _span("submit.detect"):
-                self.detector.model.detect_pages_u8(stage[s:e], out=out[s:e], stream=stream)
+                self.detector.model.detect_pages_u8((stage if pages_dev is None else pages_dev)[s:e], out=out[s:e],
+                                                    stream=stream)
             for i in range(s, e):
                 qo = None if quads_override is None else quads_override[i]
                 if sh is None:
                     job = (pages[i], prob[i] if prob_override is None else prob_override[i], qo)
+                    if pages_dev is not None:
+                        job = (("shape", h0, w0), job[1], qo, None, "geom")
+                elif pages_dev is not None:
+                    if prob_override is not None:
+                        np.copyto(prob[i], prob_override[i])
+                    job = (("shape", h0, w0), ob.desc(i * prob[i].nbytes, prob[i].shape, np.float32), qo, None, "geom")
                 else:
                     if prob_override is not None:   # benchmarks with random detector weights: overwrite the D2H result
                         np.copyto(prob[i], prob_override[i])
@@ -485,9 +594,18 @@ class BatchedOCR:
                            arena.desc(i * cap, (cap,), np.uint8))
                 futs.append(_Done(_host_stage(job)) if pool is None else pool.submit(_host_stage, job))
         if pool is None:
-            return _Handle(futs, None, 0)
+            return _Handle(futs, None, 0, pages_dev)
         self._slot_busy[self._slot] = futs
-        return _Handle(futs, arena, cap)
+        return _Handle(futs, arena, cap, pages_dev)
+
+    @staticmethod
+    def _upload_pages(stage, stream=None):
+        """(n, H0, W0, 3) uint8 staging tensor -> the same pages in HBM (asynchronous on `stream`)."""
+        import torch
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                return stage.to("cuda", non_blocking=True)
+        return stage.to("cuda", non_blocking=True)
 
     def collect(self, handle, stream=None):
         """Waits for the host stage of a submitted batch, recognises all its crops in one packed device call and
@@ -498,7 +616,18 @@ class BatchedOCR:
         with _span("collect.wait_host"):
             host = [f.result() for f in handle.futures]
         arena = handle.arena
-        if arena is not None:
+        if handle.pages_dev is not None:
+            fixed, base = [], 0
+            for i, h in enumerate(host):
+                g = h[2]
+                g["page"] = i
+                if TRACE is not None and len(h) > 5:
+                    TRACE.append(("worker.post", "worker", h[5][0], h[5][1]))
+                    TRACE.append(("worker.geometry", "worker", h[5][1], h[5][2]))
+                fixed.append((h[0], h[1], _PageGeoms(g, base), h[3], h[4]))
+                base += len(g)
+            host = fixed
+        elif arena is not None:
             an = arena.np
             fixed = []
             for i, h in enumerate(host):
@@ -517,7 +646,7 @@ class BatchedOCR:
             host = fixed
         rec_in = [(h[2], h[3], len(h[0])) for h in host]
         with _span("collect.recognize"):
-            rec_out = self.recognize_pooled(rec_in, stream, arena=arena)
+            rec_out = self.recognize_pooled(rec_in, stream, arena=arena, pages_dev=handle.pages_dev)
         return host, rec_out
 
     def _assemble(self, host, rec_out):
@@ -621,8 +750,24 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
 class _Handle:
     """What `submit` returns: the host-stage futures of a batch + the crop arena its workers write into."""
 
-    def __init__(self, futures, arena, cap):
-        self.futures, self.arena, self.cap = futures, arena, cap
+    def __init__(self, futures, arena, cap, pages_dev=None):
+        self.futures, self.arena, self.cap, self.pages_dev = futures, arena, cap, pages_dev
+
+
+class _HostCanvases:
+    """Device-cut canvases brought to the host (page-locked) for the cross-rank exchange; quacks like the crop arena."""
+
+    def __init__(self, canv_dev, stream=None):
+        import torch
+        self.torch = torch.empty(canv_dev.shape, dtype=torch.uint8, pin_memory=True)
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                self.torch.copy_(canv_dev, non_blocking=True)
+            stream.synchronize()
+        else:
+            self.torch.copy_(canv_dev)
+            torch.cuda.current_stream().synchronize()
+        self.np = self.torch.numpy()
 
 
 class _Done:
