@@ -245,7 +245,28 @@ def main():
             _lib.check(L.ytk_dbnet_forward_u8(det.model._ensure(), pages_dev[s:e].data_ptr(), 1, e - s, 1200, 1600,
                                               prob_dev[s:e].data_ptr(), 1, None))
 
+    sel_geoms = None
+    if ocr.device_crops:
+        # device-side crop extraction: the canvases of every step are cut on the GPU from the resident pages (same flat
+        # order as the packed host canvases above), so `value` covers detector + crop kernels + recognizer
+        from yomitoku_b200.data import crop_geometry
+        from yomitoku_b200.models import extract_crops_device
+        flat_geoms = []
+        for pi, ((canv, cw, nq), q) in enumerate(zip(per_page, quads)):
+            g, keep = crop_geometry((1200, 1600), q, rec._cfg.data.img_size, True, page=pi)
+            order = np.argsort(cw).tolist()
+            plan = plan_mini_batches([c.shape[1] for c in canv], order, True, rec._cfg.data.batch_size, None, None)
+            flat_geoms.append(g[np.asarray([i for b in plan for i in b], np.int64)])
+        sel_geoms = np.concatenate(flat_geoms)
+        chk, chk_total = extract_crops_device(pages_dev, sel_geoms)
+        if chk_total != total or not torch.equal(chk[:total], buf_dev[:total]):
+            raise RuntimeError("device-cut canvases differ from the OpenCV canvases")
+        del chk
+
     def rec_step():
+        if sel_geoms is not None:
+            canv_dev, _ = extract_crops_device(pages_dev, sel_geoms)
+            return rec.model.run_packed(canv_dev, total, descs, n_crops, g0)
         return rec.model.run_packed(buf_dev, total, descs, n_crops, g0)
 
     def sync_all():
@@ -323,11 +344,12 @@ def main():
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        h2d = P * 1200 * 1600 * 3 + total
+        # device_crops: the crops never cross PCIe, only their 136-byte records do
+        h2d = P * 1200 * 1600 * 3 + (n_crops * 136 if ocr.device_crops else total)
         d2h = P * Hn * Wn * 4 + n_crops * 101 * 8
         e2e = {"value": world * P * args.steps / dt, "unit": "pages/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "words_per_page": n_words / (args.steps * P),
-               "host_workers": ocr.workers}
+               "host_workers": ocr.workers, "device_crops": bool(ocr.device_crops)}
     ocr.close()
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -350,6 +372,8 @@ def main():
                              (P * 1.2 + 4.0),
                        "ar_steps": int(L.ytk_parseq_last_steps(rec.model._ensure())),
                        "weights": "seeded random init (from_pretrained=False)",
+                       "crops": "cut on the GPU from the resident pages (ytk_extract_crops_u8, checked equal to the "
+                                "OpenCV canvases)" if sel_geoms is not None else "cut on the host (OpenCV)",
                        "recognizer_phase_ms": phase_value},
             "crops_per_s": world * n_crops * args.steps / (rec_ms / 1e3),
             "det_pages_per_s": world * P * args.steps / (det_ms / 1e3),

@@ -147,6 +147,84 @@ def _worker_pipeline(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_pipeline_dev(rank, world, port, q):
+    """BatchedOCR._run_groups_dev across 2 ranks: crops that exist only as records are cut "on the device" (stand-in:
+    the product's crop arithmetic compiled for the host), brought to the host once and balanced across ranks."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import ctypes
+
+        from oracle import build_crop_host
+        from yomitoku_b200 import data as D
+        from yomitoku_b200 import models as M
+        from yomitoku_b200 import pipeline as pl
+        from yomitoku_b200.config import TextRecognizerPARSeqLargeV41Config, to_config
+        from yomitoku_b200.synth import synthetic_page
+        cfg = to_config(TextRecognizerPARSeqLargeV41Config())
+        host = ctypes.CDLL(build_crop_host.build())
+
+        class Rec:
+            _cfg = cfg
+            model = _StubModel(cfg)
+
+        class FakeDev:
+            def __init__(self, arr):
+                self.arr = arr
+
+        def fake_extract(pages_dev, geoms, stream=None):
+            sb, cb = D.layout_crop_buffers(geoms)
+            scratch, canv = np.zeros(max(sb, 1), np.uint8), np.zeros(max(cb, 1), np.uint8)
+            vp = ctypes.c_void_p
+            host.crop_host_extract(pages_dev.ctypes.data_as(vp), pages_dev.shape[1], pages_dev.shape[2],
+                                   geoms.ctypes.data_as(vp), len(geoms), scratch.ctypes.data_as(vp),
+                                   canv.ctypes.data_as(vp))
+            return FakeDev(canv), cb
+
+        class FakeHostCanvases:
+            def __init__(self, canv_dev, stream=None):
+                self.np = canv_dev.arr
+
+        M.extract_crops_device = fake_extract
+        pl._HostCanvases = FakeHostCanvases
+        ocr = pl.BatchedOCR(None, Rec(), workers=1, device_crops=True)
+        page, quads = synthetic_page(30 + rank)
+        quads = quads[:40] if rank == 0 else quads[:6]         # unbalanced: groups must move from rank 0 to rank 1
+        geoms, keep = D.crop_geometry(page.shape, quads, cfg.data.img_size, True, page=0)
+        ds = D.ParseqDataset(cfg, page, quads, num_workers=1, dynamic_width=True)
+        order = np.argsort(geoms["cw"]).tolist()
+        groups, expect = [], []
+        for s in range(0, len(order), 5):
+            b = order[s:s + 5]
+            widths = [int(geoms["canvas_w"][i]) for i in b]
+            groups.append((widths, [max(widths)] * len(b), np.asarray(b, np.int64)))
+            expect.append(_fake_recognise([ds.data[i] for i in b]))
+        res = ocr._run_groups_dev(groups, geoms, np.ascontiguousarray(page)[None], None)
+        for (ids, probs, glen), (eid, ep) in zip(res, expect):
+            assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101
+        q.put((rank, "ok", None))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipeline_groups_device_crops_world2():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pipeline_dev, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, status, _ in out:
+        assert status == "ok", status
+
+
 def test_pipeline_groups_arena_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

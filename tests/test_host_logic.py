@@ -241,3 +241,146 @@ def test_batched_pipeline_with_stub_models():
 def unicodedata_nfkc(s):
     import unicodedata
     return unicodedata.normalize("NFKC", s)
+
+
+def test_batched_pipeline_device_crops_with_stub_models(monkeypatch):
+    """CPU: the device_crops path of BatchedOCR (pages kept "on the device", workers return quads + crop records only,
+    canvases cut by ytk_extract_crops_u8 in group order) with the three device calls replaced by stand-ins; the crop
+    stand-in runs the product's own crop arithmetic compiled for the host (oracle/crop_host.cpp).  Every word must get
+    the canvas the one-page OpenCV path (ParseqDataset) cuts for it, and stream() must equal per-batch calls."""
+    import ctypes
+
+    from oracle import build_crop_host
+    from yomitoku_b200 import models as M
+    from yomitoku_b200.data import ParseqDataset, layout_crop_buffers
+    from yomitoku_b200.pipeline import BatchedOCR
+
+    host = ctypes.CDLL(build_crop_host.build())
+    det = TextDetector(from_pretrained=False, device="cpu")
+    rec = TextRecognizer(model_name="parseq-tiny-dynw-v4", from_pretrained=False, device="cpu", dynamic_width=True,
+                         batch_bucketing=True)
+    Hn, Wn = 1184, 1600
+    batches, maps = [], []
+    for k in range(3):
+        pages, pm = [], []
+        for i in range(2):
+            p, q = synthetic_page(90 + 2 * k + i)
+            pages.append(p)
+            pm.append(synthetic_prob_map(q, (Hn, Wn), (1200, 1600)))
+        batches.append(pages)
+        maps.append(pm)
+    det.model.input_size = lambda h, w: (Hn, Wn)
+    det.model.detect_pages_u8 = lambda pages, out=None, stream=None: out
+    S = rec.model.max_label_length + 1
+
+    class FakeDev:      # stands for the flat uint8 cuda tensor of canvases
+        def __init__(self, arr):
+            self.arr = arr
+
+        def data_ptr(self):
+            return self.arr.ctypes.data
+
+    def fake_extract(pages_dev, geoms, stream=None):
+        sb, cb = layout_crop_buffers(geoms)
+        scratch, canv = np.zeros(max(sb, 1), np.uint8), np.full(max(cb, 1), 99, np.uint8)
+        pg = np.ascontiguousarray(pages_dev.numpy())
+        vp = ctypes.c_void_p
+        for i in sorted(set(geoms["page"].tolist())):       # the host harness takes one page at a time
+            sel = np.ascontiguousarray(geoms[geoms["page"] == i])
+            sel["page"] = 0
+            host.crop_host_extract(pg[i].ctypes.data_as(vp), pg.shape[1], pg.shape[2], sel.ctypes.data_as(vp), len(sel),
+                                   scratch.ctypes.data_as(vp), canv.ctypes.data_as(vp))
+        return FakeDev(canv), cb
+
+    def fake_ptr(ptr, on_device, total, descs, n, n_groups, stream=None):
+        assert on_device == 1
+        raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
+        ids = np.zeros((n, S), np.int32)
+        for r, d in enumerate(descs):
+            c = raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3]
+            ids[r, 0] = 1 + int(c.astype(np.int64).sum()) % 7000
+        return ids, np.full((n, S), 0.5, np.float32), np.full((n_groups,), S, np.int32)
+
+    monkeypatch.setattr(M, "extract_crops_device", fake_extract)
+    rec.model.run_packed_ptr = fake_ptr
+    ocr = BatchedOCR(det, rec, workers=2, det_batch=1, device_crops=True)
+    ocr._upload_pages = lambda stage, stream=None: stage.clone()
+    try:
+        got = list(ocr.stream(batches, lookahead=2, prob_override=maps))
+        again = [ocr(pg, prob_override=pm) for pg, pm in zip(batches, maps)]
+    finally:
+        ocr.close()
+    post = DBnetPostProcessor(**dict(det._cfg.post_process))
+    for k in range(3):
+        for i in range(2):
+            quads, scores = post({"binary": maps[k][i][None, None]}, (1200, 1600))
+            ds = ParseqDataset(rec._cfg, batches[k][i], quads, num_workers=1, dynamic_width=True)
+            words = got[k][i].words
+            assert [w.points for w in words] == quads and len(words) == len(ds) > 100
+            expect = [rec.tokenizer._itos[1 + int(c.astype(np.int64).sum()) % 7000] for c in ds.data]
+            assert [w.content[0] for w in words] == [unicodedata_nfkc(e)[0] for e in expect]
+        assert [[w.content for w in pg.words] for pg in again[k]] == [[w.content for w in pg.words] for pg in got[k]]
+
+
+def test_recognizer_call_device_crops_with_stub_models(monkeypatch):
+    """CPU: TextRecognizer.__call__ on the device_crops path (records -> order -> plan -> canvases cut in plan order)
+    against the host path (ParseqDataset), both with the PARSeq call replaced by a checksum stand-in; one quad is
+    invalid (dropped), which also switches the bucketing off exactly like the reference."""
+    import ctypes
+
+    from oracle import build_crop_host
+    from yomitoku_b200 import models as M
+    from yomitoku_b200.data import layout_crop_buffers
+
+    host = ctypes.CDLL(build_crop_host.build())
+    S = 26
+
+    def make(dev):
+        rec = TextRecognizer(model_name="parseq-tiny-dynw-v4", from_pretrained=False, device="cpu", dynamic_width=True,
+                             batch_bucketing=True)
+        rec.device_crops = dev
+        rec._upload_page = lambda img: torch.from_numpy(np.ascontiguousarray(img))[None]
+
+        def checks(raw, descs, n, n_groups):
+            ids = np.zeros((n, S), np.int32)
+            for r, d in enumerate(descs):
+                c = raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3]
+                ids[r, 0] = 1 + (int(c.astype(np.int64).sum()) * 31 + int(d["wp"]) * 7 + int(d["group"])) % 7000
+            return ids, np.full((n, S), 0.5, np.float32), np.full((n_groups,), S, np.int32)
+
+        def fake_ptr(ptr, on_device, total, descs, n, n_groups, stream=None):
+            raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
+            return checks(raw, descs, n, n_groups)
+
+        def fake_crops(canvases, padded, groups, n_groups):
+            buf, total, descs, _ = rec.model.pack_crops(canvases, padded, groups)
+            return checks(buf.numpy(), [dict(pix_off=d.pix_off, w=d.w, wp=d.wp, group=d.group) for d in descs[:len(canvases)]],
+                          len(canvases), n_groups)
+
+        rec.model.run_packed_ptr = fake_ptr
+        rec.model.recognize_crops = fake_crops
+        return rec
+
+    class FakeDev:
+        def __init__(self, arr):
+            self.arr = arr
+
+        def data_ptr(self):
+            return self.arr.ctypes.data
+
+    def fake_extract(pages_dev, geoms, stream=None):
+        sb, cb = layout_crop_buffers(geoms)
+        scratch, canv = np.zeros(max(sb, 1), np.uint8), np.full(max(cb, 1), 99, np.uint8)
+        pg = np.ascontiguousarray(pages_dev.numpy())
+        vp = ctypes.c_void_p
+        host.crop_host_extract(pg.ctypes.data_as(vp), pg.shape[1], pg.shape[2], geoms.ctypes.data_as(vp), len(geoms),
+                               scratch.ctypes.data_as(vp), canv.ctypes.data_as(vp))
+        return FakeDev(canv), cb
+
+    monkeypatch.setattr(M, "extract_crops_device", fake_extract)
+    page, quads = synthetic_page(5)
+    for qs in (quads[:70], quads[:30] + [[[-5, 3], [40, 3], [40, 20], [-5, 20]]] + quads[30:60], None):
+        a, _ = make(True)(page, qs)
+        b, _ = make(False)(page, qs)
+        assert a.contents == b.contents and a.directions == b.directions and a.points == b.points
+        assert len(a.contents) == (1 if qs is None else 70 if len(qs) == 70 else 60)

@@ -213,7 +213,7 @@ class BatchedOCR:
         # available with source_downscale (the pyramid levels are host images).
         if device_crops is None:
             device_crops = os.environ.get("YTK_DEVICE_CROPS", "0") == "1"
-        self.device_crops = bool(device_crops) and not recognizer.source_downscale
+        self.device_crops = bool(device_crops) and not getattr(recognizer, "source_downscale", False)
         self.det_batch = det_batch
         self.max_tokens = max_tokens
         self.workers = workers if workers is not None else max(1, min(32, (os.cpu_count() or 2) - 2))

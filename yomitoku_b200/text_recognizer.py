@@ -12,6 +12,7 @@ as ONE packed ragged launch sequence (`PARSeq.recognize_crops`); only (token id,
 `infer_onnx` / `num_parallel_batches` are accepted and ignored (no ONNX path; the reference's parallel path is
 unreachable, Appendix A17).
 """
+import os
 import unicodedata
 
 import cv2
@@ -21,7 +22,7 @@ from .base import BaseModelCatalog, BaseModule
 from .config import (TextRecognizerPARSeqConfig, TextRecognizerPARSeqLargeV41Config, TextRecognizerPARSeqSmallConfig,
                      TextRecognizerPARSeqTinyConfig, TextRecognizerPARSeqTinyDynwV4Config,
                      TextRecognizerPARSeqV2Config)
-from .data import ParseqDataset, resize_with_padding
+from .data import ParseqDataset, crop_geometry, resize_with_padding
 from .models import PARSeq
 from .postprocessor import ParseqTokenizer as Tokenizer
 from .schemas import TextRecognizerSchema
@@ -99,6 +100,10 @@ class TextRecognizer(BaseModule):
         self.dynamic_width = dynamic_width
         self.num_parallel_batches = num_parallel_batches
         self.source_downscale = source_downscale
+        # device-side crop extraction (csrc/crop_ops.cu, bit-exact with the OpenCV path): the page goes to HBM once and
+        # the canvases are cut there.  Off for the side paths that need host images of the crops (orientation
+        # fallback re-reads roi_images, the source_downscale pyramid is built with cv2 on the host).
+        self.device_crops = os.environ.get("YTK_DEVICE_CROPS", "0") == "1"
         self.model.to(self.device)
 
     # ------------------------------------------------------------------------------------------ batching
@@ -187,8 +192,62 @@ class TextRecognizer(BaseModule):
             if r_scores[j] > scores[idx] and r_scores[j] >= self.rec_orientation_fallback_thresh:
                 preds[idx], scores[idx], directions[idx] = r_preds[j], r_scores[j], r_dirs[j]
 
+    @staticmethod
+    def _upload_page(img):
+        import torch
+        return torch.from_numpy(np.ascontiguousarray(img))[None].to("cuda")
+
+    def _call_device_crops(self, img, points):
+        """`__call__` with the crops cut on the GPU: same order / plan / pairing decisions as the host path, taken
+        from the crop records (canvas and content widths follow from the quads alone)."""
+        from . import _lib, models
+        if points is None:
+            h, w = img.shape[:2]
+            points = [[[0, 0], [w, 0], [w, h], [0, h]]]
+        geoms, keep = crop_geometry(img.shape, points, self._cfg.data.img_size, self.dynamic_width)
+        n = len(geoms)
+        if n == 0:
+            return TextRecognizerSchema(contents=[], scores=[], points=points, directions=[])
+        order = None
+        if self.batch_bucketing and n == len(points) and n > 1:
+            order = np.argsort(geoms["cw"]).tolist()
+        widths = geoms["canvas_w"].tolist()
+        plan = plan_mini_batches(widths, order, self.dynamic_width, self._cfg.data.batch_size,
+                                 getattr(self._cfg.data, "width_budget", None),
+                                 getattr(self._cfg.data, "max_batch_size", None))
+        flat = [i for b in plan for i in b]
+        padded, group = self._collate_widths(widths, plan)
+        sel = geoms[np.asarray(flat, np.int64)].copy()
+        page_dev = self._upload_page(img)
+        canv, total = models.extract_crops_device(page_dev, sel)
+        ph, pw = self._cfg.encoder.patch_size
+        gh = self._cfg.data.img_size[0] // ph
+        wp = np.asarray([padded[i] for i in flat], np.int64)
+        ntok = gh * (wp // pw)
+        descs = np.zeros(n, dtype=np.dtype(_lib.YtkCrop))
+        descs["pix_off"], descs["w"], descs["wp"] = sel["pix_off"], sel["canvas_w"], wp
+        descs["tok_off"], descs["ntok"] = np.cumsum(ntok) - ntok, ntok
+        descs["group"] = [group[i] for i in flat]
+        ids, probs, glen = self.model.run_packed_ptr(canv.data_ptr(), 1, total, descs, n, len(plan))
+        if self.model.refine_iters == 0:
+            for k, i in enumerate(flat):
+                L = int(glen[group[i]])
+                ids[k, L:] = self.tokenizer.eos_id
+                probs[k, L:] = 1.0
+        pts = [points[i] for i in order] if order is not None else points
+        p, s, d = self.postprocess_ids(ids, probs, pts[:n])
+        if order is not None:
+            inverse = np.argsort(order)
+            p, s, d = [p[i] for i in inverse], [s[i] for i in inverse], [d[i] for i in inverse]
+        return TextRecognizerSchema(contents=p, scores=s, points=points, directions=d)
+
     def __call__(self, img, points=None, vis=None):
         """img: BGR page; points: list of quads (4 clockwise points).  Returns (TextRecognizerSchema, vis)."""
+        if self.device_crops and not (self.source_downscale or self.rec_orientation_fallback):
+            results = self._call_device_crops(img, points)
+            if self.visualize and vis is None:
+                vis = img.copy()
+            return results, vis
         plan, points, dataset, order = self.preprocess(img, points)
         n = len(dataset)
         if n == 0:
