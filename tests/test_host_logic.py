@@ -222,8 +222,15 @@ def test_batched_pipeline_with_stub_models():
     try:
         got = list(ocr.stream(batches, lookahead=2, prob_override=maps))
         again = [ocr(pg, prob_override=pm) for pg, pm in zip(batches, maps)]
+        # manual use: four batches submitted before the first is collected - unrecognised batches keep their staging
+        # slot (the ring grows instead of overwriting a crop arena that has not been read yet)
+        handles = [ocr.submit(pg, pm) for pg, pm in zip(batches, maps)]
+        assert ocr._ring == 4
+        manual = [ocr.collect(h) for h in handles]
     finally:
         ocr.close()
+    assert [[[w.content for w in pg.words] for pg in b] for b in manual] == \
+        [[[w.content for w in pg.words] for pg in b] for b in got]
     post = DBnetPostProcessor(**dict(det._cfg.post_process))
     assert len(got) == 4
     for k in range(4):

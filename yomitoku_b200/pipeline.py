@@ -219,8 +219,9 @@ class BatchedOCR:
         self.workers = workers if workers is not None else max(1, min(32, (os.cpu_count() or 2) - 2))
         self._pool = None
         self._prob_ring = {}
-        self._slot = 0              # ring slot (pages + probability maps) of the batch being submitted
-        self._slot_busy = {}        # slot -> futures of the batch that last used it
+        self._slot = 0              # ring slot (pages + probability maps + crop arena) of the batch being submitted
+        self._ring = 3              # number of ring slots
+        self._slot_busy = {}        # slot -> (host-stage futures, handle) of the batch that last used it
         self._last_shared = None
         self.crop_cap = 8 << 20     # arena bytes per page; doubled when a page spills
 
@@ -539,16 +540,27 @@ class BatchedOCR:
         return out
 
     # ------------------------------------------------------------------------------------------ whole path
-    def submit(self, pages, prob_override=None, quads_override=None, stream=None):
+    def submit(self, pages, prob_override=None, quads_override=None, stream=None, wait_recognized=False):
         """Stage 1 (device, synchronous: a few ms per page) + hand the host stage to the worker pool.  Returns a handle
         for `collect`.  Submitting batch i+1 before collecting batch i overlaps its host stage (contours, unclip, crop
         extraction) with the recognition of batch i on the GPU."""
         pool = self._get_pool()
-        # staging ring: 3 slots; a slot is reused only after the host stage of its previous batch has finished
-        self._slot = (self._slot + 1) % 3
+        # staging ring (pages, probability maps, crop arena): a slot is reused only after the host stage of its
+        # previous batch has finished AND that batch has been recognised (the recognizer's H2D copy reads the arena).
+        # stream() waits for that; with manual submit()/collect() an unrecognised batch keeps its slot and the ring grows
+        self._slot = (self._slot + 1) % self._ring
         with _span("submit.wait_slot"):
-            for f in self._slot_busy.pop(self._slot, []):
-                f.result()
+            prev = self._slot_busy.pop(self._slot, None)
+            if prev is not None:
+                for f in prev[0]:
+                    f.result()
+                if not prev[1].done.is_set():
+                    if wait_recognized:
+                        prev[1].done.wait()
+                    else:
+                        self._slot_busy[self._slot] = prev
+                        self._slot = self._ring
+                        self._ring += 1
         n = len(pages)
         stage, out = self._stage(pages, shared=pool is not None)
         prob = out.numpy()
@@ -595,8 +607,9 @@ class BatchedOCR:
                 futs.append(_Done(_host_stage(job)) if pool is None else pool.submit(_host_stage, job))
         if pool is None:
             return _Handle(futs, None, 0, pages_dev)
-        self._slot_busy[self._slot] = futs
-        return _Handle(futs, arena, cap, pages_dev)
+        handle = _Handle(futs, arena, cap, pages_dev)
+        self._slot_busy[self._slot] = (futs, handle)
+        return handle
 
     @staticmethod
     def _upload_pages(stage, stream=None):
@@ -613,6 +626,12 @@ class BatchedOCR:
         return self._assemble(*self._recognize_handle(handle, stream))
 
     def _recognize_handle(self, handle, stream=None):
+        try:
+            return self._recognize_handle_impl(handle, stream)
+        finally:
+            handle.done.set()       # the staging slot of this batch may be reused
+
+    def _recognize_handle_impl(self, handle, stream=None):
         with _span("collect.wait_host"):
             host = [f.result() for f in handle.futures]
         arena = handle.arena
@@ -709,7 +728,7 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
                     pass
                 po = None if prob_override is None else prob_override[k]
                 qo = None if quads_override is None else quads_override[k]
-                q.put(ocr.submit(pages, po, qo, stream=det_stream))
+                q.put(ocr.submit(pages, po, qo, stream=det_stream, wait_recognized=True))
         except BaseException as e:  # surfaced in the consumer
             err.append(e)
         finally:
@@ -728,8 +747,11 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
                 q2.put(ocr._recognize_handle(h, stream=rec_stream))
         except BaseException as e:
             err.append(e)
-            while q.get() is not None:      # keep draining so that the producer can finish
-                pass
+            while True:                     # keep draining (and releasing staging slots) so that the producer can finish
+                h = q.get()
+                if h is None:
+                    break
+                h.done.set()
         finally:
             q2.put(None)
 
@@ -751,7 +773,9 @@ class _Handle:
     """What `submit` returns: the host-stage futures of a batch + the crop arena its workers write into."""
 
     def __init__(self, futures, arena, cap, pages_dev=None):
+        import threading
         self.futures, self.arena, self.cap, self.pages_dev = futures, arena, cap, pages_dev
+        self.done = threading.Event()       # set once the batch has been recognised (or abandoned)
 
 
 class _HostCanvases:
