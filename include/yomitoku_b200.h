@@ -156,8 +156,11 @@ typedef struct {
 } ytk_crop_geom;
 
 /* pages_dev: [n_pages, H0, W0, 3] uint8 BGR in device memory (e.g. the buffer handed to ytk_dbnet_forward_u8 with
- * pages_on_device = 1); geoms: host array; scratch_dev / canvases_dev: caller-owned device buffers.  Asynchronous on
- * cuda_stream (the geoms array may be reused as soon as the call returns). */
+ * pages_on_device = 1); geoms: host array (pageable: may be reused as soon as the call returns; page-locked: must stay
+ * valid until the stream has passed the call); scratch_dev / canvases_dev: caller-owned device buffers.  scratch_dev
+ * holds the rectified ROIs (at roi_off) and, 16-byte aligned after the last ROI, a copy of the n_crops records, so
+ * scratch_bytes >= align16(max(roi_off + w*h*3)) + n_crops * sizeof(ytk_crop_geom): the call allocates nothing.
+ * Asynchronous on cuda_stream: one H2D copy of the records + two kernel launches. */
 int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, const ytk_crop_geom* geoms, int n_crops,
                          uint8_t* scratch_dev, long long scratch_bytes, uint8_t* canvases_dev, long long canvases_bytes,
                          void* cuda_stream);

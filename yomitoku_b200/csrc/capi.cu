@@ -1,6 +1,7 @@
 // extern "C" surface of libytk_b200.so (declared in include/yomitoku_b200.h).
 #include "../../include/yomitoku_b200.h"
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -250,6 +251,7 @@ int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, 
         ytk::set_error("ytk_extract_crops_u8: null or empty argument");
         return YTK_ERR;
     }
+    long long roi_end = 0;
     for (int i = 0; i < n_crops; ++i) {
         const ytk_crop_geom& g = geoms[i];
         const long long sw = g.rot ? g.h : g.w, sh = g.rot ? g.w : g.h;
@@ -265,6 +267,15 @@ int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, 
                            g.ch, g.canvas_w, g.canvas_h);
             return YTK_ERR;
         }
+        roi_end = std::max(roi_end, g.roi_off + (long long)g.w * g.h * 3);
+    }
+    // the records are staged in the caller's scratch buffer, 16-byte aligned after the ROIs: no allocation here
+    const long long rec_off = (roi_end + 15) / 16 * 16;
+    const long long rec_bytes = (long long)n_crops * (long long)sizeof(ytk::CropGeom);
+    if (rec_off + rec_bytes > scratch_bytes) {
+        ytk::set_error("ytk_extract_crops_u8: scratch_dev holds %lld bytes, need %lld (ROIs) + %lld (records)", scratch_bytes,
+                       rec_off, rec_bytes);
+        return YTK_ERR;
     }
     cudaPointerAttributes attr;
     if (cudaPointerGetAttributes(&attr, pages_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
@@ -274,16 +285,14 @@ int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, 
     }
     cudaSetDevice(attr.device);  // host threads start on device 0: the device that owns the pages is the one that counts
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
-    ytk::CropGeom* dev = nullptr;
-    const size_t bytes = (size_t)n_crops * sizeof(ytk::CropGeom);
-    cudaError_t err = cudaMallocAsync(reinterpret_cast<void**>(&dev), bytes, st);
-    if (err == cudaSuccess) err = cudaMemcpyAsync(dev, geoms, bytes, cudaMemcpyHostToDevice, st);
-    int rc = 0;
-    if (err == cudaSuccess)
-        rc = ytk::launch_extract_crops(pages_dev, H0, W0, dev, n_crops, scratch_dev, canvases_dev, st);
-    if (dev) cudaFreeAsync(dev, st);
-    if (err != cudaSuccess || rc) {
-        ytk::set_error("ytk_extract_crops_u8: %s", err != cudaSuccess ? cudaGetErrorString(err) : "kernel launch failed");
+    ytk::CropGeom* dev = reinterpret_cast<ytk::CropGeom*>(scratch_dev + rec_off);
+    cudaError_t err = cudaMemcpyAsync(dev, geoms, (size_t)rec_bytes, cudaMemcpyHostToDevice, st);
+    if (err != cudaSuccess) {
+        ytk::set_error("ytk_extract_crops_u8: record upload failed: %s", cudaGetErrorString(err));
+        return YTK_ERR;
+    }
+    if (ytk::launch_extract_crops(pages_dev, H0, W0, dev, n_crops, scratch_dev, canvases_dev, st)) {
+        ytk::set_error("ytk_extract_crops_u8: kernel launch failed");
         return YTK_ERR;
     }
     return YTK_OK;

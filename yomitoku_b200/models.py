@@ -100,6 +100,8 @@ def extract_crops_device(pages_dev, geoms, stream=None):
         raise ValueError("extract_crops_device: geoms must be a contiguous CROP_GEOM_DTYPE array")
     scratch_bytes, total = layout_crop_buffers(geoms)      # writes roi_off / pix_off into the caller's records
     ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(pages_dev.device)
+    # scratch = ROIs + (16-byte aligned) the device copy of the records (include/yomitoku_b200.h)
+    scratch_bytes = (scratch_bytes + 15) // 16 * 16 + geoms.nbytes
     with ctx:
         scratch = torch.empty(max(scratch_bytes, 1), dtype=torch.uint8, device=pages_dev.device)
         canv = torch.empty(max(total, 1), dtype=torch.uint8, device=pages_dev.device)
