@@ -159,6 +159,7 @@ def _worker_pipeline_dev(rank, world, port, q):
         from oracle import build_crop_host
         from yomitoku_b200 import data as D
         from yomitoku_b200 import models as M
+        from yomitoku_b200 import parallel as par_mod
         from yomitoku_b200 import pipeline as pl
         from yomitoku_b200.config import TextRecognizerPARSeqLargeV41Config, to_config
         from yomitoku_b200.synth import synthetic_page
@@ -172,6 +173,9 @@ def _worker_pipeline_dev(rank, world, port, q):
         class FakeDev:
             def __init__(self, arr):
                 self.arr = arr
+
+            def data_ptr(self):
+                return self.arr.ctypes.data
 
         def fake_extract(pages_dev, geoms, stream=None):
             sb, cb = D.layout_crop_buffers(geoms)
@@ -200,9 +204,14 @@ def _worker_pipeline_dev(rank, world, port, q):
             widths = [int(geoms["canvas_w"][i]) for i in b]
             groups.append((widths, [max(widths)] * len(b), np.asarray(b, np.int64)))
             expect.append(_fake_recognise([ds.data[i] for i in b]))
+        moved = []
+        orig_pack = par_mod._pack_group
+        par_mod._pack_group = lambda canv, padded, gid: (moved.append(gid), orig_pack(canv, padded, gid))[1]
         res = ocr._run_groups_dev(groups, geoms, np.ascontiguousarray(page)[None], None)
         for (ids, probs, glen), (eid, ep) in zip(res, expect):
             assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101
+        # rank 0 (8 groups) hands some groups to rank 1 (2 groups); the rest never left the "device"
+        assert (0 < len(moved) < len(groups)) if rank == 0 else not moved
         q.put((rank, "ok", None))
     except Exception:  # pragma: no cover
         import traceback

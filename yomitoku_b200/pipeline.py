@@ -387,28 +387,39 @@ class BatchedOCR:
 
     def _run_groups_dev(self, groups, geoms, pages_dev, stream=None):
         """Groups whose crops exist only as records: groups = (widths, padded widths, record indices into `geoms`).
-        The canvases of a <= max_tokens chunk are cut on the device (ytk_extract_crops_u8) in group order and go to
-        PARSeq without leaving HBM.  With torch.distributed the canvases are brought to the host once and take the
-        arena path, so that groups can still be balanced across ranks."""
-        import torch
+        Groups recognised on this rank are cut on the device and never leave HBM (`_run_groups_dev_local`).  With
+        torch.distributed, only the groups the balancer moves to another rank are cut separately and brought to the
+        host (page-locked) for the crop scatter; with balanced ranks nothing moves and no canvas touches PCIe."""
         import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return self._run_groups_dev_local(groups, geoms, pages_dev, stream)
+        from .models import extract_crops_device
+
+        def pixels(ks):
+            sel = geoms[np.concatenate([groups[k][2] for k in ks])].copy()
+            canv, _ = extract_crops_device(pages_dev, sel, stream)
+            host = _HostCanvases(canv, stream).np
+            out, j = [], 0
+            for k in ks:
+                rows = sel[j:j + len(groups[k][0])]
+                out.append([host[int(r["pix_off"]):int(r["pix_off"]) + int(r["canvas_h"]) * int(r["canvas_w"]) * 3]
+                            .reshape(int(r["canvas_h"]), int(r["canvas_w"]), 3) for r in rows])
+                j += len(rows)
+            return out
+
+        return self._run_groups_dist(
+            groups, pixels,
+            lambda ks: self._run_groups_dev_local([groups[k] for k in ks], geoms, pages_dev, stream), stream)
+
+    def _run_groups_dev_local(self, groups, geoms, pages_dev, stream=None):
+        """This rank's share of `_run_groups_dev`: the canvases of a <= max_tokens chunk are cut on the device
+        (ytk_extract_crops_u8) in group order and go to PARSeq without leaving HBM."""
         from . import _lib
         from .models import extract_crops_device
         rec = self.recognizer
         cfg = rec._cfg
         ph, pw = cfg.encoder.patch_size
         gh = cfg.data.img_size[0] // ph
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            idx = np.concatenate([g[2] for g in groups]) if groups else np.zeros(0, np.int64)
-            sel = geoms[idx].copy()
-            canv, _ = extract_crops_device(pages_dev, sel, stream)
-            host = _HostCanvases(canv, stream)
-            offs, k = sel["pix_off"], 0
-            agroups = []
-            for g in groups:
-                agroups.append((g[0], g[1], offs[k:k + len(g[0])]))
-                k += len(g[0])
-            return self._run_groups(agroups, stream, host, int(sel["canvas_h"][0]) if len(sel) else 32)
         out = [None] * len(groups)
         gtok = [gh * (int(np.sum(g[1])) // pw) for g in groups]
         dt = np.dtype(_lib.YtkCrop)
@@ -450,10 +461,31 @@ class BatchedOCR:
         (canvases, padded widths) or, with `arena`, (widths, padded widths, arena offsets); only groups that leave this
         rank are ever materialised as pixel arrays."""
         import torch.distributed as dist
-        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+
+        def run_mine(ks):
+            sel = [groups[k] for k in ks]
             if arena is not None:
-                return self._run_groups_arena(groups, arena, height, stream)
-            return self._run_groups_local(groups, stream)
+                return self._run_groups_arena(sel, arena, height, stream)
+            return self._run_groups_local(sel, stream)
+
+        if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+            return run_mine(range(len(groups)))
+
+        def pixels(ks):
+            if arena is None:
+                return [groups[k][0] for k in ks]
+            an = arena.np
+            return [[an[int(o):int(o) + height * int(w) * 3].reshape(height, int(w), 3)
+                     for w, o in zip(groups[k][0], groups[k][2])] for k in ks]
+
+        return self._run_groups_dist(groups, pixels, run_mine, stream)
+
+    def _run_groups_dist(self, groups, pixels, run_mine, stream=None):
+        """The multi-rank part of `_run_groups` / `_run_groups_dev`.  groups[k][1] = padded widths (the cost);
+        pixels(ks) -> canvases (host arrays) of the groups ks that leave this rank; run_mine(ks) -> results of the
+        groups ks that stay.  Balances whole groups across ranks, scatters the leaving ones, recognises own + received
+        groups, returns every group's (ids, probs, group_len) to its owner."""
+        import torch.distributed as dist
         from . import parallel as par
         cfg = self.recognizer._cfg
         ph, pw = cfg.encoder.patch_size
@@ -461,20 +493,12 @@ class BatchedOCR:
         rank = dist.get_rank()
         costs = [gh * (int(np.sum(g[1])) // pw) for g in groups]
         assign = par.balance_groups(par.gather_costs(costs), dist.get_world_size())[rank]
-
-        def pixels(g):
-            if arena is None:
-                return g[0]
-            an = arena.np
-            return [an[int(o):int(o) + height * int(w) * 3].reshape(height, int(w), 3) for w, o in zip(g[0], g[2])]
-
-        send = [(pixels(g) if assign[k] != rank else None, g[1]) for k, g in enumerate(groups)]
-        work = par.exchange_groups(send, assign, cfg.data.img_size[0])
+        leaving = [k for k in range(len(groups)) if assign[k] != rank]
         mine = [k for k in range(len(groups)) if assign[k] == rank]        # exchange_groups lists own groups first
-        if arena is not None:
-            res = self._run_groups_arena([groups[k] for k in mine], arena, height, stream)
-        else:
-            res = self._run_groups_local([groups[k] for k in mine], stream)
+        pix = dict(zip(leaving, pixels(leaving))) if leaving else {}
+        send = [(pix.get(k), g[1]) for k, g in enumerate(groups)]
+        work = par.exchange_groups(send, assign, cfg.data.img_size[0])
+        res = list(run_mine(mine)) if mine else []
         foreign = work[len(mine):]
         if foreign:
             res = res + self._run_groups_local([(w[2], w[3]) for w in foreign], stream)
