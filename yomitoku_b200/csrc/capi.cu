@@ -2,6 +2,7 @@
 #include "../../include/yomitoku_b200.h"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -22,7 +23,12 @@ struct ytk_parseq {
 
 struct ytk_dbnet {
     ytk::DbnetModel model;
+    // launch plans + activation buffers per input shape (n, Hn, Wn); least recently used ones are dropped beyond
+    // max_engines (YTK_DBNET_MAX_ENGINES, default 6) so that a stream of differently sized pages cannot exhaust HBM
     std::map<std::tuple<int, int, int>, std::unique_ptr<ytk::DbnetEngine>> engines;
+    std::map<std::tuple<int, int, int>, unsigned long long> last_use;
+    unsigned long long tick = 0;
+    int max_engines = 6;
     std::mutex mu;
     int device = 0;
     int shortest = 1280, limit = 1600;
@@ -32,8 +38,17 @@ struct ytk_dbnet {
 
 static ytk::DbnetEngine* get_engine(ytk_dbnet* h, int n, int Hn, int Wn) {
     auto key = std::make_tuple(n, Hn, Wn);
+    h->last_use[key] = ++h->tick;
     auto it = h->engines.find(key);
     if (it != h->engines.end()) return it->second.get();
+    while ((int)h->engines.size() >= h->max_engines && !h->engines.empty()) {
+        auto victim = h->engines.begin();
+        for (auto e = h->engines.begin(); e != h->engines.end(); ++e)
+            if (h->last_use[e->first] < h->last_use[victim->first]) victim = e;
+        cudaDeviceSynchronize();  // its last run may still be in flight on some stream
+        h->last_use.erase(victim->first);
+        h->engines.erase(victim);
+    }
     auto e = std::make_unique<ytk::DbnetEngine>();
     if (e->build(h->model, n, Hn, Wn)) return nullptr;
     ytk::DbnetEngine* p = e.get();
@@ -130,6 +145,7 @@ int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size
     cudaGetDevice(&h->device);
     h->shortest = shortest_size;
     h->limit = limit_size;
+    if (const char* me = getenv("YTK_DBNET_MAX_ENGINES")) h->max_engines = std::max(1, atoi(me));
     if (h->model.load(ws)) return YTK_ERR;
     *out = h.release();
     return YTK_OK;
