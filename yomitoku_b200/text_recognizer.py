@@ -210,7 +210,9 @@ class TextRecognizer(BaseModule):
             return TextRecognizerSchema(contents=[], scores=[], points=points, directions=[])
         order = None
         if self.batch_bucketing and n == len(points) and n > 1:
-            order = np.argsort(geoms["cw"]).tolist()
+            # a Python list -> int64, like the reference's np.argsort(dataset.content_widths): numpy's unstable sort may
+            # order ties differently for another dtype
+            order = np.argsort(geoms["cw"].tolist()).tolist()
         widths = geoms["canvas_w"].tolist()
         plan = plan_mini_batches(widths, order, self.dynamic_width, self._cfg.data.batch_size,
                                  getattr(self._cfg.data, "width_budget", None),
