@@ -150,7 +150,8 @@ typedef struct {
     int page;          /* index into pages_dev */
     int x0, y0, rw, rh; /* bounding-box slice of the (int64-truncated) quad inside the page */
     int w, h;          /* rectified size: (int |p0p1|, int |p1p2|) */
-    int rot;           /* 1 = rotate 90 degrees counter-clockwise after the warp (h > 2w) */
+    int rot;           /* bit 0: rotate 90 degrees counter-clockwise after the warp (h > 2w); bit 1: then rotate by 180
+                          degrees (the orientation fallback's second look, text_recognizer.py:319-328) */
     int cw, ch;        /* content size after the down-scale-only fit (calc_resize_without_padding) */
     int canvas_w, canvas_h;
 } ytk_crop_geom;

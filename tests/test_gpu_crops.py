@@ -81,6 +81,21 @@ def test_device_crops_match_opencv_and_host_build_on_random_quads():
                                                                        rot=int(geoms[i]["rot"])))
 
 
+def test_device_orientation_fallback_crops_match_opencv():
+    """Record bit `rot & 2` (the orientation fallback's 180-degree second look on the fixed canvas)."""
+    cv2.setNumThreads(1)
+    rng = np.random.default_rng(78)
+    H, W = 900, 1400
+    page = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    quads = [random_quad(rng, H, W, k % 6) for k in range(36)]
+    ds = D.ParseqDataset(CFG, page, quads, num_workers=1, dynamic_width=True)
+    geoms, keep = D.crop_geometry(page.shape, quads, CFG.data.img_size, True)
+    geoms["rot"] |= 2
+    geoms["canvas_w"] = CFG.data.img_size[1]
+    for got, roi in zip(device_extract(page[None], geoms), ds.roi_images):
+        assert np.array_equal(got, D.resize_with_padding(cv2.rotate(roi, cv2.ROTATE_180), CFG.data.img_size))
+
+
 def test_extract_crops_rejects_inconsistent_records():
     from yomitoku_b200 import _lib
     page = torch.zeros((1, 100, 200, 3), dtype=torch.uint8, device="cuda")
@@ -155,6 +170,14 @@ def test_recognizer_call_device_crops_equals_host_crops():
     d, _ = rec(page, None)
     assert a.contents == b.contents and a.directions == b.directions and np.allclose(a.scores, b.scores, atol=1e-6)
     assert c.contents == d.contents
+    # orientation fallback: every crop scoring below the threshold takes the 180-degree second look on both paths;
+    # identical canvases -> identical decisions and results
+    rec.rec_orientation_fallback, rec.rec_orientation_fallback_thresh = True, 0.9
+    e, _ = rec(page, quads[:40])
+    rec.device_crops = True
+    f, _ = rec(page, quads[:40])
+    rec.rec_orientation_fallback, rec.device_crops = False, False
+    assert e.contents == f.contents and np.allclose(e.scores, f.scores, atol=1e-6)
 
 
 def test_host_canvases_copy():

@@ -349,11 +349,16 @@ def test_recognizer_call_device_crops_with_stub_models(monkeypatch):
         rec._upload_page = lambda img: torch.from_numpy(np.ascontiguousarray(img))[None]
 
         def checks(raw, descs, n, n_groups):
+            # ids[0] / the score depend on WHERE the pixels are (a 180-degree turn changes them), on the padded width
+            # and on the mini-batch index; position 1 is EOS, so the score is probs[0]
             ids = np.zeros((n, S), np.int32)
+            probs = np.ones((n, S), np.float32)
             for r, d in enumerate(descs):
-                c = raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3]
-                ids[r, 0] = 1 + (int(c.astype(np.int64).sum()) * 31 + int(d["wp"]) * 7 + int(d["group"])) % 7000
-            return ids, np.full((n, S), 0.5, np.float32), np.full((n_groups,), S, np.int32)
+                c = raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3].astype(np.int64)
+                h = int((c * (1 + np.arange(c.size) % 251)).sum())
+                ids[r, 0] = 1 + (h * 31 + int(d["wp"]) * 7 + int(d["group"])) % 7000
+                probs[r, 0] = 0.55 + 0.44 * ((h % 1000) / 1000.0)
+            return ids, probs, np.full((n_groups,), S, np.int32)
 
         def fake_ptr(ptr, on_device, total, descs, n, n_groups, stream=None):
             raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
@@ -386,8 +391,16 @@ def test_recognizer_call_device_crops_with_stub_models(monkeypatch):
 
     monkeypatch.setattr(M, "extract_crops_device", fake_extract)
     page, quads = synthetic_page(5)
-    for qs in (quads[:70], quads[:30] + [[[-5, 3], [40, 3], [40, 20], [-5, 20]]] + quads[30:60], None):
-        a, _ = make(True)(page, qs)
-        b, _ = make(False)(page, qs)
-        assert a.contents == b.contents and a.directions == b.directions and a.points == b.points
-        assert len(a.contents) == (1 if qs is None else 70 if len(qs) == 70 else 60)
+    tall = [[[300, 100], [330, 100], [330, 400], [300, 400]]]      # vertical line: rotated by 90 degrees first
+    for fallback in (False, True):
+        for qs in (quads[:70] + tall, quads[:30] + [[[-5, 3], [40, 3], [40, 20], [-5, 20]]] + quads[30:60], None):
+            ra, rb = make(True), make(False)
+            ra.rec_orientation_fallback = rb.rec_orientation_fallback = fallback
+            a, _ = ra(page, qs)
+            b, _ = rb(page, qs)
+            assert a.contents == b.contents and a.directions == b.directions and a.points == b.points
+            assert np.allclose(a.scores, b.scores)
+            assert len(a.contents) == (1 if qs is None else 71 if len(qs) == 71 else 60)
+            if fallback and qs is not None:     # the second look really replaced some results
+                c, _ = make(False)(page, qs)
+                assert 0 < sum(x != y for x, y in zip(b.contents, c.contents)) < len(b.contents)

@@ -270,10 +270,10 @@ int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, 
     long long roi_end = 0;
     for (int i = 0; i < n_crops; ++i) {
         const ytk_crop_geom& g = geoms[i];
-        const long long sw = g.rot ? g.h : g.w, sh = g.rot ? g.w : g.h;
+        const long long sw = (g.rot & 1) ? g.h : g.w, sh = (g.rot & 1) ? g.w : g.h;
         const bool ok = g.page >= 0 && g.page < n_pages && g.x0 >= 0 && g.y0 >= 0 && g.rw >= 1 && g.rh >= 1 &&
                         (long long)g.x0 + g.rw <= W0 && (long long)g.y0 + g.rh <= H0 && g.w >= 1 && g.h >= 1 &&
-                        (g.rot == 0 || g.rot == 1) && g.cw >= 1 && g.ch >= 1 && g.cw <= sw && g.ch <= sh &&
+                        g.rot >= 0 && g.rot <= 3 && g.cw >= 1 && g.ch >= 1 && g.cw <= sw && g.ch <= sh &&
                         g.cw <= g.canvas_w && g.ch <= g.canvas_h && g.roi_off >= 0 &&
                         g.roi_off + (long long)g.w * g.h * 3 <= scratch_bytes && g.pix_off >= 0 &&
                         g.pix_off + (long long)g.canvas_w * g.canvas_h * 3 <= canvases_bytes;

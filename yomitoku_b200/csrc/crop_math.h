@@ -35,7 +35,8 @@ struct CropGeom {
     int page;           // page index
     int x0, y0, rw, rh; // bounding-box slice of the quad inside the page (the image warpPerspective sees)
     int w, h;           // size of the rectified ROI before rotation: (int |p0p1|, int |p1p2|)
-    int rot;            // 1: rotate 90 degrees counter-clockwise after the warp (h > 2w)
+    int rot;            // bit 0: rotate 90 degrees counter-clockwise after the warp (h > 2w, rotate_text_image);
+                        // bit 1: then rotate by 180 degrees (orientation fallback, text_recognizer.py:319-328)
     int cw, ch;         // content size after the area resize (calc_resize_without_padding)
     int canvas_w, canvas_h;
 };
@@ -108,15 +109,21 @@ YTK_HD void warp_store(const CropGeom& g, const uint8_t* pages, int H0, int W0, 
         // 15-bit weights are 32 * (5-bit products): (sum * 32 + 2^14) >> 15 == (sum + 512) >> 10
         v[c] = (p00 * w00 + p01 * w01 + p10 * w10 + p11 * w11 + 512) >> 10;
     }
-    int orow, ocol, opitch;
-    if (g.rot) {  // ROTATE_90_COUNTERCLOCKWISE: dst (w rows x h cols), dst[i][j] = src[j][w-1-i]
+    int orow, ocol, opitch, orows;
+    if (g.rot & 1) {  // ROTATE_90_COUNTERCLOCKWISE: dst (w rows x h cols), dst[i][j] = src[j][w-1-i]
         orow = g.w - 1 - x;
         ocol = y;
         opitch = g.h;
+        orows = g.w;
     } else {
         orow = y;
         ocol = x;
         opitch = g.w;
+        orows = g.h;
+    }
+    if (g.rot & 2) {  // ROTATE_180 of that image: dst[i][j] = src[rows-1-i][cols-1-j]
+        orow = orows - 1 - orow;
+        ocol = opitch - 1 - ocol;
     }
     uint8_t* o = scratch + g.roi_off + ((long long)orow * opitch + ocol) * 3;
     o[0] = (uint8_t)v[2];  // BGR page -> RGB crop
@@ -224,7 +231,7 @@ YTK_HD void area_pixel(const uint8_t* src, int sw, int sh, int dw, int dh, int d
 YTK_HD void canvas_store(const CropGeom& g, const uint8_t* scratch, int cx, int cy, uint8_t* canvases) {
     uint8_t v[3] = {0, 0, 0};
     if (cx < g.cw && cy < g.ch) {
-        const int sw = g.rot ? g.h : g.w, sh = g.rot ? g.w : g.h;
+        const int sw = (g.rot & 1) ? g.h : g.w, sh = (g.rot & 1) ? g.w : g.h;
         area_pixel(scratch + g.roi_off, sw, sh, g.cw, g.ch, cx, cy, v);
     }
     uint8_t* o = canvases + g.pix_off + ((long long)cy * g.canvas_w + cx) * 3;

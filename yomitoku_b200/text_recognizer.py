@@ -101,8 +101,8 @@ class TextRecognizer(BaseModule):
         self.num_parallel_batches = num_parallel_batches
         self.source_downscale = source_downscale
         # device-side crop extraction (csrc/crop_ops.cu, bit-exact with the OpenCV path): the page goes to HBM once and
-        # the canvases are cut there.  Off for the side paths that need host images of the crops (orientation
-        # fallback re-reads roi_images, the source_downscale pyramid is built with cv2 on the host).
+        # the canvases are cut there, including the orientation fallback's 180-degree second look.  Not used with
+        # source_downscale (the pyramid levels are built with cv2 on the host).
         self.device_crops = os.environ.get("YTK_DEVICE_CROPS", "0") == "1"
         self.model.to(self.device)
 
@@ -197,10 +197,32 @@ class TextRecognizer(BaseModule):
         import torch
         return torch.from_numpy(np.ascontiguousarray(img))[None].to("cuda")
 
+    def _run_records(self, page_dev, sel, padded, group, n_groups):
+        """Cuts the crops of the records `sel` (already in packing order) on the GPU and runs them as one packed call;
+        padded[k] / group[k] = padded width and mini-batch index of record k.  Returns (ids, probs) with the positions
+        a `refine_iters == 0` model never produced filled like the host path does."""
+        from . import _lib, models
+        n = len(sel)
+        canv, total = models.extract_crops_device(page_dev, sel)
+        ph, pw = self._cfg.encoder.patch_size
+        gh = self._cfg.data.img_size[0] // ph
+        wp = np.asarray(padded, np.int64)
+        ntok = gh * (wp // pw)
+        descs = np.zeros(n, dtype=np.dtype(_lib.YtkCrop))
+        descs["pix_off"], descs["w"], descs["wp"] = sel["pix_off"], sel["canvas_w"], wp
+        descs["tok_off"], descs["ntok"] = np.cumsum(ntok) - ntok, ntok
+        descs["group"] = group
+        ids, probs, glen = self.model.run_packed_ptr(canv.data_ptr(), 1, total, descs, n, n_groups)
+        if self.model.refine_iters == 0:
+            for k in range(n):
+                L = int(glen[group[k]])
+                ids[k, L:] = self.tokenizer.eos_id
+                probs[k, L:] = 1.0
+        return ids, probs
+
     def _call_device_crops(self, img, points):
         """`__call__` with the crops cut on the GPU: same order / plan / pairing decisions as the host path, taken
         from the crop records (canvas and content widths follow from the quads alone)."""
-        from . import _lib, models
         if points is None:
             h, w = img.shape[:2]
             points = [[[0, 0], [w, 0], [w, h], [0, h]]]
@@ -219,33 +241,39 @@ class TextRecognizer(BaseModule):
                                  getattr(self._cfg.data, "max_batch_size", None))
         flat = [i for b in plan for i in b]
         padded, group = self._collate_widths(widths, plan)
-        sel = geoms[np.asarray(flat, np.int64)].copy()
         page_dev = self._upload_page(img)
-        canv, total = models.extract_crops_device(page_dev, sel)
-        ph, pw = self._cfg.encoder.patch_size
-        gh = self._cfg.data.img_size[0] // ph
-        wp = np.asarray([padded[i] for i in flat], np.int64)
-        ntok = gh * (wp // pw)
-        descs = np.zeros(n, dtype=np.dtype(_lib.YtkCrop))
-        descs["pix_off"], descs["w"], descs["wp"] = sel["pix_off"], sel["canvas_w"], wp
-        descs["tok_off"], descs["ntok"] = np.cumsum(ntok) - ntok, ntok
-        descs["group"] = [group[i] for i in flat]
-        ids, probs, glen = self.model.run_packed_ptr(canv.data_ptr(), 1, total, descs, n, len(plan))
-        if self.model.refine_iters == 0:
-            for k, i in enumerate(flat):
-                L = int(glen[group[i]])
-                ids[k, L:] = self.tokenizer.eos_id
-                probs[k, L:] = 1.0
+        ids, probs = self._run_records(page_dev, geoms[np.asarray(flat, np.int64)].copy(), [padded[i] for i in flat],
+                                       [group[i] for i in flat], len(plan))
         pts = [points[i] for i in order] if order is not None else points
         p, s, d = self.postprocess_ids(ids, probs, pts[:n])
         if order is not None:
             inverse = np.argsort(order)
             p, s, d = [p[i] for i in inverse], [s[i] for i in inverse], [d[i] for i in inverse]
+        if self.rec_orientation_fallback:
+            self._device_orientation_fallback(page_dev, geoms, points, p, s, d)
         return TextRecognizerSchema(contents=p, scores=s, points=points, directions=d)
+
+    def _device_orientation_fallback(self, page_dev, geoms, points, preds, scores, directions):
+        """`_apply_orientation_fallback` (reference text_recognizer.py:319-350) with the second look cut on the GPU: the
+        same rectified crop rotated by 180 degrees (record bit `rot & 2`) on the fixed-width canvas, in chunks of
+        `batch_size` (a fixed-width tensor in the reference: :205-210)."""
+        retry = [i for i, sc in enumerate(scores) if sc < self.rec_orientation_fallback_thresh]
+        if not retry:
+            return
+        sel = geoms[np.asarray(retry, np.int64)].copy()
+        sel["rot"] |= 2
+        sel["canvas_w"] = self._cfg.data.img_size[1]
+        bs = self._cfg.data.batch_size
+        group = [k // bs for k in range(len(retry))]
+        ids, probs = self._run_records(page_dev, sel, sel["canvas_w"].tolist(), group, group[-1] + 1)
+        r_preds, r_scores, r_dirs = self.postprocess_ids(ids, probs, [points[i] for i in retry])
+        for j, idx in enumerate(retry):
+            if r_scores[j] > scores[idx] and r_scores[j] >= self.rec_orientation_fallback_thresh:
+                preds[idx], scores[idx], directions[idx] = r_preds[j], r_scores[j], r_dirs[j]
 
     def __call__(self, img, points=None, vis=None):
         """img: BGR page; points: list of quads (4 clockwise points).  Returns (TextRecognizerSchema, vis)."""
-        if self.device_crops and not (self.source_downscale or self.rec_orientation_fallback):
+        if self.device_crops and not self.source_downscale:
             results = self._call_device_crops(img, points)
             if self.visualize and vis is None:
                 vis = img.copy()
