@@ -166,6 +166,13 @@ int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, 
                          uint8_t* scratch_dev, long long scratch_bytes, uint8_t* canvases_dev, long long canvases_bytes,
                          void* cuda_stream);
 
+/* One level of the recognizer's source_downscale pyramid (reference data/dataset.py:64-86):
+ * cv2.resize(page, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA) for n_pages pages [n, H, W, 3] uint8 in device
+ * memory, bit-exact with OpenCV 4.13 (2x2 cells round half up; the clipped last column / row of an odd size averages
+ * the pixels that exist).  dH = cvRound(H / 2), dW = cvRound(W / 2) (round half to even) - anything else is rejected. */
+int ytk_halve_pages_u8(const uint8_t* src_dev, int n_pages, int H, int W, uint8_t* dst_dev, int dH, int dW,
+                       void* cuda_stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,4 +32,10 @@ void crop_host_area(const uint8_t* src, int sw, int sh, int dw, int dh, uint8_t*
         for (int x = 0; x < dw; ++x) ytk::area_pixel(src, sw, sh, dw, dh, x, y, dst + ((long long)y * dw + x) * 3);
 }
 
+// cv2.resize(src, None, fx=0.5, fy=0.5, INTER_AREA): dst is [dh][dw][3] with dw = cvRound(sw / 2), dh = cvRound(sh / 2).
+void crop_host_halve(const uint8_t* src, int sw, int sh, int dw, int dh, uint8_t* dst) {
+    for (int y = 0; y < dh; ++y)
+        for (int x = 0; x < dw; ++x) ytk::halve_pixel(src, sw, sh, x, y, dst + ((long long)y * dw + x) * 3);
+}
+
 }  // extern "C"

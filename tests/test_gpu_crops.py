@@ -96,6 +96,24 @@ def test_device_orientation_fallback_crops_match_opencv():
         assert np.array_equal(got, D.resize_with_padding(cv2.rotate(roi, cv2.ROTATE_180), CFG.data.img_size))
 
 
+def test_pyramid_levels_match_opencv():
+    """ytk_halve_pages_u8 == cv2.resize(page, None, fx=0.5, fy=0.5, INTER_AREA), level after level, odd sizes included."""
+    from yomitoku_b200.models import halve_pages_device
+    cv2.setNumThreads(1)
+    rng = np.random.default_rng(31)
+    for H, W in ((1200, 1600), (1199, 1597), (37, 53), (2, 3)):
+        pages = rng.integers(0, 256, (2, H, W, 3), dtype=np.uint8)
+        dev = torch.from_numpy(pages).cuda()
+        host = [pages[0], pages[1]]
+        for level in range(3):
+            if min(host[0].shape[:2]) < 2:
+                break
+            dev = halve_pages_device(dev)
+            host = [cv2.resize(h, None, fx=0.5, fy=0.5, interpolation=cv2.INTER_AREA) for h in host]
+            got = dev.cpu().numpy()
+            assert got.shape[1:] == host[0].shape and np.array_equal(got[0], host[0]) and np.array_equal(got[1], host[1])
+
+
 def test_extract_crops_rejects_inconsistent_records():
     from yomitoku_b200 import _lib
     page = torch.zeros((1, 100, 200, 3), dtype=torch.uint8, device="cuda")
@@ -178,6 +196,16 @@ def test_recognizer_call_device_crops_equals_host_crops():
     f, _ = rec(page, quads[:40])
     rec.rec_orientation_fallback, rec.device_crops = False, False
     assert e.contents == f.contents and np.allclose(e.scores, f.scores, atol=1e-6)
+    # source_downscale: big lines are cut from pyramid levels 2 / 1 / 1 (the last one is vertical text), odd page size
+    big = [[[100, 100], [900, 100], [900, 240], [100, 240]], [[50, 300], [700, 300], [700, 370], [50, 370]],
+           [[1000, 100], [1100, 100], [1100, 900], [1000, 900]]]
+    odd = np.ascontiguousarray(page[:1199, :1597])
+    rec.source_downscale = True
+    g, _ = rec(odd, quads[:20] + big)
+    rec.device_crops = True
+    h, _ = rec(odd, quads[:20] + big)
+    rec.source_downscale, rec.device_crops = False, False
+    assert g.contents == h.contents and np.allclose(g.scores, h.scores, atol=1e-6)
 
 
 def test_host_canvases_copy():

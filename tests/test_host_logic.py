@@ -389,8 +389,35 @@ def test_recognizer_call_device_crops_with_stub_models(monkeypatch):
                                scratch.ctypes.data_as(vp), canv.ctypes.data_as(vp))
         return FakeDev(canv), cb
 
+    def fake_halve(pages_dev, stream=None):
+        src = np.ascontiguousarray(pages_dev.numpy())
+        n, H, W, _ = src.shape
+        dH, dW = int(np.rint(H * 0.5)), int(np.rint(W * 0.5))
+        dst = np.zeros((n, dH, dW, 3), np.uint8)
+        vp = ctypes.c_void_p
+        for i in range(n):
+            host.crop_host_halve(src[i].ctypes.data_as(vp), W, H, dW, dH, dst[i].ctypes.data_as(vp))
+        return torch.from_numpy(dst)
+
     monkeypatch.setattr(M, "extract_crops_device", fake_extract)
+    monkeypatch.setattr(M, "halve_pages_device", fake_halve)
+    monkeypatch.setattr(M, "concat_device_buffers",
+                        lambda parts: parts[0][0] if len(parts) == 1 else FakeDev(np.concatenate([t.arr[:n] for t, n in parts])))
     page, quads = synthetic_page(5)
+    # source_downscale: lines with a short side of 140 / 70 / 100 px come from pyramid levels 2 / 1 / 1 (the last one is
+    # vertical text); both paths must cut identical canvases from identical pyramid levels
+    big = [[[100, 100], [900, 100], [900, 240], [100, 240]], [[50, 300], [700, 300], [700, 370], [50, 370]],
+           [[1000, 100], [1100, 100], [1100, 900], [1000, 900]]]
+    for fallback in (False, True):
+        ra, rb = make(True), make(False)
+        ra.source_downscale = rb.source_downscale = True
+        ra.rec_orientation_fallback = rb.rec_orientation_fallback = fallback
+        a, _ = ra(page[:1199, :1597], quads[:20] + big)      # odd page size: clipped last column / row of the pyramid
+        b, _ = rb(page[:1199, :1597], quads[:20] + big)
+        assert a.contents == b.contents and a.directions == b.directions and np.allclose(a.scores, b.scores)
+        pages, geoms, levels = ra._device_records(page[:1199, :1597], quads[:20] + big)
+        assert levels.tolist() == [0] * 20 + [2, 1, 1] and sorted(pages) == [0, 1, 2]
+        assert tuple(pages[2].shape) == (1, 300, 399, 3) and geoms["rot"].tolist()[-3:] == [0, 0, 1]
     tall = [[[300, 100], [330, 100], [330, 400], [300, 400]]]      # vertical line: rotated by 90 degrees first
     for fallback in (False, True):
         for qs in (quads[:70] + tall, quads[:30] + [[[-5, 3], [40, 3], [40, 20], [-5, 20]]] + quads[30:60], None):

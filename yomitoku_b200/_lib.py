@@ -97,6 +97,8 @@ def _declare_crops(lib):
     lib.ytk_extract_crops_u8.restype = c_int
     lib.ytk_extract_crops_u8.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                          c_void_p]
+    lib.ytk_halve_pages_u8.restype = c_int
+    lib.ytk_halve_pages_u8.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
 
 
 def tensor_table(state_dict):

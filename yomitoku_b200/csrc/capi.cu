@@ -2,6 +2,7 @@
 #include "../../include/yomitoku_b200.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <map>
 #include <memory>
@@ -309,6 +310,29 @@ int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, 
     }
     if (ytk::launch_extract_crops(pages_dev, H0, W0, dev, n_crops, scratch_dev, canvases_dev, st)) {
         ytk::set_error("ytk_extract_crops_u8: kernel launch failed");
+        return YTK_ERR;
+    }
+    return YTK_OK;
+}
+
+int ytk_halve_pages_u8(const uint8_t* src_dev, int n_pages, int H, int W, uint8_t* dst_dev, int dH, int dW,
+                       void* cuda_stream) {
+    // cv2.resize(..., fx=0.5, fy=0.5): dsize = (cvRound(W * 0.5), cvRound(H * 0.5)), round half to even
+    const int eh = (int)nearbyint(H * 0.5), ew = (int)nearbyint(W * 0.5);
+    if (!src_dev || !dst_dev || n_pages <= 0 || H <= 0 || W <= 0 || dH != eh || dW != ew || dH < 1 || dW < 1) {
+        ytk::set_error("ytk_halve_pages_u8: bad arguments (%d pages %dx%d -> %dx%d, expected %dx%d)", n_pages, H, W, dH, dW,
+                       eh, ew);
+        return YTK_ERR;
+    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, src_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        ytk::set_error("ytk_halve_pages_u8: src_dev is not a device pointer");
+        return YTK_ERR;
+    }
+    cudaSetDevice(attr.device);
+    if (ytk::launch_halve_pages(src_dev, n_pages, H, W, dst_dev, dH, dW, static_cast<cudaStream_t>(cuda_stream))) {
+        ytk::set_error("ytk_halve_pages_u8: kernel launch failed");
         return YTK_ERR;
     }
     return YTK_OK;

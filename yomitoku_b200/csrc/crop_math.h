@@ -227,6 +227,28 @@ YTK_HD void area_pixel(const uint8_t* src, int sw, int sh, int dw, int dh, int d
     for (int c = 0; c < 3; ++c) out[c] = sat_u8(round_half_even_f(sum[c]));
 }
 
+// Pixel (dx, dy) of cv2.resize(src [sh][sw][3], None, fx=0.5, fy=0.5, INTER_AREA): one level of the source_downscale
+// pyramid (reference data/dataset.py:64-86).  dw = cvRound(sw * 0.5), dh = cvRound(sh * 0.5) (round half to even).
+// OpenCV's integer-ratio path: full 2x2 cells round half up ((sum + 2) >> 2); the clipped last column / row of an odd
+// size averages the pixels that exist, rint((float)sum / count).
+YTK_HD void halve_pixel(const uint8_t* src, int sw, int sh, int dx, int dy, uint8_t* out) {
+    const int sx0 = 2 * dx, sy0 = 2 * dy;
+    if (sy0 + 2 <= sh && dx < sw / 2) {
+        const uint8_t* p = src + ((long long)sy0 * sw + sx0) * 3;
+        const uint8_t* q = p + (long long)sw * 3;
+        for (int c = 0; c < 3; ++c) out[c] = (uint8_t)((p[c] + p[3 + c] + q[c] + q[3 + c] + 2) >> 2);
+        return;
+    }
+    int sum[3] = {0, 0, 0}, count = 0;
+    for (int sy = 0; sy < 2 && sy0 + sy < sh; ++sy)
+        for (int sx = 0; sx < 2 && sx0 + sx < sw; ++sx) {
+            const uint8_t* p = src + ((long long)(sy0 + sy) * sw + sx0 + sx) * 3;
+            sum[0] += p[0]; sum[1] += p[1]; sum[2] += p[2];
+            ++count;
+        }
+    for (int c = 0; c < 3; ++c) out[c] = count ? sat_u8(round_half_even_f((float)sum[c] / (float)count)) : (uint8_t)0;
+}
+
 // Canvas pixel (cx, cy) of crop g: the resized content top-left, black elsewhere.
 YTK_HD void canvas_store(const CropGeom& g, const uint8_t* scratch, int cx, int cy, uint8_t* canvases) {
     uint8_t v[3] = {0, 0, 0};

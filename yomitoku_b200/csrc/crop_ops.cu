@@ -7,6 +7,7 @@
 //   crop_warp_kernel    cv2.warpPerspective (bilinear, 1/32-px fixed point, zero border outside the quad's bounding
 //                       box) + the 90-degree rotation of tall crops -> rectified RGB ROI in a scratch buffer
 //   crop_canvas_kernel  cv2.resize(INTER_AREA) of the ROI (shrinking only) pasted top-left on a black canvas
+//   halve_pages_kernel  one level of the source_downscale pyramid: cv2.resize(page, None, fx=0.5, fy=0.5, INTER_AREA)
 //
 // The arithmetic lives in crop_math.h and is compiled for the host as well (oracle/crop_host.cpp), where the CPU tests
 // pin it bit for bit against OpenCV.  This file MUST be compiled with --fmad=false (yomitoku_b200/build.py): OpenCV's
@@ -50,6 +51,25 @@ __global__ void __launch_bounds__(kCanvasThreads) crop_canvas_kernel(const CropG
         const int cy = p / g.canvas_w;
         canvas_store(g, scratch, p - cy * g.canvas_w, cy, canvases);
     }
+}
+
+__global__ void halve_pages_kernel(const uint8_t* __restrict__ src, int n, int sh, int sw, uint8_t* __restrict__ dst,
+                                   int dh, int dw) {
+    const long long total = (long long)n * dh * dw;
+    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int x = (int)(idx % dw);
+    const int y = (int)((idx / dw) % dh);
+    const long long img = idx / ((long long)dw * dh);
+    halve_pixel(src + img * sh * sw * 3, sw, sh, x, y, dst + idx * 3);
+}
+
+int launch_halve_pages(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st) {
+    const long long total = (long long)n * dh * dw;
+    if (total <= 0) return 0;
+    halve_pages_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, n, sh, sw, dst, dh, dw);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
 }
 
 int launch_extract_crops(const uint8_t* pages, int H0, int W0, const CropGeom* geoms_dev, int n_crops,

@@ -12,4 +12,8 @@ namespace ytk {
 int launch_extract_crops(const uint8_t* pages, int H0, int W0, const CropGeom* geoms_dev, int n_crops,
                          uint8_t* scratch, uint8_t* canvases, cudaStream_t st);
 
+// src [n][sh][sw][3] -> dst [n][dh][dw][3] = cv2.resize(page, None, fx=0.5, fy=0.5, INTER_AREA); dh / dw = cvRound(sh / 2),
+// cvRound(sw / 2) (checked by the caller).
+int launch_halve_pages(const uint8_t* src, int n, int sh, int sw, uint8_t* dst, int dh, int dw, cudaStream_t st);
+
 }  // namespace ytk

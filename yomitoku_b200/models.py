@@ -116,6 +116,27 @@ def extract_crops_device(pages_dev, geoms, stream=None):
     return canv, total
 
 
+def halve_pages_device(pages_dev, stream=None):
+    """One level of the source_downscale pyramid on the GPU (C ABI ytk_halve_pages_u8): (n, H, W, 3) uint8 cuda tensor ->
+    (n, cvRound(H / 2), cvRound(W / 2), 3), equal to cv2.resize(page, None, fx=0.5, fy=0.5, INTER_AREA) per page."""
+    n, H, W, _ = pages_dev.shape
+    dH, dW = int(np.rint(H * 0.5)), int(np.rint(W * 0.5))      # round half to even, like cvRound
+    if dH < 1 or dW < 1:
+        raise ValueError("halve_pages_device: a %dx%d page cannot be halved" % (H, W))
+    ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(pages_dev.device)
+    with ctx:
+        out = torch.empty((n, dH, dW, 3), dtype=torch.uint8, device=pages_dev.device)
+    _lib.check(_lib.lib().ytk_halve_pages_u8(pages_dev.data_ptr(), n, H, W, out.data_ptr(), dH, dW, _stream_ptr(stream)))
+    return out
+
+
+def concat_device_buffers(parts):
+    """parts: list of (flat uint8 cuda tensor, used bytes) -> one flat uint8 tensor holding them back to back."""
+    if len(parts) == 1:
+        return parts[0][0]
+    return torch.cat([t[:n] for t, n in parts])
+
+
 # ======================================================================================================== DBNet
 def _dbnet_random_state_dict(seed=0):
     """Random init with the reference's key set (DBNet(cfg) with from_pretrained=False, base.py:84-86)."""

@@ -22,7 +22,7 @@ from .base import BaseModelCatalog, BaseModule
 from .config import (TextRecognizerPARSeqConfig, TextRecognizerPARSeqLargeV41Config, TextRecognizerPARSeqSmallConfig,
                      TextRecognizerPARSeqTinyConfig, TextRecognizerPARSeqTinyDynwV4Config,
                      TextRecognizerPARSeqV2Config)
-from .data import ParseqDataset, crop_geometry, resize_with_padding
+from .data import CROP_GEOM_DTYPE, ParseqDataset, _calc_source_levels, crop_geometry, resize_with_padding
 from .models import PARSeq
 from .postprocessor import ParseqTokenizer as Tokenizer
 from .schemas import TextRecognizerSchema
@@ -101,8 +101,8 @@ class TextRecognizer(BaseModule):
         self.num_parallel_batches = num_parallel_batches
         self.source_downscale = source_downscale
         # device-side crop extraction (csrc/crop_ops.cu, bit-exact with the OpenCV path): the page goes to HBM once and
-        # the canvases are cut there, including the orientation fallback's 180-degree second look.  Not used with
-        # source_downscale (the pyramid levels are built with cv2 on the host).
+        # the canvases are cut there - including the orientation fallback's 180-degree second look and the
+        # source_downscale pyramid.
         self.device_crops = os.environ.get("YTK_DEVICE_CROPS", "0") == "1"
         self.model.to(self.device)
 
@@ -197,22 +197,33 @@ class TextRecognizer(BaseModule):
         import torch
         return torch.from_numpy(np.ascontiguousarray(img))[None].to("cuda")
 
-    def _run_records(self, page_dev, sel, padded, group, n_groups):
-        """Cuts the crops of the records `sel` (already in packing order) on the GPU and runs them as one packed call;
-        padded[k] / group[k] = padded width and mini-batch index of record k.  Returns (ids, probs) with the positions
-        a `refine_iters == 0` model never produced filled like the host path does."""
+    def _run_records(self, pages, sel, levels, padded, group, n_groups):
+        """Cuts the crops of the records `sel` (already in packing order) on the GPU and runs them as one packed call.
+        pages[k] = the page at pyramid level k (cuda tensor), levels[r] = level of record r; padded[r] / group[r] =
+        padded width and mini-batch index of record r.  Returns (ids, probs) with the positions a `refine_iters == 0`
+        model never produced filled like the host path does."""
         from . import _lib, models
         n = len(sel)
-        canv, total = models.extract_crops_device(page_dev, sel)
+        levels = np.asarray(levels, np.int64)
+        parts, base = [], 0
+        pix_off = np.zeros(n, np.int64)
+        for k in sorted(set(levels.tolist())):          # one extraction per pyramid level (a level is one "page" size)
+            idx = np.nonzero(levels == k)[0]
+            sub = sel[idx].copy()
+            canv, total = models.extract_crops_device(pages[k], sub)
+            pix_off[idx] = base + sub["pix_off"]
+            parts.append((canv, total))
+            base += total
+        canv = models.concat_device_buffers(parts)
         ph, pw = self._cfg.encoder.patch_size
         gh = self._cfg.data.img_size[0] // ph
         wp = np.asarray(padded, np.int64)
         ntok = gh * (wp // pw)
         descs = np.zeros(n, dtype=np.dtype(_lib.YtkCrop))
-        descs["pix_off"], descs["w"], descs["wp"] = sel["pix_off"], sel["canvas_w"], wp
+        descs["pix_off"], descs["w"], descs["wp"] = pix_off, sel["canvas_w"], wp
         descs["tok_off"], descs["ntok"] = np.cumsum(ntok) - ntok, ntok
         descs["group"] = group
-        ids, probs, glen = self.model.run_packed_ptr(canv.data_ptr(), 1, total, descs, n, n_groups)
+        ids, probs, glen = self.model.run_packed_ptr(canv.data_ptr(), 1, base, descs, n, n_groups)
         if self.model.refine_iters == 0:
             for k in range(n):
                 L = int(glen[group[k]])
@@ -220,13 +231,39 @@ class TextRecognizer(BaseModule):
                 probs[k, L:] = 1.0
         return ids, probs
 
+    def _device_records(self, img, points):
+        """Page (pyramid) on the device + one crop record per valid quad, in quad order: what ParseqDataset.__init__ does
+        (reference data/dataset.py:45-95) without touching a pixel on the host.  With source_downscale a quad whose short
+        side is >= 2^k * 32 px is cut from pyramid level k with its coordinates divided by 2^k (:26-41, 64-86)."""
+        from . import models
+        size = self._cfg.data.img_size
+        pages = {0: self._upload_page(img)}
+        quad_levels = np.zeros(len(points), dtype=int)
+        if self.source_downscale and len(points) > 0:
+            quad_levels = _calc_source_levels(points, size[0])
+            for k in range(1, int(quad_levels.max()) + 1):
+                pages[k] = models.halve_pages_device(pages[k - 1])
+        rows, levels, keep = [], [], []
+        for k in sorted(set(quad_levels.tolist())):
+            idx = np.nonzero(quad_levels == k)[0]
+            quads = [points[i] if k == 0 else (np.asarray(points[i], dtype=np.float32) / (2.0 ** k)).tolist() for i in idx]
+            g, kept = crop_geometry(tuple(pages[k].shape[1:3]), quads, size, self.dynamic_width)
+            rows += list(g)
+            levels += [k] * len(g)
+            keep += [int(idx[j]) for j in kept]
+        order = np.argsort(np.asarray(keep, np.int64), kind="stable")
+        geoms = np.zeros(len(rows), dtype=CROP_GEOM_DTYPE)
+        for r, o in enumerate(order):
+            geoms[r] = rows[o]
+        return pages, geoms, np.asarray(levels, np.int64)[order]
+
     def _call_device_crops(self, img, points):
         """`__call__` with the crops cut on the GPU: same order / plan / pairing decisions as the host path, taken
         from the crop records (canvas and content widths follow from the quads alone)."""
         if points is None:
             h, w = img.shape[:2]
             points = [[[0, 0], [w, 0], [w, h], [0, h]]]
-        geoms, keep = crop_geometry(img.shape, points, self._cfg.data.img_size, self.dynamic_width)
+        pages, geoms, levels = self._device_records(img, points)
         n = len(geoms)
         if n == 0:
             return TextRecognizerSchema(contents=[], scores=[], points=points, directions=[])
@@ -239,10 +276,9 @@ class TextRecognizer(BaseModule):
         plan = plan_mini_batches(widths, order, self.dynamic_width, self._cfg.data.batch_size,
                                  getattr(self._cfg.data, "width_budget", None),
                                  getattr(self._cfg.data, "max_batch_size", None))
-        flat = [i for b in plan for i in b]
+        flat = np.asarray([i for b in plan for i in b], np.int64)
         padded, group = self._collate_widths(widths, plan)
-        page_dev = self._upload_page(img)
-        ids, probs = self._run_records(page_dev, geoms[np.asarray(flat, np.int64)].copy(), [padded[i] for i in flat],
+        ids, probs = self._run_records(pages, geoms[flat].copy(), levels[flat], [padded[i] for i in flat],
                                        [group[i] for i in flat], len(plan))
         pts = [points[i] for i in order] if order is not None else points
         p, s, d = self.postprocess_ids(ids, probs, pts[:n])
@@ -250,10 +286,10 @@ class TextRecognizer(BaseModule):
             inverse = np.argsort(order)
             p, s, d = [p[i] for i in inverse], [s[i] for i in inverse], [d[i] for i in inverse]
         if self.rec_orientation_fallback:
-            self._device_orientation_fallback(page_dev, geoms, points, p, s, d)
+            self._device_orientation_fallback(pages, geoms, levels, points, p, s, d)
         return TextRecognizerSchema(contents=p, scores=s, points=points, directions=d)
 
-    def _device_orientation_fallback(self, page_dev, geoms, points, preds, scores, directions):
+    def _device_orientation_fallback(self, pages, geoms, levels, points, preds, scores, directions):
         """`_apply_orientation_fallback` (reference text_recognizer.py:319-350) with the second look cut on the GPU: the
         same rectified crop rotated by 180 degrees (record bit `rot & 2`) on the fixed-width canvas, in chunks of
         `batch_size` (a fixed-width tensor in the reference: :205-210)."""
@@ -265,7 +301,8 @@ class TextRecognizer(BaseModule):
         sel["canvas_w"] = self._cfg.data.img_size[1]
         bs = self._cfg.data.batch_size
         group = [k // bs for k in range(len(retry))]
-        ids, probs = self._run_records(page_dev, sel, sel["canvas_w"].tolist(), group, group[-1] + 1)
+        ids, probs = self._run_records(pages, sel, levels[np.asarray(retry, np.int64)], sel["canvas_w"].tolist(), group,
+                                       group[-1] + 1)
         r_preds, r_scores, r_dirs = self.postprocess_ids(ids, probs, [points[i] for i in retry])
         for j, idx in enumerate(retry):
             if r_scores[j] > scores[idx] and r_scores[j] >= self.rec_orientation_fallback_thresh:
@@ -273,7 +310,7 @@ class TextRecognizer(BaseModule):
 
     def __call__(self, img, points=None, vis=None):
         """img: BGR page; points: list of quads (4 clockwise points).  Returns (TextRecognizerSchema, vis)."""
-        if self.device_crops and not self.source_downscale:
+        if self.device_crops:
             results = self._call_device_crops(img, points)
             if self.visualize and vis is None:
                 vis = img.copy()
