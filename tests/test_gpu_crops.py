@@ -216,3 +216,32 @@ def test_host_canvases_copy():
     for st in (None, s):
         h = _HostCanvases(t, st)
         assert h.np.dtype == np.uint8 and np.array_equal(h.np, t.cpu().numpy())
+
+
+def test_batched_ocr_device_crops_with_source_downscale():
+    """BatchedOCR with source_downscale: big lines come from pyramid levels built on the GPU for the whole batch; the
+    result must equal the host-crop path (OpenCV pyramid in the workers)."""
+    from yomitoku_b200.pipeline import BatchedOCR
+    from yomitoku_b200.synth import synthetic_page
+    o = _ocr()
+    o.recognizer.source_downscale = True
+    big = [[[100, 100], [900, 100], [900, 240], [100, 240]], [[50, 300], [700, 300], [700, 370], [50, 370]],
+           [[1000, 100], [1100, 100], [1100, 900], [1000, 900]]]
+    pages, quads = [], []
+    for i in range(3):
+        p, q = synthetic_page(160 + i)
+        pages.append(p)
+        quads.append(q[:25] + big[i:] + q[25:40])
+    host = BatchedOCR(o.detector, o.recognizer, workers=2, det_batch=2, device_crops=False)
+    dev = BatchedOCR(o.detector, o.recognizer, workers=2, det_batch=2, device_crops=True)
+    try:
+        ref = host(pages, quads_override=quads)
+        got = dev(pages, quads_override=quads)
+    finally:
+        host.close()
+        dev.close()
+        o.recognizer.source_downscale = False
+    for r, g, q in zip(ref, got, quads):
+        assert len(r.words) == len(g.words) == len(q)
+        assert [w.content for w in r.words] == [w.content for w in g.words]
+        assert np.allclose([w.rec_score for w in r.words], [w.rec_score for w in g.words], atol=1e-6)

@@ -416,8 +416,10 @@ def test_recognizer_call_device_crops_with_stub_models(monkeypatch):
         b, _ = rb(page[:1199, :1597], quads[:20] + big)
         assert a.contents == b.contents and a.directions == b.directions and np.allclose(a.scores, b.scores)
         pages, geoms, levels = ra._device_records(page[:1199, :1597], quads[:20] + big)
-        assert levels.tolist() == [0] * 20 + [2, 1, 1] and sorted(pages) == [0, 1, 2]
-        assert tuple(pages[2].shape) == (1, 300, 399, 3) and geoms["rot"].tolist()[-3:] == [0, 0, 1]
+        assert levels.tolist() == [0] * 20 + [2, 1, 1] and geoms["rot"].tolist()[-3:] == [0, 0, 1]
+        M.extract_crops_pyramid(pages, geoms, levels)
+        assert sorted(pages) == [0, 1, 2] and tuple(pages[2].shape) == (1, 300, 399, 3)
+        assert D.pyramid_shapes((1199, 1597), 2) == [(1199, 1597), (600, 798), (300, 399)]
     tall = [[[300, 100], [330, 100], [330, 400], [300, 400]]]      # vertical line: rotated by 90 degrees first
     for fallback in (False, True):
         for qs in (quads[:70] + tall, quads[:30] + [[[-5, 3], [40, 3], [40, 20], [-5, 20]]] + quads[30:60], None):
@@ -431,3 +433,89 @@ def test_recognizer_call_device_crops_with_stub_models(monkeypatch):
             if fallback and qs is not None:     # the second look really replaced some results
                 c, _ = make(False)(page, qs)
                 assert 0 < sum(x != y for x, y in zip(b.contents, c.contents)) < len(b.contents)
+
+
+def test_batched_pipeline_device_crops_source_downscale_with_stub_models(monkeypatch):
+    """CPU: BatchedOCR with device_crops AND source_downscale: the workers return records + pyramid levels, the levels
+    are built "on the device" (stand-in: the product's halve_pixel compiled for the host) for the whole batch, one
+    extraction per level; every word must get the canvas ParseqDataset(source_downscale=True) cuts for it."""
+    import ctypes
+
+    from oracle import build_crop_host
+    from yomitoku_b200 import models as M
+    from yomitoku_b200.data import ParseqDataset, layout_crop_buffers
+    from yomitoku_b200.pipeline import BatchedOCR
+
+    host = ctypes.CDLL(build_crop_host.build())
+    det = TextDetector(from_pretrained=False, device="cpu")
+    rec = TextRecognizer(model_name="parseq-tiny-dynw-v4", from_pretrained=False, device="cpu", dynamic_width=True,
+                         batch_bucketing=True, source_downscale=True)
+    det.model.input_size = lambda h, w: (1184, 1600)
+    det.model.detect_pages_u8 = lambda pages, out=None, stream=None: out
+    S = rec.model.max_label_length + 1
+    big = [[[100, 100], [900, 100], [900, 240], [100, 240]], [[50, 300], [700, 300], [700, 370], [50, 370]],
+           [[1000, 100], [1100, 100], [1100, 900], [1000, 900]]]
+    pages, quads = [], []
+    for i in range(3):
+        p, q = synthetic_page(120 + i)
+        pages.append(p)
+        quads.append(q[:25] + big[i:] + q[25:40])
+
+    class FakeDev:
+        def __init__(self, arr):
+            self.arr = arr
+
+        def data_ptr(self):
+            return self.arr.ctypes.data
+
+    vp = ctypes.c_void_p
+
+    def fake_extract(pages_dev, geoms, stream=None):
+        sb, cb = layout_crop_buffers(geoms)
+        scratch, canv = np.zeros(max(sb, 1), np.uint8), np.full(max(cb, 1), 99, np.uint8)
+        pg = np.ascontiguousarray(pages_dev.numpy())
+        for i in sorted(set(geoms["page"].tolist())):
+            m = geoms["page"] == i
+            sel = np.ascontiguousarray(geoms[m])
+            sel["page"] = 0
+            host.crop_host_extract(pg[i].ctypes.data_as(vp), pg.shape[1], pg.shape[2], sel.ctypes.data_as(vp), len(sel),
+                                   scratch.ctypes.data_as(vp), canv.ctypes.data_as(vp))
+        return FakeDev(canv), cb
+
+    def fake_halve(pages_dev, stream=None):
+        src = np.ascontiguousarray(pages_dev.numpy())
+        n, H, W, _ = src.shape
+        dH, dW = int(np.rint(H * 0.5)), int(np.rint(W * 0.5))
+        dst = np.zeros((n, dH, dW, 3), np.uint8)
+        for i in range(n):
+            host.crop_host_halve(src[i].ctypes.data_as(vp), W, H, dW, dH, dst[i].ctypes.data_as(vp))
+        return torch.from_numpy(dst)
+
+    def fake_ptr(ptr, on_device, total, descs, n, n_groups, stream=None):
+        raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
+        ids = np.zeros((n, S), np.int32)
+        for r, d in enumerate(descs):
+            c = raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3].astype(np.int64)
+            ids[r, 0] = 1 + int((c * (1 + np.arange(c.size) % 251)).sum()) % 7000
+        return ids, np.full((n, S), 0.5, np.float32), np.full((n_groups,), S, np.int32)
+
+    monkeypatch.setattr(M, "extract_crops_device", fake_extract)
+    monkeypatch.setattr(M, "halve_pages_device", fake_halve)
+    monkeypatch.setattr(M, "concat_device_buffers",
+                        lambda parts: parts[0][0] if len(parts) == 1 else FakeDev(np.concatenate([t.arr[:n] for t, n in parts])))
+    rec.model.run_packed_ptr = fake_ptr
+    ocr = BatchedOCR(det, rec, workers=2, det_batch=2, device_crops=True)
+    ocr._upload_pages = lambda stage, stream=None: stage.clone()
+    assert ocr.device_crops
+    try:
+        got = ocr(pages, quads_override=quads)
+    finally:
+        ocr.close()
+    for i in range(3):
+        ds = ParseqDataset(rec._cfg, pages[i], quads[i], num_workers=1, dynamic_width=True, source_downscale=True)
+        assert len(got[i].words) == len(ds) == len(quads[i])
+        expect = []
+        for c in ds.data:
+            v = c.reshape(-1).astype(np.int64)
+            expect.append(rec.tokenizer._itos[1 + int((v * (1 + np.arange(v.size) % 251)).sum()) % 7000])
+        assert [w.content[0] for w in got[i].words] == [unicodedata_nfkc(e)[0] for e in expect]

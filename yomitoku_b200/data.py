@@ -176,6 +176,40 @@ def crop_geometry(img_shape, quads, target_size, dynamic_width, page=0, align=8,
     return out[:k], keep
 
 
+def pyramid_shapes(img_shape, max_level):
+    """(H, W) of the source_downscale pyramid levels 0..max_level: each level is cv2.resize(prev, None, fx=0.5, fy=0.5),
+    i.e. (cvRound(H / 2), cvRound(W / 2)) with round-half-to-even (reference data/dataset.py:76-86)."""
+    shapes = [(int(img_shape[0]), int(img_shape[1]))]
+    for _ in range(max_level):
+        h, w = shapes[-1]
+        shapes.append((int(np.rint(h * 0.5)), int(np.rint(w * 0.5))))
+    return shapes
+
+
+def crop_records(img_shape, quads, target_size, dynamic_width, source_downscale=False, page=0):
+    """Crop records of one page in quad order, what `ParseqDataset.__init__` decides per quad (reference
+    data/dataset.py:45-95) without touching a pixel: with `source_downscale` a quad whose short side is >= 2^k * 32 px is
+    cut from pyramid level k with its coordinates divided by 2^k as float32 (:26-41, 64-86).
+    Returns (geoms, levels, keep): CROP_GEOM_DTYPE records of the valid quads, their pyramid level, their quad index."""
+    quad_levels = np.zeros(len(quads), dtype=int)
+    if source_downscale and len(quads) > 0:
+        quad_levels = _calc_source_levels(quads, target_size[0])
+    shapes = pyramid_shapes(img_shape, int(quad_levels.max()) if len(quads) else 0)
+    rows, levels, keep = [], [], []
+    for k in sorted(set(quad_levels.tolist())):
+        idx = np.nonzero(quad_levels == k)[0]
+        qs = [quads[i] if k == 0 else (np.asarray(quads[i], dtype=np.float32) / (2.0 ** k)).tolist() for i in idx]
+        g, kept = crop_geometry(shapes[k], qs, target_size, dynamic_width, page=page)
+        rows += list(g)
+        levels += [k] * len(g)
+        keep += [int(idx[j]) for j in kept]
+    order = np.argsort(np.asarray(keep, np.int64), kind="stable")
+    geoms = np.zeros(len(rows), dtype=CROP_GEOM_DTYPE)
+    for r, o in enumerate(order):
+        geoms[r] = rows[o]
+    return geoms, np.asarray(levels, np.int64)[order], [keep[o] for o in order]
+
+
 def layout_crop_buffers(geoms):
     """Fills roi_off / pix_off (crops packed back to back) and returns (scratch_bytes, canvas_bytes)."""
     roi = geoms["w"].astype(np.int64) * geoms["h"] * 3

@@ -130,6 +130,30 @@ def halve_pages_device(pages_dev, stream=None):
     return out
 
 
+def extract_crops_pyramid(pages, geoms, levels, stream=None):
+    """`extract_crops_device` for records that live on different pyramid levels (source_downscale).  pages: dict
+    level -> (n, H_k, W_k, 3) cuda tensor; missing levels are built on demand by halving the level below (the dict is
+    filled in place).  geoms / levels: records in packing order and their levels.  Returns (canvases, total bytes,
+    pix_off): one flat buffer, and every record's canvas offset in it (one extraction per level, back to back)."""
+    levels = np.asarray(levels, np.int64)
+    n = len(geoms)
+    pix_off = np.zeros(n, np.int64)
+    parts, base = [], 0
+    for k in sorted(set(levels.tolist())):
+        for j in range(1, k + 1):
+            if j not in pages:
+                pages[j] = halve_pages_device(pages[j - 1], stream)
+        idx = np.nonzero(levels == k)[0]
+        sub = np.ascontiguousarray(geoms[idx])
+        canv, total = extract_crops_device(pages[k], sub, stream)
+        pix_off[idx] = base + sub["pix_off"]
+        parts.append((canv, total))
+        base += total
+    if not parts:
+        raise ValueError("extract_crops_pyramid: no records")
+    return concat_device_buffers(parts), base, pix_off
+
+
 def concat_device_buffers(parts):
     """parts: list of (flat uint8 cuda tensor, used bytes) -> one flat uint8 tensor holding them back to back."""
     if len(parts) == 1:

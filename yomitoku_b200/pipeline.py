@@ -15,7 +15,7 @@ from concurrent.futures import ProcessPoolExecutor
 
 import numpy as np
 
-from .data import CROP_GEOM_DTYPE, ParseqDataset, crop_geometry, layout_crop_buffers
+from .data import CROP_GEOM_DTYPE, ParseqDataset, crop_records
 from .ocr import ocr_aggregate
 from .postprocessor import DBnetPostProcessor
 from .schemas import OCRSchema, TextDetectorSchema, TextRecognizerSchema
@@ -140,9 +140,9 @@ def _host_stage(args):
     t1 = time.perf_counter()
     if geom_only:
         if not len(quads):
-            return quads, scores, np.zeros(0, CROP_GEOM_DTYPE), [], 0
-        geoms, _ = crop_geometry(page.shape, quads, _W["cfg"].data.img_size, _W["dyn"])
-        return quads, scores, geoms, geoms["cw"].tolist(), len(geoms), (t0, t1, time.perf_counter())
+            return quads, scores, (np.zeros(0, CROP_GEOM_DTYPE), np.zeros(0, np.int64)), [], 0
+        geoms, levels, _ = crop_records(page.shape, quads, _W["cfg"].data.img_size, _W["dyn"], _W["sd"])
+        return quads, scores, (geoms, levels), geoms["cw"].tolist(), len(geoms), (t0, t1, time.perf_counter())
     ds = ParseqDataset(_W["cfg"], page, quads if len(quads) else [], num_workers=1, dynamic_width=_W["dyn"],
                        source_downscale=_W["sd"]) if len(quads) else None
     if ds is None:
@@ -194,8 +194,9 @@ class _PageGeoms:
     """Crops of one page that exist only as ytk_crop_geom records (device-side extraction): `widths` are the canvas
     widths the crops will have, `base` the index of the page's first record in the step's record array."""
 
-    def __init__(self, geoms, base):
+    def __init__(self, geoms, base, levels=None):
         self.geoms = geoms
+        self.levels = levels if levels is not None else np.zeros(len(geoms), np.int64)   # source_downscale pyramid level
         self.base = base
         self.widths = geoms["canvas_w"].tolist()
         self.height = int(geoms["canvas_h"][0]) if len(geoms) else 32
@@ -209,11 +210,11 @@ class BatchedOCR:
         self.detector = detector
         self.recognizer = recognizer
         # device-side crop extraction (csrc/crop_ops.cu): pages stay in HBM after detection, the host stage only
-        # produces quads + per-crop records, the canvases are cut on the GPU (bit-exact with the OpenCV path).  Not
-        # available with source_downscale (the pyramid levels are host images).
+        # produces quads + per-crop records, the canvases are cut on the GPU (bit-exact with the OpenCV path; with
+        # source_downscale the pyramid levels are built there too)
         if device_crops is None:
             device_crops = os.environ.get("YTK_DEVICE_CROPS", "0") == "1"
-        self.device_crops = bool(device_crops) and not getattr(recognizer, "source_downscale", False)
+        self.device_crops = bool(device_crops)
         self.det_batch = det_batch
         self.max_tokens = max_tokens
         self.workers = workers if workers is not None else max(1, min(32, (os.cpu_count() or 2) - 2))
@@ -385,37 +386,43 @@ class BatchedOCR:
             start = end
         return out
 
-    def _run_groups_dev(self, groups, geoms, pages_dev, stream=None):
+    def _run_groups_dev(self, groups, geoms, pages_dev, stream=None, levels=None):
         """Groups whose crops exist only as records: groups = (widths, padded widths, record indices into `geoms`).
         Groups recognised on this rank are cut on the device and never leave HBM (`_run_groups_dev_local`).  With
         torch.distributed, only the groups the balancer moves to another rank are cut separately and brought to the
         host (page-locked) for the crop scatter; with balanced ranks nothing moves and no canvas touches PCIe."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return self._run_groups_dev_local(groups, geoms, pages_dev, stream)
-        from .models import extract_crops_device
+            return self._run_groups_dev_local(groups, geoms, pages_dev, stream, levels)
+        from .models import extract_crops_pyramid
+        pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
+        lv = levels if levels is not None else np.zeros(len(geoms), np.int64)
 
         def pixels(ks):
-            sel = geoms[np.concatenate([groups[k][2] for k in ks])].copy()
-            canv, _ = extract_crops_device(pages_dev, sel, stream)
+            idx = np.concatenate([groups[k][2] for k in ks])
+            sel = geoms[idx].copy()
+            canv, _, offs = extract_crops_pyramid(pages, sel, lv[idx], stream)
             host = _HostCanvases(canv, stream).np
             out, j = [], 0
             for k in ks:
-                rows = sel[j:j + len(groups[k][0])]
-                out.append([host[int(r["pix_off"]):int(r["pix_off"]) + int(r["canvas_h"]) * int(r["canvas_w"]) * 3]
-                            .reshape(int(r["canvas_h"]), int(r["canvas_w"]), 3) for r in rows])
-                j += len(rows)
+                m = len(groups[k][0])
+                out.append([host[int(o):int(o) + int(r["canvas_h"]) * int(r["canvas_w"]) * 3]
+                            .reshape(int(r["canvas_h"]), int(r["canvas_w"]), 3) for r, o in zip(sel[j:j + m], offs[j:j + m])])
+                j += m
             return out
 
         return self._run_groups_dist(
             groups, pixels,
-            lambda ks: self._run_groups_dev_local([groups[k] for k in ks], geoms, pages_dev, stream), stream)
+            lambda ks: self._run_groups_dev_local([groups[k] for k in ks], geoms, pages, stream, lv), stream)
 
-    def _run_groups_dev_local(self, groups, geoms, pages_dev, stream=None):
+    def _run_groups_dev_local(self, groups, geoms, pages_dev, stream=None, levels=None):
         """This rank's share of `_run_groups_dev`: the canvases of a <= max_tokens chunk are cut on the device
-        (ytk_extract_crops_u8) in group order and go to PARSeq without leaving HBM."""
+        (ytk_extract_crops_u8, one call per source_downscale pyramid level) in group order and go to PARSeq without
+        leaving HBM."""
         from . import _lib
-        from .models import extract_crops_device
+        from .models import extract_crops_pyramid
+        pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
+        lv = levels if levels is not None else np.zeros(len(geoms), np.int64)
         rec = self.recognizer
         cfg = rec._cfg
         ph, pw = cfg.encoder.patch_size
@@ -430,14 +437,15 @@ class BatchedOCR:
                 tok += gtok[end]
                 end += 1
             chunk = groups[start:end]
-            sel = geoms[np.concatenate([g[2] for g in chunk])].copy()
+            idx = np.concatenate([g[2] for g in chunk])
+            sel = geoms[idx].copy()
             with _span("recognize.crops_device"):
-                canv, total = extract_crops_device(pages_dev, sel, stream)
+                canv, total, offs = extract_crops_pyramid(pages, sel, lv[idx], stream)
             wp = np.concatenate([np.asarray(g[1], np.int64) for g in chunk])
             n = sel.shape[0]
             ntok = gh * (wp // pw)
             descs = np.zeros(n, dtype=dt)
-            descs["pix_off"] = sel["pix_off"]
+            descs["pix_off"] = offs
             descs["w"] = sel["canvas_w"]
             descs["wp"] = wp
             descs["tok_off"] = np.cumsum(ntok) - ntok
@@ -540,7 +548,8 @@ class BatchedOCR:
             orders.append(order)
         if in_dev:
             geoms = np.concatenate([p[0].geoms for p in per_page]) if per_page else np.zeros(0, CROP_GEOM_DTYPE)
-            res = self._run_groups_dev(groups, geoms, pages_dev, stream)
+            levels = np.concatenate([p[0].levels for p in per_page]) if per_page else np.zeros(0, np.int64)
+            res = self._run_groups_dev(groups, geoms, pages_dev, stream, levels)
         else:
             res = self._run_groups(groups, stream, arena if in_arena else None,
                                    per_page[0][0].height if in_arena and per_page else 32)
@@ -662,12 +671,12 @@ class BatchedOCR:
         if handle.pages_dev is not None:
             fixed, base = [], 0
             for i, h in enumerate(host):
-                g = h[2]
+                g, lv = h[2]
                 g["page"] = i
                 if TRACE is not None and len(h) > 5:
                     TRACE.append(("worker.post", "worker", h[5][0], h[5][1]))
                     TRACE.append(("worker.geometry", "worker", h[5][1], h[5][2]))
-                fixed.append((h[0], h[1], _PageGeoms(g, base), h[3], h[4]))
+                fixed.append((h[0], h[1], _PageGeoms(g, base, lv), h[3], h[4]))
                 base += len(g)
             host = fixed
         elif arena is not None:

@@ -22,7 +22,7 @@ from .base import BaseModelCatalog, BaseModule
 from .config import (TextRecognizerPARSeqConfig, TextRecognizerPARSeqLargeV41Config, TextRecognizerPARSeqSmallConfig,
                      TextRecognizerPARSeqTinyConfig, TextRecognizerPARSeqTinyDynwV4Config,
                      TextRecognizerPARSeqV2Config)
-from .data import CROP_GEOM_DTYPE, ParseqDataset, _calc_source_levels, crop_geometry, resize_with_padding
+from .data import ParseqDataset, crop_records, resize_with_padding
 from .models import PARSeq
 from .postprocessor import ParseqTokenizer as Tokenizer
 from .schemas import TextRecognizerSchema
@@ -204,17 +204,7 @@ class TextRecognizer(BaseModule):
         model never produced filled like the host path does."""
         from . import _lib, models
         n = len(sel)
-        levels = np.asarray(levels, np.int64)
-        parts, base = [], 0
-        pix_off = np.zeros(n, np.int64)
-        for k in sorted(set(levels.tolist())):          # one extraction per pyramid level (a level is one "page" size)
-            idx = np.nonzero(levels == k)[0]
-            sub = sel[idx].copy()
-            canv, total = models.extract_crops_device(pages[k], sub)
-            pix_off[idx] = base + sub["pix_off"]
-            parts.append((canv, total))
-            base += total
-        canv = models.concat_device_buffers(parts)
+        canv, base, pix_off = models.extract_crops_pyramid(pages, sel, levels)
         ph, pw = self._cfg.encoder.patch_size
         gh = self._cfg.data.img_size[0] // ph
         wp = np.asarray(padded, np.int64)
@@ -232,30 +222,11 @@ class TextRecognizer(BaseModule):
         return ids, probs
 
     def _device_records(self, img, points):
-        """Page (pyramid) on the device + one crop record per valid quad, in quad order: what ParseqDataset.__init__ does
-        (reference data/dataset.py:45-95) without touching a pixel on the host.  With source_downscale a quad whose short
-        side is >= 2^k * 32 px is cut from pyramid level k with its coordinates divided by 2^k (:26-41, 64-86)."""
-        from . import models
-        size = self._cfg.data.img_size
-        pages = {0: self._upload_page(img)}
-        quad_levels = np.zeros(len(points), dtype=int)
-        if self.source_downscale and len(points) > 0:
-            quad_levels = _calc_source_levels(points, size[0])
-            for k in range(1, int(quad_levels.max()) + 1):
-                pages[k] = models.halve_pages_device(pages[k - 1])
-        rows, levels, keep = [], [], []
-        for k in sorted(set(quad_levels.tolist())):
-            idx = np.nonzero(quad_levels == k)[0]
-            quads = [points[i] if k == 0 else (np.asarray(points[i], dtype=np.float32) / (2.0 ** k)).tolist() for i in idx]
-            g, kept = crop_geometry(tuple(pages[k].shape[1:3]), quads, size, self.dynamic_width)
-            rows += list(g)
-            levels += [k] * len(g)
-            keep += [int(idx[j]) for j in kept]
-        order = np.argsort(np.asarray(keep, np.int64), kind="stable")
-        geoms = np.zeros(len(rows), dtype=CROP_GEOM_DTYPE)
-        for r, o in enumerate(order):
-            geoms[r] = rows[o]
-        return pages, geoms, np.asarray(levels, np.int64)[order]
+        """Page on the device + one crop record per valid quad, in quad order (data.crop_records); the pyramid levels
+        of source_downscale are built on the device when a record needs them."""
+        geoms, levels, _ = crop_records(img.shape, points, self._cfg.data.img_size, self.dynamic_width,
+                                        self.source_downscale)
+        return {0: self._upload_page(img)}, geoms, levels
 
     def _call_device_crops(self, img, points):
         """`__call__` with the crops cut on the GPU: same order / plan / pairing decisions as the host path, taken
