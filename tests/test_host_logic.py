@@ -402,7 +402,8 @@ def test_recognizer_call_device_crops_with_stub_models(monkeypatch):
     monkeypatch.setattr(M, "extract_crops_device", fake_extract)
     monkeypatch.setattr(M, "halve_pages_device", fake_halve)
     monkeypatch.setattr(M, "concat_device_buffers",
-                        lambda parts: parts[0][0] if len(parts) == 1 else FakeDev(np.concatenate([t.arr[:n] for t, n in parts])))
+                        lambda parts, stream=None: parts[0][0] if len(parts) == 1 else
+                        FakeDev(np.concatenate([t.arr[:n] for t, n in parts])))
     page, quads = synthetic_page(5)
     # source_downscale: lines with a short side of 140 / 70 / 100 px come from pyramid levels 2 / 1 / 1 (the last one is
     # vertical text); both paths must cut identical canvases from identical pyramid levels
@@ -502,7 +503,8 @@ def test_batched_pipeline_device_crops_source_downscale_with_stub_models(monkeyp
     monkeypatch.setattr(M, "extract_crops_device", fake_extract)
     monkeypatch.setattr(M, "halve_pages_device", fake_halve)
     monkeypatch.setattr(M, "concat_device_buffers",
-                        lambda parts: parts[0][0] if len(parts) == 1 else FakeDev(np.concatenate([t.arr[:n] for t, n in parts])))
+                        lambda parts, stream=None: parts[0][0] if len(parts) == 1 else
+                        FakeDev(np.concatenate([t.arr[:n] for t, n in parts])))
     rec.model.run_packed_ptr = fake_ptr
     ocr = BatchedOCR(det, rec, workers=2, det_batch=2, device_crops=True)
     ocr._upload_pages = lambda stage, stream=None: stage.clone()

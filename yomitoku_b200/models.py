@@ -151,13 +151,17 @@ def extract_crops_pyramid(pages, geoms, levels, stream=None):
         base += total
     if not parts:
         raise ValueError("extract_crops_pyramid: no records")
-    return concat_device_buffers(parts), base, pix_off
+    return concat_device_buffers(parts, stream), base, pix_off
 
 
-def concat_device_buffers(parts):
-    """parts: list of (flat uint8 cuda tensor, used bytes) -> one flat uint8 tensor holding them back to back."""
+def concat_device_buffers(parts, stream=None):
+    """parts: list of (flat uint8 cuda tensor, used bytes) -> one flat uint8 tensor holding them back to back (the
+    copy is queued on `stream`, like the kernels that filled the parts)."""
     if len(parts) == 1:
         return parts[0][0]
+    if stream is not None:
+        with torch.cuda.stream(stream):
+            return torch.cat([t[:n] for t, n in parts])
     return torch.cat([t[:n] for t, n in parts])
 
 
