@@ -9,7 +9,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from yomitoku_b200 import TextDetector, TextRecognizer, _lib  # noqa: E402
-from yomitoku_b200.data import ParseqDataset, crop_geometry, layout_crop_buffers  # noqa: E402
+from yomitoku_b200.data import ParseqDataset, crop_geometry  # noqa: E402
 from yomitoku_b200.models import extract_crops_device  # noqa: E402
 from yomitoku_b200.synth import synthetic_page  # noqa: E402
 from yomitoku_b200.text_recognizer import plan_mini_batches  # noqa: E402

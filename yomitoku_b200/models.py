@@ -10,7 +10,6 @@ Reference: src/yomitoku/models/dbnet_plus.py:233-246, src/yomitoku/models/parseq
 """
 import ctypes
 import math
-import os
 from collections import OrderedDict
 
 import numpy as np

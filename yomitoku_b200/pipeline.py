@@ -16,9 +16,8 @@ from concurrent.futures import ProcessPoolExecutor
 import numpy as np
 
 from .data import CROP_GEOM_DTYPE, ParseqDataset, crop_records
-from .ocr import ocr_aggregate
 from .postprocessor import DBnetPostProcessor
-from .schemas import OCRSchema, TextDetectorSchema, TextRecognizerSchema
+from .schemas import OCRSchema
 from .text_recognizer import plan_mini_batches
 
 _W = {}
