@@ -105,3 +105,29 @@ def test_batched_ocr_device_crops_with_source_downscale():
         assert len(r.words) == len(g.words) == len(q)
         assert [w.content for w in r.words] == [w.content for w in g.words]
         assert np.allclose([w.rec_score for w in r.words], [w.rec_score for w in g.words], atol=1e-6)
+
+
+def test_batched_ocr_orientation_fallback_equals_per_page_calls():
+    """BatchedOCR honours rec_orientation_fallback (the batch takes the device-crops path, the second look is the same
+    record with `rot |= 2`): per page identical to TextRecognizer.__call__ on the host path with the fallback on."""
+    from yomitoku_b200.pipeline import BatchedOCR
+    from yomitoku_b200.synth import synthetic_page
+    o = _ocr()
+    rec = o.recognizer
+    rec.rec_orientation_fallback, rec.rec_orientation_fallback_thresh = True, 0.9
+    pages, quads = [], []
+    for i in range(2):
+        p, q = synthetic_page(170 + i)
+        pages.append(p)
+        quads.append(q[:60])
+    b = BatchedOCR(o.detector, rec, workers=2, det_batch=2)
+    try:
+        got = b(pages, quads_override=quads)
+    finally:
+        b.close()
+    for i in range(2):
+        rec.device_crops = False
+        single, _ = rec(pages[i], quads[i])
+        assert [w.content for w in got[i].words] == single.contents
+        assert np.allclose([w.rec_score for w in got[i].words], single.scores, atol=1e-6)
+    rec.rec_orientation_fallback = False

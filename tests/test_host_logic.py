@@ -521,3 +521,89 @@ def test_batched_pipeline_device_crops_source_downscale_with_stub_models(monkeyp
             v = c.reshape(-1).astype(np.int64)
             expect.append(rec.tokenizer._itos[1 + int((v * (1 + np.arange(v.size) % 251)).sum()) % 7000])
         assert [w.content[0] for w in got[i].words] == [unicodedata_nfkc(e)[0] for e in expect]
+
+
+def test_batched_pipeline_orientation_fallback_with_stub_models(monkeypatch):
+    """CPU: BatchedOCR honours rec_orientation_fallback (it switches the batch to the device-crops path, where the second
+    look is the same record with `rot |= 2`): per page the words must equal what TextRecognizer.__call__ returns on the
+    host path with the fallback on (stand-in model: ids / score depend on where the pixels are, so a 180-degree turn
+    changes them and some rows really get replaced)."""
+    import ctypes
+
+    from oracle import build_crop_host
+    from yomitoku_b200 import models as M
+    from yomitoku_b200.data import layout_crop_buffers
+    from yomitoku_b200.pipeline import BatchedOCR
+
+    host = ctypes.CDLL(build_crop_host.build())
+    S = 26
+    vp = ctypes.c_void_p
+
+    def checks(raw, descs, n, n_groups):
+        ids = np.zeros((n, S), np.int32)
+        probs = np.ones((n, S), np.float32)
+        for r, d in enumerate(descs):
+            c = raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3].astype(np.int64)
+            h = int((c * (1 + np.arange(c.size) % 251)).sum())
+            ids[r, 0] = 1 + (h * 31 + int(d["wp"]) * 7) % 7000
+            probs[r, 0] = 0.55 + 0.44 * ((h % 1000) / 1000.0)
+        return ids, probs, np.full((n_groups,), S, np.int32)
+
+    class FakeDev:
+        def __init__(self, arr):
+            self.arr = arr
+
+        def data_ptr(self):
+            return self.arr.ctypes.data
+
+    def fake_extract(pages_dev, geoms, stream=None):
+        sb, cb = layout_crop_buffers(geoms)
+        scratch, canv = np.zeros(max(sb, 1), np.uint8), np.full(max(cb, 1), 99, np.uint8)
+        pg = np.ascontiguousarray(pages_dev.numpy())
+        for i in sorted(set(geoms["page"].tolist())):
+            sel = np.ascontiguousarray(geoms[geoms["page"] == i])
+            sel["page"] = 0
+            host.crop_host_extract(pg[i].ctypes.data_as(vp), pg.shape[1], pg.shape[2], sel.ctypes.data_as(vp), len(sel),
+                                   scratch.ctypes.data_as(vp), canv.ctypes.data_as(vp))
+        return FakeDev(canv), cb
+
+    monkeypatch.setattr(M, "extract_crops_device", fake_extract)
+    det = TextDetector(from_pretrained=False, device="cpu")
+    det.model.input_size = lambda h, w: (1184, 1600)
+    det.model.detect_pages_u8 = lambda pages, out=None, stream=None: out
+    rec = TextRecognizer(model_name="parseq-tiny-dynw-v4", from_pretrained=False, device="cpu", dynamic_width=True,
+                         batch_bucketing=True, rec_orientation_fallback=True, rec_orientation_fallback_thresh=0.75)
+
+    def fake_ptr(ptr, on_device, total, descs, n, n_groups, stream=None):
+        raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
+        return checks(raw, descs, n, n_groups)
+
+    def fake_crops(canvases, padded, groups, n_groups):
+        buf, total, descs, _ = rec.model.pack_crops(canvases, padded, groups)
+        return checks(buf.numpy(), [dict(pix_off=d.pix_off, w=d.w, wp=d.wp) for d in descs[:len(canvases)]],
+                      len(canvases), n_groups)
+
+    rec.model.run_packed_ptr = fake_ptr
+    rec.model.recognize_crops = fake_crops
+    pages, quads = [], []
+    for i in range(3):
+        p, q = synthetic_page(130 + i)
+        pages.append(p)
+        quads.append(q[:37] + [[[1000, 100], [1030, 100], [1030, 600], [1000, 600]]])     # + one vertical line
+    ocr = BatchedOCR(det, rec, workers=2, det_batch=2)            # device_crops not requested: the flag switches it on
+    ocr._upload_pages = lambda stage, stream=None: stage.clone()
+    try:
+        got = ocr(pages, quads_override=quads)
+    finally:
+        ocr.close()
+    replaced = 0
+    for i in range(3):
+        rec.device_crops = False
+        single, _ = rec(pages[i], quads[i])                        # host path incl. _apply_orientation_fallback
+        rec.rec_orientation_fallback = False
+        plain, _ = rec(pages[i], quads[i])
+        rec.rec_orientation_fallback = True
+        assert [w.content for w in got[i].words] == single.contents
+        assert np.allclose([w.rec_score for w in got[i].words], single.scores)
+        replaced += sum(a != b for a, b in zip(single.contents, plain.contents))
+    assert replaced > 0

@@ -600,7 +600,9 @@ class BatchedOCR:
         arena, cap = None, self.crop_cap
         h0, w0 = pages[0].shape[:2]
         pages_dev = None
-        if self.device_crops:
+        if self.device_crops or getattr(self.recognizer, "rec_orientation_fallback", False):
+            # (the orientation fallback's second look is implemented on the device-crops path only: its crops are the
+            # same records with one bit set, no rectified images have to come back from the workers)
             # the pages stay in HBM for the crop kernels of this batch; the tensor belongs to the handle (no ring slot
             # to guard) and the detector reads the same copy
             with _span("submit.pages_h2d"):
@@ -698,7 +700,67 @@ class BatchedOCR:
         rec_in = [(h[2], h[3], len(h[0])) for h in host]
         with _span("collect.recognize"):
             rec_out = self.recognize_pooled(rec_in, stream, arena=arena, pages_dev=handle.pages_dev)
+            if handle.pages_dev is not None and getattr(self.recognizer, "rec_orientation_fallback", False):
+                self._orientation_fallback_dev([h[2] for h in host], rec_out, handle.pages_dev, stream)
         return host, rec_out
+
+    def _orientation_fallback_dev(self, page_geoms, rec_out, pages_dev, stream=None):
+        """The recognizer's optional 180-degree second look (reference text_recognizer.py:319-350) for a whole batch:
+        per page, the crops whose score is below the threshold - in detection order, in chunks of `batch_size` like
+        TextRecognizer._apply_orientation_fallback - are cut again on the GPU rotated by 180 degrees on the fixed-width
+        canvas (record bit `rot & 2`); a row of (ids, probs) is replaced when the second look scores higher and reaches
+        the threshold.  rec_out rows are in plan order and are updated in place."""
+        rec = self.recognizer
+        cfg = rec._cfg
+        thresh = rec.rec_orientation_fallback_thresh
+        bs = cfg.data.batch_size
+        groups, owner, retries, geoms2, levels2, base = [], [], [], [], [], 0
+        for pi, (pg, (ids, probs, order)) in enumerate(zip(page_geoms, rec_out)):
+            n = len(pg)
+            retry, pos = [], None
+            if n:
+                _, scores = rec.tokenizer.decode_ids(ids, probs)
+                pos = np.argsort(order) if order is not None else np.arange(n)    # plan position of detection index i
+                retry = [i for i in range(n) if scores[int(pos[i])] < thresh]
+                retries.append((retry, pos, scores))
+            else:
+                retries.append(([], None, []))
+            if not retry:
+                continue
+            sel = pg.geoms[np.asarray(retry, np.int64)].copy()
+            sel["rot"] |= 2
+            sel["canvas_w"] = cfg.data.img_size[1]
+            geoms2.append(sel)
+            levels2.append(pg.levels[np.asarray(retry, np.int64)])
+            w = sel["canvas_w"].tolist()
+            for s0 in range(0, len(retry), bs):
+                e0 = min(len(retry), s0 + bs)
+                groups.append((w[s0:e0], w[s0:e0], base + np.arange(s0, e0, dtype=np.int64)))
+                owner.append(pi)
+            base += len(retry)
+        if not groups:
+            return
+        res = self._run_groups_dev(groups, np.concatenate(geoms2), pages_dev, stream, np.concatenate(levels2))
+        S = cfg.max_label_length + 1
+        for pi, (ids, probs, order) in enumerate(rec_out):
+            mine = [r for r, o in zip(res, owner) if o == pi]
+            if not mine:
+                continue
+            r_ids = np.concatenate([m[0] for m in mine]).copy()
+            r_probs = np.concatenate([m[1] for m in mine]).copy()
+            if rec.model.refine_iters == 0:
+                k = 0
+                for m in mine:
+                    r_ids[k:k + m[0].shape[0], m[2]:] = rec.tokenizer.eos_id
+                    r_probs[k:k + m[0].shape[0], m[2]:] = 1.0
+                    k += m[0].shape[0]
+            _, r_scores = rec.tokenizer.decode_ids(r_ids, r_probs)
+            retry, pos, scores = retries[pi]
+            for j, i in enumerate(retry):
+                k = int(pos[i])
+                if r_scores[j] > scores[k] and r_scores[j] >= thresh:
+                    ids[k, :S] = r_ids[j]
+                    probs[k, :S] = r_probs[j]
 
     def _assemble(self, host, rec_out):
         results = []
