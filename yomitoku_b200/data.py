@@ -88,7 +88,8 @@ def calc_resize_without_padding(img, target_size):
 def _paste(img, target_h, canvas_w, new_h, new_w, background_color):
     resized = cv2.resize(img, (new_w, new_h), interpolation=cv2.INTER_AREA)
     canvas = np.zeros((target_h, canvas_w, 3), dtype=np.uint8)
-    canvas[:, :] = background_color
+    if any(background_color):          # black (the only colour the path uses) is what np.zeros already holds
+        canvas[:, :] = background_color
     canvas[: resized.shape[0], : resized.shape[1], :] = resized
     return canvas
 
