@@ -1,0 +1,108 @@
+"""CPU numerics study for a planned kernel change: is "LayerNorm folded into the consumer
+GEMM" as accurate as what the device does today?
+
+  today :  h = bf16(LN(x));            y = bf16(h @ bf16(W)^T + b)                       (fp32 accumulation)
+  folded:  xb = bf16(x) (raw stream);  y = bf16(rstd * (xb @ bf16(W * g)^T - mean * c1) + c2)
+           c1[n] = sum_k bf16(W * g)[n, k],  c2 = W @ beta + b,  mean / rstd from the fp32 stream
+
+Both emulated in PyTorch on the CPU with the whole PARSeq-large encoder (bf16 operands, fp32 accumulation and residual
+stream, like csrc/parseq_engine.cu), compared with the fp32 oracle: relative error of every block's qkv / fc1 outputs
+and of the final encoder memory.  Run: python experiments/ln_fold_numerics.py [trained-like]
+"""
+import os
+import sys
+
+import torch
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from oracle import parseq as ops  # noqa: E402
+from oracle import weights  # noqa: E402
+
+
+def bf(t):
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
+def lin_today(x, g, b, W, bias, eps=1e-6):
+    h = bf(F.layer_norm(x, (x.shape[-1],), g, b, eps))
+    return bf(F.linear(h, bf(W), bias))
+
+
+def lin_folded(x, g, b, W, bias, eps=1e-6):
+    D = x.shape[-1]
+    mean = x.mean(-1, keepdim=True)
+    var = (x * x).mean(-1, keepdim=True) - mean * mean          # one-pass statistics, as an epilogue would gather them
+    rstd = torch.rsqrt(var + eps)
+    Wg = bf(W * g[None, :])
+    c1 = Wg.sum(1)
+    c2 = F.linear(b[None, :], W)[0] + bias
+    acc = F.linear(bf(x), Wg)
+    return bf(rstd * (acc - mean * c1[None, :]) + c2[None, :])
+
+
+def encoder(sd, spec, images, lin):
+    """oracle.parseq.encoder_forward with the two LN -> linear pairs of every block replaced by `lin` and the other
+    GEMM operands rounded to bf16 (what the device does); returns (memory, per-block qkv, per-block fc1 pre-GELU)."""
+    D, heads = spec.embed_dim, spec.enc_heads
+    hd = D // heads
+    p0 = "encoder."
+    x = F.conv2d(images, sd[p0 + "patch_embed.proj.weight"], sd[p0 + "patch_embed.proj.bias"], stride=spec.patch)
+    B, _, gh, gw = x.shape
+    x = x.flatten(2).transpose(1, 2)
+    fgh, fgw = spec.grid
+    x = x + sd[p0 + "pos_embed"].reshape(1, fgh, fgw, D)[:, :gh, :gw].reshape(1, gh * gw, D)
+    qs, fs = [], []
+    for i in range(spec.enc_depth):
+        p = "%sblocks.%d." % (p0, i)
+        qkv = lin(x, sd[p + "norm1.weight"], sd[p + "norm1.bias"], sd[p + "attn.qkv.weight"], sd[p + "attn.qkv.bias"])
+        qs.append(qkv)
+        q = qkv.reshape(B, -1, 3, heads, hd).permute(2, 0, 3, 1, 4)
+        att = torch.softmax((q[0] @ q[1].transpose(-1, -2)) * (hd ** -0.5), dim=-1) @ q[2]
+        att = bf(att.transpose(1, 2).reshape(B, -1, D))
+        x = x + F.linear(att, bf(sd[p + "attn.proj.weight"]), sd[p + "attn.proj.bias"])
+        f = lin(x, sd[p + "norm2.weight"], sd[p + "norm2.bias"], sd[p + "mlp.fc1.weight"], sd[p + "mlp.fc1.bias"])
+        fs.append(f)
+        x = x + F.linear(bf(F.gelu(f)), bf(sd[p + "mlp.fc2.weight"]), sd[p + "mlp.fc2.bias"])
+    return F.layer_norm(x, (D,), sd[p0 + "norm.weight"], sd[p0 + "norm.bias"], 1e-6), qs, fs
+
+
+def exact(x, g, b, W, bias, eps=1e-6):
+    return F.linear(F.layer_norm(x, (x.shape[-1],), g, b, eps), W, bias)
+
+
+def rel(a, b):
+    return float((a - b).norm() / b.norm())
+
+
+def main():
+    spec = ops.SPECS["parseq-large-v4_1"]
+    trained_like = len(sys.argv) > 1
+    sd = weights.make_parseq_state_dict(spec, seed=5, peaked=True)
+    if trained_like:
+        # what trained ViTs look like and random init does not: LayerNorm gains / shifts away from (1, 0), and a
+        # residual stream with a per-row mean that is not small against its spread (a few "massive" channels)
+        g = torch.Generator().manual_seed(1)
+        for k in list(sd):
+            if k.endswith("norm1.weight") or k.endswith("norm2.weight"):
+                sd[k] = 1.0 + 0.5 * torch.randn(sd[k].shape, generator=g)
+            if k.endswith("norm1.bias") or k.endswith("norm2.bias"):
+                sd[k] = 0.3 * torch.randn(sd[k].shape, generator=g)
+        sd["encoder.pos_embed"] = sd["encoder.pos_embed"].clone()
+        sd["encoder.pos_embed"][..., :4] += 6.0
+    torch.manual_seed(0)
+    images = torch.rand(4, 3, 32, 184) * 2 - 1
+    with torch.inference_mode():
+        m0, q0, f0 = encoder(sd, spec, images, exact)      # fp32 everywhere except the shared bf16 attention/proj/fc2
+        m1, q1, f1 = encoder(sd, spec, images, lin_today)
+        m2, q2, f2 = encoder(sd, spec, images, lin_folded)
+    print("weights:", "trained-like (LN gain/shift, massive channels)" if trained_like else "seeded init (LN gain 1, shift 0)")
+    print("block   qkv today   qkv folded   fc1 today   fc1 folded   (relative Frobenius error vs the fp32-LN run)")
+    for i in range(spec.enc_depth):
+        print("%5d   %.2e    %.2e     %.2e    %.2e" % (i, rel(q1[i], q0[i]), rel(q2[i], q0[i]), rel(f1[i], f0[i]),
+                                                        rel(f2[i], f0[i])))
+    print("encoder memory: today %.3e   folded %.3e" % (rel(m1, m0), rel(m2, m0)))
+
+
+if __name__ == "__main__":
+    main()
