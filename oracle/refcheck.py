@@ -17,6 +17,7 @@ import os
 import sys
 import types
 
+import numpy as np
 import torch
 import torch.nn as nn
 import torch.nn.functional as F
@@ -205,6 +206,89 @@ def build_reference_parseq(spec, sd, charset):
     return m.eval()
 
 
+def build_reference_postprocessor(**kwargs):
+    """The reference's own DBnetPostProcessor (postprocessor/dbnet_postporcessor.py, executed from /root/reference) with
+    the two third-party imports that are not installable offline replaced by this oracle's restatements:
+    `pyclipper.PyclipperOffset` (AddPath(JT_ROUND, ET_CLOSEDPOLYGON) + Execute) -> oracle.pipeline.clipper_offset_box,
+    `shapely.geometry.Polygon(box).area/.length` -> shoelace / perimeter in float64.  Everything else - contour order,
+    minAreaRect corner ordering, box_score_fast, the size / score filters, scaling, rounding, int16 - is the
+    reference's code, so this pins the oracle's control flow of row R3 against it."""
+    from oracle import pipeline as opipe
+
+    pc = types.ModuleType("pyclipper")
+    pc.JT_ROUND, pc.ET_CLOSEDPOLYGON = 1, 0
+
+    class PyclipperOffset:
+        def __init__(self):
+            self.path = None
+
+        def AddPath(self, path, join_type, end_type):
+            assert join_type == pc.JT_ROUND and end_type == pc.ET_CLOSEDPOLYGON
+            self.path = np.asarray(path)
+
+        def Execute(self, delta):
+            return [opipe.clipper_offset_box(self.path, float(delta)).tolist()]
+
+    pc.PyclipperOffset = PyclipperOffset
+    sh, shg = types.ModuleType("shapely"), types.ModuleType("shapely.geometry")
+
+    class Polygon:
+        def __init__(self, pts):
+            self.p = np.asarray(pts, dtype=np.float64)
+
+        @property
+        def area(self):
+            p = self.p
+            return 0.5 * abs(np.dot(p[:, 0], np.roll(p[:, 1], -1)) - np.dot(p[:, 1], np.roll(p[:, 0], -1)))
+
+        @property
+        def length(self):
+            p = self.p
+            return np.sqrt(((p - np.roll(p, -1, axis=0)) ** 2).sum(1)).sum()
+
+    shg.Polygon = Polygon
+    sh.geometry = shg
+    saved = {k: sys.modules.get(k) for k in ("pyclipper", "shapely", "shapely.geometry")}
+    sys.modules.update({"pyclipper": pc, "shapely": sh, "shapely.geometry": shg})
+    try:
+        _pkg("ytk_ref")
+        _pkg("ytk_ref.postprocessor")
+        mod = _load("ytk_ref.postprocessor.dbnet_postporcessor", "postprocessor/dbnet_postporcessor.py",
+                    "ytk_ref.postprocessor")
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return mod.DBnetPostProcessor(**kwargs)
+
+
+def reference_postprocess(post, prob, ori_hw):
+    """Runs the reference post-processor on one (H, W) float32 probability map like TextDetector.__call__ does
+    (text_detector.py:129-131: preds["binary"] is a (1, 1, H, W) tensor)."""
+    return post({"binary": torch.from_numpy(np.ascontiguousarray(prob))[None, None]}, ori_hw)
+
+
+def postprocess_cases():
+    """Seeded probability maps for the post-processor checks: blurred rectangles (axis-aligned and rotated), touching
+    blobs, tiny specks that the size / score filters drop; values quantised to 1/255 so that they can be stored exactly."""
+    import cv2
+    cases = []
+    for seed, (H, W) in ((0, (592, 800)), (1, (400, 640))):
+        rng = np.random.default_rng(900 + seed)
+        m = np.zeros((H, W), np.float32)
+        for k in range(70):
+            cx, cy = rng.uniform(30, W - 30), rng.uniform(20, H - 20)
+            w, h = rng.uniform(3, 120), rng.uniform(2, 26)
+            ang = 0.0 if k % 3 else rng.uniform(-35, 35)
+            box = cv2.boxPoints(((cx, cy), (w, h), ang)).astype(np.int32)
+            cv2.fillPoly(m, [box], float(rng.uniform(0.35, 1.0)))
+        m = cv2.GaussianBlur(m, (5, 5), 0)
+        cases.append((np.round(np.clip(m, 0, 1) * 255).astype(np.uint8), (H * 2 + 16, W * 2)))
+    return cases
+
+
 def main():
     from oracle import dbnet as odb
     from oracle import parseq as ops
@@ -254,6 +338,21 @@ def main():
         tok_o = ops.Tokenizer(charset).decode(o.softmax(-1))
         report("tokenizer decode strings+scores", tok_r[0] == tok_o[0] and
                all(abs(a - b) <= 2e-3 * max(abs(a), 1e-30) for a, b in zip(tok_r[1], tok_o[1])))
+    # ---- DBNet post-processing (row R3): the reference's own file against the oracle, three threshold sets
+    from oracle import pipeline as opipe
+    for name, kw in (("dbnetv2_1", dict(min_size=2, thresh=0.3, box_thresh=0.4, max_candidates=1500, unclip_ratio=3.5)),
+                     ("dbnetv2", dict(min_size=2, thresh=0.2, box_thresh=0.5, max_candidates=1500, unclip_ratio=5.0)),
+                     ("few", dict(min_size=2, thresh=0.3, box_thresh=0.4, max_candidates=20, unclip_ratio=3.5))):
+        post = build_reference_postprocessor(**kw)
+        for ci, (pu8, ori) in enumerate(postprocess_cases()):
+            prob = pu8.astype(np.float32) / 255.0
+            rq, rs = reference_postprocess(post, prob, ori)
+            oq, os_ = opipe.dbnet_postprocess(prob, ori, thresh=kw["thresh"], box_thresh=kw["box_thresh"],
+                                              max_candidates=kw["max_candidates"], unclip_ratio=kw["unclip_ratio"],
+                                              min_size=kw["min_size"])
+            report("dbnet post-processing %s case %d vs reference DBnetPostProcessor (clipper / shapely stand-ins)"
+                   % (name, ci), rq == oq and len(rs) == len(os_) and all(a == b for a, b in zip(rs, os_)),
+                   "boxes=%d" % len(rq))
     return 0 if ok else 1
 
 

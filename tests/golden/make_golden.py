@@ -17,6 +17,14 @@ from oracle import refcheck, weights  # noqa: E402
 OUT = os.path.dirname(os.path.abspath(__file__))
 
 
+# post-processor parameter sets of post_ref.npz (the v2_1 / v2 thresholds of the reference configs + a max_candidates cut)
+POST_PARAMS = {
+    "dbnetv2_1": dict(min_size=2, thresh=0.3, box_thresh=0.4, max_candidates=1500, unclip_ratio=3.5),
+    "dbnetv2": dict(min_size=2, thresh=0.2, box_thresh=0.5, max_candidates=1500, unclip_ratio=5.0),
+    "few": dict(min_size=2, thresh=0.3, box_thresh=0.4, max_candidates=20, unclip_ratio=3.5),
+}
+
+
 def crops_ref_page():
     """Page of crops_ref.npz: 3x3-px blocks of seeded noise (pure numpy, so the test rebuilds it instead of storing
     3.5 MB)."""
@@ -119,6 +127,20 @@ def main():
         if i % 8 == 0:
             crops2["fixed%d" % i] = fn.resize_with_padding(roi, [32, 800])
     np.savez_compressed(os.path.join(OUT, "crops_ref.npz"), quads=np.array(quads2, dtype=np.float64), **crops2)
+    # ---- DBNet post-processing (row R3): the reference's own DBnetPostProcessor (executed from /root/reference with the
+    # oracle's stand-ins for pyclipper / shapely, see oracle/refcheck.py) on seeded probability maps
+    post = {}
+    cases = refcheck.postprocess_cases()
+    for ci, (pu8, ori) in enumerate(cases):
+        post["prob%d" % ci] = pu8
+        post["ori%d" % ci] = np.array(ori)
+    for name, kw in POST_PARAMS.items():
+        ref_post = refcheck.build_reference_postprocessor(**kw)
+        for ci, (pu8, ori) in enumerate(cases):
+            q, sc = refcheck.reference_postprocess(ref_post, pu8.astype(np.float32) / 255.0, ori)
+            post["%s_quads%d" % (name, ci)] = np.array(q, dtype=np.int16).reshape(-1, 4, 2)
+            post["%s_scores%d" % (name, ci)] = np.array(sc, dtype=np.float64)
+    np.savez_compressed(os.path.join(OUT, "post_ref.npz"), **post)
     std = fn.standardization_image(page.astype(np.float32))
     np.savez_compressed(os.path.join(OUT, "host_ref.npz"), sizes=np.array(sizes), resized=np.array(res), page=page,
                         quads=np.array(quads), std=std, **crops)
