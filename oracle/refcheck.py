@@ -270,6 +270,117 @@ def reference_postprocess(post, prob, ori_hw):
     return post({"binary": torch.from_numpy(np.ascontiguousarray(prob))[None, None]}, ori_hw)
 
 
+# ------------------------------------------------------------------- the recognizer's host flow (rows R4, R5, R10, R11)
+def flow_hash(u8_chw):
+    """Position-sensitive checksum of a crop tensor as uint8 (3, 32, W); black padding contributes nothing, so it does
+    not depend on the padded width.  Shared by the stand-in models of the reference flow and of the product flow."""
+    c, y, x = np.meshgrid(np.arange(u8_chw.shape[0]), np.arange(u8_chw.shape[1]), np.arange(u8_chw.shape[2]),
+                          indexing="ij")
+    return int((u8_chw.astype(np.int64) * (1 + (c * 7 + y * 13 + x * 3) % 251)).sum())
+
+
+def flow_token(h, padded_w, batch_len, n_classes):
+    """(token id, probability) the stand-in model emits at position 0 for a crop with checksum h that sits in a
+    mini-batch of `batch_len` crops padded to `padded_w`; position 1 is EOS with probability 1."""
+    return 1 + (h * 31 + padded_w * 7 + batch_len * 3) % (n_classes - 1), 0.55 + 0.44 * ((h % 1000) / 1000.0)
+
+
+class _FlowModelOutput:
+    def __init__(self, probs):
+        self.probs = probs
+
+    def softmax(self, dim):          # the reference calls self.model(data).softmax(-1) (text_recognizer.py:255)
+        return self.probs
+
+
+def flow_model(n_classes, S):
+    """Stand-in for PARSeq in the reference flow: data (B, 3, 32, W) normalised float -> object whose .softmax(-1) is a
+    (B, S, C) distribution built from flow_token of every row."""
+    def model(data):
+        B, _, _, W = data.shape
+        u8 = torch.round((data * 0.5 + 0.5) * 255.0).to(torch.uint8).numpy()
+        probs = torch.zeros((B, S, n_classes), dtype=torch.float32)
+        probs[:, 1:, 0] = 1.0                                    # EOS from position 1 on
+        for b in range(B):
+            tok, p = flow_token(flow_hash(u8[b]), W, B, n_classes)
+            probs[b, 0, :] = (1.0 - p) / (n_classes - 1)
+            probs[b, 0, tok] = p
+        return _FlowModelOutput(probs)
+    return model
+
+
+def build_reference_recognizer_shell(charset, img_size=(32, 800), batch_size=10, width_budget=8000, max_batch_size=64,
+                                     max_label_length=25, **flags):
+    """An instance of the reference's own TextRecognizer class (text_recognizer.py executed from /root/reference)
+    without running its __init__ (which needs the HF hub / omegaconf): the attributes __call__ reads are set by hand,
+    `model` is the stand-in above, `tokenizer` the reference's ParseqTokenizer.  Every import of the module that is not
+    installable offline or not on this path is a stub module (omegaconf-based `base`, configs, models, visualizer,
+    onnx*, schemas); data/dataset.py, data/functions.py and postprocessor/parseq_tokenizer.py are the real files."""
+    import importlib.machinery
+    absent = [n for n in ("pypdfium2", "onnx", "onnxruntime") if n not in sys.modules]
+    for name in absent:       # import-time stubs only; removed again below (a spec-less stub left in sys.modules
+        m = types.ModuleType(name)          # confuses importlib.util.find_spec users such as torch._dynamo)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        sys.modules[name] = m
+    _pkg("ytk_ref")
+    _pkg("ytk_ref.data")
+    _pkg("ytk_ref.utils")
+    _pkg("ytk_ref.postprocessor")
+    _load("ytk_ref.constants", "constants.py", "ytk_ref")
+    _load("ytk_ref.utils.logger", "utils/logger.py", "ytk_ref.utils")
+    _load("ytk_ref.data.functions", "data/functions.py", "ytk_ref.data")
+    _load("ytk_ref.data.dataset", "data/dataset.py", "ytk_ref.data")
+    tk = _load("ytk_ref.postprocessor.parseq_tokenizer", "postprocessor/parseq_tokenizer.py", "ytk_ref.postprocessor")
+    sys.modules["ytk_ref.postprocessor"].ParseqTokenizer = tk.ParseqTokenizer
+
+    def stub(modname, **attrs):
+        m = types.ModuleType(modname)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[modname] = m
+        return m
+
+    class BaseModelCatalog:
+        def __init__(self):
+            self.entries = {}
+
+        def register(self, name, cfg, model):
+            self.entries[name] = (cfg, model)
+
+    class Schema(dict):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.__dict__.update(kw)
+
+    stub("ytk_ref.base", BaseModelCatalog=BaseModelCatalog, BaseModule=object)
+    stub("ytk_ref.configs", **{n: type(n, (), {}) for n in (
+        "TextRecognizerPARSeqConfig", "TextRecognizerPARSeqSmallConfig", "TextRecognizerPARSeqV2Config",
+        "TextRecognizerPARSeqTinyConfig", "TextRecognizerPARSeqLargeV41Config", "TextRecognizerPARSeqTinyDynwV4Config")})
+    stub("ytk_ref.models", PARSeq=None)
+    stub("ytk_ref.utils.misc", load_charset=lambda p: open(p, encoding="utf-8").read())
+    stub("ytk_ref.utils.visualizer", rec_visualizer=None)
+    stub("ytk_ref.schemas", TextRecognizerSchema=Schema)
+    try:
+        mod = _load("ytk_ref.text_recognizer", "text_recognizer.py", "ytk_ref")
+    finally:
+        for name in absent:
+            sys.modules.pop(name, None)
+    rec = object.__new__(mod.TextRecognizer)
+    data = AttrDict(img_size=list(img_size), batch_size=batch_size)
+    if width_budget:
+        data.width_budget, data.max_batch_size = width_budget, max_batch_size
+    rec._cfg = AttrDict(data=data, max_label_length=max_label_length)
+    rec.tokenizer = tk.ParseqTokenizer(charset)
+    rec.model = flow_model(len(rec.tokenizer) - 2, max_label_length + 1)
+    rec.device, rec.infer_onnx, rec.visualize, rec.num_parallel_batches = "cpu", False, False, 1
+    rec.dynamic_width = flags.get("dynamic_width", False)
+    rec.batch_bucketing = flags.get("batch_bucketing", False)
+    rec.source_downscale = flags.get("source_downscale", False)
+    rec.rec_orientation_fallback = flags.get("rec_orientation_fallback", False)
+    rec.rec_orientation_fallback_thresh = flags.get("rec_orientation_fallback_thresh", 0.75)
+    return rec
+
+
 def postprocess_cases():
     """Seeded probability maps for the post-processor checks: blurred rectangles (axis-aligned and rotated), touching
     blobs, tiny specks that the size / score filters drop; values quantised to 1/255 so that they can be stored exactly."""

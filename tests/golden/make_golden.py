@@ -141,6 +141,19 @@ def main():
             post["%s_quads%d" % (name, ci)] = np.array(q, dtype=np.int16).reshape(-1, 4, 2)
             post["%s_scores%d" % (name, ci)] = np.array(sc, dtype=np.float64)
     np.savez_compressed(os.path.join(OUT, "post_ref.npz"), **post)
+    # ---- the recognizer's host flow: the reference's own TextRecognizer.__call__ with a stand-in PARSeq
+    # (oracle/refcheck.py: build_reference_recognizer_shell, tests/flow_standins.py)
+    sys.path.insert(0, os.path.dirname(OUT))
+    import flow_standins as FS
+    flow = {}
+    for name in FS.CASES:
+        ref_rec, fpage, fquads = FS.reference_recognizer(name)
+        r, _ = ref_rec(fpage, fquads)
+        flow[name + "_contents"] = np.array(r["contents"], dtype=object)
+        flow[name + "_scores"] = np.array(r["scores"], dtype=np.float64)
+        flow[name + "_directions"] = np.array(r["directions"], dtype=object)
+        print("flow case %-24s %4d crops" % (name, len(r["contents"])))
+    np.savez_compressed(os.path.join(OUT, "flow_ref.npz"), **flow)
     std = fn.standardization_image(page.astype(np.float32))
     np.savez_compressed(os.path.join(OUT, "host_ref.npz"), sizes=np.array(sizes), resized=np.array(res), page=page,
                         quads=np.array(quads), std=std, **crops)
