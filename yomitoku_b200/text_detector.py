@@ -17,12 +17,16 @@ from .postprocessor import DBnetPostProcessor
 from .schemas import TextDetectorSchema
 
 
+# catalog names of the reference (text_detector.py:26-31): one architecture, three threshold / weight sets
+_DETECTORS = (("dbnet", TextDetectorDBNetConfig), ("dbnetv2", TextDetectorDBNetV2Config),
+              ("dbnetv2_1", TextDetectorDBNetV2_1Config))
+
+
 class TextDetectorModelCatalog(BaseModelCatalog):
     def __init__(self):
         super().__init__()
-        self.register("dbnet", TextDetectorDBNetConfig, DBNet)
-        self.register("dbnetv2", TextDetectorDBNetV2Config, DBNet)
-        self.register("dbnetv2_1", TextDetectorDBNetV2_1Config, DBNet)
+        for name, cfg in _DETECTORS:
+            self.register(name, cfg, DBNet)
 
 
 class TextDetector(BaseModule):
@@ -31,13 +35,12 @@ class TextDetector(BaseModule):
     def __init__(self, model_name="dbnetv2_1", path_cfg=None, device="cuda", visualize=False, from_pretrained=True,
                  infer_onnx=False):
         super().__init__()
-        self.load_model(model_name, path_cfg, from_pretrained=from_pretrained)
-        self.device = device
         self.visualize = visualize
-        self.model.eval()
-        self.post_processor = DBnetPostProcessor(**self._cfg.post_process)
         self.infer_onnx = False   # accepted for API compatibility; there is no ONNX path here
-        self.model.to(self.device)
+        self.device = device
+        self.load_model(model_name, path_cfg, from_pretrained=from_pretrained)
+        self.model.eval().to(self.device)
+        self.post_processor = DBnetPostProcessor(**self._cfg.post_process)
 
     def preprocess(self, img):
         """BGR u8 page -> normalised (1,3,H',W') fp32 tensor; reference text_detector.py:99-107 (host path)."""
