@@ -381,6 +381,72 @@ def build_reference_recognizer_shell(charset, img_size=(32, 800), batch_size=10,
     return rec
 
 
+# ------------------------------------------------------------------- the detector's host flow (rows R1, R3)
+def flow_detector_model(tensor):
+    """Stand-in for DBNet in the reference / product detector flow: a probability map that is a smooth function of the
+    normalised input tensor (1, 3, H, W): text strokes (dark) light up, the white background stays near 0."""
+    m = F.avg_pool2d(-tensor.mean(1, keepdim=True), 7, 1, 3)
+    return {"binary": torch.sigmoid(2.0 * m + 1.0)}
+
+
+def build_reference_detector_shell(shortest_size=1280, limit_size=1600, **post):
+    """An instance of the reference's own TextDetector (text_detector.py executed from /root/reference) without its
+    __init__: `preprocess` / `postprocess` / `__call__` are the reference's code, data/functions.py and the
+    post-processor are the real files (the latter with the pyclipper / shapely stand-ins), the model is
+    flow_detector_model."""
+    import importlib.machinery
+    post = post or dict(min_size=2, thresh=0.3, box_thresh=0.4, max_candidates=1500, unclip_ratio=3.5)
+    post_obj = build_reference_postprocessor(**post)
+    absent = [n for n in ("pypdfium2", "onnx", "onnxruntime") if n not in sys.modules]
+    for name in absent:
+        m = types.ModuleType(name)
+        m.__spec__ = importlib.machinery.ModuleSpec(name, None)
+        sys.modules[name] = m
+    _pkg("ytk_ref")
+    _pkg("ytk_ref.data")
+    _pkg("ytk_ref.utils")
+    _load("ytk_ref.constants", "constants.py", "ytk_ref")
+    _load("ytk_ref.utils.logger", "utils/logger.py", "ytk_ref.utils")
+    _load("ytk_ref.data.functions", "data/functions.py", "ytk_ref.data")
+
+    def stub(modname, **attrs):
+        m = types.ModuleType(modname)
+        for k, v in attrs.items():
+            setattr(m, k, v)
+        sys.modules[modname] = m
+
+    class BaseModelCatalog:
+        def __init__(self):
+            self.entries = {}
+
+        def register(self, name, cfg, model):
+            self.entries[name] = (cfg, model)
+
+    class Schema(dict):
+        def __init__(self, **kw):
+            super().__init__(**kw)
+            self.__dict__.update(kw)
+
+    stub("ytk_ref.base", BaseModelCatalog=BaseModelCatalog, BaseModule=object)
+    stub("ytk_ref.configs", **{n: type(n, (), {}) for n in (
+        "TextDetectorDBNetConfig", "TextDetectorDBNetV2Config", "TextDetectorDBNetV2_1Config")})
+    stub("ytk_ref.models", DBNet=None)
+    sys.modules["ytk_ref.postprocessor"].DBnetPostProcessor = type(post_obj)
+    stub("ytk_ref.utils.visualizer", det_visualizer=None)
+    stub("ytk_ref.schemas", TextDetectorSchema=Schema)
+    try:
+        mod = _load("ytk_ref.text_detector", "text_detector.py", "ytk_ref")
+    finally:
+        for name in absent:
+            sys.modules.pop(name, None)
+    det = object.__new__(mod.TextDetector)
+    det._cfg = AttrDict(data=AttrDict(shortest_size=shortest_size, limit_size=limit_size))
+    det.post_processor = post_obj
+    det.model = flow_detector_model
+    det.device, det.infer_onnx, det.visualize = "cpu", False, False
+    return det
+
+
 def postprocess_cases():
     """Seeded probability maps for the post-processor checks: blurred rectangles (axis-aligned and rotated), touching
     blobs, tiny specks that the size / score filters drop; values quantised to 1/255 so that they can be stored exactly."""

@@ -94,3 +94,24 @@ def reference_recognizer(name):
         rec.charset, img_size=tuple(d.img_size), batch_size=d.batch_size, width_budget=getattr(d, "width_budget", None),
         max_batch_size=getattr(d, "max_batch_size", None), max_label_length=rec._cfg.max_label_length, **CASES[name][1])
     return ref, page, quads
+
+
+# ------------------------------------------------------------------------------------------------ detector flow
+def detector_pages():
+    """Pages that need UP-scaling to the detector's input size, so that the product takes its host pre-processing path
+    (the reference's way) instead of the fused GPU kernel: landscape and portrait."""
+    import cv2
+    from yomitoku_b200.synth import synthetic_page
+    out = []
+    for seed, size in ((4, (800, 600)), (13, (510, 690))):
+        page, _ = synthetic_page(seed)
+        out.append(cv2.resize(page, size, interpolation=cv2.INTER_AREA))
+    return out
+
+
+def product_detector():
+    from oracle.refcheck import flow_detector_model
+    from yomitoku_b200 import TextDetector
+    det = TextDetector(from_pretrained=False, device="cpu")
+    det.model = flow_detector_model
+    return det

@@ -154,6 +154,16 @@ def main():
         flow[name + "_directions"] = np.array(r["directions"], dtype=object)
         print("flow case %-24s %4d crops" % (name, len(r["contents"])))
     np.savez_compressed(os.path.join(OUT, "flow_ref.npz"), **flow)
+    # ---- the detector's host flow: the reference's own TextDetector.__call__ (pre-processing, post-processing) with a
+    # stand-in DBNet, on pages that need up-scaling
+    ref_det = refcheck.build_reference_detector_shell()
+    detflow = {}
+    for i, dpage in enumerate(FS.detector_pages()):
+        r, _ = ref_det(dpage)
+        detflow["points%d" % i] = np.array(r["points"], dtype=np.int16).reshape(-1, 4, 2)
+        detflow["scores%d" % i] = np.array(r["scores"], dtype=np.float64)
+        print("detector flow page %d: %d boxes" % (i, len(r["points"])))
+    np.savez_compressed(os.path.join(OUT, "detflow_ref.npz"), **detflow)
     std = fn.standardization_image(page.astype(np.float32))
     np.savez_compressed(os.path.join(OUT, "host_ref.npz"), sizes=np.array(sizes), resized=np.array(res), page=page,
                         quads=np.array(quads), std=std, **crops)

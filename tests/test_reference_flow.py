@@ -94,3 +94,26 @@ def test_product_flow_matches_reference_live(name):
     p, _ = rec(page, quads)
     _same(p, r["contents"], r["scores"], r["directions"])
     assert p.points == r["points"]
+
+
+def test_detector_flow_matches_reference_fixture():
+    """Rows R1 (host pre-processing: flip, float32 INTER_AREA / linear resize to the floor-32 size, standardisation) and R3
+    through `TextDetector.__call__`: quads and scores the reference's own TextDetector produced with the stand-in model."""
+    z = np.load(os.path.join(HERE, "golden", "detflow_ref.npz"))
+    det = FS.product_detector()
+    for i, page in enumerate(FS.detector_pages()):
+        res, vis = det(page)
+        assert vis is None and len(res.points) > 50
+        assert res.points == z["points%d" % i].tolist()
+        assert res.scores == z["scores%d" % i].tolist()
+
+
+@pytest.mark.skipif(not refcheck.available(), reason="needs /root/reference")
+def test_detector_flow_matches_reference_live():
+    ref = refcheck.build_reference_detector_shell()
+    det = FS.product_detector()
+    for page in FS.detector_pages():
+        assert torch.equal(ref.preprocess(page), det.preprocess(page))
+        r, _ = ref(page)
+        p, _ = det(page)
+        assert p.points == r["points"] and p.scores == r["scores"]
