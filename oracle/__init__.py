@@ -15,6 +15,12 @@ unpinned" by the reference).  The oracle is therefore pinned against the referen
 `models/layers/*.py`, `postprocessor/parseq_tokenizer.py` and `data/functions.py` *by path* from /root/reference
 (with small stand-ins for the third-party packages missing in this image) and asserts equality on seeded inputs;
 `tests/golden/make_golden.py` stores reference-generated outputs as fixtures that travel to the GPU box.
+Beyond the model code, refcheck also executes the reference's own DBnetPostProcessor (pyclipper / shapely replaced by
+this oracle's restatements), its ParseqDataset and its TextRecognizer / TextDetector `__call__` methods (around
+stand-in models) to pin the host rows - post-processing, crop extraction, batching, pairing, fallback - and
+`tests/golden/{post_ref,crops_ref,flow_ref,detflow_ref}.npz` carry those outputs to machines without the reference.
+The one native piece, `oracle/crop_host.cpp`, is the PRODUCT's crop arithmetic (csrc/crop_math.h) compiled for the
+host so that the CPU tests can pin it bit for bit against OpenCV.
 Third-party arithmetic not under /root/reference and absent from the image (pyclipper 1.4.0, shapely 2.1.2,
 timm 1.0.27, omegaconf 2.3.0) is restated from its published algorithm; see oracle/postprocess.py and
 oracle/parseq.py headers.  Those pieces are "parity unpinned" against the real libraries (they cannot be

@@ -8,6 +8,11 @@ the reference's model files are loaded *by path*, unmodified, with stand-ins for
     `forward_features_dynamic` (reference code) run;
   * the `cfg` objects (OmegaConf in the reference) are attribute-dicts built from the reference's own config
     dataclasses' values.
+  * for the host rows: `pyclipper` / `shapely` -> this oracle's restatements (build_reference_postprocessor); the
+    modules the reference's text_recognizer.py / text_detector.py import but this path never executes (omegaconf-based
+    `base`, configs, models, visualizer, onnx*, schemas) -> empty stubs, so that the reference's own `__call__`,
+    `preprocess`, `_make_mini_batch`, `_collate`, `postprocess`, `_apply_orientation_fallback` and `ParseqDataset`
+    run unmodified around stand-in models (build_reference_recognizer_shell / build_reference_detector_shell).
 Nothing is copied into the repo: modules are executed from /root/reference in-process.
 
 Usage:  python -m oracle.refcheck            (prints PASS/FAIL lines; exit code 0 iff all pass)
