@@ -607,3 +607,27 @@ def test_batched_pipeline_orientation_fallback_with_stub_models(monkeypatch):
         assert np.allclose([w.rec_score for w in got[i].words], single.scores)
         replaced += sum(a != b for a, b in zip(single.contents, plain.contents))
     assert replaced > 0
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle (and everything under tests/) is checker-only: no module of the product package may import it, and the
+    product must load without it on the path."""
+    import ast
+    import glob
+    import subprocess
+    import sys
+    pkg = os.path.join(os.path.dirname(HERE), "yomitoku_b200")
+    for f in glob.glob(os.path.join(pkg, "*.py")):
+        for node in ast.walk(ast.parse(open(f, encoding="utf-8").read())):
+            names = []
+            if isinstance(node, ast.Import):
+                names = [a.name for a in node.names]
+            elif isinstance(node, ast.ImportFrom) and node.level == 0:
+                names = [node.module or ""]
+            assert not any(n.split(".")[0] in ("oracle", "tests") for n in names), (f, names)
+    code = ("import sys; sys.path = [p for p in sys.path if p not in ('', %r)]; sys.path.insert(0, %r); "
+            "import importlib, yomitoku_b200; "
+            "[importlib.import_module('yomitoku_b200.' + m) for m in ('pipeline', 'parallel', 'models', 'ocr')]; "
+            "assert 'oracle' not in sys.modules" % (os.path.dirname(HERE), os.path.dirname(HERE)))
+    # the repo root is needed to find the package itself; the assertion is that importing it pulls in no oracle module
+    assert subprocess.run([sys.executable, "-c", code], cwd="/", capture_output=True).returncode == 0
