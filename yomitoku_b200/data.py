@@ -1,10 +1,10 @@
 """Host-side image functions of the hot path (numpy / OpenCV), same names and semantics as the reference's
 src/yomitoku/data/functions.py:196-439 and data/dataset.py:19-129.
 
-These stay on the host exactly as in the reference (they are rows R1/R4 of SURVEY.md section 8a; the device-side crop
-extraction is a "next" row, section 8f-1).  The detector's resize + normalisation is ALSO available fused on the GPU
-(csrc/dbnet_ops.cu preprocess_kernel); `resize_shortest_edge` / `standardization_image` here serve the model-level
-seam and pages that need up-scaling.
+These are the host versions of rows R1 / R4 of SURVEY.md section 8a, exactly as the reference runs them; both rows also
+exist on the GPU: the detector's resize + normalisation fused in csrc/dbnet_ops.cu (preprocess_kernel; the functions
+here serve the model-level seam and pages that need up-scaling), and the crop extraction in csrc/crop_ops.cu, for which
+`crop_geometry` / `crop_records` below compute the per-quad records (everything that follows from the quads alone).
 """
 from concurrent.futures import ThreadPoolExecutor
 
