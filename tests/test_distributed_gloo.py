@@ -234,6 +234,60 @@ def test_pipeline_groups_device_crops_world2():
         assert status == "ok", status
 
 
+def _worker_pipeline_balanced(rank, world, port, q):
+    """Balanced ranks: every rank derives "nothing moves" from the gathered costs and skips the scatter / gather rounds."""
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from yomitoku_b200 import parallel as par
+        from yomitoku_b200 import pipeline as pl
+        from yomitoku_b200.config import TextRecognizerPARSeqLargeV41Config, to_config
+        cfg = to_config(TextRecognizerPARSeqLargeV41Config())
+
+        class Rec:
+            _cfg = cfg
+            model = _StubModel(cfg)
+
+        def forbidden(*a, **k):
+            raise AssertionError("no exchange expected for balanced ranks")
+
+        par.exchange_groups = forbidden
+        par.return_results = forbidden
+        ocr = pl.BatchedOCR(None, Rec(), workers=1)
+        rng = np.random.default_rng(5)                    # same widths on both ranks: equal costs
+        groups, expect = [], []
+        for gi in range(4):
+            widths = (rng.integers(9, 30, size=3) * 8).tolist()
+            canv = [np.random.default_rng(100 * rank + 10 * gi + j).integers(0, 256, size=(32, w, 3), dtype=np.uint8)
+                    for j, w in enumerate(widths)]
+            groups.append((canv, [max(widths)] * 3))
+            expect.append(_fake_recognise(canv))
+        res = ocr._run_groups(groups, None, None, 32)
+        for (ids, probs, glen), (eid, ep) in zip(res, expect):
+            assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101
+        q.put((rank, "ok", None))
+    except Exception:  # pragma: no cover
+        import traceback
+        q.put((rank, "fail: " + traceback.format_exc(), None))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_pipeline_groups_balanced_world2_skips_exchange():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_pipeline_balanced, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    out = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, status, _ in out:
+        assert status == "ok", status
+
+
 def test_pipeline_groups_arena_world2():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -499,7 +499,12 @@ class BatchedOCR:
         gh = cfg.data.img_size[0] // ph
         rank = dist.get_rank()
         costs = [gh * (int(np.sum(g[1])) // pw) for g in groups]
-        assign = par.balance_groups(par.gather_costs(costs), dist.get_world_size())[rank]
+        assign_all = par.balance_groups(par.gather_costs(costs), dist.get_world_size())
+        if all(dst == r for r, row in enumerate(assign_all) for dst in row):
+            # balanced already (every rank computes the same table from the same gathered costs): nothing moves, so
+            # the two all_to_all rounds of the scatter / gather are skipped on all ranks alike
+            return list(run_mine(range(len(groups))))
+        assign = assign_all[rank]
         leaving = [k for k in range(len(groups)) if assign[k] != rank]
         mine = [k for k in range(len(groups)) if assign[k] == rank]        # exchange_groups lists own groups first
         pix = dict(zip(leaving, pixels(leaving))) if leaving else {}
