@@ -744,6 +744,10 @@ class BatchedOCR:
                 owner.append(pi)
             base += len(retry)
         if not groups:
+            import torch.distributed as dist
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+                # the balancing round is a collective: a rank without retries still takes part in it
+                self._run_groups_dev([], np.zeros(0, CROP_GEOM_DTYPE), pages_dev, stream, np.zeros(0, np.int64))
             return
         res = self._run_groups_dev(groups, np.concatenate(geoms2), pages_dev, stream, np.concatenate(levels2))
         S = cfg.max_label_length + 1
