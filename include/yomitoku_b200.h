@@ -41,14 +41,14 @@ int ytk_gemm_profile_end(double* flops, double* ms, long long* launches);
  * bf16/fp32.  Replaces torch.nn.Conv2d + BatchNorm2d(eval, folded) + ReLU (+ residual add) of
  * torchvision ResNet-50 bottlenecks (reference models/dbnet_plus.py:30-38) and the decoder convs (:56-116).
  * mode 1 = ConvTranspose2d(kernel 2, stride 2) written as a GEMM with a pixel-shuffle epilogue (:111,:114). */
-int ytk_op_conv2d_bf16(const void* in, int N, int H, int W, int Cin, long long in_ld, const void* w, const float* bias,
+int ytk_op_conv2d_f16(const void* in, int N, int H, int W, int Cin, long long in_ld, const void* w, const float* bias,
                        int kh, int kw, int stride, int pad, int dil, int Cout, const void* resid, int resid_f32,
                        long long ldr, void* out, int out_f32, long long ldc, int act, int mode, void* cuda_stream);
 
 /* Linear layer y = act(A W^T + b (+ resid)); A [M,lda] bf16, W [N,K] bf16 (torch nn.Linear layout), K % 64 == 0.
  * Replaces nn.Linear / timm Mlp / attention projections (reference models/layers/parseq_transformer.py:43-52,
  * models/parseq.py:72). */
-int ytk_op_linear_bf16(const void* A, long long lda, int M, int K, const void* W, int N, const float* bias,
+int ytk_op_linear_f16(const void* A, long long lda, int M, int K, const void* W, int N, const float* bias,
                        const void* resid, int resid_f32, long long ldr, void* out, int out_f32, long long ldc, int act,
                        void* cuda_stream);
 

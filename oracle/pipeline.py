@@ -215,15 +215,25 @@ def recognize(sd, spec, tokenizer, img_bgr, quads, dynamic_width=False, batch_bu
         order = np.argsort(cw).tolist()
     plan = mini_batches([c.shape[1] for c in canv], order, dynamic_width, batch_size, width_budget, max_batch_size)
     pts = [quads[i] for i in order] if order is not None else quads
-    preds, scores, dirs, all_logits = [], [], [], []
+    preds, scores, dirs, all_logits, margins = [], [], [], [], []
     off = 0
     for batch in plan:
         ts = [to_tensor(canv[i]) for i in batch]
         if dynamic_width:
             wm = max(t.shape[-1] for t in ts)
             ts = [F.pad(t, (0, wm - t.shape[-1]), value=-1.0) for t in ts]
-        logits = ops.parseq_forward(sd, spec, torch.stack(ts, 0))
+        logits, paux = ops.parseq_forward(sd, spec, torch.stack(ts, 0), return_aux=True)
         s, p = tokenizer.decode(logits.softmax(-1))
+        # smallest top-2 logit gap over every greedy decision the row's string depends on (AR steps + the positions
+        # of the final logits up to and including the first EOS): rows below a tolerance are coin flips for any
+        # implementation that is not bit-identical fp32
+        top2 = logits.topk(2, -1).values
+        gap = top2[..., 0] - top2[..., 1]
+        ids_ = logits.argmax(-1)
+        for b in range(logits.shape[0]):
+            row = ids_[b].tolist()
+            m = row.index(spec.eos_id) + 1 if spec.eos_id in row else len(row)
+            margins.append(min(float(paux["ar_margin"][b].min()), float(gap[b, :m].min())))
         preds += [unicodedata.normalize("NFKC", t) for t in s]
         scores += p
         for q in pts[off:off + len(batch)]:
@@ -234,8 +244,10 @@ def recognize(sd, spec, tokenizer, img_bgr, quads, dynamic_width=False, batch_bu
     if order is not None:
         inv = np.argsort(order)
         preds, scores, dirs = [preds[i] for i in inv], [scores[i] for i in inv], [dirs[i] for i in inv]
+        margins = [margins[i] for i in inv]
     if return_aux:
-        return preds, scores, dirs, {"plan": plan, "order": order, "logits": all_logits, "canvases": canv}
+        return preds, scores, dirs, {"plan": plan, "order": order, "logits": all_logits, "canvases": canv,
+                                     "min_margin": margins}
     return preds, scores, dirs
 
 

@@ -51,17 +51,17 @@ def stats(name, got, ref, extra=None):
 
 def run_linear(M, K, N, bias=True, act=0, resid=None, out_f32=False, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
-    A = (torch.randn(M, K, generator=g) * 0.5).to(dev).bfloat16()
-    W = (torch.randn(N, K, generator=g) * 0.1).to(dev).bfloat16()
+    A = (torch.randn(M, K, generator=g) * 0.5).to(dev).half()
+    W = (torch.randn(N, K, generator=g) * 0.1).to(dev).half()
     b = torch.randn(N, generator=g).to(dev) if bias else None
     ldc = (N + 7) // 8 * 8
     R = None
     if resid == "f32":
         R = torch.randn(M, ldc, generator=g).to(dev)
-    elif resid == "bf16":
-        R = torch.randn(M, ldc, generator=g).to(dev).bfloat16()
-    out = torch.full((M, ldc), 7.0, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
-    st = L.ytk_op_linear_bf16(_lib.ptr(A), K, M, K, _lib.ptr(W), N, _lib.ptr(b), _lib.ptr(R),
+    elif resid == "f16":
+        R = torch.randn(M, ldc, generator=g).to(dev).half()
+    out = torch.full((M, ldc), 7.0, device=dev, dtype=torch.float32 if out_f32 else torch.float16)
+    st = L.ytk_op_linear_f16(_lib.ptr(A), K, M, K, _lib.ptr(W), N, _lib.ptr(b), _lib.ptr(R),
                               1 if resid == "f32" else 0, ldc, _lib.ptr(out), 1 if out_f32 else 0, ldc, act, None)
     name = "linear M%d K%d N%d b%d act%d res%s f32%d" % (M, K, N, bias, act, resid, out_f32)
     if st != 0:
@@ -85,17 +85,17 @@ def run_linear(M, K, N, bias=True, act=0, resid=None, out_f32=False, seed=0):
 
 def run_conv(N, H, W, Cin, Cout, k, stride, pad, dil, bias=True, act=0, resid=False, out_f32=False, mode=0, seed=0):
     g = torch.Generator(device="cpu").manual_seed(seed)
-    x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(dev).bfloat16()  # NHWC
+    x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(dev).half()  # NHWC
     if mode == 1:
         # ConvTranspose2d(k=2,s=2) weight [Cin, Cq, 2, 2]; GEMM weight rows = (i,j,co)
         Cq = Cout // 4
-        wt = (torch.randn(Cin, Cq, 2, 2, generator=g) * 0.1).to(dev).bfloat16()
+        wt = (torch.randn(Cin, Cq, 2, 2, generator=g) * 0.1).to(dev).half()
         wp = wt.permute(2, 3, 1, 0).reshape(Cout, Cin).contiguous()
         b = torch.randn(Cq, generator=g).to(dev) if bias else None
         bfull = b.repeat(4).contiguous() if bias else None
         Ho, Wo = H, W
-        out = torch.full((N, 2 * Ho, 2 * Wo, Cq), 7.0, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
-        st = L.ytk_op_conv2d_bf16(_lib.ptr(x), N, H, W, Cin, Cin, _lib.ptr(wp), _lib.ptr(bfull), 1, 1, 1, 0, 1, Cout,
+        out = torch.full((N, 2 * Ho, 2 * Wo, Cq), 7.0, device=dev, dtype=torch.float32 if out_f32 else torch.float16)
+        st = L.ytk_op_conv2d_f16(_lib.ptr(x), N, H, W, Cin, Cin, _lib.ptr(wp), _lib.ptr(bfull), 1, 1, 1, 0, 1, Cout,
                                   None, 0, 0, _lib.ptr(out), 1 if out_f32 else 0, Cq, act, 1, None)
         name = "convT2x2 N%d H%d W%d Cin%d Cq%d act%d" % (N, H, W, Cin, Cq, act)
         if st != 0:
@@ -108,15 +108,15 @@ def run_conv(N, H, W, Cin, Cout, k, stride, pad, dil, bias=True, act=0, resid=Fa
             ref = ref.relu()
         stats(name, out, ref.permute(0, 2, 3, 1))
         return
-    w = (torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / (Cin * k * k) ** 0.5)).to(dev).bfloat16()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) * (1.0 / (Cin * k * k) ** 0.5)).to(dev).half()
     wp = w.permute(0, 2, 3, 1).contiguous()  # [Cout][kh][kw][Cin]
     b = torch.randn(Cout, generator=g).to(dev) if bias else None
     Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
-    R = (torch.randn(N, Ho, Wo, Cout, generator=g)).to(dev).bfloat16() if resid else None
-    out = torch.full((N, Ho, Wo, Cout), 7.0, device=dev, dtype=torch.float32 if out_f32 else torch.bfloat16)
+    R = (torch.randn(N, Ho, Wo, Cout, generator=g)).to(dev).half() if resid else None
+    out = torch.full((N, Ho, Wo, Cout), 7.0, device=dev, dtype=torch.float32 if out_f32 else torch.float16)
     t0 = time.time()
-    st = L.ytk_op_conv2d_bf16(_lib.ptr(x), N, H, W, Cin, Cin, _lib.ptr(wp), _lib.ptr(b), k, k, stride, pad, dil, Cout,
+    st = L.ytk_op_conv2d_f16(_lib.ptr(x), N, H, W, Cin, Cin, _lib.ptr(wp), _lib.ptr(b), k, k, stride, pad, dil, Cout,
                               _lib.ptr(R), 0, Cout, _lib.ptr(out), 1 if out_f32 else 0, Cout, act, 0, None)
     name = "conv N%d H%d W%d Cin%d Cout%d k%d s%d p%d d%d act%d res%d f32%d" % (
         N, H, W, Cin, Cout, k, stride, pad, dil, act, resid, out_f32)
@@ -135,22 +135,22 @@ def run_conv(N, H, W, Cin, Cout, k, stride, pad, dil, bias=True, act=0, resid=Fa
 
 
 def timed_conv(N, H, W, Cin, Cout, k, stride, pad, dil, iters=20):
-    x = (torch.randn(N, H, W, Cin, device=dev) * 0.5).bfloat16()
-    wp = (torch.randn(Cout, k, k, Cin, device=dev) * 0.02).bfloat16()
+    x = (torch.randn(N, H, W, Cin, device=dev) * 0.5).half()
+    wp = (torch.randn(Cout, k, k, Cin, device=dev) * 0.02).half()
     b = torch.randn(Cout, device=dev)
     Ho = (H + 2 * pad - dil * (k - 1) - 1) // stride + 1
     Wo = (W + 2 * pad - dil * (k - 1) - 1) // stride + 1
-    out = torch.empty((N, Ho, Wo, Cout), device=dev, dtype=torch.bfloat16)
+    out = torch.empty((N, Ho, Wo, Cout), device=dev, dtype=torch.float16)
     args = (_lib.ptr(x), N, H, W, Cin, Cin, _lib.ptr(wp), _lib.ptr(b), k, k, stride, pad, dil, Cout, None, 0, 0,
             _lib.ptr(out), 0, Cout, 1, 0, None)
     for _ in range(3):
-        L.ytk_op_conv2d_bf16(*args)
+        L.ytk_op_conv2d_f16(*args)
     torch.cuda.synchronize()
     e0 = torch.cuda.Event(enable_timing=True)
     e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        L.ytk_op_conv2d_bf16(*args)
+        L.ytk_op_conv2d_f16(*args)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
@@ -175,7 +175,7 @@ def main():
         run_linear(1000, 768, 2304, act=2)
         run_linear(517, 768, 7119, out_f32=True)
         run_linear(640, 3072, 768, resid="f32", out_f32=True)
-        run_linear(33, 192, 576, resid="bf16", act=1)
+        run_linear(33, 192, 576, resid="f16", act=1)
         run_conv(1, 16, 24, 64, 64, 1, 1, 0, 1, bias=False, out_f32=True)
         run_conv(1, 16, 24, 64, 64, 3, 1, 1, 1)
         run_conv(2, 37, 50, 128, 256, 3, 1, 1, 1, act=1)

@@ -44,6 +44,7 @@ def _debug(model, n, H, W, name):
 
 def _prob_close(got, ref):
     d = np.abs(got - ref)
+    print("[dbnet] prob map mean|d| %.5f, within 0.08: %.5f, max %.4f" % (d.mean(), (d < 0.08).mean(), d.max()))
     assert d.mean() < 0.012, d.mean()
     assert (d < 0.08).mean() > 0.995, (d < 0.08).mean()
 
@@ -68,6 +69,7 @@ def test_backbone_and_prob_vs_oracle(det):
     for k in ("layer1", "layer2", "layer3", "layer4"):
         got = _debug(det.model, 2, H, W, k)
         r = feats[k].permute(0, 2, 3, 1)
+        print("[dbnet] %s rel Frobenius %.5f" % (k, ((got - r).norm() / r.norm()).item()))
         assert ((got - r).norm() / r.norm()).item() < 0.015, k
     _prob_close(prob.numpy(), ref.numpy())
 

@@ -25,8 +25,8 @@ def _check(got, ref, tol=6e-3):
 
 @pytest.mark.parametrize("M,K,N,act,resid,f32", [
     (128, 64, 64, 0, None, True), (300, 128, 200, 0, None, False), (1000, 768, 2304, 2, None, False),
-    (517, 768, 7119, 0, None, True), (640, 3072, 768, 0, "f32", True), (33, 192, 576, 1, "bf16", False),
-    (257, 192, 200, 3, "f32", False), (129, 64, 100, 0, "bf16", True),
+    (517, 768, 7119, 0, None, True), (640, 3072, 768, 0, "f32", True), (33, 192, 576, 1, "f16", False),
+    (257, 192, 200, 3, "f32", False), (129, 64, 100, 0, "f16", True),
     # >= 4 tiles per SM: CTA-pair kernel (tcgen05.mma.cta_group::2, half weight tile per SM); 75 / 149 M tiles are odd,
     # so the last pair has a ghost CTA; N = 2304 has 9 full N tiles, N = 7119 a ragged last one, K = 3072 wraps the stage ring
     (128 * 74 + 5, 768, 2304, 2, None, False), (128 * 148 + 77, 192, 768, 0, "f32", True),
@@ -34,17 +34,17 @@ def _check(got, ref, tol=6e-3):
 def test_linear(M, K, N, act, resid, f32):
     L = _lib_()
     g = torch.Generator().manual_seed(M + N)
-    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).bfloat16()
-    W = (torch.randn(N, K, generator=g) * 0.1).to(DEV).bfloat16()
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).half()
+    W = (torch.randn(N, K, generator=g) * 0.1).to(DEV).half()
     b = torch.randn(N, generator=g).to(DEV)
     ldc = (N + 7) // 8 * 8
     R = None
     if resid == "f32":
         R = torch.randn(M, ldc, generator=g).to(DEV)
-    elif resid == "bf16":
-        R = torch.randn(M, ldc, generator=g).to(DEV).bfloat16()
-    out = torch.full((M, ldc), 7.0, device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
-    _lib.check(L.ytk_op_linear_bf16(_lib.ptr(A), K, M, K, _lib.ptr(W), N, _lib.ptr(b), _lib.ptr(R),
+    elif resid == "f16":
+        R = torch.randn(M, ldc, generator=g).to(DEV).half()
+    out = torch.full((M, ldc), 7.0, device=DEV, dtype=torch.float32 if f32 else torch.float16)
+    _lib.check(L.ytk_op_linear_f16(_lib.ptr(A), K, M, K, _lib.ptr(W), N, _lib.ptr(b), _lib.ptr(R),
                                     1 if resid == "f32" else 0, ldc, _lib.ptr(out), 1 if f32 else 0, ldc, act, None))
     torch.cuda.synchronize()
     ref = A.float() @ W.float().t() + b
@@ -68,15 +68,15 @@ def test_linear(M, K, N, act, resid, f32):
 def test_conv(N, H, W, Cin, Cout, k, s, p, d, act, resid):
     L = _lib_()
     g = torch.Generator().manual_seed(H * W + Cout)
-    x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(DEV).bfloat16()
-    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV).bfloat16()
+    x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(DEV).half()
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(DEV).half()
     wp = w.permute(0, 2, 3, 1).contiguous()
     b = torch.randn(Cout, generator=g).to(DEV)
     Ho = (H + 2 * p - d * (k - 1) - 1) // s + 1
     Wo = (W + 2 * p - d * (k - 1) - 1) // s + 1
-    R = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).bfloat16() if resid else None
-    out = torch.empty((N, Ho, Wo, Cout), device=DEV, dtype=torch.bfloat16)
-    _lib.check(L.ytk_op_conv2d_bf16(_lib.ptr(x), N, H, W, Cin, Cin, _lib.ptr(wp), _lib.ptr(b), k, k, s, p, d, Cout,
+    R = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).half() if resid else None
+    out = torch.empty((N, Ho, Wo, Cout), device=DEV, dtype=torch.float16)
+    _lib.check(L.ytk_op_conv2d_f16(_lib.ptr(x), N, H, W, Cin, Cin, _lib.ptr(wp), _lib.ptr(b), k, k, s, p, d, Cout,
                                     _lib.ptr(R), 0, Cout, _lib.ptr(out), 0, Cout, act, 0, None))
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=s, padding=p, dilation=d).permute(0, 2, 3, 1)
@@ -90,12 +90,12 @@ def test_conv(N, H, W, Cin, Cout, k, s, p, d, act, resid):
 def test_conv_transpose_shuffle_epilogue():
     L = _lib_()
     g = torch.Generator().manual_seed(3)
-    x = (torch.randn(1, 20, 28, 64, generator=g) * 0.5).to(DEV).bfloat16()
-    wt = (torch.randn(64, 64, 2, 2, generator=g) * 0.1).to(DEV).bfloat16()
+    x = (torch.randn(1, 20, 28, 64, generator=g) * 0.5).to(DEV).half()
+    wt = (torch.randn(64, 64, 2, 2, generator=g) * 0.1).to(DEV).half()
     wp = wt.permute(2, 3, 1, 0).reshape(256, 64).contiguous()
     b = torch.randn(64, generator=g).to(DEV)
-    out = torch.empty((1, 40, 56, 64), device=DEV, dtype=torch.bfloat16)
-    _lib.check(L.ytk_op_conv2d_bf16(_lib.ptr(x), 1, 20, 28, 64, 64, _lib.ptr(wp), _lib.ptr(b.repeat(4).contiguous()), 1,
+    out = torch.empty((1, 40, 56, 64), device=DEV, dtype=torch.float16)
+    _lib.check(L.ytk_op_conv2d_f16(_lib.ptr(x), 1, 20, 28, 64, 64, _lib.ptr(wp), _lib.ptr(b.repeat(4).contiguous()), 1,
                                     1, 1, 0, 1, 256, None, 0, 0, _lib.ptr(out), 0, 64, 1, 1, None))
     torch.cuda.synchronize()
     ref = F.conv_transpose2d(x.float().permute(0, 3, 1, 2), wt.float(), b, stride=2).relu().permute(0, 2, 3, 1)
@@ -104,9 +104,9 @@ def test_conv_transpose_shuffle_epilogue():
 
 def test_bad_arguments_fail_loudly():
     L = _lib_()
-    x = torch.zeros(1, 8, 8, 48, device=DEV, dtype=torch.bfloat16)
-    w = torch.zeros(64, 1, 1, 48, device=DEV, dtype=torch.bfloat16)
-    out = torch.zeros(1, 8, 8, 64, device=DEV, dtype=torch.bfloat16)
-    st = L.ytk_op_conv2d_bf16(_lib.ptr(x), 1, 8, 8, 48, 48, _lib.ptr(w), None, 1, 1, 1, 0, 1, 64, None, 0, 0,
+    x = torch.zeros(1, 8, 8, 48, device=DEV, dtype=torch.float16)
+    w = torch.zeros(64, 1, 1, 48, device=DEV, dtype=torch.float16)
+    out = torch.zeros(1, 8, 8, 64, device=DEV, dtype=torch.float16)
+    st = L.ytk_op_conv2d_f16(_lib.ptr(x), 1, 8, 8, 48, 48, _lib.ptr(w), None, 1, 1, 1, 0, 1, 64, None, 0, 0,
                               _lib.ptr(out), 0, 64, 0, 0, None)
     assert st != 0 and b"multiple of 64" in L.ytk_last_error()

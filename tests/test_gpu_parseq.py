@@ -1,9 +1,10 @@
 """GPU: PARSeq engine against the CPU oracle.
 
-Stated tolerances: encoder memory relative Frobenius error < 1 %; logits of the first AR step (no token feedback)
-max |d| < 3 % of the logit standard deviation + 0.05; decoded strings CHARACTER-IDENTICAL for every row whose greedy
-decisions are not near-ties - a row may differ from the oracle only if the oracle's own top-2 margin at some AR step
-is below TAU (bf16 operands cannot resolve smaller gaps; with trained, peaked models such ties are rare)."""
+Stated tolerances (fp16 operands, fp32 accumulation): logits of rows that took the same token path max |d| < 0.5 % of
+the logit standard deviation + 0.01; decoded strings CHARACTER-IDENTICAL for every row whose greedy decisions are not
+coin flips - a row may differ from the oracle only if the oracle's own top-2 margin at some decision of that row is
+below TAU = 0.1 logits (logit std ~6), and every other row MUST match; scores within 0.05 in the log domain.
+tests/test_gpu_parseq_identity.py repeats the identity check on 2 x 2048 crops and records the margin histogram."""
 import os
 
 import numpy as np
@@ -17,7 +18,8 @@ from yomitoku_b200 import TextRecognizer
 from yomitoku_b200.synth import synthetic_page
 
 pytestmark = pytest.mark.gpu
-TAU = 0.6   # logit units; the peaked test weights have a logit std of ~6
+TAU = 0.1   # logit units; the peaked test weights have a logit std of ~6
+LOGIT_TOL = (0.005, 0.01)   # max |d| < 0.5 % of the logit std + 0.01 on rows that took the same token path
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -33,16 +35,19 @@ def _margin_aware_equal(ids_gpu, logits_ref, aux, tag):
     ids_ref = logits_ref.argmax(-1).numpy()
     ref_margin = logits_ref.topk(2, -1).values
     ref_margin = (ref_margin[..., 0] - ref_margin[..., 1]).numpy()
-    n_same = 0
+    n_same = n_low = 0
     for b in range(ids_ref.shape[0]):
         # compare up to and including the first EOS (what the tokenizer reads)
         row = ids_ref[b].tolist()
         n = row.index(0) + 1 if 0 in row else len(row)
+        low = min(float(aux["ar_margin"][b].min()), float(ref_margin[b, :n].min()))
+        n_low += low < TAU
         if np.array_equal(ids_gpu[b, :n], ids_ref[b, :n]):
             n_same += 1
             continue
-        low = min(float(aux["ar_margin"][b].min()), float(ref_margin[b, :n].min()))
         assert low < TAU, "%s row %d differs although every decision margin >= %.2f (min %.3f)" % (tag, b, TAU, low)
+    # every row outside the coin-flip set matched (asserted above); inside it most still do
+    assert n_same >= ids_ref.shape[0] - n_low
     return n_same
 
 
@@ -61,14 +66,13 @@ def test_model_seam_vs_oracle(name, B, W, seed):
     ref, aux = ops.parseq_forward(sd, spec, img, return_aux=True)
     assert got.shape == ref.shape == (B, spec.max_label_length + 1, spec.num_classes)
     n_same = _margin_aware_equal(got.argmax(-1).numpy(), ref, aux, name)
-    assert n_same >= int(0.6 * B)
     # rows whose AR decisions all had real margins took the same token path: their refined logits agree closely
     # (a row with a near-tie may emit a different token and still be "repaired" to the same ids by the refinement)
     safe = [b for b in range(B) if float(aux["ar_margin"][b].min()) >= TAU and
             torch.equal(got[b].argmax(-1), ref[b].argmax(-1))]
     if safe:
         d = (got[safe] - ref[safe]).abs().max().item()
-        assert d < 0.03 * ref.std().item() + 0.05, d
+        assert d < LOGIT_TOL[0] * ref.std().item() + LOGIT_TOL[1], d
 
 
 @pytest.mark.parametrize("over", [{"decode_ar": 0}, {"decode_ar": 0, "refine_iters": 0}, {"refine_iters": 2},
@@ -89,11 +93,10 @@ def test_decoder_switches_vs_oracle(over):
     ref, aux = ops.parseq_forward(sd, spec, img, return_aux=True)
     assert got.shape == ref.shape
     n_same = _margin_aware_equal(got.argmax(-1).numpy(), ref, aux, str(over))
-    assert n_same >= 3
     same = [b for b in range(6) if torch.equal(got[b].argmax(-1), ref[b].argmax(-1)) and
             float(aux["ar_margin"][b].min()) >= TAU]
     if same:
-        assert (got[same] - ref[same]).abs().max().item() < 0.03 * ref.std().item() + 0.05
+        assert (got[same] - ref[same]).abs().max().item() < LOGIT_TOL[0] * ref.std().item() + LOGIT_TOL[1]
 
 
 def test_reference_fixture_strings(charset_v2):
@@ -105,8 +108,8 @@ def test_reference_fixture_strings(charset_v2):
         p = rec.model(torch.from_numpy(z["img"])).softmax(-1)
         strings, scores = rec.tokenizer.decode(p)
         assert strings == list(z["strings"]), tag
-        # a score is a product of ~10 probabilities, each carrying the bf16 logit error: compare in the log domain
-        assert np.allclose(np.log(scores), np.log(z["scores"]), atol=0.35), tag
+        # a score is a product of ~10 probabilities: compare in the log domain (the orientation fallback thresholds on it)
+        assert np.allclose(np.log(scores), np.log(z["scores"]), atol=0.05), tag
 
 
 def test_repetition_stop_and_refine_off():
@@ -141,13 +144,13 @@ def test_ragged_crops_match_reference_batching(charset_v2):
                                                max_batch_size=64, return_aux=True)
     assert len(aux["plan"]) > 1                       # several reference mini-batches with different padded widths
     assert out.directions == dirs and out.points == quads
+    for a, b, m in zip(out.contents, preds, aux["min_margin"]):
+        assert a == b or m < TAU, (a, b, m)           # identical unless the oracle's own decision was a coin flip
     same = sum(a == b for a, b in zip(out.contents, preds))
-    assert same >= int(0.7 * len(quads)), same
-    # score = product of ~10 probabilities; near-tie positions (p ~ 0.4) move visibly under bf16 logit noise, so the
-    # bound is statistical: typical rows agree to 10 %, no row is off by more than a factor e^1.5
+    assert same >= len(quads) - sum(m < TAU for m in aux["min_margin"])
     dl = [abs(np.log(max(sa, 1e-30)) - np.log(max(sb, 1e-30)))
           for a, b, sa, sb in zip(out.contents, preds, out.scores, scores) if a == b]
-    assert np.median(dl) < 0.1 and max(dl) < 1.5, (np.median(dl), max(dl))
+    assert max(dl) < 0.05, (np.median(dl), max(dl))
 
 
 def test_large_model_ragged_vs_seam_consistency():

@@ -28,12 +28,12 @@ def _declare(lib):
     lib.ytk_gemm_profile_end.restype = c_int
     lib.ytk_gemm_profile_end.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                          ctypes.POINTER(c_ll)]
-    lib.ytk_op_conv2d_bf16.restype = c_int
-    lib.ytk_op_conv2d_bf16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p,
+    lib.ytk_op_conv2d_f16.restype = c_int
+    lib.ytk_op_conv2d_f16.argtypes = [c_void_p, c_int, c_int, c_int, c_int, c_ll, c_void_p, c_void_p,
                                        c_int, c_int, c_int, c_int, c_int, c_int, c_void_p, c_int, c_ll,
                                        c_void_p, c_int, c_ll, c_int, c_int, c_void_p]
-    lib.ytk_op_linear_bf16.restype = c_int
-    lib.ytk_op_linear_bf16.argtypes = [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
+    lib.ytk_op_linear_f16.restype = c_int
+    lib.ytk_op_linear_f16.argtypes = [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                        c_ll, c_void_p, c_int, c_ll, c_int, c_void_p]
 
 

@@ -93,7 +93,7 @@ int ytk_gemm_profile_end(double* flops, double* ms, long long* launches) {
     return ytk::gemm_profile_end(flops, ms, launches) ? YTK_ERR : YTK_OK;
 }
 
-int ytk_op_conv2d_bf16(const void* in, int N, int H, int W, int Cin, long long in_ld, const void* w, const float* bias,
+int ytk_op_conv2d_f16(const void* in, int N, int H, int W, int Cin, long long in_ld, const void* w, const float* bias,
                        int kh, int kw, int stride, int pad, int dil, int Cout, const void* resid, int resid_f32,
                        long long ldr, void* out, int out_f32, long long ldc, int act, int mode, void* cuda_stream) {
     ytk::ConvGeom g{N, H, W, Cin, in_ld, kh, kw, stride, pad, dil, Cout};
@@ -112,7 +112,7 @@ int ytk_op_conv2d_bf16(const void* in, int N, int H, int W, int Cin, long long i
     return ytk::gemm_plan_launch(&plan, static_cast<cudaStream_t>(cuda_stream)) ? YTK_ERR : YTK_OK;
 }
 
-int ytk_op_linear_bf16(const void* A, long long lda, int M, int K, const void* W, int N, const float* bias,
+int ytk_op_linear_f16(const void* A, long long lda, int M, int K, const void* W, int N, const float* bias,
                        const void* resid, int resid_f32, long long ldr, void* out, int out_f32, long long ldc, int act,
                        void* cuda_stream) {
     ytk::Epilogue e;
@@ -250,7 +250,7 @@ int ytk_dbnet_debug_tensor(ytk_dbnet* h, int n_pages, int Hn, int Wn, const char
     } else {
         float* tmp = nullptr;
         if (cudaMalloc(&tmp, n * 4) != cudaSuccess) return YTK_ERR;
-        ytk::launch_bf16_to_f32(t.p, tmp, n, 0);
+        ytk::launch_op_to_f32(t.p, tmp, n, 0);
         cudaError_t err = cudaMemcpy(host_out, tmp, n * 4, cudaMemcpyDeviceToHost);
         cudaFree(tmp);
         if (err != cudaSuccess) return YTK_ERR;

@@ -17,14 +17,6 @@
 namespace ytk {
 
 // ---------------------------------------------------------------------------------------------- helpers
-static inline uint16_t f2bf(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;  // NaN
-    u += 0x7fffu + ((u >> 16) & 1u);                      // round to nearest even
-    return (uint16_t)(u >> 16);
-}
-
 #define CK(x)                                                                   \
     do {                                                                        \
         cudaError_t e_ = (x);                                                   \
@@ -81,7 +73,7 @@ static int pack_conv(const TensorView* w, int Cout, int Cin, int kh, int kw, con
             for (int r = 0; r < kh; ++r)
                 for (int s = 0; s < kw; ++s) {
                     const float v = w->data[(((size_t)co * Cin + ci) * kh + r) * kw + s] * (scale ? scale[co] : 1.f);
-                    p[(((size_t)co * kh + r) * kw + s) * Cin + ci] = f2bf(v);
+                    p[(((size_t)co * kh + r) * kw + s) * Cin + ci] = f2op_host(v);
                 }
     return upload(p.data(), p.size() * 2, dev);
 }
@@ -136,7 +128,7 @@ int DbnetModel::load(const WeightSet& ws) {
                 for (int r = 0; r < 7; ++r)
                     for (int s = 0; s < 7; ++s)
                         p[((size_t)co * 7 + r) * 64 + s * 8 + c] =
-                            f2bf(w->data[(((size_t)co * 3 + c) * 7 + r) * 7 + s] * scale[co]);
+                            f2op_host(w->data[(((size_t)co * 3 + c) * 7 + r) * 7 + s] * scale[co]);
         if (upload(p.data(), p.size() * 2, &stem.w)) return 1;
         void* d = nullptr;
         if (upload(shift.data(), 64 * 4, &d)) return 1;
@@ -210,7 +202,7 @@ int DbnetModel::load(const WeightSet& ws) {
                 for (int co = 0; co < 64; ++co) {
                     const int row = (i * 2 + j) * 64 + co;
                     for (int ci = 0; ci < 64; ++ci)
-                        p[(size_t)row * 64 + ci] = f2bf(w->data[(((size_t)ci * 64 + co) * 2 + i) * 2 + j] * scale[co]);
+                        p[(size_t)row * 64 + ci] = f2op_host(w->data[(((size_t)ci * 64 + co) * 2 + i) * 2 + j] * scale[co]);
                     bias[row] = b->data[co] * scale[co] + shift[co];
                 }
         if (upload(p.data(), p.size() * 2, &convt1.w)) return 1;
@@ -372,7 +364,7 @@ int DbnetEngine::build(const DbnetModel& m, int n, int Hn_, int Wn_) {
     // ---- out_proj 3x3 convs written (through bilinear upsampling) into the concat buffer, order p4,p3,p2,p1
     void* fuse;
     if (alloc("fuse", N, H4, W4, 256, false, &fuse)) return 1;
-    if (add_conv(m.outproj[0], f[0], N, H4, W4, 256, reinterpret_cast<__nv_bfloat16*>(fuse) + 192, 256, ACT_NONE))
+    if (add_conv(m.outproj[0], f[0], N, H4, W4, 256, reinterpret_cast<op_t*>(fuse) + 192, 256, ACT_NONE))
         return 1;
     for (int i = 1; i < 4; ++i) {
         void* p;

@@ -9,12 +9,12 @@
 namespace ytk {
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-    f[0] = bf16_lo(u.x); f[1] = bf16_hi(u.x); f[2] = bf16_lo(u.y); f[3] = bf16_hi(u.y);
-    f[4] = bf16_lo(u.z); f[5] = bf16_hi(u.z); f[6] = bf16_lo(u.w); f[7] = bf16_hi(u.w);
+    f[0] = op_lo(u.x); f[1] = op_hi(u.x); f[2] = op_lo(u.y); f[3] = op_hi(u.y);
+    f[4] = op_lo(u.z); f[5] = op_hi(u.z); f[6] = op_lo(u.w); f[7] = op_hi(u.w);
 }
 __device__ __forceinline__ uint4 pack8(const float* f) {
     uint4 u;
-    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]); u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+    u.x = pack_op(f[0], f[1]); u.y = pack_op(f[2], f[3]); u.z = pack_op(f[4], f[5]); u.w = pack_op(f[6], f[7]);
     return u;
 }
 
@@ -52,7 +52,7 @@ __device__ __forceinline__ AreaTap area_tap(int d, double scale, int ssize) {
 }
 
 __global__ void preprocess_kernel(const uint8_t* __restrict__ src, int n_img, int H0, int W0, int Hn, int Wn,
-                                  __nv_bfloat16* __restrict__ dst) {
+                                  op_t* __restrict__ dst) {
     const int Hp = Hn + 6, Wp = Wn + 8;
     const long long total = (long long)n_img * Hp * Wp;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -94,7 +94,7 @@ int launch_preprocess(const uint8_t* src, int n_img, int H0, int W0, int Hn, int
     const long long total = (long long)n_img * (Hn + 6) * (Wn + 8);
     const int threads = 256;
     preprocess_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, st>>>(
-        src, n_img, H0, W0, Hn, Wn, reinterpret_cast<__nv_bfloat16*>(dst));
+        src, n_img, H0, W0, Hn, Wn, reinterpret_cast<op_t*>(dst));
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
@@ -102,7 +102,7 @@ int launch_preprocess(const uint8_t* src, int n_img, int H0, int W0, int Hn, int
 // Model-level seam: the reference hands DBNet a normalised (N,3,H,W) fp32 tensor (text_detector.py:127-129).  Repack
 // it into the same zero-padded 8-channel NHWC bf16 canvas the fused u8 path writes.
 __global__ void pack_nchw_kernel(const float* __restrict__ src, int n_img, int Hn, int Wn,
-                                 __nv_bfloat16* __restrict__ dst) {
+                                 op_t* __restrict__ dst) {
     const int Hp = Hn + 6, Wp = Wn + 8;
     const long long total = (long long)n_img * Hp * Wp;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,7 +122,7 @@ __global__ void pack_nchw_kernel(const float* __restrict__ src, int n_img, int H
 int launch_pack_nchw_f32(const float* src, int n_img, int Hn, int Wn, void* dst, cudaStream_t st) {
     const long long total = (long long)n_img * (Hn + 6) * (Wn + 8);
     pack_nchw_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(src, n_img, Hn, Wn,
-                                                                       reinterpret_cast<__nv_bfloat16*>(dst));
+                                                                       reinterpret_cast<op_t*>(dst));
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
@@ -173,7 +173,7 @@ int launch_maxpool(const void* in, void* out, int n_img, int H, int W, int C, cu
 // clamped at 0; the upper neighbour is clamped to in-1.
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void upsample_bilinear_kernel(const uint4* __restrict__ src, int n_img, int Hs, int Ws, int C8,
-                                         __nv_bfloat16* __restrict__ dst, int Hd, int Wd, long long ldd, int coff,
+                                         op_t* __restrict__ dst, int Hd, int Wd, long long ldd, int coff,
                                          int accumulate) {
     const long long total = (long long)n_img * Hd * Wd * C8;
     const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -210,7 +210,7 @@ int launch_upsample(const void* src, int n_img, int Hs, int Ws, int C, void* dst
                     int coff, int accumulate, cudaStream_t st) {
     const long long total = (long long)n_img * Hd * Wd * (C / 8);
     upsample_bilinear_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
-        reinterpret_cast<const uint4*>(src), n_img, Hs, Ws, C / 8, reinterpret_cast<__nv_bfloat16*>(dst), Hd, Wd, ldd,
+        reinterpret_cast<const uint4*>(src), n_img, Hs, Ws, C / 8, reinterpret_cast<op_t*>(dst), Hd, Wd, ldd,
         coff, accumulate);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
@@ -429,12 +429,12 @@ int launch_convt2_sigmoid(const void* x, int n_img, int H, int W, const float* h
 }
 
 // fp32 -> bf16 conversion helper for weight upload / debug
-__global__ void bf16_to_f32_kernel(const __nv_bfloat16* __restrict__ in, float* __restrict__ out, long long n) {
+__global__ void op_to_f32_kernel(const op_t* __restrict__ in, float* __restrict__ out, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __bfloat162float(in[i]);
+    if (i < n) out[i] = op2f(in[i]);
 }
-int launch_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t st) {
-    bf16_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), out, n);
+int launch_op_to_f32(const void* in, float* out, long long n, cudaStream_t st) {
+    op_to_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(reinterpret_cast<const op_t*>(in), out, n);
     return cudaGetLastError() != cudaSuccess;
 }
 

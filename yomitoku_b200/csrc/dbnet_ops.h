@@ -16,6 +16,6 @@ int launch_asf(const void* a, void* fuse, int n_img, int H, int W, const float* 
                float* m, cudaStream_t st);
 int launch_convt2_sigmoid(const void* x, int n_img, int H, int W, const float* host_w, float bias, float* prob,
                           cudaStream_t st);
-int launch_bf16_to_f32(const void* in, float* out, long long n, cudaStream_t st);
+int launch_op_to_f32(const void* in, float* out, long long n, cudaStream_t st);
 
 }  // namespace ytk

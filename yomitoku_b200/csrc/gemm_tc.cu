@@ -275,8 +275,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     } else if (warp == 1) {
         // ------------------------------------------------------------------ MMA issuer (pair mode: the leader only)
         if (lane == 0 && (cl == 1 || leader)) {
-            constexpr uint32_t idesc = umma_idesc_bf16(kBlockM, BLOCK_N);
-            constexpr uint32_t idesc2 = umma_idesc_bf16(2 * kBlockM, BLOCK_N);
+            constexpr uint32_t idesc = umma_idesc_op(kBlockM, BLOCK_N);
+            constexpr uint32_t idesc2 = umma_idesc_op(2 * kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
             int acc = 0;
@@ -295,10 +295,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int k = 0; k < kBlockK / 16; ++k) {
                         // advance 16 bf16 = 32 B inside the 128 B swizzle row: +2 in the (addr >> 4) field
                         if constexpr (PAIR)
-                            umma_bf16_cg2(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                            umma_op_cg2(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                                           idesc2, (kb | k) != 0 ? 1u : 0u);
                         else
-                            umma_bf16(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
+                            umma_op(d_tmem, da + static_cast<uint64_t>(2 * k), db + static_cast<uint64_t>(2 * k),
                                       idesc, (kb | k) != 0 ? 1u : 0u);
                     }
                     // frees the smem slot once these MMAs have read it (on both CTAs of a pair)
@@ -491,17 +491,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         if (fullc) {
 #pragma unroll
                             for (int j = 0; j < 4; ++j) {
-                                f[8 * j + 0] += bf16_lo(dres[j].x); f[8 * j + 1] += bf16_hi(dres[j].x);
-                                f[8 * j + 2] += bf16_lo(dres[j].y); f[8 * j + 3] += bf16_hi(dres[j].y);
-                                f[8 * j + 4] += bf16_lo(dres[j].z); f[8 * j + 5] += bf16_hi(dres[j].z);
-                                f[8 * j + 6] += bf16_lo(dres[j].w); f[8 * j + 7] += bf16_hi(dres[j].w);
+                                f[8 * j + 0] += op_lo(dres[j].x); f[8 * j + 1] += op_hi(dres[j].x);
+                                f[8 * j + 2] += op_lo(dres[j].y); f[8 * j + 3] += op_hi(dres[j].y);
+                                f[8 * j + 4] += op_lo(dres[j].z); f[8 * j + 5] += op_hi(dres[j].z);
+                                f[8 * j + 6] += op_lo(dres[j].w); f[8 * j + 7] += op_hi(dres[j].w);
                             }
                         } else if (row_ok) {
-                            const __nv_bfloat16* rp =
-                                reinterpret_cast<const __nv_bfloat16*>(args.resid) + opix * args.ldr + ocol;
+                            const op_t* rp =
+                                reinterpret_cast<const op_t*>(args.resid) + opix * args.ldr + ocol;
 #pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (col0 + j < args.Cout) f[j] += __bfloat162float(rp[j]);
+                                if (col0 + j < args.Cout) f[j] += op2f(rp[j]);
                         }
                     }
                     if (args.act == ACT_RELU) {
@@ -528,21 +528,21 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                     if (col0 + j < args.Cout) op[j] = f[j];
                             }
                         } else {
-                            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(args.out) + opix * args.ldc + ocol;
+                            op_t* op = reinterpret_cast<op_t*>(args.out) + opix * args.ldc + ocol;
                             if (fullc) {
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
                                     uint4 o;
-                                    o.x = pack_bf16(f[8 * j + 0], f[8 * j + 1]);
-                                    o.y = pack_bf16(f[8 * j + 2], f[8 * j + 3]);
-                                    o.z = pack_bf16(f[8 * j + 4], f[8 * j + 5]);
-                                    o.w = pack_bf16(f[8 * j + 6], f[8 * j + 7]);
+                                    o.x = pack_op(f[8 * j + 0], f[8 * j + 1]);
+                                    o.y = pack_op(f[8 * j + 2], f[8 * j + 3]);
+                                    o.z = pack_op(f[8 * j + 4], f[8 * j + 5]);
+                                    o.w = pack_op(f[8 * j + 6], f[8 * j + 7]);
                                     reinterpret_cast<uint4*>(op)[j] = o;
                                 }
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < args.Cout) op[j] = __float2bfloat16(f[j]);
+                                    if (col0 + j < args.Cout) op[j] = f2op(f[j]);
                             }
                         }
                     }
@@ -602,10 +602,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                     for (int j = 0; j < CPP / 8; ++j) {
                                         const uint4 r = rp[j];
                                         const int b = p * CPP + 8 * j;
-                                        f[b + 0] += bf16_lo(r.x); f[b + 1] += bf16_hi(r.x);
-                                        f[b + 2] += bf16_lo(r.y); f[b + 3] += bf16_hi(r.y);
-                                        f[b + 4] += bf16_lo(r.z); f[b + 5] += bf16_hi(r.z);
-                                        f[b + 6] += bf16_lo(r.w); f[b + 7] += bf16_hi(r.w);
+                                        f[b + 0] += op_lo(r.x); f[b + 1] += op_hi(r.x);
+                                        f[b + 2] += op_lo(r.y); f[b + 3] += op_hi(r.y);
+                                        f[b + 4] += op_lo(r.z); f[b + 5] += op_hi(r.z);
+                                        f[b + 6] += op_lo(r.w); f[b + 7] += op_hi(r.w);
                                     }
                                 }
                                 __syncwarp();
@@ -639,10 +639,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                                 for (int j = 0; j < CPP / 8; ++j) {
                                     const int b = p * CPP + 8 * j;
                                     uint4 o;
-                                    o.x = pack_bf16(f[b + 0], f[b + 1]);
-                                    o.y = pack_bf16(f[b + 2], f[b + 3]);
-                                    o.z = pack_bf16(f[b + 4], f[b + 5]);
-                                    o.w = pack_bf16(f[b + 6], f[b + 7]);
+                                    o.x = pack_op(f[b + 0], f[b + 1]);
+                                    o.y = pack_op(f[b + 2], f[b + 3]);
+                                    o.z = pack_op(f[b + 4], f[b + 5]);
+                                    o.w = pack_op(f[b + 6], f[b + 7]);
                                     wp[j] = o;
                                 }
                             }
@@ -712,7 +712,7 @@ static EncodeTiledFn get_encode_fn() {
     return fn;
 }
 
-int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
+int make_tmap_op_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
                       const uint32_t box[4]) {
     EncodeTiledFn fn = get_encode_fn();
     if (!fn) {
@@ -723,7 +723,7 @@ int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], 
     cuuint64_t gs[3] = {strides_b[0], strides_b[1], strides_b[2]};
     cuuint32_t bx[4] = {box[0], box[1], box[2], box[3]};
     cuuint32_t es[4] = {1, 1, 1, 1};
-    CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
+    CUresult r = fn(m, kOpFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<void*>(base), gd, gs, bx, es,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
@@ -821,7 +821,7 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
     uint64_t dims[4] = {(uint64_t)Ktot, (uint64_t)Cout, 1, 1};
     uint64_t strides[3] = {(uint64_t)Ktot * 2, (uint64_t)Ktot * 2 * Cout, (uint64_t)Ktot * 2 * Cout};
     uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)(plan->block_n / a.cluster), 1, 1};
-    if (make_tmap_bf16_4d(&plan->maps.b, w_packed, dims, strides, box)) return 1;
+    if (make_tmap_op_4d(&plan->maps.b, w_packed, dims, strides, box)) return 1;
     plan->grid = tiles < num_sms() ? tiles : num_sms();
     if (plan->grid < 1) plan->grid = 1;
     return 0;
@@ -859,7 +859,7 @@ int conv_plan_create(GemmPlan* plan, const void* in, const ConvGeom& g, const vo
     if (g.stride == 1) {
         uint64_t dims[4] = {(uint64_t)g.Cin, (uint64_t)g.W, (uint64_t)g.H, (uint64_t)g.N};
         uint64_t strides[3] = {(uint64_t)g.in_ld * es, (uint64_t)g.in_ld * es * g.W, (uint64_t)g.in_ld * es * g.W * g.H};
-        if (make_tmap_bf16_4d(&plan->maps.a[0], base, dims, strides, box)) return 1;
+        if (make_tmap_op_4d(&plan->maps.a[0], base, dims, strides, box)) return 1;
         for (int i = 1; i < 4; ++i) plan->maps.a[i] = plan->maps.a[0];
         int t = 0;
         for (int r = 0; r < g.kh; ++r)
@@ -894,7 +894,7 @@ int conv_plan_create(GemmPlan* plan, const void* in, const ConvGeom& g, const vo
             uint64_t strides[3] = {(uint64_t)g.in_ld * es * 2, (uint64_t)g.in_ld * es * g.W * 2,
                                    (uint64_t)g.in_ld * es * g.W * g.H};
             const char* pbase = base + ((size_t)ph * g.W + pw) * g.in_ld * es;
-            if (make_tmap_bf16_4d(&plan->maps.a[p], pbase, dims, strides, box)) return 1;
+            if (make_tmap_op_4d(&plan->maps.a[p], pbase, dims, strides, box)) return 1;
             if (first < 0) first = p;
         }
         for (int p = 0; p < 4; ++p)
@@ -930,7 +930,7 @@ int gemm_plan_create(GemmPlan* plan, const void* A, long long lda, int M, int K,
     uint64_t dims[4] = {(uint64_t)K, (uint64_t)M, 1, 1};
     uint64_t strides[3] = {(uint64_t)lda * 2, (uint64_t)lda * 2 * M, (uint64_t)lda * 2 * M};
     uint32_t box[4] = {(uint32_t)kBlockK, 128, 1, 1};
-    if (make_tmap_bf16_4d(&plan->maps.a[0], A, dims, strides, box)) return 1;
+    if (make_tmap_op_4d(&plan->maps.a[0], A, dims, strides, box)) return 1;
     for (int i = 1; i < 4; ++i) plan->maps.a[i] = plan->maps.a[0];
     plan->flops = 2.0 * M * (double)N * K;
     return finish_plan(plan, Wt, K, N, e, /*allow_pair=*/true);
@@ -957,7 +957,7 @@ int stem_plan_create(GemmPlan* plan, const void* in_padded, int N, int Hn, int W
         // input row 2*ho + r = 2*(ho + r/2) + (r & 1): phase p = r & 1 starts at padded row p, steps 2 rows
         uint64_t dims[4] = {64, (uint64_t)Wo, (uint64_t)((Hp - p + 1) / 2), (uint64_t)N};
         uint64_t strides[3] = {32, 2 * row_b, (uint64_t)Hp * row_b};
-        if (make_tmap_bf16_4d(&plan->maps.a[p], base + p * row_b, dims, strides, box)) return 1;
+        if (make_tmap_op_4d(&plan->maps.a[p], base + p * row_b, dims, strides, box)) return 1;
     }
     plan->maps.a[2] = plan->maps.a[0];
     plan->maps.a[3] = plan->maps.a[1];

@@ -105,7 +105,7 @@ void gemm_plan_set_m(GemmPlan* plan, int M);
 int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream);
 
 // Generic 4-D tiled bf16 tensor map with 128B swizzle (dims/strides innermost first; strides in bytes for dims 1..3).
-int make_tmap_bf16_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
+int make_tmap_op_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
                       const uint32_t box[4]);
 
 void set_error(const char* fmt, ...);

@@ -31,14 +31,6 @@ namespace ytk {
         }                                                                       \
     } while (0)
 
-static inline uint16_t f2bf(float f) {
-    uint32_t u;
-    memcpy(&u, &f, 4);
-    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;
-    u += 0x7fffu + ((u >> 16) & 1u);
-    return (uint16_t)(u >> 16);
-}
-
 // ---------------------------------------------------------------------------------------------- model
 static int up(std::vector<void*>& owned, const void* host, size_t bytes, void** dev) {
     CK(cudaMalloc(dev, bytes));
@@ -51,7 +43,7 @@ static int load_linear(std::vector<void*>& owned, const float* w, const float* b
     const int Kp = (K + 63) / 64 * 64;
     std::vector<uint16_t> p((size_t)N * Kp, 0);
     for (int n = 0; n < N; ++n)
-        for (int k = 0; k < K; ++k) p[(size_t)n * Kp + k] = f2bf(w[(size_t)n * K + k]);
+        for (int k = 0; k < K; ++k) p[(size_t)n * Kp + k] = f2op_host(w[(size_t)n * K + k]);
     if (up(owned, p.data(), p.size() * 2, &out->w)) return 1;
     void* d = nullptr;
     if (up(owned, b, (size_t)N * 4, &d)) return 1;
@@ -289,7 +281,7 @@ int ParseqModel::load(const WeightSet& ws, const ParseqCfg& c) {
                 const float* wr = sw->data + (size_t)n * D;
                 double acc = sb->data[n];
                 for (int k = 0; k < D; ++k) acc += (double)wr[k] * ln[k];
-                q[(size_t)i * Dp + hdm[n]] = f2bf((float)acc * (padded ? qs_d : 1.f));
+                q[(size_t)i * Dp + hdm[n]] = f2op_host((float)acc * (padded ? qs_d : 1.f));
             }
         }
         if (up(owned, q.data(), q.size() * 2, &q_self)) return 1;
@@ -304,7 +296,7 @@ int ParseqModel::load(const WeightSet& ws, const ParseqCfg& c) {
             const float* wr = sw->data + (size_t)(D + n) * D;
             double acc = sb->data[D + n];
             for (int k = 0; k < D; ++k) acc += (double)wr[k] * l0[k];
-            kv[(n / D) * Dp + hdm[n % D]] = f2bf((float)acc);
+            kv[(n / D) * Dp + hdm[n % D]] = f2op_host((float)acc);
         }
         if (up(owned, kv.data(), kv.size() * 2, &ckv0)) return 1;
     }
@@ -495,7 +487,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
     for (const EncBlock& bk : m->blocks) {
         if (launch_layernorm(x, Ti, D, m->Dr, bk.ln1.g, bk.ln1.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
         if (Lin::run(h, D, Ti, bk.qkv, qkv, 3 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
-        const __nv_bfloat16* q = reinterpret_cast<const __nv_bfloat16*>(qkv);
+        const op_t* q = reinterpret_cast<const op_t*>(qkv);
         if (launch_flash_attention(q, 3 * D, q + D, q + 2 * D, 3 * D, att, D, seqs_enc, B, max_ntok, c.enc_heads, hd_e,
                                    0, st))
             return 1;
@@ -560,7 +552,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
                 split_row = best;
             }
         }
-        auto b16 = [](void* p, size_t elems) { return static_cast<void*>(reinterpret_cast<__nv_bfloat16*>(p) + elems); };
+        auto b16 = [](void* p, size_t elems) { return static_cast<void*>(reinterpret_cast<op_t*>(p) + elems); };
         Part parts[2];
         for (int k = 0; k < nparts; ++k) {
             Part& p = parts[k];
@@ -654,7 +646,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             flops += p.step_flops;
             if (i + 1 < S) {
                 // K/V of the token that just entered the context: position i+1 of every row of the part
-                p.p_kv.args.out = reinterpret_cast<__nv_bfloat16*>(ckv) + r0 * S * 2 * D + (size_t)(i + 1) * 2 * D;
+                p.p_kv.args.out = reinterpret_cast<op_t*>(ckv) + r0 * S * 2 * D + (size_t)(i + 1) * 2 * D;
                 if (gemm_plan_launch(&p.p_kv, ps)) return 1;
             }
             return 0;
@@ -719,7 +711,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         // rows 0/1 see every key, row q >= 2 the keys <= q, nobody sees keys at/after the first EOS (Appendix A1)
         if (launch_refine_seqs(klen, kpad, B, S, D, seqs_self, st)) return 1;
         {
-            const __nv_bfloat16* ck = reinterpret_cast<const __nv_bfloat16*>(ckv);
+            const op_t* ck = reinterpret_cast<const op_t*>(ckv);
             if (launch_flash_attention(m->q_self, D, ck, ck + D, 2 * D, sa, D, seqs_self, B, S,
                                        c.dec_heads, hd_d, 1, st))
                 return 1;
@@ -728,7 +720,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         if (launch_layernorm(x1, R, D, m->Dr, m->norm1.g, m->norm1.b, 1e-5f, hb, nullptr, m->pos_q, S, nullptr, 0, 1, st))
             return 1;
         if (Lin::run(hb, D, R, m->cross_q, qc, D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
-        const __nv_bfloat16* kv = reinterpret_cast<const __nv_bfloat16*>(memkv);
+        const op_t* kv = reinterpret_cast<const op_t*>(memkv);
         if (launch_flash_attention(qc, D, kv, kv + D, 2 * D, oc, D, seqs_ref, B, S, c.dec_heads, hd_d, 0, st)) return 1;
         for (const CropDesc& d : b.descs) flops += 4.0 * S * (double)d.ntok * D;
         if (Lin::run(oc, D, R, m->cross_out, x1, D, 1, ACT_NONE, x1, 1, D, st, &flops)) return 1;
@@ -740,7 +732,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             return 1;
         for (int r0 = 0; r0 < R; r0 += logits_rows) {
             const int rows = std::min(logits_rows, R - r0);
-            const __nv_bfloat16* a = reinterpret_cast<const __nv_bfloat16*>(hb) + (size_t)r0 * D;
+            const op_t* a = reinterpret_cast<const op_t*>(hb) + (size_t)r0 * D;
             if (Lin::run(a, D, rows, m->head, logits, ldl, 1, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
             // the repetition patch (parseq.py:301-309) applies to the final logits only
             if (launch_softmax_max(logits, ldl, C, rows, S, 1, r0, final ? ar.rep_cut : nullptr, eos, ids, probs, st))

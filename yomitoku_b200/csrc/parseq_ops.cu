@@ -18,7 +18,7 @@ namespace ytk {
 // collate padding value -1.0 (text_recognizer.py:146-156).
 __global__ void patchify_u8_kernel(const uint8_t* __restrict__ crops, const CropDesc* __restrict__ descs, int ph,
                                    int pw, int Kpad, const float* __restrict__ pos_embed, int full_gw, int D,
-                                   __nv_bfloat16* __restrict__ A, float* __restrict__ x) {
+                                   op_t* __restrict__ A, float* __restrict__ x) {
     const CropDesc d = descs[blockIdx.y];
     const int gw = d.wp / pw;
     const int K = 3 * ph * pw;
@@ -38,7 +38,7 @@ __global__ void patchify_u8_kernel(const uint8_t* __restrict__ crops, const Crop
                     v = (u / 255.f - 0.5f) / 0.5f;
                 }
             }
-            A[row * Kpad + k] = __float2bfloat16(v);
+            A[row * Kpad + k] = f2op(v);
         }
         const float* pe = pos_embed + ((long long)gy * full_gw + gx) * D;
         for (int j = threadIdx.x; j < D; j += blockDim.x) x[row * D + j] = pe[j];
@@ -50,14 +50,14 @@ int launch_patchify_u8(const uint8_t* crops, const CropDesc* descs, int ncrops, 
     (void)T;
     dim3 grid(64, ncrops);
     patchify_u8_kernel<<<grid, 128, 0, st>>>(crops, descs, ph, pw, Kpad, pos_embed, full_gw, D,
-                                             reinterpret_cast<__nv_bfloat16*>(A), x);
+                                             reinterpret_cast<op_t*>(A), x);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
 
 __global__ void patchify_f32_kernel(const float* __restrict__ img, int W, int ph, int pw, int Kpad,
                                     const float* __restrict__ pos_embed, int full_gw, int D,
-                                    __nv_bfloat16* __restrict__ A, float* __restrict__ x) {
+                                    op_t* __restrict__ A, float* __restrict__ x) {
     const int b = blockIdx.y;
     const int gw = W / pw, gh = 32 / ph;
     const int ntok = gh * gw;
@@ -73,7 +73,7 @@ __global__ void patchify_f32_kernel(const float* __restrict__ img, int W, int ph
                 const int py = r / pw, px = r - py * pw;
                 v = img[(((long long)b * 3 + c) * 32 + gy * ph + py) * W + gx * pw + px];
             }
-            A[row * Kpad + k] = __float2bfloat16(v);
+            A[row * Kpad + k] = f2op(v);
         }
         const float* pe = pos_embed + ((long long)gy * full_gw + gx) * D;
         for (int j = threadIdx.x; j < D; j += blockDim.x) x[row * D + j] = pe[j];
@@ -84,7 +84,7 @@ int launch_patchify_f32(const float* images, int B, int W, int ph, int pw, int K
                         int full_gw, int D, void* A, float* x, cudaStream_t st) {
     dim3 grid(64, B);
     patchify_f32_kernel<<<grid, 128, 0, st>>>(images, W, ph, pw, Kpad, pos_embed, full_gw, D,
-                                              reinterpret_cast<__nv_bfloat16*>(A), x);
+                                              reinterpret_cast<op_t*>(A), x);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }
@@ -96,7 +96,7 @@ constexpr int kLnVec = 8;  // float4 per lane: D <= 1024, D % 4 == 0
 __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, int M, int D, int d_real,
                                                         const float* __restrict__ gamma,
                                                         const float* __restrict__ beta, float eps,
-                                                        __nv_bfloat16* __restrict__ out_bf16,
+                                                        op_t* __restrict__ out_bf16,
                                                         float* __restrict__ out_f32, const float* __restrict__ addvec,
                                                         int period, const int* __restrict__ add_row0_dev,
                                                         int add_row0, int writeback) {
@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, i
             y.w = (v[i].w - mean) * rstd * g.w + b.w;
             if (out_bf16) {
                 uint2 o;
-                o.x = pack_bf16(y.x, y.y);
-                o.y = pack_bf16(y.z, y.w);
+                o.x = pack_op(y.x, y.y);
+                o.y = pack_op(y.z, y.w);
                 reinterpret_cast<uint2*>(out_bf16 + (long long)warp * D)[j] = o;
             }
             if (out_f32) reinterpret_cast<float4*>(out_f32 + (long long)warp * D)[j] = y;
@@ -178,7 +178,7 @@ int launch_layernorm(float* x, int M, int D, int d_real, const float* gamma, con
     if (M <= 0) return 0;
     const int warps_per_block = 8;
     layernorm_kernel<<<(M + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        x, M, D, d_real, gamma, beta, eps, reinterpret_cast<__nv_bfloat16*>(out_bf16), out_f32, addvec,
+        x, M, D, d_real, gamma, beta, eps, reinterpret_cast<op_t*>(out_bf16), out_f32, addvec,
         period > 0 ? period : 1, add_row0_dev, add_row0, writeback);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
@@ -203,7 +203,7 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t& r0, uint32_t& r1, ui
 __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
                                                uint32_t b0, uint32_t b1) {
     asm volatile(
-        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        "mma.sync.aligned.m16n8k16.row.col.f32." YTK_OPERAND_NAME "." YTK_OPERAND_NAME ".f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
         : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
         : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
@@ -219,19 +219,19 @@ __device__ __forceinline__ void cp_async_wait_group() {
 }
 
 template <int HD, int MASKED, int QT>
-__global__ void __launch_bounds__(QT * 2, QT == 128 ? 2 : 3) flash_attn_kernel(const __nv_bfloat16* __restrict__ Q, long long ldq,
-                                                            const __nv_bfloat16* __restrict__ K,
-                                                            const __nv_bfloat16* __restrict__ V, long long ldkv,
-                                                            __nv_bfloat16* __restrict__ O, long long ldo,
+__global__ void __launch_bounds__(QT * 2, QT == 128 ? 2 : 3) flash_attn_kernel(const op_t* __restrict__ Q, long long ldq,
+                                                            const op_t* __restrict__ K,
+                                                            const op_t* __restrict__ V, long long ldkv,
+                                                            op_t* __restrict__ O, long long ldo,
                                                             const SeqDesc* __restrict__ seqs, float scale_log2) {
     // QT queries per CTA (one warp per 16), 64-key tiles double-buffered with cp.async.  Warps whose 16 queries lie
     // beyond q_len only help loading; the MMA loops stop at the last 16-key group that holds a valid key.
     constexpr int LDS = HD + 8;  // padded row (bf16 elements): 16 B aligned rows, conflict-free ldmatrix
     constexpr int NT = QT * 2;   // threads
     extern __shared__ __align__(16) unsigned char fa_smem[];
-    __nv_bfloat16* sQ = reinterpret_cast<__nv_bfloat16*>(fa_smem);  // [QT][LDS]
-    __nv_bfloat16* sK = sQ + QT * LDS;                               // [2][64][LDS]
-    __nv_bfloat16* sV = sK + 2 * 64 * LDS;                           // [2][64][LDS]
+    op_t* sQ = reinterpret_cast<op_t*>(fa_smem);  // [QT][LDS]
+    op_t* sK = sQ + QT * LDS;                               // [2][64][LDS]
+    op_t* sV = sK + 2 * 64 * LDS;                           // [2][64][LDS]
     const SeqDesc sd = seqs[blockIdx.z];
     const int q0 = blockIdx.x * QT;
     if (q0 >= sd.q_len) return;
@@ -246,8 +246,8 @@ __global__ void __launch_bounds__(QT * 2, QT == 128 ? 2 : 3) flash_attn_kernel(c
     const int ntiles = (k_end + 63) / 64;
     auto load_kv = [&](int t, int buf) {
         const int k0 = t * 64;
-        __nv_bfloat16* dK = sK + buf * 64 * LDS;
-        __nv_bfloat16* dV = sV + buf * 64 * LDS;
+        op_t* dK = sK + buf * 64 * LDS;
+        op_t* dV = sV + buf * 64 * LDS;
         const int rows = min(64, ((k_end - k0 + 15) >> 4) << 4);  // only 16-key groups that are used
         for (int i = threadIdx.x; i < rows * CH; i += NT) {
             const int r = i / CH, c = i - r * CH;
@@ -263,7 +263,7 @@ __global__ void __launch_bounds__(QT * 2, QT == 128 ? 2 : 3) flash_attn_kernel(c
         for (int i = threadIdx.x; i < qrows * CH; i += NT) {
             const int r = i / CH, c = i - r * CH;
             const bool ok = (q0 + r) < sd.q_len;
-            const __nv_bfloat16* src = Q + (long long)(sd.q_off + (ok ? q0 + r : 0)) * ldq + head * HD + c * 8;
+            const op_t* src = Q + (long long)(sd.q_off + (ok ? q0 + r : 0)) * ldq + head * HD + c * 8;
             cp_async16(smem_u32(&sQ[r * LDS + c * 8]), src, ok);
         }
     }
@@ -281,8 +281,8 @@ __global__ void __launch_bounds__(QT * 2, QT == 128 ? 2 : 3) flash_attn_kernel(c
         cp_async_wait_group<1>();  // tile t (and Q) landed; tile t+1 may still be in flight
         __syncthreads();
         if (active) {
-            const __nv_bfloat16* tK = sK + buf * 64 * LDS;
-            const __nv_bfloat16* tV = sV + buf * 64 * LDS;
+            const op_t* tK = sK + buf * 64 * LDS;
+            const op_t* tV = sV + buf * 64 * LDS;
             if (t == 0) {
 #pragma unroll
                 for (int kk = 0; kk < HD / 16; ++kk) {
@@ -363,11 +363,11 @@ __global__ void __launch_bounds__(QT * 2, QT == 128 ? 2 : 3) flash_attn_kernel(c
                     ls[1] += p2 + p3;
                     const int ks = n >> 1;
                     if ((n & 1) == 0) {
-                        pf[ks][0] = pack_bf16(p0, p1);
-                        pf[ks][1] = pack_bf16(p2, p3);
+                        pf[ks][0] = pack_op(p0, p1);
+                        pf[ks][1] = pack_op(p2, p3);
                     } else {
-                        pf[ks][2] = pack_bf16(p0, p1);
-                        pf[ks][3] = pack_bf16(p2, p3);
+                        pf[ks][2] = pack_op(p0, p1);
+                        pf[ks][3] = pack_op(p2, p3);
                     }
                 }
                 l_run[0] += ls[0];
@@ -405,18 +405,18 @@ __global__ void __launch_bounds__(QT * 2, QT == 128 ? 2 : 3) flash_attn_kernel(c
         const int r = r0 + h * 8;
         if (r < sd.q_len) {
             const float inv = 1.f / l_run[h];
-            __nv_bfloat16* op = O + (long long)(sd.o_off + r) * ldo + head * HD + (lane & 3) * 2;
+            op_t* op = O + (long long)(sd.o_off + r) * ldo + head * HD + (lane & 3) * 2;
 #pragma unroll
             for (int i = 0; i < HD / 8; ++i) {
-                *reinterpret_cast<uint32_t*>(op + i * 8) = pack_bf16(o[i][2 * h] * inv, o[i][2 * h + 1] * inv);
+                *reinterpret_cast<uint32_t*>(op + i * 8) = pack_op(o[i][2 * h] * inv, o[i][2 * h + 1] * inv);
             }
         }
     }
 }
 
 template <int HD, int MASKED, int QT>
-static int launch_fa(dim3 grid, const __nv_bfloat16* q, long long ldq, const __nv_bfloat16* k, const __nv_bfloat16* v,
-                     long long ldkv, __nv_bfloat16* o, long long ldo, const SeqDesc* seqs, float scale_log2,
+static int launch_fa(dim3 grid, const op_t* q, long long ldq, const op_t* k, const op_t* v,
+                     long long ldkv, op_t* o, long long ldo, const SeqDesc* seqs, float scale_log2,
                      cudaStream_t st) {
     constexpr int smem = (QT + 4 * 64) * (HD + 8) * 2;
     static bool attr = false;
@@ -440,9 +440,9 @@ int launch_flash_attention(const void* Q, long long ldq, const void* K, const vo
     const int qt = max_q_len > 64 ? 128 : 64;
     dim3 grid((max_q_len + qt - 1) / qt, heads, nseq);
     const float scale_log2 = 1.4426950408889634f / sqrtf((float)head_dim);
-    const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(Q), *k = reinterpret_cast<const __nv_bfloat16*>(K),
-                        *v = reinterpret_cast<const __nv_bfloat16*>(V);
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(O);
+    const op_t *q = reinterpret_cast<const op_t*>(Q), *k = reinterpret_cast<const op_t*>(K),
+                        *v = reinterpret_cast<const op_t*>(V);
+    op_t* o = reinterpret_cast<op_t*>(O);
     int rc = 0;
 #define YTK_FA(HD_)                                                                                      \
     do {                                                                                                 \
@@ -477,11 +477,11 @@ constexpr int kMaxMem = 800;
 // head dim), 32/LPK key subsets run side by side, so every lane keeps several independent 16-byte loads in flight -
 // the step is HBM-bound on exactly these reads (profiles/README_r01.md).
 template <int HD>
-__global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const __nv_bfloat16* __restrict__ qsrc,
-                                                                const __nv_bfloat16* __restrict__ kv, int B, int S,
+__global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const op_t* __restrict__ qsrc,
+                                                                const op_t* __restrict__ kv, int B, int S,
                                                                 int D, int heads, const int* __restrict__ step_dev,
                                                                 const CropDesc* __restrict__ descs,
-                                                                __nv_bfloat16* __restrict__ out) {
+                                                                op_t* __restrict__ out) {
     constexpr int NCH = HD / 8;
     constexpr int LPK = (NCH % 4 == 0) ? 4 : 2;   // lanes per key
     constexpr int CPL = NCH / LPK;                // 16-byte chunks per lane
@@ -494,7 +494,7 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
     const int part = lane % LPK, sub = lane / LPK;
     int nk;
     long long kstride;
-    const __nv_bfloat16 *qp, *kbase;
+    const op_t *qp, *kbase;
     if (mode == 0) {
         const int i = *step_dev;
         nk = i + 1;
@@ -513,8 +513,8 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
 #pragma unroll
     for (int c = 0; c < CPL; ++c) {
         const uint4 u = __ldg(reinterpret_cast<const uint4*>(qp) + part * CPL + c);
-        q[8 * c + 0] = bf16_lo(u.x); q[8 * c + 1] = bf16_hi(u.x); q[8 * c + 2] = bf16_lo(u.y); q[8 * c + 3] = bf16_hi(u.y);
-        q[8 * c + 4] = bf16_lo(u.z); q[8 * c + 5] = bf16_hi(u.z); q[8 * c + 6] = bf16_lo(u.w); q[8 * c + 7] = bf16_hi(u.w);
+        q[8 * c + 0] = op_lo(u.x); q[8 * c + 1] = op_hi(u.x); q[8 * c + 2] = op_lo(u.y); q[8 * c + 3] = op_hi(u.y);
+        q[8 * c + 4] = op_lo(u.z); q[8 * c + 5] = op_hi(u.z); q[8 * c + 6] = op_lo(u.w); q[8 * c + 7] = op_hi(u.w);
     }
     const float scale = rsqrtf((float)HD);
     float* myP = sP[warp];
@@ -528,9 +528,9 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const uint4 u = valid ? __ldg(kp + c) : make_uint4(0, 0, 0, 0);
-            s += q[8 * c + 0] * bf16_lo(u.x) + q[8 * c + 1] * bf16_hi(u.x) + q[8 * c + 2] * bf16_lo(u.y) +
-                 q[8 * c + 3] * bf16_hi(u.y) + q[8 * c + 4] * bf16_lo(u.z) + q[8 * c + 5] * bf16_hi(u.z) +
-                 q[8 * c + 6] * bf16_lo(u.w) + q[8 * c + 7] * bf16_hi(u.w);
+            s += q[8 * c + 0] * op_lo(u.x) + q[8 * c + 1] * op_hi(u.x) + q[8 * c + 2] * op_lo(u.y) +
+                 q[8 * c + 3] * op_hi(u.y) + q[8 * c + 4] * op_lo(u.z) + q[8 * c + 5] * op_hi(u.z) +
+                 q[8 * c + 6] * op_lo(u.w) + q[8 * c + 7] * op_hi(u.w);
         }
 #pragma unroll
         for (int o = 1; o < LPK; o <<= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -561,10 +561,10 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             const uint4 u = __ldg(vp + c);
-            acc[8 * c + 0] += p * bf16_lo(u.x); acc[8 * c + 1] += p * bf16_hi(u.x);
-            acc[8 * c + 2] += p * bf16_lo(u.y); acc[8 * c + 3] += p * bf16_hi(u.y);
-            acc[8 * c + 4] += p * bf16_lo(u.z); acc[8 * c + 5] += p * bf16_hi(u.z);
-            acc[8 * c + 6] += p * bf16_lo(u.w); acc[8 * c + 7] += p * bf16_hi(u.w);
+            acc[8 * c + 0] += p * op_lo(u.x); acc[8 * c + 1] += p * op_hi(u.x);
+            acc[8 * c + 2] += p * op_lo(u.y); acc[8 * c + 3] += p * op_hi(u.y);
+            acc[8 * c + 4] += p * op_lo(u.z); acc[8 * c + 5] += p * op_hi(u.z);
+            acc[8 * c + 6] += p * op_lo(u.w); acc[8 * c + 7] += p * op_hi(u.w);
         }
     }
 #pragma unroll
@@ -578,10 +578,10 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
             uint4 o;
-            o.x = pack_bf16(acc[8 * c + 0] * inv, acc[8 * c + 1] * inv);
-            o.y = pack_bf16(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv);
-            o.z = pack_bf16(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv);
-            o.w = pack_bf16(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv);
+            o.x = pack_op(acc[8 * c + 0] * inv, acc[8 * c + 1] * inv);
+            o.y = pack_op(acc[8 * c + 2] * inv, acc[8 * c + 3] * inv);
+            o.z = pack_op(acc[8 * c + 4] * inv, acc[8 * c + 5] * inv);
+            o.w = pack_op(acc[8 * c + 6] * inv, acc[8 * c + 7] * inv);
             op[c] = o;
         }
     }
@@ -591,8 +591,8 @@ static int launch_single_query_attn(int mode, const void* qsrc, const void* kv, 
                                     const int* step_dev, const CropDesc* descs, void* out, cudaStream_t st) {
     const int hd = D / heads;
     const unsigned grid = (B * heads + 3) / 4;
-    const __nv_bfloat16 *q = reinterpret_cast<const __nv_bfloat16*>(qsrc), *k = reinterpret_cast<const __nv_bfloat16*>(kv);
-    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    const op_t *q = reinterpret_cast<const op_t*>(qsrc), *k = reinterpret_cast<const op_t*>(kv);
+    op_t* o = reinterpret_cast<op_t*>(out);
     switch (hd) {
         case 32: single_query_attn_kernel<32><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
         case 48: single_query_attn_kernel<48><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
@@ -663,7 +663,7 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
                                                          int rep_min_repeats, const float* __restrict__ embed,
                                                          const float* __restrict__ pos_q, int D, int d_real,
                                                          const float* __restrict__ g_c, const float* __restrict__ b_c,
-                                                         __nv_bfloat16* __restrict__ cin) {
+                                                         op_t* __restrict__ cin) {
     __shared__ float sv[8];
     __shared__ int si[8];
     __shared__ int s_tok;
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
             const float rstd = s_stat[1];
             for (int t = 0; t < 4; ++t) {
                 const int d = threadIdx.x + t * 256;
-                if (d < D) cin[(long long)row * D + d] = __float2bfloat16((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
+                if (d < D) cin[(long long)row * D + d] = f2op((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
             }
         }
     }
@@ -820,7 +820,7 @@ int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, c
     }
     ar_control_kernel<<<B, 256, 0, st>>>(logits, ldl, C, S, row_group, g0, ngroups, a, eos_id, rep_on, rep_period_max,
                                          rep_min_run_p1, rep_min_repeats, embed, pos_q, D, d_real, g_c, b_c,
-                                         reinterpret_cast<__nv_bfloat16*>(cin));
+                                         reinterpret_cast<op_t*>(cin));
     count_launch(1);
     return cudaGetLastError() != cudaSuccess;
 }
@@ -832,7 +832,7 @@ __global__ void __launch_bounds__(256) refine_embed_kernel(const int* __restrict
                                                            int eos_id, const float* __restrict__ embed,
                                                            const float* __restrict__ pos_q, int D, int d_real,
                                                            const float* __restrict__ g_c, const float* __restrict__ b_c,
-                                                           __nv_bfloat16* __restrict__ cin, int* __restrict__ klen,
+                                                           op_t* __restrict__ cin, int* __restrict__ klen,
                                                            int* __restrict__ kpad) {
     // grid (S, B): content position `pos` of row `row`; tgt_in = [BOS, raw[0..L-2]] (parseq.py:286)
     const int pos = blockIdx.x, row = blockIdx.y;
@@ -891,7 +891,7 @@ __global__ void __launch_bounds__(256) refine_embed_kernel(const int* __restrict
     const long long orow = (long long)row * S + pos;
     for (int t = 0; t < 4; ++t) {
         const int d = threadIdx.x + t * 256;
-        if (d < D) cin[orow * D + d] = __float2bfloat16((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
+        if (d < D) cin[orow * D + d] = f2op((loc[t] - mean) * rstd * g_c[d] + b_c[d]);
     }
 }
 
@@ -900,7 +900,7 @@ int launch_refine_embed(const int* raw, const int* row_group, const int* group_l
                         void* cin, int* klen, int* kpad, cudaStream_t st) {
     dim3 grid(S, B);
     refine_embed_kernel<<<grid, 256, 0, st>>>(raw, row_group, group_len, S, bos_id, eos_id, embed, pos_q, D, d_real, g_c, b_c,
-                                              reinterpret_cast<__nv_bfloat16*>(cin), klen, kpad);
+                                              reinterpret_cast<op_t*>(cin), klen, kpad);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }

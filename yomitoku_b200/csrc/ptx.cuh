@@ -3,8 +3,10 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace ytk {
 
@@ -125,7 +127,7 @@ __device__ __forceinline__ void tc_fence_after() {
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_op(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
         "{\n\t"
@@ -153,7 +155,7 @@ __device__ __forceinline__ void tmem_relinquish_cg2() {
 __device__ __forceinline__ void tmem_dealloc_cg2(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
 }
-__device__ __forceinline__ void umma_bf16_cg2(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+__device__ __forceinline__ void umma_op_cg2(uint32_t d_tmem, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                               uint32_t accumulate) {
     asm volatile(
         "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
@@ -196,17 +198,81 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
     return d;
 }
-// Instruction descriptor for kind::f16, A=B=bf16 (K-major), D=fp32, shape M x N.
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
-           (static_cast<uint32_t>(M >> 4) << 24);
-}
-
-__device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+// ---------------------------------------------------------------- operand type of every tensor-core GEMM
+// 16-bit operands, fp32 accumulation.  Default: IEEE fp16 (11-bit significand = the precision of kind::tf32, at the
+// throughput and bytes of bf16): activations of both networks are O(1..100) (LayerNorm / folded-BatchNorm outputs,
+// fp32 residual stream in PARSeq), far inside fp16's range, and every fp32 -> fp16 conversion saturates
+// (cvt.rn.satfinite) so an outlier clamps to +-65504 instead of becoming inf.  bf16 (8-bit significand) is a
+// compile-time alternative (-DYTK_OPERAND_BF16) kept for A/B numerics runs; it costs ~8x the rounding error per
+// operand, which is what flipped greedy PARSeq decisions against the fp32 reference in round 1.
+#ifdef YTK_OPERAND_BF16
+using op_t = __nv_bfloat16;
+constexpr uint32_t kOpFmt = 1u;  // tcgen05 instruction-descriptor operand format: 1 = bf16
+#define YTK_OPERAND_NAME "bf16"
+__device__ __forceinline__ float op_lo(uint32_t u) { return __uint_as_float(u << 16); }
+__device__ __forceinline__ float op_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
+__device__ __forceinline__ uint32_t pack_op(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&t);
+}
+__device__ __forceinline__ op_t f2op(float f) { return __float2bfloat16(f); }
+__device__ __forceinline__ float op2f(op_t v) { return __bfloat162float(v); }
+__host__ inline uint16_t f2op_host(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return 0x7fc0;  // NaN
+    u += 0x7fffu + ((u >> 16) & 1u);                      // round to nearest even
+    return (uint16_t)(u >> 16);
+}
+#else
+using op_t = __half;
+constexpr uint32_t kOpFmt = 0u;  // 0 = fp16
+#define YTK_OPERAND_NAME "f16"
+__device__ __forceinline__ float op_lo(uint32_t u) {
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, l;\n\t}" : "=f"(f) : "r"(u));
+    return f;
+}
+__device__ __forceinline__ float op_hi(uint32_t u) {
+    float f;
+    asm("{\n\t.reg .b16 l, h;\n\tmov.b32 {l, h}, %1;\n\tcvt.f32.f16 %0, h;\n\t}" : "=f"(f) : "r"(u));
+    return f;
+}
+// low half = a, high half = b; saturating (no inf)
+__device__ __forceinline__ uint32_t pack_op(float a, float b) {
+    uint32_t r;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+    return r;
+}
+__device__ __forceinline__ op_t f2op(float f) {
+    unsigned short r;
+    asm("cvt.rn.satfinite.f16.f32 %0, %1;" : "=h"(r) : "f"(f));
+    return __ushort_as_half(r);
+}
+__device__ __forceinline__ float op2f(op_t v) { return __half2float(v); }
+// IEEE binary16, round to nearest even, saturating to +-65504 (same rule as the device conversions)
+__host__ inline uint16_t f2op_host(float f) {
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    const uint32_t sign = (u >> 16) & 0x8000u;
+    const uint32_t a = u & 0x7fffffffu;
+    if (a > 0x7f800000u) return (uint16_t)(sign | 0x7e00u);           // NaN
+    if (a >= 0x477ff000u) return (uint16_t)(sign | 0x7bffu);           // >= 65520 rounds past the largest finite: clamp
+    if (a < 0x33000001u) return (uint16_t)sign;                         // <= 2^-25: rounds to zero
+    int e = (int)(a >> 23) - 127;
+    uint32_t m = (a & 0x7fffffu) | 0x800000u;                           // 24-bit significand
+    int shift = (e < -14) ? (13 + (-14 - e)) : 13;                      // bits dropped (subnormal: more)
+    uint32_t q = m >> shift, rem = m & ((1u << shift) - 1u), half = 1u << (shift - 1);
+    if (rem > half || (rem == half && (q & 1u))) ++q;
+    uint32_t h = (e < -14) ? q : (((uint32_t)(e + 15) << 10) + (q - 0x400u));  // a carry out of q bumps the exponent
+    return (uint16_t)(sign | h);
+}
+#endif
+
+// Instruction descriptor for kind::f16, A=B=op_t (K-major), D=fp32, shape M x N.
+__host__ __device__ constexpr uint32_t umma_idesc_op(int M, int N) {
+    return (1u << 4) | (kOpFmt << 7) | (kOpFmt << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
 }
 
 }  // namespace ytk
