@@ -36,21 +36,42 @@ void ytk_gemm_profile_begin(void);
 int ytk_gemm_profile_end(double* flops, double* ms, long long* launches);
 
 /* ---- op level (kernel parity tests; replaces the cuDNN/cuBLAS call sites listed in SURVEY.md section 2.3) ----
- * Convolution as tcgen05 implicit GEMM.  in: NHWC bf16 [N,H,W,in_ld] (first Cin channels used), w: bf16
- * [Cout][kh][kw][Cin], bias fp32 [Cout] or NULL, resid: [N,Ho,Wo,ldr] bf16/fp32 or NULL, out: [N,Ho,Wo,ldc]
- * bf16/fp32.  Replaces torch.nn.Conv2d + BatchNorm2d(eval, folded) + ReLU (+ residual add) of
+ * Convolution as tcgen05 implicit GEMM.  in: NHWC fp16 [N,H,W,in_ld] (first Cin channels used), w: fp16
+ * [Cout][kh][kw][Cin], bias fp32 [Cout] or NULL, resid: [N,Ho,Wo,ldr] fp16/fp32 or NULL, out: [N,Ho,Wo,ldc]
+ * fp16/fp32.  Replaces torch.nn.Conv2d + BatchNorm2d(eval, folded) + ReLU (+ residual add) of
  * torchvision ResNet-50 bottlenecks (reference models/dbnet_plus.py:30-38) and the decoder convs (:56-116).
  * mode 1 = ConvTranspose2d(kernel 2, stride 2) written as a GEMM with a pixel-shuffle epilogue (:111,:114). */
 int ytk_op_conv2d_f16(const void* in, int N, int H, int W, int Cin, long long in_ld, const void* w, const float* bias,
                        int kh, int kw, int stride, int pad, int dil, int Cout, const void* resid, int resid_f32,
                        long long ldr, void* out, int out_f32, long long ldc, int act, int mode, void* cuda_stream);
 
-/* Linear layer y = act(A W^T + b (+ resid)); A [M,lda] bf16, W [N,K] bf16 (torch nn.Linear layout), K % 64 == 0.
+/* Linear layer y = act(A W^T + b (+ resid)); A [M,lda] fp16, W [N,K] fp16 (torch nn.Linear layout), K % 64 == 0.
  * Replaces nn.Linear / timm Mlp / attention projections (reference models/layers/parseq_transformer.py:43-52,
  * models/parseq.py:72). */
 int ytk_op_linear_f16(const void* A, long long lda, int M, int K, const void* W, int N, const float* bias,
                        const void* resid, int resid_f32, long long ldr, void* out, int out_f32, long long ldc, int act,
                        void* cuda_stream);
+
+/* One descriptor per packed sequence of ytk_op_attention_f16 (the layout of ytk::SeqDesc, csrc/parseq_ops.h). */
+typedef struct ytk_attn_seq {
+    int32_t q_off;     /* first query row in Q */
+    int32_t q_len;
+    int32_t o_off;     /* first output row in O */
+    int32_t k_len;     /* number of keys */
+    long long k_base;  /* element offset of key 0 inside K / V (key j at k_base + j * ldkv; a multiple of ldkv) */
+    int32_t kpad;      /* masked mode: keys >= kpad are padding */
+    int32_t pad_;
+} ytk_attn_seq;
+
+/* softmax(Q K^T / sqrt(head_dim)) V per (sequence, head) over packed ragged sequences; Q [q_rows, ldq], K / V
+ * [kv_rows, ldkv], O [*, ldo] fp16 on the device, head h = columns [h*head_dim, (h+1)*head_dim); seqs_dev: device array.
+ * masked != 0: key j visible to query i iff (i < 2 || j <= i) && j < kpad (PARSeq refinement mask, reference
+ * models/parseq.py:267-297).  impl: 0 default (tcgen05 kernel), 1 legacy mma.sync kernel, 2/3 tcgen05 kernel with the
+ * V-descriptor convention forced.  Replaces timm Attention's F.scaled_dot_product_attention (reference
+ * models/layers/parseq_transformer.py:206-234) and nn.MultiheadAttention's core (parseq_transformer.py:83-92). */
+int ytk_op_attention_f16(const void* Q, long long ldq, long long q_rows, const void* K, const void* V, long long ldkv,
+                         long long kv_rows, void* O, long long ldo, const ytk_attn_seq* seqs_dev, int nseq, int max_q_len,
+                         int heads, int head_dim, int masked, int impl, void* cuda_stream);
 
 /* ---- DBNet text detector: replaces `self.model(tensor)` in reference TextDetector.__call__
  * (src/yomitoku/text_detector.py:127-129 -> models/dbnet_plus.py:243-246) and, in the fused u8 entry, also
@@ -66,7 +87,7 @@ typedef struct {
     long long shape[4];
 } ytk_tensor;
 
-/* Folds BatchNorm, repacks weights to NHWC bf16 and uploads them.  shortest_size / limit_size are cfg.data.* of the
+/* Folds BatchNorm, repacks weights to NHWC fp16 and uploads them.  shortest_size / limit_size are cfg.data.* of the
  * detector config (reference configs/cfg_text_detector_dbnet_v2_1.py:23-26). */
 int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size, int limit_size, ytk_dbnet** out);
 void ytk_dbnet_destroy(ytk_dbnet* h);

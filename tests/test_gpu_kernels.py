@@ -110,3 +110,89 @@ def test_bad_arguments_fail_loudly():
     st = L.ytk_op_conv2d_f16(_lib.ptr(x), 1, 8, 8, 48, 48, _lib.ptr(w), None, 1, 1, 1, 0, 1, 64, None, 0, 0,
                               _lib.ptr(out), 0, 64, 0, 0, None)
     assert st != 0 and b"multiple of 64" in L.ytk_last_error()
+
+
+# ---------------------------------------------------------------------------------------------------- attention
+def _attn_case(hd, heads, lens, masked, impl, seed=0, q_shared=None, kpads=None):
+    """Packed ragged self-attention (q, k, v = column blocks of one [T, 3D] matrix) or, with q_shared = S, the refinement
+    shape (S shared queries, per-sequence key blocks of S rows with k_len / kpad).  Returns (max |d| of O, ref scale)."""
+    import ctypes
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(seed)
+    D = hd * heads
+    nseq = len(lens)
+    if q_shared is None:
+        T = sum(lens)
+        qkv = (torch.randn(T, 3 * D, generator=g) * 1.0).to(DEV).half()
+        Q, K, V = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+        ldq = ldkv = 3 * D
+        q_rows = kv_rows = T
+        out = torch.full((T, D), 7.0, device=DEV, dtype=torch.float16)
+        seqs = (_lib.YtkAttnSeq * nseq)()
+        off = 0
+        for i, n in enumerate(lens):
+            seqs[i] = _lib.YtkAttnSeq(off, n, off, n, off * 3 * D, n, 0)
+            off += n
+        max_q = max(lens)
+    else:
+        S = q_shared
+        qm = torch.randn(S, D, generator=g).to(DEV).half()
+        kv = torch.randn(nseq * S, 2 * D, generator=g).to(DEV).half()
+        Q, K, V = qm, kv[:, :D], kv[:, D:]
+        ldq, ldkv = D, 2 * D
+        q_rows, kv_rows = S, nseq * S
+        out = torch.full((nseq * S, D), 7.0, device=DEV, dtype=torch.float16)
+        seqs = (_lib.YtkAttnSeq * nseq)()
+        for i, n in enumerate(lens):
+            seqs[i] = _lib.YtkAttnSeq(0, S, i * S, n, i * S * 2 * D, kpads[i] if kpads else n, 0)
+        max_q = S
+    seqs_dev = torch.frombuffer(bytearray(bytes(seqs)), dtype=torch.uint8).to(DEV)
+    _lib.check(L.ytk_op_attention_f16(Q.data_ptr(), ldq, q_rows, K.data_ptr(), V.data_ptr(), ldkv, kv_rows,
+                                      out.data_ptr(), D, seqs_dev.data_ptr(), nseq, max_q, heads, hd,
+                                      1 if masked else 0, impl, None))
+    torch.cuda.synchronize()
+    worst = 0.0
+    for i, n in enumerate(lens):
+        if q_shared is None:
+            q = Q[seqs[i].q_off: seqs[i].q_off + n].float()
+            k = K[seqs[i].q_off: seqs[i].q_off + n].float()
+            v = V[seqs[i].q_off: seqs[i].q_off + n].float()
+            o = out[seqs[i].o_off: seqs[i].o_off + n].float()
+        else:
+            S = q_shared
+            q = Q.float()
+            k = K[i * S: i * S + n].float()
+            v = V[i * S: i * S + n].float()
+            o = out[i * S: (i + 1) * S].float()
+        q = q.reshape(q.shape[0], heads, hd).transpose(0, 1)
+        k = k.reshape(n, heads, hd).transpose(0, 1)
+        v = v.reshape(n, heads, hd).transpose(0, 1)
+        s = (q @ k.transpose(-1, -2)) / hd ** 0.5
+        if masked:
+            qi = torch.arange(q.shape[1], device=DEV)[:, None]
+            kj = torch.arange(n, device=DEV)[None, :]
+            vis = ((qi < 2) | (kj <= qi)) & (kj < (kpads[i] if kpads else n))
+            s = s.masked_fill(~vis[None], float("-inf"))
+        ref = (torch.softmax(s, -1) @ v).transpose(0, 1).reshape(q.shape[1], D)
+        worst = max(worst, (o - ref).abs().max().item())
+    return worst
+
+
+@pytest.mark.parametrize("hd,heads,lens", [(96, 8, [132, 92, 48, 200, 400, 129, 128, 4]), (32, 6, [800, 320, 64, 8, 72]),
+                                           (48, 8, [100, 260]), (64, 8, [160, 96, 31])])
+def test_attention_tc_vs_torch(hd, heads, lens):
+    """tcgen05 attention kernel (attn_tc.cu) vs fp32 softmax attention on the same fp16 operands: the only rounding the
+    kernel adds is P and O in fp16 (2^-11 relative)."""
+    d = _attn_case(hd, heads, lens, False, 2)
+    print("[attn] hd %d max|d| %.5f" % (hd, d))
+    assert d < 4e-3, d
+
+
+def test_attention_tc_masked_refinement_shape():
+    d = _attn_case(96, 8, [101, 40, 7, 1, 64, 65], True, 2, q_shared=101, kpads=[101, 33, 7, 1, 20, 65])
+    print("[attn] masked max|d| %.5f" % d)
+    assert d < 4e-3, d
+
+
+def test_attention_legacy_kernel_still_matches():
+    assert _attn_case(96, 8, [132, 92, 200], False, 1) < 4e-3

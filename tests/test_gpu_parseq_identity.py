@@ -3,11 +3,11 @@ character-identical").
 
 2048 crops per model (16 reference mini-batches of 128, ragged widths) through the product's packed path
 (`recognize_crops` -> ytk_parseq_forward_crops) and through the oracle batch by batch.  With fp16 operands / fp32
-accumulation the worst logit error is a few 1e-3 of the logit spread, so a row may differ from the oracle only where the
-ORACLE'S OWN top-2 margin is below TAU = 0.1 logits at some decision of that row (a coin flip at any precision short of
-fp32).  The test counts every differing row, records the margin histogram of all rows and of the differing ones
+accumulation the worst logit error is ~1e-3 of the logit spread (std ~6), so a row may differ from the oracle only where
+the ORACLE'S OWN top-2 margin is below TAU = 0.05 logits at some decision of that row (a coin flip at any precision short
+of fp32; measured on B200: every differing row had a margin <= 0.015, profiles/README_r02.md).  The test counts every differing row, records the margin histogram of all rows and of the differing ones
 (gpurun_out/identity_<model>.json, printed), and asserts: no differing row whose smallest decision margin is >= TAU,
-and |log score - log score_ref| <= 0.05 on identical rows (the orientation fallback thresholds on that score).
+and |log score - log score_ref| <= 0.05 on the rows above TAU (the orientation fallback thresholds on that score).
 """
 import json
 import os
@@ -21,7 +21,7 @@ from oracle import weights
 from yomitoku_b200 import TextRecognizer
 
 pytestmark = pytest.mark.gpu
-TAU = 0.1
+TAU = 0.05
 SCORE_ATOL = 0.05
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -63,7 +63,7 @@ def test_greedy_strings_identical_at_scale(name, n_groups, gsize, wlo, whi, seed
             groups.append(g)
     ids, probs, glen = rec.model.recognize_crops(canv, padded, groups, n_groups)
     n = len(canv)
-    differing, all_low, score_d = [], [], []
+    differing, all_low, score_d, score_low = [], [], [], []
     for g in range(n_groups):
         sl = slice(g * gsize, (g + 1) * gsize)
         r_ids, r_prob, r_margin, ar_margin = _oracle_group(sd, spec, canv[sl], padded[g * gsize])
@@ -74,9 +74,11 @@ def test_greedy_strings_identical_at_scale(name, n_groups, gsize, wlo, whi, seed
             low = min(float(ar_margin[b].min()), float(r_margin[b, :m].min()))
             all_low.append(low)
             if np.array_equal(ids[i, :m], r_ids[b, :m]):
+                # scores are compared on rows without coin-flip decisions: a flipped AR token that the refinement
+                # repairs leaves the string identical but legitimately changes the context the probabilities saw
                 s_gpu = float(np.log(np.maximum(probs[i, :m], 1e-30)).sum())
                 s_ref = float(np.log(np.maximum(r_prob[b, :m], 1e-30)).sum())
-                score_d.append(abs(s_gpu - s_ref))
+                (score_d if low >= TAU else score_low).append(abs(s_gpu - s_ref))
             else:
                 first = int(np.nonzero(ids[i, :m] != r_ids[b, :m])[0][0])
                 differing.append({"row": i, "first_diff_pos": first, "min_margin": low,
@@ -88,6 +90,7 @@ def test_greedy_strings_identical_at_scale(name, n_groups, gsize, wlo, whi, seed
            "min_margin_histogram_all_rows": hist, "rows_below_tau": int((all_low < TAU).sum()), "tau": TAU,
            "max_abs_log_score_diff": float(max(score_d)) if score_d else None,
            "median_abs_log_score_diff": float(np.median(score_d)) if score_d else None,
+           "max_abs_log_score_diff_coin_flip_rows": float(max(score_low)) if score_low else None,
            "mean_decoded_len": float(np.mean([(r.tolist().index(0) if 0 in r.tolist() else len(r)) for r in ids])),
            "ar_steps_per_group": [int(v) for v in glen]}
     print("\n[identity] " + json.dumps(rep))

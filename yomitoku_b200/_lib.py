@@ -35,6 +35,14 @@ def _declare(lib):
     lib.ytk_op_linear_f16.restype = c_int
     lib.ytk_op_linear_f16.argtypes = [c_void_p, c_ll, c_int, c_int, c_void_p, c_int, c_void_p, c_void_p, c_int,
                                        c_ll, c_void_p, c_int, c_ll, c_int, c_void_p]
+    lib.ytk_op_attention_f16.restype = c_int
+    lib.ytk_op_attention_f16.argtypes = [c_void_p, c_ll, c_ll, c_void_p, c_void_p, c_ll, c_ll, c_void_p, c_ll, c_void_p,
+                                         c_int, c_int, c_int, c_int, c_int, c_int, c_void_p]
+
+
+class YtkAttnSeq(ctypes.Structure):
+    _fields_ = [("q_off", c_int), ("q_len", c_int), ("o_off", c_int), ("k_len", c_int), ("k_base", c_ll),
+                ("kpad", c_int), ("pad_", c_int)]
 
 
 class YtkTensor(ctypes.Structure):

@@ -129,6 +129,18 @@ int ytk_op_linear_f16(const void* A, long long lda, int M, int K, const void* W,
     return ytk::gemm_plan_launch(&plan, static_cast<cudaStream_t>(cuda_stream)) ? YTK_ERR : YTK_OK;
 }
 
+static_assert(sizeof(ytk_attn_seq) == sizeof(ytk::SeqDesc), "ytk_attn_seq and ytk::SeqDesc must have one layout");
+
+int ytk_op_attention_f16(const void* Q, long long ldq, long long q_rows, const void* K, const void* V, long long ldkv,
+                         long long kv_rows, void* O, long long ldo, const ytk_attn_seq* seqs_dev, int nseq, int max_q_len,
+                         int heads, int head_dim, int masked, int impl, void* cuda_stream) {
+    return ytk::launch_flash_attention(Q, ldq, q_rows, K, V, ldkv, kv_rows, O, ldo,
+                                       reinterpret_cast<const ytk::SeqDesc*>(seqs_dev), nseq, max_q_len, heads, head_dim,
+                                       masked, static_cast<cudaStream_t>(cuda_stream), impl)
+               ? YTK_ERR
+               : YTK_OK;
+}
+
 int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size, int limit_size, ytk_dbnet** out) {
     if (!tensors || !out) {
         ytk::set_error("ytk_dbnet_create: null argument");

@@ -488,8 +488,8 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         if (launch_layernorm(x, Ti, D, m->Dr, bk.ln1.g, bk.ln1.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
         if (Lin::run(h, D, Ti, bk.qkv, qkv, 3 * D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
         const op_t* q = reinterpret_cast<const op_t*>(qkv);
-        if (launch_flash_attention(q, 3 * D, q + D, q + 2 * D, 3 * D, att, D, seqs_enc, B, max_ntok, c.enc_heads, hd_e,
-                                   0, st))
+        if (launch_flash_attention(q, 3 * D, Ti, q + D, q + 2 * D, 3 * D, Ti, att, D, seqs_enc, B, max_ntok, c.enc_heads,
+                                   hd_e, 0, st))
             return 1;
         if (Lin::run(att, D, Ti, bk.proj, x, D, 1, ACT_NONE, x, 1, D, st, &flops)) return 1;
         if (launch_layernorm(x, Ti, D, m->Dr, bk.ln2.g, bk.ln2.b, 1e-6f, h, nullptr, nullptr, 1, nullptr, 0, 0, st)) return 1;
@@ -712,7 +712,7 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         if (launch_refine_seqs(klen, kpad, B, S, D, seqs_self, st)) return 1;
         {
             const op_t* ck = reinterpret_cast<const op_t*>(ckv);
-            if (launch_flash_attention(m->q_self, D, ck, ck + D, 2 * D, sa, D, seqs_self, B, S,
+            if (launch_flash_attention(m->q_self, D, S, ck, ck + D, 2 * D, R, sa, D, seqs_self, B, S,
                                        c.dec_heads, hd_d, 1, st))
                 return 1;
         }
@@ -721,7 +721,8 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             return 1;
         if (Lin::run(hb, D, R, m->cross_q, qc, D, 0, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
         const op_t* kv = reinterpret_cast<const op_t*>(memkv);
-        if (launch_flash_attention(qc, D, kv, kv + D, 2 * D, oc, D, seqs_ref, B, S, c.dec_heads, hd_d, 0, st)) return 1;
+        if (launch_flash_attention(qc, D, R, kv, kv + D, 2 * D, Ti, oc, D, seqs_ref, B, S, c.dec_heads, hd_d, 0, st))
+            return 1;
         for (const CropDesc& d : b.descs) flops += 4.0 * S * (double)d.ntok * D;
         if (Lin::run(oc, D, R, m->cross_out, x1, D, 1, ACT_NONE, x1, 1, D, st, &flops)) return 1;
         if (launch_layernorm(x1, R, D, m->Dr, m->norm2.g, m->norm2.b, 1e-5f, hb, nullptr, nullptr, 1, nullptr, 0, 0, st))

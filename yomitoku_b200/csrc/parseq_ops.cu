@@ -432,10 +432,23 @@ static int launch_fa(dim3 grid, const op_t* q, long long ldq, const op_t* k, con
     return 0;
 }
 
-int launch_flash_attention(const void* Q, long long ldq, const void* K, const void* V, long long ldkv, void* O,
-                           long long ldo, const SeqDesc* seqs, int nseq, int max_q_len, int heads, int head_dim,
-                           int masked, cudaStream_t st) {
+int launch_flash_attention(const void* Q, long long ldq, long long q_rows, const void* K, const void* V, long long ldkv,
+                           long long kv_rows, void* O, long long ldo, const SeqDesc* seqs, int nseq, int max_q_len,
+                           int heads, int head_dim, int masked, cudaStream_t st, int impl) {
     if (nseq <= 0) return 0;
+    if (impl == 0) {
+        // YTK_ATTN=legacy: the round-1 mma.sync kernel; YTK_ATTN=vswap: tcgen05 kernel with the other V descriptor
+        static const int env_impl = [] {
+            const char* e = getenv("YTK_ATTN");
+            if (e && e[0] == 'l') return 1;
+            if (e && e[0] == 'v') return 3;
+            return 2;
+        }();
+        impl = env_impl;
+    }
+    if (impl >= 2)
+        return launch_attention_tc(Q, ldq, q_rows, K, V, ldkv, kv_rows, O, ldo, seqs, nseq, heads, head_dim, masked,
+                                   impl == 3 ? 1 : 0, st);
     // 128-query tiles (8 warps) halve the K/V re-reads of the typical 92..200-token crop; short sequences keep 64
     const int qt = max_q_len > 64 ? 128 : 64;
     dim3 grid((max_q_len + qt - 1) / qt, heads, nseq);
