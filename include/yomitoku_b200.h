@@ -91,6 +91,8 @@ typedef struct {
  * detector config (reference configs/cfg_text_detector_dbnet_v2_1.py:23-26). */
 int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size, int limit_size, ytk_dbnet** out);
 void ytk_dbnet_destroy(ytk_dbnet* h);
+/* CUDA device ordinal a handle is bound to (the device that was current at create()). */
+int ytk_dbnet_device(const ytk_dbnet* h);
 /* network input size for an H0 x W0 page = reference resize_shortest_edge (data/functions.py:212-224) */
 int ytk_dbnet_input_size(const ytk_dbnet* h, int H0, int W0, int* Hn, int* Wn);
 /* pages: [n_pages, H0, W0, 3] uint8 BGR (caller-owned; device pointer iff pages_on_device, else host - pinned for
@@ -135,6 +137,7 @@ typedef struct {
 
 int ytk_parseq_create(const ytk_tensor* tensors, int n_tensors, const ytk_parseq_cfg* cfg, ytk_parseq** out);
 void ytk_parseq_destroy(ytk_parseq* h);
+int ytk_parseq_device(const ytk_parseq* h);
 void ytk_parseq_set_refine_iters(ytk_parseq* h, int refine_iters);
 /* crops: packed canvases; host pointer (pinned memory for async copies) or, iff crops_on_device, a device pointer
  * (the copy is skipped).  Outputs (host): ids / probs

@@ -71,17 +71,19 @@ def clipper_offset_box(box, delta):
     sn, cs = math.sin(2 * math.pi / steps), math.cos(2 * math.pi / steps)
     per_rad = steps / (2 * math.pi)
     out = []
+    k = n - 1
     for j in range(n):
-        nk, nj = normals[j - 1], normals[j]
+        nk, nj = normals[k], normals[j]
         sin_a = nk[0] * nj[1] - nj[0] * nk[1]
         cos_a = nk[0] * nj[0] + nj[1] * nk[1]
         p = pts[j].astype(np.float64)
         if abs(sin_a * delta) < 1.0 and cos_a > 0:
-            out.append(_round_half_away(p + nk * delta))
+            out.append(_round_half_away(p + nk * delta))   # OffsetPoint returns here, BEFORE `k = j` (Clipper 6.4.2)
             continue
         sin_a = min(1.0, max(-1.0, sin_a))
         if sin_a * delta < 0:
             out += [_round_half_away(p + nk * delta), pts[j], _round_half_away(p + nj * delta)]
+            k = j
             continue
         m = max(int(_round_half_away(np.float64(per_rad * abs(math.atan2(sin_a, cos_a))))), 1)
         vx, vy = nk
@@ -89,6 +91,7 @@ def clipper_offset_box(box, delta):
             out.append(_round_half_away(p + np.array([vx, vy]) * delta))
             vx, vy = vx * cs - sn * vy, vx * sn + vy * cs
         out.append(_round_half_away(p + nj * delta))
+        k = j
     return np.array(out, dtype=np.int64)
 
 

@@ -149,7 +149,9 @@ def _worker_pipeline(rank, world, port, q):
 
 def _worker_pipeline_dev(rank, world, port, q):
     """BatchedOCR._run_groups_dev across 2 ranks: crops that exist only as records are cut "on the device" (stand-in:
-    the product's crop arithmetic compiled for the host), brought to the host once and balanced across ranks."""
+    the product's crop arithmetic compiled for the host, tensors on the CPU under gloo); the groups the balancer moves
+    travel as ONE flat uint8 tensor per rank through parallel.exchange_canvases_dev (all_to_all_single) and are
+    recognised straight from the receive buffer."""
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -170,13 +172,6 @@ def _worker_pipeline_dev(rank, world, port, q):
             _cfg = cfg
             model = _StubModel(cfg)
 
-        class FakeDev:
-            def __init__(self, arr):
-                self.arr = arr
-
-            def data_ptr(self):
-                return self.arr.ctypes.data
-
         def fake_extract(pages_dev, geoms, stream=None):
             sb, cb = D.layout_crop_buffers(geoms)
             scratch, canv = np.zeros(max(sb, 1), np.uint8), np.zeros(max(cb, 1), np.uint8)
@@ -184,14 +179,9 @@ def _worker_pipeline_dev(rank, world, port, q):
             host.crop_host_extract(pages_dev.ctypes.data_as(vp), pages_dev.shape[1], pages_dev.shape[2],
                                    geoms.ctypes.data_as(vp), len(geoms), scratch.ctypes.data_as(vp),
                                    canv.ctypes.data_as(vp))
-            return FakeDev(canv), cb
-
-        class FakeHostCanvases:
-            def __init__(self, canv_dev, stream=None):
-                self.np = canv_dev.arr
+            return torch.from_numpy(canv), cb          # the "device" of this test is the CPU (gloo)
 
         M.extract_crops_device = fake_extract
-        pl._HostCanvases = FakeHostCanvases
         ocr = pl.BatchedOCR(None, Rec(), workers=1, device_crops=True)
         page, quads = synthetic_page(30 + rank)
         quads = quads[:40] if rank == 0 else quads[:6]         # unbalanced: groups must move from rank 0 to rank 1
@@ -205,13 +195,24 @@ def _worker_pipeline_dev(rank, world, port, q):
             groups.append((widths, [max(widths)] * len(b), np.asarray(b, np.int64)))
             expect.append(_fake_recognise([ds.data[i] for i in b]))
         moved = []
-        orig_pack = par_mod._pack_group
-        par_mod._pack_group = lambda canv, padded, gid: (moved.append(gid), orig_pack(canv, padded, gid))[1]
+        orig_x = par_mod.exchange_canvases_dev
+
+        def spy(canv, byte_splits, metas):
+            assert isinstance(canv, torch.Tensor) and canv.dtype == torch.uint8     # one flat buffer, never host lists
+            moved.append([int(b) for b in byte_splits])
+            return orig_x(canv, byte_splits, metas)
+
+        par_mod.exchange_canvases_dev = spy
+        par_mod.exchange_groups = None              # the host-staged scatter must not be used any more
         res = ocr._run_groups_dev(groups, geoms, np.ascontiguousarray(page)[None], None)
         for (ids, probs, glen), (eid, ep) in zip(res, expect):
             assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101
-        # rank 0 (8 groups) hands some groups to rank 1 (2 groups); the rest never left the "device"
-        assert (0 < len(moved) < len(groups)) if rank == 0 else not moved
+        # rank 0 (8 groups) hands some groups to rank 1 (2 groups) as one buffer; rank 1 sends nothing
+        assert len(moved) == 1
+        assert (moved[0][1] > 0 and moved[0][0] == 0) if rank == 0 else sum(moved[0]) == 0
+        assert par_mod.STATS["exchange_calls"] == 1
+        assert (par_mod.STATS["exchange_bytes_sent"] > 0) == (rank == 0)
+        assert (par_mod.STATS["exchange_bytes_received"] > 0) == (rank == 1)
         q.put((rank, "ok", None))
     except Exception:  # pragma: no cover
         import traceback

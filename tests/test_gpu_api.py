@@ -84,3 +84,21 @@ def test_document_analyzer_shell():
     page, _ = synthetic_page(1)
     res, ocr_vis, layout_vis = da(page)
     assert layout_vis is None and isinstance(res.words, list)
+
+
+def test_handles_bind_to_the_requested_device():
+    """`TextDetector(device="cuda:k")` / `TextRecognizer(device="cuda:k")` run on GPU k (reference: model.to(self.device),
+    base.py:106-121), not on whatever device the calling thread happens to have current."""
+    import torch
+    from yomitoku_b200 import TextDetector, TextRecognizer, _lib
+    k = torch.cuda.device_count() - 1           # the last GPU: differs from the current device (0) on multi-GPU boxes
+    det = TextDetector(from_pretrained=False, device="cuda:%d" % k)
+    rec = TextRecognizer(model_name="parseq-tiny-dynw-v4", from_pretrained=False, device="cuda:%d" % k)
+    L = _lib.lib()
+    assert L.ytk_dbnet_device(det.model._ensure()) == k
+    assert L.ytk_parseq_device(rec.model._ensure()) == k
+    assert det.model.cuda_device().index == k
+    # moving a materialised model drops the handle; the next use re-creates it on the new device
+    rec.model.to("cuda:0")
+    assert (rec.model._handle is None) == (k != 0)
+    assert L.ytk_parseq_device(rec.model._ensure()) == 0

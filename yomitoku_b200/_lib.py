@@ -55,6 +55,10 @@ def _declare_dbnet(lib):
     lib.ytk_dbnet_create.argtypes = [P(YtkTensor), c_int, c_int, c_int, P(c_void_p)]
     lib.ytk_dbnet_destroy.restype = None
     lib.ytk_dbnet_destroy.argtypes = [c_void_p]
+    lib.ytk_dbnet_device.restype = c_int
+    lib.ytk_dbnet_device.argtypes = [c_void_p]
+    lib.ytk_parseq_device.restype = c_int
+    lib.ytk_parseq_device.argtypes = [c_void_p]
     lib.ytk_dbnet_input_size.restype = c_int
     lib.ytk_dbnet_input_size.argtypes = [c_void_p, c_int, c_int, P(c_int), P(c_int)]
     lib.ytk_dbnet_forward_u8.restype = c_int

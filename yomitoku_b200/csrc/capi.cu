@@ -35,7 +35,19 @@ struct ytk_dbnet {
     int shortest = 1280, limit = 1600;
     void* stage = nullptr;  // device staging for host inputs
     size_t stage_bytes = 0;
+    // The staging buffer and an engine's input / activation / probability buffers are shared by all calls on this
+    // handle.  A call that leaves its output on the device returns while its kernels are still queued, so every call
+    // first makes its stream wait for the previous call's last operation (recorded here), whatever stream that was on.
+    cudaEvent_t last_done = nullptr;
 };
+
+static void order_after_previous(ytk_dbnet* h, cudaStream_t st) {
+    if (h->last_done) cudaStreamWaitEvent(st, h->last_done, 0);
+}
+static void mark_done(ytk_dbnet* h, cudaStream_t st) {
+    if (!h->last_done) cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming);
+    if (h->last_done) cudaEventRecord(h->last_done, st);
+}
 
 static ytk::DbnetEngine* get_engine(ytk_dbnet* h, int n, int Hn, int Wn) {
     auto key = std::make_tuple(n, Hn, Wn);
@@ -59,6 +71,7 @@ static ytk::DbnetEngine* get_engine(ytk_dbnet* h, int n, int Hn, int Wn) {
 
 static int ensure_stage(ytk_dbnet* h, size_t bytes) {
     if (h->stage_bytes >= bytes) return 0;
+    if (h->last_done) cudaEventSynchronize(h->last_done);  // the previous call may still be reading the old buffer
     if (h->stage) cudaFree(h->stage);
     h->stage = nullptr;
     h->stage_bytes = 0;
@@ -70,11 +83,12 @@ static int ensure_stage(ytk_dbnet* h, size_t bytes) {
     return 0;
 }
 
-static int finish_forward(ytk::DbnetEngine* e, float* prob_out, int out_on_device, cudaStream_t st) {
+static int finish_forward(ytk_dbnet* h, ytk::DbnetEngine* e, float* prob_out, int out_on_device, cudaStream_t st) {
     if (e->run(st)) return YTK_ERR;
     const size_t bytes = (size_t)e->N * e->Hn * e->Wn * sizeof(float);
     cudaError_t err = cudaMemcpyAsync(prob_out, e->prob, bytes,
                                       out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, st);
+    mark_done(h, st);
     if (err == cudaSuccess && !out_on_device) err = cudaStreamSynchronize(st);
     if (err != cudaSuccess) {
         ytk::set_error("DBNet output copy failed: %s", cudaGetErrorString(err));
@@ -166,9 +180,17 @@ int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size
 
 void ytk_dbnet_destroy(ytk_dbnet* h) {
     if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->last_done) {
+        cudaEventSynchronize(h->last_done);
+        cudaEventDestroy(h->last_done);
+    }
     if (h->stage) cudaFree(h->stage);
     delete h;
 }
+
+int ytk_dbnet_device(const ytk_dbnet* h) { return h ? h->device : -1; }
+int ytk_parseq_device(const ytk_parseq* h) { return h ? h->device : -1; }
 
 int ytk_dbnet_input_size(const ytk_dbnet* h, int H0, int W0, int* Hn, int* Wn) {
     ytk::dbnet_input_size(H0, W0, h->shortest, h->limit, Hn, Wn);
@@ -190,6 +212,7 @@ int ytk_dbnet_forward_u8(ytk_dbnet* h, const uint8_t* pages, int pages_on_device
     }
     ytk::DbnetEngine* e = get_engine(h, n_pages, Hn, Wn);
     if (!e) return YTK_ERR;
+    order_after_previous(h, st);
     const uint8_t* src = pages;
     if (!pages_on_device) {
         const size_t bytes = (size_t)n_pages * H0 * W0 * 3;
@@ -204,7 +227,7 @@ int ytk_dbnet_forward_u8(ytk_dbnet* h, const uint8_t* pages, int pages_on_device
         ytk::set_error("preprocess launch failed");
         return YTK_ERR;
     }
-    return finish_forward(e, prob_out, out_on_device, st);
+    return finish_forward(h, e, prob_out, out_on_device, st);
 }
 
 int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x, int x_on_device, int n, int H, int W, float* prob_out,
@@ -214,6 +237,7 @@ int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x, int x_on_device, int n, 
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     ytk::DbnetEngine* e = get_engine(h, n, H, W);
     if (!e) return YTK_ERR;
+    order_after_previous(h, st);
     const float* src = x;
     if (!x_on_device) {
         const size_t bytes = (size_t)n * 3 * H * W * 4;
@@ -228,7 +252,7 @@ int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x, int x_on_device, int n, 
         ytk::set_error("input pack launch failed");
         return YTK_ERR;
     }
-    return finish_forward(e, prob_out, out_on_device, st);
+    return finish_forward(h, e, prob_out, out_on_device, st);
 }
 
 double ytk_dbnet_flops(ytk_dbnet* h, int n_pages, int Hn, int Wn) {

@@ -41,8 +41,20 @@ class _DeviceModel:
         return self
 
     def to(self, device):
-        self._device = torch.device(device) if not isinstance(device, torch.device) else device
+        """Like nn.Module.to(device): the C handle is created on (and bound to) this device.  Moving an already
+        materialised model drops the handle; the next forward re-creates it on the new device."""
+        new = torch.device(device) if not isinstance(device, torch.device) else device
+        if new != self._device:
+            self._release()
+        self._device = new
         return self
+
+    def cuda_device(self):
+        """torch.device the device calls run on: the one given to `.to()`, or the thread's current CUDA device when the
+        model was never moved (`cuda` without an index means the current device, as in torch)."""
+        if self._device.type == "cuda" and self._device.index is not None:
+            return self._device
+        return torch.device("cuda", torch.cuda.current_device())
 
     def state_dict(self):
         return OrderedDict(self._sd)
@@ -239,7 +251,8 @@ class DBNet(_DeviceModel):
             L = _lib.lib()
             tab, keep = _lib.tensor_table(self._sd)
             h = ctypes.c_void_p()
-            _lib.check(L.ytk_dbnet_create(tab, len(tab), self._shortest, self._limit, ctypes.byref(h)))
+            with torch.cuda.device(self.cuda_device()):     # the handle binds to the device current at create()
+                _lib.check(L.ytk_dbnet_create(tab, len(tab), self._shortest, self._limit, ctypes.byref(h)))
             self._handle = h
         return self._handle
 
@@ -385,7 +398,8 @@ class PARSeq(_DeviceModel):
                                    self._refine_iters, 1 if self.repetition_stop else 0, self.rep_period_max,
                                    self.rep_min_run_p1, self.rep_min_repeats, 1 if self.decode_ar else 0)
             h = ctypes.c_void_p()
-            _lib.check(L.ytk_parseq_create(tab, len(tab), ctypes.byref(cc), ctypes.byref(h)))
+            with torch.cuda.device(self.cuda_device()):     # the handle binds to the device current at create()
+                _lib.check(L.ytk_parseq_create(tab, len(tab), ctypes.byref(cc), ctypes.byref(h)))
             self._handle = h
         return self._handle
 

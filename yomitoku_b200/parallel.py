@@ -80,6 +80,63 @@ def _all_to_all_bytes(send_chunks):
     return out
 
 
+STATS = {"exchange_calls": 0, "exchange_bytes_sent": 0, "exchange_bytes_received": 0, "exchange_ms": 0.0}
+
+
+def exchange_canvases_dev(canv, byte_splits, metas):
+    """The crop scatter without touching the host: GPU-to-GPU all_to_all over NCCL / NVLink.
+
+    canv: flat uint8 tensor ON THE COMPUTE DEVICE holding the canvases of every group that leaves this rank, ordered by
+    destination rank; byte_splits[k] = bytes of it that go to rank k; metas[k] = int32 numpy array describing those
+    groups ([gid, n, (w, wp, byte offset in the chunk) * n] per group).  Returns (recv, recv_splits, recv_metas): one flat uint8 tensor on the same
+    device with the canvases this rank received (ordered by source rank), the bytes per source and the parsed
+    descriptors per source.  Under gloo (CPU tests) the tensors are CPU tensors and the same code runs."""
+    import time
+    world = dist.get_world_size()
+    device = canv.device
+    t0 = time.perf_counter()
+    meta_t = [torch.from_numpy(np.ascontiguousarray(m, dtype=np.int32).view(np.uint8).copy()) for m in metas]
+    sizes = torch.tensor([[int(byte_splits[k]), int(meta_t[k].numel())] for k in range(world)], dtype=torch.int64,
+                         device=device)
+    recv_sizes = torch.empty_like(sizes)
+    dist.all_to_all_single(recv_sizes, sizes)
+    rs = recv_sizes.cpu().tolist()
+    recv_splits = [int(r[0]) for r in rs]
+    meta_splits = [int(r[1]) for r in rs]
+    recv = torch.empty(int(sum(recv_splits)), dtype=torch.uint8, device=device)
+    dist.all_to_all_single(recv, canv[: int(sum(byte_splits))], output_split_sizes=recv_splits,
+                           input_split_sizes=[int(b) for b in byte_splits])
+    msend = torch.cat(meta_t).to(device) if sum(m.numel() for m in meta_t) else torch.empty(0, dtype=torch.uint8,
+                                                                                           device=device)
+    mrecv = torch.empty(int(sum(meta_splits)), dtype=torch.uint8, device=device)
+    dist.all_to_all_single(mrecv, msend, output_split_sizes=meta_splits,
+                           input_split_sizes=[int(m.numel()) for m in meta_t])
+    mh = mrecv.cpu().numpy()
+    recv_metas, off = [], 0
+    for n in meta_splits:
+        recv_metas.append(mh[off:off + n].view(np.int32).copy())
+        off += n
+    if device.type == "cuda":
+        torch.cuda.current_stream(device).synchronize()
+    STATS["exchange_calls"] += 1
+    STATS["exchange_bytes_sent"] += int(sum(byte_splits))
+    STATS["exchange_bytes_received"] += int(sum(recv_splits))
+    STATS["exchange_ms"] += (time.perf_counter() - t0) * 1e3
+    return recv, recv_splits, recv_metas
+
+
+def parse_group_meta(meta):
+    """int32 [gid, n, (w, wp, byte offset inside the sender's chunk) * n] * groups -> list of (gid, widths, padded
+    widths, offsets)."""
+    out, off = [], 0
+    while off < len(meta):
+        gid, n = int(meta[off]), int(meta[off + 1])
+        wm = meta[off + 2: off + 2 + 3 * n].reshape(n, 3)
+        out.append((gid, wm[:, 0].astype(np.int64), wm[:, 1].astype(np.int64), wm[:, 2].astype(np.int64)))
+        off += 2 + 3 * n
+    return out
+
+
 def _pack_group(canvases, padded, gid):
     """-> uint8 tensor: header int32 [n, gid], per crop int32 [w, wp], then the canvases back to back."""
     n = len(canvases)

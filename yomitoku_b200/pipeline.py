@@ -212,7 +212,10 @@ class BatchedOCR:
         # produces quads + per-crop records, the canvases are cut on the GPU (bit-exact with the OpenCV path; with
         # source_downscale the pyramid levels are built there too)
         if device_crops is None:
-            device_crops = os.environ.get("YTK_DEVICE_CROPS", "0") == "1"
+            # default ON (round 2): the host stage then only post-processes probability maps; YTK_DEVICE_CROPS=0 selects
+            # the OpenCV host path (the reference's way) for A/B runs
+            import torch
+            device_crops = os.environ.get("YTK_DEVICE_CROPS", "1") != "0" and torch.cuda.is_available()
         self.device_crops = bool(device_crops)
         self.det_batch = det_batch
         self.max_tokens = max_tokens
@@ -388,31 +391,119 @@ class BatchedOCR:
     def _run_groups_dev(self, groups, geoms, pages_dev, stream=None, levels=None):
         """Groups whose crops exist only as records: groups = (widths, padded widths, record indices into `geoms`).
         Groups recognised on this rank are cut on the device and never leave HBM (`_run_groups_dev_local`).  With
-        torch.distributed, only the groups the balancer moves to another rank are cut separately and brought to the
-        host (page-locked) for the crop scatter; with balanced ranks nothing moves and no canvas touches PCIe."""
+        torch.distributed, the groups the balancer moves to another rank are cut into one device buffer ordered by
+        destination and travel GPU-to-GPU (`parallel.exchange_canvases_dev`: all_to_all_single over NCCL / NVLink); the
+        receiving rank recognises them straight from the receive buffer.  No canvas touches the host on any rank."""
+        import torch
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return self._run_groups_dev_local(groups, geoms, pages_dev, stream, levels)
+        from . import parallel as par
         from .models import extract_crops_pyramid
         pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
         lv = levels if levels is not None else np.zeros(len(geoms), np.int64)
+        cfg = self.recognizer._cfg
+        ph, pw = cfg.encoder.patch_size
+        gh = cfg.data.img_size[0] // ph
+        world, rank = dist.get_world_size(), dist.get_rank()
+        costs = [gh * (int(np.sum(g[1])) // pw) for g in groups]
+        assign_all = par.balance_groups(par.gather_costs(costs), world)
+        if all(dst == r for r, row in enumerate(assign_all) for dst in row):
+            return self._run_groups_dev_local(groups, geoms, pages, stream, lv)   # same decision on every rank
+        assign = assign_all[rank]
+        mine = [k for k in range(len(groups)) if assign[k] == rank]
+        leaving = sorted((k for k in range(len(groups)) if assign[k] != rank), key=lambda k: (assign[k], k))
+        ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
+        with ctx:
+            # ---- cut the leaving groups on the device: one chunk per destination rank, chunks back to back
+            byte_splits = [0] * world
+            metas = [[] for _ in range(world)]
+            parts = []
+            for dst in range(world):
+                ks = [k for k in leaving if assign[k] == dst]
+                if not ks:
+                    continue
+                idx = np.concatenate([groups[k][2] for k in ks])
+                sel = geoms[idx].copy()
+                canv_d, total_d, offs_d = extract_crops_pyramid(pages, sel, lv[idx], stream)
+                parts.append((canv_d, total_d))
+                byte_splits[dst] = int(total_d)
+                j = 0
+                for k in ks:
+                    m = len(groups[k][0])
+                    metas[dst] += [k, m] + [v for w, p, o in zip(groups[k][0], groups[k][1], offs_d[j:j + m])
+                                            for v in (int(w), int(p), int(o))]
+                    j += m
+            if parts:
+                from .models import concat_device_buffers
+                canv = concat_device_buffers(parts, stream)
+                if len(parts) == 1:
+                    canv = canv[: parts[0][1]]
+            else:
+                some = next(iter(pages.values()))
+                canv = torch.empty(0, dtype=torch.uint8, device=getattr(some, "device", "cpu"))
+            recv, recv_splits, recv_metas = par.exchange_canvases_dev(
+                canv, byte_splits, [np.asarray(m, np.int32) for m in metas])
+        # ---- own groups straight from the resident pages, foreign groups straight from the receive buffer
+        res = list(self._run_groups_dev_local([groups[k] for k in mine], geoms, pages, stream, lv)) if mine else []
+        work = [(rank, k, None, groups[k][1]) for k in mine]
+        foreign, base = [], 0
+        height = cfg.data.img_size[0]
+        for src, meta in enumerate(recv_metas):
+            for gid, w, wp, offs_g in par.parse_group_meta(meta):
+                foreign.append((w, wp, base + offs_g))
+                work.append((src, gid, None, wp.tolist()))
+            base += recv_splits[src]
+        if foreign:
+            res = res + self._run_groups_buf(foreign, recv, height, stream)
+        S = cfg.max_label_length + 1
+        packed = []
+        for (ids, probs, glen) in res:
+            packed.append((np.concatenate([ids, np.full((ids.shape[0], 1), glen, np.int32)], axis=1),
+                           np.concatenate([probs, np.zeros((probs.shape[0], 1), np.float32)], axis=1)))
+        back = par.return_results(work, packed, len(groups), S + 1)
+        return [(i[:, :S], p[:, :S], int(i[0, S]) if len(i) else 0) for i, p in back]
 
-        def pixels(ks):
-            idx = np.concatenate([groups[k][2] for k in ks])
-            sel = geoms[idx].copy()
-            canv, _, offs = extract_crops_pyramid(pages, sel, lv[idx], stream)
-            host = _HostCanvases(canv, stream).np
-            out, j = [], 0
-            for k in ks:
+    def _run_groups_buf(self, groups, buf, height, stream=None):
+        """groups = (widths, padded widths, byte offsets into `buf`), `buf` a flat uint8 tensor on the compute device
+        (the receive buffer of the crop scatter): one packed recognizer call per <= max_tokens chunk."""
+        from . import _lib
+        rec = self.recognizer
+        cfg = rec._cfg
+        ph, pw = cfg.encoder.patch_size
+        gh = cfg.data.img_size[0] // ph
+        out = [None] * len(groups)
+        gtok = [gh * (int(np.sum(g[1])) // pw) for g in groups]
+        dt = np.dtype(_lib.YtkCrop)
+        start = 0
+        while start < len(groups):
+            end, tok = start, 0
+            while end < len(groups) and not (end > start and tok + gtok[end] > self.max_tokens):
+                tok += gtok[end]
+                end += 1
+            sel = groups[start:end]
+            w = np.concatenate([np.asarray(g[0], np.int64) for g in sel])
+            wp = np.concatenate([np.asarray(g[1], np.int64) for g in sel])
+            offs = np.concatenate([g[2] for g in sel])
+            n = w.shape[0]
+            ntok = gh * (wp // pw)
+            descs = np.zeros(n, dtype=dt)
+            descs["pix_off"] = offs
+            descs["w"] = w
+            descs["wp"] = wp
+            descs["tok_off"] = np.cumsum(ntok) - ntok
+            descs["ntok"] = ntok
+            descs["group"] = np.repeat(np.arange(end - start), [len(g[0]) for g in sel])
+            with _span("recognize.device"):
+                ids, probs, glen = rec.model.run_packed_ptr(buf.data_ptr(), 1, int(buf.numel()), descs, n, end - start,
+                                                            stream=stream)
+            off = 0
+            for k in range(start, end):
                 m = len(groups[k][0])
-                out.append([host[int(o):int(o) + int(r["canvas_h"]) * int(r["canvas_w"]) * 3]
-                            .reshape(int(r["canvas_h"]), int(r["canvas_w"]), 3) for r, o in zip(sel[j:j + m], offs[j:j + m])])
-                j += m
-            return out
-
-        return self._run_groups_dist(
-            groups, pixels,
-            lambda ks: self._run_groups_dev_local([groups[k] for k in ks], geoms, pages, stream, lv), stream)
+                out[k] = (ids[off:off + m], probs[off:off + m], int(glen[k - start]))
+                off += m
+            start = end
+        return out
 
     def _run_groups_dev_local(self, groups, geoms, pages_dev, stream=None, levels=None):
         """This rank's share of `_run_groups_dev`: the canvases of a <= max_tokens chunk are cut on the device
@@ -650,14 +741,15 @@ class BatchedOCR:
         self._slot_busy[self._slot] = (futs, handle)
         return handle
 
-    @staticmethod
-    def _upload_pages(stage, stream=None):
-        """(n, H0, W0, 3) uint8 staging tensor -> the same pages in HBM (asynchronous on `stream`)."""
+    def _upload_pages(self, stage, stream=None):
+        """(n, H0, W0, 3) uint8 staging tensor -> the same pages in HBM of the detector's device (asynchronous on
+        `stream`)."""
         import torch
+        dev = self.detector.model.cuda_device() if hasattr(self.detector.model, "cuda_device") else "cuda"
         if stream is not None:
             with torch.cuda.stream(stream):
-                return stage.to("cuda", non_blocking=True)
-        return stage.to("cuda", non_blocking=True)
+                return stage.to(dev, non_blocking=True)
+        return stage.to(dev, non_blocking=True)
 
     def collect(self, handle, stream=None):
         """Waits for the host stage of a submitted batch, recognises all its crops in one packed device call and
@@ -895,6 +987,14 @@ class _HostCanvases:
             self.torch.copy_(canv_dev)
             torch.cuda.current_stream().synchronize()
         self.np = self.torch.numpy()
+
+
+class _NullCtx:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        return False
 
 
 class _Done:

@@ -51,3 +51,36 @@ def synthetic_prob_map(quads, hw, page_hw, blur=5):
         dx, dy = 3, 3
         m[int((y0 + dy) * sy):int((y1 - dy) * sy), int((x0 + dx) * sx):int((x1 - dx) * sx)] = 1.0
     return cv2.GaussianBlur(m, (blur, blur), 0) * 0.9 + 0.02
+
+
+def peaked_parseq_state_dict(sd, eos_id=0, head_gain=6.0, seed=0):
+    """Turns a seeded random PARSeq state_dict (models._parseq_random_state_dict: the reference's init scheme, which
+    never emits EOS) into a trained-LIKE one for benchmarks: O(1) activations through the encoder / decoder, a head
+    whose logits are far from uniform, and a positional ramp towards the EOS class so that greedy decoding stops at
+    varied, image-dependent lengths (~5-40 tokens) like real text lines do.  Same construction as the test weights of
+    oracle/weights.py (which the product must not import); the values are synthetic, only their scale is realistic."""
+    import math
+
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    out = {k: v.clone() for k, v in sd.items()}
+    D = out["pos_queries"].shape[-1]
+    wstd = 1.0 / math.sqrt(D)
+    for k, v in out.items():
+        if not torch.is_floating_point(v) or v.dim() < 2 or k.endswith("pos_embed") or k == "pos_queries":
+            continue
+        if k.endswith("patch_embed.proj.weight") or k == "head.weight":
+            continue
+        fan_in = v.shape[-1]
+        gain = 0.5 if (k.endswith("proj.weight") and "attn" in k) or k.endswith("fc2.weight") else 1.0
+        out[k] = torch.randn(v.shape, generator=g).clamp_(-2, 2) * (gain / math.sqrt(fan_in))
+    out["encoder.pos_embed"] = 0.2 * torch.randn(out["encoder.pos_embed"].shape, generator=g)
+    C = out["head.weight"].shape[0]
+    out["head.weight"] = torch.randn(C, D, generator=g) * (head_gain / math.sqrt(D))
+    out["text_embed.embedding.weight"] = torch.randn(out["text_embed.embedding.weight"].shape, generator=g) * wstd
+    S = out["pos_queries"].shape[1]
+    pq = torch.randn(1, S, D, generator=g) * 0.5
+    w_eos = out["head.weight"][eos_id] / out["head.weight"][eos_id].norm()
+    ramp = (torch.arange(S, dtype=torch.float32) - 6.0) * 0.35
+    out["pos_queries"] = pq + ramp[None, :, None] * w_eos[None, None, :] * math.sqrt(D) * 0.5
+    return out

@@ -103,7 +103,7 @@ class TextRecognizer(BaseModule):
         # device-side crop extraction (csrc/crop_ops.cu, bit-exact with the OpenCV path): the page goes to HBM once and
         # the canvases are cut there - including the orientation fallback's 180-degree second look and the
         # source_downscale pyramid.
-        self.device_crops = os.environ.get("YTK_DEVICE_CROPS", "0") == "1"
+        self.device_crops = os.environ.get("YTK_DEVICE_CROPS", "1") != "0" and self.device.type == "cuda"
         self.model.to(self.device)
 
     # ------------------------------------------------------------------------------------------ batching
@@ -192,10 +192,9 @@ class TextRecognizer(BaseModule):
             if r_scores[j] > scores[idx] and r_scores[j] >= self.rec_orientation_fallback_thresh:
                 preds[idx], scores[idx], directions[idx] = r_preds[j], r_scores[j], r_dirs[j]
 
-    @staticmethod
-    def _upload_page(img):
+    def _upload_page(self, img):
         import torch
-        return torch.from_numpy(np.ascontiguousarray(img))[None].to("cuda")
+        return torch.from_numpy(np.ascontiguousarray(img))[None].to(self.model.cuda_device())
 
     def _run_records(self, pages, sel, levels, padded, group, n_groups):
         """Cuts the crops of the records `sel` (already in packing order) on the GPU and runs them as one packed call.
