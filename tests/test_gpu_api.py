@@ -102,3 +102,42 @@ def test_handles_bind_to_the_requested_device():
     rec.model.to("cuda:0")
     assert (rec.model._handle is None) == (k != 0)
     assert L.ytk_parseq_device(rec.model._ensure()) == 0
+
+
+def test_document_analyzer_batched_pages_equal_single_page_calls():
+    """DocumentAnalyzer with a plugged-in layout analyzer (stub returning a table + a paragraph region): the batched
+    multi-page form `analyze_pages` (BatchedOCR underneath) gives, page by page, what the reference-style one-page
+    `__call__` gives - with and without split_text_across_cells (lines cut at the cell borders before recognition)."""
+    import numpy as np
+    from yomitoku_b200 import DocumentAnalyzer
+    from yomitoku_b200 import schemas as S
+    from yomitoku_b200.synth import synthetic_page
+
+    def layout(img):
+        cells = [S.TableCellSchema(col=c + 1, row=r + 1, col_span=1, row_span=1,
+                                   box=[20 + 316 * c, 10 + 58 * r, 20 + 316 * (c + 1), 10 + 58 * (r + 1)], contents=None)
+                 for r in range(4) for c in range(3)]
+        rows = [S.TableLineSchema(box=[20, 10 + 58 * r, 968, 68 + 58 * r], score=0.9) for r in range(4)]
+        cols = [S.TableLineSchema(box=[20 + 316 * c, 10, 336 + 316 * c, 242], score=0.9) for c in range(3)]
+        table = S.TableStructureRecognizerSchema(box=[20, 10, 968, 242], n_row=4, n_col=3, rows=rows, cols=cols,
+                                                 spans=[], cells=cells, order=0)
+        para = S.Element(id=None, box=[0, 600, 1600, 900], score=0.9, role=None, contents=None)
+        return S.LayoutAnalyzerSchema(paragraphs=[para], tables=[table], figures=[]), None
+
+    cfg = {"ocr": {"text_detector": {"from_pretrained": False},
+                   "text_recognizer": {"from_pretrained": False, "model_name": "parseq-tiny-dynw-v4",
+                                       "dynamic_width": True, "batch_bucketing": True}}}
+    pages = [synthetic_page(60)[0], synthetic_page(61)[0]]
+    for split in (False, True):
+        an = DocumentAnalyzer(configs=cfg, device="cuda", layout_analyzer=layout, split_text_across_cells=split)
+        single = [an(p)[0] for p in pages]
+        batched = an.analyze_pages(pages)
+        assert len(batched) == 2
+        for a, b in zip(single, batched):
+            assert [w.points for w in a.words] == [w.points for w in b.words]
+            assert [w.content for w in a.words] == [w.content for w in b.words]
+            assert [p.contents for p in a.paragraphs] == [p.contents for p in b.paragraphs]
+            assert [p.order for p in a.paragraphs] == [p.order for p in b.paragraphs]
+            assert [[c.contents for c in t.cells] for t in a.tables] == [[c.contents for c in t.cells] for t in b.tables]
+            assert np.allclose([w.rec_score for w in a.words], [w.rec_score for w in b.words], atol=1e-6)
+        an._batched.close()

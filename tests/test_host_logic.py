@@ -631,3 +631,25 @@ def test_product_never_imports_the_oracle():
             "assert 'oracle' not in sys.modules" % (os.path.dirname(HERE), os.path.dirname(HERE)))
     # the repo root is needed to find the package itself; the assertion is that importing it pulls in no oracle module
     assert subprocess.run([sys.executable, "-c", code], cwd="/", capture_output=True).returncode == 0
+
+
+def test_vectorised_clipper_offset_equals_scalar_routine():
+    """postprocessor.offset_boxes_round (one page's boxes at once) == offset_convex_polygon_round box by box: same
+    double-precision operations in the same order, so equality, not tolerance - including boxes whose integer
+    truncation collapses vertices (handled by the scalar fallback)."""
+    import cv2
+    from yomitoku_b200.postprocessor import offset_boxes_round, offset_convex_polygon_round
+    rng = np.random.default_rng(3)
+    boxes, deltas = [], []
+    for i in range(600):
+        c = rng.uniform(50, 1500, 2)
+        size = (float(rng.uniform(3, 400)), float(rng.uniform(3, 60))) if i % 7 else \
+            (float(rng.uniform(0.2, 2.5)), float(rng.uniform(0.2, 2.5)))
+        ang = float(rng.uniform(-90, 90)) if i % 3 else 0.0
+        boxes.append(cv2.boxPoints(((float(c[0]), float(c[1])), size, ang)))
+        deltas.append(float(rng.uniform(0.5, 12)))
+    ref = [offset_convex_polygon_round(b, d) for b, d in zip(boxes, deltas)]
+    got = offset_boxes_round(np.array(boxes), np.array(deltas))
+    for a, b in zip(ref, got):
+        assert a.shape == b.shape and np.array_equal(a, b)
+    assert offset_boxes_round(np.zeros((0, 4, 2)), np.zeros(0)) == []

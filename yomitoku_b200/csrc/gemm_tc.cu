@@ -33,6 +33,14 @@ static std::atomic<long long> g_launches{0};
 void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
+int pdl_launch_attr(cudaLaunchAttribute* attr) {
+    static const bool off = getenv("YTK_NO_PDL") != nullptr;
+    if (off) return 0;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    return 1;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -207,6 +215,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     if constexpr (PAIR) cluster_sync_all();  // the peer's barriers must be initialised before anything is signalled on them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // programmatic dependent launch: the prologue above overlapped the previous kernel's tail; operands, residuals and
+    // the output buffer may only be touched from here on
+    pdl_wait();
+    pdl_launch_dependents();
 
     const int tiles_m = args.n_img * args.tiles_h * args.tiles_w;
     const int num_kb = args.ntaps * args.kpt;
@@ -370,6 +382,8 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             const uint32_t t_addr =
                 tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
             [[maybe_unused]] float dots[4] = {0.f, 0.f, 0.f, 0.f};
+            [[maybe_unused]] float rm_m = -INFINITY, rm_s = 0.f;   // EPI_ROWMAX: running (max, sum exp, arg-max)
+            [[maybe_unused]] int rm_i = 0x7fffffff;
 #pragma unroll 1
             for (int c = 0; c < BLOCK_N / 32; ++c) {
                 if (((kFin ? (c >> 1) : c) & 1) != wset) continue;  // chunk belongs to the other warp set
@@ -435,7 +449,33 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + min(col0 + j, args.Cout - 1));
                     }
                 }
-                if constexpr (kFin) {
+                if constexpr (MODE == EPI_ROWMAX) {
+                    // chunk statistics over the valid columns, then one merge into the running triple
+                    const int nvalid = min(32, args.Cout - col0);
+                    float cm = -INFINITY;
+                    int ci = 0x7fffffff;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float v = j < nvalid ? f[j] : -INFINITY;
+                        f[j] = v;
+                        if (v > cm) {            // strict: the smallest index wins among equals (ascending j)
+                            cm = v;
+                            ci = col0 + j;
+                        }
+                    }
+                    float cs = 0.f;
+                    if (args.act != ACT_RELU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) cs += __expf(f[j] - cm);   // exp(-inf) = 0 for masked columns
+                    }
+                    if (cm > rm_m) {             // chunks arrive in ascending column order: ties keep the earlier index
+                        rm_s = rm_s * __expf(rm_m - cm) + cs;
+                        rm_m = cm;
+                        rm_i = ci;
+                    } else {
+                        rm_s += cs * __expf(cm - rm_m);
+                    }
+                } else if constexpr (kFin) {
                     // fused ConvTranspose2d(64->1, 2, 2) + sigmoid: this chunk holds 32 of the 64 channels of output
                     // pixel (2h+i, 2w+j) of the first transposed conv (after BN+ReLU)
                     const int chan0 = (c & 1) * 32;
@@ -673,6 +713,17 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     }
                 }
             }
+            if constexpr (MODE == EPI_ROWMAX) {
+                if (row_ok) {
+                    const long long pixo = (static_cast<long long>(tc.img) * args.Ho + hh) * args.Wo + ww;
+                    float4 o;
+                    o.x = rm_m;
+                    o.y = rm_s;
+                    o.z = __int_as_float(rm_i);
+                    o.w = 0.f;
+                    reinterpret_cast<float4*>(args.out)[pixo * args.ldc + (tc.n0 / BLOCK_N) * 2 + wset] = o;
+                }
+            }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -788,7 +839,14 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
         set_error("gemm plan: null output");
         return 1;
     }
-    if (e.mode == EPI_CONVT_FINAL) {
+    if (e.mode == EPI_ROWMAX) {
+        if (e.resid != nullptr) {
+            set_error("gemm plan: ROWMAX takes no residual");
+            return 1;
+        }
+        a.out_f32 = 1;
+        a.ldc = 2LL * a.tiles_n;   // float4 partials per row
+    } else if (e.mode == EPI_CONVT_FINAL) {
         if (Cout != 256 || e.fin_w == nullptr || !e.out_f32) {
             set_error("gemm plan: CONVT_FINAL needs Cout=256, fp32 output and the final conv weights");
             return 1;
@@ -813,7 +871,8 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
     const int tiles = tiles_m * a.tiles_n;
     static const bool no_cluster = getenv("YTK_NO_CLUSTER") != nullptr;
     static const bool pair_conv = getenv("YTK_PAIR_CONV") != nullptr;
-    a.cluster = (!no_cluster && (allow_pair || pair_conv) && e.mode != EPI_CONVT_FINAL && tiles >= 4 * num_sms() &&
+    a.cluster = (!no_cluster && (allow_pair || pair_conv) && e.mode != EPI_CONVT_FINAL && e.mode != EPI_ROWMAX &&
+                 tiles >= 4 * num_sms() &&
                  tiles_m >= 8)
                     ? 2
                     : 1;
@@ -999,7 +1058,7 @@ static int launch_variant3(const GemmPlan* plan, cudaStream_t stream) {
         // fewer than num_sms / 2), capped by the number of work units
         const int cl = plan->args.cluster;
         cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute attr[1];
+        cudaLaunchAttribute attr[2];
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = cl;
         attr[0].val.clusterDim.y = 1;
@@ -1008,7 +1067,7 @@ static int launch_variant3(const GemmPlan* plan, cudaStream_t stream) {
         cfg.dynamicSmemBytes = Cfg::kSmemBytes;
         cfg.stream = stream;
         cfg.attrs = attr;
-        cfg.numAttrs = 1;
+        cfg.numAttrs = 1 + pdl_launch_attr(attr + 1);
         static int max_clusters = -1;
         if (max_clusters < 0) {
             cfg.gridDim = dim3((num_sms() / cl) * cl);
@@ -1034,9 +1093,16 @@ static int launch_variant3(const GemmPlan* plan, cudaStream_t stream) {
         }
         return 0;
     } else {
-        kern<<<plan->grid, kThreads, Cfg::kSmemBytes, stream>>>(plan->maps, plan->args);
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute attr[1];
+        cfg.gridDim = dim3(plan->grid);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+        cfg.stream = stream;
+        cfg.attrs = attr;
+        cfg.numAttrs = pdl_launch_attr(attr);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan->maps, plan->args);
         count_launch();
-        cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) {
             set_error("gemm_tc_kernel<%d,%d,%d,%d,%d> launch: %s", BLOCK_N, OUT_F32, RESID, MODE, DIRECT,
                       cudaGetErrorString(e));
@@ -1086,6 +1152,7 @@ static int launch_bn(const GemmPlan* plan, cudaStream_t stream) {
         set_error("CONVT_FINAL needs BLOCK_N = 256");
         return 1;
     }
+    if (a.mode == EPI_ROWMAX) return launch_variant3<BLOCK_N, 1, 0, EPI_ROWMAX, 0, 0>(plan, stream);
     if (a.mode == EPI_SHUFFLE2X) {
         if (resid == 0 && !a.out_f32) return launch_variant<BLOCK_N, 0, 0, EPI_SHUFFLE2X>(plan, stream);
         if (resid == 0 && a.out_f32) return launch_variant<BLOCK_N, 1, 0, EPI_SHUFFLE2X>(plan, stream);

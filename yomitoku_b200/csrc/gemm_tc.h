@@ -24,6 +24,12 @@ enum EpiMode : int {
     // DBNet binarize tail: ConvT(64->64,2,2)+BN+ReLU as above (Cout = 256) immediately followed by
     // ConvT(64->1,2,2)+sigmoid evaluated in registers; out = fp32 probability map [N, 4*Ho, 4*Wo]
     EPI_CONVT_FINAL = 2,
+    // Row-wise softmax statistics instead of the output matrix (the PARSeq head, K9 of SURVEY.md section 2.3): for every
+    // row and every 32-column slice owner (two epilogue warps per row and N tile) the running (max, sum exp(x - max),
+    // arg-max) of x = acc + bias over the columns < Cout; `out` is a float4 array [rows][2 * tiles_n] = {max, sum,
+    // bit-cast index, 0}.  The [rows, Cout] fp32 logits never touch HBM; a tiny kernel merges the partials
+    // (parseq_ops.cu: ar_control_kernel / rowmax_finalize_kernel).  act == ACT_RELU skips the sum (arg-max only).
+    EPI_ROWMAX = 3,
 };
 
 struct ConvTap {
@@ -108,6 +114,9 @@ int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream);
 int make_tmap_op_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
                       const uint32_t box[4]);
 
+// Launch attribute set for kernels that call pdl_wait() (ptx.cuh): programmatic stream serialization unless YTK_NO_PDL
+// is set.  Returns the number of attributes written to attr[0..].
+int pdl_launch_attr(cudaLaunchAttribute* attr);
 void set_error(const char* fmt, ...);
 const char* last_error();
 int num_sms();

@@ -553,6 +553,8 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             }
         }
         auto b16 = [](void* p, size_t elems) { return static_cast<void*>(reinterpret_cast<op_t*>(p) + elems); };
+        // the [rows, C] logits are materialised only when the caller wants the AR logits themselves
+        const bool fused_head = !(logits_out && c.refine_iters == 0) && getenv("YTK_NO_FUSED_HEAD") == nullptr;
         Part parts[2];
         for (int k = 0; k < nparts; ++k) {
             Part& p = parts[k];
@@ -594,7 +596,19 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             if (mk(&p.p_l1, b16(hb, r0 * D), D, m->lin1, b16(mlpb, r0 * m->lin1.N), m->lin1.N, 0, ACT_GELU, nullptr, 0, 0))
                 return 1;
             if (mk(&p.p_l2, b16(mlpb, r0 * m->lin1.N), m->lin1.N, m->lin2, x1p, D, 1, ACT_NONE, x1p, 1, D)) return 1;
-            if (mk(&p.p_hd, b16(hb, r0 * D), D, m->head, logits + r0 * ldl, ldl, 1, ACT_NONE, nullptr, 0, 0)) return 1;
+            if (fused_head) {
+                // head GEMM with the row-max epilogue: (max, sum exp, arg-max) partials instead of [rows, C] fp32 logits
+                // (the partials live in the logits buffer: 16 bytes x 2 * tiles_n per row)
+                Epilogue ep;
+                ep.bias = m->head.b;
+                ep.out = logits + r0 * ldl;
+                ep.out_f32 = 1;
+                ep.mode = EPI_ROWMAX;
+                ep.act = c.refine_iters == 0 ? ACT_NONE : ACT_RELU;   // arg-max only unless the AR logits ARE the output
+                if (gemm_plan_create(&p.p_hd, b16(hb, r0 * D), D, p.rows, m->head.K, m->head.w, m->head.N, ep)) return 1;
+                // partial rows start at float4 index row * ldc: re-base this part's output inside the shared buffer
+                p.p_hd.args.out = reinterpret_cast<float4*>(logits) + r0 * p.p_hd.args.ldc;
+            } else if (mk(&p.p_hd, b16(hb, r0 * D), D, m->head, logits + r0 * ldl, ldl, 1, ACT_NONE, nullptr, 0, 0)) return 1;
             if (mk(&p.p_kv, b16(cin, r0 * D), D, m->self_kv, b16(ckv, r0 * S * 2 * D), (long long)S * 2 * D, 0, ACT_NONE,
                    nullptr, 0, 0))
                 return 1;
@@ -611,6 +625,9 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             float* x1p = x1 + r0 * D;
             void* hbp = b16(hb, r0 * D);
             float* lg = logits + r0 * ldl;
+            const long long ldp = p.p_hd.args.ldc;              // fused head: float4 partials per row
+            const int npart = fused_head ? (int)ldp : 0;
+            if (fused_head) lg = reinterpret_cast<float*>(reinterpret_cast<float4*>(logits) + r0 * ldp);
             if (launch_dec_self_attn(m->q_self, b16(ckv, r0 * S * 2 * D), p.rows, S, D, c.dec_heads, p.a.step,
                                      b16(sa, r0 * D), ps))
                 return 1;
@@ -633,13 +650,19 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
                 return 1;
             if (gemm_plan_launch(&p.p_hd, ps)) return 1;
             if (c.refine_iters == 0) {
-                if (launch_softmax_max(lg, ldl, C, p.rows, S, S, i, nullptr, eos, ids + r0 * S, probs + r0 * S, ps)) return 1;
+                if (fused_head) {
+                    if (launch_rowmax_finalize(lg, ldp, npart, C, p.rows, S, S, i, nullptr, eos, ids + r0 * S,
+                                               probs + r0 * S, ps))
+                        return 1;
+                } else if (launch_softmax_max(lg, ldl, C, p.rows, S, S, i, nullptr, eos, ids + r0 * S, probs + r0 * S, ps))
+                    return 1;
                 if (logits_out)
                     CK(cudaMemcpy2DAsync(logits_out + (r0 * S + (size_t)i) * C, (size_t)S * C * 4, lg, ldl * 4,
                                          (size_t)C * 4, p.rows,
                                          logits_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ps));
             }
-            if (launch_ar_control(lg, ldl, C, p.rows, S, row_group + p.r0, p.g0, p.ng, p.a, eos, c.rep_on, c.rep_period_max,
+            if (launch_ar_control(lg, fused_head ? ldp : ldl, C, npart, p.rows, S, row_group + p.r0, p.g0, p.ng, p.a, eos,
+                                  c.rep_on, c.rep_period_max,
                                   c.rep_min_run_p1, c.rep_min_repeats, m->embed, m->pos_q, D, m->Dr, m->norm_c.g, m->norm_c.b,
                                   b16(cin, r0 * D), ps))
                 return 1;
@@ -734,6 +757,23 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
         for (int r0 = 0; r0 < R; r0 += logits_rows) {
             const int rows = std::min(logits_rows, R - r0);
             const op_t* a = reinterpret_cast<const op_t*>(hb) + (size_t)r0 * D;
+            const bool want_logits = logits_out && final;
+            if (!want_logits && getenv("YTK_NO_FUSED_HEAD") == nullptr) {
+                // head GEMM -> softmax statistics in the epilogue: only (id, probability) per position exist in HBM
+                Epilogue ep;
+                ep.bias = m->head.b;
+                ep.out = logits;
+                ep.out_f32 = 1;
+                ep.mode = EPI_ROWMAX;
+                GemmPlan hp;
+                if (gemm_plan_create(&hp, a, D, rows, m->head.K, m->head.w, m->head.N, ep)) return 1;
+                flops += hp.flops;
+                if (gemm_plan_launch(&hp, st)) return 1;
+                if (launch_rowmax_finalize(logits, hp.args.ldc, (int)hp.args.ldc, C, rows, S, 1, r0,
+                                           final ? ar.rep_cut : nullptr, eos, ids, probs, st))
+                    return 1;
+                continue;
+            }
             if (Lin::run(a, D, rows, m->head, logits, ldl, 1, ACT_NONE, nullptr, 0, 0, st, &flops)) return 1;
             // the repetition patch (parseq.py:301-309) applies to the final logits only
             if (launch_softmax_max(logits, ldl, C, rows, S, 1, r0, final ? ar.rep_cut : nullptr, eos, ids, probs, st))

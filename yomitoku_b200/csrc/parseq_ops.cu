@@ -11,6 +11,20 @@
 
 namespace ytk {
 
+// Launch with programmatic stream serialization (kernels below that start with pdl_wait(): the chain of an AR step).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_launch_attr(attr);
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // =================================================================================================== patchify
 // Replaces timm PatchEmbed.proj's im2col (reference parseq_transformer.py:220-227): the conv itself is a tcgen05 GEMM;
 // this kernel writes its A operand and seeds the fp32 residual stream with the cropped positional embedding.
@@ -100,6 +114,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, i
                                                         float* __restrict__ out_f32, const float* __restrict__ addvec,
                                                         int period, const int* __restrict__ add_row0_dev,
                                                         int add_row0, int writeback) {
+    pdl_wait();
+    pdl_launch_dependents();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= M) return;
@@ -177,11 +193,12 @@ int launch_layernorm(float* x, int M, int D, int d_real, const float* gamma, con
     }
     if (M <= 0) return 0;
     const int warps_per_block = 8;
-    layernorm_kernel<<<(M + warps_per_block - 1) / warps_per_block, warps_per_block * 32, 0, st>>>(
-        x, M, D, d_real, gamma, beta, eps, reinterpret_cast<op_t*>(out_bf16), out_f32, addvec,
-        period > 0 ? period : 1, add_row0_dev, add_row0, writeback);
+    const cudaError_t e = launch_pdl(layernorm_kernel, dim3((M + warps_per_block - 1) / warps_per_block),
+                                     dim3(warps_per_block * 32), 0, st, x, M, D, d_real, gamma, beta, eps,
+                                     reinterpret_cast<op_t*>(out_bf16), out_f32, addvec, period > 0 ? period : 1,
+                                     add_row0_dev, add_row0, writeback);
     count_launch();
-    return cudaGetLastError() != cudaSuccess;
+    return e != cudaSuccess;
 }
 
 // =================================================================================================== flash attention
@@ -500,6 +517,8 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
     constexpr int CPL = NCH / LPK;                // 16-byte chunks per lane
     constexpr int NSUB = 32 / LPK;                // key subsets
     __shared__ float sP[4][kMaxMem];
+    pdl_wait();
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wid = blockIdx.x * 4 + warp;
     if (wid >= B * heads) return;
@@ -606,15 +625,16 @@ static int launch_single_query_attn(int mode, const void* qsrc, const void* kv, 
     const unsigned grid = (B * heads + 3) / 4;
     const op_t *q = reinterpret_cast<const op_t*>(qsrc), *k = reinterpret_cast<const op_t*>(kv);
     op_t* o = reinterpret_cast<op_t*>(out);
+    cudaError_t e;
     switch (hd) {
-        case 32: single_query_attn_kernel<32><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
-        case 48: single_query_attn_kernel<48><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
-        case 64: single_query_attn_kernel<64><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
-        case 96: single_query_attn_kernel<96><<<grid, 128, 0, st>>>(mode, q, k, B, S, D, heads, step_dev, descs, o); break;
+        case 32: e = launch_pdl(single_query_attn_kernel<32>, dim3(grid), dim3(128), 0, st, mode, q, k, B, S, D, heads, step_dev, descs, o); break;
+        case 48: e = launch_pdl(single_query_attn_kernel<48>, dim3(grid), dim3(128), 0, st, mode, q, k, B, S, D, heads, step_dev, descs, o); break;
+        case 64: e = launch_pdl(single_query_attn_kernel<64>, dim3(grid), dim3(128), 0, st, mode, q, k, B, S, D, heads, step_dev, descs, o); break;
+        case 96: e = launch_pdl(single_query_attn_kernel<96>, dim3(grid), dim3(128), 0, st, mode, q, k, B, S, D, heads, step_dev, descs, o); break;
         default: set_error("single-query attention: head dim %d unsupported (32/48/64/96)", hd); return 1;
     }
     count_launch();
-    return cudaGetLastError() != cudaSuccess;
+    return e != cudaSuccess;
 }
 
 // Query stream vs. content K/V cache (reference DecoderLayer.forward_stream self_attn, parseq_transformer.py:83-90):
@@ -670,7 +690,7 @@ __device__ int detect_repeat(const int* seq, int n, int period_max, int min_run_
     return -1;
 }
 
-__global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict__ logits, long long ldl, int C, int S,
+__global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict__ logits, long long ldl, int C, int npart, int S,
                                                          const int* __restrict__ row_group, int g0, int ngroups,
                                                          ArState a, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1,
                                                          int rep_min_repeats, const float* __restrict__ embed,
@@ -683,6 +703,8 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
     __shared__ float s_stat[2];
     __shared__ float red[8];
     __shared__ int s_last;
+    pdl_wait();
+    pdl_launch_dependents();
     const int row = blockIdx.x;
     const int i = *a.step;
     const int j = i + 1;
@@ -692,7 +714,18 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
         const float* lr = logits + (long long)row * ldl;
         float best = -INFINITY;
         int bi = 0x7fffffff;
-        {
+        if (npart > 0) {
+            // fused head epilogue (gemm_tc EPI_ROWMAX): `logits` holds float4 partials {max, sum, index, -}, ldl per row
+            const float4* pr = reinterpret_cast<const float4*>(logits) + (long long)row * ldl;
+            for (int v = threadIdx.x; v < npart; v += blockDim.x) {
+                const float4 x = __ldg(pr + v);
+                const int xi = __float_as_int(x.z);
+                if (x.x > best || (x.x == best && xi < bi)) {
+                    best = x.x;
+                    bi = xi;
+                }
+            }
+        } else {
             const int nvec = C >> 2;
             const float4* l4 = reinterpret_cast<const float4*>(lr);
             for (int v = threadIdx.x; v < nvec; v += blockDim.x) {   // strict '>' keeps the smallest index (ascending)
@@ -823,7 +856,7 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
     }
 }
 
-int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int g0,
+int launch_ar_control(const float* logits, long long ldl, int C, int npart, int B, int S, const int* row_group, int g0,
                       int ngroups, ArState a, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
                       const float* embed, const float* pos_q, int D, int d_real, const float* g_c, const float* b_c,
                       void* cin, cudaStream_t st) {
@@ -831,11 +864,11 @@ int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, c
         set_error("ar_control: D=%d too large", D);
         return 1;
     }
-    ar_control_kernel<<<B, 256, 0, st>>>(logits, ldl, C, S, row_group, g0, ngroups, a, eos_id, rep_on, rep_period_max,
-                                         rep_min_run_p1, rep_min_repeats, embed, pos_q, D, d_real, g_c, b_c,
-                                         reinterpret_cast<op_t*>(cin));
+    const cudaError_t e = launch_pdl(ar_control_kernel, dim3(B), dim3(256), 0, st, logits, ldl, C, npart, S, row_group, g0,
+                                     ngroups, a, eos_id, rep_on, rep_period_max, rep_min_run_p1, rep_min_repeats, embed,
+                                     pos_q, D, d_real, g_c, b_c, reinterpret_cast<op_t*>(cin));
     count_launch(1);
-    return cudaGetLastError() != cudaSuccess;
+    return e != cudaSuccess;
 }
 
 // =================================================================================================== refinement embed
@@ -989,6 +1022,55 @@ __global__ void __launch_bounds__(256) softmax_max_kernel(const float* __restric
         ids[g] = a.i;
         probs[g] = 1.f / a.s;
     }
+}
+
+// Same result from the partials of the fused head epilogue (gemm_tc EPI_ROWMAX): one warp per row merges the
+// 2 * tiles_n (max, sum exp, arg-max) triples.
+__global__ void __launch_bounds__(256) rowmax_finalize_kernel(const float4* __restrict__ part, long long ldp, int npart,
+                                                              int rows, int C, int S, long long g_stride, long long g_off,
+                                                              const int* __restrict__ rep_cut, int eos_id,
+                                                              int* __restrict__ ids, float* __restrict__ probs) {
+    const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const long long g = (long long)r * g_stride + g_off;
+    const int crop = (int)(g / S), pos = (int)(g % S);
+    if (rep_cut != nullptr && rep_cut[crop] == pos) {
+        if (lane == 0) {
+            ids[g] = eos_id;
+            probs[g] = 1.f / (1.f + (float)(C - 1) * expf(-60.f));
+        }
+        return;
+    }
+    SmStat st{-INFINITY, 0.f, 0x7fffffff};
+    const float4* pr = part + (long long)r * ldp;
+    for (int v = lane; v < npart; v += 32) {
+        const float4 x = __ldg(pr + v);
+        SmStat b{x.x, x.y, __float_as_int(x.z)};
+        sm_merge(st, b);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        SmStat b;
+        b.m = __shfl_xor_sync(0xffffffffu, st.m, o);
+        b.s = __shfl_xor_sync(0xffffffffu, st.s, o);
+        b.i = __shfl_xor_sync(0xffffffffu, st.i, o);
+        sm_merge(st, b);
+    }
+    if (lane == 0) {
+        ids[g] = st.i;
+        probs[g] = 1.f / st.s;
+    }
+}
+
+int launch_rowmax_finalize(const float* partials, long long ldp, int npart, int C, int rows, int S, long long g_stride,
+                           long long g_off, const int* rep_cut, int eos_id, int* ids, float* probs, cudaStream_t st) {
+    if (rows <= 0) return 0;
+    rowmax_finalize_kernel<<<(rows * 32 + 255) / 256, 256, 0, st>>>(reinterpret_cast<const float4*>(partials), ldp, npart,
+                                                                    rows, C, S, g_stride, g_off, rep_cut, eos_id, ids,
+                                                                    probs);
+    count_launch();
+    return cudaGetLastError() != cudaSuccess;
 }
 
 int launch_softmax_max(const float* logits, long long ldl, int C, int rows, int S, long long g_stride, long long g_off,

@@ -74,7 +74,8 @@ struct ArState {
 };
 // Arg-max over the head logits + the reference's per-step control logic (parseq.py:220-250) + content embedding of
 // the emitted token (text_embed * sqrt(D) + pos_queries[j-1]) normalised by LN_c -> cin bf16 [B, D].
-int launch_ar_control(const float* logits, long long ldl, int C, int B, int S, const int* row_group, int g0,
+// npart > 0: `logits` holds the float4 partials of the fused head epilogue (gemm_tc EPI_ROWMAX), ldl = partials per row.
+int launch_ar_control(const float* logits, long long ldl, int C, int npart, int B, int S, const int* row_group, int g0,
                       int ngroups, ArState st_, int eos_id, int rep_on, int rep_period_max, int rep_min_run_p1, int rep_min_repeats,
                       const float* embed, const float* pos_q, int D, int d_real, const float* g_c, const float* b_c,
                       void* cin, cudaStream_t st);
@@ -89,6 +90,9 @@ int launch_refine_embed(const int* raw, const int* row_group, const int* group_l
 // Output index of local row r is r * g_stride + g_off (= crop * S + position).
 int launch_softmax_max(const float* logits, long long ldl, int C, int rows, int S, long long g_stride, long long g_off,
                        const int* rep_cut, int eos_id, int* ids, float* probs, cudaStream_t st);
+// launch_softmax_max from the partials of the fused head epilogue: partials float4 [rows][ldp], npart valid per row.
+int launch_rowmax_finalize(const float* partials, long long ldp, int npart, int C, int rows, int S, long long g_stride,
+                           long long g_off, const int* rep_cut, int eos_id, int* ids, float* probs, cudaStream_t st);
 int launch_bcast_rows(const void* src, void* dst, int row_bytes, long long dst_stride_bytes, int rows,
                       cudaStream_t st);
 int launch_apply_rep_cut(const int* rep_cut, int B, int S, int C, int eos_id, int* ids, float* probs, cudaStream_t st);

@@ -40,18 +40,73 @@ class OCRSchema(BaseSchema):
     words: List[WordPrediction] = Field(..., description="Recognized words")
 
 
+Box = conlist(int, min_length=4, max_length=4)
+
+
+class Element(BaseSchema):
+    """One layout region (reference schemas/document_analyzer.py:9-29): what a layout analyzer returns per paragraph /
+    figure."""
+    id: Union[str, None] = Field(None, description="Unique identifier of the element")
+    box: Box = Field(..., description="[x1, y1, x2, y2]")
+    score: float = Field(..., description="Detection confidence")
+    role: Union[str, None] = Field(..., description="e.g. 'section_headings', 'page_header', 'page_footer'")
+    contents: Union[str, None] = Field(None, description="Text content of the element")
+
+
 class ParagraphSchema(BaseSchema):
-    box: conlist(int, min_length=4, max_length=4)
+    box: Box
     contents: Union[str, None]
     direction: Union[str, None]
     order: Union[int, None]
     role: Union[str, None]
 
 
+class TableCellSchema(BaseSchema):
+    col: int
+    row: int
+    col_span: int
+    row_span: int
+    box: Box
+    contents: Union[str, None]
+
+
+class TableLineSchema(BaseSchema):
+    box: Box
+    score: float
+
+
+class TableStructureRecognizerSchema(BaseSchema):
+    """reference schemas/document_analyzer.py:94-118."""
+    box: Box
+    n_row: int
+    n_col: int
+    rows: List[TableLineSchema]
+    cols: List[TableLineSchema]
+    spans: List[TableLineSchema] = Field(default_factory=list)
+    cells: List[TableCellSchema]
+    order: int
+
+
+class LayoutAnalyzerSchema(BaseSchema):
+    """What the layout half (reference layout_analyzer.py:38-49) hands to DocumentAnalyzer.aggregate."""
+    paragraphs: List[Element]
+    tables: List[TableStructureRecognizerSchema]
+    figures: List[Element]
+
+
+class FigureSchema(BaseSchema):
+    box: Box
+    order: Union[int, None]
+    paragraphs: List[ParagraphSchema]
+    direction: Union[str, None]
+    figure_path: Union[str, None] = None
+
+
 class DocumentAnalyzerSchema(BaseSchema):
-    """reference DocumentAnalyzerSchema; tables/figures come from the RT-DETRv2 layout models, which are outside the
-    hot path - they are empty unless a layout analyzer is plugged in."""
+    """reference DocumentAnalyzerSchema (schemas/document_analyzer.py:207-226).  Tables / figures / layout paragraphs
+    come from a layout analyzer (the RT-DETRv2 models are outside this repo's hot path); without
+    one every word becomes its own paragraph, exactly what the reference's aggregate does with an empty layout."""
     paragraphs: List[ParagraphSchema] = Field(default_factory=list)
-    tables: List[dict] = Field(default_factory=list)
+    tables: List[TableStructureRecognizerSchema] = Field(default_factory=list)
     words: List[WordPrediction] = Field(default_factory=list)
-    figures: List[dict] = Field(default_factory=list)
+    figures: List[FigureSchema] = Field(default_factory=list)
