@@ -107,7 +107,8 @@ def _pick_cpu_threads(det_sd, x):
         return _CPU_THREADS
     from oracle import dbnet as odb
     ncpu = os.cpu_count() or 1
-    cands = sorted({t for t in (16, 32, 64, ncpu) if t <= ncpu} | {min(ncpu, 8)})
+    # (more intra-op threads than 64 collapse on this workload: 128 threads took 26 s for the probe in round 2)
+    cands = sorted({t for t in (8, 16, 32, 64) if t <= ncpu} | {min(ncpu, 8)})
     sweep = {}
     xs = x[:, :, :384, :512].contiguous()      # a quarter-size map is enough to rank the settings
     for t in cands:

@@ -96,6 +96,47 @@ __device__ __forceinline__ Unit make_unit(const SeqDesc& sd, int head, int qt, l
     return u;
 }
 
+// The units of one (CTA, slot) worker in processing order: pairs p = start, start + W, ... ; inside a pair the query
+// tiles in ascending order (so that the K / V tiles of the pair stay hot in L2).  Every role of a slot walks the same
+// sequence.
+template <int MASKED>
+struct UnitIter {
+    int p, qt, nqt, head, W, npairs;
+    SeqDesc sd;
+    Unit u;
+    const AttnArgs* a;
+    __device__ __forceinline__ void load_pair() {
+        const int seq = p / a->heads;
+        head = p - seq * a->heads;
+        sd = a->seqs[seq];
+        nqt = (sd.q_len + kAtQ - 1) / kAtQ;
+    }
+    // positions on the first unit with at least one key tile; false when the worker has none
+    __device__ __forceinline__ bool begin(const AttnArgs* args, int start, int stride, int npairs_) {
+        a = args;
+        W = stride;
+        npairs = npairs_;
+        p = start;
+        qt = -1;
+        if (p >= npairs) return false;
+        load_pair();
+        return next();
+    }
+    __device__ __forceinline__ bool next() {
+        for (;;) {
+            ++qt;
+            while (qt >= nqt) {
+                p += W;
+                qt = 0;
+                if (p >= npairs) return false;
+                load_pair();
+            }
+            u = make_unit<MASKED>(sd, head, qt, a->ldkv);
+            if (u.nt > 0) return true;
+        }
+    }
+};
+
 __device__ __forceinline__ float fast_exp2(float x) {
     float r;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -221,8 +262,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                     if (warp_active) {
                         const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
                         float ls = 0.f;
+                        // only the 16-key steps the P V product reads (the rest of the tile holds no visible key)
+                        const int nch = ((min(kAtKV, u.k_end - key0) + 15) >> 4) * 2;
 #pragma unroll
                         for (int ch = 0; ch < 8; ++ch) {
+                            if (ch >= nch) break;
                             float pv[8];
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
@@ -283,34 +327,49 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
             uint8_t* sQ = smem + s * Cfg::kSlotBytes;
             uint8_t* sKV = sQ + Cfg::kQBytes + Cfg::kPBytes;
             uint32_t nu = 0, ck = 0;
-            for (int p = static_cast<int>(blockIdx.x) * 2 + s; p < npairs; p += W) {
-                const int seq = p / args.heads, head = p - seq * args.heads;
-                const SeqDesc sd = args.seqs[seq];
-                const int nqt = (sd.q_len + kAtQ - 1) / kAtQ;
-                for (int qt = 0; qt < nqt; ++qt) {
-                    const Unit u = make_unit<MASKED>(sd, head, qt, args.ldkv);
-                    if (u.nt <= 0) continue;
-                    mbar_wait(&b.q_empty, (nu & 1u) ^ 1u);
-                    mbar_expect_tx(&b.q_full, Cfg::kQBytes);
+            UnitIter<MASKED> it, pf;     // pf runs one unit ahead: its tiles are pulled into L2 while `it` is being fed
+            bool more = it.begin(&args, static_cast<int>(blockIdx.x) * 2 + s, W, npairs);
+            bool pf_more = pf.begin(&args, static_cast<int>(blockIdx.x) * 2 + s, W, npairs);
+            if (pf_more) pf_more = pf.next();
+            while (more) {
+                const Unit u = it.u;
+                const int head = u.head;
+                if (pf_more) {
+                    const Unit& n = pf.u;
 #pragma unroll
-                    for (int blk = 0; blk < NB; ++blk)
-                        tma_load_4d(sQ + blk * (kAtQ * 128), &maps.q, &b.q_full, head * HD + blk * 64, u.q_row, 0, 0);
-                    ++nu;
-                    for (int t = 0; t < u.nt; ++t, ++ck) {
-                        const uint32_t st = ck & 1u;
-                        mbar_wait(&b.kv_empty[st], ((ck >> 1) & 1u) ^ 1u);
-                        mbar_expect_tx(&b.kv_full[st], Cfg::kStageBytes);
-                        uint8_t* sK = sKV + st * Cfg::kStageBytes;
-                        uint8_t* sV = sK + Cfg::kKBytes;
+                    for (int blk = 0; blk < NB; ++blk) tma_prefetch_l2_4d(&maps.q, n.head * HD + blk * 64, n.q_row, 0, 0);
+                    if (n.q0 == 0) {      // the pair's first query tile brings its keys / values in (later tiles re-read them)
+                        const int nt = min(n.nt, 6);
+                        for (int t = 0; t < nt; ++t)
 #pragma unroll
-                        for (int blk = 0; blk < NB; ++blk) {
-                            tma_load_4d(sK + blk * (kAtKV * 128), &maps.k, &b.kv_full[st], head * HD + blk * 64,
-                                        u.k_row + t * kAtKV, 0, 0);
-                            tma_load_4d(sV + blk * (kAtKV * 128), &maps.v, &b.kv_full[st], head * HD + blk * 64,
-                                        u.k_row + t * kAtKV, 0, 0);
-                        }
+                            for (int blk = 0; blk < NB; ++blk) {
+                                tma_prefetch_l2_4d(&maps.k, n.head * HD + blk * 64, n.k_row + t * kAtKV, 0, 0);
+                                tma_prefetch_l2_4d(&maps.v, n.head * HD + blk * 64, n.k_row + t * kAtKV, 0, 0);
+                            }
+                    }
+                    pf_more = pf.next();
+                }
+                mbar_wait(&b.q_empty, (nu & 1u) ^ 1u);
+                mbar_expect_tx(&b.q_full, Cfg::kQBytes);
+#pragma unroll
+                for (int blk = 0; blk < NB; ++blk)
+                    tma_load_4d(sQ + blk * (kAtQ * 128), &maps.q, &b.q_full, head * HD + blk * 64, u.q_row, 0, 0);
+                ++nu;
+                for (int t = 0; t < u.nt; ++t, ++ck) {
+                    const uint32_t st = ck & 1u;
+                    mbar_wait(&b.kv_empty[st], ((ck >> 1) & 1u) ^ 1u);
+                    mbar_expect_tx(&b.kv_full[st], Cfg::kStageBytes);
+                    uint8_t* sK = sKV + st * Cfg::kStageBytes;
+                    uint8_t* sV = sK + Cfg::kKBytes;
+#pragma unroll
+                    for (int blk = 0; blk < NB; ++blk) {
+                        tma_load_4d(sK + blk * (kAtKV * 128), &maps.k, &b.kv_full[st], head * HD + blk * 64,
+                                    u.k_row + t * kAtKV, 0, 0);
+                        tma_load_4d(sV + blk * (kAtKV * 128), &maps.v, &b.kv_full[st], head * HD + blk * 64,
+                                    u.k_row + t * kAtKV, 0, 0);
                     }
                 }
+                more = it.next();
             }
         }
     } else {

@@ -101,6 +101,14 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
         : "memory");
 }
 
+// L2 prefetch of a tile (no shared memory, no barrier): the later load of the same box hits L2
+__device__ __forceinline__ void tma_prefetch_l2_4d(const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+                 : "memory");
+}
+
 // CTA-pair variant (.cta_group::2): the data lands in THIS CTA's shared memory, the transaction bytes are signalled
 // on `bar_cluster_addr`, a shared::cluster address that may belong to the peer CTA (the pair's leader).
 __device__ __forceinline__ void tma_load_4d_cg2(void* dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0,
