@@ -114,8 +114,8 @@ __global__ void __launch_bounds__(256) layernorm_kernel(float* __restrict__ x, i
                                                         float* __restrict__ out_f32, const float* __restrict__ addvec,
                                                         int period, const int* __restrict__ add_row0_dev,
                                                         int add_row0, int writeback) {
-    pdl_wait();
-    pdl_launch_dependents();
+    pdl_wait();   // (no early launch_dependents: this grid runs in many waves and a dependent persistent GEMM CTA that
+                  // becomes resident early takes its SM away from the remaining waves - measured: AR loop +17 ms)
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= M) return;
@@ -517,8 +517,8 @@ __global__ void __launch_bounds__(128) single_query_attn_kernel(int mode, const 
     constexpr int CPL = NCH / LPK;                // 16-byte chunks per lane
     constexpr int NSUB = 32 / LPK;                // key subsets
     __shared__ float sP[4][kMaxMem];
-    pdl_wait();
-    pdl_launch_dependents();
+    pdl_wait();   // (no early launch_dependents: this grid runs in many waves and a dependent persistent GEMM CTA that
+                  // becomes resident early takes its SM away from the remaining waves - measured: AR loop +17 ms)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wid = blockIdx.x * 4 + warp;
     if (wid >= B * heads) return;
@@ -703,8 +703,8 @@ __global__ void __launch_bounds__(256) ar_control_kernel(const float* __restrict
     __shared__ float s_stat[2];
     __shared__ float red[8];
     __shared__ int s_last;
-    pdl_wait();
-    pdl_launch_dependents();
+    pdl_wait();   // (no early launch_dependents: this grid runs in many waves and a dependent persistent GEMM CTA that
+                  // becomes resident early takes its SM away from the remaining waves - measured: AR loop +17 ms)
     const int row = blockIdx.x;
     const int i = *a.step;
     const int j = i + 1;
