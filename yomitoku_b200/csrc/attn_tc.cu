@@ -143,7 +143,7 @@ __device__ __forceinline__ float fast_exp2(float x) {
     return r;
 }
 
-template <int HD, int MASKED>
+template <int HD, int MASKED, int PT>
 __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_constant__ AttnMaps maps,
                                                                 const AttnArgs args) {
     using Cfg = AtCfg<HD>;
@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                 mbar_init(&b.kv_full[i], 1);
                 mbar_init(&b.kv_empty[i], 1);
                 mbar_init(&b.s_full[i], 1);
-                mbar_init(&b.s_free[i], 4);
+                mbar_init(&b.s_free[i], PT ? 1 : 4);   // PT: released by the MMA thread's commit after the P V product
             }
             mbar_init(&b.p_full, 4);
             mbar_init(&b.p_empty, 1);
@@ -217,9 +217,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                         tmem_ld_32x32(t_lane + buf * 64u + 32u, reinterpret_cast<uint32_t(&)[32]>(sv[32]));
                         tmem_ld_wait();
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&b.s_free[buf]);  // the S buffer may be overwritten (tile t + 2)
+                    if constexpr (!PT) {
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&b.s_free[buf]);  // the S buffer may be overwritten (tile t + 2)
+                    }
                     const int key0 = t * kAtKV;
                     float mt = -INFINITY;
                     if (warp_active) {
@@ -242,7 +244,31 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                         m_ref = mt;
                         l_run *= factor;
                     }
-                    // P buffer free <=> PV of the previous tile (of this slot) complete <=> O stable
+                    // exponentials first (registers only) ...
+                    const int nch = ((min(kAtKV, u.k_end - key0) + 15) >> 4) * 2;   // 8-key chunks the P V product reads
+                    uint32_t pk[32];
+                    if (warp_active) {
+                        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
+                        float ls = 0.f;
+#pragma unroll
+                        for (int ch = 0; ch < 8; ++ch) {
+                            if (ch < nch) {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const float p0 = fast_exp2(__uint_as_float(sv[ch * 8 + 2 * j]) - m_use);  // exp2(-inf) = 0
+                                    const float p1 = fast_exp2(__uint_as_float(sv[ch * 8 + 2 * j + 1]) - m_use);
+                                    ls += p0 + p1;
+                                    pk[ch * 4 + j] = pack_op(p0, p1);
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) pk[ch * 4 + j] = 0u;
+                            }
+                        }
+                        l_run += ls;
+                    }
+                    // ... then the only point that depends on the previous tile's P V product (by now it has almost always
+                    // completed): smem mode - the P buffer is free; both modes - O is stable and may be rescaled
                     mbar_wait(&b.p_empty, (c & 1u) ^ 1u);
                     if (t > 0 && __any_sync(0xffffffffu, moved)) {
                         tc_fence_after();
@@ -260,29 +286,20 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                         }
                     }
                     if (warp_active) {
-                        const float m_use = (m_ref == -INFINITY) ? 0.f : m_ref;
-                        float ls = 0.f;
-                        // only the 16-key steps the P V product reads (the rest of the tile holds no visible key)
-                        const int nch = ((min(kAtKV, u.k_end - key0) + 15) >> 4) * 2;
+                        if constexpr (PT) {
+                            // P overwrites the S buffer it came from: 64 fp16 = 32 columns of this thread's lane
+                            tmem_st_32x32(t_lane + buf * 64u, pk);
+                            tmem_st_wait();
+                        } else {
 #pragma unroll
-                        for (int ch = 0; ch < 8; ++ch) {
-                            if (ch >= nch) break;
-                            float pv[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                pv[j] = fast_exp2(__uint_as_float(sv[ch * 8 + j]) - m_use);  // exp2(-inf) = 0
-                                ls += pv[j];
+                            for (int ch = 0; ch < 8; ++ch) {
+                                if (ch < nch)
+                                    *reinterpret_cast<uint4*>(p_row + ((ch ^ (row & 7)) << 4)) =
+                                        make_uint4(pk[ch * 4], pk[ch * 4 + 1], pk[ch * 4 + 2], pk[ch * 4 + 3]);
                             }
-                            uint4 o;
-                            o.x = pack_op(pv[0], pv[1]);
-                            o.y = pack_op(pv[2], pv[3]);
-                            o.z = pack_op(pv[4], pv[5]);
-                            o.w = pack_op(pv[6], pv[7]);
-                            *reinterpret_cast<uint4*>(p_row + ((ch ^ (row & 7)) << 4)) = o;
                         }
-                        l_run += ls;
                     }
-                    fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the MMA's operand reads
+                    if constexpr (!PT) fence_proxy_async_smem();  // P (generic-proxy stores) -> visible to the MMA's operand reads
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&b.p_full);
@@ -468,10 +485,17 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                             const int ksteps = (nkeys + 15) >> 4;
                             const uint32_t v_addr = kv_addr + stg * Cfg::kStageBytes + Cfg::kKBytes;
                             for (int j = 0; j < ksteps; ++j) {
-                                const uint64_t da = umma_desc_sw128(p_addr) + static_cast<uint64_t>(2 * j);
                                 const uint64_t db = umma_desc_sw128_mn(v_addr + j * 2048, kAtKV * 128, args.vswap);
-                                umma_op(t_slot + 128u, da, db, idesc_pv, (S.tp | j) != 0 ? 1u : 0u);
+                                if constexpr (PT) {
+                                    // A = P from tensor memory: 16 keys = 8 columns of the tile's S buffer
+                                    umma_op_ts(t_slot + 128u, t_slot + stg * 64u + j * 8u, db, idesc_pv,
+                                               (S.tp | j) != 0 ? 1u : 0u);
+                                } else {
+                                    const uint64_t da = umma_desc_sw128(p_addr) + static_cast<uint64_t>(2 * j);
+                                    umma_op(t_slot + 128u, da, db, idesc_pv, (S.tp | j) != 0 ? 1u : 0u);
+                                }
                             }
+                            if constexpr (PT) umma_commit(&b.s_free[stg]);   // P read: the S buffer may take tile t + 2
                             umma_commit(&b.kv_empty[stg]);
                             umma_commit(&b.p_empty);
                             if (S.tp == S.u.nt - 1) umma_commit(&b.o_full);
@@ -496,11 +520,11 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
     }
 }
 
-template <int HD, int MASKED>
+template <int HD, int MASKED, int PT>
 int launch_attn(const AttnMaps& maps, const AttnArgs& a, int grid, cudaStream_t st) {
     using Cfg = AtCfg<HD>;
     static bool attr = false;
-    auto kern = attn_tc_kernel<HD, MASKED>;
+    auto kern = attn_tc_kernel<HD, MASKED, PT>;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) {
@@ -554,15 +578,18 @@ int launch_attention_tc(const void* Q, long long ldq, long long q_rows, const vo
     a.scale_log2 = 1.4426950408889634f / sqrtf(static_cast<float>(head_dim));
     a.O = reinterpret_cast<op_t*>(O);
     a.ldo = ldo;
-    a.vswap = vswap;
+    a.vswap = vswap & 1;
+    const bool p_tmem = (vswap & 2) != 0;
     const int pairs = nseq * heads;
     int grid = (pairs + 1) / 2;
     if (grid > num_sms()) grid = num_sms();
     int rc = 0;
-#define YTK_AT(HD_)                                                   \
-    do {                                                              \
-        if (masked) rc = launch_attn<HD_, 1>(maps, a, grid, st);      \
-        else rc = launch_attn<HD_, 0>(maps, a, grid, st);             \
+#define YTK_AT(HD_)                                                             \
+    do {                                                                        \
+        if (masked && p_tmem) rc = launch_attn<HD_, 1, 1>(maps, a, grid, st);   \
+        else if (masked) rc = launch_attn<HD_, 1, 0>(maps, a, grid, st);        \
+        else if (p_tmem) rc = launch_attn<HD_, 0, 1>(maps, a, grid, st);        \
+        else rc = launch_attn<HD_, 0, 0>(maps, a, grid, st);                    \
     } while (0)
     switch (head_dim) {
         case 32: YTK_AT(32); break;

@@ -34,8 +34,13 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 
 int pdl_launch_attr(cudaLaunchAttribute* attr) {
-    static const bool off = getenv("YTK_NO_PDL") != nullptr;
-    if (off) return 0;
+    // Opt-in (YTK_PDL=1).  Measured on B200 (profiles/README_r02.md): with programmatic stream serialization the AR
+    // loop of 3200 rows took 77-80 ms instead of 62-63 ms and the encoder 95.5 instead of 92 ms - a dependent persistent
+    // GEMM CTA that becomes resident early takes its SM away from the remaining waves of the multi-wave kernel before
+    // it, which costs more than the overlapped prologue saves.  The kernels keep their griddepcontrol.wait (a no-op for a
+    // normal launch) so that the experiment stays one environment variable away.
+    static const bool on = getenv("YTK_PDL") != nullptr && getenv("YTK_NO_PDL") == nullptr;
+    if (!on) return 0;
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     return 1;
@@ -111,12 +116,12 @@ __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
     // |x| is clamped at 1e4 (erf is 1 and exp(-z^2) is 0 in fp32 long before): keeps the shared reciprocal below finite
     const f32x2 z = mul2(pk2(fminf(fabsf(x0), 1e4f), fminf(fabsf(x1), 1e4f)),
                          pk2(0.70710678118654752440f, 0.70710678118654752440f));
-    float d0, d1, r;
+    float d0, d1, rq;
     upk2(fma2(pk2(0.3275911f, 0.3275911f), z, pk2(1.f, 1.f)), d0, d1);   // in [1, 2400]
     // one reciprocal for both: 1/d0 = d1 / (d0 d1), 1/d1 = d0 / (d0 d1) - the epilogue is bound by the MUFU pipe
     // (one ex2 + one rcp per element), this takes it to 1.5 per element for three FMULs
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d0 * d1));
-    const f32x2 t = mul2(pk2(d1, d0), pk2(r, r));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(d0 * d1));
+    const f32x2 t = mul2(pk2(d1, d0), pk2(rq, rq));
     f32x2 p = fma2(pk2(0.5307027145f, 0.5307027145f), t, pk2(-0.7265760135f, -0.7265760135f));
     p = fma2(p, t, pk2(0.7107068705f, 0.7107068705f));
     p = fma2(p, t, pk2(-0.142248368f, -0.142248368f));

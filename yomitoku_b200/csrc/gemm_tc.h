@@ -114,8 +114,8 @@ int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream);
 int make_tmap_op_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], const uint64_t strides_b[3],
                       const uint32_t box[4]);
 
-// Launch attribute set for kernels that call pdl_wait() (ptx.cuh): programmatic stream serialization unless YTK_NO_PDL
-// is set.  Returns the number of attributes written to attr[0..].
+// Launch attribute set for kernels that call pdl_wait() (ptx.cuh): programmatic stream serialization when YTK_PDL=1
+// (off by default: measured slower, see gemm_tc.cu).  Returns the number of attributes written to attr[0..].
 int pdl_launch_attr(cudaLaunchAttribute* attr);
 void set_error(const char* fmt, ...);
 const char* last_error();

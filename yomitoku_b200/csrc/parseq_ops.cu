@@ -455,17 +455,19 @@ int launch_flash_attention(const void* Q, long long ldq, long long q_rows, const
     if (nseq <= 0) return 0;
     if (impl == 0) {
         // YTK_ATTN=legacy: the round-1 mma.sync kernel; YTK_ATTN=vswap: tcgen05 kernel with the other V descriptor
+        // YTK_ATTN=legacy: the round-1 mma.sync kernel; smem: tcgen05 kernel with P staged in shared memory;
+        // default: tcgen05 kernel with P in tensor memory
         static const int env_impl = [] {
             const char* e = getenv("YTK_ATTN");
             if (e && e[0] == 'l') return 1;
-            if (e && e[0] == 'v') return 3;
-            return 2;
+            if (e && e[0] == 's') return 2;
+            return 4;
         }();
         impl = env_impl;
     }
-    if (impl >= 2)
+    if (impl >= 2)   // 2: P in smem, 3: P in smem + swapped V descriptor (debug), 4: P in TMEM
         return launch_attention_tc(Q, ldq, q_rows, K, V, ldkv, kv_rows, O, ldo, seqs, nseq, heads, head_dim, masked,
-                                   impl == 3 ? 1 : 0, st);
+                                   impl == 3 ? 1 : (impl == 4 ? 2 : 0), st);
     // 128-query tiles (8 warps) halve the K/V re-reads of the typical 92..200-token crop; short sequences keep 64
     const int qt = max_q_len > 64 ? 128 : 64;
     dim3 grid((max_q_len + qt - 1) / qt, heads, nseq);

@@ -388,7 +388,7 @@ class BatchedOCR:
             start = end
         return out
 
-    def _run_groups_dev(self, groups, geoms, pages_dev, stream=None, levels=None):
+    def _run_groups_dev(self, groups, geoms, pages_dev, stream=None, levels=None, plan=None):
         """Groups whose crops exist only as records: groups = (widths, padded widths, record indices into `geoms`).
         Groups recognised on this rank are cut on the device and never leave HBM (`_run_groups_dev_local`).  With
         torch.distributed, the groups the balancer moves to another rank are cut into one device buffer ordered by
@@ -397,7 +397,7 @@ class BatchedOCR:
         import torch
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
-            return self._run_groups_dev_local(groups, geoms, pages_dev, stream, levels)
+            return self._run_groups_dev_local(groups, geoms, pages_dev, stream, levels, plan)
         from . import parallel as par
         from .models import extract_crops_pyramid
         pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
@@ -505,22 +505,18 @@ class BatchedOCR:
             start = end
         return out
 
-    def _run_groups_dev_local(self, groups, geoms, pages_dev, stream=None, levels=None):
-        """This rank's share of `_run_groups_dev`: the canvases of a <= max_tokens chunk are cut on the device
-        (ytk_extract_crops_u8, one call per source_downscale pyramid level) in group order and go to PARSeq without
-        leaving HBM."""
+    def _plan_groups_dev(self, groups, geoms, levels=None):
+        """Host-side planning of `_run_groups_dev_local` (no device call): <= max_tokens chunks ending on group
+        boundaries, with the records, padded widths and recognizer descriptors of every chunk.  `BatchedOCR.stream` runs
+        this for batch i + 1 in its own thread while batch i is on the GPU."""
         from . import _lib
-        from .models import extract_crops_pyramid
-        pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
         lv = levels if levels is not None else np.zeros(len(geoms), np.int64)
-        rec = self.recognizer
-        cfg = rec._cfg
+        cfg = self.recognizer._cfg
         ph, pw = cfg.encoder.patch_size
         gh = cfg.data.img_size[0] // ph
-        out = [None] * len(groups)
         gtok = [gh * (int(np.sum(g[1])) // pw) for g in groups]
         dt = np.dtype(_lib.YtkCrop)
-        start = 0
+        chunks, start = [], 0
         while start < len(groups):
             end, tok = start, 0
             while end < len(groups) and not (end > start and tok + gtok[end] > self.max_tokens):
@@ -528,29 +524,43 @@ class BatchedOCR:
                 end += 1
             chunk = groups[start:end]
             idx = np.concatenate([g[2] for g in chunk])
-            sel = geoms[idx].copy()
-            with _span("recognize.crops_device"):
-                canv, total, offs = extract_crops_pyramid(pages, sel, lv[idx], stream)
             wp = np.concatenate([np.asarray(g[1], np.int64) for g in chunk])
+            sel = geoms[idx].copy()
             n = sel.shape[0]
             ntok = gh * (wp // pw)
             descs = np.zeros(n, dtype=dt)
-            descs["pix_off"] = offs
             descs["w"] = sel["canvas_w"]
             descs["wp"] = wp
             descs["tok_off"] = np.cumsum(ntok) - ntok
             descs["ntok"] = ntok
             descs["group"] = np.repeat(np.arange(end - start), [len(g[0]) for g in chunk])
+            chunks.append({"start": start, "end": end, "sel": sel, "lv": lv[idx], "descs": descs, "n": n,
+                           "sizes": [len(g[0]) for g in chunk]})
+            start = end
+        return chunks
+
+    def _run_groups_dev_local(self, groups, geoms, pages_dev, stream=None, levels=None, plan=None):
+        """This rank's share of `_run_groups_dev`: the canvases of a <= max_tokens chunk are cut on the device
+        (ytk_extract_crops_u8, one call per source_downscale pyramid level) in group order and go to PARSeq without
+        leaving HBM.  `plan` = `_plan_groups_dev(groups, geoms, levels)` when it was prepared ahead of time."""
+        from .models import extract_crops_pyramid
+        pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
+        rec = self.recognizer
+        if plan is None:
+            plan = self._plan_groups_dev(groups, geoms, levels)
+        out = [None] * len(groups)
+        for ch in plan:
+            with _span("recognize.crops_device"):
+                canv, total, offs = extract_crops_pyramid(pages, ch["sel"], ch["lv"], stream)
+            ch["descs"]["pix_off"] = offs
             with _span("recognize.device"):
-                ids, probs, glen = rec.model.run_packed_ptr(canv.data_ptr(), 1, total, descs, n, end - start,
-                                                            stream=stream)
+                ids, probs, glen = rec.model.run_packed_ptr(canv.data_ptr(), 1, total, ch["descs"], ch["n"],
+                                                            ch["end"] - ch["start"], stream=stream)
             del canv
             off = 0
-            for k in range(start, end):
-                m = len(groups[k][0])
-                out[k] = (ids[off:off + m], probs[off:off + m], int(glen[k - start]))
+            for k, m in zip(range(ch["start"], ch["end"]), ch["sizes"]):
+                out[k] = (ids[off:off + m], probs[off:off + m], int(glen[k - ch["start"]]))
                 off += m
-            start = end
         return out
 
     def _run_groups(self, groups, stream=None, arena=None, height=32):
@@ -614,10 +624,10 @@ class BatchedOCR:
         back = par.return_results(work, packed, len(groups), S + 1)
         return [(i[:, :S], p[:, :S], int(i[0, S]) if len(i) else 0) for i, p in back]
 
-    def recognize_pooled(self, per_page, stream=None, arena=None, pages_dev=None):
-        """Device stage 2: per_page = list of (canvases, content_widths, n_quads); canvases is a list of arrays or a
-        `_PageCrops` view of `arena`.  Returns per page (ids, probs, order) with rows in the page's *plan* order,
-        exactly like TextRecognizer._run_plan."""
+    def prepare_pooled(self, per_page, arena=None, pages_dev=None):
+        """Host-only half of `recognize_pooled`: the reference grouping of every page (bucketing order, mini-batch plan,
+        padded widths) flattened into the group list of the batch, plus - for device-cut crops on a single rank - the
+        chunk plan of the packed recognizer call.  No device call, so it can run ahead of the GPU."""
         rec = self.recognizer
         cfg = rec._cfg
         in_arena = arena is not None and all(isinstance(p[0], _PageCrops) for p in per_page)
@@ -641,16 +651,29 @@ class BatchedOCR:
                     groups.append(([canv[i] for i in b], [padded[i] for i in b]))
                 owner.append(pi)
             orders.append(order)
+        prep = {"groups": groups, "owner": owner, "orders": orders, "in_dev": in_dev, "in_arena": in_arena,
+                "n_pages": len(per_page), "height": per_page[0][0].height if in_arena and per_page else 32}
         if in_dev:
-            geoms = np.concatenate([p[0].geoms for p in per_page]) if per_page else np.zeros(0, CROP_GEOM_DTYPE)
-            levels = np.concatenate([p[0].levels for p in per_page]) if per_page else np.zeros(0, np.int64)
-            res = self._run_groups_dev(groups, geoms, pages_dev, stream, levels)
+            prep["geoms"] = np.concatenate([p[0].geoms for p in per_page]) if per_page else np.zeros(0, CROP_GEOM_DTYPE)
+            prep["levels"] = np.concatenate([p[0].levels for p in per_page]) if per_page else np.zeros(0, np.int64)
+            import torch.distributed as dist
+            if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
+                prep["plan"] = self._plan_groups_dev(groups, prep["geoms"], prep["levels"])
+        return prep
+
+    def run_prepared(self, prep, stream=None, arena=None, pages_dev=None):
+        """Device half of `recognize_pooled`: returns per page (ids, probs, order) with rows in the page's *plan* order,
+        exactly like TextRecognizer._run_plan."""
+        rec = self.recognizer
+        cfg = rec._cfg
+        groups, owner, orders = prep["groups"], prep["owner"], prep["orders"]
+        if prep["in_dev"]:
+            res = self._run_groups_dev(groups, prep["geoms"], pages_dev, stream, prep["levels"], prep.get("plan"))
         else:
-            res = self._run_groups(groups, stream, arena if in_arena else None,
-                                   per_page[0][0].height if in_arena and per_page else 32)
+            res = self._run_groups(groups, stream, arena if prep["in_arena"] else None, prep["height"])
         S = cfg.max_label_length + 1
         out = []
-        for pi in range(len(per_page)):
+        for pi in range(prep["n_pages"]):
             mine = [r for r, o in zip(res, owner) if o == pi]
             if not mine:
                 out.append((np.zeros((0, S), np.int32), np.zeros((0, S), np.float32), orders[pi]))
@@ -666,6 +689,11 @@ class BatchedOCR:
                     k += n
             out.append((ids, probs, orders[pi]))
         return out
+
+    def recognize_pooled(self, per_page, stream=None, arena=None, pages_dev=None):
+        """Device stage 2: per_page = list of (canvases, content_widths, n_quads); canvases is a list of arrays, a
+        `_PageCrops` view of `arena` or a `_PageGeoms` (records only, cut on the device)."""
+        return self.run_prepared(self.prepare_pooled(per_page, arena, pages_dev), stream, arena, pages_dev)
 
     # ------------------------------------------------------------------------------------------ whole path
     def submit(self, pages, prob_override=None, quads_override=None, stream=None, wait_recognized=False):
@@ -758,11 +786,13 @@ class BatchedOCR:
 
     def _recognize_handle(self, handle, stream=None):
         try:
-            return self._recognize_handle_impl(handle, stream)
+            return self._run_handle(handle, self._prepare_handle(handle), stream)
         finally:
             handle.done.set()       # the staging slot of this batch may be reused
 
-    def _recognize_handle_impl(self, handle, stream=None):
+    def _prepare_handle(self, handle):
+        """Waits for the host stage of a batch and plans its recognizer call (host only; `stream()` runs this one batch
+        ahead of the GPU in its own thread)."""
         with _span("collect.wait_host"):
             host = [f.result() for f in handle.futures]
         arena = handle.arena
@@ -795,8 +825,14 @@ class BatchedOCR:
                 fixed.append(h)
             host = fixed
         rec_in = [(h[2], h[3], len(h[0])) for h in host]
+        with _span("collect.prepare"):
+            prep = self.prepare_pooled(rec_in, arena=arena, pages_dev=handle.pages_dev)
+        return host, prep, arena
+
+    def _run_handle(self, handle, prepared, stream=None):
+        host, prep, arena = prepared
         with _span("collect.recognize"):
-            rec_out = self.recognize_pooled(rec_in, stream, arena=arena, pages_dev=handle.pages_dev)
+            rec_out = self.run_prepared(prep, stream, arena=arena, pages_dev=handle.pages_dev)
             if handle.pages_dev is not None and getattr(self.recognizer, "rec_orientation_fallback", False):
                 self._orientation_fallback_dev([h[2] for h in host], rec_out, handle.pages_dev, stream)
         return host, rec_out
@@ -900,10 +936,12 @@ class BatchedOCR:
 
 
 def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
-    """Generator behind BatchedOCR.stream, three stages in order: a detector thread (own CUDA stream) runs up to
-    `lookahead` batches ahead and feeds the host pool; a recognizer thread waits for each batch's host stage and runs
-    the packed PARSeq call on its own stream; the calling thread turns ids into strings / schemas and yields.  ctypes
-    releases the GIL inside the C calls, so DBNet(i+2), host stage(i+1), PARSeq(i) and assembly(i-1) overlap."""
+    """Generator behind BatchedOCR.stream, four stages in order: a detector thread (own CUDA stream) runs up to
+    `lookahead` batches ahead and feeds the host pool; a planner thread waits for each batch's host stage and builds the
+    recognizer call (grouping, records, descriptors: host only); a recognizer thread does nothing but the device calls
+    on its own stream, so the GPU goes from one batch's PARSeq straight into the next one's; the calling thread turns ids
+    into strings / schemas and yields.  ctypes releases the GIL inside the C calls, so DBNet(i+2), host stage and
+    planning(i+1), PARSeq(i) and assembly(i-1) overlap."""
     import queue
     import threading
     import torch
@@ -929,28 +967,56 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
         finally:
             q.put(None)
 
+    q1 = queue.Queue(maxsize=2)
     q2 = queue.Queue(maxsize=2)
+
+    def planner():
+        """host stage results -> recognizer plan, one batch ahead of the GPU (pure host work)"""
+        try:
+            while True:
+                h = q.get()
+                if h is None:
+                    break
+                try:
+                    q1.put((h, ocr._prepare_handle(h)))
+                except BaseException:
+                    h.done.set()
+                    raise
+        except BaseException as e:
+            err.append(e)
+            while True:
+                h = q.get()
+                if h is None:
+                    break
+                h.done.set()
+        finally:
+            q1.put(None)
 
     def recognizer():
         try:
             if dev is not None:
                 torch.cuda.set_device(dev)
             while True:
-                h = q.get()
-                if h is None:
+                item = q1.get()
+                if item is None:
                     break
-                q2.put(ocr._recognize_handle(h, stream=rec_stream))
+                h, prepared = item
+                try:
+                    q2.put(ocr._run_handle(h, prepared, stream=rec_stream))
+                finally:
+                    h.done.set()       # the staging slot of this batch may be reused
         except BaseException as e:
             err.append(e)
             while True:                     # keep draining (and releasing staging slots) so that the producer can finish
-                h = q.get()
-                if h is None:
+                item = q1.get()
+                if item is None:
                     break
-                h.done.set()
+                item[0].done.set()
         finally:
             q2.put(None)
 
-    threads = [threading.Thread(target=producer, daemon=True), threading.Thread(target=recognizer, daemon=True)]
+    threads = [threading.Thread(target=producer, daemon=True), threading.Thread(target=planner, daemon=True),
+               threading.Thread(target=recognizer, daemon=True)]
     for t in threads:
         t.start()
     while True:
