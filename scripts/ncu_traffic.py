@@ -19,7 +19,7 @@ def main(path, per_step, out=None):
     for x in csv.DictReader(lines):
         i = int(x["ID"])
         if i not in by_id:
-            by_id[i] = {"name": re.sub(r"\(.*", "", x["Kernel Name"]).split("<")[0].split("::")[-1]}
+            by_id[i] = {"name": re.sub(r"\(.*", "", x["Kernel Name"]).split("<")[0].split("::")[-1].replace("void ", "")}
             order.append(i)
         m = x["Metric Name"]
         if m == "gpu__time_duration.sum":

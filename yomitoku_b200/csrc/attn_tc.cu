@@ -4,9 +4,9 @@
 // (reference models/parseq.py:264-299: cross-attention over the encoder memory, and the masked self-attention over the
 // content stream whose mask has rows 0 and 1 cleared).
 //
-// One persistent CTA per SM runs TWO independent pipelines ("slots"); a slot works through its own list of units
-// (sequence, head, 128-query tile) and owns a Q tile, a P tile, a 2-stage K/V ring in shared memory and 256 TMEM
-// columns (two 128x64 fp32 S buffers + one 128xhd fp32 O accumulator):
+// One persistent CTA per SM runs TWO independent pipelines ("slots"); the units (sequence, head, 128-query tile) of the
+// CTA's (sequence, head) pairs are dealt to the slots alternately; a slot owns a Q tile, a P tile, a 2-stage K/V ring in
+// shared memory and 256 TMEM columns (two 128x64 fp32 S buffers + one 128xhd fp32 O accumulator):
 //   warp 8+s  lane 0 : TMA producer of slot s  - Q tile once per unit, K/V tiles of 64 keys (SWIZZLE_128B boxes)
 //   warp 10   lane 0 : MMA issuer for BOTH slots (polls their barriers): S = Q K^T (tcgen05.mma, K-major operands),
 //                      O += P V (P from shared memory K-major, V as MN-major B operand - the tile is stored exactly as
@@ -96,12 +96,14 @@ __device__ __forceinline__ Unit make_unit(const SeqDesc& sd, int head, int qt, l
     return u;
 }
 
-// The units of one (CTA, slot) worker in processing order: pairs p = start, start + W, ... ; inside a pair the query
-// tiles in ascending order (so that the K / V tiles of the pair stay hot in L2).  Every role of a slot walks the same
-// sequence.
+// The units of one (CTA, slot) worker in processing order.  A CTA owns the pairs p = blockIdx, blockIdx + gridDim, ...;
+// their units (query tiles in ascending order) are dealt to the two slots alternately, so the two query tiles of a
+// sequence a little longer than 128 tokens run side by side (both slots read the pair's K / V tiles, the second time
+// out of L2) instead of one after the other - the short tail tile is pure pipeline latency.  Every role of a slot walks
+// the same sequence.
 template <int MASKED>
 struct UnitIter {
-    int p, qt, nqt, head, W, npairs;
+    int p, qt, nqt, head, W, npairs, slot, count;
     SeqDesc sd;
     Unit u;
     const AttnArgs* a;
@@ -111,12 +113,14 @@ struct UnitIter {
         sd = a->seqs[seq];
         nqt = (sd.q_len + kAtQ - 1) / kAtQ;
     }
-    // positions on the first unit with at least one key tile; false when the worker has none
-    __device__ __forceinline__ bool begin(const AttnArgs* args, int start, int stride, int npairs_) {
+    // positions on the slot's first unit; false when it has none
+    __device__ __forceinline__ bool begin(const AttnArgs* args, int cta, int ncta, int npairs_, int slot_) {
         a = args;
-        W = stride;
+        W = ncta;
         npairs = npairs_;
-        p = start;
+        slot = slot_;
+        count = 0;
+        p = cta;
         qt = -1;
         if (p >= npairs) return false;
         load_pair();
@@ -132,7 +136,8 @@ struct UnitIter {
                 load_pair();
             }
             u = make_unit<MASKED>(sd, head, qt, a->ldkv);
-            if (u.nt > 0) return true;
+            if (u.nt <= 0) continue;
+            if ((count++ & 1) == slot) return true;
         }
     }
 };
@@ -186,7 +191,6 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
 
     const int npairs = args.nseq * args.heads;
-    const int W = 2 * static_cast<int>(gridDim.x);  // workers = (CTA, slot)
 
     if (warp < 8) {
         // ------------------------------------------------------------------ softmax + epilogue, slot = warp / 4
@@ -197,13 +201,12 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
         uint8_t* p_row = sP + (row >> 3) * 1024 + (row & 7) * 128;
         const uint32_t t_lane = tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(s * 256);
         uint32_t nu = 0, c = 0;
-        for (int p = static_cast<int>(blockIdx.x) * 2 + s; p < npairs; p += W) {
-            const int seq = p / args.heads, head = p - seq * args.heads;
-            const SeqDesc sd = args.seqs[seq];
-            const int nqt = (sd.q_len + kAtQ - 1) / kAtQ;
-            for (int qt = 0; qt < nqt; ++qt) {
-                const Unit u = make_unit<MASKED>(sd, head, qt, args.ldkv);
-                if (u.nt <= 0) continue;
+        UnitIter<MASKED> it;
+        for (bool more = it.begin(&args, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), npairs, s); more;
+             more = it.next()) {
+            {
+                const Unit u = it.u;
+                const int head = u.head;
                 const bool warp_active = q * 32 < u.rows;  // warp-uniform
                 const int qi = u.q0 + row;                 // this thread's query index inside the sequence
                 float m_ref = -INFINITY, l_run = 0.f;
@@ -345,8 +348,8 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
             uint8_t* sKV = sQ + Cfg::kQBytes + Cfg::kPBytes;
             uint32_t nu = 0, ck = 0;
             UnitIter<MASKED> it, pf;     // pf runs one unit ahead: its tiles are pulled into L2 while `it` is being fed
-            bool more = it.begin(&args, static_cast<int>(blockIdx.x) * 2 + s, W, npairs);
-            bool pf_more = pf.begin(&args, static_cast<int>(blockIdx.x) * 2 + s, W, npairs);
+            bool more = it.begin(&args, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), npairs, s);
+            bool pf_more = pf.begin(&args, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x), npairs, s);
             if (pf_more) pf_more = pf.next();
             while (more) {
                 const Unit u = it.u;
@@ -355,7 +358,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                     const Unit& n = pf.u;
 #pragma unroll
                     for (int blk = 0; blk < NB; ++blk) tma_prefetch_l2_4d(&maps.q, n.head * HD + blk * 64, n.q_row, 0, 0);
-                    if (n.q0 == 0) {      // the pair's first query tile brings its keys / values in (later tiles re-read them)
+                    {
                         const int nt = min(n.nt, 6);
                         for (int t = 0; t < nt; ++t)
 #pragma unroll
@@ -393,46 +396,21 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
         // ------------------------------------------------------------------ MMA issuer (one thread, both slots)
         if (lane == 0) {
             struct St {
-                int p, qt, nqt, head;
-                SeqDesc sd;
+                UnitIter<MASKED> it;
                 Unit u;
                 int ts, tp;
                 uint32_t nu, cs, cpv;
                 bool done;
             } st[2];
             auto next_unit = [&](St& S, bool first, int s) {
-                // advance to the next unit with at least one key tile
-                for (;;) {
-                    if (first) {
-                        S.p = static_cast<int>(blockIdx.x) * 2 + s;
-                        S.qt = 0;
-                        first = false;
-                        if (S.p >= npairs) {
-                            S.done = true;
-                            return;
-                        }
-                        const int seq = S.p / args.heads;
-                        S.head = S.p - seq * args.heads;
-                        S.sd = args.seqs[seq];
-                        S.nqt = (S.sd.q_len + kAtQ - 1) / kAtQ;
-                    } else {
-                        ++S.qt;
-                    }
-                    while (S.qt >= S.nqt) {
-                        S.p += W;
-                        S.qt = 0;
-                        if (S.p >= npairs) {
-                            S.done = true;
-                            return;
-                        }
-                        const int seq = S.p / args.heads;
-                        S.head = S.p - seq * args.heads;
-                        S.sd = args.seqs[seq];
-                        S.nqt = (S.sd.q_len + kAtQ - 1) / kAtQ;
-                    }
-                    S.u = make_unit<MASKED>(S.sd, S.head, S.qt, args.ldkv);
-                    if (S.u.nt > 0) break;
+                const bool more = first ? S.it.begin(&args, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x),
+                                                     npairs, s)
+                                        : S.it.next();
+                if (!more) {
+                    S.done = true;
+                    return;
                 }
+                S.u = S.it.u;
                 S.ts = 0;
                 S.tp = 0;
             };
@@ -581,8 +559,7 @@ int launch_attention_tc(const void* Q, long long ldq, long long q_rows, const vo
     a.vswap = vswap & 1;
     const bool p_tmem = (vswap & 2) != 0;
     const int pairs = nseq * heads;
-    int grid = (pairs + 1) / 2;
-    if (grid > num_sms()) grid = num_sms();
+    int grid = pairs < num_sms() ? pairs : num_sms();   // a CTA owns pairs, its two slots share their query tiles
     int rc = 0;
 #define YTK_AT(HD_)                                                             \
     do {                                                                        \

@@ -455,13 +455,14 @@ int launch_flash_attention(const void* Q, long long ldq, long long q_rows, const
     if (nseq <= 0) return 0;
     if (impl == 0) {
         // YTK_ATTN=legacy: the round-1 mma.sync kernel; YTK_ATTN=vswap: tcgen05 kernel with the other V descriptor
-        // YTK_ATTN=legacy: the round-1 mma.sync kernel; smem: tcgen05 kernel with P staged in shared memory;
-        // default: tcgen05 kernel with P in tensor memory
+        // YTK_ATTN=legacy: the round-1 mma.sync kernel; ptmem: tcgen05 kernel with the P tile in tensor memory (A operand
+        // from TMEM - correct, but measured 17 % slower than staging P in shared memory: the S buffer is then held until
+        // the P V product has read it); default: tcgen05 kernel, P in shared memory
         static const int env_impl = [] {
             const char* e = getenv("YTK_ATTN");
             if (e && e[0] == 'l') return 1;
-            if (e && e[0] == 's') return 2;
-            return 4;
+            if (e && e[0] == 'p') return 4;
+            return 2;
         }();
         impl = env_impl;
     }

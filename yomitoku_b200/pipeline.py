@@ -916,8 +916,7 @@ class BatchedOCR:
                     p, s, d = [p[i] for i in inv], [s[i] for i in inv], [d[i] for i in inv]
             # same pairing as ocr_aggregate (reference ocr.py:6-24); the values are produced by this module with
             # the right types, so the pydantic models are built without re-validating every coordinate
-            words = [WordPrediction.model_construct(points=q, content=c, direction=dd, det_score=float(ds),
-                                                    rec_score=float(rs))
+            words = [_fast_word(WordPrediction, q, c, dd, float(ds), float(rs))
                      for q, ds, c, rs, dd in zip(quads, scores, p, s, d)]
             results.append(OCRSchema.model_construct(words=words))
         _t.__exit__()
@@ -1017,15 +1016,23 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
 
     threads = [threading.Thread(target=producer, daemon=True), threading.Thread(target=planner, daemon=True),
                threading.Thread(target=recognizer, daemon=True)]
-    for t in threads:
-        t.start()
-    while True:
-        item = q2.get()
-        if item is None:
-            break
-        yield ocr._assemble(*item)
-    for t in threads:
-        t.join()
+    import sys
+    # the device threads hold the GIL for microseconds between C calls; with the default 5 ms switch interval each of
+    # those hand-overs can stall behind the assembly thread (tens of ms of pure Python per batch) and idle the GPU
+    old_interval = sys.getswitchinterval()
+    sys.setswitchinterval(min(old_interval, 0.0005))
+    try:
+        for t in threads:
+            t.start()
+        while True:
+            item = q2.get()
+            if item is None:
+                break
+            yield ocr._assemble(*item)
+        for t in threads:
+            t.join()
+    finally:
+        sys.setswitchinterval(old_interval)
     if err:
         raise err[0]
 
@@ -1053,6 +1060,21 @@ class _HostCanvases:
             self.torch.copy_(canv_dev)
             torch.cuda.current_stream().synchronize()
         self.np = self.torch.numpy()
+
+
+_WORD_FIELDS = frozenset(("points", "content", "direction", "rec_score", "det_score"))
+
+
+def _fast_word(cls, points, content, direction, det_score, rec_score):
+    """WordPrediction.model_construct(...) without its per-call bookkeeping (no defaults, no aliases to resolve): the
+    assembly thread builds thousands of these per batch while holding the GIL the device threads also need."""
+    m = cls.__new__(cls)
+    object.__setattr__(m, "__dict__", {"points": points, "content": content, "direction": direction,
+                                       "rec_score": rec_score, "det_score": det_score})
+    object.__setattr__(m, "__pydantic_fields_set__", set(_WORD_FIELDS))
+    object.__setattr__(m, "__pydantic_extra__", None)
+    object.__setattr__(m, "__pydantic_private__", None)
+    return m
 
 
 class _NullCtx:
