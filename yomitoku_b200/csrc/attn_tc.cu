@@ -4,9 +4,9 @@
 // (reference models/parseq.py:264-299: cross-attention over the encoder memory, and the masked self-attention over the
 // content stream whose mask has rows 0 and 1 cleared).
 //
-// One persistent CTA per SM runs TWO independent pipelines ("slots"); the units (sequence, head, 128-query tile) of the
-// CTA's (sequence, head) pairs are dealt to the slots alternately; a slot owns a Q tile, a P tile, a 2-stage K/V ring in
-// shared memory and 256 TMEM columns (two 128x64 fp32 S buffers + one 128xhd fp32 O accumulator):
+// One persistent CTA per SM runs TWO independent pipelines ("slots"); a slot works through its own list of units
+// (sequence, head, 128-query tile) and owns a Q tile, a P tile, a 2-stage K/V ring in shared memory and 256 TMEM
+// columns (two 128x64 fp32 S buffers + one 128xhd fp32 O accumulator):
 //   warp 8+s  lane 0 : TMA producer of slot s  - Q tile once per unit, K/V tiles of 64 keys (SWIZZLE_128B boxes)
 //   warp 10   lane 0 : MMA issuer for BOTH slots (polls their barriers): S = Q K^T (tcgen05.mma, K-major operands),
 //                      O += P V (P from shared memory K-major, V as MN-major B operand - the tile is stored exactly as
@@ -96,11 +96,11 @@ __device__ __forceinline__ Unit make_unit(const SeqDesc& sd, int head, int qt, l
     return u;
 }
 
-// The units of one (CTA, slot) worker in processing order.  A CTA owns the pairs p = blockIdx, blockIdx + gridDim, ...;
-// their units (query tiles in ascending order) are dealt to the two slots alternately, so the two query tiles of a
-// sequence a little longer than 128 tokens run side by side (both slots read the pair's K / V tiles, the second time
-// out of L2) instead of one after the other - the short tail tile is pure pipeline latency.  Every role of a slot walks
-// the same sequence.
+// The units of one (CTA, slot) worker in processing order: the worker owns the pairs p = 2 * cta + slot, + 2 * ncta,
+// ...; inside a pair the query tiles in ascending order, back to back, so that the pair's K / V tiles are still in L2
+// for the second tile.  (Dealing a pair's two query tiles to the two slots of a CTA was measured (profiles/README_r02.md): the slots drift
+// apart, K / V come from DRAM twice - 4.2 instead of 2.0 GB per layer - and the layer takes 1.78 instead of 1.13 ms.)
+// Every role of a slot walks the same sequence.
 template <int MASKED>
 struct UnitIter {
     int p, qt, nqt, head, W, npairs, slot, count;
@@ -116,11 +116,11 @@ struct UnitIter {
     // positions on the slot's first unit; false when it has none
     __device__ __forceinline__ bool begin(const AttnArgs* args, int cta, int ncta, int npairs_, int slot_) {
         a = args;
-        W = ncta;
+        W = 2 * ncta;
         npairs = npairs_;
         slot = slot_;
         count = 0;
-        p = cta;
+        p = 2 * cta + slot_;
         qt = -1;
         if (p >= npairs) return false;
         load_pair();
@@ -137,7 +137,8 @@ struct UnitIter {
             }
             u = make_unit<MASKED>(sd, head, qt, a->ldkv);
             if (u.nt <= 0) continue;
-            if ((count++ & 1) == slot) return true;
+            ++count;
+            return true;
         }
     }
 };
@@ -358,7 +359,7 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                     const Unit& n = pf.u;
 #pragma unroll
                     for (int blk = 0; blk < NB; ++blk) tma_prefetch_l2_4d(&maps.q, n.head * HD + blk * 64, n.q_row, 0, 0);
-                    {
+                    if (n.q0 == 0) {      // the pair's first query tile brings its keys / values in (later tiles re-read them)
                         const int nt = min(n.nt, 6);
                         for (int t = 0; t < nt; ++t)
 #pragma unroll
@@ -559,7 +560,8 @@ int launch_attention_tc(const void* Q, long long ldq, long long q_rows, const vo
     a.vswap = vswap & 1;
     const bool p_tmem = (vswap & 2) != 0;
     const int pairs = nseq * heads;
-    int grid = pairs < num_sms() ? pairs : num_sms();   // a CTA owns pairs, its two slots share their query tiles
+    int grid = (pairs + 1) / 2;
+    if (grid > num_sms()) grid = num_sms();
     int rc = 0;
 #define YTK_AT(HD_)                                                             \
     do {                                                                        \
