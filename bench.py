@@ -541,7 +541,9 @@ def main():
             "exchange": {"bytes_sent_per_step_all_ranks": xbytes_all / args.steps,
                          "ms_per_step_max_rank": float(cmax[2].item()) / args.steps,
                          "calls_per_step": x_value["exchange_calls"] / args.steps,
-                         "path": "device uint8 canvases, torch.distributed all_to_all_single over NCCL (no host staging)"},
+                         "path": "device uint8 canvases, ONE torch.distributed all_to_all_single over NCCL per step (no host "
+                                 "staging); costs / assignment / descriptors and the returned ids / probabilities travel over "
+                                 "host-side gloo groups; ms = host time around the enqueue"},
             "roofline": {"bound": "tensor",
                          "achieved": g_tf / (g_ms / 1e3), "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                          "frac": g_tf / (g_ms / 1e3) / pk["bf16_tflops_sustained"],

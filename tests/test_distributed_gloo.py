@@ -150,7 +150,7 @@ def _worker_pipeline(rank, world, port, q):
 def _worker_pipeline_dev(rank, world, port, q):
     """BatchedOCR._run_groups_dev across 2 ranks: crops that exist only as records are cut "on the device" (stand-in:
     the product's crop arithmetic compiled for the host, tensors on the CPU under gloo); the groups the balancer moves
-    travel as ONE flat uint8 tensor per rank through parallel.exchange_canvases_dev (all_to_all_single) and are
+    travel as ONE flat uint8 tensor per rank through parallel.exchange_canvases_planned (all_to_all_single, split sizes agreed on by the planners over gloo) and are
     recognised straight from the receive buffer."""
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
@@ -195,24 +195,34 @@ def _worker_pipeline_dev(rank, world, port, q):
             groups.append((widths, [max(widths)] * len(b), np.asarray(b, np.int64)))
             expect.append(_fake_recognise([ds.data[i] for i in b]))
         moved = []
-        orig_x = par_mod.exchange_canvases_dev
+        orig_x = par_mod.exchange_canvases_planned
 
-        def spy(canv, byte_splits, metas):
+        def spy(canv, send_splits, recv_splits):
             assert isinstance(canv, torch.Tensor) and canv.dtype == torch.uint8     # one flat buffer, never host lists
-            moved.append([int(b) for b in byte_splits])
-            return orig_x(canv, byte_splits, metas)
+            moved.append(([int(b) for b in send_splits], [int(b) for b in recv_splits]))
+            return orig_x(canv, send_splits, recv_splits)
 
-        par_mod.exchange_canvases_dev = spy
+        par_mod.exchange_canvases_planned = spy
         par_mod.exchange_groups = None              # the host-staged scatter must not be used any more
-        res = ocr._run_groups_dev(groups, geoms, np.ascontiguousarray(page)[None], None)
+        # the three phases separately, as stream() runs them (planner / recognizer / assembly thread)
+        lv = np.zeros(len(geoms), np.int64)
+        dplan = ocr._plan_groups_dist(groups, geoms, lv)
+        assert dplan["moves"] and (len(dplan["send"]) > 0) == (rank == 0)
+        pending = ocr._run_groups_dist_dev(groups, geoms, np.ascontiguousarray(page)[None], None, lv, dplan)
+        res = ocr._finish_results(pending)
         for (ids, probs, glen), (eid, ep) in zip(res, expect):
             assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101
         # rank 0 (8 groups) hands some groups to rank 1 (2 groups) as one buffer; rank 1 sends nothing
         assert len(moved) == 1
-        assert (moved[0][1] > 0 and moved[0][0] == 0) if rank == 0 else sum(moved[0]) == 0
+        send, recv = moved[0]
+        assert (send[1] > 0 and send[0] == 0 and sum(recv) == 0) if rank == 0 else (sum(send) == 0 and recv[0] > 0)
         assert par_mod.STATS["exchange_calls"] == 1
         assert (par_mod.STATS["exchange_bytes_sent"] > 0) == (rank == 0)
         assert (par_mod.STATS["exchange_bytes_received"] > 0) == (rank == 1)
+        # and the one-call wrapper gives the same
+        res2 = ocr._run_groups_dev(groups, geoms, np.ascontiguousarray(page)[None], None)
+        for (ids, probs, glen), (eid, ep) in zip(res2, expect):
+            assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101
         q.put((rank, "ok", None))
     except Exception:  # pragma: no cover
         import traceback

@@ -396,49 +396,55 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
     } else {
         // ------------------------------------------------------------------ MMA issuer (one thread, both slots)
         if (lane == 0) {
-            struct St {
+            // Two cursors per slot: the S cursor may run into the NEXT unit (its Q tile arrives as soon as the last Q K^T of
+            // the current unit has been issued, S buffers and K/V stages free up tile by tile) while the P V cursor is
+            // still on the current one - the next unit's first score tile is then ready when the softmax warps come
+            // out of the epilogue.
+            struct Cur {
                 UnitIter<MASKED> it;
                 Unit u;
-                int ts, tp;
-                uint32_t nu, cs, cpv;
+                int t;        // next key tile of `u`
+                uint32_t n;   // units this cursor has finished
                 bool done;
+            };
+            struct St {
+                Cur s, p;
+                uint32_t cs, cpv;   // key tiles issued as S / as P V (per slot, across units)
             } st[2];
-            auto next_unit = [&](St& S, bool first, int s) {
-                const bool more = first ? S.it.begin(&args, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x),
-                                                     npairs, s)
-                                        : S.it.next();
-                if (!more) {
-                    S.done = true;
-                    return;
-                }
-                S.u = S.it.u;
-                S.ts = 0;
-                S.tp = 0;
+            auto advance = [&](Cur& c, bool first, int slot) {
+                const bool more = first ? c.it.begin(&args, static_cast<int>(blockIdx.x), static_cast<int>(gridDim.x),
+                                                     npairs, slot)
+                                        : c.it.next();
+                c.done = !more;
+                if (more) c.u = c.it.u;
+                c.t = 0;
             };
             for (int s = 0; s < 2; ++s) {
-                st[s].done = false;
-                st[s].nu = st[s].cs = st[s].cpv = 0;
-                next_unit(st[s], true, s);
+                st[s].cs = st[s].cpv = 0;
+                st[s].s.n = st[s].p.n = 0;
+                advance(st[s].s, true, s);
+                advance(st[s].p, true, s);
             }
             constexpr uint32_t idesc_pv = umma_idesc_op(kAtQ, HD) | kIdescBMajorMN;
-            while (!(st[0].done && st[1].done)) {
+            while (!(st[0].p.done && st[1].p.done)) {
 #pragma unroll
                 for (int s = 0; s < 2; ++s) {
                     St& S = st[s];
-                    if (S.done) continue;
+                    if (S.p.done) continue;
                     SlotBars& b = bars[s];
                     const uint32_t q_addr = smem_u32(smem + s * Cfg::kSlotBytes);
                     const uint32_t p_addr = q_addr + Cfg::kQBytes;
                     const uint32_t kv_addr = p_addr + Cfg::kPBytes;
                     const uint32_t t_slot = tmem_base + static_cast<uint32_t>(s * 256);
-                    // ---- S = Q K^T of the next key tile
-                    if (S.ts < S.u.nt) {
+                    // ---- S = Q K^T of the next key tile (of the current or the following unit)
+                    if (!S.s.done) {
                         const uint32_t buf = S.cs & 1u, par = (S.cs >> 1) & 1u;
                         bool ok = mbar_test(&b.kv_full[buf], par) && mbar_test(&b.s_free[buf], par ^ 1u);
-                        if (ok && S.ts == 0) ok = mbar_test(&b.q_full, S.nu & 1u);
+                        if (ok && S.s.t == 0) ok = mbar_test(&b.q_full, S.s.n & 1u);
                         if (ok) {
                             tc_fence_after();
-                            const int nkeys = min(kAtKV, S.u.k_end - S.ts * kAtKV);
+                            const Unit& u = S.s.u;
+                            const int nkeys = min(kAtKV, u.k_end - S.s.t * kAtKV);
                             const uint32_t idesc_s = umma_idesc_op(kAtQ, (nkeys + 15) & ~15);
                             const uint32_t k_addr = kv_addr + buf * Cfg::kStageBytes;
 #pragma unroll
@@ -448,19 +454,23 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                                 umma_op(t_slot + buf * 64u, da, db, idesc_s, j != 0 ? 1u : 0u);
                             }
                             umma_commit(&b.s_full[buf]);
-                            if (S.ts == S.u.nt - 1) umma_commit(&b.q_empty);  // Q tile consumed
-                            ++S.ts;
                             ++S.cs;
+                            if (++S.s.t == u.nt) {
+                                umma_commit(&b.q_empty);   // Q tile consumed: the producer may load the next unit's
+                                ++S.s.n;
+                                advance(S.s, false, s);
+                            }
                         }
                     }
                     // ---- O += P V of the oldest key tile whose P is ready
-                    if (S.tp < S.ts) {
+                    if (S.cpv < S.cs) {
                         bool ok = mbar_test(&b.p_full, S.cpv & 1u);
-                        if (ok && S.tp == 0) ok = mbar_test(&b.o_free, (S.nu & 1u) ^ 1u);  // previous unit's O read out
+                        if (ok && S.p.t == 0) ok = mbar_test(&b.o_free, (S.p.n & 1u) ^ 1u);  // previous unit's O read out
                         if (ok) {
                             tc_fence_after();
+                            const Unit& u = S.p.u;
                             const uint32_t stg = S.cpv & 1u;
-                            const int nkeys = min(kAtKV, S.u.k_end - S.tp * kAtKV);
+                            const int nkeys = min(kAtKV, u.k_end - S.p.t * kAtKV);
                             const int ksteps = (nkeys + 15) >> 4;
                             const uint32_t v_addr = kv_addr + stg * Cfg::kStageBytes + Cfg::kKBytes;
                             for (int j = 0; j < ksteps; ++j) {
@@ -468,21 +478,20 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
                                 if constexpr (PT) {
                                     // A = P from tensor memory: 16 keys = 8 columns of the tile's S buffer
                                     umma_op_ts(t_slot + 128u, t_slot + stg * 64u + j * 8u, db, idesc_pv,
-                                               (S.tp | j) != 0 ? 1u : 0u);
+                                               (S.p.t | j) != 0 ? 1u : 0u);
                                 } else {
                                     const uint64_t da = umma_desc_sw128(p_addr) + static_cast<uint64_t>(2 * j);
-                                    umma_op(t_slot + 128u, da, db, idesc_pv, (S.tp | j) != 0 ? 1u : 0u);
+                                    umma_op(t_slot + 128u, da, db, idesc_pv, (S.p.t | j) != 0 ? 1u : 0u);
                                 }
                             }
                             if constexpr (PT) umma_commit(&b.s_free[stg]);   // P read: the S buffer may take tile t + 2
                             umma_commit(&b.kv_empty[stg]);
                             umma_commit(&b.p_empty);
-                            if (S.tp == S.u.nt - 1) umma_commit(&b.o_full);
-                            ++S.tp;
                             ++S.cpv;
-                            if (S.tp == S.u.nt) {
-                                ++S.nu;
-                                next_unit(S, false, s);
+                            if (++S.p.t == u.nt) {
+                                umma_commit(&b.o_full);
+                                ++S.p.n;
+                                advance(S.p, false, s);
                             }
                         }
                     }

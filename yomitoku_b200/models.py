@@ -165,6 +165,20 @@ def extract_crops_pyramid(pages, geoms, levels, stream=None):
     return concat_device_buffers(parts, stream), base, pix_off
 
 
+def plan_crop_offsets(geoms, levels):
+    """Host-only twin of `extract_crops_pyramid`'s packing: (total bytes, pix_off per record) of the buffer it will
+    produce for these records (one block per pyramid level in ascending order, canvases back to back inside a block)."""
+    levels = np.asarray(levels, np.int64)
+    pix_off = np.zeros(len(geoms), np.int64)
+    base = 0
+    for k in sorted(set(levels.tolist())):
+        idx = np.nonzero(levels == k)[0]
+        size = geoms["canvas_w"][idx].astype(np.int64) * geoms["canvas_h"][idx] * 3
+        pix_off[idx] = base + np.cumsum(size) - size
+        base += int(size.sum())
+    return base, pix_off
+
+
 def concat_device_buffers(parts, stream=None):
     """parts: list of (flat uint8 cuda tensor, used bytes) -> one flat uint8 tensor holding them back to back (the
     copy is queued on `stream`, like the kernels that filled the parts)."""

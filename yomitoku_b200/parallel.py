@@ -3,11 +3,15 @@ gloo in the CPU tests).  The reference has no distributed code at all (SURVEY.md
 
 What crosses the fabric - never inside a forward pass:
   * `broadcast_state_dict`   one-time weight broadcast from rank 0 (one flat buffer per dtype);
-  * `exchange_groups`        the crop scatter: whole reference mini-batches ("groups": the unit whose rows must stay
-                             together because the AR loop stops per group) move between ranks so that every GPU gets a
-                             balanced number of encoder tokens; packed u8 canvases + int32 descriptors travel with
-                             all_to_all_single and split sizes;
-  * `return_results`         the result gather: (ids int32, probs fp32) per crop back to the owning rank.
+  * the crop scatter         whole reference mini-batches ("groups": the unit whose rows must stay together because
+                             the AR loop stops per group) move between ranks so that every GPU gets a balanced number
+                             of encoder tokens.  Control plane on host-side gloo groups (`meta_group`: costs,
+                             assignment, descriptors - exchanged one batch ahead by the planner threads), data plane
+                             `exchange_canvases_planned`: ONE all_to_all_single of device uint8 canvases over NCCL;
+  * the result gather        (ids int32, probs fp32) per crop back to the owning rank over a second gloo group
+                             (`BatchedOCR._finish_results`, assembly thread).
+  * `exchange_groups` / `return_results`: the host-staged variant for crops cut by OpenCV on the host
+                             (`YTK_DEVICE_CROPS=0`).
 Pages are sharded by rank for detection (page p -> rank p // pages_per_rank); that needs no communication.
 """
 import numpy as np
@@ -82,59 +86,41 @@ def _all_to_all_bytes(send_chunks):
 
 STATS = {"exchange_calls": 0, "exchange_bytes_sent": 0, "exchange_bytes_received": 0, "exchange_ms": 0.0}
 
+_META = {}
 
-def exchange_canvases_dev(canv, byte_splits, metas):
-    """The crop scatter without touching the host: GPU-to-GPU all_to_all over NCCL / NVLink.
 
-    canv: flat uint8 tensor ON THE COMPUTE DEVICE holding the canvases of every group that leaves this rank, ordered by
-    destination rank; byte_splits[k] = bytes of it that go to rank k; metas[k] = int32 numpy array describing those
-    groups ([gid, n, (w, wp, byte offset in the chunk) * n] per group).  Returns (recv, recv_splits, recv_metas): one flat uint8 tensor on the same
-    device with the canvases this rank received (ordered by source rank), the bytes per source and the parsed
-    descriptors per source.  Under gloo (CPU tests) the tensors are CPU tensors and the same code runs."""
+def meta_group(which):
+    """A host-side (gloo) process group for small control messages, one per purpose ("plan": group costs / descriptors
+    exchanged by the planner threads one batch ahead of the GPU, "results": ids / probabilities of groups that were
+    recognised on another rank, exchanged by the assembly threads).  They never touch the NCCL communicator the
+    recognizer thread uses for the canvases, so the three kinds of traffic cannot block each other.  Created
+    collectively on first use (every rank reaches that point in the same order); with a gloo default group the default
+    group itself serves "plan" and one extra group "results"."""
+    if which not in _META:
+        _META[which] = dist.new_group(backend="gloo")
+    return _META[which]
+
+
+def all_gather_objects(obj, which):
+    """all_gather of one picklable object per rank over the `which` meta group -> list indexed by rank."""
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj, group=meta_group(which))
+    return out
+
+
+def exchange_canvases_planned(canv, send_splits, recv_splits):
+    """The crop scatter proper, with split sizes already agreed on by the planners: ONE all_to_all_single of device uint8
+    canvases over NCCL / NVLink (CPU tensors under gloo).  Returns the flat receive buffer (ordered by source rank)."""
     import time
-    world = dist.get_world_size()
-    device = canv.device
     t0 = time.perf_counter()
-    meta_t = [torch.from_numpy(np.ascontiguousarray(m, dtype=np.int32).view(np.uint8).copy()) for m in metas]
-    sizes = torch.tensor([[int(byte_splits[k]), int(meta_t[k].numel())] for k in range(world)], dtype=torch.int64,
-                         device=device)
-    recv_sizes = torch.empty_like(sizes)
-    dist.all_to_all_single(recv_sizes, sizes)
-    rs = recv_sizes.cpu().tolist()
-    recv_splits = [int(r[0]) for r in rs]
-    meta_splits = [int(r[1]) for r in rs]
-    recv = torch.empty(int(sum(recv_splits)), dtype=torch.uint8, device=device)
-    dist.all_to_all_single(recv, canv[: int(sum(byte_splits))], output_split_sizes=recv_splits,
-                           input_split_sizes=[int(b) for b in byte_splits])
-    msend = torch.cat(meta_t).to(device) if sum(m.numel() for m in meta_t) else torch.empty(0, dtype=torch.uint8,
-                                                                                           device=device)
-    mrecv = torch.empty(int(sum(meta_splits)), dtype=torch.uint8, device=device)
-    dist.all_to_all_single(mrecv, msend, output_split_sizes=meta_splits,
-                           input_split_sizes=[int(m.numel()) for m in meta_t])
-    mh = mrecv.cpu().numpy()
-    recv_metas, off = [], 0
-    for n in meta_splits:
-        recv_metas.append(mh[off:off + n].view(np.int32).copy())
-        off += n
-    if device.type == "cuda":
-        torch.cuda.current_stream(device).synchronize()
+    recv = torch.empty(int(sum(recv_splits)), dtype=torch.uint8, device=canv.device)
+    dist.all_to_all_single(recv, canv[: int(sum(send_splits))], output_split_sizes=[int(v) for v in recv_splits],
+                           input_split_sizes=[int(v) for v in send_splits])
     STATS["exchange_calls"] += 1
-    STATS["exchange_bytes_sent"] += int(sum(byte_splits))
+    STATS["exchange_bytes_sent"] += int(sum(send_splits))
     STATS["exchange_bytes_received"] += int(sum(recv_splits))
     STATS["exchange_ms"] += (time.perf_counter() - t0) * 1e3
-    return recv, recv_splits, recv_metas
-
-
-def parse_group_meta(meta):
-    """int32 [gid, n, (w, wp, byte offset inside the sender's chunk) * n] * groups -> list of (gid, widths, padded
-    widths, offsets)."""
-    out, off = [], 0
-    while off < len(meta):
-        gid, n = int(meta[off]), int(meta[off + 1])
-        wm = meta[off + 2: off + 2 + 3 * n].reshape(n, 3)
-        out.append((gid, wm[:, 0].astype(np.int64), wm[:, 1].astype(np.int64), wm[:, 2].astype(np.int64)))
-        off += 2 + 3 * n
-    return out
+    return recv
 
 
 def _pack_group(canvases, padded, gid):

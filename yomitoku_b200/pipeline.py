@@ -390,79 +390,126 @@ class BatchedOCR:
 
     def _run_groups_dev(self, groups, geoms, pages_dev, stream=None, levels=None, plan=None):
         """Groups whose crops exist only as records: groups = (widths, padded widths, record indices into `geoms`).
-        Groups recognised on this rank are cut on the device and never leave HBM (`_run_groups_dev_local`).  With
-        torch.distributed, the groups the balancer moves to another rank are cut into one device buffer ordered by
-        destination and travel GPU-to-GPU (`parallel.exchange_canvases_dev`: all_to_all_single over NCCL / NVLink); the
-        receiving rank recognises them straight from the receive buffer.  No canvas touches the host on any rank."""
-        import torch
+        Single rank: cut on the device and recognised without leaving HBM (`_run_groups_dev_local`).  With
+        torch.distributed the call has three phases that `stream()` runs in three different threads -
+        `_plan_groups_dist` (host: costs, balancing and descriptors over a gloo group), `_run_groups_dist_dev`
+        (device: the leaving groups are cut into one buffer ordered by destination and travel GPU-to-GPU with ONE
+        all_to_all_single over NCCL / NVLink; own and received groups are recognised) and `_finish_results` (host: ids /
+        probabilities of groups recognised elsewhere come back over a second gloo group).  No canvas touches the host
+        on any rank.  This wrapper runs the three phases back to back."""
         import torch.distributed as dist
         if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
             return self._run_groups_dev_local(groups, geoms, pages_dev, stream, levels, plan)
-        from . import parallel as par
-        from .models import extract_crops_pyramid
-        pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
         lv = levels if levels is not None else np.zeros(len(geoms), np.int64)
+        dplan = plan if isinstance(plan, dict) else self._plan_groups_dist(groups, geoms, lv)
+        return self._finish_results(self._run_groups_dist_dev(groups, geoms, pages_dev, stream, lv, dplan))
+
+    def _plan_groups_dist(self, groups, geoms, levels):
+        """Phase 1 (host only; collectives on the "plan" gloo group): every rank learns all group costs, derives the
+        same assignment, and tells the others what it will send - after this no rank needs another control message
+        before its device work."""
+        import torch.distributed as dist
+        from . import parallel as par
+        from .models import plan_crop_offsets
         cfg = self.recognizer._cfg
         ph, pw = cfg.encoder.patch_size
         gh = cfg.data.img_size[0] // ph
         world, rank = dist.get_world_size(), dist.get_rank()
         costs = [gh * (int(np.sum(g[1])) // pw) for g in groups]
-        assign_all = par.balance_groups(par.gather_costs(costs), world)
+        assign_all = par.balance_groups(par.all_gather_objects(costs, "plan"), world)
         if all(dst == r for r, row in enumerate(assign_all) for dst in row):
-            return self._run_groups_dev_local(groups, geoms, pages, stream, lv)   # same decision on every rank
+            return {"dist": True, "moves": False, "plan": self._plan_groups_dev(groups, geoms, levels)}
         assign = assign_all[rank]
         mine = [k for k in range(len(groups)) if assign[k] == rank]
-        leaving = sorted((k for k in range(len(groups)) if assign[k] != rank), key=lambda k: (assign[k], k))
+        send, outgoing, send_splits = [], {}, [0] * world
+        for dst in range(world):
+            ks = [k for k in range(len(groups)) if assign[k] == dst and dst != rank]
+            if not ks:
+                continue
+            idx = np.concatenate([groups[k][2] for k in ks])
+            sel, lvs = geoms[idx].copy(), levels[idx]
+            total, offs = plan_crop_offsets(sel, lvs)
+            send.append((dst, sel, lvs, total))
+            send_splits[dst] = total
+            rows, j = [], 0
+            for k in ks:
+                m = len(groups[k][0])
+                rows.append((k, np.asarray(groups[k][0], np.int64), np.asarray(groups[k][1], np.int64), offs[j:j + m]))
+                j += m
+            outgoing[dst] = {"bytes": total, "groups": rows}
+        everyone = par.all_gather_objects(outgoing, "plan")
+        recv_splits, foreign, work, base = [0] * world, [], [], 0
+        for src in range(world):
+            d = everyone[src].get(rank) if src != rank else None
+            if d is None:
+                continue
+            recv_splits[src] = int(d["bytes"])
+            for gid, w, wp, offs in d["groups"]:
+                foreign.append((w, wp, base + offs))
+                work.append((src, int(gid)))
+            base += int(d["bytes"])
+        return {"dist": True, "moves": True, "mine": mine,
+                "mine_plan": self._plan_groups_dev([groups[k] for k in mine], geoms, levels) if mine else [],
+                "send": send, "send_splits": send_splits, "recv_splits": recv_splits, "foreign": foreign,
+                "foreign_work": work, "n_groups": len(groups), "away": {k: assign[k] for k in range(len(groups))
+                                                                        if assign[k] != rank}}
+
+    def _run_groups_dist_dev(self, groups, geoms, pages_dev, stream, levels, dplan):
+        """Phase 2 (device): returns a `_PendingResults` (own groups done, results of foreign groups to hand back)."""
+        import torch
+        from . import parallel as par
+        from .models import concat_device_buffers, extract_crops_pyramid
+        pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
+        if not dplan["moves"]:
+            return _PendingResults(self._run_groups_dev_local(groups, geoms, pages, stream, levels, dplan["plan"]), None,
+                                   None)
+        cfg = self.recognizer._cfg
         ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
         with ctx:
-            # ---- cut the leaving groups on the device: one chunk per destination rank, chunks back to back
-            byte_splits = [0] * world
-            metas = [[] for _ in range(world)]
             parts = []
-            for dst in range(world):
-                ks = [k for k in leaving if assign[k] == dst]
-                if not ks:
-                    continue
-                idx = np.concatenate([groups[k][2] for k in ks])
-                sel = geoms[idx].copy()
-                canv_d, total_d, offs_d = extract_crops_pyramid(pages, sel, lv[idx], stream)
+            for dst, sel, lvs, total in dplan["send"]:      # ascending destination = the order of the split sizes
+                canv_d, total_d, _ = extract_crops_pyramid(pages, sel, lvs, stream)
+                assert total_d == total
                 parts.append((canv_d, total_d))
-                byte_splits[dst] = int(total_d)
-                j = 0
-                for k in ks:
-                    m = len(groups[k][0])
-                    metas[dst] += [k, m] + [v for w, p, o in zip(groups[k][0], groups[k][1], offs_d[j:j + m])
-                                            for v in (int(w), int(p), int(o))]
-                    j += m
             if parts:
-                from .models import concat_device_buffers
                 canv = concat_device_buffers(parts, stream)
                 if len(parts) == 1:
                     canv = canv[: parts[0][1]]
             else:
                 some = next(iter(pages.values()))
                 canv = torch.empty(0, dtype=torch.uint8, device=getattr(some, "device", "cpu"))
-            recv, recv_splits, recv_metas = par.exchange_canvases_dev(
-                canv, byte_splits, [np.asarray(m, np.int32) for m in metas])
-        # ---- own groups straight from the resident pages, foreign groups straight from the receive buffer
-        res = list(self._run_groups_dev_local([groups[k] for k in mine], geoms, pages, stream, lv)) if mine else []
-        work = [(rank, k, None, groups[k][1]) for k in mine]
-        foreign, base = [], 0
-        height = cfg.data.img_size[0]
-        for src, meta in enumerate(recv_metas):
-            for gid, w, wp, offs_g in par.parse_group_meta(meta):
-                foreign.append((w, wp, base + offs_g))
-                work.append((src, gid, None, wp.tolist()))
-            base += recv_splits[src]
-        if foreign:
-            res = res + self._run_groups_buf(foreign, recv, height, stream)
-        S = cfg.max_label_length + 1
-        packed = []
-        for (ids, probs, glen) in res:
-            packed.append((np.concatenate([ids, np.full((ids.shape[0], 1), glen, np.int32)], axis=1),
-                           np.concatenate([probs, np.zeros((probs.shape[0], 1), np.float32)], axis=1)))
-        back = par.return_results(work, packed, len(groups), S + 1)
-        return [(i[:, :S], p[:, :S], int(i[0, S]) if len(i) else 0) for i, p in back]
+            recv = par.exchange_canvases_planned(canv, dplan["send_splits"], dplan["recv_splits"])
+        mine = dplan["mine"]
+        res = self._run_groups_dev_local([groups[k] for k in mine], geoms, pages, stream, levels,
+                                         dplan["mine_plan"]) if mine else []
+        out = [None] * dplan["n_groups"]
+        for k, r in zip(mine, res):
+            out[k] = r
+        back = []
+        if dplan["foreign"]:
+            fres = self._run_groups_buf(dplan["foreign"], recv, cfg.data.img_size[0], stream)
+            back = [(src, gid, ids, probs, glen) for (src, gid), (ids, probs, glen) in zip(dplan["foreign_work"], fres)]
+        return _PendingResults(out, back, dplan["away"])
+
+    def _finish_results(self, pending):
+        """Phase 3 (host; collectives on the "results" gloo group): results of the groups this rank sent away."""
+        if isinstance(pending, list):
+            return pending
+        if pending.back is None:
+            return pending.out
+        from . import parallel as par
+        import torch.distributed as dist
+        rank = dist.get_rank()
+        outgoing = {}
+        for src, gid, ids, probs, glen in pending.back:
+            outgoing.setdefault(src, []).append((gid, np.ascontiguousarray(ids), np.ascontiguousarray(probs), int(glen)))
+        for everyone in par.all_gather_objects(outgoing, "results"):
+            for gid, ids, probs, glen in everyone.get(rank, []):
+                pending.out[gid] = (ids, probs, glen)
+        missing = [k for k, r in enumerate(pending.out) if r is None]
+        if missing:
+            raise RuntimeError("crop scatter: no result came back for groups %s" % missing[:8])
+        return pending.out
 
     def _run_groups_buf(self, groups, buf, height, stream=None):
         """groups = (widths, padded widths, byte offsets into `buf`), `buf` a flat uint8 tensor on the compute device
@@ -659,18 +706,31 @@ class BatchedOCR:
             import torch.distributed as dist
             if not (dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1):
                 prep["plan"] = self._plan_groups_dev(groups, prep["geoms"], prep["levels"])
+            else:       # costs / balancing / descriptors now, in this (planner) thread, over the host-side group
+                prep["plan"] = self._plan_groups_dist(groups, prep["geoms"], prep["levels"])
         return prep
 
-    def run_prepared(self, prep, stream=None, arena=None, pages_dev=None):
-        """Device half of `recognize_pooled`: returns per page (ids, probs, order) with rows in the page's *plan* order,
-        exactly like TextRecognizer._run_plan."""
+    def run_prepared(self, prep, stream=None, arena=None, pages_dev=None, finish=True):
+        """Device half of `recognize_pooled`.  finish=True: returns per page (ids, probs, order) with rows in the page's
+        *plan* order, exactly like TextRecognizer._run_plan.  finish=False (`stream()` with several ranks): returns the
+        raw group results, possibly pending on other ranks - `finish_prepared` completes them in another thread."""
+        groups = prep["groups"]
+        if prep["in_dev"]:
+            plan = prep.get("plan")
+            if isinstance(plan, dict):
+                lv = prep["levels"]
+                raw = self._run_groups_dist_dev(groups, prep["geoms"], pages_dev, stream, lv, plan)
+            else:
+                raw = self._run_groups_dev(groups, prep["geoms"], pages_dev, stream, prep["levels"], plan)
+        else:
+            raw = self._run_groups(groups, stream, arena if prep["in_arena"] else None, prep["height"])
+        return self.finish_prepared(prep, raw) if finish else raw
+
+    def finish_prepared(self, prep, raw):
         rec = self.recognizer
         cfg = rec._cfg
-        groups, owner, orders = prep["groups"], prep["owner"], prep["orders"]
-        if prep["in_dev"]:
-            res = self._run_groups_dev(groups, prep["geoms"], pages_dev, stream, prep["levels"], prep.get("plan"))
-        else:
-            res = self._run_groups(groups, stream, arena if prep["in_arena"] else None, prep["height"])
+        res = self._finish_results(raw)
+        owner, orders = prep["owner"], prep["orders"]
         S = cfg.max_label_length + 1
         out = []
         for pi in range(prep["n_pages"]):
@@ -829,13 +889,24 @@ class BatchedOCR:
             prep = self.prepare_pooled(rec_in, arena=arena, pages_dev=handle.pages_dev)
         return host, prep, arena
 
-    def _run_handle(self, handle, prepared, stream=None):
+    def _run_handle(self, handle, prepared, stream=None, defer=False):
+        """defer=True (`stream()`): the device work of this batch only; what other ranks still owe is collected by
+        `_finish_handle` in the assembly thread, so the GPU goes straight into the next batch."""
         host, prep, arena = prepared
+        fallback = handle.pages_dev is not None and getattr(self.recognizer, "rec_orientation_fallback", False)
         with _span("collect.recognize"):
+            if defer and not fallback:
+                return host, (prep, self.run_prepared(prep, stream, arena=arena, pages_dev=handle.pages_dev, finish=False))
             rec_out = self.run_prepared(prep, stream, arena=arena, pages_dev=handle.pages_dev)
-            if handle.pages_dev is not None and getattr(self.recognizer, "rec_orientation_fallback", False):
+            if fallback:
                 self._orientation_fallback_dev([h[2] for h in host], rec_out, handle.pages_dev, stream)
         return host, rec_out
+
+    def _finish_handle(self, item):
+        host, rec = item
+        if isinstance(rec, tuple):
+            rec = self.finish_prepared(*rec)
+        return host, rec
 
     def _orientation_fallback_dev(self, page_geoms, rec_out, pages_dev, stream=None):
         """The recognizer's optional 180-degree second look (reference text_recognizer.py:319-350) for a whole batch:
@@ -1001,7 +1072,7 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
                     break
                 h, prepared = item
                 try:
-                    q2.put(ocr._run_handle(h, prepared, stream=rec_stream))
+                    q2.put(ocr._run_handle(h, prepared, stream=rec_stream, defer=True))
                 finally:
                     h.done.set()       # the staging slot of this batch may be reused
         except BaseException as e:
@@ -1028,7 +1099,7 @@ def _stream_impl(ocr, batches, lookahead, prob_override, quads_override):
             item = q2.get()
             if item is None:
                 break
-            yield ocr._assemble(*item)
+            yield ocr._assemble(*ocr._finish_handle(item))
         for t in threads:
             t.join()
     finally:
@@ -1075,6 +1146,14 @@ def _fast_word(cls, points, content, direction, det_score, rec_score):
     object.__setattr__(m, "__pydantic_extra__", None)
     object.__setattr__(m, "__pydantic_private__", None)
     return m
+
+
+class _PendingResults:
+    """Phase-2 output of the multi-rank recognizer call: `out[k]` = (ids, probs, group_len) of the groups recognised
+    here (None for the ones sent away), `back` = results this rank owes to other ranks (None: nothing moved at all)."""
+
+    def __init__(self, out, back, away):
+        self.out, self.back, self.away = out, back, away
 
 
 class _NullCtx:
