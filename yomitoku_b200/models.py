@@ -386,6 +386,15 @@ class PARSeq(_DeviceModel):
         self.rep_min_repeats = int(getattr(cfg, "rep_min_repeats", 3))
         self._sd = _parseq_random_state_dict(cfg, seed)
 
+    def __setattr__(self, name, value):
+        # the repetition-stop knobs and decode_ar are baked into the C handle at creation: changing one afterwards (the
+        # reference reads them from the module at every forward, models/parseq.py:93-96,189) drops the handle so that
+        # the next forward re-creates it with the new values instead of silently keeping the old ones
+        if name in ("repetition_stop", "rep_period_max", "rep_min_run_p1", "rep_min_repeats", "decode_ar") and \
+                getattr(self, "_handle", None) is not None and getattr(self, name, value) != value:
+            self._release()
+        object.__setattr__(self, name, value)
+
     @property
     def refine_iters(self):
         return self._refine_iters

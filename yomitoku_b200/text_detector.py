@@ -9,7 +9,7 @@ ONNX / multi-backend dispatch is out of scope for this path.
 import numpy as np
 import torch
 
-from .base import BaseModelCatalog, BaseModule
+from .base import BaseModelCatalog, BaseModule, logger
 from .config import TextDetectorDBNetConfig, TextDetectorDBNetV2_1Config, TextDetectorDBNetV2Config
 from .data import array_to_tensor, resize_shortest_edge, shortest_edge_size, standardization_image
 from .models import DBNet
@@ -36,6 +36,8 @@ class TextDetector(BaseModule):
                  infer_onnx=False):
         super().__init__()
         self.visualize = visualize
+        if infer_onnx:
+            logger.warning("TextDetector(infer_onnx=True): there is no ONNX path in yomitoku_b200, the CUDA engine is used")
         self.infer_onnx = False   # accepted for API compatibility; there is no ONNX path here
         self.device = device
         self.load_model(model_name, path_cfg, from_pretrained=from_pretrained)

@@ -18,7 +18,7 @@ import unicodedata
 import cv2
 import numpy as np
 
-from .base import BaseModelCatalog, BaseModule
+from .base import BaseModelCatalog, BaseModule, logger
 from .config import (TextRecognizerPARSeqConfig, TextRecognizerPARSeqLargeV41Config, TextRecognizerPARSeqSmallConfig,
                      TextRecognizerPARSeqTinyConfig, TextRecognizerPARSeqTinyDynwV4Config,
                      TextRecognizerPARSeqV2Config)
@@ -93,6 +93,11 @@ class TextRecognizer(BaseModule):
         self.model.tokenizer = self.tokenizer
         self.model.eval()
         self.visualize = visualize
+        if infer_onnx:
+            logger.warning("TextRecognizer(infer_onnx=True): there is no ONNX path in yomitoku_b200, the CUDA engine is used")
+        if visualize:
+            logger.warning("TextRecognizer(visualize=True): the recognized text is not drawn (the reference's "
+                           "rec_visualizer needs its bundled font); `vis` is the detector's image or a copy of the page")
         self.infer_onnx = False
         self.rec_orientation_fallback = rec_orientation_fallback
         self.rec_orientation_fallback_thresh = rec_orientation_fallback_thresh
