@@ -207,18 +207,19 @@ def _worker_pipeline_dev(rank, world, port, q):
         # the three phases separately, as stream() runs them (planner / recognizer / assembly thread)
         lv = np.zeros(len(geoms), np.int64)
         dplan = ocr._plan_groups_dist(groups, geoms, lv)
-        assert dplan["moves"] and (len(dplan["send"]) > 0) == (rank == 0)
+        assert dplan["moves"] and (rank != 0 or len(dplan["send"]) > 0)     # rank 0 (8 groups) must hand some over
         pending = ocr._run_groups_dist_dev(groups, geoms, np.ascontiguousarray(page)[None], None, lv, dplan)
         res = ocr._finish_results(pending)
         for (ids, probs, glen), (eid, ep) in zip(res, expect):
             assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101
-        # rank 0 (8 groups) hands some groups to rank 1 (2 groups) as one buffer; rank 1 sends nothing
+        # rank 0 (8 groups) hands several groups to rank 1 (2 groups) as one buffer (the balancer may send a small
+        # group of rank 1 the other way); what one rank sends is what the other receives
         assert len(moved) == 1
         send, recv = moved[0]
-        assert (send[1] > 0 and send[0] == 0 and sum(recv) == 0) if rank == 0 else (sum(send) == 0 and recv[0] > 0)
+        assert send[rank] == 0 and recv[rank] == 0
+        assert (send[1] > 0) if rank == 0 else (recv[0] > 0)
         assert par_mod.STATS["exchange_calls"] == 1
-        assert (par_mod.STATS["exchange_bytes_sent"] > 0) == (rank == 0)
-        assert (par_mod.STATS["exchange_bytes_received"] > 0) == (rank == 1)
+        assert par_mod.STATS["exchange_bytes_sent"] == sum(send) and par_mod.STATS["exchange_bytes_received"] == sum(recv)
         # and the one-call wrapper gives the same
         res2 = ocr._run_groups_dev(groups, geoms, np.ascontiguousarray(page)[None], None)
         for (ids, probs, glen), (eid, ep) in zip(res2, expect):

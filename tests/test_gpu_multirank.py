@@ -58,7 +58,7 @@ def _worker(rank, world, port, q):
         assert len(got) == len(ref) == len(groups)
         for (ids, probs, glen), (rid, rp, rg) in zip(got, ref):
             assert np.array_equal(ids, rid) and np.array_equal(probs, rp) and glen == rg
-        assert (moved > 0) == (rank == 0) and (recvd > 0) == (rank == 1), (rank, moved, recvd)
+        assert (moved > 0) if rank == 0 else (recvd > 0), (rank, moved, recvd)      # rank 0 must hand groups to rank 1
         q.put((rank, "ok", moved))
     except Exception:  # pragma: no cover
         import traceback

@@ -21,6 +21,10 @@ from .schemas import OCRSchema
 from .text_recognizer import plan_mini_batches
 
 _W = {}
+# Cost of a mini-batch group for the cross-rank balancer, in encoder-token units: the encoder and the attention over the
+# encoder memory scale with the group's tokens, the AR steps / refinement / head with its rows.  Measured on B200
+# (profiles/README_r02.md, 101 AR steps): ~0.31 us per token and ~12.5 us per row, i.e. one row costs about 40 tokens.
+ROW_COST_TOKENS = 40
 TRACE = None     # set to a list to collect (stage, thread name, t0, t1) tuples (scripts/gpu_trace_e2e.py)
 
 
@@ -415,7 +419,7 @@ class BatchedOCR:
         ph, pw = cfg.encoder.patch_size
         gh = cfg.data.img_size[0] // ph
         world, rank = dist.get_world_size(), dist.get_rank()
-        costs = [gh * (int(np.sum(g[1])) // pw) for g in groups]
+        costs = [gh * (int(np.sum(g[1])) // pw) + ROW_COST_TOKENS * len(g[1]) for g in groups]
         assign_all = par.balance_groups(par.all_gather_objects(costs, "plan"), world)
         if all(dst == r for r, row in enumerate(assign_all) for dst in row):
             return {"dist": True, "moves": False, "plan": self._plan_groups_dev(groups, geoms, levels)}
@@ -646,7 +650,7 @@ class BatchedOCR:
         ph, pw = cfg.encoder.patch_size
         gh = cfg.data.img_size[0] // ph
         rank = dist.get_rank()
-        costs = [gh * (int(np.sum(g[1])) // pw) for g in groups]
+        costs = [gh * (int(np.sum(g[1])) // pw) + ROW_COST_TOKENS * len(g[1]) for g in groups]
         assign_all = par.balance_groups(par.gather_costs(costs), dist.get_world_size())
         if all(dst == r for r, row in enumerate(assign_all) for dst in row):
             # balanced already (every rank computes the same table from the same gathered costs): nothing moves, so
