@@ -354,11 +354,22 @@ def main():
     pages_dev = torch.from_numpy(np.stack(pages)).cuda()
     prob_dev = torch.empty((P, Hn, Wn), dtype=torch.float32, device="cuda")
 
+    # device front half of the post-processing (threshold, components, row runs): it runs on the synthetic maps, the
+    # random-weight maps above are noise
+    syn_dev = torch.from_numpy(np.stack(probs_syn)).cuda()
+    post_labels = torch.empty((ocr.det_batch, Hn, Wn), dtype=torch.int32, device="cuda")
+    post_runs = torch.empty((ocr.det_batch, 32768, 24), dtype=torch.uint8, device="cuda")
+    post_meta = torch.empty((P, 4), dtype=torch.int32, device="cuda")
+
     def det_step():
         for s in range(0, P, ocr.det_batch):
             e = min(P, s + ocr.det_batch)
             _lib.check(L.ytk_dbnet_forward_u8(det.model._ensure(), pages_dev[s:e].data_ptr(), 1, e - s, 1200, 1600,
                                               prob_dev[s:e].data_ptr(), 1, None))
+            if det.device_post:
+                _lib.check(L.ytk_dbnet_post_front(syn_dev[s:e].data_ptr(), e - s, Hn, Wn, float(det.post_processor.thresh), post_labels.data_ptr(),
+                                                  post_labels.numel() * 4, post_runs.data_ptr(), 32768,
+                                                  post_meta[s:e].data_ptr(), None))
 
     # per-page crop records + reference grouping (exactly what BatchedOCR.recognize_pooled builds from the host stage)
     per_page, base = [], 0
@@ -453,16 +464,20 @@ def main():
     e2e = None
     if not args.no_e2e:
         nw = max(3, args.warmup)
-        for _ in ocr.stream([pages] * nw, lookahead=2, prob_override=[probs_syn] * nw):
+        # the synthetic maps stand in for the detector's output (random weights give noise): with the device-side
+        # post-processing that output lives in HBM, so the stand-ins are device tensors too (a D2D copy per page)
+        po = [torch.from_numpy(p).cuda() for p in probs_syn] if det.device_post else probs_syn
+        for _ in ocr.stream([pages] * nw, lookahead=2, prob_override=[po] * nw):
             pass
         sync_all()
         x1 = dict(par.STATS)
+        d2h0, front0, host0 = ocr.post_d2h_bytes, ocr.post_front_pages, ocr.post_host_pages
         t0 = time.perf_counter()
         n_words = 0
         # documented pipelined use of the public API: `BatchedOCR.stream` runs the detector + host stage of the next
         # batches (own thread, own CUDA stream, process pool) while the recognizer works on the current one; exactly
         # `steps` batches of P pages go through
-        for res in ocr.stream([pages] * args.steps, lookahead=2, prob_override=[probs_syn] * args.steps):
+        for res in ocr.stream([pages] * args.steps, lookahead=2, prob_override=[po] * args.steps):
             n_words += sum(len(r.words) for r in res)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
@@ -473,12 +488,14 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
             dist.all_reduce(xs, op=dist.ReduceOp.SUM)
         dt = float(tt.item())
-        # the crops never cross PCIe, only their 136-byte records do; results: ids + probs per crop
+        # the crops never cross PCIe, only their 136-byte records do; results: ids + probs per crop; detector stage:
+        # the components' row runs (24 bytes each) instead of the maps when the device post-processing front runs
         h2d = P * 1200 * 1600 * 3 + n_crops * 136
-        d2h = P * Hn * Wn * 4 + n_crops * 101 * 8
+        d2h = (ocr.post_d2h_bytes - d2h0) // args.steps + n_crops * 101 * 8
         e2e = {"value": world * P * args.steps / dt, "unit": "pages/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "words_per_page": float(xs[1].item()) / (args.steps * P * world),
-               "host_workers": ocr.workers, "device_crops": True,
+               "host_workers": ocr.workers, "device_crops": True, "device_post": bool(det.device_post),
+               "post_front_pages": ocr.post_front_pages - front0, "post_host_fallback_pages": ocr.post_host_pages - host0,
                "exchange_bytes_per_step_all_ranks": float(xs[0].item()) / args.steps,
                "exchange_ms_per_step_rank0": x_e2e["exchange_ms"] / args.steps}
     # ---------------- other configs (single GPU only: they are single-GPU configurations of BASELINE.json)

@@ -73,6 +73,27 @@ int ytk_op_attention_f16(const void* Q, long long ldq, long long q_rows, const v
                          long long kv_rows, void* O, long long ldo, const ytk_attn_seq* seqs_dev, int nseq, int max_q_len,
                          int heads, int head_dim, int masked, int impl, void* cuda_stream);
 
+/* ---- Device-side front half of the DBNet post-processing (reference postprocessor/dbnet_postporcessor.py:39-82:
+ * binarize, findContours, and the pixel work of minAreaRect / box_score_fast).  One record per horizontal run of an
+ * 8-connected component of (prob > thresh). ---- */
+typedef struct ytk_db_run {
+    int32_t root;  /* raster index of the component's first pixel: component id; OpenCV lists outer contours in
+                      descending order of it */
+    int32_t y;
+    int32_t x0;    /* first column */
+    int32_t x1;    /* last column, inclusive */
+    double sum;    /* sum of prob over the run */
+} ytk_db_run;
+
+/* prob_dev: [n_pages, H, W] fp32 device; scratch_dev: n_pages*H*W*4 bytes device; runs_dev: [n_pages, max_runs_per_page]
+ * device; meta_dev: [n_pages, 4] int32 device = {runs found (> max_runs_per_page means truncated), components,
+ * 4 * Euler number (8-connectivity: holes = components - Euler number), overflow flag}.  Asynchronous on the stream.
+ * The end points of a component's runs have the same minAreaRect as its OpenCV contour, sum / pixel count of the runs is
+ * box_score_fast of a component without holes; pages with holes must use the host path (the caller's decision). */
+int ytk_dbnet_post_front(const float* prob_dev, int n_pages, int H, int W, float thresh, void* scratch_dev,
+                         long long scratch_bytes, ytk_db_run* runs_dev, int max_runs_per_page, int32_t* meta_dev,
+                         void* cuda_stream);
+
 /* ---- DBNet text detector: replaces `self.model(tensor)` in reference TextDetector.__call__
  * (src/yomitoku/text_detector.py:127-129 -> models/dbnet_plus.py:243-246) and, in the fused u8 entry, also
  * TextDetector.preprocess (text_detector.py:99-107, data/functions.py:196-264). ---- */

@@ -27,3 +27,4 @@ def test_struct_layouts_match_header():
     assert ctypes.sizeof(_lib.YtkParseqCfg) == 18 * 4    # 17 config ints + decode_ar
     assert ctypes.sizeof(_lib.YtkTensor) == 8 + 8 + 8 + 32
     assert ctypes.sizeof(_lib.YtkAttnSeq) == 32          # 4 ints + long long + 2 ints
+    assert ctypes.sizeof(_lib.YtkDbRun) == 24            # 4 ints + double

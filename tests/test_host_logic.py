@@ -653,3 +653,74 @@ def test_vectorised_clipper_offset_equals_scalar_routine():
     for a, b in zip(ref, got):
         assert a.shape == b.shape and np.array_equal(a, b)
     assert offset_boxes_round(np.zeros((0, 4, 2)), np.zeros(0)) == []
+
+
+# ------------------------------------------------------------------ device front half of the post-processing (host side)
+def _blob_map(seed, holes):
+    """Random map of rotated blurred boxes; `holes` punches low-probability dots into some of them."""
+    import cv2
+    rng = np.random.default_rng(seed)
+    H, W = 300, 420
+    m = np.zeros((H, W), np.float32)
+    for _ in range(30):
+        c = (float(rng.integers(20, W - 20)), float(rng.integers(20, H - 20)))
+        wh = (float(rng.integers(6, 90)), float(rng.integers(4, 30)))
+        cv2.fillPoly(m, [cv2.boxPoints((c, wh, float(rng.uniform(-40, 40)))).astype(np.int32)], float(rng.uniform(0.5, 1.0)))
+    m = cv2.GaussianBlur(m, (7, 7), 0)
+    m += rng.uniform(0, 0.02, m.shape).astype(np.float32)
+    if holes:
+        ys, xs = np.nonzero(m > 0.6)
+        for k in rng.integers(0, len(ys), 5):
+            m[ys[k], xs[k]] = 0.0
+    return m
+
+
+def test_boxes_from_runs_equals_boxes_from_bitmap():
+    """DBnetPostProcessor.boxes_from_runs (input: what csrc/dbpost_ops.cu emits, here from the scipy twin in
+    oracle/dbpost.py) returns the quads of boxes_from_bitmap (OpenCV contours) on every map without holes."""
+    from oracle.dbpost import post_front
+    from yomitoku_b200.synth import synthetic_page, synthetic_prob_map
+    pp = DBnetPostProcessor(min_size=2, thresh=0.3, box_thresh=0.4, max_candidates=1500, unclip_ratio=3.5)
+    checked = 0
+    maps = [(_blob_map(s, False), (840, 600)) for s in range(12)]
+    _, quads = synthetic_page(3)
+    maps.append((synthetic_prob_map(quads, (1184, 1600), (1200, 1600)), (1600, 1200)))
+    for prob, (dw, dh) in maps:
+        runs, comps, holes = post_front(prob, pp.thresh)
+        if holes:
+            continue
+        b1, s1 = pp.boxes_from_bitmap(prob, prob > pp.thresh, dw, dh)
+        b2, s2 = pp.boxes_from_runs(runs, prob.shape[1], prob.shape[0], dw, dh)
+        assert b1 == b2 and len(b1) > 0
+        assert np.allclose(s1, s2, rtol=1e-12, atol=0)
+        checked += 1
+    assert checked >= 6
+
+
+def test_boxes_from_runs_order_and_limit():
+    """max_candidates keeps OpenCV's FIRST contours = the components with the largest first-pixel index."""
+    from oracle.dbpost import post_front
+    prob = _blob_map(110, False)
+    runs, comps, holes = post_front(prob, 0.3)
+    if holes:
+        pytest.skip("map has holes")
+    pp = DBnetPostProcessor(min_size=2, thresh=0.3, box_thresh=0.4, max_candidates=5, unclip_ratio=3.5)
+    b1, s1 = pp.boxes_from_bitmap(prob, prob > 0.3, 420, 300)
+    b2, s2 = pp.boxes_from_runs(runs[::-1].copy(), 420, 300, 420, 300)
+    # quads are integers: identical; the score is the same fp64 mean summed in another order (run by run instead of
+    # cv2.mean's raster order): equal to a few ulp
+    assert b1 == b2 and 0 < len(b1) <= 5 and np.allclose(s1, s2, rtol=1e-12, atol=0)
+
+
+def test_hole_count_matches_opencv_contour_count():
+    """#contours of cv2.findContours(RETR_LIST) = #components + #holes: the invariant behind the host fallback."""
+    import cv2
+    from oracle.dbpost import post_front
+    seen_holes = 0
+    for s in range(8):
+        prob = _blob_map(200 + s, holes=True)
+        runs, comps, holes = post_front(prob, 0.3)
+        contours, _ = cv2.findContours((prob > 0.3).astype(np.uint8) * 255, cv2.RETR_LIST, cv2.CHAIN_APPROX_SIMPLE)
+        assert len(contours) == comps + holes
+        seen_holes += holes
+    assert seen_holes > 0

@@ -105,7 +105,14 @@ def _declare_parseq(lib):
     lib.ytk_parseq_last_phase_ms.argtypes = [c_void_p, c_void_p]
 
 
+class YtkDbRun(ctypes.Structure):
+    _fields_ = [("root", c_int), ("y", c_int), ("x0", c_int), ("x1", c_int), ("sum", ctypes.c_double)]
+
+
 def _declare_crops(lib):
+    lib.ytk_dbnet_post_front.restype = c_int
+    lib.ytk_dbnet_post_front.argtypes = [c_void_p, c_int, c_int, c_int, ctypes.c_float, c_void_p, c_ll, c_void_p, c_int,
+                                         c_void_p, c_void_p]
     lib.ytk_extract_crops_u8.restype = c_int
     lib.ytk_extract_crops_u8.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_ll, c_void_p, c_ll,
                                          c_void_p]

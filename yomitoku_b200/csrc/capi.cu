@@ -12,6 +12,7 @@
 #include "crop_ops.h"
 #include "dbnet_engine.h"
 #include "dbnet_ops.h"
+#include "dbpost_ops.h"
 #include "gemm_tc.h"
 #include "parseq_engine.h"
 
@@ -153,6 +154,37 @@ int ytk_op_attention_f16(const void* Q, long long ldq, long long q_rows, const v
                                        masked, static_cast<cudaStream_t>(cuda_stream), impl)
                ? YTK_ERR
                : YTK_OK;
+}
+
+static_assert(sizeof(ytk_db_run) == sizeof(ytk::DbRun), "ytk_db_run and ytk::DbRun must have one layout");
+
+int ytk_dbnet_post_front(const float* prob_dev, int n_pages, int H, int W, float thresh, void* scratch_dev,
+                         long long scratch_bytes, ytk_db_run* runs_dev, int max_runs_per_page, int32_t* meta_dev,
+                         void* cuda_stream) {
+    if (!prob_dev || !scratch_dev || !runs_dev || !meta_dev || n_pages <= 0 || H <= 0 || W <= 0 || max_runs_per_page <= 0 ||
+        (long long)H * W >= 0x7fffffffLL) {
+        ytk::set_error("ytk_dbnet_post_front: bad arguments");
+        return YTK_ERR;
+    }
+    if (scratch_bytes < ytk::dbpost_scratch_bytes(n_pages, H, W)) {
+        ytk::set_error("ytk_dbnet_post_front: scratch_dev holds %lld bytes, need %lld", scratch_bytes,
+                       ytk::dbpost_scratch_bytes(n_pages, H, W));
+        return YTK_ERR;
+    }
+    cudaPointerAttributes attr;
+    if (cudaPointerGetAttributes(&attr, prob_dev) != cudaSuccess || attr.type != cudaMemoryTypeDevice) {
+        cudaGetLastError();
+        ytk::set_error("ytk_dbnet_post_front: prob_dev is not a device pointer");
+        return YTK_ERR;
+    }
+    cudaSetDevice(attr.device);
+    if (ytk::launch_dbpost_front(prob_dev, n_pages, H, W, thresh, reinterpret_cast<int*>(scratch_dev),
+                                 reinterpret_cast<ytk::DbRun*>(runs_dev), max_runs_per_page, meta_dev,
+                                 static_cast<cudaStream_t>(cuda_stream))) {
+        ytk::set_error("ytk_dbnet_post_front: kernel launch failed");
+        return YTK_ERR;
+    }
+    return YTK_OK;
 }
 
 int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size, int limit_size, ytk_dbnet** out) {

@@ -127,6 +127,45 @@ def extract_crops_device(pages_dev, geoms, stream=None):
     return canv, total
 
 
+DB_RUN_DTYPE = np.dtype([("root", "<i4"), ("y", "<i4"), ("x0", "<i4"), ("x1", "<i4"), ("sum", "<f8")])   # = ytk_db_run
+
+
+def dbnet_post_front(prob_dev, thresh, stream=None, max_runs=32768):
+    """Device-side front half of the DBNet post-processing (C ABI ytk_dbnet_post_front, csrc/dbpost_ops.cu):
+    prob_dev (n, H, W) fp32 cuda -> per page either a DB_RUN_DTYPE array (the row runs of the 8-connected components of
+    prob > thresh, input of DBnetPostProcessor.boxes_from_runs) or None when the page has to take the host path
+    (a component with a hole, which OpenCV reports as an extra contour, or more than `max_runs` runs).  Only the runs
+    (24 bytes each; a 200-line page has ~4 k) cross PCIe instead of the 7.6 MB map.  Synchronises `stream`."""
+    if not (isinstance(prob_dev, torch.Tensor) and prob_dev.is_cuda and prob_dev.dtype == torch.float32
+            and prob_dev.dim() == 3 and prob_dev.is_contiguous()):
+        raise ValueError("dbnet_post_front: prob_dev must be a contiguous (n, H, W) float32 cuda tensor")
+    n, H, W = prob_dev.shape
+    ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(prob_dev.device)
+    with ctx:
+        labels = torch.empty((n, H, W), dtype=torch.int32, device=prob_dev.device)
+        runs = torch.empty((n, max_runs, DB_RUN_DTYPE.itemsize), dtype=torch.uint8, device=prob_dev.device)
+        meta = torch.empty((n, 4), dtype=torch.int32, device=prob_dev.device)
+        _lib.check(_lib.lib().ytk_dbnet_post_front(prob_dev.data_ptr(), n, H, W, float(thresh), labels.data_ptr(),
+                                                   labels.numel() * 4, runs.data_ptr(), max_runs, meta.data_ptr(),
+                                                   _stream_ptr(stream)))
+        meta_h = meta.cpu().numpy()                           # synchronises the stream
+        out, pending = [], []
+        for i in range(n):
+            cnt, comps, euler4, overflow = (int(v) for v in meta_h[i])
+            if overflow or cnt > max_runs or comps * 4 != euler4:
+                out.append(None)
+                continue
+            host = torch.empty((cnt, DB_RUN_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
+            host.copy_(runs[i, :cnt], non_blocking=True)
+            pending.append((i, host))
+            out.append(host)
+        if pending:
+            (torch.cuda.current_stream(prob_dev.device) if stream is None else stream).synchronize()
+        for i, host in pending:
+            out[i] = host.numpy().reshape(-1).view(DB_RUN_DTYPE)
+    return out, meta_h
+
+
 def halve_pages_device(pages_dev, stream=None):
     """One level of the source_downscale pyramid on the GPU (C ABI ytk_halve_pages_u8): (n, H, W, 3) uint8 cuda tensor ->
     (n, cvRound(H / 2), cvRound(W / 2), 3), equal to cv2.resize(page, None, fx=0.5, fy=0.5, INTER_AREA) per page."""

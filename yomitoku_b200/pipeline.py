@@ -16,6 +16,7 @@ from concurrent.futures import ProcessPoolExecutor
 import numpy as np
 
 from .data import CROP_GEOM_DTYPE, ParseqDataset, crop_records
+from .models import dbnet_post_front
 from .postprocessor import DBnetPostProcessor
 from .schemas import OCRSchema
 from .text_recognizer import plan_mini_batches
@@ -137,7 +138,11 @@ def _host_stage(args):
     if isinstance(arena, tuple):
         arena = _attach(arena)
     if quads_override is None:
-        quads, scores = _W["post"]({"binary": prob[None, None]}, page.shape[:2])
+        if isinstance(prob, _Runs):
+            # front half done on the device (csrc/dbpost_ops.cu): only the components' row runs arrived
+            quads, scores = _W["post"].boxes_from_runs(prob.runs, prob.width, prob.height, page.shape[1], page.shape[0])
+        else:
+            quads, scores = _W["post"]({"binary": prob[None, None]}, page.shape[:2])
     else:
         quads, scores = quads_override, [1.0] * len(quads_override)
     t1 = time.perf_counter()
@@ -164,6 +169,13 @@ def _host_stage(args):
             spill.append(c)
     return quads, scores, _ArenaRef(widths, spill, ds.data[0].shape[0]), ds.content_widths, len(ds), \
         (t0, t1, time.perf_counter())
+
+
+class _Runs:
+    """A page's probability map reduced on the device to the row runs of its components (models.dbnet_post_front)."""
+
+    def __init__(self, runs, height, width):
+        self.runs, self.height, self.width = runs, height, width
 
 
 class _ArenaRef:
@@ -231,6 +243,9 @@ class BatchedOCR:
         self._slot_busy = {}        # slot -> (host-stage futures, handle) of the batch that last used it
         self._last_shared = None
         self.crop_cap = 8 << 20     # arena bytes per page; doubled when a page spills
+        self.post_front_pages = 0   # pages post-processed from device runs / through the downloaded map (holes)
+        self.post_host_pages = 0
+        self.post_d2h_bytes = 0     # bytes the detector stage brought back (runs + meta, or whole maps)
 
     # ------------------------------------------------------------------------------------------ host pool
     def _get_pool(self):
@@ -802,21 +817,45 @@ class BatchedOCR:
         if pool is None:
             r = self.recognizer
             _worker_init(dict(self.detector._cfg.post_process), r._cfg, r.dynamic_width, r.source_downscale)
+        # device front half of the post-processing: the maps stay in HBM, a page's row runs (~100 KB) come back instead
+        # of its 7.6 MB map; a page with a hole in a component (or too many runs) downloads its map and takes OpenCV
+        dev_post = (pages_dev is not None and quads_override is None and getattr(self.detector, "device_post", False))
+        if dev_post:
+            import torch
+            out_dev = torch.empty(out.shape, dtype=torch.float32, device=pages_dev.device)
         futs = []
         # detection in chunks of det_batch pages; a chunk's host jobs start while the next chunk is on the device
         for s in range(0, n, self.det_batch):
             e = min(n, s + self.det_batch)
             with _span("submit.detect"):
-                self.detector.model.detect_pages_u8((stage if pages_dev is None else pages_dev)[s:e], out=out[s:e],
-                                                    stream=stream)
+                self.detector.model.detect_pages_u8((stage if pages_dev is None else pages_dev)[s:e],
+                                                    out=(out_dev if dev_post else out)[s:e], stream=stream)
+            runs = [None] * (e - s)
+            if dev_post:
+                with _span("submit.post_front"):
+                    if prob_override is not None:      # benchmarks with random detector weights: replace the maps
+                        for i in range(s, e):
+                            self._override_prob(out_dev[i], prob_override[i], stream)
+                    runs, _ = dbnet_post_front(out_dev[s:e], self.detector.post_processor.thresh, stream)
+                    self.post_front_pages += sum(r is not None for r in runs)
+                    self.post_host_pages += sum(r is None for r in runs)
+                    self.post_d2h_bytes += 16 * (e - s) + sum(r.nbytes for r in runs if r is not None)
+                    for i in range(s, e):
+                        if runs[i - s] is None:
+                            out[i].copy_(out_dev[i])      # pageable or pinned host row; synchronous
+                            self.post_d2h_bytes += out[i].numel() * 4
+            else:
+                self.post_d2h_bytes += out[s:e].numel() * 4
             for i in range(s, e):
                 qo = None if quads_override is None else quads_override[i]
-                if sh is None:
-                    job = (pages[i], prob[i] if prob_override is None else prob_override[i], qo)
+                if runs[i - s] is not None:
+                    job = (("shape", h0, w0), _Runs(runs[i - s], out.shape[1], out.shape[2]), qo, None, "geom")
+                elif sh is None:
+                    job = (pages[i], prob[i] if (prob_override is None or dev_post) else prob_override[i], qo)
                     if pages_dev is not None:
                         job = (("shape", h0, w0), job[1], qo, None, "geom")
                 elif pages_dev is not None:
-                    if prob_override is not None:
+                    if prob_override is not None and not dev_post:
                         np.copyto(prob[i], prob_override[i])
                     job = (("shape", h0, w0), ob.desc(i * prob[i].nbytes, prob[i].shape, np.float32), qo, None, "geom")
                 else:
@@ -832,6 +871,17 @@ class BatchedOCR:
         handle = _Handle(futs, arena, cap, pages_dev)
         self._slot_busy[self._slot] = (futs, handle)
         return handle
+
+    @staticmethod
+    def _override_prob(dst, src, stream=None):
+        """dst (Hn, Wn) fp32 cuda <- src (numpy array or tensor on either side), asynchronous on `stream`."""
+        import torch
+        t = src if isinstance(src, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(src, dtype=np.float32))
+        if stream is not None:
+            with torch.cuda.stream(stream):
+                dst.copy_(t, non_blocking=True)
+        else:
+            dst.copy_(t, non_blocking=True)
 
     def _upload_pages(self, stage, stream=None):
         """(n, H0, W0, 3) uint8 staging tensor -> the same pages in HBM of the detector's device (asynchronous on
