@@ -558,6 +558,8 @@ def main():
             "exchange": {"bytes_sent_per_step_all_ranks": xbytes_all / args.steps,
                          "ms_per_step_max_rank": float(cmax[2].item()) / args.steps,
                          "calls_per_step": x_value["exchange_calls"] / args.steps,
+                         "plan_ms_per_step_rank0": x_value.get("plan_ms", 0.0) / args.steps,
+                         "results_ms_per_step_rank0": x_value.get("results_ms", 0.0) / args.steps,
                          "path": "device uint8 canvases, ONE torch.distributed all_to_all_single over NCCL per step (no host "
                                  "staging); costs / assignment / descriptors and the returned ids / probabilities travel over "
                                  "host-side gloo groups; ms = host time around the enqueue"},

@@ -86,6 +86,7 @@ class _StubModel:
 
     def __init__(self, cfg):
         self.cfg = cfg
+        self.calls = 0
 
     def pack_crops(self, canvases, padded, groups):
         return canvases, sum(c.size for c in canvases), None, 0
@@ -96,6 +97,7 @@ class _StubModel:
 
     def run_packed_ptr(self, ptr, on_device, total, descs, n, n_groups, stream=None):
         import ctypes
+        self.calls += 1
         raw = np.ctypeslib.as_array(ctypes.cast(ptr, ctypes.POINTER(ctypes.c_uint8)), shape=(total,))
         canv = [raw[int(d["pix_off"]):int(d["pix_off"]) + 32 * int(d["w"]) * 3].reshape(32, int(d["w"]), 3)
                 for d in descs]
@@ -197,10 +199,13 @@ def _worker_pipeline_dev(rank, world, port, q):
         moved = []
         orig_x = par_mod.exchange_canvases_planned
 
-        def spy(canv, send_splits, recv_splits):
+        def spy(canv, send_splits, recv_splits, out=None):
             assert isinstance(canv, torch.Tensor) and canv.dtype == torch.uint8     # one flat buffer, never host lists
+            # the receive buffer is the tail of the recognizer's work buffer: own and received crops go through ONE
+            # packed recognizer call
+            assert out is not None and out.numel() == sum(recv_splits)
             moved.append(([int(b) for b in send_splits], [int(b) for b in recv_splits]))
-            return orig_x(canv, send_splits, recv_splits)
+            return orig_x(canv, send_splits, recv_splits, out=out)
 
         par_mod.exchange_canvases_planned = spy
         par_mod.exchange_groups = None              # the host-staged scatter must not be used any more
@@ -208,7 +213,9 @@ def _worker_pipeline_dev(rank, world, port, q):
         lv = np.zeros(len(geoms), np.int64)
         dplan = ocr._plan_groups_dist(groups, geoms, lv)
         assert dplan["moves"] and (rank != 0 or len(dplan["send"]) > 0)     # rank 0 (8 groups) must hand some over
+        calls0 = Rec.model.calls
         pending = ocr._run_groups_dist_dev(groups, geoms, np.ascontiguousarray(page)[None], None, lv, dplan)
+        assert Rec.model.calls - calls0 == 1          # own + received groups: one packed call
         res = ocr._finish_results(pending)
         for (ids, probs, glen), (eid, ep) in zip(res, expect):
             assert np.array_equal(ids, eid) and np.array_equal(probs, ep) and glen == 101

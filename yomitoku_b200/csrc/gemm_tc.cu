@@ -1182,6 +1182,7 @@ namespace {
 struct ProfRec {
     cudaEvent_t a, b;
     double flops;
+    int pixels, cout, k, block_n, cluster, mode, act, resid, out_f32, ntaps;   // shape of the launch (YTK_GEMM_DUMP)
 };
 std::mutex g_prof_mu;
 bool g_prof_on = false;
@@ -1226,11 +1227,23 @@ int gemm_profile_end(double* flops, double* ms, long long* launches) {
     if (flops) *flops = f;
     if (ms) *ms = t;
     if (launches) *launches = (long long)g_prof.size();
+    if (const char* path = getenv("YTK_GEMM_DUMP")) {      // per-launch table of the window for shape-level analysis
+        if (FILE* fp = fopen(path, "a")) {
+            fprintf(fp, "pixels,cout,k,ntaps,block_n,cluster,mode,act,resid,out_f32,flops,ms\n");
+            for (ProfRec& r : g_prof) {
+                float e = 0.f;
+                cudaEventElapsedTime(&e, r.a, r.b);
+                fprintf(fp, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.0f,%.6f\n", r.pixels, r.cout, r.k, r.ntaps, r.block_n,
+                        r.cluster, r.mode, r.act, r.resid, r.out_f32, r.flops, e);
+            }
+            fclose(fp);
+        }
+    }
     return 0;
 }
 
 int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream) {
-    ProfRec rec{nullptr, nullptr, 0};
+    ProfRec rec{};
     bool prof = false;
     if (g_prof_on) {
         std::lock_guard<std::mutex> lk(g_prof_mu);
@@ -1238,6 +1251,17 @@ int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream) {
             rec.a = prof_event();
             rec.b = prof_event();
             rec.flops = plan->flops;
+            const GemmArgs& g = plan->args;
+            rec.pixels = g.Ho * g.Wo * g.n_img;
+            rec.cout = g.Cout;
+            rec.k = g.kpt * 64;
+            rec.ntaps = g.ntaps;
+            rec.block_n = plan->block_n;
+            rec.cluster = g.cluster;
+            rec.mode = g.mode;
+            rec.act = g.act;
+            rec.resid = g.resid ? (g.resid_f32 ? 2 : 1) : 0;
+            rec.out_f32 = g.out_f32;
             prof = true;
         }
     }

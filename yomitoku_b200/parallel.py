@@ -84,7 +84,8 @@ def _all_to_all_bytes(send_chunks):
     return out
 
 
-STATS = {"exchange_calls": 0, "exchange_bytes_sent": 0, "exchange_bytes_received": 0, "exchange_ms": 0.0}
+STATS = {"exchange_calls": 0, "exchange_bytes_sent": 0, "exchange_bytes_received": 0, "exchange_ms": 0.0,
+         "plan_ms": 0.0, "results_ms": 0.0}     # host time inside the control-plane collectives (includes waiting for peers)
 
 _META = {}
 
@@ -103,17 +104,24 @@ def meta_group(which):
 
 def all_gather_objects(obj, which):
     """all_gather of one picklable object per rank over the `which` meta group -> list indexed by rank."""
+    import time
+    t0 = time.perf_counter()
     out = [None] * dist.get_world_size()
     dist.all_gather_object(out, obj, group=meta_group(which))
+    STATS[which + "_ms"] = STATS.get(which + "_ms", 0.0) + (time.perf_counter() - t0) * 1e3
     return out
 
 
-def exchange_canvases_planned(canv, send_splits, recv_splits):
+def exchange_canvases_planned(canv, send_splits, recv_splits, out=None):
     """The crop scatter proper, with split sizes already agreed on by the planners: ONE all_to_all_single of device uint8
-    canvases over NCCL / NVLink (CPU tensors under gloo).  Returns the flat receive buffer (ordered by source rank)."""
+    canvases over NCCL / NVLink (CPU tensors under gloo).  Returns the flat receive buffer (ordered by source rank);
+    `out` = where to receive (e.g. the tail of the recognizer's work buffer)."""
     import time
     t0 = time.perf_counter()
-    recv = torch.empty(int(sum(recv_splits)), dtype=torch.uint8, device=canv.device)
+    recv = torch.empty(int(sum(recv_splits)), dtype=torch.uint8, device=canv.device) if out is None else out
+    if recv.numel() != int(sum(recv_splits)):
+        raise ValueError("exchange_canvases_planned: receive buffer has %d bytes, the plan says %d"
+                         % (recv.numel(), int(sum(recv_splits))))
     dist.all_to_all_single(recv, canv[: int(sum(send_splits))], output_split_sizes=[int(v) for v in recv_splits],
                            input_split_sizes=[int(v) for v in send_splits])
     STATS["exchange_calls"] += 1
@@ -121,6 +129,24 @@ def exchange_canvases_planned(canv, send_splits, recv_splits):
     STATS["exchange_bytes_received"] += int(sum(recv_splits))
     STATS["exchange_ms"] += (time.perf_counter() - t0) * 1e3
     return recv
+
+
+def exchange_results_planned(send, send_splits, recv_splits):
+    """The way back of the crop scatter: ids / probabilities of the groups recognised for other ranks, as ONE
+    all_to_all_single of host bytes over the "results" gloo group (the results are on the host already: the recognizer
+    call ends with their D2H copy), byte counts agreed on by the planners.  send: flat uint8 numpy array ordered by
+    destination rank.  Returns the flat uint8 numpy receive buffer ordered by source rank."""
+    import time
+    t0 = time.perf_counter()
+    if send.size != int(sum(send_splits)):
+        raise ValueError("exchange_results_planned: %d bytes to send, the plan says %d" % (send.size, int(sum(send_splits))))
+    recv = torch.empty(int(sum(recv_splits)), dtype=torch.uint8)
+    dist.all_to_all_single(recv, torch.from_numpy(np.ascontiguousarray(send)),
+                           output_split_sizes=[int(v) for v in recv_splits],
+                           input_split_sizes=[int(v) for v in send_splits], group=meta_group("results"))
+    STATS["results_ms"] += (time.perf_counter() - t0) * 1e3
+    STATS["results_bytes_sent"] = STATS.get("results_bytes_sent", 0) + int(send.size)
+    return recv.numpy()
 
 
 def _pack_group(canvases, padded, gid):

@@ -467,15 +467,40 @@ class BatchedOCR:
                 foreign.append((w, wp, base + offs))
                 work.append((src, int(gid)))
             base += int(d["bytes"])
-        return {"dist": True, "moves": True, "mine": mine,
-                "mine_plan": self._plan_groups_dev([groups[k] for k in mine], geoms, levels) if mine else [],
-                "send": send, "send_splits": send_splits, "recv_splits": recv_splits, "foreign": foreign,
-                "foreign_work": work, "n_groups": len(groups), "away": {k: assign[k] for k in range(len(groups))
-                                                                        if assign[k] != rank}}
+        # ONE packed recognizer call for own + received groups: a single work buffer [own canvases | received canvases]
+        # (two calls would run the 101-step decode loop twice, and its cost is mostly per step, not per row)
+        mine_total, mine_sel, mine_lv, unified, owner = 0, None, None, [], []
+        if mine:
+            idx = np.concatenate([groups[k][2] for k in mine])
+            mine_sel, mine_lv = geoms[idx].copy(), levels[idx]
+            mine_total, offs = plan_crop_offsets(mine_sel, mine_lv)
+            j = 0
+            for k in mine:
+                m = len(groups[k][0])
+                unified.append((np.asarray(groups[k][0], np.int64), np.asarray(groups[k][1], np.int64), offs[j:j + m]))
+                owner.append((rank, k))
+                j += m
+        unified += [(w, wp, mine_total + offs) for w, wp, offs in foreign]
+        owner += work
+        # phase 3 is planned here too: a group's result is m rows of (S int32 ids, S float32 probabilities) + its int32
+        # decode length, so every rank knows the byte counts of the result exchange before anything runs
+        S = int(self.recognizer.model.max_label_length) + 1
+        back_splits, expect_splits, expect = [0] * world, [0] * world, {}
+        for (src, _), (w, _, _) in zip(work, foreign):
+            back_splits[src] += len(w) * S * 8 + 4
+        for k in range(len(groups)):
+            if assign[k] != rank:
+                expect.setdefault(assign[k], []).append((k, len(groups[k][0])))
+                expect_splits[assign[k]] += len(groups[k][0]) * S * 8 + 4
+        return {"dist": True, "moves": True, "mine_sel": mine_sel, "mine_lv": mine_lv, "mine_total": mine_total,
+                "send": send, "send_splits": send_splits, "recv_splits": recv_splits, "unified": unified,
+                "owner": owner, "n_groups": len(groups),
+                "results": {"S": S, "back_splits": back_splits, "expect_splits": expect_splits, "expect": expect}}
 
     def _run_groups_dist_dev(self, groups, geoms, pages_dev, stream, levels, dplan):
         """Phase 2 (device): returns a `_PendingResults` (own groups done, results of foreign groups to hand back)."""
         import torch
+        import torch.distributed as dist
         from . import parallel as par
         from .models import concat_device_buffers, extract_crops_pyramid
         pages = pages_dev if isinstance(pages_dev, dict) else {0: pages_dev}
@@ -483,6 +508,7 @@ class BatchedOCR:
             return _PendingResults(self._run_groups_dev_local(groups, geoms, pages, stream, levels, dplan["plan"]), None,
                                    None)
         cfg = self.recognizer._cfg
+        rank = dist.get_rank()
         ctx = torch.cuda.stream(stream) if stream is not None else _NullCtx()
         with ctx:
             parts = []
@@ -490,25 +516,30 @@ class BatchedOCR:
                 canv_d, total_d, _ = extract_crops_pyramid(pages, sel, lvs, stream)
                 assert total_d == total
                 parts.append((canv_d, total_d))
+            some = next(iter(pages.values()))
+            device = getattr(some, "device", "cpu")
             if parts:
                 canv = concat_device_buffers(parts, stream)
                 if len(parts) == 1:
                     canv = canv[: parts[0][1]]
             else:
-                some = next(iter(pages.values()))
-                canv = torch.empty(0, dtype=torch.uint8, device=getattr(some, "device", "cpu"))
-            recv = par.exchange_canvases_planned(canv, dplan["send_splits"], dplan["recv_splits"])
-        mine = dplan["mine"]
-        res = self._run_groups_dev_local([groups[k] for k in mine], geoms, pages, stream, levels,
-                                         dplan["mine_plan"]) if mine else []
-        out = [None] * dplan["n_groups"]
-        for k, r in zip(mine, res):
-            out[k] = r
-        back = []
-        if dplan["foreign"]:
-            fres = self._run_groups_buf(dplan["foreign"], recv, cfg.data.img_size[0], stream)
-            back = [(src, gid, ids, probs, glen) for (src, gid), (ids, probs, glen) in zip(dplan["foreign_work"], fres)]
-        return _PendingResults(out, back, dplan["away"])
+                canv = torch.empty(0, dtype=torch.uint8, device=device)
+            mine_total = dplan["mine_total"]
+            work = torch.empty(mine_total + int(sum(dplan["recv_splits"])), dtype=torch.uint8, device=device)
+            if mine_total:
+                own, total_m, _ = extract_crops_pyramid(pages, dplan["mine_sel"], dplan["mine_lv"], stream)
+                assert total_m == mine_total
+                work[:mine_total].copy_(own[:mine_total], non_blocking=True)
+                del own
+            par.exchange_canvases_planned(canv, dplan["send_splits"], dplan["recv_splits"], out=work[mine_total:])
+        res = self._run_groups_buf(dplan["unified"], work, cfg.data.img_size[0], stream) if dplan["unified"] else []
+        out, back = [None] * dplan["n_groups"], []
+        for (src, gid), (ids, probs, glen) in zip(dplan["owner"], res):
+            if src == rank:
+                out[gid] = (ids, probs, glen)
+            else:
+                back.append((src, gid, ids, probs, glen))
+        return _PendingResults(out, back, dplan["results"])
 
     def _finish_results(self, pending):
         """Phase 3 (host; collectives on the "results" gloo group): results of the groups this rank sent away."""
@@ -517,14 +548,26 @@ class BatchedOCR:
         if pending.back is None:
             return pending.out
         from . import parallel as par
-        import torch.distributed as dist
-        rank = dist.get_rank()
-        outgoing = {}
-        for src, gid, ids, probs, glen in pending.back:
-            outgoing.setdefault(src, []).append((gid, np.ascontiguousarray(ids), np.ascontiguousarray(probs), int(glen)))
-        for everyone in par.all_gather_objects(outgoing, "results"):
-            for gid, ids, probs, glen in everyone.get(rank, []):
-                pending.out[gid] = (ids, probs, glen)
+        rp = pending.plan
+        S = rp["S"]
+        parts = []
+        for src, gid, ids, probs, glen in pending.back:           # grouped by source rank, ascending (the plan's order)
+            if ids.shape[1] != S:
+                raise RuntimeError("result exchange: rows of %d positions, the plan says %d" % (ids.shape[1], S))
+            parts += [np.ascontiguousarray(ids, np.int32).reshape(-1).view(np.uint8),
+                      np.ascontiguousarray(probs, np.float32).reshape(-1).view(np.uint8),
+                      np.array([glen], np.int32).view(np.uint8)]
+        send = np.concatenate(parts) if parts else np.zeros(0, np.uint8)
+        recv = par.exchange_results_planned(send, rp["back_splits"], rp["expect_splits"])
+        off = 0
+        for dst in sorted(rp["expect"]):
+            for k, m in rp["expect"][dst]:
+                nb = m * S * 4
+                ids = recv[off:off + nb].view(np.int32).reshape(m, S)
+                probs = recv[off + nb:off + 2 * nb].view(np.float32).reshape(m, S)
+                glen = int(recv[off + 2 * nb:off + 2 * nb + 4].view(np.int32)[0])
+                pending.out[k] = (ids, probs, glen)
+                off += 2 * nb + 4
         missing = [k for k, r in enumerate(pending.out) if r is None]
         if missing:
             raise RuntimeError("crop scatter: no result came back for groups %s" % missing[:8])
@@ -1206,8 +1249,8 @@ class _PendingResults:
     """Phase-2 output of the multi-rank recognizer call: `out[k]` = (ids, probs, group_len) of the groups recognised
     here (None for the ones sent away), `back` = results this rank owes to other ranks (None: nothing moved at all)."""
 
-    def __init__(self, out, back, away):
-        self.out, self.back, self.away = out, back, away
+    def __init__(self, out, back, plan):
+        self.out, self.back, self.plan = out, back, plan
 
 
 class _NullCtx:
