@@ -117,3 +117,15 @@ def test_detector_call_contract(det):
     small = np.ascontiguousarray(page[:300, :420])
     res2, _ = det(small)
     assert isinstance(res2.points, list)
+
+
+def test_forward_is_deterministic(det):
+    """Two forwards of the same pages return the same bits (the ASF channel means are summed in a fixed order), alone
+    and as part of a larger batch."""
+    pages = np.stack([synthetic_page(80 + i)[0] for i in range(3)])
+    t = torch.from_numpy(pages).cuda()
+    a = det.model.detect_pages_u8(t).cpu()
+    b = det.model.detect_pages_u8(t).cpu()
+    assert torch.equal(a, b)
+    c = det.model.detect_pages_u8(t[1:2]).cpu()
+    assert torch.equal(a[1:2], c)

@@ -377,7 +377,7 @@ int DbnetEngine::build(const DbnetModel& m, int n, int Hn_, int Wn_) {
     void *asf_a, *gsum, *gvec, *gmean, *mmap;
     if (alloc("asf_a", N, H4, W4, 64, false, &asf_a)) return 1;
     if (add_conv(m.asf_conv, fuse, N, H4, W4, 256, asf_a, 64, ACT_NONE)) return 1;
-    CK(cudaMalloc(&gsum, sizeof(float) * 64 * N));
+    CK(cudaMalloc(&gsum, sizeof(float) * 64 * kAsfPoolChunks * N));
     CK(cudaMalloc(&gvec, sizeof(float) * 64 * N));
     CK(cudaMalloc(&gmean, sizeof(float) * N));
     bufs.push_back(gsum);

@@ -218,7 +218,7 @@ int launch_upsample(const void* src, int n_img, int Hs, int Ws, int C, void* dst
 
 // ------------------------------------------------------------------------------------------------------------------
 // Adaptive Scale Fusion attention (reference dbnet_feature_attention.py:69-79 and :150-160) after its 3x3 conv.
-//   pass 1  asf_pool:    per-image channel sums of a = conv(fuse)   -> gsum[N,64]   (AdaptiveAvgPool2d(1))
+//   pass 1  asf_pool:    per-image, per-chunk channel sums of a = conv(fuse) -> gsum[N,64 chunks,64] (AdaptiveAvgPool2d(1))
 //   pass 2  asf_gate:    g = sigmoid(W2 relu(W1 mean))              -> gvec[N,64], gmean[N]
 //   pass 3  asf_cmean:   m[h,w] = mean_c(a + g)                     -> m[N,H,W] fp32
 //   pass 4  asf_apply:   s = sigmoid(w1x1 * relu(conv3x3(m))); z = s + a + g; score = sigmoid(Watt z) (4);
@@ -244,16 +244,21 @@ __global__ void asf_pool_kernel(const uint4* __restrict__ a, int HW, float* __re
     if (threadIdx.x < 64) {
         float s = 0.f;
         for (int i = 0; i < 32; ++i) s += red[i][threadIdx.x];
-        atomicAdd(gsum + img * 64 + threadIdx.x, s);
+        // one partial per (image, chunk): summed in a fixed order by asf_gate_kernel - the forward is deterministic
+        gsum[((size_t)img * gridDim.x + blockIdx.x) * 64 + threadIdx.x] = s;
     }
 }
 
-__global__ void asf_gate_kernel(const float* __restrict__ gsum, int HW, const float* __restrict__ w1 /*16x64*/,
+__global__ void asf_gate_kernel(const float* __restrict__ gsum, int chunks, int HW, const float* __restrict__ w1 /*16x64*/,
                                 const float* __restrict__ w2 /*64x16*/, float* __restrict__ gvec,
                                 float* __restrict__ gmean) {
     const int img = blockIdx.x;
     __shared__ float mean[64], hid[16], g[64];
-    if (threadIdx.x < 64) mean[threadIdx.x] = gsum[img * 64 + threadIdx.x] / (float)HW;
+    if (threadIdx.x < 64) {
+        float s = 0.f;
+        for (int c = 0; c < chunks; ++c) s += gsum[((size_t)img * chunks + c) * 64 + threadIdx.x];
+        mean[threadIdx.x] = s / (float)HW;
+    }
     __syncthreads();
     if (threadIdx.x < 16) {
         float s = 0.f;
@@ -360,10 +365,9 @@ int launch_asf(const void* a, void* fuse, int n_img, int H, int W, const float* 
                const float* host_sp3, float host_sp1, const float* host_att, float* gsum, float* gvec, float* gmean,
                float* m, cudaStream_t st) {
     const int HW = H * W;
-    cudaMemsetAsync(gsum, 0, sizeof(float) * 64 * n_img, st);
-    dim3 g1(64, n_img);
+    dim3 g1(kAsfPoolChunks, n_img);                    // gsum: [n_img][kAsfPoolChunks][64] partial channel sums
     asf_pool_kernel<<<g1, 256, 0, st>>>(reinterpret_cast<const uint4*>(a), HW, gsum);
-    asf_gate_kernel<<<n_img, 64, 0, st>>>(gsum, HW, w1_dev, w2_dev, gvec, gmean);
+    asf_gate_kernel<<<n_img, 64, 0, st>>>(gsum, kAsfPoolChunks, HW, w1_dev, w2_dev, gvec, gmean);
     const long long npix = (long long)n_img * HW;
     const long long thr = npix * 8;
     asf_cmean_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4*>(a), npix, HW, gmean,

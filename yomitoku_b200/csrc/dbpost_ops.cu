@@ -13,9 +13,9 @@
 // Components with holes produce extra (hole) contours in OpenCV; the kernels count holes with the Euler number
 // (#holes = #components - E8) and the caller falls back to the host path for such a page, so the result is exact always.
 //
-// Kernels: label_init / label_merge / label_flatten (union-find CCL, root = smallest raster index = first pixel),
-// page_stats (components, 2x2 bit-quad counts for the Euler number), emit_runs (one record per row run: root, row,
-// first / last column, sum of prob in fp64).  HBM-bound byte work: the map is read ~4 times (30 MB per page).
+// Kernels: label_seed / label_merge (union-find CCL over 32-pixel chunk runs, root = smallest raster index = first
+// pixel), page_stats (components, 2x2 bit-quad counts for the Euler number), emit_runs (one record per row run: root,
+// row, first / last column, sum of prob in fp64).  HBM-bound byte work: map + labels are read ~4 times (30 MB per page).
 #include "dbpost_ops.h"
 
 #include "gemm_tc.h"
@@ -50,12 +50,25 @@ __device__ __forceinline__ void uf_union(int* lab, int a, int b) {
     }
 }
 
-// labels are PER PAGE raster indices (page offset subtracted) so that a root is the component's first pixel
-__global__ void label_seed_kernel(const float* __restrict__ prob, float thresh, int* __restrict__ lab, int HW,
+// labels are PER PAGE raster indices (page offset subtracted) so that a root is the component's first pixel.
+// Seed: a warp looks at 32 consecutive pixels; every foreground pixel starts as a child of the first pixel of its row run
+// INSIDE that 32-pixel chunk (one ballot, no memory traffic), so the merge pass only has to join chunk runs with each
+// other - a text line blob of 400 x 25 pixels costs ~400 unions instead of 10 000 long pointer chases.
+__global__ void label_seed_kernel(const float* __restrict__ prob, float thresh, int* __restrict__ lab, int HW, int W,
                                   long long total) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    lab[i] = prob[i] > thresh ? (int)(i % HW) : -1;
+    const bool in = i < total;
+    const bool fg = in && prob[i] > thresh;
+    const unsigned mask = __ballot_sync(0xffffffffu, fg);
+    if (!in) return;
+    const int lane = threadIdx.x & 31;
+    const int p = (int)(i % HW);
+    const int x = p % W;
+    const unsigned below = ~mask & ((1u << lane) - 1u);            // background lanes in front of this one
+    int start = below ? 32 - __clz(below) : 0;                      // first lane of this lane's run in the chunk
+    const int row_first = lane - (lane < x ? lane : x);             // lanes before it belong to the previous row (or page)
+    if (start < row_first) start = row_first;
+    lab[i] = fg ? p - (lane - start) : -1;
 }
 
 __global__ void label_merge_kernel(int* __restrict__ lab, int H, int W, long long total) {
@@ -66,21 +79,20 @@ __global__ void label_merge_kernel(int* __restrict__ lab, int H, int W, long lon
     const int p = (int)(i % HW);
     if (page[p] < 0) return;
     const int y = p / W, x = p - y * W;
-    // 8-connectivity: the four neighbours that precede p in raster order
-    if (x > 0 && page[p - 1] >= 0) uf_union(page, p, p - 1);
-    if (y > 0) {
-        if (page[p - W] >= 0) uf_union(page, p, p - W);
-        if (x > 0 && page[p - W - 1] >= 0) uf_union(page, p, p - W - 1);
-        if (x + 1 < W && page[p - W + 1] >= 0) uf_union(page, p, p - W + 1);
+    const bool left = x > 0 && page[p - 1] >= 0;
+    // a run that continues across a chunk border: join the two chunk runs
+    if (left && (threadIdx.x & 31) == 0) uf_union(page, p, p - 1);
+    if (y == 0) return;
+    // 8-connectivity with the row above; unions that follow from row adjacency of already joined pixels are skipped
+    const bool up = page[p - W] >= 0;
+    const bool ul = x > 0 && page[p - W - 1] >= 0;
+    const bool ur = x + 1 < W && page[p - W + 1] >= 0;
+    if (up) {
+        if (!(left && ul)) uf_union(page, p, p - W);               // else: p - left - ul - up are joined already
+    } else {
+        if (ul && !left) uf_union(page, p, p - W - 1);             // else: left joins ul (it is left's `up`)
+        if (ur) uf_union(page, p, p - W + 1);
     }
-}
-
-__global__ void label_flatten_kernel(int* __restrict__ lab, int HW, long long total) {
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= total) return;
-    int* page = lab + (i / HW) * (long long)HW;
-    const int p = (int)(i % HW);
-    if (page[p] >= 0) page[p] = uf_find(page, p);
 }
 
 // meta[page] = {runs, components, 4 * E8 accumulator (Q1 - Q3 - 2 QD), overflow}
@@ -128,7 +140,7 @@ __global__ void emit_runs_kernel(const float* __restrict__ prob, const int* __re
         return;
     }
     DbRun r;
-    r.root = pg[p];
+    r.root = uf_find(pg, p);                              // labels are never flattened: only run starts need their root
     r.y = y;
     r.x0 = x;
     r.x1 = x1 - 1;
@@ -147,13 +159,12 @@ int launch_dbpost_front(const float* prob, int n_pages, int H, int W, float thre
     const int threads = 256;
     const unsigned grid = (unsigned)((total + threads - 1) / threads);
     if (cudaMemsetAsync(meta, 0, sizeof(int) * 4 * n_pages, st) != cudaSuccess) return 1;
-    label_seed_kernel<<<grid, threads, 0, st>>>(prob, thresh, labels, H * W, total);
+    label_seed_kernel<<<grid, threads, 0, st>>>(prob, thresh, labels, H * W, W, total);
     label_merge_kernel<<<grid, threads, 0, st>>>(labels, H, W, total);
-    label_flatten_kernel<<<grid, threads, 0, st>>>(labels, H * W, total);
     const long long total_q = (long long)n_pages * (H + 1) * (W + 1);
     page_stats_kernel<<<(unsigned)((total_q + threads - 1) / threads), threads, 0, st>>>(labels, H, W, meta, total_q);
     emit_runs_kernel<<<grid, threads, 0, st>>>(prob, labels, H, W, runs, max_runs, meta, total);
-    count_launch(5);
+    count_launch(4);
     return cudaGetLastError() != cudaSuccess;
 }
 

@@ -87,13 +87,7 @@ __device__ __noinline__ void copy_elems(void* dst, const void* src, int n, int e
     else
         for (int e = 0; e < n; ++e) reinterpret_cast<uint16_t*>(dst)[e] = reinterpret_cast<const uint16_t*>(src)[e];
 }
-// GELU(x) = 0.5 x (1 + erf(x / sqrt 2)) (torch.nn.GELU default, "exact") with erf from Abramowitz-Stegun 7.1.26
-// (|error| < 1.5e-7, i.e. below fp32 rounding of the surrounding arithmetic): one ex2 + one rcp + 7 FMAs, small
-// enough to inline 32x into the epilogue without blowing the instruction cache the way erff() does.
-// Two GELUs at once on the packed fp32x2 pipe (FFMA2 / FMUL2, sm_100): the epilogue of the fc1 GEMM is issue-bound,
-// and this form needs ~10 instead of ~19 instructions per element.  Phi(x) = x >= 0 ? 1 - h : h with
-// h = 0.5 * poly(t) * t * exp(-z^2), z = |x| / sqrt 2, t = 1 / (1 + 0.3275911 z); the last step uses
-// x * Phi(x) = x*h + max(x, 0) * (1 - 2h), which needs no select.
+// Packed fp32x2 helpers (FFMA2 / FMUL2, sm_100) for the GELU below: two values per instruction.
 using f32x2 = unsigned long long;
 __device__ __forceinline__ f32x2 pk2(float a, float b) {
     f32x2 r;
@@ -111,27 +105,25 @@ __device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
     return r;
 }
+// Exact (erf) GELU of two values, fp32, max |error| 5e-7 (2.8e-7 for |x| < 3; the form it replaces, Abramowitz-Stegun
+// 7.1.26, had 0.5 |x| 1.5e-7):
+//     GELU(x) = max(x, 0) - 0.5 t erfc(t / sqrt 2),   t = min(|x|, 5.7),   erfc(t / sqrt 2) = 2 ^ (t P(t))
+// P = degree-6 weighted minimax fit (experiments/gelu_fit.py).  One ex2 per element, no reciprocal, 7 packed FMAs per
+// pair: the fc1 epilogue is bound by instruction issue (profiles/README_r01.md), this form needs ~20 instructions per
+// pair instead of ~35.
 __device__ __forceinline__ void gelu_fast2(float& x0, float& x1) {
-    const f32x2 x = pk2(x0, x1);
-    // |x| is clamped at 1e4 (erf is 1 and exp(-z^2) is 0 in fp32 long before): keeps the shared reciprocal below finite
-    const f32x2 z = mul2(pk2(fminf(fabsf(x0), 1e4f), fminf(fabsf(x1), 1e4f)),
-                         pk2(0.70710678118654752440f, 0.70710678118654752440f));
-    float d0, d1, rq;
-    upk2(fma2(pk2(0.3275911f, 0.3275911f), z, pk2(1.f, 1.f)), d0, d1);   // in [1, 2400]
-    // one reciprocal for both: 1/d0 = d1 / (d0 d1), 1/d1 = d0 / (d0 d1) - the epilogue is bound by the MUFU pipe
-    // (one ex2 + one rcp per element), this takes it to 1.5 per element for three FMULs
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rq) : "f"(d0 * d1));
-    const f32x2 t = mul2(pk2(d1, d0), pk2(rq, rq));
-    f32x2 p = fma2(pk2(0.5307027145f, 0.5307027145f), t, pk2(-0.7265760135f, -0.7265760135f));
-    p = fma2(p, t, pk2(0.7107068705f, 0.7107068705f));
-    p = fma2(p, t, pk2(-0.142248368f, -0.142248368f));
-    p = fma2(p, t, pk2(0.127414796f, 0.127414796f));
+    const f32x2 t = pk2(fminf(fabsf(x0), 5.7f), fminf(fabsf(x1), 5.7f));
+    f32x2 p = fma2(pk2(4.278742836e-06f, 4.278742836e-06f), t, pk2(-1.279820572e-05f, -1.279820572e-05f));
+    p = fma2(p, t, pk2(-5.757861654e-04f, -5.757861654e-04f));
+    p = fma2(p, t, pk2(7.670783438e-03f, 7.670783438e-03f));
+    p = fma2(p, t, pk2(-5.294856429e-02f, -5.294856429e-02f));
+    p = fma2(p, t, pk2(-4.590439200e-01f, -4.590439200e-01f));
+    p = fma2(p, t, pk2(-1.151126981e+00f, -1.151126981e+00f));
     float a0, a1, e0, e1;
-    upk2(mul2(z, mul2(z, pk2(-1.4426950408889634f, -1.4426950408889634f))), a0, a1);
+    upk2(mul2(p, t), a0, a1);
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(a0));
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(a1));
-    const f32x2 h = mul2(mul2(p, t), pk2(e0, e1));
-    const f32x2 r = fma2(pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)), fma2(h, pk2(-2.f, -2.f), pk2(1.f, 1.f)), mul2(x, h));
+    const f32x2 r = fma2(mul2(t, pk2(-0.5f, -0.5f)), pk2(e0, e1), pk2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
     upk2(r, x0, x1);
 }
 

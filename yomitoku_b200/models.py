@@ -10,6 +10,7 @@ Reference: src/yomitoku/models/dbnet_plus.py:233-246, src/yomitoku/models/parseq
 """
 import ctypes
 import math
+import threading
 from collections import OrderedDict
 
 import numpy as np
@@ -130,40 +131,53 @@ def extract_crops_device(pages_dev, geoms, stream=None):
 DB_RUN_DTYPE = np.dtype([("root", "<i4"), ("y", "<i4"), ("x0", "<i4"), ("x1", "<i4"), ("sum", "<f8")])   # = ytk_db_run
 
 
+_POST_BUFS = {}                      # (device, n, H, W, max_runs) -> device scratch + page-locked staging, reused
+_POST_LOCK = threading.Lock()
+
+
 def dbnet_post_front(prob_dev, thresh, stream=None, max_runs=32768):
     """Device-side front half of the DBNet post-processing (C ABI ytk_dbnet_post_front, csrc/dbpost_ops.cu):
     prob_dev (n, H, W) fp32 cuda -> per page either a DB_RUN_DTYPE array (the row runs of the 8-connected components of
     prob > thresh, input of DBnetPostProcessor.boxes_from_runs) or None when the page has to take the host path
     (a component with a hole, which OpenCV reports as an extra contour, or more than `max_runs` runs).  Only the runs
-    (24 bytes each; a 200-line page has ~4 k) cross PCIe instead of the 7.6 MB map.  Synchronises `stream`."""
+    (24 bytes each; a 200-line page has ~4 k) cross PCIe instead of the 7.6 MB map.  Synchronises `stream`.
+    Returns (runs per page, meta (n, 4) int32 = {runs, components, 4 x Euler number, overflow})."""
     if not (isinstance(prob_dev, torch.Tensor) and prob_dev.is_cuda and prob_dev.dtype == torch.float32
             and prob_dev.dim() == 3 and prob_dev.is_contiguous()):
         raise ValueError("dbnet_post_front: prob_dev must be a contiguous (n, H, W) float32 cuda tensor")
     n, H, W = prob_dev.shape
-    ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(prob_dev.device)
-    with ctx:
-        labels = torch.empty((n, H, W), dtype=torch.int32, device=prob_dev.device)
-        runs = torch.empty((n, max_runs, DB_RUN_DTYPE.itemsize), dtype=torch.uint8, device=prob_dev.device)
-        meta = torch.empty((n, 4), dtype=torch.int32, device=prob_dev.device)
+    dev = prob_dev.device
+    rec = DB_RUN_DTYPE.itemsize
+    with _POST_LOCK, (torch.cuda.stream(stream) if stream is not None else torch.cuda.device(dev)):
+        key = (dev.index, n, H, W, max_runs)
+        bufs = _POST_BUFS.get(key)
+        if bufs is None:
+            # scratch of the kernels + page-locked landing zone of the results: allocated once per batch shape (a
+            # cudaHostAlloc per call would serialise against the other streams of the pipeline)
+            bufs = (torch.empty((n, H, W), dtype=torch.int32, device=dev),
+                    torch.empty((n, max_runs, rec), dtype=torch.uint8, device=dev),
+                    torch.empty((n, 4), dtype=torch.int32, device=dev),
+                    torch.empty((n, max_runs, rec), dtype=torch.uint8, pin_memory=True),
+                    torch.empty((n, 4), dtype=torch.int32, pin_memory=True))
+            if len(_POST_BUFS) >= 4:
+                _POST_BUFS.pop(next(iter(_POST_BUFS)))
+            _POST_BUFS[key] = bufs
+        labels, runs, meta, runs_h, meta_h = bufs
+        cur = torch.cuda.current_stream(dev)
         _lib.check(_lib.lib().ytk_dbnet_post_front(prob_dev.data_ptr(), n, H, W, float(thresh), labels.data_ptr(),
                                                    labels.numel() * 4, runs.data_ptr(), max_runs, meta.data_ptr(),
-                                                   _stream_ptr(stream)))
-        meta_h = meta.cpu().numpy()                           # synchronises the stream
-        out, pending = [], []
+                                                   ctypes.c_void_p(cur.cuda_stream)))
+        meta_h.copy_(meta, non_blocking=True)
+        cur.synchronize()
+        m = meta_h.numpy().copy()
+        ok = [not (int(m[i, 3]) or int(m[i, 0]) > max_runs or int(m[i, 1]) * 4 != int(m[i, 2])) for i in range(n)]
         for i in range(n):
-            cnt, comps, euler4, overflow = (int(v) for v in meta_h[i])
-            if overflow or cnt > max_runs or comps * 4 != euler4:
-                out.append(None)
-                continue
-            host = torch.empty((cnt, DB_RUN_DTYPE.itemsize), dtype=torch.uint8, pin_memory=True)
-            host.copy_(runs[i, :cnt], non_blocking=True)
-            pending.append((i, host))
-            out.append(host)
-        if pending:
-            (torch.cuda.current_stream(prob_dev.device) if stream is None else stream).synchronize()
-        for i, host in pending:
-            out[i] = host.numpy().reshape(-1).view(DB_RUN_DTYPE)
-    return out, meta_h
+            if ok[i] and m[i, 0]:
+                runs_h[i, :int(m[i, 0])].copy_(runs[i, :int(m[i, 0])], non_blocking=True)
+        cur.synchronize()
+        out = [runs_h[i, :int(m[i, 0])].numpy().reshape(-1).view(DB_RUN_DTYPE).copy() if ok[i] else None
+               for i in range(n)]
+    return out, m
 
 
 def halve_pages_device(pages_dev, stream=None):
