@@ -816,11 +816,30 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
     GemmArgs& a = plan->args;
     plan->block_n = pick_block_n(Cout);
     static const bool no_shrink = getenv("YTK_NO_SHRINK") != nullptr;  // debugging aid
+    static const bool no_wave_model = getenv("YTK_NO_WAVE_MODEL") != nullptr;  // A/B aid
     if (e.mode != EPI_CONVT_FINAL && !no_shrink) {
-        // small problems (decode steps, coarse feature maps): shrink the N tile until the persistent grid fills the SMs
         const int m_tiles = a.n_img * a.tiles_h * a.tiles_w;
-        while (plan->block_n > 64 && m_tiles * ((Cout + plan->block_n - 1) / plan->block_n) < num_sms())
-            plan->block_n >>= 1;
+        const int sms = num_sms();
+        auto tiles_at = [&](int bn) { return (long long)m_tiles * ((Cout + bn - 1) / bn); };
+        if (no_wave_model || (tiles_at(plan->block_n) + sms - 1) / sms > 6) {
+            // small problems (decode steps, coarse feature maps): shrink the N tile until the persistent grid fills the SMs
+            while (plan->block_n > 64 && tiles_at(plan->block_n) < sms) plan->block_n >>= 1;
+        } else {
+            // a handful of waves: the last, partly filled wave costs as much as a full one (3200 decode rows x 768
+            // columns = 150 tiles of 128 columns on 148 SMs = two waves).  Pick the N tile with the smallest
+            // waves x (relative time of one tile of that width); ties go to the wider tile.
+            int best = plan->block_n;
+            double best_cost = 1e30;
+            for (int bn = plan->block_n; bn >= 64; bn >>= 1) {
+                const double w = bn == 256 ? 1.9 : bn == 128 ? 1.0 : 0.56;
+                const double cost = (double)((tiles_at(bn) + sms - 1) / sms) * w;
+                if (cost < best_cost - 1e-9) {
+                    best_cost = cost;
+                    best = bn;
+                }
+            }
+            plan->block_n = best;
+        }
     }
     a.tiles_n = (Cout + plan->block_n - 1) / plan->block_n;
     a.Cout = Cout;
