@@ -25,6 +25,7 @@ extern "C" {
 #define YTK_ACT_RELU 1
 #define YTK_ACT_GELU 2
 #define YTK_ACT_SIGMOID 3
+#define YTK_ACT_SILU 4
 
 const char* ytk_last_error(void);
 int ytk_version(void);

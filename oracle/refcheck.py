@@ -211,6 +211,53 @@ def build_reference_parseq(spec, sd, charset):
     return m.eval()
 
 
+# ---------------------------------------------------------------------------------- RT-DETRv2 (layout / table models)
+def load_reference_rtdetr():
+    """(RTDETRv2 class, RTDETRPostProcessor class) executed from /root/reference.  `omegaconf` (not installable here) is
+    a two-line stand-in: the decoder only does `isinstance(num_points, ListConfig)` (rtdetrv2_decoder.py:26, 78)."""
+    if "omegaconf" not in sys.modules:
+        om = types.ModuleType("omegaconf")
+
+        class ListConfig(list):
+            pass
+
+        om.ListConfig = ListConfig
+        sys.modules["omegaconf"] = om
+    _pkg("ytk_ref")
+    _pkg("ytk_ref.models")
+    _pkg("ytk_ref.models.layers")
+    _pkg("ytk_ref.postprocessor")
+    for n in ("activate", "rtdetr_backbone", "rtdetr_hybrid_encoder", "rtdetrv2_decoder"):
+        if "ytk_ref.models.layers." + n not in sys.modules:
+            _load("ytk_ref.models.layers." + n, "models/layers/%s.py" % n, "ytk_ref.models.layers")
+    m = sys.modules.get("ytk_ref.models.rtdetr") or _load("ytk_ref.models.rtdetr", "models/rtdetr.py", "ytk_ref.models")
+    pp = sys.modules.get("ytk_ref.postprocessor.rtdetr_postprocessor") or _load(
+        "ytk_ref.postprocessor.rtdetr_postprocessor", "postprocessor/rtdetr_postprocessor.py", "ytk_ref.postprocessor")
+    return m.RTDETRv2, pp.RTDETRPostProcessor
+
+
+def reference_rtdetr_cfg(num_classes):
+    # values of reference configs/cfg_layout_parser_rtdtrv2_v2.py:10-61 / cfg_table_structure_recognizer_rtdtrv2.py
+    LC = sys.modules["omegaconf"].ListConfig
+    return AttrDict(
+        PResNet=dict(depth=50, variant="d", freeze_at=0, return_idx=[1, 2, 3], num_stages=4, freeze_norm=True),
+        HybridEncoder=dict(in_channels=[512, 1024, 2048], feat_strides=[8, 16, 32], hidden_dim=256, use_encoder_idx=[2],
+                           num_encoder_layers=1, nhead=8, dim_feedforward=1024, dropout=0.0, enc_act="gelu",
+                           expansion=1.0, depth_mult=1, act="silu"),
+        RTDETRTransformerv2=dict(num_classes=num_classes, feat_channels=[256, 256, 256], feat_strides=[8, 16, 32],
+                                 hidden_dim=256, num_levels=3, num_layers=6, num_queries=300, num_denoising=100,
+                                 label_noise_ratio=0.5, box_noise_scale=1.0, eval_spatial_size=[640, 640], eval_idx=-1,
+                                 num_points=LC([4, 4, 4]), cross_attn_method="default", query_select_method="default"))
+
+
+def build_reference_rtdetr(num_classes, sd=None):
+    RTDETRv2, _ = load_reference_rtdetr()
+    m = RTDETRv2(reference_rtdetr_cfg(num_classes))
+    if sd is not None:
+        m.load_state_dict(sd, strict=True)
+    return m.eval()
+
+
 def build_reference_postprocessor(**kwargs):
     """The reference's own DBnetPostProcessor (postprocessor/dbnet_postporcessor.py, executed from /root/reference) with
     the two third-party imports that are not installable offline replaced by this oracle's restatements:

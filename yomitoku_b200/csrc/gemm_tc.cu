@@ -553,6 +553,9 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     } else if (args.act == ACT_SIGMOID) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) f[j] = __fdividef(1.f, 1.f + __expf(-f[j]));
+                    } else if (args.act == ACT_SILU) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) f[j] = __fdividef(f[j], 1.f + __expf(-f[j]));
                     }
                     if (row_ok) {
                         if constexpr (OUT_F32) {
@@ -661,6 +664,10 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
 #pragma unroll
                                 for (int j = 0; j < CPP; ++j)
                                     f[p * CPP + j] = __fdividef(1.f, 1.f + __expf(-f[p * CPP + j]));
+                            } else if (args.act == ACT_SILU) {
+#pragma unroll
+                                for (int j = 0; j < CPP; ++j)
+                                    f[p * CPP + j] = __fdividef(f[p * CPP + j], 1.f + __expf(-f[p * CPP + j]));
                             }
                             if constexpr (OUT_F32) {
                                 float4* wp = reinterpret_cast<float4*>(my_row);
@@ -816,7 +823,10 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
     GemmArgs& a = plan->args;
     plan->block_n = pick_block_n(Cout);
     static const bool no_shrink = getenv("YTK_NO_SHRINK") != nullptr;  // debugging aid
-    static const bool no_wave_model = getenv("YTK_NO_WAVE_MODEL") != nullptr;  // A/B aid
+    // YTK_WAVE_MODEL=1: choose the N tile of few-wave problems by waves x relative tile time.  Measured and rejected
+    // (profiles/README_r02.md): 64-wide tiles cost 0.75, not 0.56, of a 128-wide tile (3200 x 768 x 3072: 59.8 vs
+    // 45.0 us), the AR loop went from 62.4 to 66.0 ms.  Kept as an experiment switch only.
+    static const bool no_wave_model = getenv("YTK_WAVE_MODEL") == nullptr;
     if (e.mode != EPI_CONVT_FINAL && !no_shrink) {
         const int m_tiles = a.n_img * a.tiles_h * a.tiles_w;
         const int sms = num_sms();

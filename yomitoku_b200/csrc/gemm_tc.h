@@ -17,7 +17,7 @@ namespace ytk {
 
 constexpr int kMaxTaps = 9;
 
-enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3 };
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2, ACT_SIGMOID = 3, ACT_SILU = 4 };
 enum EpiMode : int {
     EPI_NORMAL = 0,
     EPI_SHUFFLE2X = 1,  // ConvTranspose2d(k=2,s=2): column block (i,j) of width Cout/4 goes to pixel (2h+i, 2w+j)
