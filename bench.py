@@ -251,6 +251,34 @@ def config2_line(det, L, pk, steps=20, warmup=5):
                          "gemm_kernel": g}}
 
 
+def config5_layout_line(L, pk, batch=8, steps=10, warmup=3):
+    """The model BASELINE config 5 adds to the OCR path: RT-DETRv2 (layout parser; the table structure recognizer is the
+    same network with 3 classes), `batch` synthetic 640x640 inputs resident in HBM -> pred_logits / pred_boxes in HBM."""
+    from yomitoku_b200 import _lib
+    from yomitoku_b200.config import LayoutParserRTDETRv2V2Config, to_config
+    from yomitoku_b200.models import RTDETRv2
+    m = RTDETRv2(cfg=to_config(LayoutParserRTDETRv2V2Config())).to("cuda")
+    x = torch.rand(batch, 3, 640, 640, device="cuda")
+    lg = torch.empty((batch, 300, 6), dtype=torch.float32, device="cuda")
+    bx = torch.empty((batch, 300, 4), dtype=torch.float32, device="cuda")
+
+    def step():
+        _lib.check(L.ytk_rtdetr_forward_f32(m._ensure(), x.data_ptr(), 1, batch, lg.data_ptr(), bx.data_ptr(), 1, None))
+    ms = _time_ms(step, steps, warmup)
+    flops = m.flops(batch)
+    g = _gemm_window(L, step)
+    return {"metric": "images/sec (RT-DETRv2 layout parser forward, 640x640, batch %d)" % batch,
+            "value": batch / (ms / 1e3), "unit": "images/s", "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "dtype": "f16", "higher_is_better": True,
+            "config": {"workload": "BASELINE config 5's extra model: RT-DETRv2 (PResNet-50d + HybridEncoder + 6-layer "
+                                   "deformable decoder, 300 queries), %d synthetic 640x640 inputs, 1 B200, inputs and outputs "
+                                   "resident in HBM, random weights" % batch},
+            "roofline": {"bound": "tensor", "achieved": flops / 1e12 / (ms / 1e3), "peak": pk["bf16_tflops"],
+                         "unit": "TFLOP/s", "frac": flops / 1e12 / (ms / 1e3) / pk["bf16_tflops"],
+                         "gflop_per_image": flops / batch / 1e9, "peak_source": pk["source"] + " bf16_tflops (burst: short run)",
+                         "gemm_kernel": g}}
+
+
 def config3_line(rec, L, pk, n_crops=512, steps=5, warmup=3):
     """BASELINE config 3: TextRecognizer PARSeq (full), 512 crops, dynamic_width + batch_bucketing, 1 B200: crops/s with
     the crops resident in HBM (reference grouping: sorted chunks of 128, each padded to its own maximum)."""
@@ -503,6 +531,7 @@ def main():
     if world == 1 and not args.no_extra:
         other.append(config2_line(det, L, pk))
         other.append(config3_line(rec, L, pk))
+        other.append(config5_layout_line(L, pk))
         if args.weights == "random":
             # the same step with trained-like weights whose rows emit EOS: the AR loop stops when every row of a
             # mini-batch holds an EOS, which shifts the step towards the encoder

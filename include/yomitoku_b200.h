@@ -219,6 +219,30 @@ int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, 
 int ytk_halve_pages_u8(const uint8_t* src_dev, int n_pages, int H, int W, uint8_t* dst_dev, int dH, int dW,
                        void* cuda_stream);
 
+/* ---- RT-DETRv2 layout parser / table structure recognizer: replaces `self.model(img_tensor)` in reference
+ * LayoutParser.__call__ (src/yomitoku/layout_parser.py:258-262 -> models/rtdetr.py:17-22) and
+ * TableStructureRecognizer.__call__ (table_structure_recognizer.py:272-276).  One architecture, two weight sets
+ * (num_classes 6 / 3). ---- */
+typedef struct ytk_rtdetr ytk_rtdetr;
+
+/* tensors: the reference's state_dict (RTDETRv2(cfg).state_dict() keys, host fp32; the boolean `decoder.valid_mask` may
+ * be passed as 0/1 floats or left out - it is derived from the finite entries of `decoder.anchors`).  img_size: the square
+ * evaluation size (cfg.data.img_size = eval_spatial_size, 640). */
+int ytk_rtdetr_create(const ytk_tensor* tensors, int n_tensors, int num_classes, int num_queries, int img_size,
+                      ytk_rtdetr** out);
+void ytk_rtdetr_destroy(ytk_rtdetr* h);
+int ytk_rtdetr_device(const ytk_rtdetr* h);
+/* x: [n, 3, img, img] fp32 in [0, 1] (what the reference's transforms produce), host or device.
+ * pred_logits: [n, num_queries, num_classes] fp32, pred_boxes: [n, num_queries, 4] fp32 (cx, cy, w, h in [0, 1]) - the
+ * "pred_logits" / "pred_boxes" of the reference's output dict, rows in the decoder's query order (descending encoder
+ * score).  Outputs on the host: the call returns after the copy; on the device: asynchronous on the stream. */
+int ytk_rtdetr_forward_f32(ytk_rtdetr* h, const float* x, int x_on_device, int n, float* pred_logits, float* pred_boxes,
+                           int out_on_device, void* cuda_stream);
+double ytk_rtdetr_flops(ytk_rtdetr* h, int n);
+/* test hook: copies an intermediate activation (by name, see rtdetr_engine.cu) of the LAST forward of batch size n to
+ * the host as fp32; shape4 = {n, h, w, c} (token matrices: {1, 1, rows, c}) */
+int ytk_rtdetr_debug_tensor(ytk_rtdetr* h, int n, const char* name, float* host_out, long long capacity, int* shape4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,13 +77,25 @@ def test_stream_equals_batched_calls():
         assert [[w.points for w in page.words] for page in g] == [[w.points for w in page.words] for page in r]
 
 
-def test_document_analyzer_shell():
-    da = DocumentAnalyzer(configs={"ocr": {"text_detector": {"from_pretrained": False},
+def test_document_analyzer_default_layout_models():
+    """DocumentAnalyzer as the reference builds it: OCR + LayoutAnalyzer (RT-DETRv2 layout parser and table structure
+    recognizer on the device engine), random weights."""
+    from yomitoku_b200.layout_analyzer import LayoutAnalyzer
+    nop = {"from_pretrained": False}
+    da = DocumentAnalyzer(configs={"ocr": {"text_detector": nop,
                                            "text_recognizer": {"from_pretrained": False,
-                                                               "model_name": "parseq-tiny-dynw-v4"}}}, device="cuda")
+                                                               "model_name": "parseq-tiny-dynw-v4"}},
+                                   "layout_analyzer": {"layout_parser": nop, "table_structure_recognizer": nop}},
+                          device="cuda")
+    assert isinstance(da.layout, LayoutAnalyzer)
     page, _ = synthetic_page(1)
     res, ocr_vis, layout_vis = da(page)
-    assert layout_vis is None and isinstance(res.words, list)
+    assert layout_vis is None and isinstance(res.words, list) and len(res.words) > 0
+    off = DocumentAnalyzer(configs={"ocr": {"text_detector": nop,
+                                            "text_recognizer": {"from_pretrained": False,
+                                                                "model_name": "parseq-tiny-dynw-v4"}}},
+                           device="cuda", layout_analyzer=False)
+    assert off.layout is None
 
 
 def test_handles_bind_to_the_requested_device():

@@ -120,6 +120,22 @@ def _declare_crops(lib):
     lib.ytk_halve_pages_u8.argtypes = [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p]
 
 
+def _declare_rtdetr(lib):
+    P = ctypes.POINTER
+    lib.ytk_rtdetr_create.restype = c_int
+    lib.ytk_rtdetr_create.argtypes = [P(YtkTensor), c_int, c_int, c_int, c_int, P(c_void_p)]
+    lib.ytk_rtdetr_destroy.restype = None
+    lib.ytk_rtdetr_destroy.argtypes = [c_void_p]
+    lib.ytk_rtdetr_device.restype = c_int
+    lib.ytk_rtdetr_device.argtypes = [c_void_p]
+    lib.ytk_rtdetr_forward_f32.restype = c_int
+    lib.ytk_rtdetr_forward_f32.argtypes = [c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p, c_int, c_void_p]
+    lib.ytk_rtdetr_flops.restype = ctypes.c_double
+    lib.ytk_rtdetr_flops.argtypes = [c_void_p, c_int]
+    lib.ytk_rtdetr_debug_tensor.restype = c_int
+    lib.ytk_rtdetr_debug_tensor.argtypes = [c_void_p, c_int, ctypes.c_char_p, c_void_p, c_ll, P(c_int)]
+
+
 def tensor_table(state_dict):
     """state_dict (name -> torch tensor) -> (ctypes array of YtkTensor, keep-alive list). Tensors are converted to
     contiguous host fp32; integer buffers (num_batches_tracked) are skipped."""
@@ -153,6 +169,7 @@ def lib():
     _declare_dbnet(l)
     _declare_parseq(l)
     _declare_crops(l)
+    _declare_rtdetr(l)
     _lib = l
     return l
 

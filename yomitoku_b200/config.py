@@ -119,3 +119,40 @@ TextRecognizerPARSeqLargeV41Config = _parseq(_R + "parseq-large-v4_1", "charsetv
 TextRecognizerPARSeqTinyDynwV4Config = _parseq(_R + "parseq-tiny-dynw-v4", "charsetv2.txt", 7121, 192, 6, 12, (4, 8),
                                                dec_heads=6, batch_size=10, font="ShipporiMinchoB1-Bold.ttf",
                                                extra_data={"width_budget": 8000, "max_batch_size": 64})
+
+
+# ------------------------------------------------------------------------------------------------ layout models
+def _rtdetr(repo, num_classes, thresh_score, category, role=None):
+    """Values of reference configs/cfg_layout_parser_rtdtrv2{,_v2}.py and cfg_table_structure_recognizer_rtdtrv2.py."""
+    def make():
+        cfg = {
+            "hf_hub_repo": repo,
+            "thresh_score": thresh_score,
+            "data": {"img_size": [640, 640]},
+            "PResNet": {"depth": 50, "variant": "d", "freeze_at": 0, "return_idx": [1, 2, 3], "num_stages": 4,
+                        "freeze_norm": True},
+            "HybridEncoder": {"in_channels": [512, 1024, 2048], "feat_strides": [8, 16, 32], "hidden_dim": 256,
+                              "use_encoder_idx": [2], "num_encoder_layers": 1, "nhead": 8, "dim_feedforward": 1024,
+                              "dropout": 0.0, "enc_act": "gelu", "expansion": 1.0, "depth_mult": 1, "act": "silu"},
+            "RTDETRTransformerv2": {"num_classes": num_classes, "feat_channels": [256, 256, 256],
+                                    "feat_strides": [8, 16, 32], "hidden_dim": 256, "num_levels": 3, "num_layers": 6,
+                                    "num_queries": 300, "num_denoising": 100, "label_noise_ratio": 0.5,
+                                    "box_noise_scale": 1.0, "eval_spatial_size": [640, 640], "eval_idx": -1,
+                                    "num_points": [4, 4, 4], "cross_attn_method": "default",
+                                    "query_select_method": "default"},
+            "category": list(category),
+        }
+        if role is not None:
+            cfg["role"] = list(role)
+        return cfg
+    return make
+
+
+_LAYOUT_CATEGORY = ["tables", "figures", "paragraphs", "section_headings", "page_header", "page_footer"]
+_LAYOUT_ROLE = ["section_headings", "page_header", "page_footer"]
+LayoutParserRTDETRv2Config = _rtdetr("KotaroKinoshita/yomitoku-layout-parser-rtdtrv2-open-beta", 6, 0.5,
+                                     _LAYOUT_CATEGORY, _LAYOUT_ROLE)
+LayoutParserRTDETRv2V2Config = _rtdetr("KotaroKinoshita/yomitoku-layout-parser-rtdtrv2-v2", 6, 0.5, _LAYOUT_CATEGORY,
+                                       _LAYOUT_ROLE)
+TableStructureRecognizerRTDETRv2Config = _rtdetr(
+    "KotaroKinoshita/yomitoku-table-structure-recognizer-rtdtrv2-open-beta", 3, 0.4, ["row", "col", "span"])

@@ -15,6 +15,7 @@
 #include "dbpost_ops.h"
 #include "gemm_tc.h"
 #include "parseq_engine.h"
+#include "rtdetr_engine.h"
 
 struct ytk_parseq {
     ytk::ParseqModel model;
@@ -507,3 +508,142 @@ void ytk_parseq_last_phase_ms(ytk_parseq* h, float* ms4) {
 }
 
 }  // extern "C"
+
+
+// ------------------------------------------------------------------------------------------------ RT-DETRv2
+struct ytk_rtdetr {
+    ytk::RtdetrModel model;
+    std::map<int, std::unique_ptr<ytk::RtdetrEngine>> engines;   // per batch size
+    std::mutex mu;
+    int device = 0;
+    cudaEvent_t last_done = nullptr;   // buffers of an engine are shared by all calls: order them (see ytk_dbnet)
+};
+
+static ytk::RtdetrEngine* rt_engine(ytk_rtdetr* h, int n) {
+    auto it = h->engines.find(n);
+    if (it != h->engines.end()) return it->second.get();
+    if (h->engines.size() >= 4) {
+        cudaDeviceSynchronize();
+        h->engines.erase(h->engines.begin());
+    }
+    auto e = std::make_unique<ytk::RtdetrEngine>();
+    if (e->build(h->model, n)) return nullptr;
+    ytk::RtdetrEngine* p = e.get();
+    h->engines[n] = std::move(e);
+    return p;
+}
+
+int ytk_rtdetr_create(const ytk_tensor* tensors, int n_tensors, int num_classes, int num_queries, int img_size,
+                      ytk_rtdetr** out) {
+    if (!tensors || !out) {
+        ytk::set_error("ytk_rtdetr_create: null argument");
+        return YTK_ERR;
+    }
+    ytk::WeightSet ws;
+    for (int i = 0; i < n_tensors; ++i) {
+        ytk::TensorView v;
+        v.data = tensors[i].data;
+        v.ndim = tensors[i].ndim;
+        for (int d = 0; d < 4; ++d) v.shape[d] = d < v.ndim ? tensors[i].shape[d] : 1;
+        ws.map[tensors[i].name] = v;
+    }
+    auto h = std::make_unique<ytk_rtdetr>();
+    cudaGetDevice(&h->device);
+    ytk::RtCfg cfg;
+    cfg.num_classes = num_classes;
+    cfg.num_queries = num_queries;
+    cfg.img = img_size;
+    if (num_classes < 1 || num_classes > 8 || num_queries < 1) {
+        ytk::set_error("ytk_rtdetr_create: num_classes %d (1..8) / num_queries %d unsupported", num_classes, num_queries);
+        return YTK_ERR;
+    }
+    if (h->model.load(ws, cfg)) return YTK_ERR;
+    *out = h.release();
+    return YTK_OK;
+}
+
+void ytk_rtdetr_destroy(ytk_rtdetr* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->last_done) {
+        cudaEventSynchronize(h->last_done);
+        cudaEventDestroy(h->last_done);
+    }
+    cudaDeviceSynchronize();
+    delete h;
+}
+
+int ytk_rtdetr_device(const ytk_rtdetr* h) { return h ? h->device : -1; }
+
+int ytk_rtdetr_forward_f32(ytk_rtdetr* h, const float* x, int x_on_device, int n, float* pred_logits, float* pred_boxes,
+                           int out_on_device, void* cuda_stream) {
+    if (!h || !x || !pred_logits || !pred_boxes || n < 1) {
+        ytk::set_error("ytk_rtdetr_forward_f32: null or empty argument");
+        return YTK_ERR;
+    }
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
+    ytk::RtdetrEngine* e = rt_engine(h, n);
+    if (!e) return YTK_ERR;
+    if (h->last_done) cudaStreamWaitEvent(st, h->last_done, 0);
+    const int S = h->model.cfg.img, K = h->model.cfg.num_queries, C = h->model.cfg.num_classes;
+    const float* src = x;
+    if (!x_on_device) {
+        if (cudaMemcpyAsync(e->in_f32, x, (size_t)n * 3 * S * S * 4, cudaMemcpyHostToDevice, st) != cudaSuccess) {
+            ytk::set_error("H2D copy of the input tensor failed");
+            return YTK_ERR;
+        }
+        src = e->in_f32;
+    }
+    if (ytk::launch_rt_pack_input(src, n, S, S, e->input, st) || e->run(st)) return YTK_ERR;
+    const cudaMemcpyKind kind = out_on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost;
+    cudaError_t err = cudaMemcpyAsync(pred_logits, e->out_logits, (size_t)n * K * C * 4, kind, st);
+    if (err == cudaSuccess) err = cudaMemcpyAsync(pred_boxes, e->boxes, (size_t)n * K * 16, kind, st);
+    if (!h->last_done) cudaEventCreateWithFlags(&h->last_done, cudaEventDisableTiming);
+    if (h->last_done) cudaEventRecord(h->last_done, st);
+    if (err == cudaSuccess && !out_on_device) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) {
+        ytk::set_error("RT-DETRv2 output copy failed: %s", cudaGetErrorString(err));
+        return YTK_ERR;
+    }
+    return YTK_OK;
+}
+
+double ytk_rtdetr_flops(ytk_rtdetr* h, int n) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    ytk::RtdetrEngine* e = rt_engine(h, n);
+    return e ? e->flops : -1.0;
+}
+
+int ytk_rtdetr_debug_tensor(ytk_rtdetr* h, int n, const char* name, float* host_out, long long capacity, int* shape4) {
+    std::lock_guard<std::mutex> lk(h->mu);
+    cudaSetDevice(h->device);
+    ytk::RtdetrEngine* e = rt_engine(h, n);
+    if (!e) return YTK_ERR;
+    auto it = e->dbg.find(name);
+    if (it == e->dbg.end() || !it->second.p) {
+        ytk::set_error("no debug tensor named '%s'", name);
+        return YTK_ERR;
+    }
+    const ytk::DebugTensor& t = it->second;
+    const long long cnt = (long long)t.n * t.h * t.w * t.c;
+    shape4[0] = t.n; shape4[1] = t.h; shape4[2] = t.w; shape4[3] = t.c;
+    if (cnt > capacity) {
+        ytk::set_error("debug tensor '%s' needs %lld floats, capacity %lld", name, cnt, capacity);
+        return YTK_ERR;
+    }
+    cudaDeviceSynchronize();
+    if (t.f32) {
+        if (cudaMemcpy(host_out, t.p, cnt * 4, cudaMemcpyDeviceToHost) != cudaSuccess) return YTK_ERR;
+    } else {
+        float* tmp = nullptr;
+        if (cudaMalloc(&tmp, cnt * 4) != cudaSuccess) return YTK_ERR;
+        ytk::launch_op_to_f32(t.p, tmp, cnt, 0);
+        cudaError_t err = cudaMemcpy(host_out, tmp, cnt * 4, cudaMemcpyDeviceToHost);
+        cudaFree(tmp);
+        if (err != cudaSuccess) return YTK_ERR;
+    }
+    return YTK_OK;
+}

@@ -67,7 +67,7 @@ __global__ void avgpool2_kernel(const uint4* __restrict__ in, uint4* __restrict_
 }
 
 // F.interpolate(scale_factor=2, mode="nearest") written into channels [coff, coff + C) of a wider NHWC buffer
-__global__ void upsample_nearest2_kernel(const uint4* __restrict__ src, int n_img, int Hs, int Ws, int C8,
+__global__ void upsample_nearest2_kernel(const op_t* __restrict__ src, long long lds, int n_img, int Hs, int Ws, int C8,
                                          op_t* __restrict__ dst, long long ldd, int coff) {
     const int Hd = 2 * Hs, Wd = 2 * Ws;
     const long long total = (long long)n_img * Hd * Wd * C8;
@@ -77,7 +77,7 @@ __global__ void upsample_nearest2_kernel(const uint4* __restrict__ src, int n_im
     const int wd = (int)((idx / C8) % Wd);
     const int hd = (int)((idx / ((long long)C8 * Wd)) % Hd);
     const int img = (int)(idx / ((long long)C8 * Wd * Hd));
-    const uint4 v = __ldg(src + (((size_t)img * Hs + (hd >> 1)) * Ws + (wd >> 1)) * C8 + c);
+    const uint4 v = __ldg(reinterpret_cast<const uint4*>(src + (((size_t)img * Hs + (hd >> 1)) * Ws + (wd >> 1)) * lds + c * 8));
     *reinterpret_cast<uint4*>(dst + (((size_t)img * Hd + hd) * Wd + wd) * ldd + coff + c * 8) = v;
 }
 
@@ -291,10 +291,10 @@ int launch_rt_avgpool2(const void* in, void* out, int n_img, int H, int W, int C
     return cudaGetLastError() != cudaSuccess;
 }
 
-int launch_rt_upsample_nearest2(const void* src, int n_img, int Hs, int Ws, int C, void* dst, long long ldd, int coff,
-                                cudaStream_t st) {
+int launch_rt_upsample_nearest2(const void* src, long long lds, int n_img, int Hs, int Ws, int C, void* dst, long long ldd,
+                                int coff, cudaStream_t st) {
     const long long total = (long long)n_img * 4 * Hs * Ws * (C / 8);
-    upsample_nearest2_kernel<<<blocks_for(total), 256, 0, st>>>(reinterpret_cast<const uint4*>(src), n_img, Hs, Ws, C / 8,
+    upsample_nearest2_kernel<<<blocks_for(total), 256, 0, st>>>(reinterpret_cast<const op_t*>(src), lds, n_img, Hs, Ws, C / 8,
                                                                 reinterpret_cast<op_t*>(dst), ldd, coff);
     count_launch();
     return cudaGetLastError() != cudaSuccess;

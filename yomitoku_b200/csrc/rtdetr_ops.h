@@ -36,8 +36,9 @@ __host__ __device__ inline int rt_row_anchor(const RtLevels& lv, int n_img, long
 
 int launch_rt_pack_input(const float* src_nchw, int n_img, int H, int W, void* dst_nhwc64, cudaStream_t st);
 int launch_rt_avgpool2(const void* in, void* out, int n_img, int H, int W, int C, cudaStream_t st);
-int launch_rt_upsample_nearest2(const void* src, int n_img, int Hs, int Ws, int C, void* dst, long long ldd, int coff,
-                                cudaStream_t st);
+// nearest x2 of src [n, Hs, Ws, C] (row pitch lds elements) into channels [coff, coff + C) of dst [n, 2Hs, 2Ws, ldd]
+int launch_rt_upsample_nearest2(const void* src, long long lds, int n_img, int Hs, int Ws, int C, void* dst, long long ldd,
+                                int coff, cudaStream_t st);
 // out = a + b (fp16 [rows, C]); with b_f32: out = a + b_f32[row % period] (fp32 table [period, C])
 int launch_rt_add(const void* a, const void* b, const float* b_f32, int C, int period, void* out, long long rows,
                   cudaStream_t st);

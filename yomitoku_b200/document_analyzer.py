@@ -290,12 +290,16 @@ class DocumentAnalyzer:
             raise ValueError("configs must be a dict. See the https://kotaro-kinoshita.github.io/yomitoku/module/#config")
         self.text_detector = TextDetector(**default_configs["ocr"]["text_detector"])
         self.text_recognizer = TextRecognizer(**default_configs["ocr"]["text_recognizer"])
-        self.layout = layout_analyzer
-        if layout_analyzer is None and split_text_across_cells:
-            raise NotImplementedError(
-                "split_text_across_cells needs table cells: pass layout_analyzer= (an object with the reference's "
-                "`layout(img) -> (LayoutAnalyzerSchema, vis)` protocol); the RT-DETRv2 layout models are not part of "
-                "this repo (SURVEY.md section 8f)")
+        # layout half: by default the reference's LayoutAnalyzer (RT-DETRv2 layout parser + table structure recognizer,
+        # layout_analyzer.py:7-36) on the device engine; any object with its `layout(img) -> (LayoutAnalyzerSchema, vis)`
+        # protocol can be passed instead; False = no layout (every word becomes its own paragraph)
+        if layout_analyzer is None:
+            from .layout_analyzer import LayoutAnalyzer
+            layout_analyzer = LayoutAnalyzer(configs=default_configs["layout_analyzer"], device=device, visualize=visualize)
+        self.layout = layout_analyzer or None
+        if self.layout is None and split_text_across_cells:
+            raise NotImplementedError("split_text_across_cells needs table cells: it cannot be combined with "
+                                      "layout_analyzer=False")
         self.visualize = visualize
         self.ignore_meta = ignore_meta
         self.reading_order = reading_order
@@ -392,7 +396,19 @@ class DocumentAnalyzer:
             self._batched = BatchedOCR(self.text_detector, self.text_recognizer)
         ocr = self._batched
         with ThreadPoolExecutor(max_workers=max(1, min(4, len(pages)))) as ex:
-            if layouts is None:
+            if layouts is None and hasattr(self.layout, "analyze_pages"):
+                # the built-in LayoutAnalyzer: all pages' layouts in one device batch (its own thread: the OCR stages
+                # below run meanwhile)
+                f_all = ex.submit(self.layout.analyze_pages, pages)
+
+                class _One:
+                    def __init__(self, i):
+                        self.i = i
+
+                    def result(self):
+                        return f_all.result()[self.i], None
+                f_lay = [_One(i) for i in range(len(pages))]
+            elif layouts is None:
                 f_lay = [ex.submit(self._layout, p) for p in pages]
             if self.split_text_across_cells:
                 dets = self.text_detector.detect_pages(pages)

@@ -581,3 +581,188 @@ class PARSeq(_DeviceModel):
         a = (ctypes.c_float * 4)()
         _lib.lib().ytk_parseq_last_phase_ms(self._ensure(), a)
         return dict(zip(("encoder", "ar", "refine", "copy"), [float(v) for v in a]))
+
+
+# ======================================================================================================== RT-DETRv2
+def _rtdetr_anchors(img=640, strides=(8, 16, 32), grid_size=0.05, eps=1e-2):
+    """`decoder.anchors` / `decoder.valid_mask` buffers of the reference (rtdetrv2_decoder.py:648-678): cell centres and
+    level-scaled sizes in logit space, inf where any coordinate leaves (eps, 1 - eps)."""
+    out = []
+    for lvl, s in enumerate(strides):
+        n = int(img / s)
+        gy, gx = torch.meshgrid(torch.arange(n), torch.arange(n), indexing="ij")
+        xy = (torch.stack([gx, gy], -1).unsqueeze(0) + 0.5) / torch.tensor([n, n], dtype=torch.float32)
+        out.append(torch.cat([xy, torch.ones_like(xy) * grid_size * (2.0 ** lvl)], -1).reshape(-1, n * n, 4))
+    a = torch.cat(out, 1)
+    valid = ((a > eps) * (a < 1 - eps)).all(-1, keepdim=True)
+    return torch.where(valid, torch.log(a / (1 - a)), torch.inf), valid
+
+
+def _rtdetr_random_state_dict(num_classes, seed=0):
+    """Random init with the reference's key set and shapes (RTDETRv2(cfg).state_dict(), from_pretrained=False)."""
+    g = torch.Generator().manual_seed(seed)
+    sd = OrderedDict()
+    D, F, L, P, H = 256, 1024, 6, 12, 8
+
+    def conv_norm(p, cout, cin, k, tracked):
+        sd[p + ".conv.weight"] = _he_conv(g, cout, cin, k, k)
+        sd[p + ".norm.weight"] = torch.ones(cout)
+        sd[p + ".norm.bias"] = torch.zeros(cout)
+        sd[p + ".norm.running_mean"] = torch.zeros(cout)
+        sd[p + ".norm.running_var"] = torch.ones(cout)
+        if tracked:
+            sd[p + ".norm.num_batches_tracked"] = torch.tensor(0)
+
+    def linear(p, cout, cin, bias=0.0):
+        bound = math.sqrt(6.0 / (cin + cout))
+        sd[p + ".weight"] = (torch.rand(cout, cin, generator=g) * 2 - 1) * bound
+        sd[p + ".bias"] = torch.full((cout,), float(bias))
+
+    def ln(p):
+        sd[p + ".weight"] = torch.ones(D)
+        sd[p + ".bias"] = torch.zeros(D)
+
+    def mha(p):
+        sd[p + ".in_proj_weight"] = (torch.rand(3 * D, D, generator=g) * 2 - 1) * math.sqrt(6.0 / (4 * D))
+        sd[p + ".in_proj_bias"] = torch.zeros(3 * D)
+        linear(p + ".out_proj", D, D)
+
+    conv_norm("backbone.conv1.conv1_1", 32, 3, 3, False)
+    conv_norm("backbone.conv1.conv1_2", 32, 32, 3, False)
+    conv_norm("backbone.conv1.conv1_3", 64, 32, 3, False)
+    cin = 64
+    for s, (n, ch) in enumerate(zip((3, 4, 6, 3), (64, 128, 256, 512))):
+        for b in range(n):
+            p = "backbone.res_layers.%d.blocks.%d" % (s, b)
+            conv_norm(p + ".branch2a", ch, cin, 1, False)
+            conv_norm(p + ".branch2b", ch, ch, 3, False)
+            conv_norm(p + ".branch2c", ch * 4, ch, 1, False)
+            if b == 0:
+                conv_norm(p + (".short.conv" if s else ".short"), ch * 4, cin, 1, False)
+            cin = ch * 4
+    for i, c in enumerate((512, 1024, 2048)):
+        conv_norm("encoder.input_proj.%d" % i, D, c, 1, True)
+    p = "encoder.encoder.0.layers.0"
+    mha(p + ".self_attn")
+    linear(p + ".linear1", F, D)
+    linear(p + ".linear2", D, F)
+    ln(p + ".norm1")
+    ln(p + ".norm2")
+    for kind in ("fpn_blocks", "pan_blocks"):
+        for i in range(2):
+            q = "encoder.%s.%d" % (kind, i)
+            conv_norm(q + ".conv1", D, 2 * D, 1, True)
+            conv_norm(q + ".conv2", D, 2 * D, 1, True)
+            for j in range(3):
+                conv_norm("%s.bottlenecks.%d.conv1" % (q, j), D, D, 3, True)
+                conv_norm("%s.bottlenecks.%d.conv2" % (q, j), D, D, 1, True)
+    for i in range(2):
+        conv_norm("encoder.lateral_convs.%d" % i, D, D, 1, True)
+        conv_norm("encoder.downsample_convs.%d" % i, D, D, 3, True)
+    sd["decoder.anchors"], sd["decoder.valid_mask"] = _rtdetr_anchors()
+    for i in range(3):
+        conv_norm("decoder.input_proj.%d" % i, D, D, 1, True)
+    prior = -math.log(99.0)
+    for i in range(L):
+        p = "decoder.decoder.layers.%d" % i
+        mha(p + ".self_attn")
+        ln(p + ".norm1")
+        sd[p + ".cross_attn.num_points_scale"] = torch.full((P,), 0.25)
+        sd[p + ".cross_attn.sampling_offsets.weight"] = torch.zeros(H * P * 2, D)
+        th = torch.arange(H, dtype=torch.float32) * (2.0 * math.pi / H)
+        gi = torch.stack([th.cos(), th.sin()], -1)
+        gi = (gi / gi.abs().max(-1, keepdim=True).values).reshape(H, 1, 2).tile([1, P, 1])
+        sd[p + ".cross_attn.sampling_offsets.bias"] = (gi * torch.arange(1, 5).repeat(3).reshape(1, -1, 1)).flatten()
+        sd[p + ".cross_attn.attention_weights.weight"] = torch.zeros(H * P, D)
+        sd[p + ".cross_attn.attention_weights.bias"] = torch.zeros(H * P)
+        linear(p + ".cross_attn.value_proj", D, D)
+        linear(p + ".cross_attn.output_proj", D, D)
+        ln(p + ".norm2")
+        linear(p + ".linear1", F, D)
+        linear(p + ".linear2", D, F)
+        ln(p + ".norm3")
+        linear("decoder.dec_score_head.%d" % i, num_classes, D, prior)
+        for j, (co, ci) in enumerate(((D, D), (D, D), (4, D))):
+            linear("decoder.dec_bbox_head.%d.layers.%d" % (i, j), co, ci)
+        sd["decoder.dec_bbox_head.%d.layers.2.weight" % i].zero_()
+    sd["decoder.denoising_class_embed.weight"] = torch.randn(num_classes + 1, D, generator=g)
+    linear("decoder.query_pos_head.layers.0", 2 * D, 4)
+    linear("decoder.query_pos_head.layers.1", D, 2 * D)
+    linear("decoder.enc_output.proj", D, D)
+    ln("decoder.enc_output.norm")
+    linear("decoder.enc_score_head", num_classes, D, prior)
+    for j, (co, ci) in enumerate(((D, D), (D, D), (4, D))):
+        linear("decoder.enc_bbox_head.layers.%d" % j, co, ci)
+    sd["decoder.enc_bbox_head.layers.2.weight"].zero_()
+    return sd
+
+
+class RTDETRv2(_DeviceModel):
+    """reference models/rtdetr.py:9-22 (PResNet-50d + HybridEncoder + RTDETRTransformerv2, eval).  `model(tensor)` takes
+    the (n, 3, 640, 640) fp32 tensor in [0, 1] that LayoutParser / TableStructureRecognizer.preprocess produce and returns
+    {"pred_logits": (n, 300, C), "pred_boxes": (n, 300, 4)} on the tensor's device.  The forward is the sm_100a engine
+    behind ytk_rtdetr_forward_f32 (csrc/rtdetr_engine.cu); there is no CPU fallback."""
+
+    def __init__(self, cfg=None, seed=0):
+        super().__init__()
+        self.cfg = cfg
+        d = cfg.RTDETRTransformerv2 if cfg is not None else None
+        self.num_classes = int(d.num_classes) if d is not None else 6
+        self.num_queries = int(d.num_queries) if d is not None else 300
+        self.img_size = int(cfg.data.img_size[0]) if cfg is not None else 640
+        if cfg is not None and (list(cfg.data.img_size) != [self.img_size] * 2 or
+                                list(d.eval_spatial_size) != [self.img_size] * 2):
+            raise ValueError("RTDETRv2: square img_size == eval_spatial_size expected, got %s / %s"
+                             % (list(cfg.data.img_size), list(d.eval_spatial_size)))
+        self._sd = _rtdetr_random_state_dict(self.num_classes, seed)
+
+    def _ensure(self):
+        self._require_cuda()
+        if self._handle is None:
+            tab, keep = _lib.tensor_table(self._sd)
+            h = ctypes.c_void_p()
+            with torch.cuda.device(self.cuda_device()):
+                _lib.check(_lib.lib().ytk_rtdetr_create(tab, len(tab), self.num_classes, self.num_queries, self.img_size,
+                                                        ctypes.byref(h)))
+            self._handle = h
+        return self._handle
+
+    def _release(self):
+        if self._handle is not None:
+            _lib.lib().ytk_rtdetr_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self._release()
+        except Exception:
+            pass
+
+    def __call__(self, tensor, targets=None):
+        return self.forward(tensor)
+
+    def forward(self, tensor, stream=None):
+        h = self._ensure()
+        S = self.img_size
+        if tensor.dim() != 4 or tuple(tensor.shape[1:]) != (3, S, S):
+            raise ValueError("RTDETRv2 expects (n, 3, %d, %d), got %s" % (S, S, tuple(tensor.shape)))
+        x = tensor.detach().to(torch.float32).contiguous()
+        n = x.shape[0]
+        logits = torch.empty((n, self.num_queries, self.num_classes), dtype=torch.float32, device=x.device)
+        boxes = torch.empty((n, self.num_queries, 4), dtype=torch.float32, device=x.device)
+        on_dev = 1 if x.is_cuda else 0
+        _lib.check(_lib.lib().ytk_rtdetr_forward_f32(h, x.data_ptr(), on_dev, n, logits.data_ptr(), boxes.data_ptr(), on_dev,
+                                                     _stream_ptr(stream)))
+        return {"pred_logits": logits, "pred_boxes": boxes}
+
+    def flops(self, n=1):
+        return _lib.lib().ytk_rtdetr_flops(self._ensure(), n)
+
+    def debug_tensor(self, n, name):
+        """Intermediate activation of the last forward of batch size n (test hook) as a numpy array."""
+        cap = 64 << 20
+        buf = torch.empty(cap, dtype=torch.float32)
+        shape = (ctypes.c_int * 4)()
+        _lib.check(_lib.lib().ytk_rtdetr_debug_tensor(self._ensure(), n, name.encode(), buf.data_ptr(), cap, shape))
+        dims = [int(v) for v in shape]
+        return buf[: dims[0] * dims[1] * dims[2] * dims[3]].reshape(dims).numpy().copy()

@@ -87,6 +87,13 @@ class TableStructureRecognizerSchema(BaseSchema):
     order: int
 
 
+class LayoutParserSchema(BaseSchema):
+    """reference schemas/document_analyzer.py:183-186: what LayoutParser returns (tables are plain regions here)."""
+    paragraphs: List[Element]
+    tables: List[Element]
+    figures: List[Element]
+
+
 class LayoutAnalyzerSchema(BaseSchema):
     """What the layout half (reference layout_analyzer.py:38-49) hands to DocumentAnalyzer.aggregate."""
     paragraphs: List[Element]
