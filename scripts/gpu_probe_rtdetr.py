@@ -24,6 +24,16 @@ m = RTDETRv2(cfg=cfg)
 m.load_state_dict(sd)
 m.to("cuda")
 x = rtdetr_input(21 if kind == "layout" else 22, n=n)
+if os.environ.get("RT_ONCE"):
+    # for ncu launch lists: two forwards from resident inputs, nothing else
+    from yomitoku_b200 import _lib
+    xd = x.cuda()
+    m(xd)
+    c0 = _lib.lib().ytk_launch_count()
+    m(xd)
+    torch.cuda.synchronize()
+    print("launches_per_forward %d" % (_lib.lib().ytk_launch_count() - c0))
+    sys.exit(0)
 aux = {}
 t0 = time.time()
 ref = R.forward(sd, spec, x, aux)

@@ -238,16 +238,21 @@ int RtdetrModel::load(const WeightSet& ws, const RtCfg& c) {
     {
         const TensorView *a = ws.need(de + "anchors", (long long)lv.total * 4), *v = ws.find(de + "valid_mask");
         if (!a) return 1;
-        std::vector<unsigned char> vm(lv.total);
+        std::vector<int> bad;
         for (int i = 0; i < lv.total; ++i) {
             bool ok = true;
             for (int k = 0; k < 4; ++k) ok = ok && std::isfinite(a->data[(size_t)i * 4 + k]);
-            vm[i] = (v && v->numel() == lv.total) ? (v->data[i] != 0.f) : ok;
+            if (v && v->numel() == lv.total) ok = v->data[i] != 0.f;
+            if (!ok) bad.push_back(i);
         }
         void *da = nullptr, *dv = nullptr;
-        if (up(owned, a->data, (size_t)lv.total * 16, &da) || up(owned, vm.data(), vm.size(), &dv)) return 1;
+        if (up(owned, a->data, (size_t)lv.total * 16, &da)) return 1;
         anchors = reinterpret_cast<float*>(da);
-        valid = reinterpret_cast<unsigned char*>(dv);
+        n_invalid = (int)bad.size();
+        if (n_invalid) {
+            if (up(owned, bad.data(), bad.size() * 4, &dv)) return 1;
+            invalid = reinterpret_cast<int*>(dv);
+        }
     }
     if (load_linear(owned, ws, de + "enc_output.proj", D, D, &enc_out) || load_ln(owned, ws, de + "enc_output.norm", D, &enc_out_ln))
         return 1;
@@ -540,7 +545,7 @@ int RtdetrEngine::build(const RtdetrModel& model, int n) {
     if (linear(model.value_all, mem, D, (int)RM, val, c.num_layers * D, false, ACT_NONE)) return 1;
     if (linear(model.enc_out, mem, D, (int)RM, eo32, D, true, ACT_NONE)) return 1;
     steps.push_back([=](cudaStream_t st) {
-        return launch_rt_mask_invalid(reinterpret_cast<float*>(eo32), D, mp->enc_out.b, mp->valid, lv, N, st);
+        return launch_rt_mask_invalid(reinterpret_cast<float*>(eo32), D, mp->enc_out.b, mp->invalid, mp->n_invalid, lv, N, st);
     });
     steps.push_back([=](cudaStream_t st) {
         return launch_layernorm(reinterpret_cast<float*>(eo32), (int)RM, D, D, mp->enc_out_ln.g, mp->enc_out_ln.b, 1e-5f, om16,

@@ -59,7 +59,8 @@ struct RtdetrModel {
     RtLn enc_out_ln;
     float *qpos0_w = nullptr, *qpos0_b = nullptr;      // query_pos_head.layers.0 (fp32, K = 4)
     float* anchors = nullptr;                          // fp32 [L, 4] logit space (inf where invalid)
-    unsigned char* valid = nullptr;                    // [L]
+    int* invalid = nullptr;                            // anchors outside the valid mask (device list)
+    int n_invalid = 0;
     std::vector<RtDecLayer> layers;
     RtLevels lv;
     std::vector<void*> owned;

@@ -102,14 +102,12 @@ __global__ void add_f16_kernel(const uint4* __restrict__ a, const uint4* __restr
 }
 
 // rows outside the anchors' valid mask see a zero memory row (rtdetrv2_decoder.py:694): their enc_output.proj result is
-// the bias.  x: fp32 [rows, D] GEMM output in LEVEL-MAJOR row order (all images of level 0, then level 1, ...).
+// the bias.  x: fp32 [rows, D] GEMM output in LEVEL-MAJOR row order; one block per (invalid anchor, image).
 __global__ void mask_invalid_rows_kernel(float* __restrict__ x, int D, const float* __restrict__ bias,
-                                         const unsigned char* __restrict__ valid, RtLevels lv, int n_img, long long rows) {
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= rows * D) return;
-    const long long row = idx / D;
-    const int a = rt_row_anchor(lv, n_img, row);
-    if (!valid[a]) x[idx] = bias[idx % D];
+                                         const int* __restrict__ invalid, int n_invalid, RtLevels lv, int n_img) {
+    const int a = invalid[blockIdx.x % n_invalid], img = blockIdx.x / n_invalid;
+    const long long row = rt_anchor_row(lv, n_img, img, a);
+    for (int c = threadIdx.x; c < D; c += blockDim.x) x[row * D + c] = bias[c];
 }
 
 // score[img][anchor] = max over classes of the encoder logits (level-major rows -> anchor-major scores)
@@ -310,10 +308,10 @@ int launch_rt_add(const void* a, const void* b, const float* b_f32, int C, int p
     return cudaGetLastError() != cudaSuccess;
 }
 
-int launch_rt_mask_invalid(float* x, int D, const float* bias, const unsigned char* valid, const RtLevels& lv, int n_img,
-                           cudaStream_t st) {
-    const long long rows = (long long)lv.total * n_img;
-    mask_invalid_rows_kernel<<<blocks_for(rows * D), 256, 0, st>>>(x, D, bias, valid, lv, n_img, rows);
+int launch_rt_mask_invalid(float* x, int D, const float* bias, const int* invalid, int n_invalid, const RtLevels& lv,
+                           int n_img, cudaStream_t st) {
+    if (n_invalid <= 0) return 0;
+    mask_invalid_rows_kernel<<<n_invalid * n_img, 128, 0, st>>>(x, D, bias, invalid, n_invalid, lv, n_img);
     count_launch();
     return cudaGetLastError() != cudaSuccess;
 }

@@ -42,8 +42,9 @@ int launch_rt_upsample_nearest2(const void* src, long long lds, int n_img, int H
 // out = a + b (fp16 [rows, C]); with b_f32: out = a + b_f32[row % period] (fp32 table [period, C])
 int launch_rt_add(const void* a, const void* b, const float* b_f32, int C, int period, void* out, long long rows,
                   cudaStream_t st);
-int launch_rt_mask_invalid(float* x, int D, const float* bias, const unsigned char* valid, const RtLevels& lv, int n_img,
-                           cudaStream_t st);
+// x[row(anchor, img), :] = bias for the anchors listed in `invalid` (device array of anchor ids)
+int launch_rt_mask_invalid(float* x, int D, const float* bias, const int* invalid, int n_invalid, const RtLevels& lv,
+                           int n_img, cudaStream_t st);
 int launch_rt_enc_scores(const float* logits, long long ldl, int C, const RtLevels& lv, int n_img, float* scores,
                          cudaStream_t st);
 // per image: indices of the K largest of L scores, descending (ties: smaller index first)
