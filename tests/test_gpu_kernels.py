@@ -30,14 +30,18 @@ def _check(got, ref, tol=6e-3):
     # >= 4 tiles per SM: CTA-pair kernel (tcgen05.mma.cta_group::2, half weight tile per SM); 75 / 149 M tiles are odd,
     # so the last pair has a ghost CTA; N = 2304 has 9 full N tiles, N = 7119 a ragged last one, K = 3072 wraps the stage ring
     (128 * 74 + 5, 768, 2304, 2, None, False), (128 * 148 + 77, 192, 768, 0, "f32", True),
-    (128 * 21 + 1, 768, 7119, 0, None, True), (128 * 200, 3072, 768, 0, "f32", True)])
+    (128 * 21 + 1, 768, 7119, 0, None, True), (128 * 200, 3072, 768, 0, "f32", True),
+    # TMA epilogue (residual boxes by TMA load, results by TMA store): ragged N with a 16-bit residual, one N tile of 64,
+    # fp32 in / out over many tiles per CTA (the residual ring wraps), GELU + fp16 residual
+    (1000, 128, 72, 0, "f16", False), (4000, 64, 64, 1, "f16", False), (128 * 500 + 3, 64, 256, 0, "f32", True),
+    (128 * 300 + 64, 128, 328, 2, "f16", False)])
 def test_linear(M, K, N, act, resid, f32):
     L = _lib_()
     g = torch.Generator().manual_seed(M + N)
     A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).half()
     W = (torch.randn(N, K, generator=g) * 0.1).to(DEV).half()
     b = torch.randn(N, generator=g).to(DEV)
-    ldc = (N + 7) // 8 * 8
+    ldc = (N + 7) // 8 * 8 + 8    # pad columns keep a sentinel: nothing is written past Cout
     R = None
     if resid == "f32":
         R = torch.randn(M, ldc, generator=g).to(DEV)
@@ -66,6 +70,35 @@ def test_linear(M, K, N, act, resid, f32):
     (1, 296, 400, 64, 64, 3, 1, 1, 1, 1, False), (1, 296, 400, 64, 256, 1, 1, 0, 1, 1, True),
     (3, 148, 200, 128, 128, 3, 2, 1, 1, 1, False)])
 def test_conv(N, H, W, Cin, Cout, k, s, p, d, act, resid):
+    _conv_case(N, H, W, Cin, Cout, k, s, p, d, act, resid)
+
+
+@pytest.mark.parametrize("N,H,W,Cin,Cout,k,s,p,d,act,resid", [
+    # narrow maps: the 128-pixel tile is a 16 x 8 / 8 x 16 / 4 x 32 patch, an epilogue warp's TMA box covers 4 / 2 / 1 rows
+    (2, 20, 8, 64, 96, 3, 1, 1, 1, 1, True), (1, 9, 16, 64, 64, 3, 1, 1, 1, 0, True),
+    (3, 13, 30, 128, 40, 1, 1, 0, 1, 1, True), (2, 50, 37, 64, 264, 3, 1, 1, 1, 1, False)])
+def test_conv_tma_epilogue_patch_shapes(N, H, W, Cin, Cout, k, s, p, d, act, resid):
+    _conv_case(N, H, W, Cin, Cout, k, s, p, d, act, resid, pad=24)
+
+
+def test_linear_residual_in_place_fp32():
+    """x += A W^T + b with the residual tensor = the output tensor (PARSeq's residual stream): every box is loaded before
+    the same box is stored."""
+    L = _lib_()
+    g = torch.Generator().manual_seed(5)
+    M, K, N = 128 * 90 + 17, 768, 768
+    A = (torch.randn(M, K, generator=g) * 0.5).to(DEV).half()
+    W = (torch.randn(N, K, generator=g) * 0.05).to(DEV).half()
+    b = torch.randn(N, generator=g).to(DEV)
+    x = torch.randn(M, N, generator=g).to(DEV)
+    ref = x + A.float() @ W.float().t() + b
+    _lib.check(L.ytk_op_linear_f16(_lib.ptr(A), K, M, K, _lib.ptr(W), N, _lib.ptr(b), _lib.ptr(x), 1, N, _lib.ptr(x), 1,
+                                    N, 0, None))
+    torch.cuda.synchronize()
+    _check(x, ref, 1e-5)
+
+
+def _conv_case(N, H, W, Cin, Cout, k, s, p, d, act, resid, pad=0):
     L = _lib_()
     g = torch.Generator().manual_seed(H * W + Cout)
     x = (torch.randn(N, H, W, Cin, generator=g) * 0.5).to(DEV).half()
@@ -75,16 +108,19 @@ def test_conv(N, H, W, Cin, Cout, k, s, p, d, act, resid):
     Ho = (H + 2 * p - d * (k - 1) - 1) // s + 1
     Wo = (W + 2 * p - d * (k - 1) - 1) // s + 1
     R = torch.randn(N, Ho, Wo, Cout, generator=g).to(DEV).half() if resid else None
-    out = torch.empty((N, Ho, Wo, Cout), device=DEV, dtype=torch.float16)
+    # pad > 0: the output lives in a wider buffer (channel pitch Cout + pad) whose extra channels must stay untouched
+    out = torch.full((N, Ho, Wo, Cout + pad), 7.0, device=DEV, dtype=torch.float16)
     _lib.check(L.ytk_op_conv2d_f16(_lib.ptr(x), N, H, W, Cin, Cin, _lib.ptr(wp), _lib.ptr(b), k, k, s, p, d, Cout,
-                                    _lib.ptr(R), 0, Cout, _lib.ptr(out), 0, Cout, act, 0, None))
+                                    _lib.ptr(R), 0, Cout, _lib.ptr(out), 0, Cout + pad, act, 0, None))
     torch.cuda.synchronize()
     ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=s, padding=p, dilation=d).permute(0, 2, 3, 1)
     if R is not None:
         ref = ref + R.float()
     if act == 1:
         ref = ref.relu()
-    _check(out, ref)
+    _check(out[..., :Cout], ref)
+    if pad:
+        assert (out[..., Cout:].float() == 7.0).all()
 
 
 def test_conv_transpose_shuffle_epilogue():

@@ -38,17 +38,16 @@ def _oracle_group(sd, spec, canv, wp):
     return ids.numpy(), prob.numpy(), (top2[..., 0] - top2[..., 1]).numpy(), aux["ar_margin"].numpy()
 
 
-@pytest.mark.parametrize("name,n_groups,gsize,wlo,whi,seed", [
+CASES = [
     ("parseq-tiny-dynw-v4", 16, 128, 64, 320, 21),
     ("parseq-large-v4_1", 16, 128, 64, 200, 22),
-])
-def test_greedy_strings_identical_at_scale(name, n_groups, gsize, wlo, whi, seed):
-    torch.set_num_threads(max(1, min(64, os.cpu_count() or 1)))
-    spec = ops.SPECS[name]
-    sd = weights.make_parseq_state_dict(spec, seed=seed, peaked=True)
-    rec = TextRecognizer(model_name=name, from_pretrained=False, device="cuda", dynamic_width=True,
-                         batch_bucketing=True)
-    rec.model.load_state_dict(sd)
+]
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+
+def make_inputs(n_groups, gsize, wlo, whi, seed):
+    """The seeded crop set: n_groups reference mini-batches of gsize ragged canvases (numpy PCG64: the same bytes on
+    every machine)."""
     rng = np.random.default_rng(seed)
     canv, padded, groups = [], [], []
     for g in range(n_groups):
@@ -61,17 +60,59 @@ def test_greedy_strings_identical_at_scale(name, n_groups, gsize, wlo, whi, seed
             canv.append(np.clip(img, 0, 255).astype(np.uint8))
             padded.append(wp)
             groups.append(g)
+    return canv, padded, groups
+
+
+def oracle_all(name, n_groups, gsize, wlo, whi, seed):
+    """fp32 oracle over the whole crop set, group by group: ids, max-probabilities, top-2 logit margins of the final
+    logits and the smallest AR-decision margin per row."""
+    spec = ops.SPECS[name]
+    sd = weights.make_parseq_state_dict(spec, seed=seed, peaked=True)
+    canv, padded, _ = make_inputs(n_groups, gsize, wlo, whi, seed)
+    out = [[], [], [], []]
+    for g in range(n_groups):
+        sl = slice(g * gsize, (g + 1) * gsize)
+        r = _oracle_group(sd, spec, canv[sl], padded[g * gsize])
+        out[0].append(r[0])
+        out[1].append(r[1])
+        out[2].append(r[2])
+        out[3].append(r[3].min(-1) if r[3].ndim > 1 else r[3])
+    return [np.concatenate(o, 0) for o in out]
+
+
+def _reference(name, n_groups, gsize, wlo, whi, seed):
+    """Oracle outputs for the case: the committed fixture (tests/golden/identity_<model>.npz, written by
+    tests/golden/make_golden_identity.py = oracle_all() above on the build container's CPU) or, without it or with
+    YTK_IDENTITY_LIVE=1, the oracle run here (minutes of host time for the large model)."""
+    path = os.path.join(GOLDEN, "identity_%s.npz" % name)
+    if os.path.exists(path) and os.environ.get("YTK_IDENTITY_LIVE") != "1":
+        z = np.load(path)
+        assert tuple(int(v) for v in z["case"]) == (n_groups, gsize, wlo, whi, seed), "fixture made for another case"
+        return z["ids"].astype(np.int64), z["prob"], z["margin"], z["ar_margin_min"], "fixture"
+    torch.set_num_threads(max(1, min(64, os.cpu_count() or 1)))
+    return (*oracle_all(name, n_groups, gsize, wlo, whi, seed), "live")
+
+
+@pytest.mark.parametrize("name,n_groups,gsize,wlo,whi,seed", CASES)
+def test_greedy_strings_identical_at_scale(name, n_groups, gsize, wlo, whi, seed):
+    spec = ops.SPECS[name]
+    sd = weights.make_parseq_state_dict(spec, seed=seed, peaked=True)
+    rec = TextRecognizer(model_name=name, from_pretrained=False, device="cuda", dynamic_width=True,
+                         batch_bucketing=True)
+    rec.model.load_state_dict(sd)
+    canv, padded, groups = make_inputs(n_groups, gsize, wlo, whi, seed)
+    R_ids, R_prob, R_margin, R_armin, ref_src = _reference(name, n_groups, gsize, wlo, whi, seed)
     ids, probs, glen = rec.model.recognize_crops(canv, padded, groups, n_groups)
     n = len(canv)
     differing, all_low, score_d, score_low = [], [], [], []
     for g in range(n_groups):
         sl = slice(g * gsize, (g + 1) * gsize)
-        r_ids, r_prob, r_margin, ar_margin = _oracle_group(sd, spec, canv[sl], padded[g * gsize])
+        r_ids, r_prob, r_margin, ar_min = R_ids[sl], R_prob[sl], R_margin[sl], R_armin[sl]
         for b in range(gsize):
             i = g * gsize + b
             row = r_ids[b].tolist()
             m = row.index(0) + 1 if 0 in row else len(row)      # positions the tokenizer reads (incl. the EOS)
-            low = min(float(ar_margin[b].min()), float(r_margin[b, :m].min()))
+            low = min(float(ar_min[b]), float(r_margin[b, :m].min()))
             all_low.append(low)
             if np.array_equal(ids[i, :m], r_ids[b, :m]):
                 # scores are compared on rows without coin-flip decisions: a flipped AR token that the refinement
@@ -86,7 +127,7 @@ def test_greedy_strings_identical_at_scale(name, n_groups, gsize, wlo, whi, seed
     all_low = np.asarray(all_low)
     edges = [0.0, 0.01, 0.03, 0.1, 0.3, 1.0, 3.0, np.inf]
     hist = {("[%g,%g)" % (a, b)): int(((all_low >= a) & (all_low < b)).sum()) for a, b in zip(edges[:-1], edges[1:])}
-    rep = {"model": name, "rows": n, "differing_rows": len(differing), "differing": differing[:50],
+    rep = {"model": name, "rows": n, "oracle": ref_src, "differing_rows": len(differing), "differing": differing[:50],
            "min_margin_histogram_all_rows": hist, "rows_below_tau": int((all_low < TAU).sum()), "tau": TAU,
            "max_abs_log_score_diff": float(max(score_d)) if score_d else None,
            "median_abs_log_score_diff": float(np.median(score_d)) if score_d else None,

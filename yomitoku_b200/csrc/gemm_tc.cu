@@ -64,20 +64,31 @@ constexpr int kABytes = kBlockM * kBlockK * 2;
 constexpr int kThreads = 320;       // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kStagePitch = 80;     // bytes per staged row: 64 B payload + 16 B pad (conflict-free 16 B accesses)
 constexpr int kEpiStageBytes = 8 * 32 * kStagePitch;
-constexpr bool kDirectDefault = false;  // default epilogue store path when YTK_EPI is unset
 
-template <int BLOCK_N>
+// TMA epilogue (DIRECT == 2): every epilogue warp owns a small ring of 2 KB buffers (32 tile rows x 64 bytes, 64-byte
+// swizzled = the layout a TMA box of that shape has in shared memory).  With a residual the ring is 4 deep: three
+// residual boxes are in flight (loaded by TMA long before the accumulator is ready) while the fourth is being stored;
+// without one, 2 buffers double-buffer the TMA stores.
+constexpr int kEpiBufBytes = 32 * 64;
+constexpr int epi_tma_nbuf(int resid) { return resid ? 4 : 2; }
+constexpr int kSmemLimit = 232448;  // 227 KB of dynamic shared memory per CTA
+constexpr int kSmemFixed = 1024 /*final-conv weights*/ + 1024 /*align slack*/ + 512 /*barriers*/;
+
+template <int BLOCK_N, int EPI_BYTES = kEpiStageBytes>
 struct TileCfg {
     static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (196608 / kStageBytes) > 8 ? 8 : (196608 / kStageBytes);
+    static constexpr int kRingBudget = kSmemLimit - kSmemFixed - EPI_BYTES;
+    static constexpr int kStages = (kRingBudget / kStageBytes) > 8 ? 8 : (kRingBudget / kStageBytes);
     // CTA-pair mode: a CTA stages only half of the weight tile; the ring lives in the same kStages * kStageBytes bytes
     static constexpr int kStageBytes2 = kABytes + kBBytes / 2;
-    static constexpr int kStages2 =
-        (kStages * kStageBytes / kStageBytes2) > 8 ? 8 : (kStages * kStageBytes / kStageBytes2);
+    static constexpr int kStages2 = (kRingBudget / kStageBytes2) > 8 ? 8 : (kRingBudget / kStageBytes2);
+    static constexpr int kRingBytes =
+        kStages * kStageBytes > kStages2 * kStageBytes2 ? kStages * kStageBytes : kStages2 * kStageBytes2;
     static constexpr int kTmemCols = 2 * BLOCK_N;  // two accumulator buffers; 128/256/512 are powers of two
-    static constexpr int kSmemBytes =
-        kStages * kStageBytes + kEpiStageBytes + 1024 /*final-conv weights*/ + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kRingBytes + EPI_BYTES + kSmemFixed;
+    static_assert(kSmemBytes <= kSmemLimit, "shared memory budget");
+    static_assert(kRingBytes % 2048 == 0, "epilogue buffers must stay 2 KB aligned");
 };
 
 // ragged last columns of a row segment: element-wise copy (rare; kept out of line)
@@ -147,10 +158,17 @@ __device__ __forceinline__ TileCoord decode_tile(const GemmArgs& a, int tile, in
 // Epilogue variants are compile-time (OUT_F32: fp32 vs bf16 output; RESID: 0 none, 1 bf16, 2 fp32; MODE: EpiMode) so
 // that each instantiation carries only its own store path - one kernel with every path inlined is ~190 KB of SASS and
 // thrashes the instruction cache.
+template <int BLOCK_N, int RESID, int DIRECT>
+using KernelCfg = TileCfg<BLOCK_N, DIRECT == 2 ? 8 * epi_tma_nbuf(RESID) * kEpiBufBytes : kEpiStageBytes>;
+
+// DIRECT: 0 = staged epilogue (registers -> per-warp shared staging -> coalesced per-thread global accesses),
+//         1 = row per thread straight to global memory (A/B aid, not dispatched),
+//         2 = TMA epilogue (EPI_NORMAL only): residual boxes arrive by TMA, results leave by TMA store.
 template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT, int PAIR>
 __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_constant__ GemmMaps maps,
                                                               const __grid_constant__ GemmArgs args) {
-    using Cfg = TileCfg<BLOCK_N>;
+    using Cfg = KernelCfg<BLOCK_N, RESID, DIRECT>;
+    constexpr int kEpiBytes = Cfg::kSmemBytes - Cfg::kRingBytes - kSmemFixed;
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // 1024 B alignment for SWIZZLE_128B
@@ -174,13 +192,14 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
     const int stage_bytes = cl > 1 ? Cfg::kStageBytes2 : Cfg::kStageBytes;
     const int nstages = cl > 1 ? Cfg::kStages2 : Cfg::kStages;
 
-    uint8_t* epi_stage = smem + Cfg::kStages * Cfg::kStageBytes;  // same carve-up in both modes (ring <= this size)
-    float* fin_w = reinterpret_cast<float*>(epi_stage + kEpiStageBytes);  // [4][64] weights of the fused final conv
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiStageBytes + 1024);
+    uint8_t* epi_stage = smem + Cfg::kRingBytes;  // same carve-up in both modes (either ring fits in kRingBytes)
+    float* fin_w = reinterpret_cast<float*>(epi_stage + kEpiBytes);  // [4][64] weights of the fused final conv
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(epi_stage + kEpiBytes + 1024);
     uint64_t* empty_bar = full_bar + 8;
     uint64_t* tfull_bar = empty_bar + 8;
     uint64_t* tempty_bar = tfull_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    [[maybe_unused]] uint64_t* rbar_base = tempty_bar + 3;  // TMA epilogue: [8 warps][4] residual-box barriers
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -194,9 +213,19 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             mbar_init(&tfull_bar[i], 1);
             mbar_init(&tempty_bar[i], 8 * cl);  // one arrive per epilogue warp (of both CTAs in pair mode)
         }
+        if constexpr (DIRECT == 2 && RESID != 0) {
+            for (int i = 0; i < 32; ++i) mbar_init(&rbar_base[i], 1);
+        }
         fence_mbar_init();
         tma_prefetch_desc(&maps.a[0]);
         tma_prefetch_desc(&maps.b);
+        if constexpr (DIRECT == 2) {
+            tma_prefetch_desc(&maps.out);
+            if constexpr (RESID != 0) {
+                tma_prefetch_desc(&maps.resid);
+                tma_prefetch_desc(&maps.resid_pf);
+            }
+        }
     }
     if (warp == 1) {
         if constexpr (PAIR) {
@@ -245,10 +274,26 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             // pair mode: every TMA of the pair signals the leader's full barrier
             uint32_t full0 = 0u;
             if constexpr (PAIR) full0 = mapa_u32(&full_bar[0], 0);
+            // TMA epilogue with a residual: the rows of the NEXT tile's residual go to L2 as one whole-tile request, so
+            // that the epilogue warps' 64-byte boxes hit L2 instead of fetching DRAM piecemeal
+            [[maybe_unused]] auto prefetch_resid = [&](int u2) {
+                if (u2 >= total_units) return;
+                bool gh;
+                const int t2 = unit_tile(u2, gh);
+                if (gh) return;
+                const TileCoord c2 = decode_tile(args, t2, BLOCK_N);
+                tma_prefetch_l2_4d(&maps.resid_pf, c2.n0, c2.w0, c2.h0, c2.img);
+            };
+            if constexpr (DIRECT == 2 && RESID != 0) {
+                if (args.epi_pf) prefetch_resid(worker);
+            }
             for (int u = worker; u < total_units; u += n_workers) {
                 bool ghost;
                 const int tile = unit_tile(u, ghost);
                 const TileCoord tc = decode_tile(args, tile, BLOCK_N);
+                if constexpr (DIRECT == 2 && RESID != 0) {
+                    if (args.epi_pf) prefetch_resid(u + n_workers);
+                }
                 // does the pair's rank-1 tile exist?  (the leader must know how many bytes to expect)
                 const bool peer_ghost = cl > 1 && ((u / args.tiles_n) * 2 + 1 >= tiles_m);
                 int tap = 0, cb = 0;
@@ -333,6 +378,207 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
         // Two warps per TMEM lane quadrant; each owns every other 32-column chunk.  Values go
         // TMEM -> registers (row per thread) -> bias/residual/activation -> per-warp shared staging -> coalesced
         // 16-byte global stores (4 lanes per 64-byte row segment), so DRAM sees whole sectors.
+        if constexpr (DIRECT == 2) {
+            // ---- TMA epilogue.  A "pass" is one warp's share of 64 output bytes per row: 32 tile rows x CPP columns,
+            // one 2 KB box.  The warp's passes (units -> its chunks -> passes) form one sequence that indexes a ring of
+            // NBUF boxes: residual boxes are loaded LOOK passes ahead by lane 0 (so their latency hides behind the MMAs
+            // of the tile and the passes in between), a thread adds its own row in place, and lane 0 hands the box to a
+            // TMA store.  Rows / columns outside the tensor are zero-filled on load and dropped on store by the hardware.
+            static_assert(MODE == EPI_NORMAL, "TMA epilogue: plain stores only");
+            static_assert(RESID == 0 || (RESID == 2) == (OUT_F32 != 0), "TMA epilogue: residual and output boxes match");
+            constexpr int NBUF = epi_tma_nbuf(RESID);
+            constexpr int LOOK = NBUF - 1;
+            constexpr int CPP = OUT_F32 ? 16 : 32;
+            constexpr int NPASS = 32 / CPP;
+            const int q = warp & 3;            // TMEM lane quadrant this warp may access
+            const int wset = (warp - 2) >> 2;  // 0 or 1
+            const int bw_mask = (1 << args.bw_log2) - 1;
+            const int qw = (q * 32) & bw_mask;          // where the quadrant's 32 rows start inside the BH x BW patch
+            const int qh = (q * 32) >> args.bw_log2;
+            uint8_t* bufs = epi_stage + (warp - 2) * (NBUF * kEpiBufBytes);
+            [[maybe_unused]] uint64_t* rbar = rbar_base + (warp - 2) * 4;
+            const int sw = args.epi_swz ? ((lane >> 1) & 3) : 0;   // SWIZZLE_64B: 16 B chunk ^= (row / 2) % 4
+            const int row_off = lane * 64;
+            // residual prefetch cursor (lane 0 only): position (unit, chunk, pass) of the next box to load
+            [[maybe_unused]] int pf_u = worker, pf_c = wset, pf_p = 0, pf_g = 0;
+            [[maybe_unused]] TileCoord pf_tc{};
+            [[maybe_unused]] auto pf_seek = [&]() {   // moves the cursor to the next existing pass at or after its position
+                while (pf_u < total_units) {
+                    bool gh;
+                    const int tile = unit_tile(pf_u, gh);
+                    if (!gh) {
+                        pf_tc = decode_tile(args, tile, BLOCK_N);
+                        if (pf_c < BLOCK_N / 32 && pf_tc.n0 + pf_c * 32 + pf_p * CPP < args.Cout) return;
+                    }
+                    pf_c = wset;       // nothing (left) for this warp in the unit
+                    pf_p = 0;
+                    pf_u += n_workers;
+                }
+            };
+            [[maybe_unused]] auto pf_step = [&]() {
+                if (++pf_p == NPASS) {
+                    pf_p = 0;
+                    pf_c += 2;
+                }
+                pf_seek();
+            };
+            [[maybe_unused]] auto pf_issue = [&]() {
+                const int b = pf_g % NBUF;
+                mbar_expect_tx(&rbar[b], kEpiBufBytes);
+                tma_load_4d(bufs + b * kEpiBufBytes, &maps.resid, &rbar[b], pf_tc.n0 + pf_c * 32 + pf_p * CPP,
+                            pf_tc.w0 + qw, pf_tc.h0 + qh, pf_tc.img);
+                ++pf_g;
+            };
+            if constexpr (RESID != 0) {
+                if (lane == 0) {
+                    pf_seek();
+                    for (int k = 0; k < LOOK && pf_u < total_units; ++k) {
+                        pf_issue();
+                        pf_step();
+                    }
+                }
+            }
+            int gc = 0;  // passes consumed so far (warp-uniform)
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int u = worker; u < total_units; u += n_workers) {
+                bool ghost;
+                const int tile = unit_tile(u, ghost);
+                if (ghost) {  // nothing to store: just hand the accumulator buffer back to the leader
+                    mbar_wait(&tfull_bar[acc], acc_phase);
+                    tc_fence_after();
+                    tc_fence_before();
+                    __syncwarp();
+                    if constexpr (PAIR) {
+                        if (lane == 0) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));
+                    }
+                    acc ^= 1;
+                    if (acc == 0) acc_phase ^= 1u;
+                    continue;
+                }
+                const TileCoord tc = decode_tile(args, tile, BLOCK_N);
+                mbar_wait(&tfull_bar[acc], acc_phase);
+                tc_fence_after();
+                const uint32_t t_addr =
+                    tmem_base + (static_cast<uint32_t>(q * 32) << 16) + static_cast<uint32_t>(acc * BLOCK_N);
+#pragma unroll 1
+                for (int c = wset; c < BLOCK_N / 32; c += 2) {
+                    const int col0 = tc.n0 + c * 32;
+                    if (col0 >= args.Cout) break;  // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld_32x32(t_addr + static_cast<uint32_t>(c * 32), v);
+                    tmem_ld_wait();
+                    float f[32];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+                    if (args.bias != nullptr) {
+                        if (col0 + 32 <= args.Cout) {
+                            const float4* b4 = reinterpret_cast<const float4*>(args.bias + col0);
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const float4 b = __ldg(b4 + j);
+                                f[4 * j + 0] += b.x;
+                                f[4 * j + 1] += b.y;
+                                f[4 * j + 2] += b.z;
+                                f[4 * j + 3] += b.w;
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) f[j] += __ldg(args.bias + min(col0 + j, args.Cout - 1));
+                        }
+                    }
+#pragma unroll
+                    for (int p = 0; p < NPASS; ++p) {
+                        if (col0 + p * CPP < args.Cout) {   // warp-uniform; the cursor above skips the same passes
+                            const int b = gc % NBUF;
+                            uint8_t* box = bufs + b * kEpiBufBytes;
+                            uint8_t* my_row = box + row_off;
+                            if constexpr (RESID != 0) {
+                                mbar_wait(&rbar[b], static_cast<uint32_t>(gc / NBUF) & 1u);
+#pragma unroll
+                                for (int j = 0; j < 4; ++j) {
+                                    const uint4 r = *reinterpret_cast<const uint4*>(my_row + ((j ^ sw) << 4));
+                                    if constexpr (RESID == 2) {
+                                        f[p * 16 + 4 * j + 0] += __uint_as_float(r.x);
+                                        f[p * 16 + 4 * j + 1] += __uint_as_float(r.y);
+                                        f[p * 16 + 4 * j + 2] += __uint_as_float(r.z);
+                                        f[p * 16 + 4 * j + 3] += __uint_as_float(r.w);
+                                    } else {
+                                        const int e = p * CPP + 8 * j;
+                                        f[e + 0] += op_lo(r.x); f[e + 1] += op_hi(r.x);
+                                        f[e + 2] += op_lo(r.y); f[e + 3] += op_hi(r.y);
+                                        f[e + 4] += op_lo(r.z); f[e + 5] += op_hi(r.z);
+                                        f[e + 6] += op_lo(r.w); f[e + 7] += op_hi(r.w);
+                                    }
+                                }
+                            } else {
+                                // the store that used this buffer NBUF passes ago must have read it
+                                if (lane == 0) bulk_wait_read<NBUF - 1>();
+                                __syncwarp();
+                            }
+                            if (args.act == ACT_RELU) {
+#pragma unroll
+                                for (int j = 0; j < CPP; ++j) f[p * CPP + j] = fmaxf(f[p * CPP + j], 0.f);
+                            } else if (args.act == ACT_GELU) {
+#pragma unroll
+                                for (int j = 0; j < CPP; j += 2) gelu_fast2(f[p * CPP + j], f[p * CPP + j + 1]);
+                            } else if (args.act == ACT_SIGMOID) {
+#pragma unroll
+                                for (int j = 0; j < CPP; ++j)
+                                    f[p * CPP + j] = __fdividef(1.f, 1.f + __expf(-f[p * CPP + j]));
+                            } else if (args.act == ACT_SILU) {
+#pragma unroll
+                                for (int j = 0; j < CPP; ++j)
+                                    f[p * CPP + j] = __fdividef(f[p * CPP + j], 1.f + __expf(-f[p * CPP + j]));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                uint4 o;
+                                if constexpr (OUT_F32) {
+                                    o.x = __float_as_uint(f[p * 16 + 4 * j + 0]);
+                                    o.y = __float_as_uint(f[p * 16 + 4 * j + 1]);
+                                    o.z = __float_as_uint(f[p * 16 + 4 * j + 2]);
+                                    o.w = __float_as_uint(f[p * 16 + 4 * j + 3]);
+                                } else {
+                                    const int e = p * CPP + 8 * j;
+                                    o.x = pack_op(f[e + 0], f[e + 1]);
+                                    o.y = pack_op(f[e + 2], f[e + 3]);
+                                    o.z = pack_op(f[e + 4], f[e + 5]);
+                                    o.w = pack_op(f[e + 6], f[e + 7]);
+                                }
+                                *reinterpret_cast<uint4*>(my_row + ((j ^ sw) << 4)) = o;
+                            }
+                            fence_proxy_async_smem();   // the rows just written -> visible to the TMA store
+                            __syncwarp();
+                            if (lane == 0) {
+                                tma_store_4d(&maps.out, box, col0 + p * CPP, tc.w0 + qw, tc.h0 + qh, tc.img);
+                                bulk_commit();
+                                if constexpr (RESID != 0) {
+                                    if (pf_u < total_units) {
+                                        // the next box goes where pass gc - 1 was stored from: all but the store just
+                                        // committed must have read their source
+                                        bulk_wait_read<1>();
+                                        pf_issue();
+                                        pf_step();
+                                    }
+                                }
+                            }
+                            ++gc;
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) {
+                    if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(&tempty_bar[acc], 0));  // the leader's MMA thread waits
+                    else mbar_arrive(&tempty_bar[acc]);
+                }
+                acc ^= 1;
+                if (acc == 0) acc_phase ^= 1u;
+            }
+            if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the last stores' reads
+            __syncwarp();
+        } else {
         constexpr bool kFin = (MODE == EPI_CONVT_FINAL);
         constexpr bool kWide = (OUT_F32 != 0) || (RESID == 2);  // 16 columns (64 B of fp32) per staging pass
         constexpr int CPP = kWide ? 16 : 32;
@@ -393,7 +639,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                 // that their latency overlaps the accumulator load and the bias math
                 // DIRECT variant: the thread's own row segment (32 columns) straight from / to global memory
                 [[maybe_unused]] uint4 dres[RESID == 2 ? 8 : 4];
-                if constexpr (RESID != 0 && !kFin && DIRECT) {
+                if constexpr (RESID != 0 && !kFin && DIRECT == 1) {
                     const long long pixo = (static_cast<long long>(tc.img) * args.Ho + hh) * args.Wo + ww;
                     const bool fullc = row_ok && (col0 + 32 <= args.Cout);
                     const uint4* gp = reinterpret_cast<const uint4*>(reinterpret_cast<const char*>(args.resid) +
@@ -402,7 +648,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                     for (int j = 0; j < (RESID == 2 ? 8 : 4); ++j) dres[j] = fullc ? gp[j] : make_uint4(0, 0, 0, 0);
                 }
                 [[maybe_unused]] uint4 rres[NPASS][4];
-                if constexpr (RESID != 0 && !kFin && !DIRECT) {
+                if constexpr (RESID != 0 && !kFin && DIRECT == 0) {
                     constexpr int per16r = 16 / RESZ;
                     int ocol_r = col0, sub_r = 0;
                     if constexpr (MODE == EPI_SHUFFLE2X) {
@@ -501,7 +747,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
                         }
                         dots[0] = dots[1] = dots[2] = dots[3] = 0.f;
                     }
-                } else if constexpr (DIRECT) {
+                } else if constexpr (DIRECT == 1) {
                     int ocol = col0, sub = 0;
                     long long opix = (static_cast<long long>(tc.img) * args.Ho + hh) * args.Wo + ww;
                     if constexpr (MODE == EPI_SHUFFLE2X) {
@@ -740,6 +986,7 @@ __global__ void __launch_bounds__(kThreads, 1) gemm_tc_kernel(const __grid_const
             acc ^= 1;
             if (acc == 0) acc_phase ^= 1u;
         }
+        }  // legacy (DIRECT 0 / 1) epilogue
     }
 
     tc_fence_before();
@@ -793,6 +1040,55 @@ int make_tmap_op_4d(CUtensorMap* m, const void* base, const uint64_t dims[4], co
         return 1;
     }
     return 0;
+}
+
+// Output / residual tensor [n_img][Ho][Wo][Cout] (row pitch ld elements) as a 4-D map whose box is one epilogue warp's
+// share of a pass: 64 bytes of columns x the 32 tile rows of a TMEM lane quadrant (32 consecutive pixels of a row when
+// the patch is at least 32 wide, else 32 / BW full patch rows).
+static int make_tmap_epi(CUtensorMap* m, const void* base, int f32, const GemmArgs& a, int Cout, long long ld, int swz,
+                         int tile_cols = 0) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled entry point unavailable (no CUDA driver?)");
+        return 1;
+    }
+    const uint64_t es = f32 ? 4 : 2;
+    const int bw = 1 << a.bw_log2;
+    cuuint64_t gd[4] = {(cuuint64_t)Cout, (cuuint64_t)a.Wo, (cuuint64_t)a.Ho, (cuuint64_t)a.n_img};
+    cuuint64_t gs[3] = {(cuuint64_t)ld * es, (cuuint64_t)ld * es * a.Wo, (cuuint64_t)ld * es * a.Wo * a.Ho};
+    cuuint32_t bx[4] = {(cuuint32_t)(64 / es), (cuuint32_t)(bw < 32 ? bw : 32), (cuuint32_t)(bw < 32 ? 32 / bw : 1), 1};
+    if (tile_cols > 0) {   // prefetch map: the whole BH x BW x BLOCK_N output tile
+        bx[0] = (cuuint32_t)tile_cols;
+        bx[1] = (cuuint32_t)bw;
+        bx[2] = (cuuint32_t)(128 / bw);
+        swz = 0;
+    }
+    static const bool l2_256 = !(getenv("YTK_EPI_L2P") != nullptr && getenv("YTK_EPI_L2P")[0] == '1');
+    cuuint32_t est[4] = {1, 1, 1, 1};
+    const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                       : (kOpFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+    CUresult r = fn(m, dt, 4, const_cast<void*>(base), gd, gs, bx, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    swz ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                    l2_256 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (epilogue box) failed (%d): dims=%llu,%llu,%llu,%llu ld=%lld f32=%d base=%p",
+                  (int)r, (unsigned long long)gd[0], (unsigned long long)gd[1], (unsigned long long)gd[2],
+                  (unsigned long long)gd[3], ld, f32, base);
+        return 1;
+    }
+    return 0;
+}
+
+// Epilogue path: YTK_EPI=staged keeps the per-thread global accesses everywhere (A/B aid); default = TMA where the
+// plan allows it.  YTK_EPI_SWZ=0 builds unswizzled boxes (debugging aid: bank conflicts, same results).
+static int epi_mode_env() {
+    static int mode = -1;
+    if (mode < 0) {
+        const char* e = getenv("YTK_EPI");
+        mode = (e && e[0] == 's') ? 0 : 2;
+    }
+    return mode;
 }
 
 static int pick_block_n(int Cout) {
@@ -905,6 +1201,29 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
                  tiles_m >= 8)
                     ? 2
                     : 1;
+    // TMA epilogue: plain stores whose residual (if any) has the output's element size; 16-byte aligned bases
+    // and rows whose extent is a multiple of 16 bytes: measured on B200, a TMA store clips the box at the tensor's inner
+    // extent in 16-byte units (Cout = 7119 fp32 columns: column 7119 of a 7120-wide buffer was written)
+    a.epi_tma = 0;
+    a.epi_swz = 0;
+    a.epi_pf = 0;
+    if (epi_mode_env() == 2 && e.mode == EPI_NORMAL && (e.resid == nullptr || (e.resid_f32 != 0) == (e.out_f32 != 0)) &&
+        ((long long)Cout * (e.out_f32 ? 4 : 2)) % 16 == 0 &&
+        (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.resid) & 15) == 0) {
+        static const bool no_swz = getenv("YTK_EPI_SWZ") != nullptr && getenv("YTK_EPI_SWZ")[0] == '0';
+        static const bool no_pf = getenv("YTK_EPI_PF") != nullptr && getenv("YTK_EPI_PF")[0] == '0';
+        a.epi_tma = 1;
+        a.epi_swz = no_swz ? 0 : 1;
+        if (make_tmap_epi(&plan->maps.out, e.out, e.out_f32, a, Cout, e.ldc, a.epi_swz)) return 1;
+        if (e.resid != nullptr) {
+            if (make_tmap_epi(&plan->maps.resid, e.resid, e.resid_f32, a, Cout, e.ldr, a.epi_swz)) return 1;
+            if (make_tmap_epi(&plan->maps.resid_pf, e.resid, e.resid_f32, a, Cout, e.ldr, 0, plan->block_n)) return 1;
+            a.epi_pf = no_pf ? 0 : 1;
+        } else {
+            plan->maps.resid = plan->maps.out;
+            plan->maps.resid_pf = plan->maps.out;
+        }
+    }
     // weights: [Cout][Ktot] bf16, K-major; in cluster mode a CTA fetches block_n / cluster rows per k block
     uint64_t dims[4] = {(uint64_t)Ktot, (uint64_t)Cout, 1, 1};
     uint64_t strides[3] = {(uint64_t)Ktot * 2, (uint64_t)Ktot * 2 * Cout, (uint64_t)Ktot * 2 * Cout};
@@ -1058,8 +1377,20 @@ int stem_plan_create(GemmPlan* plan, const void* in_padded, int N, int Hn, int W
     return finish_plan(plan, w_packed, 7 * 64, 64, e);
 }
 
+int gemm_plan_set_out(GemmPlan* plan, void* out) {
+    GemmArgs& a = plan->args;
+    a.out = out;
+    if (!a.epi_tma) return 0;
+    if ((reinterpret_cast<uintptr_t>(out) & 15) != 0) {
+        set_error("gemm_plan_set_out: output must be 16-byte aligned for the TMA epilogue");
+        return 1;
+    }
+    return make_tmap_epi(&plan->maps.out, out, a.out_f32, a, a.Cout, a.ldc, a.epi_swz);
+}
+
 void gemm_plan_set_m(GemmPlan* plan, int M) {
     GemmArgs& a = plan->args;
+    a.epi_tma = 0;   // the epilogue tensor maps were encoded for the original extent
     const double per_row = a.Wo > 0 ? plan->flops / a.Wo : 0.0;
     a.Wo = M;
     a.tiles_w = (M + 127) / 128;
@@ -1071,7 +1402,7 @@ void gemm_plan_set_m(GemmPlan* plan, int M) {
 
 template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT, int PAIR>
 static int launch_variant3(const GemmPlan* plan, cudaStream_t stream) {
-    using Cfg = TileCfg<BLOCK_N>;
+    using Cfg = KernelCfg<BLOCK_N, RESID, DIRECT>;
     static bool attr_set = false;
     auto kern = gemm_tc_kernel<BLOCK_N, OUT_F32, RESID, MODE, DIRECT, PAIR>;
     if (!attr_set) {
@@ -1143,33 +1474,19 @@ static int launch_variant3(const GemmPlan* plan, cudaStream_t stream) {
 
 template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT>
 static int launch_variant2(const GemmPlan* plan, cudaStream_t stream) {
-    if constexpr (MODE != EPI_CONVT_FINAL && DIRECT == 0) {
+    if constexpr (MODE != EPI_CONVT_FINAL) {
         if (plan->args.cluster > 1) return launch_variant3<BLOCK_N, OUT_F32, RESID, MODE, DIRECT, 1>(plan, stream);
     }
     return launch_variant3<BLOCK_N, OUT_F32, RESID, MODE, DIRECT, 0>(plan, stream);
 }
 
-// Epilogue store path: staged (coalesced through shared memory) or direct (row per thread).  YTK_EPI=direct|staged
-// overrides the default for A/B measurements.
-static int epi_direct_mode() {
-    static int mode = -1;
-    if (mode < 0) {
-        const char* e = getenv("YTK_EPI");
-        mode = (e && e[0] == 'd') ? 1 : ((e && e[0] == 's') ? 0 : 2);  // 2 = per-variant default
-    }
-    return mode;
-}
-
+// Epilogue path per plan: the TMA epilogue (args.epi_tma, set by finish_plan) or the staged one.
 template <int BLOCK_N, int OUT_F32, int RESID, int MODE>
 static int launch_variant(const GemmPlan* plan, cudaStream_t stream) {
-    if constexpr (MODE == EPI_CONVT_FINAL) {
-        return launch_variant2<BLOCK_N, OUT_F32, RESID, MODE, 0>(plan, stream);
-    } else {
-        const int m = epi_direct_mode();
-        const bool direct = (m == 1) || (m == 2 && kDirectDefault);
-        if (direct) return launch_variant2<BLOCK_N, OUT_F32, RESID, MODE, 1>(plan, stream);
-        return launch_variant2<BLOCK_N, OUT_F32, RESID, MODE, 0>(plan, stream);
+    if constexpr (MODE == EPI_NORMAL && (RESID == 0 || (RESID == 2) == (OUT_F32 != 0))) {
+        if (plan->args.epi_tma) return launch_variant2<BLOCK_N, OUT_F32, RESID, MODE, 2>(plan, stream);
     }
+    return launch_variant2<BLOCK_N, OUT_F32, RESID, MODE, 0>(plan, stream);
 }
 
 template <int BLOCK_N>

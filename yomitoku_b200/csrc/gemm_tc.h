@@ -41,6 +41,11 @@ struct ConvTap {
 struct alignas(64) GemmMaps {
     CUtensorMap a[4];
     CUtensorMap b;
+    // TMA epilogue (args.epi_tma): the output tensor [n_img][Ho][Wo][Cout] and the residual tensor of the same shape,
+    // 64-byte-swizzled boxes of 32 tile rows x 64 bytes (one epilogue warp's share of a pass)
+    CUtensorMap out;
+    CUtensorMap resid;
+    CUtensorMap resid_pf;   // the residual tensor again, box = a whole output tile (L2 prefetch one tile ahead)
 };
 
 struct GemmArgs {
@@ -62,6 +67,11 @@ struct GemmArgs {
     int mode;
     const float* fin_w;            // EPI_CONVT_FINAL: device [4][64] fp32, k = i'*2+j' of the last transposed conv
     float fin_b;
+    int epi_tma;                   // 1: the epilogue moves residual and output tiles with TMA (EPI_NORMAL plans whose
+                                   // residual, if any, has the output's element size); 0: per-thread global accesses
+    int epi_swz;                   // 1: the TMA epilogue's boxes are 64-byte swizzled (conflict-free row accesses)
+    int epi_pf;                    // 1: the TMA producer prefetches the next tile's residual rows into L2 (whole rows of
+                                   // the tile in one request instead of 64-byte pieces fetched from DRAM one by one)
     int cluster;                   // 1, or 2: CTA pairs (thread-block cluster) work on M-adjacent tiles of one N tile
                                    // and multicast the weight tile - each CTA fetches half of it from L2
 };
@@ -108,6 +118,9 @@ int stem_plan_create(GemmPlan* plan, const void* in_padded, int N, int Hn, int W
                      const Epilogue& e);
 // Same but the M extent can be changed per launch (rows beyond M are never stored).
 void gemm_plan_set_m(GemmPlan* plan, int M);
+// Points a prepared plan at another output buffer of the same shape and pitch (the AR loop's K/V cache slot of the
+// step); re-encodes the output tensor map when the plan stores through TMA.  Returns 0 on success.
+int gemm_plan_set_out(GemmPlan* plan, void* out);
 int gemm_plan_launch(const GemmPlan* plan, cudaStream_t stream);
 
 // Generic 4-D tiled bf16 tensor map with 128B swizzle (dims/strides innermost first; strides in bytes for dims 1..3).

@@ -669,7 +669,8 @@ int ParseqEngine::forward(const ParseqBatch& b, int* ids_out, float* probs_out, 
             flops += p.step_flops;
             if (i + 1 < S) {
                 // K/V of the token that just entered the context: position i+1 of every row of the part
-                p.p_kv.args.out = reinterpret_cast<op_t*>(ckv) + r0 * S * 2 * D + (size_t)(i + 1) * 2 * D;
+                if (gemm_plan_set_out(&p.p_kv, reinterpret_cast<op_t*>(ckv) + r0 * S * 2 * D + (size_t)(i + 1) * 2 * D))
+                    return 1;
                 if (gemm_plan_launch(&p.p_kv, ps)) return 1;
             }
             return 0;
