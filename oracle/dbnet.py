@@ -71,8 +71,8 @@ def scale_feature_selection(sd, fuse, feats, prefix="decoder.concat_attention.")
     return torch.cat([score[:, i:i + 1] * feats[i] for i in range(4)], dim=1)
 
 
-def decoder_forward(sd, feats, prefix="decoder."):
-    """reference dbnet_plus.py:200-230."""
+def decoder_fuse(sd, feats, prefix="decoder."):
+    """reference dbnet_plus.py:200-227: FPN + adaptive scale fusion, the (N,256,H/4,W/4) input of the binarize head."""
     names = ["layer1", "layer2", "layer3", "layer4"]
     f = {n: F.conv2d(feats[n], sd[prefix + "input_proj.%s.weight" % n]) for n in names}
     # top-down accumulation, cumulative (SURVEY.md Appendix A18); interpolate only when the sizes differ (:212)
@@ -86,12 +86,20 @@ def decoder_forward(sd, feats, prefix="decoder."):
     p3 = _up(F.conv2d(f["layer3"], sd[prefix + "out_proj.layer3.0.weight"], padding=1), scale=4)
     p4 = _up(F.conv2d(f["layer4"], sd[prefix + "out_proj.layer4.0.weight"], padding=1), scale=4)
     fp = [p4, p3, p2, p1]                                                   # fp[::-1] in the reference (:225-226)
-    fuse = scale_feature_selection(sd, torch.cat(fp, dim=1), fp, prefix + "concat_attention.")
+    return scale_feature_selection(sd, torch.cat(fp, dim=1), fp, prefix + "concat_attention.")
+
+
+def binarize_logits(sd, fuse, prefix="decoder."):
+    """reference dbnet_plus.py:100-116 (the `binarize` Sequential) without the final sigmoid."""
     b = prefix + "binarize."
     x = F.relu(_bn(sd, b + "1", F.conv2d(fuse, sd[b + "0.weight"], padding=1)))
     x = F.relu(_bn(sd, b + "4", F.conv_transpose2d(x, sd[b + "3.weight"], sd[b + "3.bias"], stride=2)))
-    x = F.conv_transpose2d(x, sd[b + "6.weight"], sd[b + "6.bias"], stride=2)
-    return torch.sigmoid(x)
+    return F.conv_transpose2d(x, sd[b + "6.weight"], sd[b + "6.bias"], stride=2)
+
+
+def decoder_forward(sd, feats, prefix="decoder."):
+    """reference dbnet_plus.py:200-230."""
+    return torch.sigmoid(binarize_logits(sd, decoder_fuse(sd, feats, prefix), prefix))
 
 
 @torch.inference_mode()

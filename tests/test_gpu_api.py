@@ -88,6 +88,8 @@ def test_document_analyzer_default_layout_models():
                                    "layout_analyzer": {"layout_parser": nop, "table_structure_recognizer": nop}},
                           device="cuda")
     assert isinstance(da.layout, LayoutAnalyzer)
+    from trained_head import load_trained_head
+    load_trained_head(da.text_detector.model)       # the detector's own map holds the page's text lines (~250 boxes)
     page, _ = synthetic_page(1)
     res, ocr_vis, layout_vis = da(page)
     assert layout_vis is None and isinstance(res.words, list) and len(res.words) > 0
@@ -142,6 +144,10 @@ def test_document_analyzer_batched_pages_equal_single_page_calls():
     pages = [synthetic_page(60)[0], synthetic_page(61)[0]]
     for split in (False, True):
         an = DocumentAnalyzer(configs=cfg, device="cuda", layout_analyzer=layout, split_text_across_cells=split)
+        from trained_head import load_trained_head
+        # trained binarize head: the detector finds the pages' text lines (~250 boxes) instead of the > 1000 junk
+        # components a random head yields (the test took 100 s on them)
+        load_trained_head(an.text_detector.model)
         single = [an(p)[0] for p in pages]
         batched = an.analyze_pages(pages)
         assert len(batched) == 2

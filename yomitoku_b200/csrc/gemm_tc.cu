@@ -1063,7 +1063,8 @@ static int make_tmap_epi(CUtensorMap* m, const void* base, int f32, const GemmAr
         bx[2] = (cuuint32_t)(128 / bw);
         swz = 0;
     }
-    static const bool l2_256 = !(getenv("YTK_EPI_L2P") != nullptr && getenv("YTK_EPI_L2P")[0] == '1');
+    // L2 promotion of the box fetches: 128 B by default; YTK_EPI_L2P=256 measured no better (profiles/README_r02.md)
+    static const bool l2_256 = getenv("YTK_EPI_L2P") != nullptr && getenv("YTK_EPI_L2P")[0] == '2';
     cuuint32_t est[4] = {1, 1, 1, 1};
     const CUtensorMapDataType dt = f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                        : (kOpFmt ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
@@ -1211,7 +1212,10 @@ static int finish_plan(GemmPlan* plan, const void* w_packed, int Ktot, int Cout,
         ((long long)Cout * (e.out_f32 ? 4 : 2)) % 16 == 0 &&
         (reinterpret_cast<uintptr_t>(e.out) & 15) == 0 && (reinterpret_cast<uintptr_t>(e.resid) & 15) == 0) {
         static const bool no_swz = getenv("YTK_EPI_SWZ") != nullptr && getenv("YTK_EPI_SWZ")[0] == '0';
-        static const bool no_pf = getenv("YTK_EPI_PF") != nullptr && getenv("YTK_EPI_PF")[0] == '0';
+        // whole-tile L2 prefetch of the residual one tile ahead: opt-in (YTK_EPI_PF=1).  Measured (call 19, one box):
+        // proj 10.40 ms with it vs 9.37-9.66 without, fc2 20.6 vs 19.0-19.3, DBNet residual 1x1 convs 1.60 vs 1.42 ms -
+        // the 64-byte boxes are not what limits these kernels.
+        static const bool no_pf = !(getenv("YTK_EPI_PF") != nullptr && getenv("YTK_EPI_PF")[0] == '1');
         a.epi_tma = 1;
         a.epi_swz = no_swz ? 0 : 1;
         if (make_tmap_epi(&plan->maps.out, e.out, e.out_f32, a, Cout, e.ldc, a.epi_swz)) return 1;
