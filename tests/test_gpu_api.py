@@ -112,10 +112,22 @@ def test_handles_bind_to_the_requested_device():
     assert L.ytk_dbnet_device(det.model._ensure()) == k
     assert L.ytk_parseq_device(rec.model._ensure()) == k
     assert det.model.cuda_device().index == k
+    # a forward on GPU k from a thread whose current device is 0: same bits as the same weights on GPU 0 (kernels whose
+    # shared-memory attribute was first set on the other device included), and the caller's current device is untouched
+    cur = torch.cuda.current_device()
+    page, _ = synthetic_page(3)
+    pk = det.model.detect_pages_u8(page)
+    assert torch.cuda.current_device() == cur
+    assert pk.device.type == "cpu" or pk.device.index == k
+    det0 = TextDetector(from_pretrained=False, device="cuda:0")
+    p0 = det0.model.detect_pages_u8(page)
+    assert torch.equal(pk.cpu(), p0.cpu())
+    assert torch.cuda.current_device() == cur
     # moving a materialised model drops the handle; the next use re-creates it on the new device
     rec.model.to("cuda:0")
     assert (rec.model._handle is None) == (k != 0)
     assert L.ytk_parseq_device(rec.model._ensure()) == 0
+    assert torch.cuda.current_device() == cur
 
 
 def test_document_analyzer_batched_pages_equal_single_page_calls():

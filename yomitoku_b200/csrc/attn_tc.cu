@@ -511,15 +511,14 @@ __global__ void __launch_bounds__(kAtThreads, 1) attn_tc_kernel(const __grid_con
 template <int HD, int MASKED, int PT>
 int launch_attn(const AttnMaps& maps, const AttnArgs& a, int grid, cudaStream_t st) {
     using Cfg = AtCfg<HD>;
-    static bool attr = false;
+    static unsigned long long attr_done = 0;   // per device
     auto kern = attn_tc_kernel<HD, MASKED, PT>;
-    if (!attr) {
+    if (first_launch_on_device(&attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) {
             set_error("attention: cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
             return 1;
         }
-        attr = true;
     }
     kern<<<grid, kAtThreads, Cfg::kSmemBytes, st>>>(maps, a);
     return 0;

@@ -17,6 +17,22 @@
 #include "parseq_engine.h"
 #include "rtdetr_engine.h"
 
+// Binds the calling host thread to a device for the duration of an API call and puts the previous device back (host
+// threads start on device 0, and a handle on cuda:1 must not leave "the current device" changed for the caller - PyTorch
+// allocates `device="cuda"` tensors on it).
+struct DevGuard {
+    int prev = -1, dev = -1;
+    explicit DevGuard(int d) : dev(d) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0 && prev != dev) cudaSetDevice(prev);
+    }
+    DevGuard(const DevGuard&) = delete;
+    DevGuard& operator=(const DevGuard&) = delete;
+};
+
 struct ytk_parseq {
     ytk::ParseqModel model;
     ytk::ParseqEngine engine;
@@ -178,7 +194,7 @@ int ytk_dbnet_post_front(const float* prob_dev, int n_pages, int H, int W, float
         ytk::set_error("ytk_dbnet_post_front: prob_dev is not a device pointer");
         return YTK_ERR;
     }
-    cudaSetDevice(attr.device);
+    DevGuard dev_guard(attr.device);
     if (ytk::launch_dbpost_front(prob_dev, n_pages, H, W, thresh, reinterpret_cast<int*>(scratch_dev),
                                  reinterpret_cast<ytk::DbRun*>(runs_dev), max_runs_per_page, meta_dev,
                                  static_cast<cudaStream_t>(cuda_stream))) {
@@ -213,7 +229,7 @@ int ytk_dbnet_create(const ytk_tensor* tensors, int n_tensors, int shortest_size
 
 void ytk_dbnet_destroy(ytk_dbnet* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DevGuard dev_guard(h->device);
     if (h->last_done) {
         cudaEventSynchronize(h->last_done);
         cudaEventDestroy(h->last_done);
@@ -233,7 +249,7 @@ int ytk_dbnet_input_size(const ytk_dbnet* h, int H0, int W0, int* Hn, int* Wn) {
 int ytk_dbnet_forward_u8(ytk_dbnet* h, const uint8_t* pages, int pages_on_device, int n_pages, int H0, int W0,
                          float* prob_out, int out_on_device, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
+    DevGuard dev_guard(h->device);  // host threads start on device 0: the handle's device is the one that counts
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     int Hn, Wn;
     ytk::dbnet_input_size(H0, W0, h->shortest, h->limit, &Hn, &Wn);
@@ -266,7 +282,7 @@ int ytk_dbnet_forward_u8(ytk_dbnet* h, const uint8_t* pages, int pages_on_device
 int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x, int x_on_device, int n, int H, int W, float* prob_out,
                           int out_on_device, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
+    DevGuard dev_guard(h->device);  // host threads start on device 0: the handle's device is the one that counts
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     ytk::DbnetEngine* e = get_engine(h, n, H, W);
     if (!e) return YTK_ERR;
@@ -290,7 +306,7 @@ int ytk_dbnet_forward_f32(ytk_dbnet* h, const float* x, int x_on_device, int n, 
 
 double ytk_dbnet_flops(ytk_dbnet* h, int n_pages, int Hn, int Wn) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
+    DevGuard dev_guard(h->device);  // host threads start on device 0: the handle's device is the one that counts
     ytk::DbnetEngine* e = get_engine(h, n_pages, Hn, Wn);
     return e ? e->flops : -1.0;
 }
@@ -298,7 +314,7 @@ double ytk_dbnet_flops(ytk_dbnet* h, int n_pages, int Hn, int Wn) {
 int ytk_dbnet_debug_tensor(ytk_dbnet* h, int n_pages, int Hn, int Wn, const char* name, float* host_out,
                            long long capacity, int* shape4) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
+    DevGuard dev_guard(h->device);  // host threads start on device 0: the handle's device is the one that counts
     ytk::DbnetEngine* e = get_engine(h, n_pages, Hn, Wn);
     if (!e) return YTK_ERR;
     auto it = e->dbg.find(name);
@@ -369,7 +385,7 @@ int ytk_extract_crops_u8(const uint8_t* pages_dev, int n_pages, int H0, int W0, 
         ytk::set_error("ytk_extract_crops_u8: pages_dev is not a device pointer");
         return YTK_ERR;
     }
-    cudaSetDevice(attr.device);  // host threads start on device 0: the device that owns the pages is the one that counts
+    DevGuard dev_guard(attr.device);  // host threads start on device 0: the device that owns the pages is the one that counts
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     ytk::CropGeom* dev = reinterpret_cast<ytk::CropGeom*>(scratch_dev + rec_off);
     cudaError_t err = cudaMemcpyAsync(dev, geoms, (size_t)rec_bytes, cudaMemcpyHostToDevice, st);
@@ -399,7 +415,7 @@ int ytk_halve_pages_u8(const uint8_t* src_dev, int n_pages, int H, int W, uint8_
         ytk::set_error("ytk_halve_pages_u8: src_dev is not a device pointer");
         return YTK_ERR;
     }
-    cudaSetDevice(attr.device);
+    DevGuard dev_guard(attr.device);
     if (ytk::launch_halve_pages(src_dev, n_pages, H, W, dst_dev, dH, dW, static_cast<cudaStream_t>(cuda_stream))) {
         ytk::set_error("ytk_halve_pages_u8: kernel launch failed");
         return YTK_ERR;
@@ -436,7 +452,7 @@ void ytk_parseq_destroy(ytk_parseq* h) { delete h; }
 
 void ytk_parseq_set_refine_iters(ytk_parseq* h, int refine_iters) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
+    DevGuard dev_guard(h->device);  // host threads start on device 0: the handle's device is the one that counts
     h->model.cfg.refine_iters = refine_iters;
 }
 
@@ -444,7 +460,7 @@ int ytk_parseq_forward_crops(ytk_parseq* h, const uint8_t* crops_ptr, int crops_
                              const ytk_crop* crops, int n_crops, int n_groups, int32_t* ids_out, float* probs_out,
                              int32_t* group_len_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
+    DevGuard dev_guard(h->device);  // host threads start on device 0: the handle's device is the one that counts
     ytk::ParseqBatch b;
     b.crops = crops_ptr;
     b.crops_on_device = crops_on_device;
@@ -472,7 +488,7 @@ int ytk_parseq_forward_f32(ytk_parseq* h, const float* images, int images_on_dev
                            int logits_on_device, int32_t* ids_out, float* probs_out, int32_t* steps_out,
                            int32_t* rep_cut_out, float* memory_out, void* cuda_stream) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);  // host threads start on device 0: the handle's device is the one that counts
+    DevGuard dev_guard(h->device);  // host threads start on device 0: the handle's device is the one that counts
     const int pw = h->model.cfg.pw, gh = h->model.gh;
     if (W % pw != 0 || W > h->model.cfg.img_w || W <= 0) {
         ytk::set_error("ytk_parseq_forward_f32: width %d must be a positive multiple of %d and <= %d", W, pw,
@@ -564,7 +580,7 @@ int ytk_rtdetr_create(const ytk_tensor* tensors, int n_tensors, int num_classes,
 
 void ytk_rtdetr_destroy(ytk_rtdetr* h) {
     if (!h) return;
-    cudaSetDevice(h->device);
+    DevGuard dev_guard(h->device);
     if (h->last_done) {
         cudaEventSynchronize(h->last_done);
         cudaEventDestroy(h->last_done);
@@ -582,7 +598,7 @@ int ytk_rtdetr_forward_f32(ytk_rtdetr* h, const float* x, int x_on_device, int n
         return YTK_ERR;
     }
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);
+    DevGuard dev_guard(h->device);
     cudaStream_t st = static_cast<cudaStream_t>(cuda_stream);
     ytk::RtdetrEngine* e = rt_engine(h, n);
     if (!e) return YTK_ERR;
@@ -612,14 +628,14 @@ int ytk_rtdetr_forward_f32(ytk_rtdetr* h, const float* x, int x_on_device, int n
 
 double ytk_rtdetr_flops(ytk_rtdetr* h, int n) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);
+    DevGuard dev_guard(h->device);
     ytk::RtdetrEngine* e = rt_engine(h, n);
     return e ? e->flops : -1.0;
 }
 
 int ytk_rtdetr_debug_tensor(ytk_rtdetr* h, int n, const char* name, float* host_out, long long capacity, int* shape4) {
     std::lock_guard<std::mutex> lk(h->mu);
-    cudaSetDevice(h->device);
+    DevGuard dev_guard(h->device);
     ytk::RtdetrEngine* e = rt_engine(h, n);
     if (!e) return YTK_ERR;
     auto it = e->dbg.find(name);

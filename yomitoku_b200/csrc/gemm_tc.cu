@@ -46,6 +46,15 @@ int pdl_launch_attr(cudaLaunchAttribute* attr) {
     return 1;
 }
 
+bool first_launch_on_device(unsigned long long* mask) {
+    int d = 0;
+    cudaGetDevice(&d);
+    const unsigned long long bit = 1ull << (d & 63);
+    if (*mask & bit) return false;
+    *mask |= bit;     // two threads racing here both set the attribute: harmless
+    return true;
+}
+
 int num_sms() {
     static int n = 0;
     if (n == 0) {
@@ -1407,15 +1416,14 @@ void gemm_plan_set_m(GemmPlan* plan, int M) {
 template <int BLOCK_N, int OUT_F32, int RESID, int MODE, int DIRECT, int PAIR>
 static int launch_variant3(const GemmPlan* plan, cudaStream_t stream) {
     using Cfg = KernelCfg<BLOCK_N, RESID, DIRECT>;
-    static bool attr_set = false;
+    static unsigned long long attr_done = 0;   // per device (a process may hold handles on several GPUs)
     auto kern = gemm_tc_kernel<BLOCK_N, OUT_F32, RESID, MODE, DIRECT, PAIR>;
-    if (!attr_set) {
+    if (first_launch_on_device(&attr_done)) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes);
         if (e != cudaSuccess) {
             set_error("cudaFuncSetAttribute(smem=%d): %s", Cfg::kSmemBytes, cudaGetErrorString(e));
             return 1;
         }
-        attr_set = true;
     }
     if constexpr (PAIR != 0) {
         // persistent grid = every cluster the device can hold at once (clusters cannot straddle GPCs, so this can be

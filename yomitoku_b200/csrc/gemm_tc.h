@@ -133,6 +133,9 @@ int pdl_launch_attr(cudaLaunchAttribute* attr);
 void set_error(const char* fmt, ...);
 const char* last_error();
 int num_sms();
+// Function attributes (the dynamic shared memory limit) are per device: returns true the first time it is called for
+// `*mask` on the calling thread's current device (bit d of the mask = done on device d).
+bool first_launch_on_device(unsigned long long* mask);
 void count_launch(int n = 1);
 long long launch_count();
 // Timing window over gemm_tc_kernel launches: CUDA events on the launching stream around every launch between begin and

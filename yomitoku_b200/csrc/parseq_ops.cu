@@ -436,14 +436,13 @@ static int launch_fa(dim3 grid, const op_t* q, long long ldq, const op_t* k, con
                      long long ldkv, op_t* o, long long ldo, const SeqDesc* seqs, float scale_log2,
                      cudaStream_t st) {
     constexpr int smem = (QT + 4 * 64) * (HD + 8) * 2;
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_done = 0;   // per device
+    if (first_launch_on_device(&attr_done)) {
         if (cudaFuncSetAttribute(flash_attn_kernel<HD, MASKED, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
             cudaSuccess) {
             set_error("flash attention: cannot reserve %d bytes of shared memory", smem);
             return 1;
         }
-        attr = true;
     }
     flash_attn_kernel<HD, MASKED, QT><<<grid, QT * 2, smem, st>>>(q, ldq, k, v, ldkv, o, ldo, seqs, scale_log2);
     return 0;

@@ -328,13 +328,12 @@ int launch_rt_topk(const float* scores, int n_img, int L, int K, int* out_idx, c
     int NP = 1;
     while (NP < L) NP <<= 1;
     const size_t smem = (size_t)NP * sizeof(unsigned long long);
-    static bool attr = false;
-    if (!attr) {
+    static unsigned long long attr_done = 0;   // per device
+    if (first_launch_on_device(&attr_done)) {
         if (cudaFuncSetAttribute(topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024) != cudaSuccess) {
             set_error("topk: cannot raise the shared memory limit");
             return 1;
         }
-        attr = true;
     }
     if (smem > 200 * 1024 || K > L) {
         set_error("topk: %d candidates / k = %d unsupported", L, K);
