@@ -1,10 +1,13 @@
 // tcgen05 implicit-GEMM convolution / linear kernel for sm_100a.  See gemm_tc.h for the contract.
 //
-// Warp roles (192 threads, 1 CTA per SM, persistent over output tiles):
+// Warp roles (320 threads, 1 CTA per SM, persistent over output tiles):
 //   warp 0      : TMA producer  (one elected lane) - A patch box + W box per 64-wide K block, STAGES-deep ring
 //   warp 1      : MMA issuer    (one lane)         - 4 x tcgen05.mma (K=16) per K block into a TMEM accumulator
-//   warps 2..5  : epilogue      (128 threads)      - tcgen05.ld -> bias/residual/activation -> global stores
-// Pipelines: smem full/empty mbarriers (TMA <-> MMA) and TMEM full/empty mbarriers (MMA <-> epilogue, 2 buffers).
+//   warps 2..9  : epilogue      (256 threads)      - tcgen05.ld -> bias/residual/activation -> TMA boxes (residual in by
+//                                                    cp.async.bulk.tensor, result out by TMA store) or, for the plans the
+//                                                    TMA path does not cover, staged per-thread global accesses
+// Pipelines: smem full/empty mbarriers (TMA <-> MMA), TMEM full/empty mbarriers (MMA <-> epilogue, 2 buffers) and, in
+// the TMA epilogue, one mbarrier per residual box of every epilogue warp's ring.
 #include "gemm_tc.h"
 
 #include <cstdarg>
