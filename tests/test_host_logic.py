@@ -148,6 +148,53 @@ def test_clipper_offset_properties():
                           offset_convex_polygon_round(rot, 5.0)[:, 0].min())   # orientation is fixed internally
 
 
+def test_unclip_against_the_geometric_definition():
+    """The Clipper restatements (product and oracle) against the DEFINITION of a round-join offset instead of against
+    each other: the offset of a convex polygon by delta is its Minkowski sum with a disk - every output vertex lies at
+    distance delta from the input polygon, the area is A + L * delta + pi * delta^2 (minus the chord deficit of the
+    arc tolerance 0.25, plus / minus the integer rounding of the vertices), and for a rectangle w x h the minimum-area
+    rectangle of the result - the only thing the reference reads from it (dbnet_postporcessor.py:66) - is
+    (w + 2 delta) x (h + 2 delta) at the same angle.  pyclipper itself is not installable here (DESIGN.md section 2);
+    this pins the arithmetic that is restated from it to the geometry it implements."""
+    import cv2
+    rng = np.random.default_rng(7)
+
+    def dist_to_polygon(pts, poly):
+        d = np.full(len(pts), np.inf)
+        for i in range(len(poly)):
+            a, b = poly[i], poly[(i + 1) % len(poly)]
+            ab = b - a
+            t = np.clip(((pts - a) @ ab) / max(float(ab @ ab), 1e-12), 0.0, 1.0)
+            d = np.minimum(d, np.linalg.norm(pts - (a + t[:, None] * ab), axis=1))
+        return d
+
+    for _ in range(200):
+        w, h = rng.uniform(12, 400), rng.uniform(6, 60)
+        ang = rng.uniform(-90, 90)
+        cx, cy = rng.uniform(300, 1200, size=2)
+        box = cv2.boxPoints(((float(cx), float(cy)), (float(w), float(h)), float(ang))).astype(np.float32)
+        delta = float(rng.uniform(1.5, 40))
+        tb = np.trunc(box).astype(np.float64)                      # Clipper works on the int-truncated vertices
+        (_, _), (tw, th), _ = cv2.minAreaRect(tb.astype(np.float32))
+        area = 0.5 * abs(np.dot(tb[:, 0], np.roll(tb[:, 1], -1)) - np.dot(tb[:, 1], np.roll(tb[:, 0], -1)))
+        perim = np.linalg.norm(tb - np.roll(tb, -1, axis=0), axis=1).sum()
+        for fn in (offset_convex_polygon_round, opipe.clipper_offset_box):
+            out = np.asarray(fn(box, delta), dtype=np.float64)
+            assert len(out) >= 8
+            # (1) every vertex at distance delta from the polygon (integer rounding: half a pixel diagonal)
+            d = dist_to_polygon(out, tb)
+            assert np.abs(d - delta).max() <= 0.75, (np.abs(d - delta).max(), delta)
+            # (2) area of the Minkowski sum; the chords of the four round joins lose at most arc_tolerance * arc length
+            a_out = 0.5 * abs(np.dot(out[:, 0], np.roll(out[:, 1], -1)) - np.dot(out[:, 1], np.roll(out[:, 0], -1)))
+            a_exact = area + perim * delta + np.pi * delta * delta
+            slack = 0.25 * 2 * np.pi * delta + 0.75 * (perim + 2 * np.pi * delta)
+            assert -slack <= a_out - a_exact <= 0.75 * (perim + 2 * np.pi * delta), (a_out, a_exact)
+            # (3) what the reference reads: the minimum-area rectangle grows by delta on every side
+            (_, _), (ow, oh), _ = cv2.minAreaRect(out.astype(np.float32))
+            got, want = sorted((ow, oh)), sorted((tw + 2 * delta, th + 2 * delta))
+            assert abs(got[0] - want[0]) <= 1.5 and abs(got[1] - want[1]) <= 1.5, (got, want)
+
+
 def test_tokenizer_decode_ids_matches_oracle(charset_v2):
     tok, otok = ParseqTokenizer(charset_v2), ops.Tokenizer(charset_v2)
     assert (tok.eos_id, tok.bos_id, tok.pad_id) == (0, 7119, 7120) and len(tok) == 7121
