@@ -11,7 +11,8 @@ from oracle import pipeline as opipe
 from yomitoku_b200 import OCR, DocumentAnalyzer, TextDetector, TextRecognizer
 from yomitoku_b200 import data as D
 from yomitoku_b200.base import BaseModelCatalog, BaseModule
-from yomitoku_b200.postprocessor import DBnetPostProcessor, ParseqTokenizer, offset_convex_polygon_round
+from yomitoku_b200.postprocessor import (DBnetPostProcessor, ParseqTokenizer, offset_convex_polygon_round,
+                                         polygon_area_length)
 from yomitoku_b200.synth import synthetic_page, synthetic_prob_map
 from yomitoku_b200.text_recognizer import plan_mini_batches
 
@@ -174,6 +175,9 @@ def test_unclip_against_the_geometric_definition():
         cx, cy = rng.uniform(300, 1200, size=2)
         box = cv2.boxPoints(((float(cx), float(cy)), (float(w), float(h)), float(ang))).astype(np.float32)
         delta = float(rng.uniform(1.5, 40))
+        # shapely's Polygon(box).area / .length (dbnet_postporcessor.py:88,94) of a rectangle: w * h and 2 (w + h)
+        a_box, l_box = polygon_area_length(box)
+        assert abs(a_box - w * h) <= 1e-3 * w * h + 0.05 and abs(l_box - 2 * (w + h)) <= 1e-3 * (w + h) + 0.05
         tb = np.trunc(box).astype(np.float64)                      # Clipper works on the int-truncated vertices
         (_, _), (tw, th), _ = cv2.minAreaRect(tb.astype(np.float32))
         area = 0.5 * abs(np.dot(tb[:, 0], np.roll(tb[:, 1], -1)) - np.dot(tb[:, 1], np.roll(tb[:, 0], -1)))
